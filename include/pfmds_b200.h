@@ -1,0 +1,123 @@
+/*
+ * pfmds_b200 — C ABI of the B200-native MD inner loop (libpfmds_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of AlexanderSidorenkov/PFMDS: everything the
+ * reference executes inside `do md_step=0,md_step_limit` of md()
+ * (code_source/MOLECULAR_DYNAMICS/md_simulation.f90:114-243).  The reference has no FFI of its own
+ * (it is one Fortran process); the seam is the set of module procedures md() calls, and each entry
+ * point below names the reference procedures it replaces.  Plain C types only: an ISO_C_BINDING
+ * Fortran host, the C++ run_md_simulation host in pfmds_b200/host/ and ctypes all bind the same
+ * symbols.
+ *
+ * Conventions
+ *  - all reals are FP64, all indices int32, exactly like the reference built with -fdefault-real-8;
+ *  - per-atom arrays are xyz-interleaved `a[3*i+k]` in FILE order (Fortran `a(3,N)`), atom and group
+ *    numbers are 1-based as in the settings file;
+ *  - every call returns 0 on success or a PFMDS_ERR_* code; pfmds_last_error() gives the message
+ *    (the reference's own `stop` text where one exists);
+ *  - one host thread drives one context; contexts are independent (own CUDA stream), so several
+ *    can share a GPU (ensemble mode) or sit one per GPU;
+ *  - pfmds_advance only enqueues work; positions, velocities, forces and neighbour lists stay on
+ *    the device until pfmds_energies / pfmds_diagnostics / pfmds_download / pfmds_synchronize.
+ */
+#ifndef PFMDS_B200_H
+#define PFMDS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pfmds_ctx pfmds_ctx;
+
+enum {
+    PFMDS_OK = 0,
+    PFMDS_ERR_INVALID = 1,             /* bad argument / call order */
+    PFMDS_ERR_CUDA = 2,                /* CUDA runtime failure (no device, out of memory, ...) */
+    PFMDS_ERR_OUT_OF_CELL = 10,        /* "particle out of cell"            md_general.f90:342-364 */
+    PFMDS_ERR_TOO_MANY_NEIGHBOURS = 11,/* "error: too many neighbours"      md_neighbours.f90:80,151 */
+    PFMDS_ERR_GR_NEIGHBOURS = 12,      /* "not enough / too many gr nearest neibs" graphenenorm.f90:26,30 */
+    PFMDS_ERR_NHC_PARAMS = 13,         /* "error: wrong nhc parameters"     md_integrators.f90:187 */
+    PFMDS_ERR_LIST_SIZE = 14,          /* nl%N mismatches                   md_neighbours.f90:64,134; LennardJonesCosine.f90:60 */
+    PFMDS_ERR_UNKNOWN_INTERACTION = 15,/* "error: unknown interaction name" md_interactions.f90:119-120 */
+    PFMDS_ERR_UNSUPPORTED = 20         /* input the reference accepts but this path refuses loudly */
+};
+
+enum { PFMDS_NVE = 0, PFMDS_NVT = 1, PFMDS_NVMS = 2 };  /* integrator_name 'nve' (or any other) / 'nvt' / 'nvms' */
+
+/* Replaces read_box_size + read_particles handing their arrays to md() (md_read_write.f90:22-61;
+ * types particles / simulation_cell, md_general.f90:9-17).  Arrays are copied. */
+int pfmds_create(pfmds_ctx** ctx, int device, int n_atoms, const double* positions, const double* velocities,
+                 const double* masses, const double box_size[3]);
+
+/* create_particle_group (md_general.f90:57-80): `indexes` are the 1-based atom numbers in the
+ * reference's order (type column first, file order second). */
+int pfmds_set_group(pfmds_ctx* ctx, int group_num, int n, const int* indexes);
+
+/* all_moving / xyz_moving / z_moving / all_atoms group numbers (md_simulation.f90:57-60). */
+int pfmds_set_roles(pfmds_ctx* ctx, int all_moving_group, int xyz_moving_group, int z_moving_group, int all_atoms_group);
+
+/* create_nose_hoover_chain + set_nose_hoover_chain (md_integrators.f90:165-198), one per settings line. */
+int pfmds_add_nhc(pfmds_ctx* ctx, int group_num, double temperature, int M, double q1);
+
+/* zero_momentum_period, invert_z_vel (md_simulation.f90:55,72). */
+int pfmds_set_misc(pfmds_ctx* ctx, int zero_momentum_period, int invert_z_vel);
+
+/* One block of create_interactions (md_interactions.f90:59-136).  `name` in lj, lj1g, ljc, morsec,
+ * tb, rjl.  `params` in parameter-file order:
+ *   lj, lj1g: eps sig R1 R2            ljc: eps sig delt R1 R2 simplified(0/1)
+ *   morsec: d r a delt R1 R2 simplified    tb: d s b r0 delt a0 c0 d0 R1 R2    rjl: A0 xi p q r0 R1 R2
+ * nl_n neighbour-list lines (2, 1, 3, 3, 1, 1): group_nums[2*nl_n] = g1 g2 per line, then capacity,
+ * r_cut and update_period per line.  Call in file order: forces accumulate in that order and
+ * ljc/morsec take their nearest-3 list from the first tb interaction added before them. */
+int pfmds_add_interaction(pfmds_ctx* ctx, const char* name, int n_params, const double* params, int nl_n,
+                          const int* group_nums, const int* neighb_num_max, const double* r_cut, const int* update_period);
+
+/* Runs md steps first_md_step .. first_md_step+n_steps-1 on the device: per step check_positions,
+ * invert_z_velocities, [nvt: integrate_nose_hoover_chain], velocity half-kick, drift + wrap,
+ * update_interactions_neighbour_lists (cell-binned rebuild when mod(step,period)==0), zero_momentum,
+ * zero_forces + calculate_forces, half-kick, [nvt: NHC], [nvms: quench]   (md_simulation.f90:138-186;
+ * step 0 only evaluates lists and forces).  Asynchronous. */
+int pfmds_advance(pfmds_ctx* ctx, int integrator, double dt, int first_md_step, int n_steps);
+
+/* calculate_potential_energies + calculate_temperature(all_moving) + calculate_nose_hoover_chain_energy
+ * (md_simulation.f90:191-198).  e_inter[n_interactions], e_nhc[n_nhc].  Synchronises. */
+int pfmds_energies(pfmds_ctx* ctx, double* e_inter, double* kinetic_energy, double* temperature, double* e_nhc);
+
+/* calculate_force_sum, calculate_mass_center, calculate_mass_center_velocity over all_atoms,
+ * find_max_velocity, nlists_load (md_simulation.f90:212-223; md_interactions.f90:427-444).
+ * nl_load has one entry per neighbour-list line in file order.  Synchronises. */
+int pfmds_diagnostics(pfmds_ctx* ctx, double force_sum[3], double mass_center[3], double mass_center_velocity[3],
+                      double* max_velocity, int* nl_load);
+
+/* Copies state back in file order; any pointer may be NULL.  Synchronises. */
+int pfmds_download(pfmds_ctx* ctx, double* positions, double* velocities, double* forces);
+
+/* The reference-shaped view of one neighbour list (type neighbour_list, md_general.f90:30-35):
+ * rows in group-1 order, entries = 1-based group-2 local numbers in ascending order,
+ * nlist[row*neighb_num_max + p].  For parity tests and debugging.  Synchronises. */
+int pfmds_neighbours(pfmds_ctx* ctx, int interaction, int list, int* nlist, int* nnum, int* lessnnum);
+
+/* gr_norm(3,N) of an ljc / morsec interaction, rows in group-1 order (graphenenorm.f90:38-56). */
+int pfmds_normals(pfmds_ctx* ctx, int interaction, double* gr_norm);
+
+/* x(M), v(M) of thermostat k (0-based), for exact restarts and tests. */
+int pfmds_get_nhc(pfmds_ctx* ctx, int k, double* x, double* v);
+int pfmds_set_nhc(pfmds_ctx* ctx, int k, const double* x, const double* v);
+
+/* Seconds spent per phase, from CUDA events, when PFMDS_TIMERS=1 is set in the environment
+ * (otherwise zeros): pos_vel, nlists, nlsearch, nldistance, forces, energy — the buckets of the
+ * reference's PERFOMANCE table (md_simulation.f90:250-259). */
+int pfmds_timers(pfmds_ctx* ctx, double seconds[6]);
+
+/* Number of kernel launches issued so far by this context and device-time of the last advance (ms). */
+int pfmds_launch_count(pfmds_ctx* ctx, long long* launches);
+
+int pfmds_synchronize(pfmds_ctx* ctx);
+const char* pfmds_last_error(pfmds_ctx* ctx);
+int pfmds_destroy(pfmds_ctx* ctx);
+const char* pfmds_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

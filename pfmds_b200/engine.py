@@ -1,0 +1,214 @@
+"""ctypes binding of the C ABI in include/pfmds_b200.h.
+
+`Engine` speaks to libpfmds_b200.so (the CUDA product).  The same class can be pointed at another
+library exporting the same shapes under a different prefix — the tests use that to drive the CPU
+oracle (prefix ``oracle_``) through identical calls; the product itself never loads the oracle.
+There is no CPU fallback: if the CUDA library is missing or no GPU is present, construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+NVE, NVT, NVMS = 0, 1, 2
+KIND = {"nve": NVE, "nvt": NVT, "nvms": NVMS}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpfmds_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class PfmdsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pfmds error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+_SIGS = {
+    "create": [C.POINTER(C.c_void_p), C.c_int, C.c_int, _dp, _dp, _dp, _dp],
+    "set_group": [C.c_void_p, C.c_int, C.c_int, _ip],
+    "set_roles": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int],
+    "add_nhc": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double],
+    "set_misc": [C.c_void_p, C.c_int, C.c_int],
+    "add_interaction": [C.c_void_p, C.c_char_p, C.c_int, _dp, C.c_int, _ip, _ip, _dp, _ip],
+    "advance": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int],
+    "energies": [C.c_void_p, _dp, _dp, _dp, _dp],
+    "diagnostics": [C.c_void_p, _dp, _dp, _dp, _dp, _ip],
+    "download": [C.c_void_p, _dp, _dp, _dp],
+    "neighbours": [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip],
+    "normals": [C.c_void_p, C.c_int, _dp],
+    "get_nhc": [C.c_void_p, C.c_int, _dp, _dp],
+    "set_nhc": [C.c_void_p, C.c_int, _dp, _dp],
+    "timers": [C.c_void_p, _dp],
+    "launch_count": [C.c_void_p, C.POINTER(C.c_longlong)],
+    "synchronize": [C.c_void_p],
+    "destroy": [C.c_void_p],
+}
+
+
+def load_library(path=LIB_PATH, prefix="pfmds_"):
+    if not os.path.exists(path):
+        raise FileNotFoundError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    lib = C.CDLL(path)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, prefix + name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    getattr(lib, prefix + "last_error").argtypes = [C.c_void_p]
+    getattr(lib, prefix + "last_error").restype = C.c_char_p
+    getattr(lib, prefix + "version").restype = C.c_char_p
+    return lib
+
+
+class Engine:
+    """One simulation context (one CUDA stream on one device)."""
+
+    def __init__(self, pos, vel, mass, box, device=0, lib_path=LIB_PATH, prefix="pfmds_"):
+        self._lib = load_library(lib_path, prefix)
+        self._p = prefix
+        self._ctx = C.c_void_p()
+        self.n = int(len(mass))
+        pos = np.ascontiguousarray(pos, np.float64).reshape(-1)
+        vel = np.ascontiguousarray(vel, np.float64).reshape(-1)
+        mass = np.ascontiguousarray(mass, np.float64)
+        box = np.ascontiguousarray(box, np.float64)
+        self.groups = {}
+        self.inter = []   # (name, [(g1,g2,max,rcut,period)])
+        self.nhc_M = []
+        self._call("create", C.byref(self._ctx), device, self.n, _d(pos), _d(vel), _d(mass), _d(box))
+
+    def _call(self, name, *args):
+        rc = getattr(self._lib, self._p + name)(*args)
+        if rc != 0:
+            msg = getattr(self._lib, self._p + "last_error")(self._ctx)
+            raise PfmdsError(rc, (msg or b"").decode(errors="replace"))
+
+    # ---- setup ----
+    def set_group(self, g, idx1):
+        idx1 = np.ascontiguousarray(idx1, np.int32)
+        self.groups[g] = idx1
+        self._call("set_group", self._ctx, g, len(idx1), _i(idx1))
+
+    def set_roles(self, all_moving, xyz_moving, z_moving, all_atoms):
+        self.roles = (all_moving, xyz_moving, z_moving, all_atoms)
+        self._call("set_roles", self._ctx, all_moving, xyz_moving, z_moving, all_atoms)
+
+    def add_nhc(self, group, temperature, M, q1):
+        self.nhc_M.append(M)
+        self._call("add_nhc", self._ctx, group, float(temperature), M, float(q1))
+
+    def set_misc(self, zero_momentum_period, invert_z_vel):
+        self._call("set_misc", self._ctx, int(zero_momentum_period), int(bool(invert_z_vel)))
+
+    def add_interaction(self, name, params, lists):
+        p = np.ascontiguousarray(params, np.float64)
+        gn = np.ascontiguousarray([g for l in lists for g in l[:2]], np.int32)
+        mx = np.ascontiguousarray([l[2] for l in lists], np.int32)
+        rc = np.ascontiguousarray([l[3] for l in lists], np.float64)
+        pe = np.ascontiguousarray([l[4] for l in lists], np.int32)
+        self._call("add_interaction", self._ctx, name.encode(), len(p), _d(p), len(lists), _i(gn), _i(mx), _d(rc), _i(pe))
+        self.inter.append((name, list(lists)))
+
+    # ---- hot path ----
+    def advance(self, integrator, dt, first_md_step, n_steps):
+        kind = KIND[integrator] if isinstance(integrator, str) else int(integrator)
+        self._call("advance", self._ctx, kind, float(dt), int(first_md_step), int(n_steps))
+
+    def synchronize(self):
+        self._call("synchronize", self._ctx)
+
+    # ---- observables ----
+    def energies(self):
+        e = np.zeros(max(1, len(self.inter)))
+        en = np.zeros(max(1, len(self.nhc_M)))
+        ke, t = C.c_double(), C.c_double()
+        self._call("energies", self._ctx, _d(e), C.byref(ke), C.byref(t), _d(en))
+        return e[: len(self.inter)].copy(), ke.value, t.value, en[: len(self.nhc_M)].copy()
+
+    def diagnostics(self):
+        fs, mc, mcv = np.zeros(3), np.zeros(3), np.zeros(3)
+        vmax = C.c_double()
+        nl = np.zeros(max(1, sum(len(l) for _, l in self.inter)), np.int32)
+        self._call("diagnostics", self._ctx, _d(fs), _d(mc), _d(mcv), C.byref(vmax), _i(nl))
+        return fs, mc, mcv, vmax.value, nl
+
+    def download(self, forces=True):
+        pos, vel = np.zeros((self.n, 3)), np.zeros((self.n, 3))
+        frc = np.zeros((self.n, 3)) if forces else None
+        self._call("download", self._ctx, _d(pos), _d(vel), _d(frc))
+        return pos, vel, frc
+
+    def neighbours(self, interaction, lst):
+        g1, _, mx, _, _ = self.inter[interaction][1][lst]
+        rows = len(self.groups[g1])
+        nlist = np.zeros((rows, mx), np.int32)
+        nnum = np.zeros(rows, np.int32)
+        less = np.zeros(rows, np.int32)
+        self._call("neighbours", self._ctx, interaction, lst, _i(nlist), _i(nnum), _i(less))
+        return nlist, nnum, less
+
+    def normals(self, interaction):
+        g1 = self.inter[interaction][1][2][0]
+        out = np.zeros((len(self.groups[g1]), 3))
+        self._call("normals", self._ctx, interaction, _d(out))
+        return out
+
+    def get_nhc(self, k):
+        x, v = np.zeros(self.nhc_M[k]), np.zeros(self.nhc_M[k])
+        self._call("get_nhc", self._ctx, k, _d(x), _d(v))
+        return x, v
+
+    def set_nhc(self, k, x, v):
+        x = np.ascontiguousarray(x, np.float64)
+        v = np.ascontiguousarray(v, np.float64)
+        self._call("set_nhc", self._ctx, k, _d(x), _d(v))
+
+    def timers(self):
+        t = np.zeros(6)
+        self._call("timers", self._ctx, _d(t))
+        return t
+
+    def launch_count(self):
+        n = C.c_longlong()
+        self._call("launch_count", self._ctx, C.byref(n))
+        return n.value
+
+    def close(self):
+        if self._ctx:
+            getattr(self._lib, self._p + "destroy")(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def configure(case, device=0, lib_path=LIB_PATH, prefix="pfmds_"):
+    """Build an Engine from a case dict of pfmds_b200.inputs (same calls md() makes, md_simulation.f90:48-93)."""
+    from .inputs import group_indexes
+
+    e = Engine(case["pos"], case["vel"], case["mass"], case["box"], device=device, lib_path=lib_path, prefix=prefix)
+    for g in range(1, len(case["groups"]) + 1):
+        e.set_group(g, group_indexes(case, g))
+    r = case["roles"]
+    e.set_roles(r["all_moving"], r["xyz_moving"], r["z_moving"], r["all_atoms"])
+    for g, t, m, q in case["nhc"]:
+        e.add_nhc(g, t, m, q)
+    e.set_misc(case["zero_momentum_period"], case["invert_z_vel"])
+    for it in case["interactions"]:
+        e.add_interaction(it["name"], it["params"], it["lists"])
+    return e
