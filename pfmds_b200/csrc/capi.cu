@@ -1,0 +1,561 @@
+// pfmds_b200 — the C ABI of include/pfmds_b200.h and the per-step orchestration of the device
+// kernels (the body of `do md_step` in code_source/MOLECULAR_DYNAMICS/md_simulation.f90:138-186).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pfmds_b200.h"
+#include "ctx.hpp"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
+
+namespace {
+
+struct Fail { int code; std::string msg; };
+[[noreturn]] void fail(int code, const std::string& m) { throw Fail{code, m}; }
+
+template <class Fn>
+int guarded(pfmds_ctx* c, Fn fn) {
+    try { fn(); return PFMDS_OK; }
+    catch (const Fail& f) { if (c) c->err_msg = f.msg; return f.code; }
+    catch (const std::string& s) { if (c) c->err_msg = s; return PFMDS_ERR_CUDA; }
+    catch (const std::exception& e) { if (c) c->err_msg = e.what(); return PFMDS_ERR_INVALID; }
+}
+
+int kind_of(const std::string& n) {
+    if (n == "lj") return K_LJ;
+    if (n == "lj1g") return K_LJ1G;
+    if (n == "ljc") return K_LJC;
+    if (n == "morsec") return K_MORSEC;
+    if (n == "tb") return K_TB;
+    if (n == "rjl") return K_RJL;
+    return -1;
+}
+int nl_n_of(int kind) { return kind == K_LJ ? 2 : (kind == K_LJC || kind == K_MORSEC) ? 3 : 1; }
+
+const std::vector<int>& group_of(pfmds_ctx* c, int g) {
+    if (g < 1 || g > (int)c->groups.size()) fail(PFMDS_ERR_INVALID, "error: group number " + std::to_string(g) + " is not defined");
+    return c->groups[(size_t)g - 1];
+}
+
+// poll the device error word; turns the first recorded condition into the reference's message
+void check_device_error(pfmds_ctx* c) {
+    int h[PFMDS_ERRW];
+    CK(cudaMemcpyAsync(h, c->err, sizeof h, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (h[0] == 0) return;
+    if (h[0] == E_OUT_OF_CELL) fail(PFMDS_ERR_OUT_OF_CELL, " " + std::to_string(h[1] + 1) + "  particle out of cell");
+    if (h[0] == E_TOO_MANY) fail(PFMDS_ERR_TOO_MANY_NEIGHBOURS, "error: too many neighbours (atom " + std::to_string(h[1] + 1) + ", " + std::to_string(h[2]) + " found)");
+    if (h[0] == E_GR_NEIB)
+        fail(PFMDS_ERR_GR_NEIGHBOURS, std::string(h[2] > 3 ? "error: too many gr nearest neibs" : "error: not enough gr nearest neibs") + " (atom " +
+                                          std::to_string(h[1] + 1) + ", " + std::to_string(h[2]) + " found)");
+    fail(PFMDS_ERR_CUDA, "device error " + std::to_string(h[0]));
+}
+
+// Validate the description, build the masks, allocate the lists.  Runs once, at the first advance.
+void finalize(pfmds_ctx* c) {
+    if (c->finalized) return;
+    const int N = c->N;
+    if (c->groups.size() > PFMDS_MAX_GROUPS) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: more than 32 atom groups");
+    c->h_gmask.assign((size_t)N, 0u);
+    for (size_t g = 0; g < c->groups.size(); ++g)
+        for (int i1 : c->groups[g]) {
+            if (i1 < 1 || i1 > N) fail(PFMDS_ERR_INVALID, "error: atom index out of range in group " + std::to_string(g + 1));
+            uint32_t b = 1u << g;
+            if (c->h_gmask[(size_t)i1 - 1] & b)
+                fail(PFMDS_ERR_UNSUPPORTED, "unsupported: atom " + std::to_string(i1) + " listed twice in group " + std::to_string(g + 1));
+            c->h_gmask[(size_t)i1 - 1] |= b;
+        }
+    group_of(c, c->all_moving); group_of(c, c->xyz_moving); group_of(c, c->z_moving); group_of(c, c->all_atoms);
+    auto monotone = [&](int g) { const auto& v = group_of(c, g); return std::is_sorted(v.begin(), v.end()); };
+    int first_tb = -1;
+    for (size_t k = 0; k < c->inter.size(); ++k)
+        if (c->inter[k].kind == K_TB) { first_tb = (int)k; break; }
+    for (size_t k = 0; k < c->inter.size(); ++k) {
+        Inter& it = c->inter[k];
+        for (int j = 0; j < it.nl_n; ++j) { group_of(c, it.nl[j].g1); group_of(c, it.nl[j].g2); }
+        NList& a = it.nl[0];
+        if (it.kind == K_LJ1G || it.kind == K_TB || it.kind == K_RJL) {
+            // the reference indexes group-1 rows with group-2 local numbers in these potentials
+            // (LennardJones_1g.f90:83, TersoffBrenner.f90:56-59, RosatoGuillopeLegrand.f90:88)
+            if (group_of(c, a.g1) != group_of(c, a.g2)) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: " + it.name + " needs group1 == group2");
+        }
+        if (it.kind == K_LJ1G && !monotone(a.g1))
+            fail(PFMDS_ERR_UNSUPPORTED, "unsupported: lj1g group indexes are not ascending; the reference's half-list rule (lessnnum, "
+                                        "md_neighbours.f90:78) silently drops pairs for such groups");
+        if (it.kind == K_LJ || it.kind == K_LJC || it.kind == K_MORSEC) {
+            // nl(2) is the converse of nl(1): rows = group2 of line 1, r_cut and period of line 1, capacity of line 2
+            NList& b = it.nl[1];
+            if (group_of(c, a.g2).size() > group_of(c, b.g1).size()) fail(PFMDS_ERR_LIST_SIZE, "error: group2%N>cnl%N");
+            b.g1 = a.g2; b.g2 = a.g1; b.rcut = a.rcut; b.period = a.period;
+        }
+        if (it.kind == K_LJC || it.kind == K_MORSEC) {
+            NList& n3 = it.nl[2];
+            if (first_tb >= 0) {
+                if (first_tb > (int)k)
+                    fail(PFMDS_ERR_UNSUPPORTED, "unsupported: 'tb' must be listed before '" + it.name + "' (the nearest-neighbour list is taken from it, md_interactions.f90:157-167)");
+                if (n3.maxn != 3) fail(PFMDS_ERR_LIST_SIZE, "error: nl_nn%neighb_num_max/=nnum_nn");
+                if (group_of(c, c->inter[first_tb].nl[0].g1) != group_of(c, a.g1)) fail(PFMDS_ERR_LIST_SIZE, "error: nl%N/=nl_nn%N");
+                n3.from_tb = true; n3.src_inter = first_tb;
+                n3.g1 = n3.g2 = a.g1;
+                n3.period = c->inter[first_tb].nl[0].period;
+            } else {
+                if (n3.maxn != 3) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: the nearest-neighbour list of " + it.name + " must have capacity 3");
+                if (group_of(c, n3.g1) != group_of(c, a.g1)) fail(PFMDS_ERR_LIST_SIZE, "error: nl%N/=nl_nn%N");
+            }
+        }
+        for (int j = 0; j < it.nl_n; ++j) {
+            NList& l = it.nl[j];
+            if (l.maxn < 1 || l.period < 1 || !(l.rcut > 0)) fail(PFMDS_ERR_INVALID, "error: bad neighbour list parameters");
+            CK(cudaMalloc(&l.nlist, sizeof(int) * (size_t)l.maxn * c->stride));
+            CK(cudaMalloc(&l.nnum, sizeof(int) * c->stride));
+            CK(cudaMemsetAsync(l.nnum, 0, sizeof(int) * c->stride, c->st));
+        }
+        if (it.kind == K_RJL) CK(cudaMalloc(&it.aux, sizeof(double) * c->stride));
+        if (it.kind == K_TB) CK(cudaMalloc(&it.aux, sizeof(double) * (size_t)a.maxn * c->stride));
+        if (it.kind == K_LJC || it.kind == K_MORSEC) {
+            CK(cudaMalloc(&it.gnorm, sizeof(double4) * c->stride));
+            CK(cudaMalloc(&it.tvec, sizeof(double4) * c->stride));
+            CK(cudaMemsetAsync(it.gnorm, 0, sizeof(double4) * c->stride, c->st));
+            CK(cudaMemsetAsync(it.tvec, 0, sizeof(double4) * c->stride, c->st));
+        }
+    }
+    for (auto& t : c->nhc) {
+        t.L = (int)group_of(c, t.group).size();
+        if (t.L < 1) fail(PFMDS_ERR_NHC_PARAMS, "error: wrong nhc parameters");
+        // q(i) = q(1)/(3L), i >= 2  (md_integrators.f90:192-195)
+        std::vector<double> st((size_t)3 * t.M + 2, 0.);
+        double q1;
+        CK(cudaMemcpy(&q1, t.state + 2 * t.M, sizeof(double), cudaMemcpyDeviceToHost));
+        st[2 * (size_t)t.M] = q1;
+        for (int i = 1; i < t.M; ++i) st[2 * (size_t)t.M + i] = q1 / (3. * t.L);
+        st[3 * (size_t)t.M] = 1.;
+        CK(cudaMemcpy(t.state, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemcpyAsync(c->gmask, c->h_gmask.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, c->st));
+    if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
+    nl_setup_grid(c);
+    CK(cudaStreamSynchronize(c->st));
+    c->finalized = true;
+}
+
+struct PhaseTimer {
+    pfmds_ctx* c; int slot;
+    PhaseTimer(pfmds_ctx* c_, int s) : c(c_), slot(s) { if (c->timers_on) cudaEventRecord(c->ev0, c->st); }
+    ~PhaseTimer() {
+        if (!c->timers_on) return;
+        cudaEventRecord(c->ev1, c->st);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->t_phase[slot] += ms * 1e-3;
+    }
+};
+
+// update_interactions_neighbour_lists, md_interactions.f90:138-178
+void update_lists(pfmds_ctx* c, int step) {
+    bool any = false, all = true;
+    for (auto& it : c->inter) {
+        for (int j = 0; j < it.nl_n; ++j) {
+            NList& l = it.nl[j];
+            bool rb = (step % l.period == 0) || !l.built;
+            any |= rb;
+            all &= rb;
+        }
+    }
+    if (any) {
+        PhaseTimer t(c, 2);
+        nl_bin_atoms(c, all);
+        for (auto& it : c->inter) {
+            for (int j = 0; j < it.nl_n; ++j) {
+                NList& l = it.nl[j];
+                if (!((step % l.period == 0) || !l.built)) continue;
+                if (l.from_tb) nl_nearest3_from(c, l, c->inter[(size_t)l.src_inter].nl[0]);
+                else nl_build(c, l);
+            }
+        }
+    }
+    for (size_t k = 0; k < c->inter.size(); ++k) normals_interaction(c, (int)k);  // update_norm_in_graphene, every step
+}
+
+void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call) {
+    {
+        PhaseTimer t(c, 0);
+        if (first_of_call) integ_check_positions(c);
+        if (c->invert_z) integ_invert_z(c);
+        if (step != 0) {
+            if (kind == PFMDS_NVT)
+                for (auto& th : c->nhc) integ_nhc_half(c, th, dt);
+            integ_kick_drift(c, dt);
+        }
+    }
+    {
+        PhaseTimer t(c, 1);
+        update_lists(c, step);
+    }
+    {
+        PhaseTimer t(c, 4);
+        if (step % c->zero_momentum_period == 0) integ_zero_momentum(c);
+        forces_zero(c);
+        for (size_t k = 0; k < c->inter.size(); ++k) forces_interaction(c, (int)k);
+    }
+    if (step != 0) {
+        PhaseTimer t(c, 0);
+        integ_kick(c, dt);
+        if (kind == PFMDS_NVT)
+            for (auto& th : c->nhc) integ_nhc_half(c, th, dt);
+        if (kind == PFMDS_NVMS) integ_quench(c);
+    }
+}
+
+__global__ void k_max_int(int n, const int* __restrict__ a, int* out) {
+    int m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, a[i]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, const double* vel, const double* mass, const double box[3]) {
+    if (!out) return PFMDS_ERR_INVALID;
+    pfmds_ctx* c = new pfmds_ctx;
+    *out = c;
+    return guarded(c, [&] {
+        if (n_atoms < 1 || !pos || !vel || !mass || !box) fail(PFMDS_ERR_INVALID, "error: bad arguments to pfmds_create");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            fail(PFMDS_ERR_CUDA, "no CUDA device: pfmds_b200 has no CPU fallback");
+        if (device < 0 || device >= ndev) fail(PFMDS_ERR_INVALID, "error: CUDA device " + std::to_string(device) + " does not exist");
+        c->dev = device;
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        c->N = n_atoms;
+        c->stride = ((size_t)n_atoms + 31) / 32 * 32;
+        for (int k = 0; k < 3; ++k) { c->box.L[k] = box[k]; c->box.h[k] = 0.5 * box[k]; }  // md_read_write.f90:32-35
+        const size_t S = c->stride;
+        CK(cudaMalloc(&c->pos, sizeof(double4) * S)); CK(cudaMalloc(&c->pos2, sizeof(double4) * S));
+        CK(cudaMalloc(&c->vel, sizeof(double4) * S)); CK(cudaMalloc(&c->vel2, sizeof(double4) * S));
+        CK(cudaMalloc(&c->frc, sizeof(double4) * S));
+        CK(cudaMalloc(&c->gmask, sizeof(uint32_t) * S)); CK(cudaMalloc(&c->gmask2, sizeof(uint32_t) * S));
+        CK(cudaMalloc(&c->orig, sizeof(int) * S)); CK(cudaMalloc(&c->orig2, sizeof(int) * S));
+        CK(cudaMalloc(&c->cell_atoms, sizeof(int) * S)); CK(cudaMalloc(&c->cid, sizeof(int) * S));
+        size_t nparts = (S + 127) / 128 + RED_BLOCKS;
+        CK(cudaMalloc(&c->part, sizeof(double) * 16 * nparts));
+        CK(cudaMalloc(&c->red, sizeof(double) * 64));
+        CK(cudaMalloc(&c->err, sizeof(int) * PFMDS_ERRW));
+        CK(cudaMemset(c->err, 0, sizeof(int) * PFMDS_ERRW));
+        CK(cudaMemset(c->frc, 0, sizeof(double4) * S));
+        std::vector<double4> hp(S, make_double4(0, 0, 0, 0)), hv(S, make_double4(0, 0, 0, 1));
+        std::vector<int> ho(S, 0);
+        for (int i = 0; i < n_atoms; ++i) {
+            hp[(size_t)i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0.);
+            hv[(size_t)i] = make_double4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], mass[i]);
+            ho[(size_t)i] = i;
+        }
+        CK(cudaMemcpy(c->pos, hp.data(), sizeof(double4) * S, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->vel, hv.data(), sizeof(double4) * S, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->orig, ho.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+        CK(cudaMemset(c->gmask, 0, sizeof(uint32_t) * S));
+        const char* tm = std::getenv("PFMDS_TIMERS");
+        c->timers_on = tm && tm[0] == '1';
+        CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    });
+}
+
+int pfmds_set_group(pfmds_ctx* c, int g, int n, const int* idx) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (c->finalized) fail(PFMDS_ERR_INVALID, "error: groups must be defined before the first pfmds_advance");
+        if (g < 1 || n < 0 || (n > 0 && !idx)) fail(PFMDS_ERR_INVALID, "error: bad arguments to pfmds_set_group");
+        if ((int)c->groups.size() < g) c->groups.resize((size_t)g);
+        c->groups[(size_t)g - 1].assign(idx, idx + n);
+    });
+}
+
+int pfmds_set_roles(pfmds_ctx* c, int am, int xyz, int z, int all) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] { c->all_moving = am; c->xyz_moving = xyz; c->z_moving = z; c->all_atoms = all; });
+}
+
+int pfmds_add_nhc(pfmds_ctx* c, int g, double T, int M, double q1) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (c->finalized) fail(PFMDS_ERR_INVALID, "error: thermostats must be defined before the first pfmds_advance");
+        if (M < 1 || q1 < 0. || T < 0.) fail(PFMDS_ERR_NHC_PARAMS, "error: wrong nhc parameters");  // md_integrators.f90:187
+        Nhc t; t.group = g; t.M = M; t.temperature = T;
+        CK(cudaMalloc(&t.state, sizeof(double) * ((size_t)3 * M + 2)));
+        std::vector<double> st((size_t)3 * M + 2, 0.);
+        st[2 * (size_t)M] = q1;
+        CK(cudaMemcpy(t.state, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+        c->nhc.push_back(t);
+    });
+}
+
+int pfmds_set_misc(pfmds_ctx* c, int zmp, int inv) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (zmp < 1) fail(PFMDS_ERR_INVALID, "error: zero_momentum_period must be positive");
+        c->zero_momentum_period = zmp; c->invert_z = inv != 0;
+    });
+}
+
+int pfmds_add_interaction(pfmds_ctx* c, const char* name, int np, const double* p, int nl_n, const int* gn, const int* maxn, const double* rcut,
+                          const int* period) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (c->finalized) fail(PFMDS_ERR_INVALID, "error: interactions must be defined before the first pfmds_advance");
+        Inter it;
+        it.name = name ? name : "";
+        it.kind = kind_of(it.name);
+        if (it.kind < 0) fail(PFMDS_ERR_UNKNOWN_INTERACTION, "error: unknown interaction name");  // md_interactions.f90:119-120
+        it.nl_n = nl_n_of(it.kind);
+        if (nl_n != it.nl_n) fail(PFMDS_ERR_INVALID, "error: " + it.name + " needs " + std::to_string(it.nl_n) + " neighbour list lines");
+        auto need = [&](int n) { if (np != n || !p) fail(PFMDS_ERR_INVALID, "error: " + it.name + " needs " + std::to_string(n) + " parameters"); };
+        switch (it.kind) {
+        case K_LJ: need(4); it.lj = LJp{p[0], p[1], p[2], p[3]}; break;
+        case K_LJ1G: {  // LennardJones_1g.f90:21-24
+            need(4);
+            double s2 = p[1] * p[1], s6 = s2 * s2 * s2, s12 = s6 * s6;
+            it.lj1g = LJ1Gp{p[2], p[3], 4. * p[0] * s6, 4. * p[0] * s12, 6. * 4. * p[0] * s6, 12. * 4. * p[0] * s12};
+            break;
+        }
+        case K_LJC: need(6); it.ljc = LJCp{p[0], p[1], p[2], p[3], p[4], p[5] != 0.}; break;
+        case K_MORSEC: need(7); it.mor = MORp{p[0], p[1], p[2], p[3], p[4], p[5], p[6] != 0.}; break;
+        case K_TB: need(10); it.tb = TBp{p[0], p[1], p[2], p[3], p[4], p[5], p[6] * p[6], p[7] * p[7], p[8], p[9]}; break;  // TersoffBrenner.f90:19-20
+        case K_RJL: need(7); it.rjl = RJLp{p[0], p[1], p[2], p[3], p[4], p[5], p[6]}; break;
+        }
+        for (int j = 0; j < nl_n; ++j) {
+            it.nl[j].g1 = gn[2 * j]; it.nl[j].g2 = gn[2 * j + 1]; it.nl[j].maxn = maxn[j]; it.nl[j].rcut = rcut[j]; it.nl[j].period = period[j];
+        }
+        c->inter.push_back(it);
+    });
+}
+
+int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (n < 0 || first < 0) fail(PFMDS_ERR_INVALID, "error: bad step range");
+        CK(cudaSetDevice(c->dev));
+        finalize(c);
+        for (int s = first; s < first + n; ++s) do_step(c, s, kind, dt, s == first);
+        CK(cudaGetLastError());
+    });
+}
+
+int pfmds_synchronize(pfmds_ctx* c) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] { CK(cudaSetDevice(c->dev)); CK(cudaStreamSynchronize(c->st)); check_device_error(c); });
+}
+
+int pfmds_energies(pfmds_ctx* c, double* e_inter, double* ke, double* temp, double* e_nhc) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        finalize(c);
+        {
+            PhaseTimer t(c, 5);
+            for (size_t k = 0; k < c->inter.size(); ++k) energy_interaction(c, (int)k);
+            integ_kinetic_energy(c, c->all_moving, c->red);
+        }
+        std::vector<double> he(c->inter.size() + 1, 0.);
+        if (!c->inter.empty()) CK(cudaMemcpyAsync(he.data(), c->energy, sizeof(double) * c->inter.size(), cudaMemcpyDeviceToHost, c->st));
+        double hke = 0;
+        CK(cudaMemcpyAsync(&hke, c->red, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        std::vector<std::vector<double>> hs(c->nhc.size());
+        for (size_t k = 0; k < c->nhc.size(); ++k) {
+            hs[k].resize((size_t)3 * c->nhc[k].M + 2);
+            CK(cudaMemcpyAsync(hs[k].data(), c->nhc[k].state, sizeof(double) * hs[k].size(), cudaMemcpyDeviceToHost, c->st));
+        }
+        check_device_error(c);  // synchronises
+        if (e_inter) for (size_t k = 0; k < c->inter.size(); ++k) e_inter[k] = he[k];
+        if (ke) *ke = hke;
+        // calculate_temperature, md_general.f90:301-311
+        if (temp) *temp = 2 * hke / PFMDS_KB / (3 * (double)(int)group_of(c, c->all_moving).size());
+        if (e_nhc)
+            for (size_t k = 0; k < c->nhc.size(); ++k) {  // calculate_nose_hoover_chain_energy, md_integrators.f90:247-260
+                const Nhc& t = c->nhc[k];
+                const double *x = hs[k].data(), *v = x + t.M, *q = x + 2 * t.M;
+                double kt = PFMDS_KB * t.temperature;
+                double e = q[0] / 2 * (v[0] * v[0]) + 3. * t.L * kt * x[0];
+                for (int i = 1; i < t.M; ++i) e = e + q[i] / 2 * (v[i] * v[i]) + kt * x[i];
+                e_nhc[k] = e;
+            }
+    });
+}
+
+int pfmds_diagnostics(pfmds_ctx* c, double fs[3], double mc[3], double mcv[3], double* vmax, int* nl_load) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        finalize(c);
+        integ_diagnostics(c, c->red + 32);
+        size_t nl_total = 0;
+        for (auto& it : c->inter) nl_total += (size_t)it.nl_n;
+        int* d_max = nullptr;
+        std::vector<int> hmax(nl_total + 1, 0);
+        if (nl_total) {
+            CK(cudaMalloc(&d_max, sizeof(int) * nl_total));
+            CK(cudaMemsetAsync(d_max, 0, sizeof(int) * nl_total, c->st));
+            size_t k = 0;
+            for (auto& it : c->inter)
+                for (int j = 0; j < it.nl_n; ++j, ++k) { k_max_int<<<64, 256, 0, c->st>>>(c->N, it.nl[j].nnum, d_max + k); c->launches += 1; }
+            CK(cudaMemcpyAsync(hmax.data(), d_max, sizeof(int) * nl_total, cudaMemcpyDeviceToHost, c->st));
+        }
+        double h[11];
+        CK(cudaMemcpyAsync(h, c->red + 32, sizeof h, cudaMemcpyDeviceToHost, c->st));
+        check_device_error(c);
+        if (d_max) cudaFree(d_max);
+        for (int k = 0; k < 3; ++k) {
+            if (fs) fs[k] = h[k];
+            if (mc) mc[k] = h[3 + k] / h[9];
+            if (mcv) mcv[k] = h[6 + k] / h[9];
+        }
+        if (vmax) *vmax = std::sqrt(h[10]);
+        if (nl_load) for (size_t k = 0; k < nl_total; ++k) nl_load[k] = hmax[k];
+    });
+}
+
+int pfmds_download(pfmds_ctx* c, double* pos, double* vel, double* frc) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        const size_t N = (size_t)c->N;
+        std::vector<int> ho(N);
+        std::vector<double4> buf(N);
+        CK(cudaMemcpyAsync(ho.data(), c->orig, sizeof(int) * N, cudaMemcpyDeviceToHost, c->st));
+        auto pull = [&](const double4* d, double* out) {
+            if (!out) return;
+            CK(cudaMemcpyAsync(buf.data(), d, sizeof(double4) * N, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            for (size_t s = 0; s < N; ++s) { double* o = out + 3 * (size_t)ho[s]; o[0] = buf[s].x; o[1] = buf[s].y; o[2] = buf[s].z; }
+        };
+        CK(cudaStreamSynchronize(c->st));
+        pull(c->pos, pos); pull(c->vel, vel); pull(c->frc, frc);
+        check_device_error(c);
+    });
+}
+
+int pfmds_neighbours(pfmds_ctx* c, int inter, int list, int* nlist, int* nnum, int* lessnnum) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        if (!c->finalized) fail(PFMDS_ERR_INVALID, "error: no neighbour lists before the first pfmds_advance");
+        if (inter < 0 || inter >= (int)c->inter.size() || list < 0 || list >= c->inter[(size_t)inter].nl_n) fail(PFMDS_ERR_INVALID, "error: no such neighbour list");
+        const NList& l = c->inter[(size_t)inter].nl[list];
+        const size_t N = (size_t)c->N, S = c->stride;
+        std::vector<int> ho(N), hn(N), hl((size_t)l.maxn * S);
+        CK(cudaMemcpyAsync(ho.data(), c->orig, sizeof(int) * N, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hn.data(), l.nnum, sizeof(int) * N, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hl.data(), l.nlist, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, c->st));
+        check_device_error(c);
+        const auto& G1 = group_of(c, l.g1);
+        const auto& G2 = group_of(c, l.g2);
+        std::vector<int> slot_of(N), local2(N, -1);
+        for (size_t s = 0; s < N; ++s) slot_of[(size_t)ho[s]] = (int)s;
+        for (size_t k = 0; k < G2.size(); ++k) local2[(size_t)G2[k] - 1] = (int)k;
+        std::vector<std::pair<int, int>> row;  // (group-2 local, file index)
+        for (size_t r = 0; r < G1.size(); ++r) {
+            int fi = G1[r] - 1, s = slot_of[(size_t)fi];
+            row.clear();
+            for (int p = 0; p < hn[(size_t)s]; ++p) {
+                int fj = ho[(size_t)hl[(size_t)p * S + (size_t)s]];
+                row.emplace_back(local2[(size_t)fj], fj);
+            }
+            std::sort(row.begin(), row.end());
+            int less = -1;
+            for (size_t p = 0; p < row.size(); ++p)
+                if (less == -1 && fi < row[p].second) less = (int)p;  // md_neighbours.f90:78
+            if (nnum) nnum[r] = (int)row.size();
+            if (lessnnum) lessnnum[r] = less == -1 ? (int)row.size() : less;
+            if (nlist)
+                for (int p = 0; p < l.maxn; ++p) nlist[r * (size_t)l.maxn + (size_t)p] = p < (int)row.size() ? row[(size_t)p].first + 1 : 0;
+        }
+    });
+}
+
+int pfmds_normals(pfmds_ctx* c, int inter, double* out) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        if (inter < 0 || inter >= (int)c->inter.size() || !c->inter[(size_t)inter].gnorm) fail(PFMDS_ERR_INVALID, "error: not an ljc/morsec interaction");
+        const Inter& it = c->inter[(size_t)inter];
+        const size_t N = (size_t)c->N;
+        std::vector<int> ho(N);
+        std::vector<double4> g(N);
+        CK(cudaMemcpyAsync(ho.data(), c->orig, sizeof(int) * N, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(g.data(), it.gnorm, sizeof(double4) * N, cudaMemcpyDeviceToHost, c->st));
+        check_device_error(c);
+        std::vector<int> slot_of(N);
+        for (size_t s = 0; s < N; ++s) slot_of[(size_t)ho[s]] = (int)s;
+        const auto& G1 = group_of(c, it.nl[0].g1);
+        for (size_t r = 0; r < G1.size(); ++r) {
+            const double4& v = g[(size_t)slot_of[(size_t)G1[r] - 1]];
+            out[3 * r] = v.x; out[3 * r + 1] = v.y; out[3 * r + 2] = v.z;
+        }
+    });
+}
+
+int pfmds_get_nhc(pfmds_ctx* c, int k, double* x, double* v) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (k < 0 || k >= (int)c->nhc.size()) fail(PFMDS_ERR_INVALID, "error: no such thermostat");
+        CK(cudaSetDevice(c->dev));
+        CK(cudaStreamSynchronize(c->st));
+        const Nhc& t = c->nhc[(size_t)k];
+        if (x) CK(cudaMemcpy(x, t.state, sizeof(double) * t.M, cudaMemcpyDeviceToHost));
+        if (v) CK(cudaMemcpy(v, t.state + t.M, sizeof(double) * t.M, cudaMemcpyDeviceToHost));
+    });
+}
+int pfmds_set_nhc(pfmds_ctx* c, int k, const double* x, const double* v) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (k < 0 || k >= (int)c->nhc.size()) fail(PFMDS_ERR_INVALID, "error: no such thermostat");
+        CK(cudaSetDevice(c->dev));
+        CK(cudaStreamSynchronize(c->st));
+        const Nhc& t = c->nhc[(size_t)k];
+        if (x) CK(cudaMemcpy(t.state, x, sizeof(double) * t.M, cudaMemcpyHostToDevice));
+        if (v) CK(cudaMemcpy(t.state + t.M, v, sizeof(double) * t.M, cudaMemcpyHostToDevice));
+    });
+}
+
+int pfmds_timers(pfmds_ctx* c, double s[6]) {
+    if (!c || !s) return PFMDS_ERR_INVALID;
+    // slots: 0 pos_vel, 1 nlists, 2 nlsearch, 3 nldistance (no such pass on the device), 4 forces, 5 energy
+    for (int k = 0; k < 6; ++k) s[k] = c->t_phase[k];
+    return PFMDS_OK;
+}
+int pfmds_launch_count(pfmds_ctx* c, long long* n) {
+    if (!c || !n) return PFMDS_ERR_INVALID;
+    *n = c->launches;
+    return PFMDS_OK;
+}
+const char* pfmds_last_error(pfmds_ctx* c) { return c ? c->err_msg.c_str() : "null context"; }
+
+int pfmds_destroy(pfmds_ctx* c) {
+    if (!c) return PFMDS_OK;
+    cudaSetDevice(c->dev);
+    if (c->st) cudaStreamSynchronize(c->st);
+    for (auto& it : c->inter) {
+        for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nnum); }
+        cudaFree(it.aux); cudaFree(it.gnorm); cudaFree(it.tvec);
+    }
+    for (auto& t : c->nhc) cudaFree(t.state);
+    void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,
+                    c->cid, c->scan_tmp, c->part, c->red, c->energy, c->err};
+    for (void* p : ptrs) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+    return PFMDS_OK;
+}
+const char* pfmds_version(void) { return "pfmds_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// pfmds_b200 — device-side data model shared by all kernels (sm_100a, FP64).
+//
+// Layout in HBM (one context = one simulation):
+//   pos[N]  double4 {x,y,z,scratch}   32-byte records: one sector per neighbour gather
+//   vel[N]  double4 {vx,vy,vz,mass}   the kick/KE kernels get the mass with the velocity
+//   frc[N]  double4 {fx,fy,fz,-}
+//   gmask[N] uint32  bit g-1 set when the atom is in settings-file group g
+//   orig[N]  int     file-order index of the atom stored at this slot
+// Atoms are stored in cell order (re-sorted whenever every neighbour list is rebuilt) so that the
+// j-atoms of a warp's i-atoms sit in a few contiguous ranges; `orig` maps back for I/O.
+// A neighbour list is an ELL block: nlist[p*stride + i] (stride = N rounded up to 32) so that the
+// 32 lanes of a warp read slot p of 32 consecutive atoms with one coalesced request; entries are
+// slot indices, only int32 indices are stored and distances are recomputed in registers every
+// step (the reference caches dr(3,max,N) and |dr| instead: md_general.f90:30-35).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PFMDS_MAX_GROUPS 32
+#define PFMDS_ERRW 4  // error word: code, detail a, detail b, spare
+
+// the reference's FP64 literals (md_general.f90:165,304; md_integrators.f90:62,211; cut_off_function.f90:8)
+#define PFMDS_MASS_COEF (1.6605389217 / 1.6021765654 * 100.0)
+#define PFMDS_KB (1.3806488 / 1.6021765654 * 1.0e-4)
+#define PFMDS_PI 3.14159265358979
+
+enum { K_LJ = 0, K_LJ1G = 1, K_LJC = 2, K_MORSEC = 3, K_TB = 4, K_RJL = 5 };
+
+struct BoxD { double L[3]; double h[3]; };
+
+// device error codes mirror include/pfmds_b200.h
+enum { E_OUT_OF_CELL = 10, E_TOO_MANY = 11, E_GR_NEIB = 12 };
+
+__device__ __forceinline__ void raise_error(int* err, int code, int a, int b) {
+    if (atomicCAS(&err[0], 0, code) == 0) { err[1] = a; err[2] = b; }
+}
+
+// minimum image, bit-identical to dr - half*(sign(1,dr-half)+sign(1,dr+half))  (md_general.f90:423-441)
+__device__ __forceinline__ double min_image(double d, double half, double L) {
+    if (d >= half) d -= L;
+    else if (d < -half) d += L;
+    return d;
+}
+
+// cosine switch and its derivative divided by r (cut_off_function.f90:6-28); called only for r < R2
+__device__ __forceinline__ void fcut_dfcut(double r, double R1, double R2, double& f, double& dfr) {
+    if (r < R1) { f = 1.0; dfr = 0.0; return; }
+    double s, c;
+    sincos(PFMDS_PI * (r - R1) / (R2 - R1), &s, &c);
+    f = (1.0 + c) / 2;
+    dfr = -s * PFMDS_PI / (R2 - R1) / r / 2;
+}
+__device__ __forceinline__ double fcut_only(double r, double R1, double R2) {
+    if (r < R1) return 1.0;
+    return (1.0 + cos(PFMDS_PI * (r - R1) / (R2 - R1))) / 2;
+}
+
+// block-wide sum of `v` (blockDim.x multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (w == 0)
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// parameters of one interaction, passed by value to the kernels
+struct LJp { double eps, sig, R1, R2; };
+struct LJ1Gp { double R1, R2, c6, c12, c6t6, c12t12; };
+struct LJCp { double eps, sig, delt, R1, R2; int simplified; };          // ljc
+struct MORp { double d, r, a, delt, R1, R2; int simplified; };           // morsec
+struct TBp { double d, s, b, r0, delt, a0, c02, d02, R1, R2; };
+struct RJLp { double A0, xi, p, q, r0, R1, R2; };
+
+struct ListView { const int* nlist; const int* nnum; size_t stride; };

@@ -1,0 +1,103 @@
+// pfmds_b200 — host-side context behind the opaque pfmds_ctx of include/pfmds_b200.h, and the
+// launch wrappers the C ABI calls (defined in nl.cu, forces.cu, integrate.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct NList {
+    int g1 = 0, g2 = 0, maxn = 0, period = 1;
+    double rcut = 0;
+    int* nlist = nullptr;  // ELL [maxn][stride]
+    int* nnum = nullptr;   // [stride]
+    bool from_tb = false;  // ljc/morsec nl(3) derived from the first tb list (graphenenorm.f90:58-71)
+    int src_inter = -1;
+    bool built = false;
+    ListView view(size_t stride) const { return ListView{nlist, nnum, stride}; }
+};
+
+struct Inter {
+    int kind = -1;
+    std::string name;
+    int nl_n = 0;
+    NList nl[3];
+    LJp lj{}; LJ1Gp lj1g{}; LJCp ljc{}; MORp mor{}; TBp tb{}; RJLp rjl{};
+    double* aux = nullptr;    // rjl: 1/Eb per atom [N]; tb: bond orders B, ELL [maxn][stride]
+    double4* gnorm = nullptr; // ljc/morsec: unit normal per carbon atom {nx,ny,nz,-}
+    double4* tvec = nullptr;  // ljc/morsec: T_i = sum_p V2 V3 f_c/(n_i.dr) dr  (normal-derivative term)
+};
+
+struct Nhc {
+    int group = 0, M = 0, L = 0;
+    double temperature = 0;
+    double* state = nullptr;  // device: x[M], v[M], q[M], then s, e
+};
+
+struct pfmds_ctx {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    int N = 0;
+    size_t stride = 0;  // N rounded up to 32
+    BoxD box{};
+    // state, double-buffered for the cell re-sort
+    double4 *pos = nullptr, *vel = nullptr, *frc = nullptr, *pos2 = nullptr, *vel2 = nullptr;
+    uint32_t *gmask = nullptr, *gmask2 = nullptr;
+    int *orig = nullptr, *orig2 = nullptr;
+    // cell grid
+    int ncell[3]{1, 1, 1};
+    int ncells = 0;
+    double cell_rc = 0;
+    int *cell_cnt = nullptr, *cell_start = nullptr, *cell_atoms = nullptr, *cid = nullptr, *scan_tmp = nullptr;
+    bool identity_order = false;  // cell_atoms[k]==k (atoms physically in cell order)
+    // reductions
+    double* part = nullptr;   // [RED_BLOCKS][8] block partials
+    double* red = nullptr;    // [64] reduced values
+    double* energy = nullptr; // [n_inter] device energies
+    int* err = nullptr;       // [PFMDS_ERRW]
+    // host description
+    std::vector<std::vector<int>> groups;  // 1-based group -> 1-based file indexes
+    std::vector<uint32_t> h_gmask;         // by file index
+    int all_moving = 1, xyz_moving = 1, z_moving = 1, all_atoms = 1;
+    int zero_momentum_period = 1;
+    bool invert_z = false;
+    std::vector<Inter> inter;
+    std::vector<Nhc> nhc;
+    bool finalized = false;
+    long long launches = 0;
+    std::string err_msg;
+    // phase timers (PFMDS_TIMERS=1)
+    bool timers_on = false;
+    double t_phase[6]{0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define RED_BLOCKS 592  // 148 SMs x 4
+#define RED_THREADS 256
+
+// ---- nl.cu ----
+void nl_setup_grid(pfmds_ctx* c);
+void nl_bin_atoms(pfmds_ctx* c, bool reorder);
+void nl_build(pfmds_ctx* c, NList& l);
+void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src);
+
+// ---- forces.cu ----
+void forces_zero(pfmds_ctx* c);
+void forces_interaction(pfmds_ctx* c, int k);
+void normals_interaction(pfmds_ctx* c, int k);
+void energy_interaction(pfmds_ctx* c, int k);  // result in c->energy[k]
+
+// ---- integrate.cu ----
+void integ_check_positions(pfmds_ctx* c);
+void integ_invert_z(pfmds_ctx* c);
+void integ_nhc_half(pfmds_ctx* c, Nhc& t, double dt);
+void integ_kick_drift(pfmds_ctx* c, double dt);
+void integ_kick(pfmds_ctx* c, double dt);
+void integ_quench(pfmds_ctx* c);
+void integ_zero_momentum(pfmds_ctx* c);
+void integ_nhc_energy(pfmds_ctx* c, Nhc& t);
+// out[0]=KE(group) ; group sums for diagnostics: out[0..2]=sum F, [3..5]=sum m x, [6..8]=sum m v, [9]=sum m, [10]=max v^2
+void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out);
+void integ_diagnostics(pfmds_ctx* c, double* d_out);

@@ -1,0 +1,493 @@
+// pfmds_b200 — force and energy kernels for lj, lj1g, ljc, morsec, rjl, tb (sm_100a, FP64).
+//
+// Every kernel is a gather: one thread owns one list-owner atom, walks its ELL row (coalesced int32
+// loads), gathers the partner's 32-byte position record, recomputes the min-image dr and |dr| in
+// registers and accumulates the force on its own atom only — no atomics, deterministic.  The
+// reference does the same sums over cached dr/moddr arrays (INTERACTION_POTENTIALS/*.f90); parity
+// is to 1e-9 relative, the summation order inside a row differs (cell order instead of ascending j).
+//
+// FP64-pipe bound: see DESIGN.md for the per-pair operation counts the roofline uses.
+#include <cstdio>
+#include <string>
+
+#include "ctx.hpp"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
+#define FT 128  // threads per block for the force kernels
+
+struct Vec { double x, y, z; };
+__device__ __forceinline__ double dot(const Vec& a, const Vec& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+__device__ __forceinline__ Vec bond_vec(const double4& pi, const double4& pj, const BoxD& box, double& r2) {
+    Vec d;
+    d.x = min_image(pj.x - pi.x, box.h[0], box.L[0]);
+    d.y = min_image(pj.y - pi.y, box.h[1], box.L[1]);
+    d.z = min_image(pj.z - pi.z, box.h[2], box.L[2]);
+    r2 = d.x * d.x + d.y * d.y + d.z * d.z;
+    return d;
+}
+
+__device__ __forceinline__ void add_force(double4* frc, int i, double fx, double fy, double fz) {
+    double4 f = frc[i];
+    f.x += fx; f.y += fy; f.z += fz;
+    frc[i] = f;
+}
+
+// per-block partial of the per-thread energy; the final sum is done by k_sum_partials in block order
+__device__ __forceinline__ void store_partial(double e, double* part) {
+    double s = block_sum(e);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void k_sum_partials(int n, const double* __restrict__ part, double scale, double* out) {
+    double s = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) *out = s * scale;
+}
+
+// ---- lj : LennardJones.f90:23-69 ----------------------------------------------------------------
+template <bool F, bool E>
+__global__ void __launch_bounds__(FT) k_lj(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJp P, BoxD box,
+                                           double* part) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0, fx = 0, fy = 0, fz = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = pos[i];
+        const double R22 = P.R2 * P.R2, s2 = P.sig * P.sig;
+        for (int p = 0; p < n; ++p) {
+            int j = lv.nlist[(size_t)p * lv.stride + i];
+            double r2;
+            Vec d = bond_vec(pi, pos[j], box, r2);
+            double r = sqrt(r2);
+            if (r < P.R2) {
+                (void)R22;
+                double ir2 = 1.0 / r2;
+                double q = s2 * ir2, V = q * q * q;
+                double f, dfr;
+                fcut_dfcut(r, P.R1, P.R2, f, dfr);
+                if (E) e += 4 * P.eps * V * (V - 1.) * f;
+                if (F) {
+                    double c = 4. * P.eps * (V * (12. * V - 6.) * ir2 * f - V * (V - 1.) * dfr);
+                    fx -= c * d.x; fy -= c * d.y; fz -= c * d.z;
+                }
+            }
+        }
+        if (F) add_force(frc, i, fx, fy, fz);
+    }
+    if (E) store_partial(e, part);
+}
+
+// ---- lj1g : LennardJones_1g.f90:28-117, cut_off_poly.f90 ------------------------------------------
+// The reference visits each pair once (p <= lessnnum) and scatters +-F*dr to both atoms; with a
+// symmetric full list the same sum is a gather over all neighbours.  The switch derivative keeps the
+// reference's missing 1/(R2-R1) factor (cut_off_poly.f90:41).
+template <bool F, bool E>
+__global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJ1Gp P, BoxD box,
+                                             double* part) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0, fx = 0, fy = 0, fz = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = pos[i];
+        const double R22 = P.R2 * P.R2, iw = 1.0 / (P.R2 - P.R1);
+        for (int p = 0; p < n; ++p) {
+            int j = lv.nlist[(size_t)p * lv.stride + i];
+            double r2;
+            Vec d = bond_vec(pi, pos[j], box, r2);
+            if (r2 < R22) {  // beyond R2 the quintic switch and its derivative are exactly 0
+                double invr2 = 1.0 / r2;
+                double U = invr2 * invr2 * invr2;
+                double f = 1.0, dfr = 0.0;
+                if (r2 > P.R1 * P.R1) {
+                    double r = sqrt(r2);
+                    double x = (r - P.R1) * iw, x2 = x * x;
+                    f = 1. + x2 * x * (-10. + 15. * x - 6. * x2);
+                    dfr = r * x2 * (-30. + 60. * x - 30. * x2);
+                }
+                if (E) e += U * (P.c12 * U - P.c6) * f;
+                if (F) {
+                    double c = U * invr2 * ((P.c12t12 * U - P.c6t6) * f - (P.c12 * U - P.c6) * dfr);
+                    fx -= c * d.x; fy -= c * d.y; fz -= c * d.z;
+                }
+            }
+        }
+        if (F) add_force(frc, i, fx, fy, fz);
+    }
+    if (E) store_partial(e, part);
+}
+
+// ---- rjl : RosatoGuillopeLegrand.f90:23-94 --------------------------------------------------------
+// pass 1: band sum  Eb2_i = sum exp(-2q(r/r0-1)) f_c ; stores 1/sqrt(Eb2).  With E: the atom's energy.
+template <bool E>
+__global__ void __launch_bounds__(FT) k_rjl_density(int N, const double4* __restrict__ pos, ListView lv, RJLp P, BoxD box,
+                                                    double* __restrict__ inv_eb, double* part) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = pos[i];
+        const double R22 = P.R2 * P.R2, ir0 = 1.0 / P.r0;
+        double sq = 0, sp = 0;
+        for (int p = 0; p < n; ++p) {
+            int j = lv.nlist[(size_t)p * lv.stride + i];
+            double r2;
+            bond_vec(pi, pos[j], box, r2);
+            if (r2 < R22) {
+                double r = sqrt(r2);
+                double t = r * ir0 - 1.;
+                double f = fcut_only(r, P.R1, P.R2);
+                sq += exp(-2. * P.q * t) * f;
+                if (E) sp += exp(-P.p * t) * f;
+            }
+        }
+        double eb = sqrt(sq);
+        inv_eb[i] = 1.0 / eb;
+        if (E) e = P.A0 * sp - P.xi * eb;
+    }
+    if (E) store_partial(e, part);
+}
+// pass 2: gather with 1/Eb_i + 1/Eb_j
+__global__ void __launch_bounds__(FT) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RJLp P, BoxD box,
+                                                  const double* __restrict__ inv_eb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int n = lv.nnum[i];
+    if (n == 0) return;
+    const double4 pi = pos[i];
+    const double R22 = P.R2 * P.R2, ir0 = 1.0 / P.r0, ie_i = inv_eb[i];
+    const double pr = P.p * ir0, qr = P.q * ir0;
+    double fx = 0, fy = 0, fz = 0;
+    for (int p = 0; p < n; ++p) {
+        int j = lv.nlist[(size_t)p * lv.stride + i];
+        double r2;
+        Vec d = bond_vec(pi, pos[j], box, r2);
+        if (r2 < R22) {
+            double r = sqrt(r2);
+            double t = r * ir0 - 1.;
+            double f, dfr;
+            fcut_dfcut(r, P.R1, P.R2, f, dfr);
+            double ep = exp(-P.p * t), eq = exp(-2. * P.q * t);
+            double c = (2. * P.A0 * (pr * f - dfr * r) * ep - P.xi * (qr * f - dfr / 2. * r) * (ie_i + inv_eb[j]) * eq) / r;
+            fx -= c * d.x; fy -= c * d.y; fz -= c * d.z;
+        }
+    }
+    add_force(frc, i, fx, fy, fz);
+}
+
+// ---- tb : TersoffBrenner.f90:26-150 -------------------------------------------------------------
+__device__ __forceinline__ double tb_G(double c1, const TBp& T) { return 1. + T.c02 / T.d02 - T.c02 / (T.d02 + c1 * c1); }  // c1 = 1+cos
+
+// pass A: bond orders B(p,i) = (1 + a0 sum_{q!=p} f_c(r_q) G(theta_pq))^-delt, 0 for r_p >= R2  (:83-96)
+__global__ void __launch_bounds__(FT) k_tb_bond(int N, const double4* __restrict__ pos, ListView lv, TBp T, BoxD box, double* __restrict__ B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int n = lv.nnum[i];
+    if (n == 0) return;
+    const double4 pi = pos[i];
+    for (int p = 0; p < n; ++p) {
+        double rp2;
+        Vec dp = bond_vec(pi, pos[lv.nlist[(size_t)p * lv.stride + i]], box, rp2);
+        double rp = sqrt(rp2), b = 0.;
+        if (rp < T.R2) {
+            double z = 0.;
+            for (int q = 0; q < n; ++q) {
+                if (q == p) continue;
+                double rq2;
+                Vec dq = bond_vec(pi, pos[lv.nlist[(size_t)q * lv.stride + i]], box, rq2);
+                double rq = sqrt(rq2);
+                if (rq < T.R2) z += fcut_only(rq, T.R1, T.R2) * tb_G(1. + dot(dp, dq) / (rp * rq), T);
+            }
+            b = pow(1. + T.a0 * z, -T.delt);
+        }
+        B[(size_t)p * lv.stride + i] = b;
+    }
+}
+// pass B: forces (:99-146) and/or energy (:53-66).  Bonds and partners beyond R2 contribute exactly
+// zero in the reference (f_cut = df_cut = 0, B = 0) and are skipped.
+template <bool F, bool E>
+__global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, TBp T, BoxD box,
+                                                 const double* __restrict__ B, double* part) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0, fx = 0, fy = 0, fz = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = pos[i];
+        const double ex = 1. / T.delt + 1.;
+        const double s2s = sqrt(2. * T.s), s2is = sqrt(2. / T.s), dpre = T.d / (T.s - 1.);
+        for (int p = 0; p < n; ++p) {
+            int j = lv.nlist[(size_t)p * lv.stride + i];
+            const double4 pj = pos[j];
+            double rp2;
+            Vec dp = bond_vec(pi, pj, box, rp2);
+            double rp = sqrt(rp2);
+            if (!(rp < T.R2)) continue;
+            double Bip = B[(size_t)p * lv.stride + i];
+            // reverse slot: i in j's row
+            int nj = lv.nnum[j], l = 0;
+            for (; l < nj; ++l)
+                if (lv.nlist[(size_t)l * lv.stride + j] == i) break;
+            if (l >= nj) continue;  // cannot happen: same group, same r_cut, symmetric dr2
+            double Bjl = B[(size_t)l * lv.stride + j];
+            double f_c, dfr_p;
+            fcut_dfcut(rp, T.R1, T.R2, f_c, dfr_p);
+            double a = -s2s * T.b * (rp - T.r0);
+            double ea = exp(a), eas = exp(a / T.s);
+            if (E) {
+                if (j > i) e += f_c * dpre * (ea - (Bip + Bjl) / 2 * T.s * eas);
+            }
+            if (F) {
+                Vec dB = {0., 0., 0.};
+                for (int q = 0; q < n; ++q) {  // :112-120 own row
+                    if (q == p) continue;
+                    double rq2;
+                    Vec dq = bond_vec(pi, pos[lv.nlist[(size_t)q * lv.stride + i]], box, rq2);
+                    double rq = sqrt(rq2);
+                    if (!(rq < T.R2)) continue;
+                    double fq, dfq;
+                    fcut_dfcut(rq, T.R1, T.R2, fq, dfq);
+                    double rr = 1. / rp / rq, cosi = dot(dp, dq) * rr, c1 = 1. + cosi, den = T.d02 + c1 * c1;
+                    double g1 = fq * 2. * T.a0 * T.c02 * c1 / (den * den);
+                    double g2 = dfq * T.a0 * tb_G(c1, T);
+                    dB.x += g1 * ((dp.x + dq.x) * rr - cosi * (dp.x / rp2 + dq.x / rq2)) + g2 * dq.x;
+                    dB.y += g1 * ((dp.y + dq.y) * rr - cosi * (dp.y / rp2 + dq.y / rq2)) + g2 * dq.y;
+                    dB.z += g1 * ((dp.z + dq.z) * rr - cosi * (dp.z / rp2 + dq.z / rq2)) + g2 * dq.z;
+                }
+                double bp = pow(Bip, ex);
+                dB.x *= bp; dB.y *= bp; dB.z *= bp;
+                const Vec dl = {-dp.x, -dp.y, -dp.z};  // j -> i
+                double bl = pow(Bjl, ex);
+                double cx = 0, cy = 0, cz = 0;  // cross terms :142-152
+                for (int q = 0; q < nj; ++q) {  // :126-133 and :142-152 share the geometry of j's row
+                    if (q == l) continue;
+                    double rq2;
+                    Vec dq = bond_vec(pj, pos[lv.nlist[(size_t)q * lv.stride + j]], box, rq2);
+                    double rq = sqrt(rq2);
+                    if (!(rq < T.R2)) continue;
+                    double fq = fcut_only(rq, T.R1, T.R2);
+                    double rr = 1. / rp / rq, cosi = dot(dl, dq) * rr, c1 = 1. + cosi, den = T.d02 + c1 * c1;
+                    double gg = 2. * T.a0 * T.c02 * c1 / (den * den);
+                    Vec w = {-dq.x * rr + cosi * dl.x / rp2, -dq.y * rr + cosi * dl.y / rp2, -dq.z * rr + cosi * dl.z / rp2};
+                    double g = bl * fq * gg;
+                    dB.x += g * w.x; dB.y += g * w.y; dB.z += g * w.z;
+                    double pre = T.delt / 2 * pow(B[(size_t)q * lv.stride + j], ex);
+                    double g1 = f_c * gg, g2 = dfr_p * T.a0 * tb_G(c1, T);
+                    double tail = fq * dpre * T.s * exp(-s2s * T.b * (rq - T.r0) / T.s);
+                    cx += pre * (g1 * w.x + dp.x * g2) * tail;
+                    cy += pre * (g1 * w.y + dp.y * g2) * tail;
+                    cz += pre * (g1 * w.z + dp.z * g2) * tail;
+                }
+                double h = -T.delt / 2.;
+                dB.x *= h; dB.y *= h; dB.z *= h;
+                double dff = dfr_p / f_c;
+                double k1 = (dff - s2s * T.b / rp) * ea;       // multiplies dp
+                double k2 = (Bip + Bjl) / 2 * (dff - s2is * T.b / rp);
+                double A = f_c * dpre, se = T.s * eas;
+                fx += A * (dp.x * k1 - (dB.x + k2 * dp.x) * se) + cx;
+                fy += A * (dp.y * k1 - (dB.y + k2 * dp.y) * se) + cy;
+                fz += A * (dp.z * k1 - (dB.z + k2 * dp.z) * se) + cz;
+            }
+        }
+        if (F) add_force(frc, i, fx, fy, fz);
+    }
+    if (E) store_partial(e, part);
+}
+
+// ---- graphene normals : graphenenorm.f90:38-56 ----------------------------------------------------
+__global__ void k_normals(int N, const double4* __restrict__ pos, ListView nn, BoxD box, int simplified, double4* __restrict__ gnorm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (nn.nnum[i] != 3) return;
+    if (simplified) { gnorm[i] = make_double4(0., 0., 1., 0.); return; }  // LennardJonesCosine.f90:62
+    const double4 pi = pos[i];
+    double r2;
+    Vec d1 = bond_vec(pi, pos[nn.nlist[i]], box, r2);
+    Vec d2 = bond_vec(pi, pos[nn.nlist[nn.stride + i]], box, r2);
+    Vec d3 = bond_vec(pi, pos[nn.nlist[2 * nn.stride + i]], box, r2);
+    Vec a = {d2.x - d1.x, d2.y - d1.y, d2.z - d1.z}, b = {d1.x - d3.x, d1.y - d3.y, d1.z - d3.z};
+    Vec n = {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+    if (n.z < 0.) { n.x = -n.x; n.y = -n.y; n.z = -n.z; }
+    double len = sqrt(dot(n, n));
+    gnorm[i] = make_double4(n.x / len, n.y / len, n.z / len, 0.);
+}
+
+// ---- ljc / morsec : LennardJonesCosine.f90, MorseCosine.f90 ---------------------------------------
+struct CosP { double pe, sig, a, r0, delt, R1, R2; };  // pe = 4 eps (ljc) or d (morsec)
+template <bool MORSE>
+__device__ __forceinline__ double cos_V2(double r, double r2, const CosP& P) {
+    if (MORSE) return exp(-P.a * (r - P.r0));
+    double q = P.sig * P.sig / r2;
+    return q * q * q;
+}
+// Direct term for the atoms of one side.  GRAPHENE: owner i is a carbon atom with its own normal and
+// the kernel also accumulates T_i = sum_p V2 V3 f_c /(n_i.dr) dr for the normal-derivative term.
+// Otherwise the owner is a metal atom and the normal is that of the carbon partner (:112-139).
+template <bool MORSE, bool GRAPHENE, bool F, bool E>
+__global__ void __launch_bounds__(FT) k_cos_direct(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CosP P, BoxD box,
+                                                   const double4* __restrict__ gnorm, double4* __restrict__ tvec, double* part) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0, fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = pos[i];
+        double4 nv = GRAPHENE ? gnorm[i] : make_double4(0, 0, 0, 0);
+        for (int p = 0; p < n; ++p) {
+            int j = lv.nlist[(size_t)p * lv.stride + i];
+            double r2;
+            Vec d = bond_vec(pi, pos[j], box, r2);
+            double r = sqrt(r2);
+            if (r < P.R2) {
+                if (!GRAPHENE) nv = gnorm[j];
+                double nd = nv.x * d.x + nv.y * d.y + nv.z * d.z;
+                double V2 = cos_V2<MORSE>(r, r2, P), V1 = V2 * V2;
+                double cosn = fabs(nd) / r;
+                if (MORSE && !GRAPHENE) cosn = fabs(nd) / (sqrt(nv.x * nv.x + nv.y * nv.y + nv.z * nv.z) * r);  // MorseCosine.f90:127
+                double V3 = pow(cosn, P.delt);
+                double f, dfr;
+                fcut_dfcut(r, P.R1, P.R2, f, dfr);
+                if (E) e += MORSE ? P.pe * (V1 - 2. * V2 * V3) * f : P.pe * (V1 - V2 * V3) * f;
+                if (F) {
+                    double cr, cn;
+                    if (MORSE) {
+                        cr = 2. * (P.a * V1 - (P.a + P.delt / r) * V2 * V3) / r * f - (V1 - 2. * V2 * V3) * dfr;
+                        cn = 2. * P.delt * V2 * V3 / nd * f;
+                    } else {
+                        cr = (12. * V1 - (6. + P.delt) * V2 * V3) / r2 * f - (V1 - V2 * V3) * dfr;
+                        cn = P.delt * V2 * V3 / nd * f;
+                    }
+                    fx -= P.pe * (cr * d.x + cn * nv.x);
+                    fy -= P.pe * (cr * d.y + cn * nv.y);
+                    fz -= P.pe * (cr * d.z + cn * nv.z);
+                    if (GRAPHENE) {
+                        double w = V2 * V3 * f / nd;
+                        tx += w * d.x; ty += w * d.y; tz += w * d.z;
+                    }
+                }
+            }
+        }
+        if (F) {
+            add_force(frc, i, fx, fy, fz);
+            if (GRAPHENE) tvec[i] = make_double4(tx, ty, tz, 0.);
+        }
+    } else if (F && GRAPHENE && i < N) {
+        tvec[i] = make_double4(0., 0., 0., 0.);
+    }
+    if (E) store_partial(e, part);
+}
+// Normal-derivative term (LennardJonesCosine.f90:81-106): for each of the three nearest carbons j of
+// i, with i in slot l1 of j's row and l2,l3 the cyclic successors,
+//   F_i -= pref*delt * n_j * (T_j . (d12 (d23.d31) - d31 (d23.d12))) / (|d12|^2|d31|^2 - (d12.d31)^2)
+// where the reference's inner sum over j's metal neighbours has been collected into T_j.
+__global__ void __launch_bounds__(FT) k_cos_indirect(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView nn, double pref_delt,
+                                                     BoxD box, const double4* __restrict__ gnorm, const double4* __restrict__ tvec) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (nn.nnum[i] != 3) return;
+    double fx = 0, fy = 0, fz = 0;
+    for (int q = 0; q < 3; ++q) {
+        int j = nn.nlist[(size_t)q * nn.stride + i];
+        int a0 = nn.nlist[j], a1 = nn.nlist[nn.stride + j], a2 = nn.nlist[2 * nn.stride + j];
+        int l1 = a0 == i ? 0 : (a1 == i ? 1 : (a2 == i ? 2 : 3));
+        if (l1 > 2) continue;  // reference stops with 'l1>3'; the nearest-3 relation is symmetric
+        int k1 = l1 == 0 ? a0 : (l1 == 1 ? a1 : a2), k2 = l1 == 0 ? a1 : (l1 == 1 ? a2 : a0), k3 = l1 == 0 ? a2 : (l1 == 1 ? a0 : a1);
+        const double4 pj = pos[j];
+        double r2;
+        Vec e1 = bond_vec(pj, pos[k1], box, r2), e2 = bond_vec(pj, pos[k2], box, r2), e3 = bond_vec(pj, pos[k3], box, r2);
+        Vec d12 = {e2.x - e1.x, e2.y - e1.y, e2.z - e1.z}, d31 = {e1.x - e3.x, e1.y - e3.y, e1.z - e3.z}, d23 = {e3.x - e2.x, e3.y - e2.y, e3.z - e2.z};
+        double s2331 = dot(d23, d31), s2312 = dot(d23, d12);
+        Vec w = {d12.x * s2331 - d31.x * s2312, d12.y * s2331 - d31.y * s2312, d12.z * s2331 - d31.z * s2312};
+        double d1231 = dot(d12, d31);
+        double den = dot(d12, d12) * dot(d31, d31) - d1231 * d1231;
+        double4 t = tvec[j], nj = gnorm[j];
+        double c = pref_delt * (t.x * w.x + t.y * w.y + t.z * w.z) / den;
+        fx -= c * nj.x; fy -= c * nj.y; fz -= c * nj.z;
+    }
+    add_force(frc, i, fx, fy, fz);
+}
+
+// ------------------------------------------------------------------------------------------------
+void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
+    CK(cudaMemsetAsync(c->frc, 0, sizeof(double4) * (size_t)c->N, c->st));
+}
+
+static CosP cosp_of(const Inter& it) {
+    CosP P{};
+    if (it.kind == K_LJC) { P.pe = 4. * it.ljc.eps; P.sig = it.ljc.sig; P.delt = it.ljc.delt; P.R1 = it.ljc.R1; P.R2 = it.ljc.R2; }
+    else { P.pe = it.mor.d; P.a = it.mor.a; P.r0 = it.mor.r; P.delt = it.mor.delt; P.R1 = it.mor.R1; P.R2 = it.mor.R2; }
+    return P;
+}
+
+void normals_interaction(pfmds_ctx* c, int k) {  // update_norm_in_graphene, md_interactions.f90:195-208
+    Inter& it = c->inter[k];
+    if (it.kind != K_LJC && it.kind != K_MORSEC) return;
+    const int N = c->N, nb = (N + FT - 1) / FT;
+    int simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
+    k_normals<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[2].view(c->stride), c->box, simp, it.gnorm);
+    c->launches += 1;
+}
+
+void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interactions.f90:210-242
+    Inter& it = c->inter[k];
+    const int N = c->N, nb = (N + FT - 1) / FT;
+    const size_t st = c->stride;
+    switch (it.kind) {
+    case K_LJ:
+        k_lj<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr);
+        k_lj<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr);
+        c->launches += 2;
+        break;
+    case K_LJ1G:
+        k_lj1g<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr);
+        c->launches += 1;
+        break;
+    case K_RJL:
+        k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.rjl, c->box, it.aux, nullptr);
+        k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.rjl, c->box, it.aux);
+        c->launches += 2;
+        break;
+    case K_TB:
+        k_tb_bond<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux);
+        k_tb_force<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.tb, c->box, it.aux, nullptr);
+        c->launches += 2;
+        break;
+    case K_LJC:
+    case K_MORSEC: {
+        CosP P = cosp_of(it);
+        bool simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
+        if (it.kind == K_LJC) {
+            k_cos_direct<false, true, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr);
+            if (!simp) k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec);
+            k_cos_direct<false, false, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr);
+        } else {
+            k_cos_direct<true, true, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr);
+            if (!simp) k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec);
+            k_cos_direct<true, false, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr);
+        }
+        c->launches += simp ? 2 : 3;
+        break;
+    }
+    }
+    CK(cudaGetLastError());
+}
+
+void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90:244-261: always on nl(1)
+    Inter& it = c->inter[k];
+    const int N = c->N, nb = (N + FT - 1) / FT;
+    const size_t st = c->stride;
+    double scale = 1.0;
+    switch (it.kind) {
+    case K_LJ: k_lj<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
+    case K_LJ1G: k_lj1g<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
+    case K_RJL: k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.rjl, c->box, it.aux, c->part); break;
+    case K_TB:
+        k_tb_bond<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux);
+        k_tb_force<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.tb, c->box, it.aux, c->part);
+        c->launches += 1;
+        break;
+    case K_LJC: k_cos_direct<false, true, false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
+    case K_MORSEC: k_cos_direct<true, true, false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
+    }
+    k_sum_partials<<<1, 1024, 0, c->st>>>(nb, c->part, scale, c->energy + k);
+    c->launches += 2;
+    CK(cudaGetLastError());
+}

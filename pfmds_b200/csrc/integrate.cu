@@ -1,0 +1,273 @@
+// pfmds_b200 — velocity-Verlet kicks/drifts, Nose-Hoover chain, statics quench, group reductions.
+// Replaces code_source/MOLECULAR_DYNAMICS/md_integrators.f90 (all) and the reductions / checks of
+// md_general.f90:96-112,161-311,342-398.  Group membership is a per-atom bit mask, so one pass over
+// the slot-ordered arrays serves any settings-file group.  All reductions are two-stage with a
+// fixed grid and a fixed summation order: results are run-to-run reproducible (the reference's
+// OpenMP partial sums are not).
+#include <cstdio>
+#include <string>
+
+#include "ctx.hpp"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
+#define IT 256
+
+// md_general.f90:342-364 — every atom, tolerance 1e-7, negated condition so NaN is caught too
+__device__ __forceinline__ bool outside(double x, double L) { return !(x > (0. - 0.0000001) && x < (L + 0.0000001)); }
+
+__global__ void k_check_positions(int N, const double4* __restrict__ pos, const int* __restrict__ orig, BoxD box, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double4 p = pos[i];
+    if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
+}
+void integ_check_positions(pfmds_ctx* c) {
+    k_check_positions<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->orig, c->box, c->err);
+    c->launches += 1;
+}
+
+// md_general.f90:382-398
+__global__ void k_invert_z(int N, const double4* __restrict__ pos, double4* __restrict__ vel, double zl, double zh) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double z = pos[i].z, vz = vel[i].z;
+    if ((z > zl && z < (zl + zh) / 2 && vz > 0.) || (z < zh && z > (zl + zh) / 2 && vz < 0.)) vel[i].z = -vz;
+}
+void integ_invert_z(pfmds_ctx* c) {
+    k_invert_z<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, 0.8 * c->box.L[2], 0.9 * c->box.L[2]);
+    c->launches += 1;
+}
+
+// ---- kinetic energy of a group: md_general.f90:161-182 ---------------------------------------------
+__global__ void __launch_bounds__(IT) k_ke_partial(int N, const double4* __restrict__ vel, const uint32_t* __restrict__ gmask, uint32_t bit,
+                                                   double* __restrict__ part) {
+    double s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        if (gmask[i] & bit) {
+            double4 v = vel[i];
+            s += v.w * (v.x * v.x + v.y * v.y + v.z * v.z) / 2 * PFMDS_MASS_COEF;
+        }
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void k_sum_to(int n, const double* __restrict__ part, double* out) {
+    double s = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) *out = s;
+}
+void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out) {
+    k_ke_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->gmask, 1u << (group - 1), c->part);
+    k_sum_to<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, d_out);
+    c->launches += 2;
+}
+
+// ---- Nose-Hoover chain half step: md_integrators.f90:200-245 ---------------------------------------
+// state = x[M], v[M], q[M], s.  One block sums the KE partials (fixed order), thread 0 runs the chain.
+__global__ void k_nhc(int nparts, const double* __restrict__ part, double* state, int M, int L, double temperature, double ts2, double ts3,
+                      double ts4) {
+    double ke = 0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i];
+    ke = block_sum(ke);
+    if (threadIdx.x != 0) return;
+    double* x = state;
+    double* v = state + M;
+    const double* q = state + 2 * M;
+    double kt = PFMDS_KB * temperature;
+    double kedif = 2. * ke - 3. * L * kt, b = 0.;
+    if (M == 1) {
+        v[0] = v[0] + kedif / q[0] * ts3;
+    } else {
+        v[M - 1] = v[M - 1] + (q[M - 2] * v[M - 2] * v[M - 2] - kt) / q[M - 1] * ts3;
+        for (int i = M - 2; i >= 1; --i) {
+            b = exp(-v[i + 1] * ts4);
+            v[i] = v[i] * (b * b) + (q[i - 1] * v[i - 1] * v[i - 1] - kt) / q[i] * ts3 * b;
+        }
+        b = exp(-v[1] * ts4);
+        v[0] = v[0] * (b * b) + kedif / q[0] * ts3 * b;
+    }
+    double s = exp(-v[0] * ts2);
+    state[3 * M] = s;
+    kedif = 2. * ke * (s * s) - 3. * L * kt;
+    for (int i = 0; i < M; ++i) x[i] = x[i] + v[i] * ts2;
+    if (M == 1) {
+        v[0] = v[0] + kedif / q[0] * ts3;
+    } else {
+        v[0] = v[0] * (b * b) + kedif / q[0] * ts3 * b;  // the reference reuses the last b here (:236)
+        for (int i = 1; i <= M - 2; ++i) {
+            b = exp(-v[i + 1] * ts4);
+            v[i] = v[i] * (b * b) + (q[i - 1] * v[i - 1] * v[i - 1] - kt) / q[i] * ts3 * b;
+        }
+        v[M - 1] = v[M - 1] + (q[M - 2] * v[M - 2] * v[M - 2] - kt) / q[M - 1] * ts3;
+    }
+}
+// scale_velocities, md_general.f90:96-112
+__global__ void k_scale(int N, double4* __restrict__ vel, const uint32_t* __restrict__ gmask, uint32_t bit, const double* __restrict__ s_ptr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (gmask[i] & bit) {
+        double s = *s_ptr;
+        double4 v = vel[i];
+        v.x *= s; v.y *= s; v.z *= s;
+        vel[i] = v;
+    }
+}
+void integ_nhc_half(pfmds_ctx* c, Nhc& t, double dt) {
+    uint32_t bit = 1u << (t.group - 1);
+    k_ke_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->gmask, bit, c->part);
+    k_nhc<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, t.state, t.M, t.L, t.temperature, dt / 2, dt / 4, dt / 8);
+    k_scale<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, bit, t.state + 3 * t.M);
+    c->launches += 3;
+}
+
+// ---- velocity Verlet: md_integrators.f90:7-97 ------------------------------------------------------
+// First half of a step: half-kick then drift + one wrap.  xyz group: all components; z group: z only.
+// The position test of check_positions is applied to the positions the step starts from.
+__global__ void __launch_bounds__(IT) k_kick_drift(int N, double4* __restrict__ pos, double4* __restrict__ vel, const double4* __restrict__ frc,
+                                                   const uint32_t* __restrict__ gmask, const int* __restrict__ orig, uint32_t bxyz, uint32_t bz,
+                                                   double ts1, double ts2, BoxD box, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t g = gmask[i];
+    bool mx = g & bxyz, mz = g & bz;
+    if (!mx && !mz) return;
+    double4 p = pos[i], v = vel[i], f = frc[i];
+    if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
+    if (mx) {
+        v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
+        v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
+        v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+    }
+    if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+    if (mx) {
+        p.x = p.x + v.x * ts1; if (p.x > box.L[0]) p.x = p.x - box.L[0]; else if (p.x < 0.) p.x = p.x + box.L[0];
+        p.y = p.y + v.y * ts1; if (p.y > box.L[1]) p.y = p.y - box.L[1]; else if (p.y < 0.) p.y = p.y + box.L[1];
+        p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2];
+    }
+    if (mz) { p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2]; }
+    pos[i] = p;
+    vel[i] = v;
+}
+void integ_kick_drift(pfmds_ctx* c, double dt) {
+    k_kick_drift<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
+                                                         1u << (c->z_moving - 1), dt, dt / 2, c->box, c->err);
+    c->launches += 1;
+}
+__global__ void __launch_bounds__(IT) k_kick(int N, double4* __restrict__ vel, const double4* __restrict__ frc, const uint32_t* __restrict__ gmask,
+                                             uint32_t bxyz, uint32_t bz, double ts2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t g = gmask[i];
+    bool mx = g & bxyz, mz = g & bz;
+    if (!mx && !mz) return;
+    double4 v = vel[i], f = frc[i];
+    if (mx) {
+        v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
+        v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
+        v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+    }
+    if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+    vel[i] = v;
+}
+void integ_kick(pfmds_ctx* c, double dt) {
+    k_kick<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2);
+    c->launches += 1;
+}
+
+// ---- molecular statics quench: md_integrators.f90:99-145 -------------------------------------------
+__global__ void k_quench(int N, double4* __restrict__ vel, const double4* __restrict__ frc, const uint32_t* __restrict__ gmask, uint32_t bxyz,
+                         uint32_t bz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t g = gmask[i];
+    bool mx = g & bxyz, mz = g & bz;
+    if (!mx && !mz) return;
+    double4 v = vel[i], f = frc[i];
+    if (mx) {
+        double fv = f.x * v.x + f.y * v.y + f.z * v.z, ff = f.x * f.x + f.y * f.y + f.z * f.z;
+        if (fv > 0. && ff > 1.0e-12) { v.x = fv / ff * f.x; v.y = fv / ff * f.y; v.z = fv / ff * f.z; }
+        else { v.x = 0.; v.y = 0.; v.z = 0.; }
+    }
+    if (mz) {
+        double fv = f.x * v.x + f.y * v.y + f.z * v.z;
+        if (!(fv > 0.)) { v.x = 0.; v.y = 0.; v.z = 0.; }
+    }
+    vel[i] = v;
+}
+void integ_quench(pfmds_ctx* c) {
+    k_quench<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1));
+    c->launches += 1;
+}
+
+// ---- group sums: momentum removal and the stdout diagnostics ---------------------------------------
+// part layout per block: [0..2] sum F, [3..5] sum m x, [6..8] sum m v, [9] sum m, [10] max |v|^2 (all atoms)
+__global__ void __launch_bounds__(IT) k_sums_partial(int N, const double4* __restrict__ pos, const double4* __restrict__ vel,
+                                                     const double4* __restrict__ frc, const uint32_t* __restrict__ gmask, uint32_t bit,
+                                                     double* __restrict__ part) {
+    double a[11];
+    for (int k = 0; k < 11; ++k) a[k] = 0.;
+    a[10] = -1.;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        double4 v = vel[i];
+        double v2 = v.x * v.x + v.y * v.y + v.z * v.z;
+        if (a[10] < v2) a[10] = v2;
+        if (gmask[i] & bit) {
+            double4 p = pos[i], f = frc[i];
+            a[0] += f.x; a[1] += f.y; a[2] += f.z;
+            a[3] += v.w * p.x; a[4] += v.w * p.y; a[5] += v.w * p.z;
+            a[6] += v.w * v.x; a[7] += v.w * v.y; a[8] += v.w * v.z;
+            a[9] += v.w;
+        }
+    }
+    for (int k = 0; k < 10; ++k) {
+        double s = block_sum(a[k]);
+        if (threadIdx.x == 0) part[blockIdx.x * 16 + k] = s;
+    }
+    // block max
+    __shared__ double mx[IT / 32];
+    double m = a[10];
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) mx[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < IT / 32; ++w) m = fmax(m, mx[w]);
+        part[blockIdx.x * 16 + 10] = m;
+    }
+}
+__global__ void k_sums_final(int nb, const double* __restrict__ part, double* out) {
+    for (int k = 0; k < 10; ++k) {
+        double s = 0;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) s += part[i * 16 + k];
+        s = block_sum(s);
+        if (threadIdx.x == 0) out[k] = s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double m = -1.;
+        for (int i = 0; i < nb; ++i) m = fmax(m, part[i * 16 + 10]);
+        out[10] = m;
+    }
+}
+void integ_diagnostics(pfmds_ctx* c, double* d_out) {
+    k_sums_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, 1u << (c->all_atoms - 1), c->part);
+    k_sums_final<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, d_out);
+    c->launches += 2;
+}
+// zero_momentum, md_general.f90:236-253
+__global__ void k_sub_mcv(int N, double4* __restrict__ vel, const uint32_t* __restrict__ gmask, uint32_t bit, const double* __restrict__ sums) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (gmask[i] & bit) {
+        double totm = sums[9];
+        double4 v = vel[i];
+        v.x = v.x - sums[6] / totm; v.y = v.y - sums[7] / totm; v.z = v.z - sums[8] / totm;
+        vel[i] = v;
+    }
+}
+void integ_zero_momentum(pfmds_ctx* c) {
+    integ_diagnostics(c, c->red + 16);
+    k_sub_mcv<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, 1u << (c->all_atoms - 1), c->red + 16);
+    c->launches += 1;
+}

@@ -1,0 +1,279 @@
+// pfmds_b200 — cell-binned Verlet neighbour-list build (replaces the reference's O(N1*N2) search,
+// code_source/MOLECULAR_DYNAMICS/md_neighbours.f90:56-100, its per-step distance refresh :104-124 and
+// the serial converse list :128-160).
+//
+// Membership rule reproduced bit-for-bit: global i != j and dx*dx+dy*dy+dz*dz < r_cut*r_cut with the
+// products and sums rounded separately (no FMA contraction) on the min-image dr of find_distance
+// (md_general.f90:423-441).  Lists are rebuilt only when mod(md_step,update_period)==0, exactly like
+// update_neighbour_list (:32-52); between rebuilds membership is frozen and distances are recomputed
+// in registers by the force kernels, so no "distance" or "converse" pass exists here.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "ctx.hpp"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+void nl_setup_grid(pfmds_ctx* c) {
+    double rc = 0;
+    for (auto& it : c->inter)
+        for (int j = 0; j < it.nl_n; ++j) rc = std::max(rc, it.nl[j].rcut);
+    if (rc <= 0) rc = 1.0;
+    // Positions may sit up to 1e-7 outside [0,L] (check_positions tolerance, md_general.f90:346) and are
+    // clamped into the edge cells, so the cells are made a little wider than r_cut.
+    c->cell_rc = rc * (1.0 + 1e-9) + 1e-5;
+    long long total = 1;
+    for (int k = 0; k < 3; ++k) {
+        int n = (int)std::floor(c->box.L[k] / c->cell_rc);
+        if (n < 1) n = 1;
+        if (n > 1024) n = 1024;
+        c->ncell[k] = n;
+        total *= n;
+    }
+    // keep the cell table bounded for sparse, huge boxes
+    while (total > 64ll * 1024 * 1024) {
+        int k = (c->ncell[0] >= c->ncell[1] && c->ncell[0] >= c->ncell[2]) ? 0 : (c->ncell[1] >= c->ncell[2] ? 1 : 2);
+        total /= c->ncell[k];
+        c->ncell[k] = (c->ncell[k] + 1) / 2;
+        total *= c->ncell[k];
+    }
+    c->ncells = (int)total;
+    if (c->cell_cnt) { cudaFree(c->cell_cnt); cudaFree(c->cell_start); cudaFree(c->scan_tmp); }
+    CK(cudaMalloc(&c->cell_cnt, sizeof(int) * (size_t)(c->ncells + 1)));
+    CK(cudaMalloc(&c->cell_start, sizeof(int) * (size_t)(c->ncells + 1)));
+    CK(cudaMalloc(&c->scan_tmp, sizeof(int) * (size_t)(c->ncells / 2048 + 2)));
+}
+
+struct GridD { int n[3]; double inv[3]; };
+
+__device__ __forceinline__ int cell_coord(double x, double inv, int n) {
+    int c = (int)floor(x * inv);
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+__global__ void k_cell_count(int N, const double4* __restrict__ pos, GridD g, int* __restrict__ cid, int* __restrict__ cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double4 p = pos[i];
+    int cx = cell_coord(p.x, g.inv[0], g.n[0]), cy = cell_coord(p.y, g.inv[1], g.n[1]), cz = cell_coord(p.z, g.inv[2], g.n[2]);
+    int c = (cz * g.n[1] + cy) * g.n[0] + cx;
+    cid[i] = c;
+    atomicAdd(&cnt[c], 1);
+}
+
+// exclusive scan, 2048 items per block (1024 threads x 2), block totals to `sums`
+__global__ void k_scan_block(int n, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ sums) {
+    __shared__ int sh[32];
+    int base = blockIdx.x * 2048 + threadIdx.x * 2;
+    int a = base < n ? in[base] : 0, b = base + 1 < n ? in[base + 1] : 0;
+    int v = a + b, incl = v;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) sh[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = sh[lane], si = s;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+        sh[lane] = si - s;
+        if (lane == 31) sums[blockIdx.x] = si;
+    }
+    __syncthreads();
+    int excl = incl - v + sh[w];
+    if (base < n) out[base] = excl;
+    if (base + 1 < n) out[base + 1] = excl + a;
+}
+__global__ void k_scan_sums(int nb, int* sums) {  // single block, serial over chunks of 1024
+    __shared__ int carry;
+    __shared__ int sh[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < nb ? sums[i] : 0, incl = v;
+        int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) sh[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int s = sh[lane], si = s;
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+            sh[lane] = si - s;
+        }
+        __syncthreads();
+        int excl = incl - v + sh[w] + carry;
+        if (i < nb) sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void k_scan_add(int n, int* out, const int* __restrict__ sums, int total_slot, int total) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += sums[i / 2048];
+    if (i == 0) out[total_slot] = total;
+}
+
+__global__ void k_cell_scatter(int N, const int* __restrict__ cid, const int* __restrict__ start, int* __restrict__ cursor, int* __restrict__ atoms) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int c = cid[i];
+    atoms[start[c] + atomicAdd(&cursor[c], 1)] = i;
+}
+// deterministic order inside each cell: ascending slot index (insertion sort, cells hold tens of atoms)
+__global__ void k_cell_sort(int ncells, const int* __restrict__ start, int* __restrict__ atoms) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    int b = start[c], e = start[c + 1];
+    for (int i = b + 1; i < e; ++i) {
+        int v = atoms[i], k = i - 1;
+        while (k >= b && atoms[k] > v) { atoms[k + 1] = atoms[k]; --k; }
+        atoms[k + 1] = v;
+    }
+}
+__global__ void k_permute(int N, const int* __restrict__ order, const double4* __restrict__ pos, const double4* __restrict__ vel,
+                          const uint32_t* __restrict__ gm, const int* __restrict__ orig, double4* __restrict__ pos2, double4* __restrict__ vel2,
+                          uint32_t* __restrict__ gm2, int* __restrict__ orig2) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    int s = order[k];
+    pos2[k] = pos[s];
+    vel2[k] = vel[s];
+    gm2[k] = gm[s];
+    orig2[k] = orig[s];
+}
+__global__ void k_iota(int N, int* a) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N) a[k] = k;
+}
+
+// Bin every atom into the cell grid; with `reorder` the state arrays are physically permuted into
+// cell order (only legal when every neighbour list is rebuilt in the same step, since lists hold
+// slot indices).
+void nl_bin_atoms(pfmds_ctx* c, bool reorder) {
+    const int N = c->N, T = 256, nb = (N + T - 1) / T;
+    GridD g;
+    for (int k = 0; k < 3; ++k) { g.n[k] = c->ncell[k]; g.inv[k] = c->ncell[k] / c->box.L[k]; }
+    CK(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)(c->ncells + 1), c->st));
+    k_cell_count<<<nb, T, 0, c->st>>>(N, c->pos, g, c->cid, c->cell_cnt);
+    int sb = (c->ncells + 2047) / 2048;
+    k_scan_block<<<sb, 1024, 0, c->st>>>(c->ncells, c->cell_cnt, c->cell_start, c->scan_tmp);
+    k_scan_sums<<<1, 1024, 0, c->st>>>(sb, c->scan_tmp);
+    k_scan_add<<<(c->ncells + T - 1) / T, T, 0, c->st>>>(c->ncells, c->cell_start, c->scan_tmp, c->ncells, N);
+    CK(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)(c->ncells + 1), c->st));
+    k_cell_scatter<<<nb, T, 0, c->st>>>(N, c->cid, c->cell_start, c->cell_cnt, c->cell_atoms);
+    k_cell_sort<<<(c->ncells + T - 1) / T, T, 0, c->st>>>(c->ncells, c->cell_start, c->cell_atoms);
+    c->launches += 6;
+    if (reorder) {
+        k_permute<<<nb, T, 0, c->st>>>(N, c->cell_atoms, c->pos, c->vel, c->gmask, c->orig, c->pos2, c->vel2, c->gmask2, c->orig2);
+        std::swap(c->pos, c->pos2);
+        std::swap(c->vel, c->vel2);
+        std::swap(c->gmask, c->gmask2);
+        std::swap(c->orig, c->orig2);
+        k_iota<<<nb, T, 0, c->st>>>(N, c->cell_atoms);
+        c->identity_order = true;
+        c->launches += 2;
+    } else {
+        c->identity_order = false;
+    }
+    CK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// One thread per list-owner atom walks the 27 (or fewer, for boxes under three cells wide) cells
+// around it.  dr2 uses __dmul_rn/__dadd_rn so the compiler cannot contract it into FMAs: the set
+// {j : dr2 < rc2} is then bit-identical to the reference's brute-force scan.
+template <bool IDENT>
+__global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict__ pos, const uint32_t* __restrict__ gmask,
+                                               const int* __restrict__ orig, const int* __restrict__ cid, const int* __restrict__ cstart,
+                                               const int* __restrict__ catoms, GridD g, BoxD box, uint32_t bit1, uint32_t bit2, double rc2,
+                                               int maxn, size_t stride, int* __restrict__ nlist, int* __restrict__ nnum, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (!(gmask[i] & bit1)) { nnum[i] = 0; return; }
+    const double4 pi = pos[i];
+    // same binning expression as k_cell_count (cid[] is stale after a physical re-sort)
+    const int cx = cell_coord(pi.x, g.inv[0], g.n[0]), cy = cell_coord(pi.y, g.inv[1], g.n[1]), cz = cell_coord(pi.z, g.inv[2], g.n[2]);
+    const int lo0 = g.n[0] >= 3 ? -1 : 0, hi0 = g.n[0] >= 2 ? 1 : 0;
+    const int lo1 = g.n[1] >= 3 ? -1 : 0, hi1 = g.n[1] >= 2 ? 1 : 0;
+    const int lo2 = g.n[2] >= 3 ? -1 : 0, hi2 = g.n[2] >= 2 ? 1 : 0;
+    int cnt = 0;
+    for (int oz = lo2; oz <= hi2; ++oz) {
+        int z = cz + oz; z = z < 0 ? z + g.n[2] : (z >= g.n[2] ? z - g.n[2] : z);
+        for (int oy = lo1; oy <= hi1; ++oy) {
+            int y = cy + oy; y = y < 0 ? y + g.n[1] : (y >= g.n[1] ? y - g.n[1] : y);
+            for (int ox = lo0; ox <= hi0; ++ox) {
+                int x = cx + ox; x = x < 0 ? x + g.n[0] : (x >= g.n[0] ? x - g.n[0] : x);
+                int cc = (z * g.n[1] + y) * g.n[0] + x;
+                int b = cstart[cc], e = cstart[cc + 1];
+                for (int s = b; s < e; ++s) {
+                    int j = IDENT ? s : catoms[s];
+                    if (j == i) continue;
+                    if (!(gmask[j] & bit2)) continue;
+                    double4 pj = pos[j];
+                    double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]);
+                    double dy = min_image(pj.y - pi.y, box.h[1], box.L[1]);
+                    double dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
+                    double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    if (dr2 < rc2) {
+                        if (cnt < maxn) nlist[(size_t)cnt * stride + i] = j;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    }
+    if (cnt > maxn) { raise_error(err, E_TOO_MANY, orig[i], cnt); cnt = maxn; }  // md_neighbours.f90:80
+    nnum[i] = cnt;
+}
+
+void nl_build(pfmds_ctx* c, NList& l) {
+    const int N = c->N, T = 128, nb = (N + T - 1) / T;
+    GridD g;
+    for (int k = 0; k < 3; ++k) { g.n[k] = c->ncell[k]; g.inv[k] = c->ncell[k] / c->box.L[k]; }
+    uint32_t b1 = 1u << (l.g1 - 1), b2 = 1u << (l.g2 - 1);
+    double rc2 = l.rcut * l.rcut;
+    if (c->identity_order)
+        k_build<true><<<nb, T, 0, c->st>>>(N, c->pos, c->gmask, c->orig, c->cid, c->cell_start, c->cell_atoms, g, c->box, b1, b2, rc2, l.maxn,
+                                           c->stride, l.nlist, l.nnum, c->err);
+    else
+        k_build<false><<<nb, T, 0, c->st>>>(N, c->pos, c->gmask, c->orig, c->cid, c->cell_start, c->cell_atoms, g, c->box, b1, b2, rc2, l.maxn,
+                                            c->stride, l.nlist, l.nnum, c->err);
+    c->launches += 1;
+    l.built = true;
+    CK(cudaGetLastError());
+}
+
+// graphenenorm.f90:8-36: the entries of the carbon (tb) list closer than r_cut_nn; exactly three.
+__global__ void k_nearest3(int N, const double4* __restrict__ pos, const int* __restrict__ orig, ListView src, BoxD box, double rc_nn,
+                           size_t stride, int* __restrict__ nn, int* __restrict__ nnnum, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int n = src.nnum[i];
+    if (n == 0) { nnnum[i] = 0; return; }
+    const double4 pi = pos[i];
+    int k = 0;
+    for (int p = 0; p < n; ++p) {
+        int j = src.nlist[(size_t)p * src.stride + i];
+        double4 pj = pos[j];
+        double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]);
+        double dy = min_image(pj.y - pi.y, box.h[1], box.L[1]);
+        double dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
+        double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (sqrt(dr2) < rc_nn) {
+            if (k < 3) nn[(size_t)k * stride + i] = j;
+            ++k;
+        }
+    }
+    if (k != 3) raise_error(err, E_GR_NEIB, orig[i], k);
+    nnnum[i] = k < 3 ? k : 3;
+}
+
+void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
+    const int N = c->N, T = 128, nb = (N + T - 1) / T;
+    k_nearest3<<<nb, T, 0, c->st>>>(N, c->pos, c->orig, src.view(c->stride), c->box, nn.rcut, c->stride, nn.nlist, nn.nnum, c->err);
+    c->launches += 1;
+    nn.built = true;
+    CK(cudaGetLastError());
+}
