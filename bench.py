@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — atom-steps/s of the PFMDS MD inner loop on B200 (BASELINE.json metric).
+
+Workload at N=1: BASELINE.json configs[1] — Cu fcc crystal, rjl (Rosato-Guillope-Legrand), NVT at
+300 K, 63^3 cells = 1 000 188 atoms, dt 2 fs, neighbour-list rebuild every 20 steps, synthetic
+lattice with Maxwell velocities (seed 2).  One "step" is one MD step of md()'s loop
+(md_simulation.f90:138-186) through the C ABI (pfmds_advance), including the rebuilds that fall
+into the timed region.  N>1 (torchrun, one rank per GPU): the reference's MPI ensemble mode — every
+rank integrates its own replica of the workload (different velocity seed), no data-path collective;
+`value` is the sum over ranks divided by the slowest rank's device time ("scaling": "weak").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cu_fcc|lj_fluid|ab_gas|graphene_cu]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic (source-level) FP64 operation counts per listed directed pair, DESIGN.md §4 / SURVEY.md §8d:
+# FMA = 2, every exp/sqrt/div/sin/cos = 1.  distance + min-image = 30.
+FLOPS_PER_PAIR = {"rjl_force": 30 + 45, "rjl_density": 30 + 25, "lj1g": 30 + 41, "lj": 30 + 25, "tb_force": 0, "cos_graphene": 30 + 60, "cos_metal": 30 + 60}
+# algorithmic HBM bytes per list-owner atom and launch: 4n (int32 row) + per-atom records
+BYTES_PER_ATOM = {"rjl_force": lambda n: 4 * n + 32 + 32 + 64 + 8 + 4, "rjl_density": lambda n: 4 * n + 32 + 32 + 8 + 4,
+                  "lj1g": lambda n: 4 * n + 32 + 32 + 64 + 4, "lj": lambda n: 4 * n + 32 + 32 + 64 + 4}
+
+
+def build_case(workload, seed, steps):
+    from pfmds_b200 import inputs
+    if workload == "cu_fcc":
+        return inputs.cu_fcc(ncell=63, seed=seed, steps=steps), "nvt", "Cu fcc 63^3x4 = 1000188 atoms, rjl, NVT 300 K, dt 2 fs, r_cut 6.5, rebuild/20"
+    if workload == "lj_fluid":
+        return inputs.lj_fluid(n_side=128, seed=seed, steps=steps), "nve", "LJ fluid (lj1g) 128^3 = 2097152 atoms, NVE, dt 0.5 fs, r_cut 7.5, rebuild/20"
+    if workload == "ab_gas":
+        return inputs.ab_gas(seed=seed), "nvt", "A/B LJ gas 22^3 = 10648 atoms, lj + 2 x lj1g, NVT 100 K, dt 0.5 fs"
+    if workload == "graphene_cu":
+        return inputs.graphene_on_cu(seed=seed), "nvt", "graphene on Cu(111) moire, 11028 atoms, tb + ljc + rjl, NVT 300 K, dt 1 fs"
+    raise SystemExit("unknown workload " + workload)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_sample(steps, threads=None):
+    """The CPU oracle (oracle/, the reference's algorithm restated in C++/OpenMP; kind "port") timed on the
+    host cores on a bounded sample of the same workload: Cu fcc 20^3 cells = 32 000 atoms (the reference's
+    O(N^2) rebuild makes 10^6 atoms infeasible: ~10^12 pair tests per rebuild)."""
+    from pfmds_b200 import inputs
+    from pfmds_b200.engine import configure, load_library
+    lib = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    if not os.path.exists(lib):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    cores = threads or os.cpu_count() or 1
+    L = load_library(lib, "oracle_")
+    L.oracle_set_threads.restype = int
+    cores = L.oracle_set_threads(int(cores))
+    case = inputs.cu_fcc(ncell=20, steps=steps)
+    n = len(case["mass"])
+    e = configure(case, lib_path=lib, prefix="oracle_")
+    t0 = time.perf_counter()
+    e.advance("nvt", 2.0, 0, 1)
+    e.advance("nvt", 2.0, 1, steps)
+    dt = time.perf_counter() - t0
+    return n, steps, dt, cores
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (the C++/OpenMP restatement in oracle/; the
+    Fortran original cannot be compiled in this image) on all host cores, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    k = max(1, min(args.steps, 200))
+    w = max(0, min(args.warmup, 20))
+    n, steps, dt, cores = cpu_baseline_sample(k + w)
+    value = n * (steps + 1) / dt
+    sample = "Cu fcc 20^3x4 = %d atoms (bounded sample of the 1000188-atom workload), step 0 + %d NVT steps, rebuild/20 by the reference's O(N^2) search" % (n, steps)
+    line = {
+        "impl": "reference", "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+        "ms_per_step": dt / (steps + 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Cu fcc, rjl, NVT 300 K, dt 2 fs (BASELINE.json configs[1]); CPU arm runs a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=21)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="cu_fcc")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from pfmds_b200.build import build
+    from pfmds_b200.engine import configure, measure_peaks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (pfmds_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    build()
+
+    K, W = args.steps, max(3, args.warmup)
+    case, integrator, desc = build_case(args.workload, seed=2 + rank, steps=K + W)
+    dt = case["integrators"][0][1]
+    n_atoms = len(case["mass"])
+    eng = configure(case, device=local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: step 0 (lists + forces) and W-1 steps ----
+    eng.advance(integrator, dt, 0, W)
+    eng.synchronize()
+    pairs = eng.pair_count(0, 0)
+
+    # ---- timed region: exactly K steps, device events on the library's stream, clocks sampled meanwhile ----
+    launches0 = eng.launch_count()
+    eng.set_profiling(True)
+    barrier()
+    with ClockSampler(local) as cs:
+        eng.timer_start()
+        eng.advance(integrator, dt, W, K)
+        ms = eng.timer_stop()
+        barrier()
+    ktimes = eng.kernel_times()
+    eng.set_profiling(False)
+    launches = eng.launch_count() - launches0
+    ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    value = n_atoms * world * K / (ms_max * 1e-3)
+
+    # ---- e2e: through the C ABI with host buffers.  Per run: H2D of positions+velocities from pinned host
+    # memory, then every step pfmds_advance(1) + pfmds_energies (D2H of the step's energies, what md() logs
+    # with the reference's default out_period=1), and a final D2H of positions, velocities and forces.
+    e2e = None
+    if not args.no_e2e:
+        ke2e = min(K, 100)
+        hp = torch.empty((n_atoms, 3), dtype=torch.float64).pin_memory()
+        hv = torch.empty((n_atoms, 3), dtype=torch.float64).pin_memory()
+        hp.numpy()[:] = case["pos"]
+        hv.numpy()[:] = case["vel"]
+        barrier()
+        t0 = time.perf_counter()
+        eng.upload_ptr(hp.data_ptr(), hv.data_ptr())
+        eng.advance(integrator, dt, 0, 1)
+        e_bytes = 0
+        for s in range(1, ke2e + 1):
+            eng.advance(integrator, dt, s, 1)
+            e = eng.energies()
+            e_bytes = 8 * (len(e[0]) + 1 + len(e[3]) * (3 * 3 + 2)) + 16
+        out = eng.download()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_atoms * world * ke2e / float(te.item()), "unit": "atom-steps/s", "h2d_bytes_per_step": int(2 * 24 * n_atoms / ke2e),
+               "d2h_bytes_per_step": int(e_bytes + (3 * 32 + 4) * n_atoms / ke2e), "steps": ke2e,
+               "what": "pfmds_upload(H2D pinned) + %d x [pfmds_advance(1) + pfmds_energies (D2H)] + pfmds_download(D2H)" % ke2e}
+        del out
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ----
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_file):
+        try:
+            hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    dfma_tf, copy_gbs = measure_peaks(local)
+    top = max(ktimes.items(), key=lambda kv: kv[1][0]) if ktimes else (None, (0, 0))
+    roofline = None
+    if top[0] is not None:
+        name, (tot_ms, cnt) = top
+        avg_ms = tot_ms / max(cnt, 1)
+        n_per_atom = pairs / n_atoms
+        flops = pairs * FLOPS_PER_PAIR.get(name, 0)
+        byts = n_atoms * BYTES_PER_ATOM.get(name, lambda n: 0)(n_per_atom)
+        ach_tf = flops / (avg_ms * 1e-3) * 1e-12
+        ach_gbs = byts / (avg_ms * 1e-3) * 1e-9
+        roofline = {
+            "kernel": name, "bound": "fp64", "achieved": ach_tf, "peak": dfma_tf, "unit": "TFLOP/s", "frac": ach_tf / dfma_tf if dfma_tf else None,
+            "peak_source": "pfmds_measure_peaks: DFMA micro-benchmark run live in this bench (MEASURED_PEAKS.json carries no FP64 figure)",
+            "avg_launch_ms": avg_ms, "launches": cnt, "share_of_step": tot_ms / ms, "flop_per_pair": FLOPS_PER_PAIR.get(name, 0), "pairs_per_launch": pairs,
+            "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src, "copy_gbs_live": copy_gbs},
+            "traffic": None,
+        }
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        n, steps, tcpu, cores = cpu_baseline_sample(20)
+        cpu = {"value": n * (steps + 1) / tcpu, "unit": "atom-steps/s", "cores": cores, "kind": "port",
+               "sample": "Cu fcc 20^3x4 = %d atoms, step 0 + %d NVT steps (1 O(N^2) rebuild), C++/OpenMP restatement of the reference, %.1f s" % (n, steps, tcpu)}
+    line = {
+        "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "atoms_per_gpu": n_atoms, "parallelism": "ensemble x%d (independent replicas, reference MPI mode)" % world if world > 1 else "single GPU",
+                   "l2": "working set (lists %.0f MB + state) exceeds the 126 MB L2" % (pairs * 4 / 1e6), "ns_per_day": K / (ms_max * 1e-3) * dt * 86400e-6},
+        "clocks": cs.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

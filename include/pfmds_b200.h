@@ -109,6 +109,25 @@ int pfmds_set_nhc(pfmds_ctx* ctx, int k, const double* x, const double* v);
  * reference's PERFOMANCE table (md_simulation.f90:250-259). */
 int pfmds_timers(pfmds_ctx* ctx, double seconds[6]);
 
+/* Overwrite positions and/or velocities (file order, either may be NULL) of a live context, e.g. to
+ * restart from a snapshot; every neighbour list is rebuilt at the next step. */
+int pfmds_upload(pfmds_ctx* ctx, const double* positions, const double* velocities);
+
+/* Sum of nnum over the rows of one neighbour list (directed pairs), for work models. */
+int pfmds_pair_count(pfmds_ctx* ctx, int interaction, int list, long long* pairs);
+
+/* Per-kernel device times: with profiling on, CUDA events bracket every launch of each kernel class on
+ * the context's stream.  pfmds_kernel_times fills ms[k], count[k] for k < n (classes named by
+ * pfmds_kernel_name).  pfmds_timer_start/stop time a region on the context's stream. */
+int pfmds_set_profiling(pfmds_ctx* ctx, int on);
+int pfmds_kernel_times(pfmds_ctx* ctx, int n, double* ms, long long* count);
+const char* pfmds_kernel_name(int k);
+int pfmds_timer_start(pfmds_ctx* ctx);
+int pfmds_timer_stop(pfmds_ctx* ctx, double* ms);
+
+/* Roofline denominators measured on the device: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s). */
+int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs);
+
 /* Number of kernel launches issued so far by this context and device-time of the last advance (ms). */
 int pfmds_launch_count(pfmds_ctx* ctx, long long* launches);
 

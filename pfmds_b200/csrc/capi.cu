@@ -221,6 +221,64 @@ __global__ void k_max_int(int n, const int* __restrict__ a, int* out) {
 
 }  // namespace
 
+// ---- per-kernel profiling -------------------------------------------------------------------------
+void prof_flush(pfmds_ctx* c) {
+    if (c->prof_used == 0) return;
+    cudaStreamSynchronize(c->st);
+    for (size_t k = 0; k < c->prof_used; ++k) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]);
+        c->prof_ms[c->prof_slot[k]] += ms;
+        c->prof_cnt[c->prof_slot[k]] += 1;
+    }
+    c->prof_used = 0;
+}
+KTimer::KTimer(pfmds_ctx* c_, int slot_) : c(c_), slot(slot_) {
+    if (!c->prof_on) return;
+    if (c->prof_used * 2 + 2 > c->prof_ev.size()) {
+        if (c->prof_ev.size() >= 16384) prof_flush(c);
+        else for (int k = 0; k < 1024; ++k) { cudaEvent_t e; cudaEventCreate(&e); c->prof_ev.push_back(e); }
+    }
+    if (c->prof_slot.size() < c->prof_ev.size() / 2) c->prof_slot.resize(c->prof_ev.size() / 2);
+    cudaEventRecord(c->prof_ev[2 * c->prof_used], c->st);
+}
+KTimer::~KTimer() {
+    if (!c->prof_on) return;
+    cudaEventRecord(c->prof_ev[2 * c->prof_used + 1], c->st);
+    c->prof_slot[c->prof_used] = slot;
+    c->prof_used += 1;
+}
+
+// ---- peak micro-benchmarks (the roofline denominators MEASURED_PEAKS.json does not carry) ----------
+// 8 independent DFMA chains per thread; 2 flop per DFMA.
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, double* out) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;
+}
+__global__ void k_copy(size_t n, const double4* __restrict__ a, double4* __restrict__ b) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+__global__ void k_sum_int(int n, const int* __restrict__ a, unsigned long long* out) {
+    unsigned long long s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)a[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+__global__ void k_upload_scatter(int N, const int* __restrict__ orig, const double* __restrict__ hp, const double* __restrict__ hv,
+                                 double4* __restrict__ pos, double4* __restrict__ vel) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    int f = orig[s];
+    if (hp) { double4 p = pos[s]; p.x = hp[3 * f]; p.y = hp[3 * f + 1]; p.z = hp[3 * f + 2]; pos[s] = p; }
+    if (hv) { double4 v = vel[s]; v.x = hv[3 * f]; v.y = hv[3 * f + 1]; v.z = hv[3 * f + 2]; vel[s] = v; }
+}
+
 extern "C" {
 
 int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, const double* vel, const double* mass, const double box[3]) {
@@ -525,6 +583,135 @@ int pfmds_set_nhc(pfmds_ctx* c, int k, const double* x, const double* v) {
     });
 }
 
+
+int pfmds_upload(pfmds_ctx* c, const double* pos, const double* vel) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        const size_t n3 = 3 * (size_t)c->N;
+        double *dp = nullptr, *dv = nullptr;
+        if (pos) { CK(cudaMallocAsync(&dp, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
+        if (vel) { CK(cudaMallocAsync(&dv, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
+        k_upload_scatter<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->orig, dp, dv, c->pos, c->vel);
+        c->launches += 1;
+        if (dp) CK(cudaFreeAsync(dp, c->st));
+        if (dv) CK(cudaFreeAsync(dv, c->st));
+        // membership of every list was decided on the old positions: rebuild at the next step
+        for (auto& it : c->inter) for (int j = 0; j < it.nl_n; ++j) it.nl[j].built = false;
+    });
+}
+
+int pfmds_pair_count(pfmds_ctx* c, int inter, int list, long long* pairs) {
+    if (!c || !pairs) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        if (!c->finalized || inter < 0 || inter >= (int)c->inter.size() || list < 0 || list >= c->inter[(size_t)inter].nl_n) fail(PFMDS_ERR_INVALID, "error: no such neighbour list");
+        unsigned long long* d = nullptr;
+        CK(cudaMalloc(&d, sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->st));
+        k_sum_int<<<256, 256, 0, c->st>>>(c->N, c->inter[(size_t)inter].nl[list].nnum, d);
+        unsigned long long h = 0;
+        CK(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        cudaFree(d);
+        *pairs = (long long)h;
+    });
+}
+
+int pfmds_set_profiling(pfmds_ctx* c, int on) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        prof_flush(c);
+        c->prof_on = on != 0;
+        if (on) { for (int k = 0; k < 32; ++k) { c->prof_ms[k] = 0; c->prof_cnt[k] = 0; } }
+    });
+}
+int pfmds_kernel_times(pfmds_ctx* c, int n, double* ms, long long* count) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        prof_flush(c);
+        for (int k = 0; k < n && k < KS_COUNT; ++k) { if (ms) ms[k] = c->prof_ms[k]; if (count) count[k] = c->prof_cnt[k]; }
+    });
+}
+const char* pfmds_kernel_name(int k) {
+    static const char* names[KS_COUNT] = {"nl_bin", "nl_build", "lj", "lj1g", "rjl_density", "rjl_force", "tb_bond", "tb_force", "cos_graphene",
+                                          "cos_indirect", "cos_metal", "normals", "kick_drift", "kick", "nhc", "zero_forces", "other"};
+    return (k >= 0 && k < KS_COUNT) ? names[k] : "";
+}
+
+int pfmds_timer_start(pfmds_ctx* c) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        if (!c->tm0) { CK(cudaEventCreate(&c->tm0)); CK(cudaEventCreate(&c->tm1)); }
+        CK(cudaStreamSynchronize(c->st));
+        CK(cudaEventRecord(c->tm0, c->st));
+    });
+}
+int pfmds_timer_stop(pfmds_ctx* c, double* ms) {
+    if (!c || !ms) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        if (!c->tm0) fail(PFMDS_ERR_INVALID, "error: pfmds_timer_stop without pfmds_timer_start");
+        CK(cudaEventRecord(c->tm1, c->st));
+        CK(cudaEventSynchronize(c->tm1));
+        float f = 0;
+        CK(cudaEventElapsedTime(&f, c->tm0, c->tm1));
+        *ms = f;
+        check_device_error(c);
+    });
+}
+
+// FP64 FMA peak (TFLOP/s) and device-to-device copy bandwidth (GB/s, read+write) of `device`.
+int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs) {
+    try {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp pr;
+        CK(cudaGetDeviceProperties(&pr, device));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        double* d = nullptr;
+        CK(cudaMalloc(&d, 64));
+        const int iters = 1 << 16, blocks = pr.multiProcessorCount * 8, threads = 256;
+        double best = 0;
+        for (int rep = 0; rep < 5; ++rep) {
+            CK(cudaEventRecord(e0));
+            k_dfma_peak<<<blocks, threads>>>(iters, 1.0 + rep, d);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) * 1e-12;
+            if (rep > 0 && tf > best) best = tf;
+        }
+        if (dfma_tflops) *dfma_tflops = best;
+        cudaFree(d);
+        if (copy_gbs) {
+            const size_t n = (size_t)1 << 25;  // 2 x 1 GiB buffers of double4
+            double4 *a = nullptr, *b = nullptr;
+            CK(cudaMalloc(&a, n * sizeof(double4))); CK(cudaMalloc(&b, n * sizeof(double4)));
+            CK(cudaMemset(a, 0, n * sizeof(double4)));
+            double bw = 0;
+            for (int rep = 0; rep < 5; ++rep) {
+                CK(cudaEventRecord(e0));
+                k_copy<<<pr.multiProcessorCount * 16, 512>>>(n, a, b);
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                double g = 2.0 * n * sizeof(double4) / (ms * 1e-3) * 1e-9;
+                if (rep > 0 && g > bw) bw = g;
+            }
+            *copy_gbs = bw;
+            cudaFree(a); cudaFree(b);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return PFMDS_OK;
+    } catch (...) { return PFMDS_ERR_CUDA; }
+}
+
 int pfmds_timers(pfmds_ctx* c, double s[6]) {
     if (!c || !s) return PFMDS_ERR_INVALID;
     // slots: 0 pos_vel, 1 nlists, 2 nlsearch, 3 nldistance (no such pass on the device), 4 forces, 5 energy
@@ -552,6 +739,8 @@ int pfmds_destroy(pfmds_ctx* c) {
     for (void* p : ptrs) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
+    for (auto e : c->prof_ev) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
     return PFMDS_OK;

@@ -72,6 +72,27 @@ struct pfmds_ctx {
     bool timers_on = false;
     double t_phase[6]{0, 0, 0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // pfmds_timer_start / pfmds_timer_stop
+    // per-kernel profiling
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;  // pairs
+    std::vector<int> prof_slot;
+    size_t prof_used = 0;
+    double prof_ms[32]{};
+    long long prof_cnt[32]{};
+};
+
+// per-kernel device timing (pfmds_set_profiling): CUDA events recorded on the context's stream around
+// every launch of a kernel class, accumulated at synchronisation points
+enum { KS_NL_BIN = 0, KS_NL_BUILD, KS_LJ, KS_LJ1G, KS_RJL_DENSITY, KS_RJL_FORCE, KS_TB_BOND, KS_TB_FORCE, KS_COS_GRAPHENE, KS_COS_INDIRECT,
+       KS_COS_METAL, KS_NORMALS, KS_KICK_DRIFT, KS_KICK, KS_NHC, KS_ZERO_FORCES, KS_OTHER, KS_COUNT };
+
+void prof_flush(pfmds_ctx* c);
+struct KTimer {
+    pfmds_ctx* c;
+    int slot;
+    KTimer(pfmds_ctx* c_, int slot_);
+    ~KTimer();
 };
 
 #define RED_BLOCKS 592  // 148 SMs x 4

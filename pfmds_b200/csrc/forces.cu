@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(FT) k_cos_indirect(int N, const double4* __res
 
 // ------------------------------------------------------------------------------------------------
 void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
+    KTimer kt(c, KS_ZERO_FORCES);
     CK(cudaMemsetAsync(c->frc, 0, sizeof(double4) * (size_t)c->N, c->st));
 }
 
@@ -422,6 +423,7 @@ void normals_interaction(pfmds_ctx* c, int k) {  // update_norm_in_graphene, md_
     if (it.kind != K_LJC && it.kind != K_MORSEC) return;
     const int N = c->N, nb = (N + FT - 1) / FT;
     int simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
+    KTimer kt(c, KS_NORMALS);
     k_normals<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[2].view(c->stride), c->box, simp, it.gnorm);
     c->launches += 1;
 }
@@ -432,22 +434,22 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
     const size_t st = c->stride;
     switch (it.kind) {
     case K_LJ:
-        k_lj<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr);
-        k_lj<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr);
+        { KTimer kt(c, KS_LJ); k_lj<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); }
+        { KTimer kt(c, KS_LJ); k_lj<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); }
         c->launches += 2;
         break;
     case K_LJ1G:
-        k_lj1g<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr);
+        { KTimer kt(c, KS_LJ1G); k_lj1g<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); }
         c->launches += 1;
         break;
     case K_RJL:
-        k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.rjl, c->box, it.aux, nullptr);
-        k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.rjl, c->box, it.aux);
+        { KTimer kt(c, KS_RJL_DENSITY); k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.rjl, c->box, it.aux, nullptr); }
+        { KTimer kt(c, KS_RJL_FORCE); k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.rjl, c->box, it.aux); }
         c->launches += 2;
         break;
     case K_TB:
-        k_tb_bond<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux);
-        k_tb_force<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.tb, c->box, it.aux, nullptr);
+        { KTimer kt(c, KS_TB_BOND); k_tb_bond<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux); }
+        { KTimer kt(c, KS_TB_FORCE); k_tb_force<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.tb, c->box, it.aux, nullptr); }
         c->launches += 2;
         break;
     case K_LJC:
@@ -455,13 +457,13 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
         CosP P = cosp_of(it);
         bool simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
         if (it.kind == K_LJC) {
-            k_cos_direct<false, true, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr);
-            if (!simp) k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec);
-            k_cos_direct<false, false, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr);
+            { KTimer kt(c, KS_COS_GRAPHENE); k_cos_direct<false, true, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec); }
+            { KTimer kt(c, KS_COS_METAL); k_cos_direct<false, false, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         } else {
-            k_cos_direct<true, true, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr);
-            if (!simp) k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec);
-            k_cos_direct<true, false, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr);
+            { KTimer kt(c, KS_COS_GRAPHENE); k_cos_direct<true, true, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec); }
+            { KTimer kt(c, KS_COS_METAL); k_cos_direct<true, false, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         }
         c->launches += simp ? 2 : 3;
         break;

@@ -115,6 +115,7 @@ __global__ void k_scale(int N, double4* __restrict__ vel, const uint32_t* __rest
 }
 void integ_nhc_half(pfmds_ctx* c, Nhc& t, double dt) {
     uint32_t bit = 1u << (t.group - 1);
+    KTimer kt(c, KS_NHC);
     k_ke_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->gmask, bit, c->part);
     k_nhc<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, t.state, t.M, t.L, t.temperature, dt / 2, dt / 4, dt / 8);
     k_scale<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, bit, t.state + 3 * t.M);
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(IT) k_kick_drift(int N, double4* __restrict__ 
     vel[i] = v;
 }
 void integ_kick_drift(pfmds_ctx* c, double dt) {
+    KTimer kt(c, KS_KICK_DRIFT);
     k_kick_drift<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
                                                          1u << (c->z_moving - 1), dt, dt / 2, c->box, c->err);
     c->launches += 1;
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(IT) k_kick(int N, double4* __restrict__ vel, c
     vel[i] = v;
 }
 void integ_kick(pfmds_ctx* c, double dt) {
+    KTimer kt(c, KS_KICK);
     k_kick<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2);
     c->launches += 1;
 }

@@ -153,6 +153,7 @@ __global__ void k_iota(int N, int* a) {
 // slot indices).
 void nl_bin_atoms(pfmds_ctx* c, bool reorder) {
     const int N = c->N, T = 256, nb = (N + T - 1) / T;
+    KTimer kt(c, KS_NL_BIN);
     GridD g;
     for (int k = 0; k < 3; ++k) { g.n[k] = c->ncell[k]; g.inv[k] = c->ncell[k] / c->box.L[k]; }
     CK(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)(c->ncells + 1), c->st));
@@ -234,6 +235,7 @@ void nl_build(pfmds_ctx* c, NList& l) {
     for (int k = 0; k < 3; ++k) { g.n[k] = c->ncell[k]; g.inv[k] = c->ncell[k] / c->box.L[k]; }
     uint32_t b1 = 1u << (l.g1 - 1), b2 = 1u << (l.g2 - 1);
     double rc2 = l.rcut * l.rcut;
+    KTimer kt(c, KS_NL_BUILD);
     if (c->identity_order)
         k_build<true><<<nb, T, 0, c->st>>>(N, c->pos, c->gmask, c->orig, c->cid, c->cell_start, c->cell_atoms, g, c->box, b1, b2, rc2, l.maxn,
                                            c->stride, l.nlist, l.nnum, c->err);
@@ -272,6 +274,7 @@ __global__ void k_nearest3(int N, const double4* __restrict__ pos, const int* __
 
 void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     const int N = c->N, T = 128, nb = (N + T - 1) / T;
+    KTimer kt(c, KS_NL_BUILD);
     k_nearest3<<<nb, T, 0, c->st>>>(N, c->pos, c->orig, src.view(c->stride), c->box, nn.rcut, c->stride, nn.nlist, nn.nnum, c->err);
     c->launches += 1;
     nn.built = true;

@@ -52,10 +52,19 @@ _SIGS = {
     "get_nhc": [C.c_void_p, C.c_int, _dp, _dp],
     "set_nhc": [C.c_void_p, C.c_int, _dp, _dp],
     "timers": [C.c_void_p, _dp],
+    "upload": [C.c_void_p, _dp, _dp],
+    "pair_count": [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_longlong)],
+    "set_profiling": [C.c_void_p, C.c_int],
+    "kernel_times": [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_longlong)],
+    "timer_start": [C.c_void_p],
+    "timer_stop": [C.c_void_p, _dp],
     "launch_count": [C.c_void_p, C.POINTER(C.c_longlong)],
     "synchronize": [C.c_void_p],
     "destroy": [C.c_void_p],
 }
+
+
+_OPTIONAL = ("upload", "pair_count", "set_profiling", "kernel_times", "timer_start", "timer_stop")  # product-only entry points
 
 
 def load_library(path=LIB_PATH, prefix="pfmds_"):
@@ -63,7 +72,11 @@ def load_library(path=LIB_PATH, prefix="pfmds_"):
         raise FileNotFoundError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`" % path)
     lib = C.CDLL(path)
     for name, args in _SIGS.items():
-        fn = getattr(lib, prefix + name)
+        fn = getattr(lib, prefix + name, None)
+        if fn is None:
+            if name in _OPTIONAL:
+                continue
+            raise AttributeError("%s does not export %s%s" % (path, prefix, name))
         fn.argtypes = args
         fn.restype = C.c_int
     getattr(lib, prefix + "last_error").argtypes = [C.c_void_p]
@@ -175,6 +188,42 @@ class Engine:
         v = np.ascontiguousarray(v, np.float64)
         self._call("set_nhc", self._ctx, k, _d(x), _d(v))
 
+    def upload(self, pos=None, vel=None):
+        pos = None if pos is None else np.ascontiguousarray(pos, np.float64).reshape(-1)
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float64).reshape(-1)
+        self._call("upload", self._ctx, _d(pos), _d(vel))
+
+    def upload_ptr(self, pos_ptr, vel_ptr):
+        """Upload from raw host addresses (e.g. pinned torch tensors)."""
+        self._call("upload", self._ctx, C.cast(pos_ptr, _dp), C.cast(vel_ptr, _dp))
+
+    def pair_count(self, interaction, lst):
+        n = C.c_longlong()
+        self._call("pair_count", self._ctx, interaction, lst, C.byref(n))
+        return n.value
+
+    def set_profiling(self, on):
+        self._call("set_profiling", self._ctx, int(bool(on)))
+
+    def kernel_times(self):
+        """{kernel class: (total ms, launches)} measured with CUDA events on the context's stream."""
+        n = 17
+        ms = np.zeros(n)
+        cnt = np.zeros(n, np.int64)
+        self._call("kernel_times", self._ctx, n, _d(ms), cnt.ctypes.data_as(C.POINTER(C.c_longlong)))
+        name = getattr(self._lib, self._p + "kernel_name")
+        name.restype = C.c_char_p
+        name.argtypes = [C.c_int]
+        return {name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k] > 0}
+
+    def timer_start(self):
+        self._call("timer_start", self._ctx)
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._call("timer_stop", self._ctx, C.byref(ms))
+        return ms.value
+
     def timers(self):
         t = np.zeros(6)
         self._call("timers", self._ctx, _d(t))
@@ -195,6 +244,18 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+def measure_peaks(device=0, lib_path=LIB_PATH):
+    """(FP64 FMA TFLOP/s, copy GB/s) measured on the device by the library's micro-benchmarks."""
+    lib = load_library(lib_path)
+    lib.pfmds_measure_peaks.argtypes = [C.c_int, _dp, _dp]
+    lib.pfmds_measure_peaks.restype = C.c_int
+    a, b = C.c_double(), C.c_double()
+    rc = lib.pfmds_measure_peaks(device, C.byref(a), C.byref(b))
+    if rc != 0:
+        raise PfmdsError(rc, "pfmds_measure_peaks failed")
+    return a.value, b.value
 
 
 def configure(case, device=0, lib_path=LIB_PATH, prefix="pfmds_"):
