@@ -1,3 +1,8 @@
-set -x
-python __graft_entry__.py smoke 2>&1 | tail -3
-python bench.py --steps 100 --warmup 21 > gpurun_out/bench_first.json 2> gpurun_out/bench_first.err; tail -c 3000 gpurun_out/bench_first.json; tail -5 gpurun_out/bench_first.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 100 --warmup 21 --no-cpu-baseline --no-e2e 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('value %.4g ms/step %.4f'%(d['value'],d['ms_per_step'])); print(d['kernels_ms_per_step']); print(d['roofline']['frac'], d['clocks'])
+    else: print(l.rstrip())
+"

@@ -108,14 +108,27 @@ void finalize(pfmds_ctx* c) {
                 if (group_of(c, n3.g1) != group_of(c, a.g1)) fail(PFMDS_ERR_LIST_SIZE, "error: nl%N/=nl_nn%N");
             }
         }
+        {   // switch radii of the owning potential drive the row partition (nl.cu k_partition)
+            double R1 = 0, R2 = 0;
+            switch (it.kind) {
+            case K_LJ: R1 = it.lj.R1; R2 = it.lj.R2; break;
+            case K_LJ1G: R1 = it.lj1g.R1; R2 = it.lj1g.R2; break;
+            case K_LJC: R1 = it.ljc.R1; R2 = it.ljc.R2; break;
+            case K_MORSEC: R1 = it.mor.R1; R2 = it.mor.R2; break;
+            case K_RJL: R1 = it.rjl.R1; R2 = it.rjl.R2; break;
+            default: break;
+            }
+            int np = it.kind == K_TB ? 0 : (it.kind == K_LJ1G || it.kind == K_RJL ? 1 : 2);
+            for (int j = 0; j < np; ++j) { it.nl[j].partition = true; it.nl[j].part_r1sq = R1 * R1; it.nl[j].part_r2sq = R2 * R2; }
+        }
         for (int j = 0; j < it.nl_n; ++j) {
             NList& l = it.nl[j];
             if (l.maxn < 1 || l.period < 1 || !(l.rcut > 0)) fail(PFMDS_ERR_INVALID, "error: bad neighbour list parameters");
+            if (l.partition) CK(cudaMalloc(&l.nlist_alt, sizeof(int) * (size_t)l.maxn * c->stride));
             CK(cudaMalloc(&l.nlist, sizeof(int) * (size_t)l.maxn * c->stride));
             CK(cudaMalloc(&l.nnum, sizeof(int) * c->stride));
             CK(cudaMemsetAsync(l.nnum, 0, sizeof(int) * c->stride, c->st));
         }
-        if (it.kind == K_RJL) CK(cudaMalloc(&it.aux, sizeof(double) * c->stride));
         if (it.kind == K_TB) CK(cudaMalloc(&it.aux, sizeof(double) * (size_t)a.maxn * c->stride));
         if (it.kind == K_LJC || it.kind == K_MORSEC) {
             CK(cudaMalloc(&it.gnorm, sizeof(double4) * c->stride));
@@ -175,7 +188,7 @@ void update_lists(pfmds_ctx* c, int step) {
                 NList& l = it.nl[j];
                 if (!((step % l.period == 0) || !l.built)) continue;
                 if (l.from_tb) nl_nearest3_from(c, l, c->inter[(size_t)l.src_inter].nl[0]);
-                else nl_build(c, l);
+                else { nl_build(c, l); nl_partition(c, l); }
             }
         }
     }
@@ -730,7 +743,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     cudaSetDevice(c->dev);
     if (c->st) cudaStreamSynchronize(c->st);
     for (auto& it : c->inter) {
-        for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nnum); }
+        for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nlist_alt); cudaFree(it.nl[j].nnum); }
         cudaFree(it.aux); cudaFree(it.gnorm); cudaFree(it.tvec);
     }
     for (auto& t : c->nhc) cudaFree(t.state);

@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mathx.cuh"
+
 #define PFMDS_MAX_GROUPS 32
 #define PFMDS_ERRW 4  // error word: code, detail a, detail b, spare
 
@@ -46,13 +48,24 @@ __device__ __forceinline__ double min_image(double d, double half, double L) {
 __device__ __forceinline__ void fcut_dfcut(double r, double R1, double R2, double& f, double& dfr) {
     if (r < R1) { f = 1.0; dfr = 0.0; return; }
     double s, c;
-    sincos(PFMDS_PI * (r - R1) / (R2 - R1), &s, &c);
+    mx::sincos_0pi(PFMDS_PI * (r - R1) / (R2 - R1), s, c);
     f = (1.0 + c) / 2;
     dfr = -s * PFMDS_PI / (R2 - R1) / r / 2;
 }
 __device__ __forceinline__ double fcut_only(double r, double R1, double R2) {
     if (r < R1) return 1.0;
-    return (1.0 + cos(PFMDS_PI * (r - R1) / (R2 - R1))) / 2;
+    double s, c;
+    mx::sincos_0pi(PFMDS_PI * (r - R1) / (R2 - R1), s, c);
+    return (1.0 + c) / 2;
+}
+// Minimum image for the force kernels: the comparison with half the box is done on the high words
+// (integer pipe).  It can differ from min_image() only when |d| is within 2^-20 relative of L/2, where
+// either image is farther than every potential cut-off (the box is at least 2 r_cut wide), so the
+// contribution is zero both ways.  List building keeps the exact FP64 test.
+__device__ __forceinline__ double min_image_fast(double d, int half_hi, double L) {
+    int hi = __double2hiint(d);
+    if ((hi & 0x7fffffff) >= half_hi) d += (hi < 0) ? L : -L;
+    return d;
 }
 
 // block-wide sum of `v` (blockDim.x multiple of 32, <= 1024); result valid in thread 0

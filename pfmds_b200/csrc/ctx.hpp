@@ -16,6 +16,10 @@ struct NList {
     bool from_tb = false;  // ljc/morsec nl(3) derived from the first tb list (graphenenorm.f90:58-71)
     int src_inter = -1;
     bool built = false;
+    // rows are re-ordered after every build into [r < R1 | R1 <= r < R2 | r >= R2] (distances at build time)
+    bool partition = false;
+    double part_r1sq = 0, part_r2sq = 0;
+    int* nlist_alt = nullptr;
     ListView view(size_t stride) const { return ListView{nlist, nnum, stride}; }
 };
 
@@ -25,7 +29,7 @@ struct Inter {
     int nl_n = 0;
     NList nl[3];
     LJp lj{}; LJ1Gp lj1g{}; LJCp ljc{}; MORp mor{}; TBp tb{}; RJLp rjl{};
-    double* aux = nullptr;    // rjl: 1/Eb per atom [N]; tb: bond orders B, ELL [maxn][stride]
+    double* aux = nullptr;    // tb: bond orders B, ELL [maxn][stride]  (rjl keeps 1/Eb in pos[].w)
     double4* gnorm = nullptr; // ljc/morsec: unit normal per carbon atom {nx,ny,nz,-}
     double4* tvec = nullptr;  // ljc/morsec: T_i = sum_p V2 V3 f_c/(n_i.dr) dr  (normal-derivative term)
 };
@@ -103,6 +107,7 @@ void nl_setup_grid(pfmds_ctx* c);
 void nl_bin_atoms(pfmds_ctx* c, bool reorder);
 void nl_build(pfmds_ctx* c, NList& l);
 void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src);
+void nl_partition(pfmds_ctx* c, NList& l);
 
 // ---- forces.cu ----
 void forces_zero(pfmds_ctx* c);

@@ -8,6 +8,7 @@
 //
 // FP64-pipe bound: see DESIGN.md for the per-pair operation counts the roofline uses.
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 #include "ctx.hpp"
@@ -118,58 +119,107 @@ __global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ 
 }
 
 // ---- rjl : RosatoGuillopeLegrand.f90:23-94 --------------------------------------------------------
-// pass 1: band sum  Eb2_i = sum exp(-2q(r/r0-1)) f_c ; stores 1/sqrt(Eb2).  With E: the atom's energy.
+// Two passes over the same ELL row (the reference makes three and caches both exponentials per pair,
+// :60-67; recomputing them costs less than the 16 B/pair round trip through HBM).
+//   pass 1  Eb2_i = sum_j exp(-2q(r/r0-1)) f_c(r);  1/sqrt(Eb2_i) is written into pos[i].w so that pass 2
+//           gets it with the same 32-byte gather that brings the partner's position.
+//   pass 2  F_i -= [2 A0 (p/r0 f_c - f_c'/r r) e^{-p t} - xi (q/r0 f_c - f_c'/r r/2)(1/Eb_i + 1/Eb_j) e^{-2q t}]/r dr
+// Rows are class-partitioned at build time (r < R1 | switch zone | beyond R2, nl.cu k_partition) so the
+// lanes of a warp take the same branch; in a crystal the shells line up exactly.
+struct RjlC { double R1, R22, R12, qa, qb, pa, pb, A0, xi, a1, a2, sw, pi_sw; };
+// half-box high words for min_image_fast; INT_MAX-like sentinel would disable wrapping, so tiny boxes use the exact test instead
+struct HalfHi { int x, y, z, exact; };
+static HalfHi half_hi_of(const BoxD& b, double R2) {
+    HalfHi h;
+    long long v;
+    memcpy(&v, &b.h[0], 8); h.x = (int)(v >> 32);
+    memcpy(&v, &b.h[1], 8); h.y = (int)(v >> 32);
+    memcpy(&v, &b.h[2], 8); h.z = (int)(v >> 32);
+    double hm = b.h[0] < b.h[1] ? (b.h[0] < b.h[2] ? b.h[0] : b.h[2]) : (b.h[1] < b.h[2] ? b.h[1] : b.h[2]);
+    h.exact = !(hm >= R2 * (1.0 + 4e-6));
+    return h;
+}
+__device__ __forceinline__ double mi_sel(double d, int hh, double half, double L, int exact) {
+    return exact ? min_image(d, half, L) : min_image_fast(d, hh, L);
+}
+// exp arguments are affine in r: -2q(r/r0-1) = qa r + qb, -p(r/r0-1) = pa r + pb
+static RjlC rjl_consts(const RJLp& P) {
+    RjlC c;
+    c.R1 = P.R1; c.R12 = P.R1 * P.R1; c.R22 = P.R2 * P.R2;
+    c.qa = -2. * P.q / P.r0; c.qb = 2. * P.q; c.pa = -P.p / P.r0; c.pb = P.p;
+    c.A0 = P.A0; c.xi = P.xi; c.a1 = 2. * P.A0 * P.p / P.r0; c.a2 = P.xi * P.q / P.r0;
+    c.sw = PFMDS_PI / (P.R2 - P.R1); c.pi_sw = c.sw / 2;
+    return c;
+}
+
 template <bool E>
-__global__ void __launch_bounds__(FT) k_rjl_density(int N, const double4* __restrict__ pos, ListView lv, RJLp P, BoxD box,
-                                                    double* __restrict__ inv_eb, double* part) {
+__global__ void __launch_bounds__(FT, 8) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, HalfHi H, double* part) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
-        const double4 pi = pos[i];
-        const double R22 = P.R2 * P.R2, ir0 = 1.0 / P.r0;
+        const double2 pxy = *reinterpret_cast<const double2*>(&pos[i]);
+        const double pz = reinterpret_cast<const double*>(&pos[i])[2];
         double sq = 0, sp = 0;
+        const int* row = lv.nlist + i;
         for (int p = 0; p < n; ++p) {
-            int j = lv.nlist[(size_t)p * lv.stride + i];
-            double r2;
-            bond_vec(pi, pos[j], box, r2);
-            if (r2 < R22) {
-                double r = sqrt(r2);
-                double t = r * ir0 - 1.;
-                double f = fcut_only(r, P.R1, P.R2);
-                sq += exp(-2. * P.q * t) * f;
-                if (E) sp += exp(-P.p * t) * f;
+            int j = row[(size_t)p * lv.stride];
+            const double2 qxy = *reinterpret_cast<const double2*>(&pos[j]);  // x,y and z only: .w is being written by this kernel
+            const double qz = reinterpret_cast<const double*>(&pos[j])[2];
+            double dx = mi_sel(qxy.x - pxy.x, H.x, box.h[0], box.L[0], H.exact);
+            double dy = mi_sel(qxy.y - pxy.y, H.y, box.h[1], box.L[1], H.exact);
+            double dz = mi_sel(qz - pz, H.z, box.h[2], box.L[2], H.exact);
+            double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            if (r2 < C.R22) {
+                double r = r2 * mx::rsqrt_fast(r2);
+                double eq = mx::exp_fast(fma(C.qa, r, C.qb));
+                double f = 1.0;
+                if (r2 >= C.R12) {
+                    double s, c;
+                    mx::sincos_0pi((r - C.R1) * C.sw, s, c);
+                    f = fma(c, 0.5, 0.5);
+                }
+                sq = fma(eq, f, sq);
+                if (E) sp = fma(mx::exp_fast(fma(C.pa, r, C.pb)), f, sp);
             }
         }
-        double eb = sqrt(sq);
-        inv_eb[i] = 1.0 / eb;
-        if (E) e = P.A0 * sp - P.xi * eb;
+        double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
+        reinterpret_cast<double*>(&pos[i])[3] = ie;
+        if (E) e = C.A0 * sp - C.xi * (sq * ie);
     }
     if (E) store_partial(e, part);
 }
-// pass 2: gather with 1/Eb_i + 1/Eb_j
-__global__ void __launch_bounds__(FT) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RJLp P, BoxD box,
-                                                  const double* __restrict__ inv_eb) {
+__global__ void __launch_bounds__(FT, 8) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box, HalfHi H) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int n = lv.nnum[i];
     if (n == 0) return;
     const double4 pi = pos[i];
-    const double R22 = P.R2 * P.R2, ir0 = 1.0 / P.r0, ie_i = inv_eb[i];
-    const double pr = P.p * ir0, qr = P.q * ir0;
     double fx = 0, fy = 0, fz = 0;
+    const int* row = lv.nlist + i;
     for (int p = 0; p < n; ++p) {
-        int j = lv.nlist[(size_t)p * lv.stride + i];
-        double r2;
-        Vec d = bond_vec(pi, pos[j], box, r2);
-        if (r2 < R22) {
-            double r = sqrt(r2);
-            double t = r * ir0 - 1.;
-            double f, dfr;
-            fcut_dfcut(r, P.R1, P.R2, f, dfr);
-            double ep = exp(-P.p * t), eq = exp(-2. * P.q * t);
-            double c = (2. * P.A0 * (pr * f - dfr * r) * ep - P.xi * (qr * f - dfr / 2. * r) * (ie_i + inv_eb[j]) * eq) / r;
-            fx -= c * d.x; fy -= c * d.y; fz -= c * d.z;
+        int j = row[(size_t)p * lv.stride];
+        const double4 pj = pos[j];
+        double dx = mi_sel(pj.x - pi.x, H.x, box.h[0], box.L[0], H.exact);
+        double dy = mi_sel(pj.y - pi.y, H.y, box.h[1], box.L[1], H.exact);
+        double dz = mi_sel(pj.z - pi.z, H.z, box.h[2], box.L[2], H.exact);
+        double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (r2 < C.R22) {
+            double ir = mx::rsqrt_fast(r2);
+            double r = r2 * ir;
+            double ep = mx::exp_fast(fma(C.pa, r, C.pb)), eq = mx::exp_fast(fma(C.qa, r, C.qb));
+            double ies = pi.w + pj.w;
+            double c;
+            if (r2 < C.R12) {
+                c = (C.a1 * ep - C.a2 * ies * eq) * ir;
+            } else {
+                double s, cs;
+                mx::sincos_0pi((r - C.R1) * C.sw, s, cs);
+                double f = fma(cs, 0.5, 0.5);
+                double dfr_r = -s * C.pi_sw;  // f_c'(r) = df_cut * r
+                c = (2. * C.A0 * (-C.pa * f - dfr_r) * ep - C.xi * (-0.5 * C.qa * f - 0.5 * dfr_r) * ies * eq) * ir;
+            }
+            fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
         }
     }
     add_force(frc, i, fx, fy, fz);
@@ -232,7 +282,7 @@ __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restric
             double f_c, dfr_p;
             fcut_dfcut(rp, T.R1, T.R2, f_c, dfr_p);
             double a = -s2s * T.b * (rp - T.r0);
-            double ea = exp(a), eas = exp(a / T.s);
+            double ea = mx::exp_fast(a), eas = mx::exp_fast(a / T.s);
             if (E) {
                 if (j > i) e += f_c * dpre * (ea - (Bip + Bjl) / 2 * T.s * eas);
             }
@@ -272,7 +322,7 @@ __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restric
                     dB.x += g * w.x; dB.y += g * w.y; dB.z += g * w.z;
                     double pre = T.delt / 2 * pow(B[(size_t)q * lv.stride + j], ex);
                     double g1 = f_c * gg, g2 = dfr_p * T.a0 * tb_G(c1, T);
-                    double tail = fq * dpre * T.s * exp(-s2s * T.b * (rq - T.r0) / T.s);
+                    double tail = fq * dpre * T.s * mx::exp_fast(-s2s * T.b * (rq - T.r0) / T.s);
                     cx += pre * (g1 * w.x + dp.x * g2) * tail;
                     cy += pre * (g1 * w.y + dp.y * g2) * tail;
                     cz += pre * (g1 * w.z + dp.z * g2) * tail;
@@ -315,7 +365,7 @@ __global__ void k_normals(int N, const double4* __restrict__ pos, ListView nn, B
 struct CosP { double pe, sig, a, r0, delt, R1, R2; };  // pe = 4 eps (ljc) or d (morsec)
 template <bool MORSE>
 __device__ __forceinline__ double cos_V2(double r, double r2, const CosP& P) {
-    if (MORSE) return exp(-P.a * (r - P.r0));
+    if (MORSE) return mx::exp_fast(-P.a * (r - P.r0));
     double q = P.sig * P.sig / r2;
     return q * q * q;
 }
@@ -443,8 +493,8 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
         c->launches += 1;
         break;
     case K_RJL:
-        { KTimer kt(c, KS_RJL_DENSITY); k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.rjl, c->box, it.aux, nullptr); }
-        { KTimer kt(c, KS_RJL_FORCE); k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.rjl, c->box, it.aux); }
+        { KTimer kt(c, KS_RJL_DENSITY); k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, half_hi_of(c->box, it.rjl.R2), nullptr); }
+        { KTimer kt(c, KS_RJL_FORCE); k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), rjl_consts(it.rjl), c->box, half_hi_of(c->box, it.rjl.R2)); }
         c->launches += 2;
         break;
     case K_TB:
@@ -480,7 +530,7 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     switch (it.kind) {
     case K_LJ: k_lj<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
     case K_LJ1G: k_lj1g<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
-    case K_RJL: k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.rjl, c->box, it.aux, c->part); break;
+    case K_RJL: k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, half_hi_of(c->box, it.rjl.R2), c->part); break;
     case K_TB:
         k_tb_bond<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux);
         k_tb_force<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.tb, c->box, it.aux, c->part);

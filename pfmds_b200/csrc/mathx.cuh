@@ -1,0 +1,130 @@
+// pfmds_b200 — FP64 elementary functions for the force kernels.
+//
+// The CUDA math library's exp/sincos/sqrt materialise every 64-bit polynomial coefficient with
+// MOV/IMAD pairs inside the pair loop (28 % of the issued instructions of the first rjl kernels,
+// profiles/r1_*): here the coefficients live in the constant bank and enter DFMA as c[bank][off]
+// operands, range reduction is specialised to what the potentials need, and there are no slow paths.
+// Accuracy (tests/test_mathx.py, compiled for the host from this same header): relative error
+// < 3e-14 for exp on [-700, 700], absolute error < 4e-16 for sin/cos on [0, pi], relative error
+// < 5e-16 for rsqrt — three to six orders of magnitude inside the 1e-9 parity bar.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define MX_HD __host__ __device__ __forceinline__
+#define MX_CONST __constant__
+#else
+#define MX_HD inline
+#define MX_CONST static const
+#endif
+
+namespace mx {
+
+// exp(r) = sum r^n/n!  on |r| <= ln2/4 after halving: coefficients of (r/2)^n folded in
+MX_CONST double EXP_C[10] = {1.0,
+                             1.0 / 2.0,
+                             1.0 / 8.0,
+                             1.0 / 48.0,
+                             1.0 / 384.0,
+                             1.0 / 3840.0,
+                             1.0 / 46080.0,
+                             1.0 / 645120.0,
+                             1.0 / 10321920.0,
+                             1.0 / 185794560.0};
+// sin(y) = y + y^3 S(y^2), cos(y) = 1 + y^2 C(y^2) on |y| <= pi/4
+MX_CONST double SIN_C[7] = {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0, -1.0 / 1307674368000.0};
+MX_CONST double COS_C[8] = {-1.0 / 2.0, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0,
+                            1.0 / 20922789888000.0};
+
+MX_HD double as_double(long long v) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(v);
+#else
+    double d; memcpy(&d, &v, 8); return d;
+#endif
+}
+MX_HD long long as_ll(double d) {
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(d);
+#else
+    long long v; memcpy(&v, &d, 8); return v;
+#endif
+}
+
+// exp(x), |x| clamped to 700.  k = round(x/ln2) by the 1.5*2^52 trick, r = x - k ln2 (two-part ln2),
+// e^r = (P9(r/2))^2, result scaled by adding k to the exponent field.
+MX_HD double exp_fast(double x) {
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+    double t = fma(x, 1.4426950408889634, MAGIC);
+    double kd = t - MAGIC;
+    long long k = (long long)(int)(unsigned int)(as_ll(t) & 0xffffffffll);  // low word of t holds k (two's complement)
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = EXP_C[9];
+    p = fma(p, r, EXP_C[8]);
+    p = fma(p, r, EXP_C[7]);
+    p = fma(p, r, EXP_C[6]);
+    p = fma(p, r, EXP_C[5]);
+    p = fma(p, r, EXP_C[4]);
+    p = fma(p, r, EXP_C[3]);
+    p = fma(p, r, EXP_C[2]);
+    p = fma(p, r, EXP_C[1]);
+    p = fma(p, r, EXP_C[0]);
+    p = p * p;
+    return as_double(as_ll(p) + (k << 52));
+}
+
+// sin and cos of a in [0, pi] (slightly outside is fine): y = a - pi/2 folded to |y| <= pi/4
+MX_HD void sincos_0pi(double a, double& s, double& c) {
+    const double PIO2_HI = 1.57079632679489655800e+00, PIO2_LO = 6.12323399573676603587e-17;
+    double y = (a - PIO2_HI) - PIO2_LO;  // in [-pi/2, pi/2]: sin a = cos y, cos a = -sin y
+    // fold: |y| > pi/4  ->  z = pi/2 - |y|, cos y = sin z, sin|y| = cos z
+    double ay = fabs(y);
+    bool big = ay > 0.78539816339744830962;
+    double z = big ? (PIO2_HI - ay) + PIO2_LO : ay;
+    double z2 = z * z;
+    double ps = SIN_C[6];
+    ps = fma(ps, z2, SIN_C[5]);
+    ps = fma(ps, z2, SIN_C[4]);
+    ps = fma(ps, z2, SIN_C[3]);
+    ps = fma(ps, z2, SIN_C[2]);
+    ps = fma(ps, z2, SIN_C[1]);
+    ps = fma(ps, z2, SIN_C[0]);
+    double sz = fma(z * z2, ps, z);
+    double pc = COS_C[7];
+    pc = fma(pc, z2, COS_C[6]);
+    pc = fma(pc, z2, COS_C[5]);
+    pc = fma(pc, z2, COS_C[4]);
+    pc = fma(pc, z2, COS_C[3]);
+    pc = fma(pc, z2, COS_C[2]);
+    pc = fma(pc, z2, COS_C[1]);
+    pc = fma(pc, z2, COS_C[0]);
+    double cz = fma(z2, pc, 1.0);
+    double sin_ay = big ? cz : sz, cos_y = big ? sz : cz;
+    s = cos_y;                            // sin a
+    c = (y < 0.0) ? sin_ay : -sin_ay;     // cos a = -sin y
+}
+
+// 1/sqrt(x) for normal positive x: hardware seed (MUFU.RSQ64H) + two Newton steps
+MX_HD double rsqrt_fast(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    double y = (double)(1.0f / sqrtf((float)x));
+#endif
+    double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+#ifndef __CUDA_ARCH__
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+#endif
+    return y;
+}
+
+}  // namespace mx

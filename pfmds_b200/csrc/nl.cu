@@ -280,3 +280,44 @@ void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     nn.built = true;
     CK(cudaGetLastError());
 }
+
+// ------------------------------------------------------------------------------------------------
+// Class partition of every row (distances at build time): entries with r < R1 first, then the switch
+// zone R1 <= r < R2, then r >= R2.  Membership is untouched — this only permutes a row — but the lanes
+// of a warp, which walk slot p of 32 neighbouring atoms together, then mostly agree on the branch the
+// potential takes (in a crystal the coordination shells line up exactly).
+__global__ void __launch_bounds__(128) k_partition(int N, const double4* __restrict__ pos, const int* __restrict__ nlist, const int* __restrict__ nnum,
+                                                   size_t stride, BoxD box, double r1sq, double r2sq, int* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int n = nnum[i];
+    if (n == 0) return;
+    const double4 pi = pos[i];
+    int c0 = 0, c1 = 0;
+    for (int p = 0; p < n; ++p) {
+        double4 pj = pos[nlist[(size_t)p * stride + i]];
+        double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]), dy = min_image(pj.y - pi.y, box.h[1], box.L[1]), dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
+        double r2 = dx * dx + dy * dy + dz * dz;
+        c0 += r2 < r1sq;
+        c1 += (r2 >= r1sq) & (r2 < r2sq);
+    }
+    int o0 = 0, o1 = c0, o2 = c0 + c1;
+    for (int p = 0; p < n; ++p) {
+        int j = nlist[(size_t)p * stride + i];
+        double4 pj = pos[j];
+        double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]), dy = min_image(pj.y - pi.y, box.h[1], box.L[1]), dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
+        double r2 = dx * dx + dy * dy + dz * dz;
+        int slot = r2 < r1sq ? o0++ : (r2 < r2sq ? o1++ : o2++);
+        out[(size_t)slot * stride + i] = j;
+    }
+}
+
+void nl_partition(pfmds_ctx* c, NList& l) {
+    if (!l.partition) return;
+    const int N = c->N, T = 128, nb = (N + T - 1) / T;
+    KTimer kt(c, KS_NL_BUILD);
+    k_partition<<<nb, T, 0, c->st>>>(N, c->pos, l.nlist, l.nnum, c->stride, c->box, l.part_r1sq, l.part_r2sq, l.nlist_alt);
+    std::swap(l.nlist, l.nlist_alt);
+    c->launches += 1;
+    CK(cudaGetLastError());
+}

@@ -1,0 +1,9 @@
+// host build of pfmds_b200/csrc/mathx.cuh for accuracy tests (tests/test_mathx.py)
+#include <cmath>
+#include <cstdio>
+#include "../pfmds_b200/csrc/mathx.cuh"
+extern "C" {
+double mx_exp(double x) { return mx::exp_fast(x); }
+void mx_sincos(double a, double* s, double* c) { mx::sincos_0pi(a, *s, *c); }
+double mx_rsqrt(double x) { return mx::rsqrt_fast(x); }
+}

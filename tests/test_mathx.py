@@ -1,0 +1,50 @@
+"""Accuracy of the constant-bank FP64 elementary functions (pfmds_b200/csrc/mathx.cuh), host build."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("mx") / "libmx.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "mathx_host.cpp")], check=True)
+    L = C.CDLL(out)
+    L.mx_exp.restype = C.c_double
+    L.mx_exp.argtypes = [C.c_double]
+    L.mx_rsqrt.restype = C.c_double
+    L.mx_rsqrt.argtypes = [C.c_double]
+    L.mx_sincos.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    return L
+
+
+def test_exp(lib):
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([rng.uniform(-700, 700, 20000), rng.uniform(-20, 20, 20000), rng.uniform(-1, 1, 5000), [0.0, -0.0, 1e-300, 700.0, -700.0]])
+    got = np.array([lib.mx_exp(float(x)) for x in xs])
+    ref = np.exp(xs.astype(np.longdouble)).astype(np.float64)
+    assert np.max(np.abs(got - ref) / ref) < 3e-14
+
+
+def test_sincos(lib):
+    rng = np.random.default_rng(2)
+    xs = np.concatenate([rng.uniform(0, np.pi, 40000), [0.0, np.pi / 4, np.pi / 2, 3 * np.pi / 4, np.pi, 3.14159265358979]])
+    s, c = C.c_double(), C.c_double()
+    err = 0.0
+    for x in xs:
+        lib.mx_sincos(float(x), C.byref(s), C.byref(c))
+        err = max(err, abs(s.value - float(np.sin(np.longdouble(x)))), abs(c.value - float(np.cos(np.longdouble(x)))))
+    assert err < 4e-16
+
+
+def test_rsqrt(lib):
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.uniform(0.01, 200, 20000), 10.0 ** rng.uniform(-10, 10, 5000)])
+    got = np.array([lib.mx_rsqrt(float(x)) for x in xs])
+    ref = (1 / np.sqrt(xs.astype(np.longdouble))).astype(np.float64)
+    assert np.max(np.abs(got - ref) / ref) < 5e-16
