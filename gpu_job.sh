@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python bench.py --steps 100 --warmup 21 --no-cpu-baseline --no-e2e 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:

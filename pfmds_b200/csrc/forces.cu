@@ -139,12 +139,13 @@ static HalfHi half_hi_of(const BoxD& b, double R2) {
     h.exact = !(hm >= R2 * (1.0 + 4e-6));
     return h;
 }
-__device__ __forceinline__ double mi_sel(double d, int hh, double half, double L, int exact) {
-    return exact ? min_image(d, half, L) : min_image_fast(d, hh, L);
-}
+
 // exp arguments are affine in r: -2q(r/r0-1) = qa r + qb, -p(r/r0-1) = pa r + pb
 static RjlC rjl_consts(const RJLp& P) {
     RjlC c;
+    // exp_nc needs |argument| < 700 for every r in (0, R2): |2q|, |p| and their values at R2 bound it
+    if (!(fabs(2. * P.q) < 600. && fabs(P.p) < 600. && fabs(2. * P.q * (P.R2 / P.r0 - 1.)) < 600. && fabs(P.p * (P.R2 / P.r0 - 1.)) < 600.))
+        throw std::string("rjl parameters out of the supported range (|p|, |2q| and their products with R2/r0-1 must stay below 600)");
     c.R1 = P.R1; c.R12 = P.R1 * P.R1; c.R22 = P.R2 * P.R2;
     c.qa = -2. * P.q / P.r0; c.qb = 2. * P.q; c.pa = -P.p / P.r0; c.pb = P.p;
     c.A0 = P.A0; c.xi = P.xi; c.a1 = 2. * P.A0 * P.p / P.r0; c.a2 = P.xi * P.q / P.r0;
@@ -152,8 +153,14 @@ static RjlC rjl_consts(const RJLp& P) {
     return c;
 }
 
-template <bool E>
-__global__ void __launch_bounds__(FT, 8) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, HalfHi H, double* part) {
+// Both kernels are software-pipelined by hand: the row index for slot p+2 and the position record for
+// slot p+1 are requested before the arithmetic of slot p, so a warp keeps two dependent memory levels
+// (index -> gather) in flight under ~100 FP64 instructions of work.
+#ifndef RJL_MINB
+#define RJL_MINB 6
+#endif
+template <bool E, bool EXACT>
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, HalfHi H, double* part) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
     int n = i < N ? lv.nnum[i] : 0;
@@ -162,25 +169,31 @@ __global__ void __launch_bounds__(FT, 8) k_rjl_density(int N, double4* pos, List
         const double pz = reinterpret_cast<const double*>(&pos[i])[2];
         double sq = 0, sp = 0;
         const int* row = lv.nlist + i;
+        int jn = row[0];
+        int jnn = n > 1 ? row[lv.stride] : jn;
+        // x,y and z only: .w of every record is being written by this kernel
+        double2 nxy = *reinterpret_cast<const double2*>(&pos[jn]);
+        double nz = reinterpret_cast<const double*>(&pos[jn])[2];
         for (int p = 0; p < n; ++p) {
-            int j = row[(size_t)p * lv.stride];
-            const double2 qxy = *reinterpret_cast<const double2*>(&pos[j]);  // x,y and z only: .w is being written by this kernel
-            const double qz = reinterpret_cast<const double*>(&pos[j])[2];
-            double dx = mi_sel(qxy.x - pxy.x, H.x, box.h[0], box.L[0], H.exact);
-            double dy = mi_sel(qxy.y - pxy.y, H.y, box.h[1], box.L[1], H.exact);
-            double dz = mi_sel(qz - pz, H.z, box.h[2], box.L[2], H.exact);
+            const double2 qxy = nxy;
+            const double qz = nz;
+            nxy = *reinterpret_cast<const double2*>(&pos[jnn]);
+            nz = reinterpret_cast<const double*>(&pos[jnn])[2];
+            if (p + 2 < n) jnn = row[(size_t)(p + 2) * lv.stride];
+            double dx = qxy.x - pxy.x, dy = qxy.y - pxy.y, dz = qz - pz;
+            if (EXACT) { dx = min_image(dx, box.h[0], box.L[0]); dy = min_image(dy, box.h[1], box.L[1]); dz = min_image(dz, box.h[2], box.L[2]); }
+            else { dx = min_image_fast(dx, H.x, box.L[0]); dy = min_image_fast(dy, H.y, box.L[1]); dz = min_image_fast(dz, H.z, box.L[2]); }
             double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             if (r2 < C.R22) {
                 double r = r2 * mx::rsqrt_fast(r2);
-                double eq = mx::exp_fast(fma(C.qa, r, C.qb));
+                double eq = mx::exp_nc(fma(C.qa, r, C.qb));
                 double f = 1.0;
                 if (r2 >= C.R12) {
-                    double s, c;
-                    mx::sincos_0pi((r - C.R1) * C.sw, s, c);
-                    f = fma(c, 0.5, 0.5);
+                    double s;
+                    mx::cos_switch((r - C.R1) * C.sw, f, s);
                 }
                 sq = fma(eq, f, sq);
-                if (E) sp = fma(mx::exp_fast(fma(C.pa, r, C.pb)), f, sp);
+                if (E) sp = fma(mx::exp_nc(fma(C.pa, r, C.pb)), f, sp);
             }
         }
         double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
@@ -189,7 +202,9 @@ __global__ void __launch_bounds__(FT, 8) k_rjl_density(int N, double4* pos, List
     }
     if (E) store_partial(e, part);
 }
-__global__ void __launch_bounds__(FT, 8) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box, HalfHi H) {
+template <bool EXACT>
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
+                                                            HalfHi H) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int n = lv.nnum[i];
@@ -197,25 +212,28 @@ __global__ void __launch_bounds__(FT, 8) k_rjl_force(int N, const double4* __res
     const double4 pi = pos[i];
     double fx = 0, fy = 0, fz = 0;
     const int* row = lv.nlist + i;
+    int jn = row[0];
+    int jnn = n > 1 ? row[lv.stride] : jn;
+    double4 pn = pos[jn];
     for (int p = 0; p < n; ++p) {
-        int j = row[(size_t)p * lv.stride];
-        const double4 pj = pos[j];
-        double dx = mi_sel(pj.x - pi.x, H.x, box.h[0], box.L[0], H.exact);
-        double dy = mi_sel(pj.y - pi.y, H.y, box.h[1], box.L[1], H.exact);
-        double dz = mi_sel(pj.z - pi.z, H.z, box.h[2], box.L[2], H.exact);
+        const double4 pj = pn;
+        pn = pos[jnn];
+        if (p + 2 < n) jnn = row[(size_t)(p + 2) * lv.stride];
+        double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+        if (EXACT) { dx = min_image(dx, box.h[0], box.L[0]); dy = min_image(dy, box.h[1], box.L[1]); dz = min_image(dz, box.h[2], box.L[2]); }
+        else { dx = min_image_fast(dx, H.x, box.L[0]); dy = min_image_fast(dy, H.y, box.L[1]); dz = min_image_fast(dz, H.z, box.L[2]); }
         double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         if (r2 < C.R22) {
             double ir = mx::rsqrt_fast(r2);
             double r = r2 * ir;
-            double ep = mx::exp_fast(fma(C.pa, r, C.pb)), eq = mx::exp_fast(fma(C.qa, r, C.qb));
+            double ep = mx::exp_nc(fma(C.pa, r, C.pb)), eq = mx::exp_nc(fma(C.qa, r, C.qb));
             double ies = pi.w + pj.w;
             double c;
             if (r2 < C.R12) {
                 c = (C.a1 * ep - C.a2 * ies * eq) * ir;
             } else {
-                double s, cs;
-                mx::sincos_0pi((r - C.R1) * C.sw, s, cs);
-                double f = fma(cs, 0.5, 0.5);
+                double f, s;
+                mx::cos_switch((r - C.R1) * C.sw, f, s);
                 double dfr_r = -s * C.pi_sw;  // f_c'(r) = df_cut * r
                 c = (2. * C.A0 * (-C.pa * f - dfr_r) * ep - C.xi * (-0.5 * C.qa * f - 0.5 * dfr_r) * ies * eq) * ir;
             }
@@ -493,8 +511,20 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
         c->launches += 1;
         break;
     case K_RJL:
-        { KTimer kt(c, KS_RJL_DENSITY); k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, half_hi_of(c->box, it.rjl.R2), nullptr); }
-        { KTimer kt(c, KS_RJL_FORCE); k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), rjl_consts(it.rjl), c->box, half_hi_of(c->box, it.rjl.R2)); }
+    {
+        const RjlC C = rjl_consts(it.rjl);
+        const HalfHi H = half_hi_of(c->box, it.rjl.R2);
+        {
+            KTimer kt(c, KS_RJL_DENSITY);
+            if (H.exact) k_rjl_density<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, H, nullptr);
+            else k_rjl_density<false, false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, H, nullptr);
+        }
+        {
+            KTimer kt(c, KS_RJL_FORCE);
+            if (H.exact) k_rjl_force<true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, H);
+            else k_rjl_force<false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, H);
+        }
+    }
         c->launches += 2;
         break;
     case K_TB:
@@ -530,7 +560,12 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     switch (it.kind) {
     case K_LJ: k_lj<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
     case K_LJ1G: k_lj1g<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
-    case K_RJL: k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, half_hi_of(c->box, it.rjl.R2), c->part); break;
+    case K_RJL: {
+        const HalfHi H = half_hi_of(c->box, it.rjl.R2);
+        if (H.exact) k_rjl_density<true, true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, H, c->part);
+        else k_rjl_density<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, H, c->part);
+        break;
+    }
     case K_TB:
         k_tb_bond<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux);
         k_tb_force<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.tb, c->box, it.aux, c->part);

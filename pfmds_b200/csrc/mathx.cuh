@@ -76,6 +76,56 @@ MX_HD double exp_fast(double x) {
     return as_double(as_ll(p) + (k << 52));
 }
 
+// exp(x) without the clamp, for arguments the caller has bounded to |x| < 700
+MX_HD double exp_nc(double x) {
+    const double MAGIC = 6755399441055744.0;
+    double t = fma(x, 1.4426950408889634, MAGIC);
+    double kd = t - MAGIC;
+    long long k = (long long)(int)(unsigned int)(as_ll(t) & 0xffffffffll);
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = EXP_C[9];
+    p = fma(p, r, EXP_C[8]);
+    p = fma(p, r, EXP_C[7]);
+    p = fma(p, r, EXP_C[6]);
+    p = fma(p, r, EXP_C[5]);
+    p = fma(p, r, EXP_C[4]);
+    p = fma(p, r, EXP_C[3]);
+    p = fma(p, r, EXP_C[2]);
+    p = fma(p, r, EXP_C[1]);
+    p = fma(p, r, EXP_C[0]);
+    p = p * p;
+    return as_double(as_ll(p) + (k << 52));
+}
+
+// Cosine switch without selects: for a in [0, pi], u = a/2 - pi/4 in [-pi/4, pi/4],
+//   (1 + cos a)/2 = cos^2(a/2) = (cos u - sin u)^2 / 2,   sin a = (cos u - sin u)(cos u + sin u).
+MX_HD void cos_switch(double a, double& half_one_plus_cos, double& sin_a) {
+    const double PIO4_HI = 7.85398163397448279e-01, PIO4_LO = 3.06161699786838302e-17;
+    double u = (fma(a, 0.5, -PIO4_HI)) - PIO4_LO;
+    double u2 = u * u;
+    double ps = SIN_C[6];
+    ps = fma(ps, u2, SIN_C[5]);
+    ps = fma(ps, u2, SIN_C[4]);
+    ps = fma(ps, u2, SIN_C[3]);
+    ps = fma(ps, u2, SIN_C[2]);
+    ps = fma(ps, u2, SIN_C[1]);
+    ps = fma(ps, u2, SIN_C[0]);
+    double su = fma(u * u2, ps, u);
+    double pc = COS_C[7];
+    pc = fma(pc, u2, COS_C[6]);
+    pc = fma(pc, u2, COS_C[5]);
+    pc = fma(pc, u2, COS_C[4]);
+    pc = fma(pc, u2, COS_C[3]);
+    pc = fma(pc, u2, COS_C[2]);
+    pc = fma(pc, u2, COS_C[1]);
+    pc = fma(pc, u2, COS_C[0]);
+    double cu = fma(u2, pc, 1.0);
+    double d = cu - su;
+    half_one_plus_cos = 0.5 * d * d;
+    sin_a = d * (cu + su);
+}
+
 // sin and cos of a in [0, pi] (slightly outside is fine): y = a - pi/2 folded to |y| <= pi/4
 MX_HD void sincos_0pi(double a, double& s, double& c) {
     const double PIO2_HI = 1.57079632679489655800e+00, PIO2_LO = 6.12323399573676603587e-17;

@@ -42,6 +42,28 @@ def test_sincos(lib):
     assert err < 4e-16
 
 
+def test_cos_switch(lib):
+    lib.mx_cos_switch.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    rng = np.random.default_rng(4)
+    xs = np.concatenate([rng.uniform(0, np.pi, 40000), [0.0, np.pi / 2, np.pi, 3.14159265358979, 1e-9, np.pi - 1e-9]])
+    f, s = C.c_double(), C.c_double()
+    err = 0.0
+    for x in xs:
+        lib.mx_cos_switch(float(x), C.byref(f), C.byref(s))
+        xl = np.longdouble(x)
+        err = max(err, abs(f.value - float((1 + np.cos(xl)) / 2)), abs(s.value - float(np.sin(xl))))
+    assert err < 5e-16
+
+
+def test_exp_nc(lib):
+    lib.mx_exp_nc.restype = C.c_double
+    lib.mx_exp_nc.argtypes = [C.c_double]
+    xs = np.random.default_rng(5).uniform(-600, 600, 20000)
+    got = np.array([lib.mx_exp_nc(float(x)) for x in xs])
+    ref = np.exp(xs.astype(np.longdouble)).astype(np.float64)
+    assert np.max(np.abs(got - ref) / ref) < 3e-14
+
+
 def test_rsqrt(lib):
     rng = np.random.default_rng(3)
     xs = np.concatenate([rng.uniform(0.01, 200, 20000), 10.0 ** rng.uniform(-10, 10, 5000)])
