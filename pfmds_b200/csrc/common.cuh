@@ -68,6 +68,19 @@ __device__ __forceinline__ double min_image_fast(double d, int half_hi, double L
     return d;
 }
 
+// One 256-bit load per 32-byte record (sm_100a LDG.E.256): a gather of 32 records costs the L1 one
+// request instead of the two LDG.128 the compiler emits for a double4.
+__device__ __forceinline__ double4 ld256_nc(const double4* p) {  // read-only data
+    double4 v;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double4 ld256(const double4* p) {
+    double4 v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+
 // block-wide sum of `v` (blockDim.x multiple of 32, <= 1024); result valid in thread 0
 __device__ __forceinline__ double block_sum(double v) {
     __shared__ double sh[32];

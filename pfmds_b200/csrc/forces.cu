@@ -127,19 +127,6 @@ __global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ 
 // Rows are class-partitioned at build time (r < R1 | switch zone | beyond R2, nl.cu k_partition) so the
 // lanes of a warp take the same branch; in a crystal the shells line up exactly.
 struct RjlC { double R1, R22, R12, qa, qb, pa, pb, A0, xi, a1, a2, sw, pi_sw; };
-// half-box high words for min_image_fast; INT_MAX-like sentinel would disable wrapping, so tiny boxes use the exact test instead
-struct HalfHi { int x, y, z, exact; };
-static HalfHi half_hi_of(const BoxD& b, double R2) {
-    HalfHi h;
-    long long v;
-    memcpy(&v, &b.h[0], 8); h.x = (int)(v >> 32);
-    memcpy(&v, &b.h[1], 8); h.y = (int)(v >> 32);
-    memcpy(&v, &b.h[2], 8); h.z = (int)(v >> 32);
-    double hm = b.h[0] < b.h[1] ? (b.h[0] < b.h[2] ? b.h[0] : b.h[2]) : (b.h[1] < b.h[2] ? b.h[1] : b.h[2]);
-    h.exact = !(hm >= R2 * (1.0 + 4e-6));
-    return h;
-}
-
 // exp arguments are affine in r: -2q(r/r0-1) = qa r + qb, -p(r/r0-1) = pa r + pb
 static RjlC rjl_consts(const RJLp& P) {
     RjlC c;
@@ -153,93 +140,130 @@ static RjlC rjl_consts(const RJLp& P) {
     return c;
 }
 
-// Both kernels are software-pipelined by hand: the row index for slot p+2 and the position record for
-// slot p+1 are requested before the arithmetic of slot p, so a warp keeps two dependent memory levels
-// (index -> gather) in flight under ~100 FP64 instructions of work.
+// Both kernels are software-pipelined by hand, two slots per trip with ping-pong registers: the row
+// indices are requested two to three slots ahead and each 32-byte record one slot ahead of its use,
+// so a warp keeps both dependent memory levels (index -> gather) in flight under ~100 FP64
+// instructions of work, without register-rotation moves.
+// Minimum image: if the largest |d_k| high word is below the high word of the smallest half-box no
+// component can need wrapping (exact, the comparison is conservative); otherwise the exact FP64 test of
+// find_distance runs.  Only atoms within r_cut of a face ever take the second path.
 #ifndef RJL_MINB
 #define RJL_MINB 6
 #endif
-template <bool E, bool EXACT>
-__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, HalfHi H, double* part) {
+struct WrapC { int min_half_hi; };
+static WrapC wrap_consts(const BoxD& b) {
+    double hm = b.h[0] < b.h[1] ? (b.h[0] < b.h[2] ? b.h[0] : b.h[2]) : (b.h[1] < b.h[2] ? b.h[1] : b.h[2]);
+    long long v;
+    memcpy(&v, &hm, 8);
+    WrapC w;
+    w.min_half_hi = (int)(v >> 32);
+    return w;
+}
+__device__ __forceinline__ void wrap3(double& dx, double& dy, double& dz, const BoxD& box, int min_half_hi) {
+    int m = max(max(__double2hiint(dx) & 0x7fffffff, __double2hiint(dy) & 0x7fffffff), __double2hiint(dz) & 0x7fffffff);
+    if (m >= min_half_hi) {
+        dx = min_image(dx, box.h[0], box.L[0]);
+        dy = min_image(dy, box.h[1], box.L[1]);
+        dz = min_image(dz, box.h[2], box.L[2]);
+    }
+}
+
+template <bool E>
+__device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& sq, double& sp) {
+    double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+    wrap3(dx, dy, dz, box, mhh);
+    double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    if (r2 < C.R22) {
+        double r = r2 * mx::rsqrt_fast(r2);
+        double eq = mx::exp_nc(fma(C.qa, r, C.qb));
+        double f = 1.0;
+        if (r2 >= C.R12) {
+            double s;
+            mx::cos_switch((r - C.R1) * C.sw, f, s);
+        }
+        sq = fma(eq, f, sq);
+        if (E) sp = fma(mx::exp_nc(fma(C.pa, r, C.pb)), f, sp);
+    }
+}
+template <bool E>
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
-        const double2 pxy = *reinterpret_cast<const double2*>(&pos[i]);
-        const double pz = reinterpret_cast<const double*>(&pos[i])[2];
+        // The .w of every record is being written by this kernel (1/Eb of its owner) while x,y,z are
+        // constant: the whole record is fetched with one request and .w is ignored here.
+        const double4 pi = ld256(&pos[i]);
         double sq = 0, sp = 0;
-        const int* row = lv.nlist + i;
-        int jn = row[0];
-        int jnn = n > 1 ? row[lv.stride] : jn;
-        // x,y and z only: .w of every record is being written by this kernel
-        double2 nxy = *reinterpret_cast<const double2*>(&pos[jn]);
-        double nz = reinterpret_cast<const double*>(&pos[jn])[2];
-        for (int p = 0; p < n; ++p) {
-            const double2 qxy = nxy;
-            const double qz = nz;
-            nxy = *reinterpret_cast<const double2*>(&pos[jnn]);
-            nz = reinterpret_cast<const double*>(&pos[jnn])[2];
-            if (p + 2 < n) jnn = row[(size_t)(p + 2) * lv.stride];
-            double dx = qxy.x - pxy.x, dy = qxy.y - pxy.y, dz = qz - pz;
-            if (EXACT) { dx = min_image(dx, box.h[0], box.L[0]); dy = min_image(dy, box.h[1], box.L[1]); dz = min_image(dz, box.h[2], box.L[2]); }
-            else { dx = min_image_fast(dx, H.x, box.L[0]); dy = min_image_fast(dy, H.y, box.L[1]); dz = min_image_fast(dz, H.z, box.L[2]); }
-            double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            if (r2 < C.R22) {
-                double r = r2 * mx::rsqrt_fast(r2);
-                double eq = mx::exp_nc(fma(C.qa, r, C.qb));
-                double f = 1.0;
-                if (r2 >= C.R12) {
-                    double s;
-                    mx::cos_switch((r - C.R1) * C.sw, f, s);
-                }
-                sq = fma(eq, f, sq);
-                if (E) sp = fma(mx::exp_nc(fma(C.pa, r, C.pb)), f, sp);
-            }
+        const int* rp = lv.nlist + i;
+        const size_t st = lv.stride;
+        int j1 = n > 1 ? rp[st] : rp[0];
+        double4 a = ld256(&pos[rp[0]]);
+        int p = 0;
+        for (; p + 1 < n; p += 2) {
+            double4 b = ld256(&pos[j1]);
+            int j2 = p + 2 < n ? rp[2 * st] : j1;
+            int j3 = p + 3 < n ? rp[3 * st] : j1;
+            rp += 2 * st;
+            rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, sq, sp);
+            a = ld256(&pos[j2]);
+            rjl_density_pair<E>(pi, b, C, box, W.min_half_hi, sq, sp);
+            j1 = j3;
         }
+        if (p < n) rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, sq, sp);
         double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
         reinterpret_cast<double*>(&pos[i])[3] = ie;
         if (E) e = C.A0 * sp - C.xi * (sq * ie);
     }
     if (E) store_partial(e, part);
 }
-template <bool EXACT>
+
+__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                               double& fz) {
+    double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+    wrap3(dx, dy, dz, box, mhh);
+    double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    if (r2 < C.R22) {
+        double ir = mx::rsqrt_fast(r2);
+        double r = r2 * ir;
+        double ep = mx::exp_nc(fma(C.pa, r, C.pb)), eq = mx::exp_nc(fma(C.qa, r, C.qb));
+        double ies = pi.w + pj.w;
+        double c;
+        if (r2 < C.R12) {
+            c = (C.a1 * ep - C.a2 * ies * eq) * ir;
+        } else {
+            double f, s;
+            mx::cos_switch((r - C.R1) * C.sw, f, s);
+            double dfr_r = -s * C.pi_sw;  // f_c'(r) = df_cut * r
+            c = (2. * C.A0 * (-C.pa * f - dfr_r) * ep - C.xi * (-0.5 * C.qa * f - 0.5 * dfr_r) * ies * eq) * ir;
+        }
+        fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
+    }
+}
 __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
-                                                            HalfHi H) {
+                                                            WrapC W) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int n = lv.nnum[i];
     if (n == 0) return;
-    const double4 pi = pos[i];
+    const double4 pi = ld256_nc(&pos[i]);
     double fx = 0, fy = 0, fz = 0;
-    const int* row = lv.nlist + i;
-    int jn = row[0];
-    int jnn = n > 1 ? row[lv.stride] : jn;
-    double4 pn = pos[jn];
-    for (int p = 0; p < n; ++p) {
-        const double4 pj = pn;
-        pn = pos[jnn];
-        if (p + 2 < n) jnn = row[(size_t)(p + 2) * lv.stride];
-        double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-        if (EXACT) { dx = min_image(dx, box.h[0], box.L[0]); dy = min_image(dy, box.h[1], box.L[1]); dz = min_image(dz, box.h[2], box.L[2]); }
-        else { dx = min_image_fast(dx, H.x, box.L[0]); dy = min_image_fast(dy, H.y, box.L[1]); dz = min_image_fast(dz, H.z, box.L[2]); }
-        double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        if (r2 < C.R22) {
-            double ir = mx::rsqrt_fast(r2);
-            double r = r2 * ir;
-            double ep = mx::exp_nc(fma(C.pa, r, C.pb)), eq = mx::exp_nc(fma(C.qa, r, C.qb));
-            double ies = pi.w + pj.w;
-            double c;
-            if (r2 < C.R12) {
-                c = (C.a1 * ep - C.a2 * ies * eq) * ir;
-            } else {
-                double f, s;
-                mx::cos_switch((r - C.R1) * C.sw, f, s);
-                double dfr_r = -s * C.pi_sw;  // f_c'(r) = df_cut * r
-                c = (2. * C.A0 * (-C.pa * f - dfr_r) * ep - C.xi * (-0.5 * C.qa * f - 0.5 * dfr_r) * ies * eq) * ir;
-            }
-            fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
-        }
+    const int* rp = lv.nlist + i;
+    const size_t st = lv.stride;
+    int j1 = n > 1 ? rp[st] : rp[0];
+    double4 a = ld256_nc(&pos[rp[0]]);
+    int p = 0;
+    for (; p + 1 < n; p += 2) {
+        double4 b = ld256_nc(&pos[j1]);
+        int j2 = p + 2 < n ? rp[2 * st] : j1;
+        int j3 = p + 3 < n ? rp[3 * st] : j1;
+        rp += 2 * st;
+        rjl_force_pair(pi, a, C, box, W.min_half_hi, fx, fy, fz);
+        a = ld256_nc(&pos[j2]);
+        rjl_force_pair(pi, b, C, box, W.min_half_hi, fx, fy, fz);
+        j1 = j3;
     }
+    if (p < n) rjl_force_pair(pi, a, C, box, W.min_half_hi, fx, fy, fz);
     add_force(frc, i, fx, fy, fz);
 }
 
@@ -513,17 +537,9 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
     case K_RJL:
     {
         const RjlC C = rjl_consts(it.rjl);
-        const HalfHi H = half_hi_of(c->box, it.rjl.R2);
-        {
-            KTimer kt(c, KS_RJL_DENSITY);
-            if (H.exact) k_rjl_density<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, H, nullptr);
-            else k_rjl_density<false, false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, H, nullptr);
-        }
-        {
-            KTimer kt(c, KS_RJL_FORCE);
-            if (H.exact) k_rjl_force<true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, H);
-            else k_rjl_force<false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, H);
-        }
+        const WrapC W = wrap_consts(c->box);
+        { KTimer kt(c, KS_RJL_DENSITY); k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr); }
+        { KTimer kt(c, KS_RJL_FORCE); k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W); }
     }
         c->launches += 2;
         break;
@@ -561,9 +577,7 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     case K_LJ: k_lj<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
     case K_LJ1G: k_lj1g<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
     case K_RJL: {
-        const HalfHi H = half_hi_of(c->box, it.rjl.R2);
-        if (H.exact) k_rjl_density<true, true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, H, c->part);
-        else k_rjl_density<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, H, c->part);
+        k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
         break;
     }
     case K_TB:
