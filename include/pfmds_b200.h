@@ -128,6 +128,10 @@ int pfmds_timer_stop(pfmds_ctx* ctx, double* ms);
 /* Roofline denominators measured on the device: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s). */
 int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs);
 
+/* Device self-test of the library's FP64 elementary functions against the CUDA math library: max errors
+ * [0] exp (relative), [1] cosine switch / sincos (absolute), [2] rsqrt (relative), [3] hardware rsqrt seed. */
+int pfmds_selftest_math(int device, double err[4]);
+
 /* Number of kernel launches issued so far by this context and device-time of the last advance (ms). */
 int pfmds_launch_count(pfmds_ctx* ctx, long long* launches);
 

@@ -274,6 +274,34 @@ __global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, doubl
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 12345.678) out[0] = s;
 }
+// device self-test of mathx.cuh against the CUDA math library: max errors over a sweep
+__global__ void k_math_selftest(int n, double* out) {
+    double e_exp = 0, e_sw = 0, e_rs = 0, e_seed = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double u = (i + 0.5) / n;
+        double x = -600. + 1200. * u;
+        double a = exp(x), b = mx::exp_nc(x);
+        e_exp = fmax(e_exp, fabs(a - b) / a);
+        b = mx::exp_fast(x);
+        e_exp = fmax(e_exp, fabs(a - b) / a);
+        double ang = 3.14159265358979 * u, f, s, sr, cr;
+        mx::cos_switch(ang, f, s);
+        sincos(ang, &sr, &cr);
+        e_sw = fmax(e_sw, fmax(fabs(f - (1. + cr) / 2), fabs(s - sr)));
+        mx::sincos_0pi(ang, s, f);
+        e_sw = fmax(e_sw, fmax(fabs(f - cr), fabs(s - sr)));
+        double v = exp(-20. + 40. * u);
+        e_rs = fmax(e_rs, fabs(mx::rsqrt_fast(v) * sqrt(v) - 1.));
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+        e_seed = fmax(e_seed, fabs(y * sqrt(v) - 1.));
+    }
+    // order-independent max through the bit pattern (all values are non-negative)
+    atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(e_exp));
+    atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(e_sw));
+    atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(e_rs));
+    atomicMax((unsigned long long*)&out[3], (unsigned long long)__double_as_longlong(e_seed));
+}
 __global__ void k_copy(size_t n, const double4* __restrict__ a, double4* __restrict__ b) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
 }
@@ -675,6 +703,21 @@ int pfmds_timer_stop(pfmds_ctx* c, double* ms) {
         *ms = f;
         check_device_error(c);
     });
+}
+
+// Max errors of the device elementary functions: [0] exp relative, [1] switch/sincos absolute,
+// [2] rsqrt relative, [3] raw MUFU.RSQ64H seed relative.
+int pfmds_selftest_math(int device, double err[4]) {
+    try {
+        CK(cudaSetDevice(device));
+        double* d = nullptr;
+        CK(cudaMalloc(&d, 4 * sizeof(double)));
+        CK(cudaMemset(d, 0, 4 * sizeof(double)));
+        k_math_selftest<<<256, 256>>>(1 << 22, d);
+        CK(cudaMemcpy(err, d, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        return PFMDS_OK;
+    } catch (...) { return PFMDS_ERR_CUDA; }
 }
 
 // FP64 FMA peak (TFLOP/s) and device-to-device copy bandwidth (GB/s, read+write) of `device`.

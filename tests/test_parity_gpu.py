@@ -133,3 +133,94 @@ def test_refuses_what_the_reference_gets_wrong_silently():
     with pytest.raises(PfmdsError) as ei:
         g.advance("nve", 1.0, 0, 1)
     assert ei.value.code == 20
+
+
+def test_device_math_functions():
+    """mathx.cuh on the device (constant-bank exp, select-free cosine switch, MUFU-seeded rsqrt) against the CUDA math library."""
+    import ctypes as C
+    from pfmds_b200.engine import load_library
+    lib = load_library()
+    err = (C.c_double * 4)()
+    lib.pfmds_selftest_math.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    assert lib.pfmds_selftest_math(0, err) == 0
+    print("device math errors: exp %.2e switch %.2e rsqrt %.2e seed %.2e" % tuple(err))
+    assert err[0] < 3e-14 and err[1] < 1e-15 and err[2] < 1e-15
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_gpu_matches_golden_fixtures(name):
+    """Against the committed fixtures (tests/golden/, frozen oracle outputs): lists bit-exact, forces/energies 1e-9."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    case = CASES[name]
+    e = gpu(case)
+    integ, dt = case["integrators"][0][0], case["integrators"][0][1]
+    e.advance(integ, dt, 0, 1)
+    assert rel_err(e.download()[2], g["frc0"]) < RTOL
+    assert np.allclose(e.energies()[0], g["e0"], rtol=RTOL, atol=0)
+    for k, j in list_ids(case):
+        nl = neighbours(e, case, k, j)
+        assert np.array_equal(nl[1], g["nnum_%d_%d" % (k, j)]) and np.array_equal(nl[0], g["nlist_%d_%d" % (k, j)])
+    e.advance(integ, dt, 1, 10)
+    p, v, f = e.download()
+    assert np.abs(p - g["pos10"]).max() < 1e-10 and rel_err(f, g["frc10"]) < 1e-8
+
+
+def test_upload_restarts_a_context():
+    case = small_cases()["cu_fcc"]
+    a, b = gpu(case), gpu(case)
+    a.advance("nve", 2.0, 0, 11)
+    p, v, _ = a.download()
+    b.advance("nve", 2.0, 0, 1)
+    b.upload(p, v)
+    b.advance("nve", 2.0, 0, 1)   # step 0: lists + forces on the uploaded state
+    a.advance("nve", 2.0, 0, 1)
+    assert rel_err(b.download()[2], a.download()[2]) < 1e-12
+
+
+def test_multi_step_advance_equals_single_steps():
+    case = small_cases()["gr_cu_morsec"]
+    a, b = gpu(case), gpu(case)
+    a.advance("nvt", 1.0, 0, 13)
+    for s in range(13):
+        b.advance("nvt", 1.0, s, 1)
+    pa, va, fa = a.download()
+    pb, vb, fb = b.download()
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(fa, fb)  # bitwise: fixed-order reductions
+
+
+def test_two_contexts_share_a_gpu():
+    """Ensemble mode: independent contexts (own streams) on one device do not interfere."""
+    c1, c2 = small_cases()["cu_fcc"], small_cases()["ab_gas"]
+    a, b, ref = gpu(c1), gpu(c2), gpu(c1)
+    for s in range(6):
+        a.advance("nvt", 2.0, s, 1)
+        b.advance("nve", 0.5, s, 1)
+    ref.advance("nvt", 2.0, 0, 6)
+    assert np.array_equal(a.download()[0], ref.download()[0])
+
+
+def test_full_size_properties_cu_fcc():
+    """BASELINE.json configs[1] at full size (1 000 188 atoms, no oracle at this size): size-independent properties.
+    sum F = 0 (Newton 3), perfect-lattice neighbour count 86, extended energy conserved, momentum stays zero."""
+    from pfmds_b200 import inputs
+    case = inputs.cu_fcc(ncell=63)
+    e = gpu(case)
+    e.advance("nvt", 2.0, 0, 1)
+    fs, mc, mcv, vmax, load = e.diagnostics()
+    f = e.download()[2]
+    assert np.abs(fs).max() < 1e-9 and np.abs(f).max() < 1e-9      # perfect fcc lattice: every force vanishes
+    assert load[0] == 86 and e.pair_count(0, 0) == 86 * e.n        # shells within 6.5 A: 12+6+24+12+24+8
+    en0 = e.energies()
+    c0 = en0[0].sum() + en0[1] + en0[3].sum()
+    assert abs(en0[2] - 300.0) < 1e-6                               # generator rescales to exactly 300 K
+    small = inputs.cu_fcc(ncell=4)                                  # perfect lattice: energy per atom is size independent
+    o = oracle(small)
+    o.advance("nvt", 2.0, 0, 1)
+    assert abs(en0[0][0] / e.n - o.energies()[0][0] / len(small["mass"])) < 1e-10 * abs(en0[0][0] / e.n)
+    e.advance("nvt", 2.0, 1, 40)
+    en1 = e.energies()
+    c1 = en1[0].sum() + en1[1] + en1[3].sum()
+    assert abs(c1 - c0) < 2e-3 * en0[1]
+    fs, mc, mcv, vmax, load = e.diagnostics()
+    assert np.abs(fs).max() < 1e-7 and np.linalg.norm(mcv) < 1e-12
