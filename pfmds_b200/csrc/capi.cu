@@ -141,13 +141,31 @@ void finalize(pfmds_ctx* c) {
         t.L = (int)group_of(c, t.group).size();
         if (t.L < 1) fail(PFMDS_ERR_NHC_PARAMS, "error: wrong nhc parameters");
         // q(i) = q(1)/(3L), i >= 2  (md_integrators.f90:192-195)
-        std::vector<double> st((size_t)3 * t.M + 2, 0.);
+        std::vector<double> st((size_t)3 * t.M + 4, 0.);
         double q1;
         CK(cudaMemcpy(&q1, t.state + 2 * t.M, sizeof(double), cudaMemcpyDeviceToHost));
         st[2 * (size_t)t.M] = q1;
         for (int i = 1; i < t.M; ++i) st[2 * (size_t)t.M + i] = q1 / (3. * t.L);
         st[3 * (size_t)t.M] = 1.;
+        st[3 * (size_t)t.M + 2] = 1.;
         CK(cudaMemcpy(t.state, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+    }
+    {   // fused NVT path needs pairwise disjoint thermostat groups
+        uint32_t seen = 0;
+        bool ok = !c->nhc.empty() && c->nhc.size() <= NHC_MAXF;
+        std::vector<uint32_t> cover((size_t)N, 0u);
+        for (size_t k = 0; ok && k < c->nhc.size(); ++k) {
+            uint32_t b = 1u << (c->nhc[k].group - 1);
+            if (seen & b) ok = false;
+            seen |= b;
+        }
+        if (ok)
+            for (size_t i = 0; i < (size_t)N && ok; ++i) {
+                int cnt = 0;
+                for (auto& t : c->nhc) cnt += (c->h_gmask[i] >> (t.group - 1)) & 1u;
+                if (cnt > 1) ok = false;
+            }
+        c->nhc_fusable = ok;
     }
     CK(cudaMemcpyAsync(c->gmask, c->h_gmask.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, c->st));
     if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
@@ -201,9 +219,15 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call) {
         if (first_of_call) integ_check_positions(c);
         if (c->invert_z) integ_invert_z(c);
         if (step != 0) {
-            if (kind == PFMDS_NVT)
-                for (auto& th : c->nhc) integ_nhc_half(c, th, dt);
-            integ_kick_drift(c, dt);
+            if (kind == PFMDS_NVT && c->nhc_fusable && c->nhc_ke_valid) {
+                integ_nvt_open_kick_drift(c, dt);  // consumes the pending closing scale of the previous step
+                c->nhc_pending = false;
+            } else {
+                integ_flush_pending(c);
+                if (kind == PFMDS_NVT)
+                    for (auto& th : c->nhc) integ_nhc_half(c, th, dt);
+                integ_kick_drift(c, dt);
+            }
         }
     }
     {
@@ -218,10 +242,17 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call) {
     }
     if (step != 0) {
         PhaseTimer t(c, 0);
-        integ_kick(c, dt);
-        if (kind == PFMDS_NVT)
-            for (auto& th : c->nhc) integ_nhc_half(c, th, dt);
-        if (kind == PFMDS_NVMS) integ_quench(c);
+        if (kind == PFMDS_NVT && c->nhc_fusable) {
+            integ_nvt_kick_close(c, dt);
+            c->nhc_pending = true;
+            c->nhc_ke_valid = true;
+        } else {
+            integ_kick(c, dt);
+            if (kind == PFMDS_NVT)
+                for (auto& th : c->nhc) integ_nhc_half(c, th, dt);
+            if (kind == PFMDS_NVMS) integ_quench(c);
+            c->nhc_ke_valid = false;
+        }
     }
 }
 
@@ -389,8 +420,8 @@ int pfmds_add_nhc(pfmds_ctx* c, int g, double T, int M, double q1) {
         if (c->finalized) fail(PFMDS_ERR_INVALID, "error: thermostats must be defined before the first pfmds_advance");
         if (M < 1 || q1 < 0. || T < 0.) fail(PFMDS_ERR_NHC_PARAMS, "error: wrong nhc parameters");  // md_integrators.f90:187
         Nhc t; t.group = g; t.M = M; t.temperature = T;
-        CK(cudaMalloc(&t.state, sizeof(double) * ((size_t)3 * M + 2)));
-        std::vector<double> st((size_t)3 * M + 2, 0.);
+        CK(cudaMalloc(&t.state, sizeof(double) * ((size_t)3 * M + 4)));
+        std::vector<double> st((size_t)3 * M + 4, 0.);
         st[2 * (size_t)M] = q1;
         CK(cudaMemcpy(t.state, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
         c->nhc.push_back(t);
@@ -458,6 +489,7 @@ int pfmds_energies(pfmds_ctx* c, double* e_inter, double* ke, double* temp, doub
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
         finalize(c);
+        integ_flush_pending(c);
         {
             PhaseTimer t(c, 5);
             for (size_t k = 0; k < c->inter.size(); ++k) energy_interaction(c, (int)k);
@@ -494,6 +526,7 @@ int pfmds_diagnostics(pfmds_ctx* c, double fs[3], double mc[3], double mcv[3], d
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
         finalize(c);
+        integ_flush_pending(c);
         integ_diagnostics(c, c->red + 32);
         size_t nl_total = 0;
         for (auto& it : c->inter) nl_total += (size_t)it.nl_n;
@@ -526,6 +559,7 @@ int pfmds_download(pfmds_ctx* c, double* pos, double* vel, double* frc) {
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
         const size_t N = (size_t)c->N;
+        integ_flush_pending(c);
         std::vector<int> ho(N);
         std::vector<double4> buf(N);
         CK(cudaMemcpyAsync(ho.data(), c->orig, sizeof(int) * N, cudaMemcpyDeviceToHost, c->st));
@@ -630,6 +664,8 @@ int pfmds_upload(pfmds_ctx* c, const double* pos, const double* vel) {
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
         const size_t n3 = 3 * (size_t)c->N;
+        integ_flush_pending(c);
+        c->nhc_ke_valid = false;
         double *dp = nullptr, *dv = nullptr;
         if (pos) { CK(cudaMallocAsync(&dp, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
         if (vel) { CK(cudaMallocAsync(&dv, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }

@@ -104,4 +104,7 @@ struct MORp { double d, r, a, delt, R1, R2; int simplified; };           // mors
 struct TBp { double d, s, b, r0, delt, a0, c02, d02, R1, R2; };
 struct RJLp { double A0, xi, p, q, r0, R1, R2; };
 
+#define NHC_MAXF 4
+struct NhcPack { int n; uint32_t bit[NHC_MAXF]; double* state[NHC_MAXF]; int M[NHC_MAXF]; int L[NHC_MAXF]; double T[NHC_MAXF]; };
+
 struct ListView { const int* nlist; const int* nnum; size_t stride; };

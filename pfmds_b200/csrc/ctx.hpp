@@ -70,6 +70,10 @@ struct pfmds_ctx {
     std::vector<Inter> inter;
     std::vector<Nhc> nhc;
     bool finalized = false;
+    // fused NVT path (integrate.cu): usable when the thermostat groups are pairwise disjoint
+    bool nhc_fusable = false;
+    bool nhc_ke_valid = false;  // state[3M+1] holds the current kinetic energy of each thermostat group
+    bool nhc_pending = false;   // state[3M+2] holds a velocity scale that has not been applied yet
     long long launches = 0;
     std::string err_msg;
     // phase timers (PFMDS_TIMERS=1)
@@ -123,7 +127,9 @@ void integ_kick_drift(pfmds_ctx* c, double dt);
 void integ_kick(pfmds_ctx* c, double dt);
 void integ_quench(pfmds_ctx* c);
 void integ_zero_momentum(pfmds_ctx* c);
-void integ_nhc_energy(pfmds_ctx* c, Nhc& t);
+void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt);
+void integ_nvt_kick_close(pfmds_ctx* c, double dt);
+void integ_flush_pending(pfmds_ctx* c);
 // out[0]=KE(group) ; group sums for diagnostics: out[0..2]=sum F, [3..5]=sum m x, [6..8]=sum m v, [9]=sum m, [10]=max v^2
 void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out);
 void integ_diagnostics(pfmds_ctx* c, double* d_out);

@@ -64,13 +64,8 @@ void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out) {
 }
 
 // ---- Nose-Hoover chain half step: md_integrators.f90:200-245 ---------------------------------------
-// state = x[M], v[M], q[M], s.  One block sums the KE partials (fixed order), thread 0 runs the chain.
-__global__ void k_nhc(int nparts, const double* __restrict__ part, double* state, int M, int L, double temperature, double ts2, double ts3,
-                      double ts4) {
-    double ke = 0;
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i];
-    ke = block_sum(ke);
-    if (threadIdx.x != 0) return;
+// state = x[M], v[M], q[M], s, ke_cached, s_pending.  Returns the velocity scale s = exp(-v1 dt/2).
+__device__ double nhc_chain(double* state, int M, int L, double temperature, double ke, double ts2, double ts3, double ts4) {
     double* x = state;
     double* v = state + M;
     const double* q = state + 2 * M;
@@ -101,6 +96,17 @@ __global__ void k_nhc(int nparts, const double* __restrict__ part, double* state
         }
         v[M - 1] = v[M - 1] + (q[M - 2] * v[M - 2] * v[M - 2] - kt) / q[M - 1] * ts3;
     }
+    state[3 * M + 1] = ke * (s * s);  // kinetic energy of the group after the scaling
+    return s;
+}
+// One block sums the KE partials (fixed order), thread 0 runs the chain.
+__global__ void k_nhc(int nparts, const double* __restrict__ part, double* state, int M, int L, double temperature, double ts2, double ts3,
+                      double ts4) {
+    double ke = 0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i];
+    ke = block_sum(ke);
+    if (threadIdx.x != 0) return;
+    nhc_chain(state, M, L, temperature, ke, ts2, ts3, ts4);
 }
 // scale_velocities, md_general.f90:96-112
 __global__ void k_scale(int N, double4* __restrict__ vel, const uint32_t* __restrict__ gmask, uint32_t bit, const double* __restrict__ s_ptr) {
@@ -273,4 +279,137 @@ void integ_zero_momentum(pfmds_ctx* c) {
     integ_diagnostics(c, c->red + 16);
     k_sub_mcv<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, 1u << (c->all_atoms - 1), c->red + 16);
     c->launches += 1;
+}
+
+// ---- fused NVT path (thermostat groups pairwise disjoint, at most NHC_MAXF of them) ------------------
+// The reference sums the kinetic energy twice per step (opening and closing half step).  Nothing but the
+// closing scale changes the velocities between the closing chain update of step n and the opening one of
+// step n+1 (invert_z only flips signs), so the opening KE is s_c^2 KE_c analytically: one reduction per
+// step, fused into the closing kick; the two scalings are folded into the next kick+drift as one factor.
+//   k_nhc_open  (1 thread / thermostat)  chain update with the cached KE  -> s_pending *= s_o
+//   k_kick_drift                         v *= s_pending, kick, drift            (pending := 1 implicitly)
+//   k_kick_ke                            closing kick + per-thermostat KE partials
+//   k_nhc_close (1 block)                fixed-order sum, chain update         -> s_pending = s_c
+__global__ void k_nhc_open(NhcPack P, double ts2, double ts3, double ts4) {
+    int k = threadIdx.x;
+    if (k >= P.n) return;
+    double* st = P.state[k];
+    int M = P.M[k];
+    double s = nhc_chain(st, M, P.L[k], P.T[k], st[3 * M + 1], ts2, ts3, ts4);
+    st[3 * M + 2] *= s;
+}
+__global__ void __launch_bounds__(IT) k_kick_drift_nvt(int N, double4* __restrict__ pos, double4* __restrict__ vel, const double4* __restrict__ frc,
+                                                       const uint32_t* __restrict__ gmask, const int* __restrict__ orig, uint32_t bxyz, uint32_t bz,
+                                                       double ts1, double ts2, BoxD box, NhcPack P, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t g = gmask[i];
+    bool mx = g & bxyz, mz = g & bz;
+    double sc = 1.0;
+    bool th = false;
+    for (int k = 0; k < P.n; ++k)
+        if (g & P.bit[k]) { sc = P.state[k][3 * P.M[k] + 2]; th = true; }
+    if (!mx && !mz && !th) return;
+    double4 v = vel[i];
+    v.x *= sc; v.y *= sc; v.z *= sc;
+    if (mx || mz) {
+        double4 p = pos[i], f = frc[i];
+        if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
+        if (mx) {
+            v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
+            v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
+            v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+        }
+        if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+        if (mx) {
+            p.x = p.x + v.x * ts1; if (p.x > box.L[0]) p.x = p.x - box.L[0]; else if (p.x < 0.) p.x = p.x + box.L[0];
+            p.y = p.y + v.y * ts1; if (p.y > box.L[1]) p.y = p.y - box.L[1]; else if (p.y < 0.) p.y = p.y + box.L[1];
+            p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2];
+        }
+        if (mz) { p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2]; }
+        pos[i] = p;
+    }
+    vel[i] = v;
+}
+__global__ void k_reset_pending(NhcPack P) {
+    int k = threadIdx.x;
+    if (k < P.n) P.state[k][3 * P.M[k] + 2] = 1.0;
+}
+__global__ void __launch_bounds__(IT) k_kick_ke(int N, double4* __restrict__ vel, const double4* __restrict__ frc, const uint32_t* __restrict__ gmask,
+                                                uint32_t bxyz, uint32_t bz, double ts2, NhcPack P, double* __restrict__ part) {
+    double ke[NHC_MAXF];
+    for (int k = 0; k < NHC_MAXF; ++k) ke[k] = 0.;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        uint32_t g = gmask[i];
+        bool mx = g & bxyz, mz = g & bz;
+        bool th = false;
+        for (int k = 0; k < P.n; ++k) th |= (g & P.bit[k]) != 0;
+        if (!mx && !mz && !th) continue;
+        double4 v = vel[i];
+        if (mx || mz) {
+            double4 f = frc[i];
+            if (mx) {
+                v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
+                v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
+                v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+            }
+            if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+            vel[i] = v;
+        }
+        double e = v.w * (v.x * v.x + v.y * v.y + v.z * v.z) / 2 * PFMDS_MASS_COEF;
+        for (int k = 0; k < P.n; ++k)
+            if (g & P.bit[k]) ke[k] += e;
+    }
+    for (int k = 0; k < P.n; ++k) {
+        double s = block_sum(ke[k]);
+        if (threadIdx.x == 0) part[blockIdx.x * NHC_MAXF + k] = s;
+    }
+}
+__global__ void k_nhc_close(int nparts, const double* __restrict__ part, NhcPack P, double ts2, double ts3, double ts4) {
+    for (int k = 0; k < P.n; ++k) {
+        double ke = 0;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i * NHC_MAXF + k];
+        ke = block_sum(ke);
+        if (threadIdx.x == 0) {
+            double* st = P.state[k];
+            int M = P.M[k];
+            double s = nhc_chain(st, M, P.L[k], P.T[k], ke, ts2, ts3, ts4);
+            st[3 * M + 2] = s;
+        }
+        __syncthreads();
+    }
+}
+static NhcPack pack_of(pfmds_ctx* c) {
+    NhcPack P{};
+    P.n = (int)c->nhc.size();
+    for (int k = 0; k < P.n; ++k) {
+        P.bit[k] = 1u << (c->nhc[k].group - 1); P.state[k] = c->nhc[k].state; P.M[k] = c->nhc[k].M; P.L[k] = c->nhc[k].L; P.T[k] = c->nhc[k].temperature;
+    }
+    return P;
+}
+void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt) {
+    NhcPack P = pack_of(c);
+    KTimer kt(c, KS_KICK_DRIFT);
+    k_nhc_open<<<1, 32, 0, c->st>>>(P, dt / 2, dt / 4, dt / 8);
+    k_kick_drift_nvt<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
+                                                             1u << (c->z_moving - 1), dt, dt / 2, c->box, P, c->err);
+    k_reset_pending<<<1, 32, 0, c->st>>>(P);
+    c->launches += 3;
+}
+void integ_nvt_kick_close(pfmds_ctx* c, double dt) {
+    NhcPack P = pack_of(c);
+    KTimer kt(c, KS_KICK);
+    k_kick_ke<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2, P, c->part);
+    k_nhc_close<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
+    c->launches += 2;
+}
+// apply scalings that are still pending (before anything else reads or changes velocities)
+void integ_flush_pending(pfmds_ctx* c) {
+    if (!c->nhc_pending) return;
+    NhcPack P = pack_of(c);
+    for (int k = 0; k < P.n; ++k)
+        k_scale<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, P.bit[k], P.state[k] + 3 * P.M[k] + 2);
+    k_reset_pending<<<1, 32, 0, c->st>>>(P);
+    c->launches += P.n + 1;
+    c->nhc_pending = false;
 }
