@@ -206,7 +206,7 @@ void update_lists(pfmds_ctx* c, int step) {
                 NList& l = it.nl[j];
                 if (!((step % l.period == 0) || !l.built)) continue;
                 if (l.from_tb) nl_nearest3_from(c, l, c->inter[(size_t)l.src_inter].nl[0]);
-                else { nl_build(c, l); nl_partition(c, l); }
+                else nl_build(c, l);
             }
         }
     }
@@ -376,6 +376,7 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         CK(cudaMalloc(&c->gmask, sizeof(uint32_t) * S)); CK(cudaMalloc(&c->gmask2, sizeof(uint32_t) * S));
         CK(cudaMalloc(&c->orig, sizeof(int) * S)); CK(cudaMalloc(&c->orig2, sizeof(int) * S));
         CK(cudaMalloc(&c->cell_atoms, sizeof(int) * S)); CK(cudaMalloc(&c->cid, sizeof(int) * S));
+        CK(cudaMalloc(&c->posf, sizeof(float4) * S));
         size_t nparts = (S + 127) / 128 + RED_BLOCKS;
         CK(cudaMalloc(&c->part, sizeof(double) * 16 * nparts));
         CK(cudaMalloc(&c->red, sizeof(double) * 64));
@@ -827,7 +828,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     }
     for (auto& t : c->nhc) cudaFree(t.state);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,
-                    c->cid, c->scan_tmp, c->part, c->red, c->energy, c->err};
+                    c->cid, c->posf, c->scan_tmp, c->part, c->red, c->energy, c->err};
     for (void* p : ptrs) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -49,6 +49,7 @@ struct pfmds_ctx {
     // state, double-buffered for the cell re-sort
     double4 *pos = nullptr, *vel = nullptr, *frc = nullptr, *pos2 = nullptr, *vel2 = nullptr;
     uint32_t *gmask = nullptr, *gmask2 = nullptr;
+    float4* posf = nullptr;  // float copy of the positions + group mask, for the list-build prefilter
     int *orig = nullptr, *orig2 = nullptr;
     // cell grid
     int ncell[3]{1, 1, 1};
@@ -111,7 +112,6 @@ void nl_setup_grid(pfmds_ctx* c);
 void nl_bin_atoms(pfmds_ctx* c, bool reorder);
 void nl_build(pfmds_ctx* c, NList& l);
 void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src);
-void nl_partition(pfmds_ctx* c, NList& l);
 
 // ---- forces.cu ----
 void forces_zero(pfmds_ctx* c);

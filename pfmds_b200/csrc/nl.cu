@@ -47,6 +47,7 @@ void nl_setup_grid(pfmds_ctx* c) {
 }
 
 struct GridD { int n[3]; double inv[3]; };
+__global__ void k_make_posf(int N, const double4* __restrict__ pos, const uint32_t* __restrict__ gmask, float4* __restrict__ posf);
 
 __device__ __forceinline__ int cell_coord(double x, double inv, int n) {
     int c = (int)floor(x * inv);
@@ -178,28 +179,45 @@ void nl_bin_atoms(pfmds_ctx* c, bool reorder) {
     } else {
         c->identity_order = false;
     }
+    k_make_posf<<<nb, T, 0, c->st>>>(N, c->pos, c->gmask, c->posf);
+    c->launches += 1;
     CK(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------------
 // One thread per list-owner atom walks the 27 (or fewer, for boxes under three cells wide) cells
-// around it.  dr2 uses __dmul_rn/__dadd_rn so the compiler cannot contract it into FMAs: the set
-// {j : dr2 < rc2} is then bit-identical to the reference's brute-force scan.
-template <bool IDENT>
-__global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict__ pos, const uint32_t* __restrict__ gmask,
-                                               const int* __restrict__ orig, const int* __restrict__ cid, const int* __restrict__ cstart,
-                                               const int* __restrict__ catoms, GridD g, BoxD box, uint32_t bit1, uint32_t bit2, double rc2,
-                                               int maxn, size_t stride, int* __restrict__ nlist, int* __restrict__ nnum, int* err) {
+// around it.  Candidates first pass an FP32 prefilter on a float4 copy of the positions that also carries
+// the group mask (one 16-byte load per candidate, FP32 pipe): r2f < r_cut^2 + margin with the margin
+// covering every float rounding, so no true neighbour is ever rejected.  Survivors (~15 %) take the exact
+// FP64 test: dr2 uses __dmul_rn/__dadd_rn so the compiler cannot contract it into FMAs and the set
+// {j : dr2 < rc2} is bit-identical to the reference's brute-force scan (md_neighbours.f90:73-87).
+// With PART the accepted entries are written class by class (r < R1 | switch zone | r >= R2, distances at
+// build time) so that the lanes of a warp later agree on the branch the potential takes: class 0 grows
+// from the front of the row, classes 1 and 2 are staged in a scratch row and appended.
+struct PrefD { float L[3], h[3], lim; int on; };
+__global__ void k_make_posf(int N, const double4* __restrict__ pos, const uint32_t* __restrict__ gmask, float4* __restrict__ posf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    if (!(gmask[i] & bit1)) { nnum[i] = 0; return; }
+    double4 p = pos[i];
+    posf[i] = make_float4((float)p.x, (float)p.y, (float)p.z, __uint_as_float(gmask[i]));
+}
+
+template <bool IDENT, bool PART>
+__global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict__ pos, const float4* __restrict__ posf, const int* __restrict__ orig,
+                                               const int* __restrict__ cstart, const int* __restrict__ catoms, GridD g, BoxD box, PrefD pf,
+                                               uint32_t bit1, uint32_t bit2, double rc2, double r1sq, double r2sq, int maxn, size_t stride,
+                                               int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float4 pif = posf[i];
+    if (!(__float_as_uint(pif.w) & bit1)) { nnum[i] = 0; return; }
     const double4 pi = pos[i];
-    // same binning expression as k_cell_count (cid[] is stale after a physical re-sort)
+    // same binning expression as k_cell_count
     const int cx = cell_coord(pi.x, g.inv[0], g.n[0]), cy = cell_coord(pi.y, g.inv[1], g.n[1]), cz = cell_coord(pi.z, g.inv[2], g.n[2]);
     const int lo0 = g.n[0] >= 3 ? -1 : 0, hi0 = g.n[0] >= 2 ? 1 : 0;
     const int lo1 = g.n[1] >= 3 ? -1 : 0, hi1 = g.n[1] >= 2 ? 1 : 0;
     const int lo2 = g.n[2] >= 3 ? -1 : 0, hi2 = g.n[2] >= 2 ? 1 : 0;
-    int cnt = 0;
+    int cnt = 0, c0 = 0, c1 = 0, c2 = 0;
     for (int oz = lo2; oz <= hi2; ++oz) {
         int z = cz + oz; z = z < 0 ? z + g.n[2] : (z >= g.n[2] ? z - g.n[2] : z);
         for (int oy = lo1; oy <= hi1; ++oy) {
@@ -210,15 +228,28 @@ __global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict_
                 int b = cstart[cc], e = cstart[cc + 1];
                 for (int s = b; s < e; ++s) {
                     int j = IDENT ? s : catoms[s];
+                    const float4 q = posf[j];
                     if (j == i) continue;
-                    if (!(gmask[j] & bit2)) continue;
+                    if (!(__float_as_uint(q.w) & bit2)) continue;
+                    if (pf.on) {
+                        float fx = q.x - pif.x, fy = q.y - pif.y, fz = q.z - pif.z;
+                        fx = fx >= pf.h[0] ? fx - pf.L[0] : (fx < -pf.h[0] ? fx + pf.L[0] : fx);
+                        fy = fy >= pf.h[1] ? fy - pf.L[1] : (fy < -pf.h[1] ? fy + pf.L[1] : fy);
+                        fz = fz >= pf.h[2] ? fz - pf.L[2] : (fz < -pf.h[2] ? fz + pf.L[2] : fz);
+                        if (!(fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim)) continue;
+                    }
                     double4 pj = pos[j];
                     double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]);
                     double dy = min_image(pj.y - pi.y, box.h[1], box.L[1]);
                     double dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
                     double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                     if (dr2 < rc2) {
-                        if (cnt < maxn) nlist[(size_t)cnt * stride + i] = j;
+                        if (cnt < maxn) {
+                            if (!PART) nlist[(size_t)cnt * stride + i] = j;
+                            else if (dr2 < r1sq) nlist[(size_t)(c0++) * stride + i] = j;
+                            else if (dr2 < r2sq) alt[(size_t)(c1++) * stride + i] = j;
+                            else alt[(size_t)(maxn - 1 - (c2++)) * stride + i] = j;
+                        }
                         ++cnt;
                     }
                 }
@@ -226,6 +257,10 @@ __global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict_
         }
     }
     if (cnt > maxn) { raise_error(err, E_TOO_MANY, orig[i], cnt); cnt = maxn; }  // md_neighbours.f90:80
+    if (PART) {
+        for (int k = 0; k < c1; ++k) nlist[(size_t)(c0 + k) * stride + i] = alt[(size_t)k * stride + i];
+        for (int k = 0; k < c2; ++k) nlist[(size_t)(c0 + c1 + k) * stride + i] = alt[(size_t)(maxn - 1 - k) * stride + i];
+    }
     nnum[i] = cnt;
 }
 
@@ -235,13 +270,19 @@ void nl_build(pfmds_ctx* c, NList& l) {
     for (int k = 0; k < 3; ++k) { g.n[k] = c->ncell[k]; g.inv[k] = c->ncell[k] / c->box.L[k]; }
     uint32_t b1 = 1u << (l.g1 - 1), b2 = 1u << (l.g2 - 1);
     double rc2 = l.rcut * l.rcut;
+    PrefD pf;
+    double Lmax = std::max(c->box.L[0], std::max(c->box.L[1], c->box.L[2])), hmin = std::min(c->box.h[0], std::min(c->box.h[1], c->box.h[2]));
+    for (int k = 0; k < 3; ++k) { pf.L[k] = (float)c->box.L[k]; pf.h[k] = (float)c->box.h[k]; }
+    // |delta d| <= 3 ulp-halves of L per component, r2 error <= 2 sqrt(3) r |delta d| + float rounding of r2; doubled
+    double dd = 2e-7 * Lmax, margin = 2.0 * (3.5 * l.rcut * dd + 4e-7 * rc2 + 3 * dd * dd);
+    pf.lim = (float)(rc2 + margin) * (1.0f + 2e-7f);
+    pf.on = hmin > l.rcut * 1.01 + 10 * dd;  // tiny boxes: the float wrap could pick another image, use the exact test only
     KTimer kt(c, KS_NL_BUILD);
-    if (c->identity_order)
-        k_build<true><<<nb, T, 0, c->st>>>(N, c->pos, c->gmask, c->orig, c->cid, c->cell_start, c->cell_atoms, g, c->box, b1, b2, rc2, l.maxn,
-                                           c->stride, l.nlist, l.nnum, c->err);
-    else
-        k_build<false><<<nb, T, 0, c->st>>>(N, c->pos, c->gmask, c->orig, c->cid, c->cell_start, c->cell_atoms, g, c->box, b1, b2, rc2, l.maxn,
-                                            c->stride, l.nlist, l.nnum, c->err);
+#define LAUNCH_BUILD(ID, PT) k_build<ID, PT><<<nb, T, 0, c->st>>>(N, c->pos, c->posf, c->orig, c->cell_start, c->cell_atoms, g, c->box, pf, b1, b2, rc2, \
+        l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err)
+    if (c->identity_order) { if (l.partition) LAUNCH_BUILD(true, true); else LAUNCH_BUILD(true, false); }
+    else { if (l.partition) LAUNCH_BUILD(false, true); else LAUNCH_BUILD(false, false); }
+#undef LAUNCH_BUILD
     c->launches += 1;
     l.built = true;
     CK(cudaGetLastError());
@@ -281,43 +322,3 @@ void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     CK(cudaGetLastError());
 }
 
-// ------------------------------------------------------------------------------------------------
-// Class partition of every row (distances at build time): entries with r < R1 first, then the switch
-// zone R1 <= r < R2, then r >= R2.  Membership is untouched — this only permutes a row — but the lanes
-// of a warp, which walk slot p of 32 neighbouring atoms together, then mostly agree on the branch the
-// potential takes (in a crystal the coordination shells line up exactly).
-__global__ void __launch_bounds__(128) k_partition(int N, const double4* __restrict__ pos, const int* __restrict__ nlist, const int* __restrict__ nnum,
-                                                   size_t stride, BoxD box, double r1sq, double r2sq, int* __restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int n = nnum[i];
-    if (n == 0) return;
-    const double4 pi = pos[i];
-    int c0 = 0, c1 = 0;
-    for (int p = 0; p < n; ++p) {
-        double4 pj = pos[nlist[(size_t)p * stride + i]];
-        double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]), dy = min_image(pj.y - pi.y, box.h[1], box.L[1]), dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
-        double r2 = dx * dx + dy * dy + dz * dz;
-        c0 += r2 < r1sq;
-        c1 += (r2 >= r1sq) & (r2 < r2sq);
-    }
-    int o0 = 0, o1 = c0, o2 = c0 + c1;
-    for (int p = 0; p < n; ++p) {
-        int j = nlist[(size_t)p * stride + i];
-        double4 pj = pos[j];
-        double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]), dy = min_image(pj.y - pi.y, box.h[1], box.L[1]), dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
-        double r2 = dx * dx + dy * dy + dz * dz;
-        int slot = r2 < r1sq ? o0++ : (r2 < r2sq ? o1++ : o2++);
-        out[(size_t)slot * stride + i] = j;
-    }
-}
-
-void nl_partition(pfmds_ctx* c, NList& l) {
-    if (!l.partition) return;
-    const int N = c->N, T = 128, nb = (N + T - 1) / T;
-    KTimer kt(c, KS_NL_BUILD);
-    k_partition<<<nb, T, 0, c->st>>>(N, c->pos, l.nlist, l.nnum, c->stride, c->box, l.part_r1sq, l.part_r2sq, l.nlist_alt);
-    std::swap(l.nlist, l.nlist_alt);
-    c->launches += 1;
-    CK(cudaGetLastError());
-}
