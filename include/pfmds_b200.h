@@ -128,6 +128,22 @@ int pfmds_timer_stop(pfmds_ctx* ctx, double* ms);
 /* Roofline denominators measured on the device: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s). */
 int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs);
 
+/* ---- slab spatial decomposition of one large cell over the GPUs of a node (BASELINE.json configs[3]; the
+ * reference has no counterpart: its only multi-process mode is the ensemble) ------------------------------
+ * Rank r owns the atoms with x in [r Lx/P, (r+1) Lx/P); ghost copies, migration at rebuild steps and the
+ * sums over ranks (KE, momentum, energies) are handled inside pfmds_advance / pfmds_energies /
+ * pfmds_diagnostics with NCCL on the context's stream.  Interactions: lj, lj1g, rjl.
+ * pfmds_slab_unique_id: rank 0 creates the id, the host broadcasts the 128 bytes to the other ranks.
+ * pfmds_create_slab: this rank's atoms (any order): 1-based global numbers, state, per-atom group bit mask
+ * (bit g-1 = member of group g, g <= 31) and the GLOBAL size of every group; `capacity` = slots for local
+ * atoms + ghosts.  Then pfmds_set_roles / add_nhc / set_misc / add_interaction / advance as usual
+ * (pfmds_set_group is not used).  pfmds_slab_download returns this rank's atoms. */
+int pfmds_slab_unique_id(char id[128]);
+int pfmds_create_slab(pfmds_ctx** ctx, int device, int rank, int nranks, const char id[128], long long n_global, int n_local,
+                      const int* global_index, const double* positions, const double* velocities, const double* masses,
+                      const unsigned int* group_mask, int n_groups, const long long* group_sizes, const double box_size[3], int capacity);
+int pfmds_slab_download(pfmds_ctx* ctx, int* n_local, int* global_index, double* positions, double* velocities, double* forces);
+
 /* Device self-test of the library's FP64 elementary functions against the CUDA math library: max errors
  * [0] exp (relative), [1] cosine switch / sincos (absolute), [2] rsqrt (relative), [3] hardware rsqrt seed. */
 int pfmds_selftest_math(int device, double err[4]);

@@ -15,7 +15,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", CXX]
-SOURCES = ["nl.cu", "forces.cu", "integrate.cu", "capi.cu"]
+SOURCES = ["nl.cu", "forces.cu", "integrate.cu", "capi.cu", "slab.cu"]
 LIB = os.path.join(CSRC, "libpfmds_b200.so")
 EXE = os.path.join(HOST, "run_md_simulation")
 
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     if verbose:
         print("\n".join(outs))
     if force or jobs or _newer(LIB, objs):
-        _run([NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB] + objs)
+        _run([NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB] + objs + ["-ldl"])
     host_deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))]
     if force or _newer(EXE, host_deps + [LIB]):
         _run([CXX, "-O2", "-std=c++17", "-o", EXE, os.path.join(HOST, "run_md_simulation.cpp"), "-L" + CSRC, "-lpfmds_b200",

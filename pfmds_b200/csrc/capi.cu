@@ -37,17 +37,29 @@ int kind_of(const std::string& n) {
 }
 int nl_n_of(int kind) { return kind == K_LJ ? 2 : (kind == K_LJC || kind == K_MORSEC) ? 3 : 1; }
 
+void finalize_slab(pfmds_ctx* c);
+
 const std::vector<int>& group_of(pfmds_ctx* c, int g) {
     if (g < 1 || g > (int)c->groups.size()) fail(PFMDS_ERR_INVALID, "error: group number " + std::to_string(g) + " is not defined");
     return c->groups[(size_t)g - 1];
 }
 
+long long group_size(pfmds_ctx* c, int g) {
+    if (c->slab) {
+        if (g < 1 || g > (int)c->group_count.size()) fail(PFMDS_ERR_INVALID, "error: group number " + std::to_string(g) + " is not defined");
+        return c->group_count[(size_t)g - 1];
+    }
+    return (long long)group_of(c, g).size();
+}
+
 // poll the device error word; turns the first recorded condition into the reference's message
 void check_device_error(pfmds_ctx* c) {
     int h[PFMDS_ERRW];
+    if (c->slab) slab_allreduce_max_int(c, c->err, 1);  // every rank stops together
     CK(cudaMemcpyAsync(h, c->err, sizeof h, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (h[0] == 0) return;
+    if (h[0] == 30) fail(PFMDS_ERR_UNSUPPORTED, "slab decomposition: an atom moved farther than one slab between two list rebuilds");
     if (h[0] == E_OUT_OF_CELL) fail(PFMDS_ERR_OUT_OF_CELL, " " + std::to_string(h[1] + 1) + "  particle out of cell");
     if (h[0] == E_TOO_MANY) fail(PFMDS_ERR_TOO_MANY_NEIGHBOURS, "error: too many neighbours (atom " + std::to_string(h[1] + 1) + ", " + std::to_string(h[2]) + " found)");
     if (h[0] == E_GR_NEIB)
@@ -56,9 +68,59 @@ void check_device_error(pfmds_ctx* c) {
     fail(PFMDS_ERR_CUDA, "device error " + std::to_string(h[0]));
 }
 
+
+// Slab mode: the masks came with pfmds_create_slab; validation works on group numbers and global sizes.
+void finalize_slab(pfmds_ctx* c) {
+    int period = -1;
+    for (auto& it : c->inter) {
+        if (it.kind != K_LJ && it.kind != K_LJ1G && it.kind != K_RJL)
+            fail(PFMDS_ERR_UNSUPPORTED, "unsupported: slab decomposition handles lj, lj1g and rjl (" + it.name + " needs ghost bond orders / normals)");
+        NList& a = it.nl[0];
+        for (int j = 0; j < it.nl_n; ++j) { group_size(c, it.nl[j].g1); group_size(c, it.nl[j].g2); }
+        if ((it.kind == K_LJ1G || it.kind == K_RJL) && a.g1 != a.g2) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: " + it.name + " needs group1 == group2");
+        if (it.kind == K_LJ) {
+            NList& b = it.nl[1];
+            if (group_size(c, a.g2) > group_size(c, b.g1)) fail(PFMDS_ERR_LIST_SIZE, "error: group2%N>cnl%N");
+            b.g1 = a.g2; b.g2 = a.g1; b.rcut = a.rcut; b.period = a.period;
+        }
+        double R1 = it.kind == K_LJ ? it.lj.R1 : it.kind == K_LJ1G ? it.lj1g.R1 : it.rjl.R1;
+        double R2 = it.kind == K_LJ ? it.lj.R2 : it.kind == K_LJ1G ? it.lj1g.R2 : it.rjl.R2;
+        for (int j = 0; j < it.nl_n; ++j) {
+            NList& l = it.nl[j];
+            if (l.maxn < 1 || l.period < 1 || !(l.rcut > 0)) fail(PFMDS_ERR_INVALID, "error: bad neighbour list parameters");
+            if (period < 0) period = l.period;
+            if (l.period != period) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: slab decomposition needs one update_period for all lists");
+            l.partition = true; l.part_r1sq = R1 * R1; l.part_r2sq = R2 * R2;
+            CK(cudaMalloc(&l.nlist_alt, sizeof(int) * (size_t)l.maxn * c->stride));
+            CK(cudaMalloc(&l.nlist, sizeof(int) * (size_t)l.maxn * c->stride));
+            CK(cudaMalloc(&l.nnum, sizeof(int) * c->stride));
+            CK(cudaMemsetAsync(l.nnum, 0, sizeof(int) * c->stride, c->st));
+        }
+    }
+    group_size(c, c->all_moving); group_size(c, c->xyz_moving); group_size(c, c->z_moving); group_size(c, c->all_atoms);
+    for (auto& t : c->nhc) {
+        t.L = (int)group_size(c, t.group);
+        if (t.L < 1) fail(PFMDS_ERR_NHC_PARAMS, "error: wrong nhc parameters");
+        std::vector<double> st((size_t)3 * t.M + 4, 0.);
+        double q1;
+        CK(cudaMemcpy(&q1, t.state + 2 * t.M, sizeof(double), cudaMemcpyDeviceToHost));
+        st[2 * (size_t)t.M] = q1;
+        for (int i = 1; i < t.M; ++i) st[2 * (size_t)t.M + i] = q1 / (3. * t.L);
+        st[3 * (size_t)t.M] = 1.;
+        st[3 * (size_t)t.M + 2] = 1.;
+        CK(cudaMemcpy(t.state, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+    }
+    c->nhc_fusable = false;  // the KE sum crosses ranks between the reduction and the chain update
+    if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
+    nl_setup_grid(c);
+    CK(cudaStreamSynchronize(c->st));
+    c->finalized = true;
+}
+
 // Validate the description, build the masks, allocate the lists.  Runs once, at the first advance.
 void finalize(pfmds_ctx* c) {
     if (c->finalized) return;
+    if (c->slab) { finalize_slab(c); return; }
     const int N = c->N;
     if (c->groups.size() > PFMDS_MAX_GROUPS) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: more than 32 atom groups");
     c->h_gmask.assign((size_t)N, 0u);
@@ -198,9 +260,12 @@ void update_lists(pfmds_ctx* c, int step) {
             all &= rb;
         }
     }
+    if (c->slab && !any) slab_exchange(c, 0);  // ghost positions follow their owners every step
     if (any) {
         PhaseTimer t(c, 2);
+        if (c->slab) slab_redistribute(c);   // finalize_slab guarantees any == all
         nl_bin_atoms(c, all);
+        if (c->slab) slab_after_reorder(c);
         for (auto& it : c->inter) {
             for (int j = 0; j < it.nl_n; ++j) {
                 NList& l = it.nl[j];
@@ -509,7 +574,7 @@ int pfmds_energies(pfmds_ctx* c, double* e_inter, double* ke, double* temp, doub
         if (e_inter) for (size_t k = 0; k < c->inter.size(); ++k) e_inter[k] = he[k];
         if (ke) *ke = hke;
         // calculate_temperature, md_general.f90:301-311
-        if (temp) *temp = 2 * hke / PFMDS_KB / (3 * (double)(int)group_of(c, c->all_moving).size());
+        if (temp) *temp = 2 * hke / PFMDS_KB / (3 * (double)group_size(c, c->all_moving));
         if (e_nhc)
             for (size_t k = 0; k < c->nhc.size(); ++k) {  // calculate_nose_hoover_chain_energy, md_integrators.f90:247-260
                 const Nhc& t = c->nhc[k];
@@ -539,6 +604,7 @@ int pfmds_diagnostics(pfmds_ctx* c, double fs[3], double mc[3], double mcv[3], d
             size_t k = 0;
             for (auto& it : c->inter)
                 for (int j = 0; j < it.nl_n; ++j, ++k) { k_max_int<<<64, 256, 0, c->st>>>(c->N, it.nl[j].nnum, d_max + k); c->launches += 1; }
+            if (c->slab) slab_allreduce_max_int(c, d_max, (int)nl_total);
             CK(cudaMemcpyAsync(hmax.data(), d_max, sizeof(int) * nl_total, cudaMemcpyDeviceToHost, c->st));
         }
         double h[11];
@@ -559,6 +625,7 @@ int pfmds_download(pfmds_ctx* c, double* pos, double* vel, double* frc) {
     if (!c) return PFMDS_ERR_INVALID;
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
+        if (c->slab) fail(PFMDS_ERR_INVALID, "error: use pfmds_slab_download on a slab context");
         const size_t N = (size_t)c->N;
         integ_flush_pending(c);
         std::vector<int> ho(N);
@@ -581,6 +648,7 @@ int pfmds_neighbours(pfmds_ctx* c, int inter, int list, int* nlist, int* nnum, i
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
         if (!c->finalized) fail(PFMDS_ERR_INVALID, "error: no neighbour lists before the first pfmds_advance");
+        if (c->slab) fail(PFMDS_ERR_INVALID, "error: pfmds_neighbours is not available on a slab context");
         if (inter < 0 || inter >= (int)c->inter.size() || list < 0 || list >= c->inter[(size_t)inter].nl_n) fail(PFMDS_ERR_INVALID, "error: no such neighbour list");
         const NList& l = c->inter[(size_t)inter].nl[list];
         const size_t N = (size_t)c->N, S = c->stride;
@@ -664,6 +732,7 @@ int pfmds_upload(pfmds_ctx* c, const double* pos, const double* vel) {
     if (!c) return PFMDS_ERR_INVALID;
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
+        if (c->slab) fail(PFMDS_ERR_INVALID, "error: pfmds_upload is not available on a slab context");
         const size_t n3 = 3 * (size_t)c->N;
         integ_flush_pending(c);
         c->nhc_ke_valid = false;
@@ -688,6 +757,7 @@ int pfmds_pair_count(pfmds_ctx* c, int inter, int list, long long* pairs) {
         CK(cudaMalloc(&d, sizeof(unsigned long long)));
         CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->st));
         k_sum_int<<<256, 256, 0, c->st>>>(c->N, c->inter[(size_t)inter].nl[list].nnum, d);
+        if (c->slab) slab_allreduce_sum_ll(c, d, 1);
         unsigned long long h = 0;
         CK(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
@@ -805,6 +875,94 @@ int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs) {
     } catch (...) { return PFMDS_ERR_CUDA; }
 }
 
+
+// ---- slab decomposition (BASELINE.json configs[3]) ----------------------------------------------------
+int pfmds_slab_unique_id(char id[128]) {
+    try { return slab_unique_id(id); } catch (...) { return PFMDS_ERR_CUDA; }
+}
+
+int pfmds_create_slab(pfmds_ctx** out, int device, int rank, int nranks, const char id[128], long long n_global, int n_local, const int* global_index,
+                      const double* pos, const double* vel, const double* mass, const unsigned int* group_mask, int n_groups,
+                      const long long* group_sizes, const double box[3], int capacity) {
+    if (!out) return PFMDS_ERR_INVALID;
+    pfmds_ctx* c = new pfmds_ctx;
+    *out = c;
+    return guarded(c, [&] {
+        if (n_local < 0 || capacity < n_local || nranks < 2 || rank < 0 || rank >= nranks || !box || n_groups < 1 || n_groups > 31)
+            fail(PFMDS_ERR_INVALID, "error: bad arguments to pfmds_create_slab");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(PFMDS_ERR_CUDA, "no CUDA device: pfmds_b200 has no CPU fallback");
+        if (device < 0 || device >= ndev) fail(PFMDS_ERR_INVALID, "error: CUDA device " + std::to_string(device) + " does not exist");
+        c->dev = device;
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        c->N = n_local;
+        c->stride = ((size_t)capacity + 31) / 32 * 32;
+        for (int k = 0; k < 3; ++k) { c->box.L[k] = box[k]; c->box.h[k] = 0.5 * box[k]; }
+        const size_t S = c->stride;
+        CK(cudaMalloc(&c->pos, sizeof(double4) * S)); CK(cudaMalloc(&c->pos2, sizeof(double4) * S));
+        CK(cudaMalloc(&c->vel, sizeof(double4) * S)); CK(cudaMalloc(&c->vel2, sizeof(double4) * S));
+        CK(cudaMalloc(&c->frc, sizeof(double4) * S));
+        CK(cudaMalloc(&c->gmask, sizeof(uint32_t) * S)); CK(cudaMalloc(&c->gmask2, sizeof(uint32_t) * S));
+        CK(cudaMalloc(&c->orig, sizeof(int) * S)); CK(cudaMalloc(&c->orig2, sizeof(int) * S));
+        CK(cudaMalloc(&c->cell_atoms, sizeof(int) * S)); CK(cudaMalloc(&c->cid, sizeof(int) * S));
+        CK(cudaMalloc(&c->posf, sizeof(float4) * S));
+        size_t nparts = (S + 127) / 128 + RED_BLOCKS;
+        CK(cudaMalloc(&c->part, sizeof(double) * 16 * nparts));
+        CK(cudaMalloc(&c->red, sizeof(double) * 64));
+        CK(cudaMalloc(&c->err, sizeof(int) * PFMDS_ERRW));
+        CK(cudaMemset(c->err, 0, sizeof(int) * PFMDS_ERRW));
+        CK(cudaMemset(c->frc, 0, sizeof(double4) * S));
+        std::vector<double4> hp(S, make_double4(0, 0, 0, 0)), hv(S, make_double4(0, 0, 0, 1));
+        std::vector<int> ho(S, 0);
+        std::vector<uint32_t> hm(S, 0u);
+        for (int i = 0; i < n_local; ++i) {
+            hp[(size_t)i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0.);
+            hv[(size_t)i] = make_double4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], mass[i]);
+            ho[(size_t)i] = global_index[i] - 1;
+            hm[(size_t)i] = group_mask[i] & 0x7fffffffu;
+        }
+        CK(cudaMemcpy(c->pos, hp.data(), sizeof(double4) * S, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->vel, hv.data(), sizeof(double4) * S, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->orig, ho.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->gmask, hm.data(), sizeof(uint32_t) * S, cudaMemcpyHostToDevice));
+        c->group_count.assign(group_sizes, group_sizes + n_groups);
+        const char* tm = std::getenv("PFMDS_TIMERS");
+        c->timers_on = tm && tm[0] == '1';
+        CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+        slab_init(c, rank, nranks, id, n_global, n_local, capacity);
+    });
+}
+
+int pfmds_slab_download(pfmds_ctx* c, int* n_local, int* global_index, double* pos, double* vel, double* frc) {
+    if (!c || !c->slab) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        integ_flush_pending(c);
+        const size_t N = (size_t)c->N;
+        std::vector<int> ho(N);
+        std::vector<uint32_t> hm(N);
+        std::vector<double4> buf(N);
+        CK(cudaMemcpyAsync(ho.data(), c->orig, sizeof(int) * N, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hm.data(), c->gmask, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        int nl = 0;
+        for (size_t s = 0; s < N; ++s)
+            if (!(hm[s] & PFMDS_GHOST)) { if (global_index) global_index[nl] = ho[s] + 1; ++nl; }
+        if (n_local) *n_local = nl;
+        auto pull = [&](const double4* d, double* out) {
+            if (!out) return;
+            CK(cudaMemcpyAsync(buf.data(), d, sizeof(double4) * N, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            size_t k = 0;
+            for (size_t s = 0; s < N; ++s)
+                if (!(hm[s] & PFMDS_GHOST)) { out[3 * k] = buf[s].x; out[3 * k + 1] = buf[s].y; out[3 * k + 2] = buf[s].z; ++k; }
+        };
+        pull(c->pos, pos); pull(c->vel, vel); pull(c->frc, frc);
+        check_device_error(c);
+    });
+}
+
 int pfmds_timers(pfmds_ctx* c, double s[6]) {
     if (!c || !s) return PFMDS_ERR_INVALID;
     // slots: 0 pos_vel, 1 nlists, 2 nlsearch, 3 nldistance (no such pass on the device), 4 forces, 5 energy
@@ -822,6 +980,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     if (!c) return PFMDS_OK;
     cudaSetDevice(c->dev);
     if (c->st) cudaStreamSynchronize(c->st);
+    slab_destroy(c);
     for (auto& it : c->inter) {
         for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nlist_alt); cudaFree(it.nl[j].nnum); }
         cudaFree(it.aux); cudaFree(it.gnorm); cudaFree(it.tvec);

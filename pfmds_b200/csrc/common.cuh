@@ -19,6 +19,7 @@
 #include "mathx.cuh"
 
 #define PFMDS_MAX_GROUPS 32
+#define PFMDS_GHOST 0x80000000u  // gmask bit of a ghost copy (slab decomposition); group 32 is unavailable in that mode
 #define PFMDS_ERRW 4  // error word: code, detail a, detail b, spare
 
 // the reference's FP64 literals (md_general.f90:165,304; md_integrators.f90:62,211; cut_off_function.f90:8)

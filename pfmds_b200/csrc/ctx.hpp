@@ -40,6 +40,8 @@ struct Nhc {
     double* state = nullptr;  // device: x[M], v[M], q[M], then s, e
 };
 
+struct Slab;
+
 struct pfmds_ctx {
     int dev = 0;
     cudaStream_t st = nullptr;
@@ -70,6 +72,10 @@ struct pfmds_ctx {
     bool invert_z = false;
     std::vector<Inter> inter;
     std::vector<Nhc> nhc;
+    // slab decomposition (slab.cu); null in single-GPU and ensemble runs
+    Slab* slab = nullptr;
+    int* newslot = nullptr;  // old slot -> new slot of the last cell re-sort
+    std::vector<long long> group_count;  // slab mode: global size of every group
     bool finalized = false;
     // fused NVT path (integrate.cu): usable when the thermostat groups are pairwise disjoint
     bool nhc_fusable = false;
@@ -112,6 +118,22 @@ void nl_setup_grid(pfmds_ctx* c);
 void nl_bin_atoms(pfmds_ctx* c, bool reorder);
 void nl_build(pfmds_ctx* c, NList& l);
 void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src);
+
+// ---- slab.cu ----
+int slab_unique_id(char* id128);
+void slab_init(pfmds_ctx* c, int rank, int nranks, const char* id128, long long n_global, int n_local, int capacity);
+void slab_destroy(pfmds_ctx* c);
+void slab_redistribute(pfmds_ctx* c);
+void slab_after_reorder(pfmds_ctx* c);
+void slab_exchange(pfmds_ctx* c, int field);
+void slab_allreduce_sum(pfmds_ctx* c, double* d, int n);
+void slab_allreduce_max(pfmds_ctx* c, double* d, int n);
+void slab_allreduce_max_int(pfmds_ctx* c, int* d, int n);
+void slab_allreduce_sum_ll(pfmds_ctx* c, unsigned long long* d, int n);
+int slab_rank(pfmds_ctx* c);
+int slab_nranks(pfmds_ctx* c);
+int slab_n_local(pfmds_ctx* c);
+long long slab_n_global(pfmds_ctx* c);
 
 // ---- forces.cu ----
 void forces_zero(pfmds_ctx* c);

@@ -169,7 +169,8 @@ __device__ __forceinline__ void wrap3(double& dx, double& dy, double& dz, const 
 }
 
 template <bool E>
-__device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& sq, double& sp) {
+__device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, const double* tab, double& sq,
+                                                 double& sp) {
     double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
     wrap3(dx, dy, dz, box, mhh);
     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -187,6 +188,7 @@ __device__ __forceinline__ void rjl_density_pair(const double4& pi, const double
 }
 template <bool E>
 __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part) {
+    const double* tab = nullptr;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
     int n = i < N ? lv.nnum[i] : 0;
@@ -205,12 +207,12 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* po
             int j2 = p + 2 < n ? rp[2 * st] : j1;
             int j3 = p + 3 < n ? rp[3 * st] : j1;
             rp += 2 * st;
-            rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, sq, sp);
+            rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, tab, sq, sp);
             a = ld256(&pos[j2]);
-            rjl_density_pair<E>(pi, b, C, box, W.min_half_hi, sq, sp);
+            rjl_density_pair<E>(pi, b, C, box, W.min_half_hi, tab, sq, sp);
             j1 = j3;
         }
-        if (p < n) rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, sq, sp);
+        if (p < n) rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, tab, sq, sp);
         double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
         reinterpret_cast<double*>(&pos[i])[3] = ie;
         if (E) e = C.A0 * sp - C.xi * (sq * ie);
@@ -218,8 +220,8 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* po
     if (E) store_partial(e, part);
 }
 
-__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& fx, double& fy,
-                                               double& fz) {
+__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, const double* tab, double& fx,
+                                               double& fy, double& fz) {
     double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
     wrap3(dx, dy, dz, box, mhh);
     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -242,6 +244,7 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
 }
 __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
                                                             WrapC W) {
+    const double* tab = nullptr;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int n = lv.nnum[i];
@@ -258,12 +261,12 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4
         int j2 = p + 2 < n ? rp[2 * st] : j1;
         int j3 = p + 3 < n ? rp[3 * st] : j1;
         rp += 2 * st;
-        rjl_force_pair(pi, a, C, box, W.min_half_hi, fx, fy, fz);
+        rjl_force_pair(pi, a, C, box, W.min_half_hi, tab, fx, fy, fz);
         a = ld256_nc(&pos[j2]);
-        rjl_force_pair(pi, b, C, box, W.min_half_hi, fx, fy, fz);
+        rjl_force_pair(pi, b, C, box, W.min_half_hi, tab, fx, fy, fz);
         j1 = j3;
     }
-    if (p < n) rjl_force_pair(pi, a, C, box, W.min_half_hi, fx, fy, fz);
+    if (p < n) rjl_force_pair(pi, a, C, box, W.min_half_hi, tab, fx, fy, fz);
     add_force(frc, i, fx, fy, fz);
 }
 
@@ -539,6 +542,7 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
         const RjlC C = rjl_consts(it.rjl);
         const WrapC W = wrap_consts(c->box);
         { KTimer kt(c, KS_RJL_DENSITY); k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr); }
+        if (c->slab) slab_exchange(c, 1);  // ghost 1/Eb from their owners
         { KTimer kt(c, KS_RJL_FORCE); k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W); }
     }
         c->launches += 2;
@@ -590,5 +594,6 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     }
     k_sum_partials<<<1, 1024, 0, c->st>>>(nb, c->part, scale, c->energy + k);
     c->launches += 2;
+    if (c->slab) slab_allreduce_sum(c, c->energy + k, 1);
     CK(cudaGetLastError());
 }

@@ -29,7 +29,7 @@ void integ_check_positions(pfmds_ctx* c) {
 // md_general.f90:382-398
 __global__ void k_invert_z(int N, const double4* __restrict__ pos, double4* __restrict__ vel, double zl, double zh) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= N) return;  // ghost copies carry zero velocities: the test below never fires for them
     double z = pos[i].z, vz = vel[i].z;
     if ((z > zl && z < (zl + zh) / 2 && vz > 0.) || (z < zh && z > (zl + zh) / 2 && vz < 0.)) vel[i].z = -vz;
 }
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(IT) k_ke_partial(int N, const double4* __restr
                                                    double* __restrict__ part) {
     double s = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        if (gmask[i] & bit) {
+        if ((gmask[i] & (bit | PFMDS_GHOST)) == bit) {
             double4 v = vel[i];
             s += v.w * (v.x * v.x + v.y * v.y + v.z * v.z) / 2 * PFMDS_MASS_COEF;
         }
@@ -61,6 +61,7 @@ void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out) {
     k_ke_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->gmask, 1u << (group - 1), c->part);
     k_sum_to<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, d_out);
     c->launches += 2;
+    if (c->slab) slab_allreduce_sum(c, d_out, 1);
 }
 
 // ---- Nose-Hoover chain half step: md_integrators.f90:200-245 ---------------------------------------
@@ -112,7 +113,7 @@ __global__ void k_nhc(int nparts, const double* __restrict__ part, double* state
 __global__ void k_scale(int N, double4* __restrict__ vel, const uint32_t* __restrict__ gmask, uint32_t bit, const double* __restrict__ s_ptr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    if (gmask[i] & bit) {
+    if ((gmask[i] & (bit | PFMDS_GHOST)) == bit) {
         double s = *s_ptr;
         double4 v = vel[i];
         v.x *= s; v.y *= s; v.z *= s;
@@ -123,6 +124,12 @@ void integ_nhc_half(pfmds_ctx* c, Nhc& t, double dt) {
     uint32_t bit = 1u << (t.group - 1);
     KTimer kt(c, KS_NHC);
     k_ke_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->gmask, bit, c->part);
+    if (c->slab) {  // sum over ranks first, then every rank runs the same chain update on the same number
+        k_sum_to<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, c->red + 48);
+        slab_allreduce_sum(c, c->red + 48, 1);
+        k_nhc<<<1, 32, 0, c->st>>>(1, c->red + 48, t.state, t.M, t.L, t.temperature, dt / 2, dt / 4, dt / 8);
+        c->launches += 1;
+    } else
     k_nhc<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, t.state, t.M, t.L, t.temperature, dt / 2, dt / 4, dt / 8);
     k_scale<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, bit, t.state + 3 * t.M);
     c->launches += 3;
@@ -137,6 +144,7 @@ __global__ void __launch_bounds__(IT) k_kick_drift(int N, double4* __restrict__ 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t g = gmask[i];
+    if (g & PFMDS_GHOST) return;
     bool mx = g & bxyz, mz = g & bz;
     if (!mx && !mz) return;
     double4 p = pos[i], v = vel[i], f = frc[i];
@@ -167,6 +175,7 @@ __global__ void __launch_bounds__(IT) k_kick(int N, double4* __restrict__ vel, c
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t g = gmask[i];
+    if (g & PFMDS_GHOST) return;
     bool mx = g & bxyz, mz = g & bz;
     if (!mx && !mz) return;
     double4 v = vel[i], f = frc[i];
@@ -190,6 +199,7 @@ __global__ void k_quench(int N, double4* __restrict__ vel, const double4* __rest
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t g = gmask[i];
+    if (g & PFMDS_GHOST) return;
     bool mx = g & bxyz, mz = g & bz;
     if (!mx && !mz) return;
     double4 v = vel[i], f = frc[i];
@@ -218,10 +228,12 @@ __global__ void __launch_bounds__(IT) k_sums_partial(int N, const double4* __res
     for (int k = 0; k < 11; ++k) a[k] = 0.;
     a[10] = -1.;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        uint32_t gm = gmask[i];
+        if (gm & PFMDS_GHOST) continue;
         double4 v = vel[i];
         double v2 = v.x * v.x + v.y * v.y + v.z * v.z;
         if (a[10] < v2) a[10] = v2;
-        if (gmask[i] & bit) {
+        if (gm & bit) {
             double4 p = pos[i], f = frc[i];
             a[0] += f.x; a[1] += f.y; a[2] += f.z;
             a[3] += v.w * p.x; a[4] += v.w * p.y; a[5] += v.w * p.z;
@@ -263,12 +275,13 @@ void integ_diagnostics(pfmds_ctx* c, double* d_out) {
     k_sums_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, 1u << (c->all_atoms - 1), c->part);
     k_sums_final<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, d_out);
     c->launches += 2;
+    if (c->slab) { slab_allreduce_sum(c, d_out, 10); slab_allreduce_max(c, d_out + 10, 1); }
 }
 // zero_momentum, md_general.f90:236-253
 __global__ void k_sub_mcv(int N, double4* __restrict__ vel, const uint32_t* __restrict__ gmask, uint32_t bit, const double* __restrict__ sums) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    if (gmask[i] & bit) {
+    if ((gmask[i] & (bit | PFMDS_GHOST)) == bit) {
         double totm = sums[9];
         double4 v = vel[i];
         v.x = v.x - sums[6] / totm; v.y = v.y - sums[7] / totm; v.z = v.z - sums[8] / totm;
@@ -304,6 +317,7 @@ __global__ void __launch_bounds__(IT) k_kick_drift_nvt(int N, double4* __restric
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t g = gmask[i];
+    if (g & PFMDS_GHOST) return;
     bool mx = g & bxyz, mz = g & bz;
     double sc = 1.0;
     bool th = false;
@@ -341,6 +355,7 @@ __global__ void __launch_bounds__(IT) k_kick_ke(int N, double4* __restrict__ vel
     for (int k = 0; k < NHC_MAXF; ++k) ke[k] = 0.;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         uint32_t g = gmask[i];
+        if (g & PFMDS_GHOST) continue;
         bool mx = g & bxyz, mz = g & bz;
         bool th = false;
         for (int k = 0; k < P.n; ++k) th |= (g & P.bit[k]) != 0;

@@ -135,10 +135,11 @@ __global__ void k_cell_sort(int ncells, const int* __restrict__ start, int* __re
 }
 __global__ void k_permute(int N, const int* __restrict__ order, const double4* __restrict__ pos, const double4* __restrict__ vel,
                           const uint32_t* __restrict__ gm, const int* __restrict__ orig, double4* __restrict__ pos2, double4* __restrict__ vel2,
-                          uint32_t* __restrict__ gm2, int* __restrict__ orig2) {
+                          uint32_t* __restrict__ gm2, int* __restrict__ orig2, int* __restrict__ newslot) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     int s = order[k];
+    if (newslot) newslot[s] = k;
     pos2[k] = pos[s];
     vel2[k] = vel[s];
     gm2[k] = gm[s];
@@ -168,7 +169,7 @@ void nl_bin_atoms(pfmds_ctx* c, bool reorder) {
     k_cell_sort<<<(c->ncells + T - 1) / T, T, 0, c->st>>>(c->ncells, c->cell_start, c->cell_atoms);
     c->launches += 6;
     if (reorder) {
-        k_permute<<<nb, T, 0, c->st>>>(N, c->cell_atoms, c->pos, c->vel, c->gmask, c->orig, c->pos2, c->vel2, c->gmask2, c->orig2);
+        k_permute<<<nb, T, 0, c->st>>>(N, c->cell_atoms, c->pos, c->vel, c->gmask, c->orig, c->pos2, c->vel2, c->gmask2, c->orig2, c->newslot);
         std::swap(c->pos, c->pos2);
         std::swap(c->vel, c->vel2);
         std::swap(c->gmask, c->gmask2);
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict_
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const float4 pif = posf[i];
-    if (!(__float_as_uint(pif.w) & bit1)) { nnum[i] = 0; return; }
+    if ((__float_as_uint(pif.w) & (bit1 | PFMDS_GHOST)) != bit1) { nnum[i] = 0; return; }  // owners: in group 1 and not a ghost copy
     const double4 pi = pos[i];
     // same binning expression as k_cell_count
     const int cx = cell_coord(pi.x, g.inv[0], g.n[0]), cy = cell_coord(pi.y, g.inv[1], g.n[1]), cz = cell_coord(pi.z, g.inv[2], g.n[2]);

@@ -1,0 +1,381 @@
+// pfmds_b200 — slab spatial decomposition of one large cell over the GPUs of a node (BASELINE.json
+// configs[3]; absent from the reference, whose only multi-process mode is the ensemble).
+//
+// Rank r owns the atoms with x in [r W, (r+1) W), W = Lx / P.  Around them it keeps ghost copies of the
+// neighbour ranks' atoms that lie within H = (largest r_cut, padded like a cell edge) of the shared face.
+// All forces are gathers, so there is no reverse (force) communication:
+//   every step      ghost positions  <- owners                (after the drift)
+//   rjl, every step ghost 1/Eb       <- owners                (between the density and the force pass)
+//   nvt / momentum  sum over ranks of the KE / momentum partial sums (ncclAllReduce, double)
+//   rebuild steps   atoms that left the slab migrate to the neighbour, ghosts are re-selected
+// The exchange is ncclSend/ncclRecv with the left and right neighbour inside one group, on the context's
+// stream, between kernels that never leave the device.  NCCL is resolved with dlopen at run time, so the
+// library has no link-time dependency on it (inside a torch process the bundled libnccl.so.2 is reused).
+// Supported interactions in this mode: lj, lj1g, rjl (tb / ljc / morsec would need ghost bond orders and
+// normals: refused).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ctx.hpp"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
+
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    void load() {
+        if (h) return;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) throw std::string("cannot load libnccl.so.2: ") + dlerror();
+#define SYM(f) *(void**)(&f) = dlsym(h, "nccl" #f); if (!f) throw std::string("libnccl lacks nccl" #f)
+        SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllReduce); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+#undef SYM
+    }
+};
+NcclApi g_nccl;
+#define NK(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) throw std::string("NCCL: ") + g_nccl.GetErrorString(r_) + " at " #x; } while (0)
+}  // namespace
+
+struct Slab {
+    int rank = 0, nranks = 1, left = 0, right = 0;
+    ncclComm_t comm = nullptr;
+    int n_local = 0, n_ghost = 0, cap = 0, cap_border = 0;
+    long long n_global = 0;
+    double W = 0, H = 0;
+    int *send_idx[2]{nullptr, nullptr}, *ghost_slot[2]{nullptr, nullptr};
+    int n_send[2]{0, 0}, n_recv[2]{0, 0};
+    double *sbuf[2]{nullptr, nullptr}, *rbuf[2]{nullptr, nullptr};
+    int *cat = nullptr, *scan[3]{nullptr, nullptr, nullptr}, *flag = nullptr, *cnt_d = nullptr, *scan_tmp = nullptr;
+    double* red_tmp = nullptr;
+};
+
+#define GHOST_BIT 0x80000000u
+#define MIG_W 9   // doubles per migrating atom: pos4, vel4, (mask, orig)
+#define GH_W 5    // doubles per new ghost: pos4, (mask, orig)
+
+// ---- small generic pieces ---------------------------------------------------------------------------
+__global__ void k_sl_scan_block(int n, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ sums) {
+    __shared__ int sh[32];
+    int base = blockIdx.x * 2048 + threadIdx.x * 2;
+    int a = base < n ? in[base] : 0, b = base + 1 < n ? in[base + 1] : 0;
+    int v = a + b, incl = v;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) sh[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = sh[lane], si = s;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+        sh[lane] = si - s;
+        if (lane == 31) sums[blockIdx.x] = si;
+    }
+    __syncthreads();
+    int excl = incl - v + sh[w];
+    if (base < n) out[base] = excl;
+    if (base + 1 < n) out[base + 1] = excl + a;
+}
+__global__ void k_sl_scan_sums(int nb, int* sums, int* total) {  // serial: nb is a few hundred at most
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < nb; ++i) { int v = sums[i]; sums[i] = run; run += v; }
+        *total = run;
+    }
+}
+__global__ void k_sl_scan_add(int n, int* out, const int* __restrict__ sums) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += sums[i / 2048];
+}
+static void exclusive_scan(pfmds_ctx* c, Slab* s, const int* in, int* out, int n, int* total_d) {
+    if (n == 0) { CK(cudaMemsetAsync(total_d, 0, sizeof(int), c->st)); return; }
+    int sb = (n + 2047) / 2048;
+    k_sl_scan_block<<<sb, 1024, 0, c->st>>>(n, in, out, s->scan_tmp);
+    k_sl_scan_sums<<<1, 32, 0, c->st>>>(sb, s->scan_tmp, total_d);
+    k_sl_scan_add<<<(n + 255) / 256, 256, 0, c->st>>>(n, out, s->scan_tmp);
+    c->launches += 3;
+}
+
+// ---- migration ---------------------------------------------------------------------------------------
+// category of every slot after the drift: 0 stays, 1 goes to the left rank, 2 to the right rank, 3 ghost (dropped)
+__global__ void k_sl_classify(int N, const double4* __restrict__ pos, const uint32_t* __restrict__ gmask, const int* __restrict__ orig, double W, int nranks,
+                              int rank, int* __restrict__ cat, int* __restrict__ f0, int* __restrict__ f1, int* __restrict__ f2, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int k = 3;
+    if (!(gmask[i] & GHOST_BIT)) {
+        int owner = (int)floor(pos[i].x / W);
+        owner = owner < 0 ? 0 : (owner >= nranks ? nranks - 1 : owner);
+        int left = (rank + nranks - 1) % nranks, right = (rank + 1) % nranks;
+        if (owner == rank) k = 0;
+        else if (owner == left) k = 1;
+        else if (owner == right) k = 2;
+        else { raise_error(err, 30, orig[i], owner); k = 0; }  // moved farther than one slab between rebuilds
+    }
+    cat[i] = k;
+    f0[i] = k == 0; f1[i] = k == 1; f2[i] = k == 2;
+}
+__global__ void k_sl_pack_migrants(int N, const double4* __restrict__ pos, const double4* __restrict__ vel, const uint32_t* __restrict__ gmask,
+                                   const int* __restrict__ orig, const int* __restrict__ cat, const int* __restrict__ s0, const int* __restrict__ s1,
+                                   const int* __restrict__ s2, double4* __restrict__ pos2, double4* __restrict__ vel2, uint32_t* __restrict__ gm2,
+                                   int* __restrict__ orig2, double* __restrict__ bl, double* __restrict__ br) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int k = cat[i];
+    if (k == 0) {
+        int d = s0[i];
+        pos2[d] = pos[i]; vel2[d] = vel[i]; gm2[d] = gmask[i]; orig2[d] = orig[i];
+    } else if (k == 1 || k == 2) {
+        double* b = (k == 1 ? bl : br) + (size_t)(k == 1 ? s1[i] : s2[i]) * MIG_W;
+        double4 p = pos[i], v = vel[i];
+        b[0] = p.x; b[1] = p.y; b[2] = p.z; b[3] = p.w; b[4] = v.x; b[5] = v.y; b[6] = v.z; b[7] = v.w;
+        b[8] = __hiloint2double((int)gmask[i], orig[i]);
+    }
+}
+__global__ void k_sl_unpack_migrants(int n, const double* __restrict__ buf, int at, double4* __restrict__ pos, double4* __restrict__ vel,
+                                     uint32_t* __restrict__ gm, int* __restrict__ orig) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* b = buf + (size_t)k * MIG_W;
+    pos[at + k] = make_double4(b[0], b[1], b[2], b[3]);
+    vel[at + k] = make_double4(b[4], b[5], b[6], b[7]);
+    gm[at + k] = (uint32_t)__double2hiint(b[8]);
+    orig[at + k] = __double2loint(b[8]);
+}
+// ---- ghost selection ---------------------------------------------------------------------------------
+__global__ void k_sl_border_flags(int N, const double4* __restrict__ pos, double x_lo, double x_hi, double H, int* __restrict__ fl, int* __restrict__ fr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double x = pos[i].x;
+    fl[i] = (x - x_lo) < H;
+    fr[i] = (x_hi - x) <= H;
+}
+__global__ void k_sl_pack_ghosts(int N, const double4* __restrict__ pos, const uint32_t* __restrict__ gmask, const int* __restrict__ orig,
+                                 const int* __restrict__ fl, const int* __restrict__ fr, const int* __restrict__ sl, const int* __restrict__ sr,
+                                 int* __restrict__ idx_l, int* __restrict__ idx_r, double* __restrict__ bl, double* __restrict__ br) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double4 p = pos[i];
+    double tag = __hiloint2double((int)(gmask[i] | GHOST_BIT), orig[i]);
+    if (fl[i]) { int d = sl[i]; idx_l[d] = i; double* b = bl + (size_t)d * GH_W; b[0] = p.x; b[1] = p.y; b[2] = p.z; b[3] = p.w; b[4] = tag; }
+    if (fr[i]) { int d = sr[i]; idx_r[d] = i; double* b = br + (size_t)d * GH_W; b[0] = p.x; b[1] = p.y; b[2] = p.z; b[3] = p.w; b[4] = tag; }
+}
+__global__ void k_sl_unpack_ghosts(int n, const double* __restrict__ buf, int at, double4* __restrict__ pos, double4* __restrict__ vel,
+                                   uint32_t* __restrict__ gm, int* __restrict__ orig, int* __restrict__ slot) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* b = buf + (size_t)k * GH_W;
+    pos[at + k] = make_double4(b[0], b[1], b[2], b[3]);
+    vel[at + k] = make_double4(0., 0., 0., 1.);
+    gm[at + k] = (uint32_t)__double2hiint(b[4]);
+    orig[at + k] = __double2loint(b[4]);
+    slot[k] = at + k;
+}
+__global__ void k_sl_remap(int n, int* __restrict__ idx, const int* __restrict__ newslot) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) idx[k] = newslot[idx[k]];
+}
+// ---- per-step halo ------------------------------------------------------------------------------------
+template <int FIELD>  // 0: x,y,z   1: w
+__global__ void k_sl_pack_halo(int n, const int* __restrict__ idx, const double4* __restrict__ pos, double* __restrict__ buf) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double4 p = pos[idx[k]];
+    if (FIELD == 0) { buf[3 * (size_t)k] = p.x; buf[3 * (size_t)k + 1] = p.y; buf[3 * (size_t)k + 2] = p.z; }
+    else buf[k] = p.w;
+}
+template <int FIELD>
+__global__ void k_sl_unpack_halo(int n, const int* __restrict__ slot, const double* __restrict__ buf, double4* __restrict__ pos) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double* p = reinterpret_cast<double*>(&pos[slot[k]]);
+    if (FIELD == 0) { p[0] = buf[3 * (size_t)k]; p[1] = buf[3 * (size_t)k + 1]; p[2] = buf[3 * (size_t)k + 2]; }
+    else p[3] = buf[k];
+}
+
+// ------------------------------------------------------------------------------------------------------
+int slab_unique_id(char* id128) {
+    g_nccl.load();
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return 0;
+}
+
+void slab_init(pfmds_ctx* c, int rank, int nranks, const char* id128, long long n_global, int n_local, int capacity) {
+    g_nccl.load();
+    Slab* s = new Slab;
+    c->slab = s;
+    s->rank = rank; s->nranks = nranks; s->left = (rank + nranks - 1) % nranks; s->right = (rank + 1) % nranks;
+    s->n_local = n_local; s->n_ghost = 0; s->cap = capacity; s->n_global = n_global;
+    s->W = c->box.L[0] / nranks;
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    NK(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
+    const size_t S = c->stride;
+    s->cap_border = (int)S;  // generous: the payload buffers can hold every slot
+    for (int d = 0; d < 2; ++d) {
+        CK(cudaMalloc(&s->send_idx[d], sizeof(int) * S));
+        CK(cudaMalloc(&s->ghost_slot[d], sizeof(int) * S));
+        CK(cudaMalloc(&s->sbuf[d], sizeof(double) * MIG_W * (S / 2 + 1024)));
+        CK(cudaMalloc(&s->rbuf[d], sizeof(double) * MIG_W * (S / 2 + 1024)));
+    }
+    CK(cudaMalloc(&s->cat, sizeof(int) * S));
+    CK(cudaMalloc(&s->flag, sizeof(int) * 3 * S));
+    for (int k = 0; k < 3; ++k) CK(cudaMalloc(&s->scan[k], sizeof(int) * S));
+    CK(cudaMalloc(&s->cnt_d, sizeof(int) * 16));
+    CK(cudaMalloc(&s->scan_tmp, sizeof(int) * (S / 2048 + 2)));
+    CK(cudaMalloc(&s->red_tmp, sizeof(double) * 64));
+    CK(cudaMalloc(&c->newslot, sizeof(int) * S));
+}
+
+void slab_destroy(pfmds_ctx* c) {
+    Slab* s = c->slab;
+    if (!s) return;
+    for (int d = 0; d < 2; ++d) { cudaFree(s->send_idx[d]); cudaFree(s->ghost_slot[d]); cudaFree(s->sbuf[d]); cudaFree(s->rbuf[d]); }
+    cudaFree(s->cat); cudaFree(s->flag); for (int k = 0; k < 3; ++k) cudaFree(s->scan[k]);
+    cudaFree(s->cnt_d); cudaFree(s->scan_tmp); cudaFree(s->red_tmp); cudaFree(c->newslot);
+    if (s->comm) g_nccl.CommDestroy(s->comm);
+    delete s;
+    c->slab = nullptr;
+}
+
+int slab_rank(pfmds_ctx* c) { return c->slab->rank; }
+int slab_nranks(pfmds_ctx* c) { return c->slab->nranks; }
+int slab_n_local(pfmds_ctx* c) { return c->slab->n_local; }
+long long slab_n_global(pfmds_ctx* c) { return c->slab->n_global; }
+
+void slab_allreduce_sum(pfmds_ctx* c, double* d, int n) {
+    NK(g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, ncclSum, c->slab->comm, c->st));
+}
+void slab_allreduce_max(pfmds_ctx* c, double* d, int n) {
+    NK(g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, ncclMax, c->slab->comm, c->st));
+}
+void slab_allreduce_max_int(pfmds_ctx* c, int* d, int n) {
+    NK(g_nccl.AllReduce(d, d, (size_t)n, ncclInt, ncclMax, c->slab->comm, c->st));
+}
+void slab_allreduce_sum_ll(pfmds_ctx* c, unsigned long long* d, int n) {
+    NK(g_nccl.AllReduce(d, d, (size_t)n, ncclUint64, ncclSum, c->slab->comm, c->st));
+}
+
+// send `ns[d]` items of width w from sbuf[d] to the neighbour in direction d (0 left, 1 right); what arrives from
+// the right neighbour was sent to ITS left, and lands in rbuf[1]
+static void neighbour_exchange(pfmds_ctx* c, Slab* s, const int* ns, const int* nr, int w) {
+    NK(g_nccl.GroupStart());
+    if (ns[0] > 0) NK(g_nccl.Send(s->sbuf[0], (size_t)ns[0] * w, ncclDouble, s->left, s->comm, c->st));
+    if (ns[1] > 0) NK(g_nccl.Send(s->sbuf[1], (size_t)ns[1] * w, ncclDouble, s->right, s->comm, c->st));
+    if (nr[1] > 0) NK(g_nccl.Recv(s->rbuf[1], (size_t)nr[1] * w, ncclDouble, s->right, s->comm, c->st));
+    if (nr[0] > 0) NK(g_nccl.Recv(s->rbuf[0], (size_t)nr[0] * w, ncclDouble, s->left, s->comm, c->st));
+    NK(g_nccl.GroupEnd());
+}
+// exchange two counts with the neighbours (host round trip: only at rebuild steps)
+static void exchange_counts(pfmds_ctx* c, Slab* s, const int* ns, int* nr) {
+    int h[2] = {ns[0], ns[1]};
+    CK(cudaMemcpyAsync(s->cnt_d + 8, h, sizeof h, cudaMemcpyHostToDevice, c->st));
+    NK(g_nccl.GroupStart());
+    NK(g_nccl.Send(s->cnt_d + 8, 1, ncclInt, s->left, s->comm, c->st));
+    NK(g_nccl.Send(s->cnt_d + 9, 1, ncclInt, s->right, s->comm, c->st));
+    NK(g_nccl.Recv(s->cnt_d + 11, 1, ncclInt, s->right, s->comm, c->st));
+    NK(g_nccl.Recv(s->cnt_d + 10, 1, ncclInt, s->left, s->comm, c->st));
+    NK(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(nr, s->cnt_d + 10, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+}
+
+// Rebuild step: migrate, then re-select and import ghosts.  Leaves c->N = n_local + n_ghost with the ghosts
+// appended; the cell re-sort that follows permutes everything and slab_after_reorder() fixes the index lists.
+void slab_redistribute(pfmds_ctx* c) {
+    Slab* s = c->slab;
+    const int T = 256;
+    const int N0 = c->N;
+    s->H = c->cell_rc;
+    if ((s->nranks == 2 && s->W <= 2.0 * s->H) || s->W <= s->H)
+        throw std::string("slab decomposition: slabs of width ") + std::to_string(s->W) + " A are too thin for a halo of " + std::to_string(s->H) + " A";
+    int *f0 = s->flag, *f1 = s->flag + c->stride, *f2 = s->flag + 2 * c->stride;
+    k_sl_classify<<<(N0 + T - 1) / T, T, 0, c->st>>>(N0, c->pos, c->gmask, c->orig, s->W, s->nranks, s->rank, s->cat, f0, f1, f2, c->err);
+    exclusive_scan(c, s, f0, s->scan[0], N0, s->cnt_d + 0);
+    exclusive_scan(c, s, f1, s->scan[1], N0, s->cnt_d + 1);
+    exclusive_scan(c, s, f2, s->scan[2], N0, s->cnt_d + 2);
+    int h[3];
+    CK(cudaMemcpyAsync(h, s->cnt_d, sizeof h, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    int ns[2] = {h[1], h[2]}, nr[2] = {0, 0};
+    exchange_counts(c, s, ns, nr);
+    const int n_stay = h[0];
+    if ((size_t)n_stay + nr[0] + nr[1] > c->stride) throw std::string("slab decomposition: capacity exceeded by migration");
+    k_sl_pack_migrants<<<(N0 + T - 1) / T, T, 0, c->st>>>(N0, c->pos, c->vel, c->gmask, c->orig, s->cat, s->scan[0], s->scan[1], s->scan[2], c->pos2,
+                                                         c->vel2, c->gmask2, c->orig2, s->sbuf[0], s->sbuf[1]);
+    std::swap(c->pos, c->pos2); std::swap(c->vel, c->vel2); std::swap(c->gmask, c->gmask2); std::swap(c->orig, c->orig2);
+    neighbour_exchange(c, s, ns, nr, MIG_W);
+    if (nr[0] > 0) k_sl_unpack_migrants<<<(nr[0] + T - 1) / T, T, 0, c->st>>>(nr[0], s->rbuf[0], n_stay, c->pos, c->vel, c->gmask, c->orig);
+    if (nr[1] > 0) k_sl_unpack_migrants<<<(nr[1] + T - 1) / T, T, 0, c->st>>>(nr[1], s->rbuf[1], n_stay + nr[0], c->pos, c->vel, c->gmask, c->orig);
+    s->n_local = n_stay + nr[0] + nr[1];
+    c->launches += 4;
+    // ghosts
+    const int NL = s->n_local;
+    const double x_lo = s->rank * s->W, x_hi = (s->rank + 1) * s->W;
+    k_sl_border_flags<<<(NL + T - 1) / T, T, 0, c->st>>>(NL, c->pos, x_lo, x_hi, s->H, f0, f1);
+    exclusive_scan(c, s, f0, s->scan[0], NL, s->cnt_d + 3);
+    exclusive_scan(c, s, f1, s->scan[1], NL, s->cnt_d + 4);
+    CK(cudaMemcpyAsync(h, s->cnt_d + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    s->n_send[0] = h[0]; s->n_send[1] = h[1];
+    exchange_counts(c, s, s->n_send, s->n_recv);
+    if ((size_t)NL + s->n_recv[0] + s->n_recv[1] > c->stride) throw std::string("slab decomposition: capacity exceeded by ghosts");
+    k_sl_pack_ghosts<<<(NL + T - 1) / T, T, 0, c->st>>>(NL, c->pos, c->gmask, c->orig, f0, f1, s->scan[0], s->scan[1], s->send_idx[0], s->send_idx[1],
+                                                       s->sbuf[0], s->sbuf[1]);
+    neighbour_exchange(c, s, s->n_send, s->n_recv, GH_W);
+    if (s->n_recv[0] > 0)
+        k_sl_unpack_ghosts<<<(s->n_recv[0] + T - 1) / T, T, 0, c->st>>>(s->n_recv[0], s->rbuf[0], NL, c->pos, c->vel, c->gmask, c->orig, s->ghost_slot[0]);
+    if (s->n_recv[1] > 0)
+        k_sl_unpack_ghosts<<<(s->n_recv[1] + T - 1) / T, T, 0, c->st>>>(s->n_recv[1], s->rbuf[1], NL + s->n_recv[0], c->pos, c->vel, c->gmask, c->orig,
+                                                                       s->ghost_slot[1]);
+    s->n_ghost = s->n_recv[0] + s->n_recv[1];
+    c->N = NL + s->n_ghost;
+    c->launches += 4;
+    CK(cudaGetLastError());
+}
+
+void slab_after_reorder(pfmds_ctx* c) {
+    Slab* s = c->slab;
+    const int T = 256;
+    for (int d = 0; d < 2; ++d) {
+        if (s->n_send[d] > 0) k_sl_remap<<<(s->n_send[d] + T - 1) / T, T, 0, c->st>>>(s->n_send[d], s->send_idx[d], c->newslot);
+        if (s->n_recv[d] > 0) k_sl_remap<<<(s->n_recv[d] + T - 1) / T, T, 0, c->st>>>(s->n_recv[d], s->ghost_slot[d], c->newslot);
+    }
+    c->launches += 4;
+}
+
+// field 0: ghost positions, field 1: ghost pos.w (1/Eb)
+void slab_exchange(pfmds_ctx* c, int field) {
+    Slab* s = c->slab;
+    const int T = 256;
+    KTimer kt(c, KS_OTHER);
+    for (int d = 0; d < 2; ++d) {
+        if (s->n_send[d] == 0) continue;
+        if (field == 0) k_sl_pack_halo<0><<<(s->n_send[d] + T - 1) / T, T, 0, c->st>>>(s->n_send[d], s->send_idx[d], c->pos, s->sbuf[d]);
+        else k_sl_pack_halo<1><<<(s->n_send[d] + T - 1) / T, T, 0, c->st>>>(s->n_send[d], s->send_idx[d], c->pos, s->sbuf[d]);
+    }
+    neighbour_exchange(c, s, s->n_send, s->n_recv, field == 0 ? 3 : 1);
+    for (int d = 0; d < 2; ++d) {
+        if (s->n_recv[d] == 0) continue;
+        if (field == 0) k_sl_unpack_halo<0><<<(s->n_recv[d] + T - 1) / T, T, 0, c->st>>>(s->n_recv[d], s->ghost_slot[d], s->rbuf[d], c->pos);
+        else k_sl_unpack_halo<1><<<(s->n_recv[d] + T - 1) / T, T, 0, c->st>>>(s->n_recv[d], s->ghost_slot[d], s->rbuf[d], c->pos);
+    }
+    c->launches += 4;
+    CK(cudaGetLastError());
+}

@@ -58,6 +58,8 @@ _SIGS = {
     "kernel_times": [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_longlong)],
     "timer_start": [C.c_void_p],
     "timer_stop": [C.c_void_p, _dp],
+    "create_slab": None,
+    "slab_download": None,
     "launch_count": [C.c_void_p, C.POINTER(C.c_longlong)],
     "synchronize": [C.c_void_p],
     "destroy": [C.c_void_p],
@@ -73,6 +75,8 @@ def load_library(path=LIB_PATH, prefix="pfmds_"):
     lib = C.CDLL(path)
     for name, args in _SIGS.items():
         fn = getattr(lib, prefix + name, None)
+        if args is None:
+            continue
         if fn is None:
             if name in _OPTIONAL:
                 continue

@@ -1,0 +1,94 @@
+"""Slab spatial decomposition driver (BASELINE.json configs[3]): one process per GPU, torch.distributed for the
+rendezvous, NCCL inside libpfmds_b200.so for the halo exchange (include/pfmds_b200.h, pfmds_create_slab)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .engine import Engine, KIND, LIB_PATH, PfmdsError, _d, _i, load_library  # noqa: F401
+from .inputs import group_indexes
+
+
+class SlabEngine(Engine):
+    """This rank's share of a case: atoms with x in [rank*Lx/world, (rank+1)*Lx/world)."""
+
+    def __init__(self, case, rank, world, device, unique_id, capacity_factor=1.6, lib_path=LIB_PATH):
+        self._lib = load_library(lib_path)
+        self._p = "pfmds_"
+        self._ctx = C.c_void_p()
+        L = self._lib
+        L.pfmds_create_slab.restype = C.c_int
+        L.pfmds_create_slab.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_longlong, C.c_int, C.POINTER(C.c_int),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint), C.c_int,
+                                        C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.c_int]
+        L.pfmds_slab_download.restype = C.c_int
+        L.pfmds_slab_download.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        box = np.ascontiguousarray(case["box"], np.float64)
+        n_global = len(case["mass"])
+        W = box[0] / world
+        owner = np.clip(np.floor(case["pos"][:, 0] / W).astype(np.int64), 0, world - 1)
+        mine = np.where(owner == rank)[0]
+        ng = len(case["groups"])
+        mask = np.zeros(n_global, np.uint32)
+        sizes = np.zeros(ng, np.int64)
+        for g in range(1, ng + 1):
+            idx = group_indexes(case, g)
+            sizes[g - 1] = len(idx)
+            mask[idx - 1] |= np.uint32(1 << (g - 1))
+        self.n = n_global
+        self.n_local0 = len(mine)
+        self.capacity = int(len(mine) * capacity_factor) + 4096
+        pos = np.ascontiguousarray(case["pos"][mine], np.float64).reshape(-1)
+        vel = np.ascontiguousarray(case["vel"][mine], np.float64).reshape(-1)
+        mass = np.ascontiguousarray(case["mass"][mine], np.float64)
+        gid = np.ascontiguousarray(mine + 1, np.int32)
+        m = np.ascontiguousarray(mask[mine], np.uint32)
+        self.groups = {g: group_indexes(case, g) for g in range(1, ng + 1)}
+        self.inter, self.nhc_M = [], []
+        self._call("create_slab", C.byref(self._ctx), device, rank, world, unique_id, n_global, len(mine), _i(gid), _d(pos), _d(vel), _d(mass),
+                   m.ctypes.data_as(C.POINTER(C.c_uint)), ng, sizes.ctypes.data_as(C.POINTER(C.c_longlong)), _d(box), self.capacity)
+
+    def set_group(self, g, idx1):
+        raise PfmdsError(1, "groups of a slab context are given at creation")
+
+    def download(self, forces=True):
+        """(global 1-based numbers, pos, vel, frc) of this rank's atoms."""
+        n = C.c_int()
+        gid = np.zeros(self.capacity, np.int32)
+        pos, vel = np.zeros((self.capacity, 3)), np.zeros((self.capacity, 3))
+        frc = np.zeros((self.capacity, 3)) if forces else None
+        self._call("slab_download", self._ctx, C.byref(n), _i(gid), _d(pos), _d(vel), _d(frc))
+        k = n.value
+        return gid[:k], pos[:k], vel[:k], (frc[:k] if forces else None)
+
+
+def make_unique_id(lib_path=LIB_PATH):
+    lib = load_library(lib_path)
+    buf = C.create_string_buffer(128)
+    lib.pfmds_slab_unique_id.argtypes = [C.c_char_p]
+    if lib.pfmds_slab_unique_id(buf) != 0:
+        raise PfmdsError(2, "pfmds_slab_unique_id failed (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
+def broadcast_unique_id(dist, device):
+    """Rank 0 creates the NCCL id of the library's communicator; torch.distributed carries the 128 bytes."""
+    import torch
+    t = torch.zeros(128, dtype=torch.uint8, device=device)
+    if dist.get_rank() == 0:
+        t = torch.tensor(list(make_unique_id()), dtype=torch.uint8, device=device)
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().tolist())
+
+
+def configure_slab(case, rank, world, device, unique_id, **kw):
+    e = SlabEngine(case, rank, world, device, unique_id, **kw)
+    r = case["roles"]
+    e.set_roles(r["all_moving"], r["xyz_moving"], r["z_moving"], r["all_atoms"])
+    for g, t, m, q in case["nhc"]:
+        e.add_nhc(g, t, m, q)
+    e.set_misc(case["zero_momentum_period"], case["invert_z_vel"])
+    for it in case["interactions"]:
+        e.add_interaction(it["name"], it["params"], it["lists"])
+    return e
