@@ -5,9 +5,13 @@ Workload at N=1: BASELINE.json configs[1] — Cu fcc crystal, rjl (Rosato-Guillo
 300 K, 63^3 cells = 1 000 188 atoms, dt 2 fs, neighbour-list rebuild every 20 steps, synthetic
 lattice with Maxwell velocities (seed 2).  One "step" is one MD step of md()'s loop
 (md_simulation.f90:138-186) through the C ABI (pfmds_advance), including the rebuilds that fall
-into the timed region.  N>1 (torchrun, one rank per GPU): the reference's MPI ensemble mode — every
-rank integrates its own replica of the workload (different velocity seed), no data-path collective;
-`value` is the sum over ranks divided by the slowest rank's device time ("scaling": "weak").
+into the timed region.  N>1 (torchrun, one rank per GPU), weak scaling at 1 000 188 atoms per GPU:
+  --decomp slab (default)   ONE crystal of N x 63 x 63 x 63 cells split into x-slabs (BASELINE.json configs[3]):
+                            ghost positions and ghost 1/Eb exchanged with the two neighbours every step,
+                            KE all-reduced for the thermostat, atoms migrate at list rebuilds (NCCL inside
+                            the library, on the context's stream);
+  --decomp ensemble         the reference's MPI mode: every rank integrates its own replica, no collective.
+`value` is the atoms of all ranks x steps divided by the slowest rank's device time.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cu_fcc|lj_fluid|ab_gas|graphene_cu]
 """
@@ -34,9 +38,12 @@ BYTES_PER_ATOM = {"rjl_force": lambda n: 4 * n + 32 + 32 + 64 + 8 + 4, "rjl_dens
                   "lj1g": lambda n: 4 * n + 32 + 32 + 64 + 4, "lj": lambda n: 4 * n + 32 + 32 + 64 + 4}
 
 
-def build_case(workload, seed, steps):
+def build_case(workload, seed, steps, nx=1):
     from pfmds_b200 import inputs
     if workload == "cu_fcc":
+        if nx > 1:
+            return (inputs.cu_fcc(cells=(63 * nx, 63, 63), seed=seed, steps=steps), "nvt",
+                    "Cu fcc %dx63x63 cells = %d atoms in x-slabs, rjl, NVT 300 K, dt 2 fs, r_cut 6.5, rebuild/20" % (63 * nx, 1000188 * nx))
         return inputs.cu_fcc(ncell=63, seed=seed, steps=steps), "nvt", "Cu fcc 63^3x4 = 1000188 atoms, rjl, NVT 300 K, dt 2 fs, r_cut 6.5, rebuild/20"
     if workload == "lj_fluid":
         return inputs.lj_fluid(n_side=128, seed=seed, steps=steps), "nve", "LJ fluid (lj1g) 128^3 = 2097152 atoms, NVE, dt 0.5 fs, r_cut 7.5, rebuild/20"
@@ -149,6 +156,7 @@ def main():
     ap.add_argument("--workload", default="cu_fcc")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--decomp", default="slab", choices=["slab", "ensemble"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -170,10 +178,19 @@ def main():
     build()
 
     K, W = args.steps, max(3, args.warmup)
-    case, integrator, desc = build_case(args.workload, seed=2 + rank, steps=K + W)
+    slab = world > 1 and args.decomp == "slab" and args.workload == "cu_fcc"
+    if slab:
+        from pfmds_b200.slab import broadcast_unique_id, configure_slab
+        case, integrator, desc = build_case(args.workload, seed=2, steps=K + W, nx=world)   # every rank builds the same crystal
+        uid = broadcast_unique_id(dist, torch.device("cuda", local))
+        eng = configure_slab(case, rank, world, local, uid, capacity_factor=1.25)
+        n_atoms = eng.n_local0
+    else:
+        case, integrator, desc = build_case(args.workload, seed=2 + rank, steps=K + W)
+        eng = configure(case, device=local)
+        n_atoms = len(case["mass"])
     dt = case["integrators"][0][1]
-    n_atoms = len(case["mass"])
-    eng = configure(case, device=local)
+    n_total = len(case["mass"]) if slab else n_atoms * world
 
     def barrier():
         if dist is not None:
@@ -183,7 +200,7 @@ def main():
     # ---- warm-up: step 0 (lists + forces) and W-1 steps ----
     eng.advance(integrator, dt, 0, W)
     eng.synchronize()
-    pairs = eng.pair_count(0, 0)
+    pairs = eng.pair_count(0, 0) // (world if slab else 1)   # the library sums over ranks in slab mode
 
     # ---- timed region: exactly K steps, device events on the library's stream, clocks sampled meanwhile ----
     launches0 = eng.launch_count()
@@ -201,7 +218,7 @@ def main():
     if dist is not None:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_max = float(ms_t.item())
-    value = n_atoms * world * K / (ms_max * 1e-3)
+    value = n_total * K / (ms_max * 1e-3)
 
     # ---- e2e: through the C ABI with host buffers.  Per run: H2D of positions+velocities from pinned host
     # memory, then every step pfmds_advance(1) + pfmds_energies (D2H of the step's energies, what md() logs
@@ -209,13 +226,21 @@ def main():
     e2e = None
     if not args.no_e2e:
         ke2e = min(K, 100)
-        hp = torch.empty((n_atoms, 3), dtype=torch.float64).pin_memory()
-        hv = torch.empty((n_atoms, 3), dtype=torch.float64).pin_memory()
-        hp.numpy()[:] = case["pos"]
-        hv.numpy()[:] = case["vel"]
+        if slab:
+            gid0, p0, v0, _ = eng.download(forces=False)
+            n_here = len(gid0)
+        else:
+            p0, v0, n_here = case["pos"], case["vel"], n_atoms
+        hp = torch.empty((n_here, 3), dtype=torch.float64).pin_memory()
+        hv = torch.empty((n_here, 3), dtype=torch.float64).pin_memory()
+        hp.numpy()[:] = p0
+        hv.numpy()[:] = v0
         barrier()
         t0 = time.perf_counter()
-        eng.upload_ptr(hp.data_ptr(), hv.data_ptr())
+        if slab:
+            eng.upload_local(hp.numpy(), hv.numpy())
+        else:
+            eng.upload_ptr(hp.data_ptr(), hv.data_ptr())
         eng.advance(integrator, dt, 0, 1)
         e_bytes = 0
         for s in range(1, ke2e + 1):
@@ -228,7 +253,7 @@ def main():
         te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_atoms * world * ke2e / float(te.item()), "unit": "atom-steps/s", "h2d_bytes_per_step": int(2 * 24 * n_atoms / ke2e),
+        e2e = {"value": n_total * ke2e / float(te.item()), "unit": "atom-steps/s", "h2d_bytes_per_step": int(2 * 24 * n_atoms / ke2e),
                "d2h_bytes_per_step": int(e_bytes + (3 * 32 + 4) * n_atoms / ke2e), "steps": ke2e,
                "what": "pfmds_upload(H2D pinned) + %d x [pfmds_advance(1) + pfmds_energies (D2H)] + pfmds_download(D2H)" % ke2e}
         del out
@@ -272,7 +297,7 @@ def main():
     line = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "atoms_per_gpu": n_atoms, "parallelism": "ensemble x%d (independent replicas, reference MPI mode)" % world if world > 1 else "single GPU",
+        "config": {"workload": desc, "atoms_per_gpu": n_atoms, "parallelism": ("x-slab decomposition over %d GPUs, NCCL halo exchange" % world if slab else "ensemble x%d (independent replicas, reference MPI mode)" % world) if world > 1 else "single GPU",
                    "l2": "working set (lists %.0f MB + state) exceeds the 126 MB L2" % (pairs * 4 / 1e6), "ns_per_day": K / (ms_max * 1e-3) * dt * 86400e-6},
         "clocks": cs.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},

@@ -143,6 +143,8 @@ int pfmds_create_slab(pfmds_ctx** ctx, int device, int rank, int nranks, const c
                       const int* global_index, const double* positions, const double* velocities, const double* masses,
                       const unsigned int* group_mask, int n_groups, const long long* group_sizes, const double box_size[3], int capacity);
 int pfmds_slab_download(pfmds_ctx* ctx, int* n_local, int* global_index, double* positions, double* velocities, double* forces);
+/* Overwrite the state of this rank's atoms, given in the order of the last pfmds_slab_download. */
+int pfmds_slab_upload(pfmds_ctx* ctx, int n_local, const double* positions, const double* velocities);
 
 /* Device self-test of the library's FP64 elementary functions against the CUDA math library: max errors
  * [0] exp (relative), [1] cosine switch / sincos (absolute), [2] rsqrt (relative), [3] hardware rsqrt seed. */

@@ -110,7 +110,11 @@ void finalize_slab(pfmds_ctx* c) {
         st[3 * (size_t)t.M + 2] = 1.;
         CK(cudaMemcpy(t.state, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
     }
-    c->nhc_fusable = false;  // the KE sum crosses ranks between the reduction and the chain update
+    c->nhc_fusable = !c->nhc.empty() && c->nhc.size() <= NHC_MAXF;  // distinct groups are assumed disjoint: checked below
+    for (size_t a = 0; a < c->nhc.size(); ++a)
+        for (size_t b = a + 1; b < c->nhc.size(); ++b)
+            if (c->nhc[a].group == c->nhc[b].group) c->nhc_fusable = false;
+    if (c->nhc.size() > 1) c->nhc_fusable = false;  // several thermostats: masks are not on the host in slab mode, keep the plain path
     if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
@@ -960,6 +964,33 @@ int pfmds_slab_download(pfmds_ctx* c, int* n_local, int* global_index, double* p
         };
         pull(c->pos, pos); pull(c->vel, vel); pull(c->frc, frc);
         check_device_error(c);
+    });
+}
+
+int pfmds_slab_upload(pfmds_ctx* c, int n_local, const double* pos, const double* vel) {
+    if (!c || !c->slab) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        integ_flush_pending(c);
+        c->nhc_ke_valid = false;
+        const size_t N = (size_t)c->N;
+        std::vector<uint32_t> hm(N);
+        CK(cudaMemcpyAsync(hm.data(), c->gmask, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        std::vector<double4> buf(N);
+        auto push = [&](double4* d, const double* in) {
+            if (!in) return;
+            CK(cudaMemcpyAsync(buf.data(), d, sizeof(double4) * N, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            size_t k = 0;
+            for (size_t s = 0; s < N; ++s)
+                if (!(hm[s] & PFMDS_GHOST)) { buf[s].x = in[3 * k]; buf[s].y = in[3 * k + 1]; buf[s].z = in[3 * k + 2]; ++k; }
+            if ((int)k != n_local) fail(PFMDS_ERR_INVALID, "error: pfmds_slab_upload expects the atoms of the last pfmds_slab_download");
+            CK(cudaMemcpyAsync(d, buf.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->st));
+            CK(cudaStreamSynchronize(c->st));
+        };
+        push(c->pos, pos); push(c->vel, vel);
+        for (auto& it : c->inter) for (int j = 0; j < it.nl_n; ++j) it.nl[j].built = false;
     });
 }
 

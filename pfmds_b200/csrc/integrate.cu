@@ -411,11 +411,27 @@ void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt) {
     k_reset_pending<<<1, 32, 0, c->st>>>(P);
     c->launches += 3;
 }
+__global__ void k_reduce_ke_partials(int nparts, const double* __restrict__ part, int n, double* __restrict__ out) {
+    for (int k = 0; k < n; ++k) {
+        double ke = 0;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i * NHC_MAXF + k];
+        ke = block_sum(ke);
+        if (threadIdx.x == 0) out[k] = ke;
+        __syncthreads();
+    }
+}
 void integ_nvt_kick_close(pfmds_ctx* c, double dt) {
     NhcPack P = pack_of(c);
     KTimer kt(c, KS_KICK);
     k_kick_ke<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2, P, c->part);
-    k_nhc_close<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
+    if (c->slab) {  // rank-local sums, one all-reduce, then every rank runs the same chain update
+        k_reduce_ke_partials<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, P.n, c->red + 48);
+        slab_allreduce_sum(c, c->red + 48, P.n);
+        k_nhc_close<<<1, 32, 0, c->st>>>(1, c->red + 48, P, dt / 2, dt / 4, dt / 8);
+        c->launches += 1;
+    } else {
+        k_nhc_close<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
+    }
     c->launches += 2;
 }
 // apply scalings that are still pending (before anything else reads or changes velocities)

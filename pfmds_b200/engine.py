@@ -60,6 +60,7 @@ _SIGS = {
     "timer_stop": [C.c_void_p, _dp],
     "create_slab": None,
     "slab_download": None,
+    "slab_upload": None,
     "launch_count": [C.c_void_p, C.POINTER(C.c_longlong)],
     "synchronize": [C.c_void_p],
     "destroy": [C.c_void_p],

@@ -63,6 +63,15 @@ class SlabEngine(Engine):
         return gid[:k], pos[:k], vel[:k], (frc[:k] if forces else None)
 
 
+    def upload_local(self, pos, vel):
+        """Overwrite this rank's atoms (order of the last download)."""
+        self._lib.pfmds_slab_upload.restype = C.c_int
+        self._lib.pfmds_slab_upload.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        pos = np.ascontiguousarray(pos, np.float64)
+        vel = np.ascontiguousarray(vel, np.float64)
+        self._call("slab_upload", self._ctx, len(pos), _d(pos.reshape(-1)), _d(vel.reshape(-1)))
+
+
 def make_unique_id(lib_path=LIB_PATH):
     lib = load_library(lib_path)
     buf = C.create_string_buffer(128)
