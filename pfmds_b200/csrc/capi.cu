@@ -195,7 +195,13 @@ void finalize(pfmds_ctx* c) {
             CK(cudaMalloc(&l.nnum, sizeof(int) * c->stride));
             CK(cudaMemsetAsync(l.nnum, 0, sizeof(int) * c->stride, c->st));
         }
-        if (it.kind == K_TB) CK(cudaMalloc(&it.aux, sizeof(double) * (size_t)a.maxn * c->stride));
+        if (it.kind == K_TB) {
+            size_t need = ((size_t)N + 127) / 128 * (size_t)a.maxn + 16;  // energy partials: one per (block, slot)
+            if (need > c->part_cap) { cudaFree(c->part); CK(cudaMalloc(&c->part, sizeof(double) * need)); c->part_cap = need; }
+            CK(cudaMalloc(&it.aux, sizeof(double) * (size_t)a.maxn * c->stride));
+            CK(cudaMalloc(&it.aux2, sizeof(double) * (size_t)a.maxn * c->stride));
+            CK(cudaMalloc(&it.fpart, sizeof(double4) * (size_t)a.maxn * c->stride));
+        }
         if (it.kind == K_LJC || it.kind == K_MORSEC) {
             CK(cudaMalloc(&it.gnorm, sizeof(double4) * c->stride));
             CK(cudaMalloc(&it.tvec, sizeof(double4) * c->stride));
@@ -448,6 +454,7 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         CK(cudaMalloc(&c->posf, sizeof(float4) * S));
         size_t nparts = (S + 127) / 128 + RED_BLOCKS;
         CK(cudaMalloc(&c->part, sizeof(double) * 16 * nparts));
+        c->part_cap = 16 * nparts;
         CK(cudaMalloc(&c->red, sizeof(double) * 64));
         CK(cudaMalloc(&c->err, sizeof(int) * PFMDS_ERRW));
         CK(cudaMemset(c->err, 0, sizeof(int) * PFMDS_ERRW));
@@ -1014,7 +1021,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     slab_destroy(c);
     for (auto& it : c->inter) {
         for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nlist_alt); cudaFree(it.nl[j].nnum); }
-        cudaFree(it.aux); cudaFree(it.gnorm); cudaFree(it.tvec);
+        cudaFree(it.aux); cudaFree(it.aux2); cudaFree(it.fpart); cudaFree(it.gnorm); cudaFree(it.tvec);
     }
     for (auto& t : c->nhc) cudaFree(t.state);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,

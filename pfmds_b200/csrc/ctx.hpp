@@ -30,6 +30,8 @@ struct Inter {
     NList nl[3];
     LJp lj{}; LJ1Gp lj1g{}; LJCp ljc{}; MORp mor{}; TBp tb{}; RJLp rjl{};
     double* aux = nullptr;    // tb: bond orders B, ELL [maxn][stride]  (rjl keeps 1/Eb in pos[].w)
+    double* aux2 = nullptr;   // tb: B^(1/delt+1)
+    double4* fpart = nullptr; // tb: per-(slot, atom) force contributions, summed per atom in slot order
     double4* gnorm = nullptr; // ljc/morsec: unit normal per carbon atom {nx,ny,nz,-}
     double4* tvec = nullptr;  // ljc/morsec: T_i = sum_p V2 V3 f_c/(n_i.dr) dr  (normal-derivative term)
 };
@@ -60,7 +62,8 @@ struct pfmds_ctx {
     int *cell_cnt = nullptr, *cell_start = nullptr, *cell_atoms = nullptr, *cid = nullptr, *scan_tmp = nullptr;
     bool identity_order = false;  // cell_atoms[k]==k (atoms physically in cell order)
     // reductions
-    double* part = nullptr;   // [RED_BLOCKS][8] block partials
+    double* part = nullptr;   // block partials of the two-stage reductions
+    size_t part_cap = 0;
     double* red = nullptr;    // [64] reduced values
     double* energy = nullptr; // [n_inter] device energies
     int* err = nullptr;       // [PFMDS_ERRW]

@@ -273,56 +273,63 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4
 // ---- tb : TersoffBrenner.f90:26-150 -------------------------------------------------------------
 __device__ __forceinline__ double tb_G(double c1, const TBp& T) { return 1. + T.c02 / T.d02 - T.c02 / (T.d02 + c1 * c1); }  // c1 = 1+cos
 
-// pass A: bond orders B(p,i) = (1 + a0 sum_{q!=p} f_c(r_q) G(theta_pq))^-delt, 0 for r_p >= R2  (:83-96)
-__global__ void __launch_bounds__(FT) k_tb_bond(int N, const double4* __restrict__ pos, ListView lv, TBp T, BoxD box, double* __restrict__ B) {
+// One thread per (atom, slot) pair — blockIdx.y is the slot — so a graphene sheet of a few thousand atoms
+// still fills the machine; the per-slot force contributions go to a scratch ELL block and are summed per atom
+// in slot order by k_tb_reduce (deterministic, no atomics).
+// pass A: bond orders B(p,i) = (1 + a0 sum_{q!=p} f_c(r_q) G(theta_pq))^-delt, 0 for r_p >= R2  (:83-96).
+// Both B and B^(1/delt+1) = (1 + a0 zeta)^-(delt+1) are stored, from one logarithm: pass B then needs no pow().
+__global__ void __launch_bounds__(FT) k_tb_bond(int N, const double4* __restrict__ pos, ListView lv, TBp T, BoxD box, double* __restrict__ B,
+                                                double* __restrict__ Bx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y;
     if (i >= N) return;
     int n = lv.nnum[i];
-    if (n == 0) return;
+    if (p >= n) return;
     const double4 pi = pos[i];
-    for (int p = 0; p < n; ++p) {
-        double rp2;
-        Vec dp = bond_vec(pi, pos[lv.nlist[(size_t)p * lv.stride + i]], box, rp2);
-        double rp = sqrt(rp2), b = 0.;
-        if (rp < T.R2) {
-            double z = 0.;
-            for (int q = 0; q < n; ++q) {
-                if (q == p) continue;
-                double rq2;
-                Vec dq = bond_vec(pi, pos[lv.nlist[(size_t)q * lv.stride + i]], box, rq2);
-                double rq = sqrt(rq2);
-                if (rq < T.R2) z += fcut_only(rq, T.R1, T.R2) * tb_G(1. + dot(dp, dq) / (rp * rq), T);
-            }
-            b = pow(1. + T.a0 * z, -T.delt);
+    double rp2;
+    Vec dp = bond_vec(pi, pos[lv.nlist[(size_t)p * lv.stride + i]], box, rp2);
+    double rp = sqrt(rp2), b = 0., bx = 0.;
+    if (rp < T.R2) {
+        double z = 0.;
+        for (int q = 0; q < n; ++q) {
+            if (q == p) continue;
+            double rq2;
+            Vec dq = bond_vec(pi, pos[lv.nlist[(size_t)q * lv.stride + i]], box, rq2);
+            double rq = sqrt(rq2);
+            if (rq < T.R2) z += fcut_only(rq, T.R1, T.R2) * tb_G(1. + dot(dp, dq) / (rp * rq), T);
         }
-        B[(size_t)p * lv.stride + i] = b;
+        double L = mx::log_fast(1. + T.a0 * z);
+        b = mx::exp_fast(-T.delt * L);
+        bx = mx::exp_fast(-(T.delt + 1.) * L);
     }
+    B[(size_t)p * lv.stride + i] = b;
+    Bx[(size_t)p * lv.stride + i] = bx;
 }
-// pass B: forces (:99-146) and/or energy (:53-66).  Bonds and partners beyond R2 contribute exactly
+// pass B: forces (:99-146) and/or energy (:53-66) of one bond.  Bonds and partners beyond R2 contribute exactly
 // zero in the reference (f_cut = df_cut = 0, B = 0) and are skipped.
 template <bool F, bool E>
-__global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, TBp T, BoxD box,
-                                                 const double* __restrict__ B, double* part) {
+__global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restrict__ pos, double4* __restrict__ fpart, ListView lv, TBp T, BoxD box,
+                                                 const double* __restrict__ B, const double* __restrict__ Bx, double* part) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y;
     double e = 0, fx = 0, fy = 0, fz = 0;
     int n = i < N ? lv.nnum[i] : 0;
-    if (n > 0) {
+    if (p < n) {
         const double4 pi = pos[i];
-        const double ex = 1. / T.delt + 1.;
         const double s2s = sqrt(2. * T.s), s2is = sqrt(2. / T.s), dpre = T.d / (T.s - 1.);
-        for (int p = 0; p < n; ++p) {
+        do {
             int j = lv.nlist[(size_t)p * lv.stride + i];
             const double4 pj = pos[j];
             double rp2;
             Vec dp = bond_vec(pi, pj, box, rp2);
             double rp = sqrt(rp2);
-            if (!(rp < T.R2)) continue;
+            if (!(rp < T.R2)) break;
             double Bip = B[(size_t)p * lv.stride + i];
             // reverse slot: i in j's row
             int nj = lv.nnum[j], l = 0;
             for (; l < nj; ++l)
                 if (lv.nlist[(size_t)l * lv.stride + j] == i) break;
-            if (l >= nj) continue;  // cannot happen: same group, same r_cut, symmetric dr2
+            if (l >= nj) break;  // cannot happen: same group, same r_cut, symmetric dr2
             double Bjl = B[(size_t)l * lv.stride + j];
             double f_c, dfr_p;
             fcut_dfcut(rp, T.R1, T.R2, f_c, dfr_p);
@@ -348,10 +355,10 @@ __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restric
                     dB.y += g1 * ((dp.y + dq.y) * rr - cosi * (dp.y / rp2 + dq.y / rq2)) + g2 * dq.y;
                     dB.z += g1 * ((dp.z + dq.z) * rr - cosi * (dp.z / rp2 + dq.z / rq2)) + g2 * dq.z;
                 }
-                double bp = pow(Bip, ex);
+                double bp = Bx[(size_t)p * lv.stride + i];
                 dB.x *= bp; dB.y *= bp; dB.z *= bp;
                 const Vec dl = {-dp.x, -dp.y, -dp.z};  // j -> i
-                double bl = pow(Bjl, ex);
+                double bl = Bx[(size_t)l * lv.stride + j];
                 double cx = 0, cy = 0, cz = 0;  // cross terms :142-152
                 for (int q = 0; q < nj; ++q) {  // :126-133 and :142-152 share the geometry of j's row
                     if (q == l) continue;
@@ -365,7 +372,7 @@ __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restric
                     Vec w = {-dq.x * rr + cosi * dl.x / rp2, -dq.y * rr + cosi * dl.y / rp2, -dq.z * rr + cosi * dl.z / rp2};
                     double g = bl * fq * gg;
                     dB.x += g * w.x; dB.y += g * w.y; dB.z += g * w.z;
-                    double pre = T.delt / 2 * pow(B[(size_t)q * lv.stride + j], ex);
+                    double pre = T.delt / 2 * Bx[(size_t)q * lv.stride + j];
                     double g1 = f_c * gg, g2 = dfr_p * T.a0 * tb_G(c1, T);
                     double tail = fq * dpre * T.s * mx::exp_fast(-s2s * T.b * (rq - T.r0) / T.s);
                     cx += pre * (g1 * w.x + dp.x * g2) * tail;
@@ -378,14 +385,29 @@ __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restric
                 double k1 = (dff - s2s * T.b / rp) * ea;       // multiplies dp
                 double k2 = (Bip + Bjl) / 2 * (dff - s2is * T.b / rp);
                 double A = f_c * dpre, se = T.s * eas;
-                fx += A * (dp.x * k1 - (dB.x + k2 * dp.x) * se) + cx;
-                fy += A * (dp.y * k1 - (dB.y + k2 * dp.y) * se) + cy;
-                fz += A * (dp.z * k1 - (dB.z + k2 * dp.z) * se) + cz;
+                fx = A * (dp.x * k1 - (dB.x + k2 * dp.x) * se) + cx;
+                fy = A * (dp.y * k1 - (dB.y + k2 * dp.y) * se) + cy;
+                fz = A * (dp.z * k1 - (dB.z + k2 * dp.z) * se) + cz;
             }
-        }
-        if (F) add_force(frc, i, fx, fy, fz);
+        } while (false);
+        if (F) fpart[(size_t)p * lv.stride + i] = make_double4(fx, fy, fz, 0.);
     }
-    if (E) store_partial(e, part);
+    if (E) {
+        double s = block_sum(e);
+        if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(FT) k_tb_reduce(int N, const double4* __restrict__ fpart, double4* __restrict__ frc, ListView lv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int n = lv.nnum[i];
+    if (n == 0) return;
+    double fx = 0, fy = 0, fz = 0;
+    for (int p = 0; p < n; ++p) {
+        double4 f = fpart[(size_t)p * lv.stride + i];
+        fx += f.x; fy += f.y; fz += f.z;
+    }
+    add_force(frc, i, fx, fy, fz);
 }
 
 // ---- graphene normals : graphenenorm.f90:38-56 ----------------------------------------------------
@@ -437,7 +459,7 @@ __global__ void __launch_bounds__(FT) k_cos_direct(int N, const double4* __restr
                 double V2 = cos_V2<MORSE>(r, r2, P), V1 = V2 * V2;
                 double cosn = fabs(nd) / r;
                 if (MORSE && !GRAPHENE) cosn = fabs(nd) / (sqrt(nv.x * nv.x + nv.y * nv.y + nv.z * nv.z) * r);  // MorseCosine.f90:127
-                double V3 = pow(cosn, P.delt);
+                double V3 = mx::pow_pos(cosn, P.delt);
                 double f, dfr;
                 fcut_dfcut(r, P.R1, P.R2, f, dfr);
                 if (E) e += MORSE ? P.pe * (V1 - 2. * V2 * V3) * f : P.pe * (V1 - V2 * V3) * f;
@@ -548,9 +570,16 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
         c->launches += 2;
         break;
     case K_TB:
-        { KTimer kt(c, KS_TB_BOND); k_tb_bond<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux); }
-        { KTimer kt(c, KS_TB_FORCE); k_tb_force<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.tb, c->box, it.aux, nullptr); }
-        c->launches += 2;
+    {
+        dim3 grid(nb, it.nl[0].maxn);
+        { KTimer kt(c, KS_TB_BOND); k_tb_bond<<<grid, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2); }
+        {
+            KTimer kt(c, KS_TB_FORCE);
+            k_tb_force<true, false><<<grid, FT, 0, c->st>>>(N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, nullptr);
+            k_tb_reduce<<<nb, FT, 0, c->st>>>(N, it.fpart, c->frc, it.nl[0].view(st));
+        }
+        c->launches += 3;
+    }
         break;
     case K_LJC:
     case K_MORSEC: {
@@ -577,6 +606,7 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     const int N = c->N, nb = (N + FT - 1) / FT;
     const size_t st = c->stride;
     double scale = 1.0;
+    int nparts = nb;
     switch (it.kind) {
     case K_LJ: k_lj<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
     case K_LJ1G: k_lj1g<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
@@ -584,15 +614,18 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
         k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
         break;
     }
-    case K_TB:
-        k_tb_bond<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux);
-        k_tb_force<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.tb, c->box, it.aux, c->part);
+    case K_TB: {
+        dim3 grid(nb, it.nl[0].maxn);
+        k_tb_bond<<<grid, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2);
+        k_tb_force<false, true><<<grid, FT, 0, c->st>>>(N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, c->part);
+        nparts = nb * it.nl[0].maxn;
         c->launches += 1;
         break;
+    }
     case K_LJC: k_cos_direct<false, true, false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
     case K_MORSEC: k_cos_direct<true, true, false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
     }
-    k_sum_partials<<<1, 1024, 0, c->st>>>(nb, c->part, scale, c->energy + k);
+    k_sum_partials<<<1, 1024, 0, c->st>>>(nparts, c->part, scale, c->energy + k);
     c->launches += 2;
     if (c->slab) slab_allreduce_sum(c, c->energy + k, 1);
     CK(cudaGetLastError());

@@ -201,4 +201,46 @@ MX_HD double rsqrt_fast(double x) {
     return fma(y * e, t, y);
 }
 
+// 1/x for normal x: hardware seed (MUFU.RCP64H) and one third-order step y <- y + y (e + e^2), e = 1 - x y.
+MX_HD double rcp_fast(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    double y = (double)(1.0f / (float)x) * (1.0 + 9e-7);
+#endif
+    double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+
+// log(x) for normal positive x: x = m 2^k with m in [sqrt(1/2), sqrt(2)), log m = 2 atanh(s), s = (m-1)/(m+1),
+// |s| <= 0.1716, odd series to s^19 (truncation 4e-18).
+MX_CONST double LOG_C[10] = {2.0, 2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0, 2.0 / 17.0, 2.0 / 19.0};
+MX_HD double log_fast(double x) {
+    long long b = as_ll(x);
+    int k = (int)(b >> 52) - 1023;
+    long long mb = (b & 0x000fffffffffffffll) | 0x3ff0000000000000ll;  // m in [1,2)
+    double m = as_double(mb);
+    if (m > 1.4142135623730951) { m *= 0.5; k += 1; }
+    double s = (m - 1.0) * rcp_fast(m + 1.0);
+    double s2 = s * s;
+    double p = LOG_C[9];
+    p = fma(p, s2, LOG_C[8]);
+    p = fma(p, s2, LOG_C[7]);
+    p = fma(p, s2, LOG_C[6]);
+    p = fma(p, s2, LOG_C[5]);
+    p = fma(p, s2, LOG_C[4]);
+    p = fma(p, s2, LOG_C[3]);
+    p = fma(p, s2, LOG_C[2]);
+    p = fma(p, s2, LOG_C[1]);
+    p = fma(p, s2, LOG_C[0]);
+    double kd = (double)k;
+    return fma(kd, 6.93147180369123816490e-01, fma(s, p, kd * 1.90821492927058770002e-10));
+}
+// x^y for x >= 0 (0^y = 0 for y > 0), as the potentials use it: exp(y log x)
+MX_HD double pow_pos(double x, double y) {
+    if (!(x > 0.0)) return 0.0;
+    return exp_fast(y * log_fast(x));
+}
+
 }  // namespace mx

@@ -78,6 +78,27 @@ def test_exp_tab(lib):
     assert len(tab) == 32 and np.max(np.abs(np.array(tab) / t - 1)) < 2e-16
 
 
+def test_log_pow_rcp(lib):
+    for f in (lib.mx_log, lib.mx_rcp):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double]
+    lib.mx_pow.restype = C.c_double
+    lib.mx_pow.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(8)
+    xs = np.concatenate([10.0 ** rng.uniform(-12, 12, 20000), rng.uniform(0.5, 2.0, 20000), 1 + rng.uniform(-1e-6, 1e-6, 2000)])
+    got = np.array([lib.mx_log(float(x)) for x in xs])
+    ref = np.log(xs.astype(np.longdouble)).astype(np.float64)
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-15 * 1e3 and np.max(np.abs(got - ref)) < 1e-14
+    got = np.array([lib.mx_rcp(float(x)) * x for x in xs])
+    assert np.max(np.abs(got - 1)) < 5e-16
+    xs = rng.uniform(1e-6, 3.0, 20000)
+    ys = rng.uniform(-3, 3, 20000)
+    got = np.array([lib.mx_pow(float(x), float(y)) for x, y in zip(xs, ys)])
+    ref = (xs.astype(np.longdouble) ** ys.astype(np.longdouble)).astype(np.float64)
+    assert np.max(np.abs(got - ref) / ref) < 1e-13
+    assert lib.mx_pow(0.0, 2.0) == 0.0
+
+
 def test_rsqrt(lib):
     rng = np.random.default_rng(3)
     xs = np.concatenate([rng.uniform(0.01, 200, 20000), 10.0 ** rng.uniform(-10, 10, 5000)])
