@@ -34,6 +34,17 @@ __device__ __forceinline__ void add_force(double4* frc, int i, double fx, double
     frc[i] = f;
 }
 
+// Small systems: SPLIT lanes share one atom's row (slot p = sub, sub+SPLIT, ...) and combine with a fixed
+// xor-shuffle tree, so a few thousand atoms still give the SMs enough warps.  SPLIT = 1 is thread-per-atom.
+template <int SPLIT>
+__device__ __forceinline__ double split_sum(double v) {
+#pragma unroll
+    for (int o = SPLIT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#define SMALL_SPLIT 8
+#define SMALL_N 100000
+
 // per-block partial of the per-thread energy; the final sum is done by k_sum_partials in block order
 __device__ __forceinline__ void store_partial(double e, double* part) {
     double s = block_sum(e);
@@ -47,16 +58,16 @@ __global__ void k_sum_partials(int n, const double* __restrict__ part, double sc
 }
 
 // ---- lj : LennardJones.f90:23-69 ----------------------------------------------------------------
-template <bool F, bool E>
+template <bool F, bool E, int SPLIT>
 __global__ void __launch_bounds__(FT) k_lj(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJp P, BoxD box,
                                            double* part) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double e = 0, fx = 0, fy = 0, fz = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
         const double4 pi = pos[i];
         const double R22 = P.R2 * P.R2, s2 = P.sig * P.sig;
-        for (int p = 0; p < n; ++p) {
+        for (int p = sub; p < n; p += SPLIT) {
             int j = lv.nlist[(size_t)p * lv.stride + i];
             double r2;
             Vec d = bond_vec(pi, pos[j], box, r2);
@@ -74,7 +85,10 @@ __global__ void __launch_bounds__(FT) k_lj(int N, const double4* __restrict__ po
                 }
             }
         }
-        if (F) add_force(frc, i, fx, fy, fz);
+    }
+    if (F) {
+        fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz);
+        if (n > 0 && sub == 0) add_force(frc, i, fx, fy, fz);
     }
     if (E) store_partial(e, part);
 }
@@ -83,16 +97,16 @@ __global__ void __launch_bounds__(FT) k_lj(int N, const double4* __restrict__ po
 // The reference visits each pair once (p <= lessnnum) and scatters +-F*dr to both atoms; with a
 // symmetric full list the same sum is a gather over all neighbours.  The switch derivative keeps the
 // reference's missing 1/(R2-R1) factor (cut_off_poly.f90:41).
-template <bool F, bool E>
+template <bool F, bool E, int SPLIT>
 __global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJ1Gp P, BoxD box,
                                              double* part) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double e = 0, fx = 0, fy = 0, fz = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
         const double4 pi = pos[i];
         const double R22 = P.R2 * P.R2, iw = 1.0 / (P.R2 - P.R1);
-        for (int p = 0; p < n; ++p) {
+        for (int p = sub; p < n; p += SPLIT) {
             int j = lv.nlist[(size_t)p * lv.stride + i];
             double r2;
             Vec d = bond_vec(pi, pos[j], box, r2);
@@ -113,7 +127,10 @@ __global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ 
                 }
             }
         }
-        if (F) add_force(frc, i, fx, fy, fz);
+    }
+    if (F) {
+        fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz);
+        if (n > 0 && sub == 0) add_force(frc, i, fx, fy, fz);
     }
     if (E) store_partial(e, part);
 }
@@ -220,6 +237,26 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* po
     if (E) store_partial(e, part);
 }
 
+// small systems: SPLIT lanes per atom, plain loop (latency is hidden by the extra warps)
+template <bool E, int SPLIT>
+__global__ void __launch_bounds__(FT) k_rjl_density_split(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
+    double e = 0, sq = 0, sp = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = ld256(&pos[i]);
+        for (int p = sub; p < n; p += SPLIT) rjl_density_pair<E>(pi, ld256(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, nullptr, sq, sp);
+    }
+    sq = split_sum<SPLIT>(sq);
+    if (E) sp = split_sum<SPLIT>(sp);
+    if (n > 0 && sub == 0) {
+        double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
+        reinterpret_cast<double*>(&pos[i])[3] = ie;
+        if (E) e = C.A0 * sp - C.xi * (sq * ie);
+    }
+    if (E) store_partial(e, part);
+}
+
 __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, const double* tab, double& fx,
                                                double& fy, double& fz) {
     double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
@@ -268,6 +305,20 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4
     }
     if (p < n) rjl_force_pair(pi, a, C, box, W.min_half_hi, tab, fx, fy, fz);
     add_force(frc, i, fx, fy, fz);
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
+                                                        WrapC W) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
+    double fx = 0, fy = 0, fz = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = ld256_nc(&pos[i]);
+        for (int p = sub; p < n; p += SPLIT) rjl_force_pair(pi, ld256_nc(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, nullptr, fx, fy, fz);
+    }
+    fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz);
+    if (n > 0 && sub == 0) add_force(frc, i, fx, fy, fz);
 }
 
 // ---- tb : TersoffBrenner.f90:26-150 -------------------------------------------------------------
@@ -439,16 +490,16 @@ __device__ __forceinline__ double cos_V2(double r, double r2, const CosP& P) {
 // Direct term for the atoms of one side.  GRAPHENE: owner i is a carbon atom with its own normal and
 // the kernel also accumulates T_i = sum_p V2 V3 f_c /(n_i.dr) dr for the normal-derivative term.
 // Otherwise the owner is a metal atom and the normal is that of the carbon partner (:112-139).
-template <bool MORSE, bool GRAPHENE, bool F, bool E>
+template <bool MORSE, bool GRAPHENE, bool F, bool E, int SPLIT>
 __global__ void __launch_bounds__(FT) k_cos_direct(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CosP P, BoxD box,
                                                    const double4* __restrict__ gnorm, double4* __restrict__ tvec, double* part) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double e = 0, fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
         const double4 pi = pos[i];
         double4 nv = GRAPHENE ? gnorm[i] : make_double4(0, 0, 0, 0);
-        for (int p = 0; p < n; ++p) {
+        for (int p = sub; p < n; p += SPLIT) {
             int j = lv.nlist[(size_t)p * lv.stride + i];
             double r2;
             Vec d = bond_vec(pi, pos[j], box, r2);
@@ -482,12 +533,14 @@ __global__ void __launch_bounds__(FT) k_cos_direct(int N, const double4* __restr
                 }
             }
         }
-        if (F) {
-            add_force(frc, i, fx, fy, fz);
+    }
+    if (F) {
+        fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz);
+        if (GRAPHENE) { tx = split_sum<SPLIT>(tx); ty = split_sum<SPLIT>(ty); tz = split_sum<SPLIT>(tz); }
+        if (sub == 0 && i < N) {
+            if (n > 0) add_force(frc, i, fx, fy, fz);
             if (GRAPHENE) tvec[i] = make_double4(tx, ty, tz, 0.);
         }
-    } else if (F && GRAPHENE && i < N) {
-        tvec[i] = make_double4(0., 0., 0., 0.);
     }
     if (E) store_partial(e, part);
 }
@@ -548,24 +601,34 @@ void normals_interaction(pfmds_ctx* c, int k) {  // update_norm_in_graphene, md_
 void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interactions.f90:210-242
     Inter& it = c->inter[k];
     const int N = c->N, nb = (N + FT - 1) / FT;
+    const bool small = N < SMALL_N;
+    const int nbs = (int)(((size_t)N * SMALL_SPLIT + FT - 1) / FT);
     const size_t st = c->stride;
     switch (it.kind) {
     case K_LJ:
-        { KTimer kt(c, KS_LJ); k_lj<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); }
-        { KTimer kt(c, KS_LJ); k_lj<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); }
+        { KTimer kt(c, KS_LJ); if (small) k_lj<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); else k_lj<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); }
+        { KTimer kt(c, KS_LJ); if (small) k_lj<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); else k_lj<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); }
         c->launches += 2;
         break;
     case K_LJ1G:
-        { KTimer kt(c, KS_LJ1G); k_lj1g<true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); }
+        { KTimer kt(c, KS_LJ1G); if (small) k_lj1g<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); else k_lj1g<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); }
         c->launches += 1;
         break;
     case K_RJL:
     {
         const RjlC C = rjl_consts(it.rjl);
         const WrapC W = wrap_consts(c->box);
-        { KTimer kt(c, KS_RJL_DENSITY); k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr); }
+        {
+            KTimer kt(c, KS_RJL_DENSITY);
+            if (small) k_rjl_density_split<false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr);
+            else k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr);
+        }
         if (c->slab) slab_exchange(c, 1);  // ghost 1/Eb from their owners
-        { KTimer kt(c, KS_RJL_FORCE); k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W); }
+        {
+            KTimer kt(c, KS_RJL_FORCE);
+            if (small) k_rjl_force_split<SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W);
+            else k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W);
+        }
     }
         c->launches += 2;
         break;
@@ -586,13 +649,13 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
         CosP P = cosp_of(it);
         bool simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
         if (it.kind == K_LJC) {
-            { KTimer kt(c, KS_COS_GRAPHENE); k_cos_direct<false, true, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_GRAPHENE); if (small) k_cos_direct<false, true, true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else k_cos_direct<false, true, true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
             if (!simp) { KTimer kt(c, KS_COS_INDIRECT); k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec); }
-            { KTimer kt(c, KS_COS_METAL); k_cos_direct<false, false, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_METAL); if (small) k_cos_direct<false, false, true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else k_cos_direct<false, false, true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         } else {
-            { KTimer kt(c, KS_COS_GRAPHENE); k_cos_direct<true, true, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_GRAPHENE); if (small) k_cos_direct<true, true, true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else k_cos_direct<true, true, true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
             if (!simp) { KTimer kt(c, KS_COS_INDIRECT); k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec); }
-            { KTimer kt(c, KS_COS_METAL); k_cos_direct<true, false, true, false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_METAL); if (small) k_cos_direct<true, false, true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else k_cos_direct<true, false, true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         }
         c->launches += simp ? 2 : 3;
         break;
@@ -606,12 +669,15 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     const int N = c->N, nb = (N + FT - 1) / FT;
     const size_t st = c->stride;
     double scale = 1.0;
-    int nparts = nb;
+    const bool small = N < SMALL_N;
+    const int nbs = (int)(((size_t)N * SMALL_SPLIT + FT - 1) / FT);
+    int nparts = small ? nbs : nb;
     switch (it.kind) {
-    case K_LJ: k_lj<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
-    case K_LJ1G: k_lj1g<false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
+    case K_LJ: if (small) k_lj<false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); else k_lj<false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
+    case K_LJ1G: if (small) k_lj1g<false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); else k_lj1g<false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
     case K_RJL: {
-        k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
+        if (small) k_rjl_density_split<true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
+        else k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
         break;
     }
     case K_TB: {
@@ -622,8 +688,8 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
         c->launches += 1;
         break;
     }
-    case K_LJC: k_cos_direct<false, true, false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
-    case K_MORSEC: k_cos_direct<true, true, false, true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
+    case K_LJC: if (small) k_cos_direct<false, true, false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); else k_cos_direct<false, true, false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
+    case K_MORSEC: if (small) k_cos_direct<true, true, false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); else k_cos_direct<true, true, false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
     }
     k_sum_partials<<<1, 1024, 0, c->st>>>(nparts, c->part, scale, c->energy + k);
     c->launches += 2;
