@@ -472,6 +472,8 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         CK(cudaMemset(c->gmask, 0, sizeof(uint32_t) * S));
         const char* tm = std::getenv("PFMDS_TIMERS");
         c->timers_on = tm && tm[0] == '1';
+        const char* gr = std::getenv("PFMDS_GRAPHS");
+        c->use_graphs = gr ? gr[0] == '1' : n_atoms < 200000;
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     });
 }
@@ -551,7 +553,46 @@ int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) {
         if (n < 0 || first < 0) fail(PFMDS_ERR_INVALID, "error: bad step range");
         CK(cudaSetDevice(c->dev));
         finalize(c);
-        for (int s = first; s < first + n; ++s) do_step(c, s, kind, dt, s == first);
+        for (int s = first; s < first + n; ++s) {
+            // Steady-state steps (no list rebuild, no momentum removal, not the first of the call) of small systems are
+            // replayed from a CUDA graph captured from this very code path: same kernels, same order, fewer launch gaps.
+            bool rebuild = false;
+            for (auto& it : c->inter)
+                for (int j = 0; j < it.nl_n; ++j) rebuild |= (s % it.nl[j].period == 0) || !it.nl[j].built;
+            const bool graphable = c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && !rebuild &&
+                                   (s % c->zero_momentum_period != 0);
+            if (!graphable) { do_step(c, s, kind, dt, s == first); continue; }
+            pfmds_ctx::StepGraph* g = nullptr;
+            for (auto& e : c->graphs)
+                if (e.kind == kind && e.dt == dt && e.pos == (const void*)c->pos && e.pending == c->nhc_pending && e.ke_valid == c->nhc_ke_valid) g = &e;
+            if (!g) {
+                pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, nullptr, 0};
+                const bool p0 = c->nhc_pending, k0 = c->nhc_ke_valid;
+                const long long l0 = c->launches;
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+                try { do_step(c, s, kind, dt, false); } catch (...) { cudaStreamEndCapture(c->st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+                CK(cudaStreamEndCapture(c->st, &graph));
+                CK(cudaGraphInstantiate(&e.exec, graph, 0));
+                CK(cudaGraphDestroy(graph));
+                e.launches = c->launches - l0;
+                c->launches = l0;
+                // capturing ran the host-side bookkeeping of one step: the flags now describe the state AFTER a step; a step
+                // is only graphable again from the same entry state, which holds in steady state (checked by the key)
+                (void)p0; (void)k0;
+                if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+                c->graphs.push_back(e);
+                g = &c->graphs.back();
+                CK(cudaGraphLaunch(g->exec, c->st));
+                c->launches += g->launches;
+                continue;
+            }
+            CK(cudaGraphLaunch(g->exec, c->st));
+            c->launches += g->launches;
+            // host-side bookkeeping of do_step for this integrator
+            if (kind == PFMDS_NVT && c->nhc_fusable) { c->nhc_pending = true; c->nhc_ke_valid = true; }
+            else { c->nhc_pending = false; c->nhc_ke_valid = false; }
+        }
         CK(cudaGetLastError());
     });
 }
@@ -1024,6 +1065,7 @@ int pfmds_destroy(pfmds_ctx* c) {
         cudaFree(it.aux); cudaFree(it.aux2); cudaFree(it.fpart); cudaFree(it.gnorm); cudaFree(it.tvec);
     }
     for (auto& t : c->nhc) cudaFree(t.state);
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,
                     c->cid, c->posf, c->scan_tmp, c->part, c->red, c->energy, c->err};
     for (void* p : ptrs) cudaFree(p);

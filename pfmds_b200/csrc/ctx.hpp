@@ -79,6 +79,10 @@ struct pfmds_ctx {
     Slab* slab = nullptr;
     int* newslot = nullptr;  // old slot -> new slot of the last cell re-sort
     std::vector<long long> group_count;  // slab mode: global size of every group
+    // CUDA graphs of the steady-state step (small systems are launch-latency bound), keyed by what is baked in
+    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid; cudaGraphExec_t exec; long long launches; };
+    std::vector<StepGraph> graphs;
+    bool use_graphs = false;
     bool finalized = false;
     // fused NVT path (integrate.cu): usable when the thermostat groups are pairwise disjoint
     bool nhc_fusable = false;
