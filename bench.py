@@ -147,6 +147,54 @@ def run_reference(args):
     return 0
 
 
+def run_ensemble(args, rank, world, local, dist, K, W):
+    """BASELINE.json configs[4]: 64 independent graphene-on-Cu runs (run_md_simulation_mpi list mode), sharded over the
+    ranks by the reference's rule mod(i-1,n)==rank-1 and executed concurrently on each GPU, one context (CUDA stream)
+    per run, driven from one host thread through the asynchronous pfmds_advance."""
+    import torch
+    from pfmds_b200 import inputs
+    from pfmds_b200.engine import configure
+    from pfmds_b200.ensemble import shard
+    runs = shard(64, world, rank)
+    ctxs = []
+    for i in runs:
+        case = inputs.graphene_on_cu(seed=i)
+        ctxs.append(configure(case, device=local))
+    n_atoms = len(case["mass"])
+    chunk = 10
+    for e in ctxs:
+        e.advance("nvt", 1.0, 0, W)
+    for e in ctxs:
+        e.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = sum(e.launch_count() for e in ctxs)
+    with ClockSampler(local) as cs:
+        for e in ctxs:
+            e.timer_start()
+        for s in range(W, W + K, chunk):
+            for e in ctxs:
+                e.advance("nvt", 1.0, s, min(chunk, W + K - s))
+        ms = max(e.timer_stop() for e in ctxs)
+        torch.cuda.synchronize()
+    launches = sum(e.launch_count() for e in ctxs) - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        line = {"metric": "atom-steps/s", "value": 64 * n_atoms * K / (ms * 1e-3), "unit": "atom-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "ensemble of 64 graphene-on-Cu(111) runs (tb + ljc + rjl, NVT 300 K, 11028 atoms each), %d per GPU on separate streams" % len(runs),
+                           "runs_per_gpu": len(runs), "l2": "each replica is L2 resident; replicas differ (seeds 1..64)"},
+                "clocks": cs.summary(), "e2e": None, "gpu_launches": launches, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +226,8 @@ def main():
     build()
 
     K, W = args.steps, max(3, args.warmup)
+    if args.workload == "ensemble_graphene":
+        return run_ensemble(args, rank, world, local, dist, K, W)
     slab = world > 1 and args.decomp == "slab" and args.workload == "cu_fcc"
     if slab:
         from pfmds_b200.slab import broadcast_unique_id, configure_slab

@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         _run([NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB] + objs + ["-ldl"])
     host_deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))]
     if force or _newer(EXE, host_deps + [LIB]):
-        _run([CXX, "-O2", "-std=c++17", "-o", EXE, os.path.join(HOST, "run_md_simulation.cpp"), "-L" + CSRC, "-lpfmds_b200",
+        _run([CXX, "-O2", "-std=c++17", "-o", EXE, os.path.join(HOST, "run_md_simulation.cpp"), "-pthread", "-L" + CSRC, "-lpfmds_b200",
               "-Wl,-rpath,$ORIGIN/../csrc"])
     return LIB
 

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "md_driver.hpp"
 
@@ -17,6 +19,7 @@ namespace pfmds_host {
 
 struct CliOptions {
     int out_period = 1, threads = 1, node_id = 0, nodes = 0;  // node_id 1-based; nodes==0: plain runner
+    int streams = 1;  // ensemble mode: runs of this rank executed concurrently (one host thread + one context/stream each)
     std::string settings_filename = "md_run_settings.txt", settings_files_list, all_out_file = "all_out.txt", output_prefix, input_path, out_path;
 };
 
@@ -42,6 +45,7 @@ int run_cli(int argc, char** argv, int default_threads, Factory make_engine) {
         else if (a == "-mpi") mpi = true;
         else if (a == "-node") { o.node_id = (int)to_int(next()); mpi = true; }
         else if (a == "-nodes") { o.nodes = (int)to_int(next()); mpi = true; }
+        else if (a == "-streams") o.streams = (int)to_int(next());
         // unknown flags are silently ignored, like the reference's select case
     }
     if (mpi) {
@@ -100,17 +104,38 @@ int run_cli(int argc, char** argv, int default_threads, Factory make_engine) {
                 ListReader lst(o.input_path + o.settings_files_list);
                 int set_num = (int)to_int(lst.record(1)[0]);
                 if (o.nodes <= set_num) {
+                    // this rank's entries; with -streams k > 1 they run k at a time, each on its own host thread with its own
+                    // engine (context + stream), and their outputs are appended in list order afterwards
+                    struct Job { int i; std::string settings, prefix; char* obuf = nullptr; size_t olen = 0; char* abuf = nullptr; size_t alen = 0; std::string err; };
+                    std::vector<Job> jobs;
                     for (int i = 1; i <= set_num; ++i) {
                         auto t = lst.record(2);
-                        if ((i - 1) % o.nodes == o.node_id - 1) {
-                            std::fprintf(out, "%s\n", line.c_str());
-                            std::fprintf(out, "RUNNING ON NODE %s OUT OF%s NODES\n", I(o.node_id, 6).c_str(), I(o.nodes, 6).c_str());
-                            std::string str = o.out_path + o.output_prefix + node + t[1];
-                            std::fprintf(out, "%s\t%s\t%s\n", I(i, 6).c_str(), t[0].c_str(), str.c_str());
+                        if ((i - 1) % o.nodes == o.node_id - 1) { Job j; j.i = i; j.settings = t[0]; j.prefix = o.out_path + o.output_prefix + node + t[1]; jobs.push_back(j); }
+                    }
+                    auto run_job = [&](Job& j) {
+                        std::FILE* jo = open_memstream(&j.obuf, &j.olen);
+                        std::FILE* ja = open_memstream(&j.abuf, &j.alen);
+                        std::fprintf(jo, "%s\n", line.c_str());
+                        std::fprintf(jo, "RUNNING ON NODE %s OUT OF%s NODES\n", I(o.node_id, 6).c_str(), I(o.nodes, 6).c_str());
+                        std::fprintf(jo, "%s\t%s\t%s\n", I(j.i, 6).c_str(), j.settings.c_str(), j.prefix.c_str());
+                        try {
                             auto eng = make_engine(o.threads);
-                            md(eng, out, all_out, o.input_path, t[0], str, o.out_period, o.threads, rand_seed);
-                            std::fprintf(all_out, "\n");
-                            std::fprintf(out, "%s\n", line.c_str());
+                            md(eng, jo, ja, o.input_path, j.settings, j.prefix, o.out_period, o.threads, rand_seed);
+                        } catch (const std::exception& e) { j.err = e.what(); }
+                        std::fprintf(ja, "\n");
+                        std::fprintf(jo, "%s\n", line.c_str());
+                        std::fclose(jo); std::fclose(ja);
+                    };
+                    const size_t k = (size_t)(o.streams < 1 ? 1 : o.streams);
+                    for (size_t b = 0; b < jobs.size(); b += k) {
+                        std::vector<std::thread> th;
+                        for (size_t q = b; q < jobs.size() && q < b + k; ++q) th.emplace_back(run_job, std::ref(jobs[q]));
+                        for (auto& t : th) t.join();
+                        for (size_t q = b; q < jobs.size() && q < b + k; ++q) {
+                            std::fwrite(jobs[q].obuf, 1, jobs[q].olen, out);
+                            std::fwrite(jobs[q].abuf, 1, jobs[q].alen, all_out);
+                            std::free(jobs[q].obuf); std::free(jobs[q].abuf);
+                            if (!jobs[q].err.empty()) { std::fclose(all_out); std::fclose(out); throw std::runtime_error(jobs[q].err); }
                         }
                     }
                 } else {
