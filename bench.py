@@ -101,6 +101,15 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r1_traffic.json, same workload); None when no capture exists for it."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
 def cpu_baseline_sample(steps, threads=None):
     """The CPU oracle (oracle/, the reference's algorithm restated in C++/OpenMP; kind "port") timed on the
     host cores on a bounded sample of the same workload: Cu fcc 20^3 cells = 32 000 atoms (the reference's
@@ -346,7 +355,7 @@ def main():
             "peak_source": "pfmds_measure_peaks: DFMA micro-benchmark run live in this bench (MEASURED_PEAKS.json carries no FP64 figure)",
             "avg_launch_ms": avg_ms, "launches": cnt, "share_of_step": tot_ms / ms_prof, "flop_per_pair": FLOPS_PER_PAIR.get(name, 0), "pairs_per_launch": pairs,
             "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src, "copy_gbs_live": copy_gbs},
-            "traffic": None,
+            "traffic": _ncu_traffic(name),
         }
     cpu = None
     if not args.no_cpu_baseline and world == 1:
