@@ -59,6 +59,7 @@ void check_device_error(pfmds_ctx* c) {
     CK(cudaMemcpyAsync(h, c->err, sizeof h, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (h[0] == 0) return;
+    if (h[0] == 31) fail(PFMDS_ERR_CUDA, "slab decomposition: a neighbour rank did not signal within 10 s (peer-memory halo)");
     if (h[0] == 30) fail(PFMDS_ERR_UNSUPPORTED, "slab decomposition: an atom moved farther than one slab between two list rebuilds");
     if (h[0] == E_OUT_OF_CELL) fail(PFMDS_ERR_OUT_OF_CELL, " " + std::to_string(h[1] + 1) + "  particle out of cell");
     if (h[0] == E_TOO_MANY) fail(PFMDS_ERR_TOO_MANY_NEIGHBOURS, "error: too many neighbours (atom " + std::to_string(h[1] + 1) + ", " + std::to_string(h[2]) + " found)");
@@ -314,6 +315,7 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call) {
         if (step % c->zero_momentum_period == 0) integ_zero_momentum(c);
         forces_zero(c);
         for (size_t k = 0; k < c->inter.size(); ++k) forces_interaction(c, (int)k);
+        if (c->slab) slab_step_done(c);
     }
     if (step != 0) {
         PhaseTimer t(c, 0);

@@ -133,6 +133,8 @@ void slab_destroy(pfmds_ctx* c);
 void slab_redistribute(pfmds_ctx* c);
 void slab_after_reorder(pfmds_ctx* c);
 void slab_exchange(pfmds_ctx* c, int field);
+void slab_step_done(pfmds_ctx* c);
+bool slab_uses_p2p(pfmds_ctx* c);
 void slab_allreduce_sum(pfmds_ctx* c, double* d, int n);
 void slab_allreduce_max(pfmds_ctx* c, double* d, int n);
 void slab_allreduce_max_int(pfmds_ctx* c, int* d, int n);

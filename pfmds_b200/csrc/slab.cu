@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -63,6 +64,16 @@ struct Slab {
     double *sbuf[2]{nullptr, nullptr}, *rbuf[2]{nullptr, nullptr};
     int *cat = nullptr, *scan[3]{nullptr, nullptr, nullptr}, *flag = nullptr, *cnt_d = nullptr, *scan_tmp = nullptr;
     double* red_tmp = nullptr;
+    // direct peer-memory halo (NVLink stores into the neighbours' ghost slots, device-side flags instead of NCCL)
+    bool p2p = false;
+    int* flags = nullptr;                       // mine, written by the neighbours: [0,1] pos ready from left/right, [2,3] 1/Eb ready, [4,5] step done
+    double4* pos_buf[2]{nullptr, nullptr};      // my two position buffers (they swap at every cell re-sort)
+    double4* peer_pos[2][2]{{nullptr, nullptr}, {nullptr, nullptr}};  // [direction][parity] the neighbours' position buffers, IPC-mapped
+    int* peer_flags[2]{nullptr, nullptr};
+    int peer_parity[2]{0, 0};
+    int* pslot[2]{nullptr, nullptr};            // ghost slot, in neighbour d, of my k-th border atom for that neighbour
+    int seq_pos = 0, seq_w = 0, seq_done = 0;
+    std::vector<void*> ipc_opened;
 };
 
 #define GHOST_BIT 0x80000000u
@@ -207,6 +218,113 @@ __global__ void k_sl_unpack_halo(int n, const int* __restrict__ slot, const doub
     else p[3] = buf[k];
 }
 
+// ---- direct peer-memory halo ---------------------------------------------------------------------------
+// One kernel stores the border atoms' x,y,z (or 1/Eb) straight into the ghost slots of both neighbours through
+// their IPC-mapped position arrays: no pack buffer, no NCCL call, no unpack kernel on the other side.
+template <int FIELD>
+__global__ void k_sl_push(int nl, const int* __restrict__ idx_l, const int* __restrict__ ps_l, double4* peer_l, int nr, const int* __restrict__ idx_r,
+                          const int* __restrict__ ps_r, double4* peer_r, const double4* __restrict__ pos) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int* idx; const int* ps; double4* peer;
+    if (k < nl) { idx = idx_l; ps = ps_l; peer = peer_l; }
+    else if (k < nl + nr) { k -= nl; idx = idx_r; ps = ps_r; peer = peer_r; }
+    else return;
+    const double4 p = pos[idx[k]];
+    double* q = reinterpret_cast<double*>(&peer[ps[k]]);
+    if (FIELD == 0) { q[0] = p.x; q[1] = p.y; q[2] = p.z; }
+    else q[3] = p.w;
+}
+// publish `seq` in both neighbours' flag words (runs after the push kernel on the same stream: its stores are complete)
+__global__ void k_sl_signal(int* to_left, int* to_right, int seq) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(to_left) = seq;
+    *reinterpret_cast<volatile int*>(to_right) = seq;
+    __threadfence_system();
+}
+// wait until both neighbours have published at least `seq`; gives up after ~10 s and records an error instead of hanging
+__global__ void k_sl_wait(const int* from_left, const int* from_right, int seq, int* err) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*reinterpret_cast<const volatile int*>(from_left) < seq || *reinterpret_cast<const volatile int*>(from_right) < seq) {
+        __nanosleep(200);
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 10000000000ull) { raise_error(err, 31, seq, 0); break; }
+    }
+    __threadfence_system();
+}
+
+static bool slab_setup_p2p(pfmds_ctx* c, Slab* s) {
+    // exchange IPC handles of my two position buffers and my flag words with both neighbours
+    struct Pack { cudaIpcMemHandle_t pos0, pos1, fl; };
+    Pack mine{}, from[2]{};
+    bool ok = true;
+    CK(cudaMalloc(&s->flags, 8 * sizeof(int)));
+    CK(cudaMemset(s->flags, 0, 8 * sizeof(int)));
+    s->pos_buf[0] = c->pos; s->pos_buf[1] = c->pos2;
+    if (cudaIpcGetMemHandle(&mine.pos0, c->pos) != cudaSuccess || cudaIpcGetMemHandle(&mine.pos1, c->pos2) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.fl, s->flags) != cudaSuccess) { ok = false; cudaGetLastError(); }
+    char *d_mine = nullptr, *d_from = nullptr;
+    CK(cudaMalloc(&d_mine, sizeof(Pack)));
+    CK(cudaMalloc(&d_from, 2 * sizeof(Pack)));
+    CK(cudaMemcpy(d_mine, &mine, sizeof(Pack), cudaMemcpyHostToDevice));
+    NK(g_nccl.GroupStart());
+    NK(g_nccl.Send(d_mine, sizeof(Pack), ncclChar, s->left, s->comm, c->st));
+    NK(g_nccl.Send(d_mine, sizeof(Pack), ncclChar, s->right, s->comm, c->st));
+    NK(g_nccl.Recv(d_from + sizeof(Pack), sizeof(Pack), ncclChar, s->right, s->comm, c->st));
+    NK(g_nccl.Recv(d_from, sizeof(Pack), ncclChar, s->left, s->comm, c->st));
+    NK(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(from, d_from, 2 * sizeof(Pack), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    cudaFree(d_mine); cudaFree(d_from);
+    const int ndist = (s->left == s->right) ? 1 : 2;
+    for (int d = 0; d < ndist && ok; ++d) {
+        void *p0 = nullptr, *p1 = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&p0, from[d].pos0, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&p1, from[d].pos1, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pf, from[d].fl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+        s->ipc_opened.push_back(p0); s->ipc_opened.push_back(p1); s->ipc_opened.push_back(pf);
+        s->peer_pos[d][0] = (double4*)p0; s->peer_pos[d][1] = (double4*)p1; s->peer_flags[d] = (int*)pf;
+    }
+    if (ndist == 1) { s->peer_pos[1][0] = s->peer_pos[0][0]; s->peer_pos[1][1] = s->peer_pos[0][1]; s->peer_flags[1] = s->peer_flags[0]; }
+    // every rank must take the same path
+    int h = ok ? 1 : 0, *dflag = s->cnt_d + 12;
+    CK(cudaMemcpy(dflag, &h, sizeof(int), cudaMemcpyHostToDevice));
+    NK(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMin, s->comm, c->st));
+    CK(cudaMemcpyAsync(&h, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (int d = 0; d < 2; ++d) CK(cudaMalloc(&s->pslot[d], sizeof(int) * c->stride));
+    return h == 1;
+}
+
+// after the re-sort of a rebuild step: tell each neighbour where its border atoms now live here, and which of my
+// two position buffers is current
+static void slab_exchange_peer_slots(pfmds_ctx* c, Slab* s) {
+    int par = (c->pos == s->pos_buf[0]) ? 0 : 1;
+    CK(cudaMemcpyAsync(s->cnt_d + 13, &par, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    NK(g_nccl.GroupStart());
+    if (s->n_recv[0] > 0) NK(g_nccl.Send(s->ghost_slot[0], (size_t)s->n_recv[0], ncclInt, s->left, s->comm, c->st));
+    if (s->n_recv[1] > 0) NK(g_nccl.Send(s->ghost_slot[1], (size_t)s->n_recv[1], ncclInt, s->right, s->comm, c->st));
+    NK(g_nccl.Send(s->cnt_d + 13, 1, ncclInt, s->left, s->comm, c->st));
+    NK(g_nccl.Send(s->cnt_d + 13, 1, ncclInt, s->right, s->comm, c->st));
+    if (s->n_send[1] > 0) NK(g_nccl.Recv(s->pslot[1], (size_t)s->n_send[1], ncclInt, s->right, s->comm, c->st));
+    if (s->n_send[0] > 0) NK(g_nccl.Recv(s->pslot[0], (size_t)s->n_send[0], ncclInt, s->left, s->comm, c->st));
+    NK(g_nccl.Recv(s->cnt_d + 15, 1, ncclInt, s->right, s->comm, c->st));
+    NK(g_nccl.Recv(s->cnt_d + 14, 1, ncclInt, s->left, s->comm, c->st));
+    NK(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(s->peer_parity, s->cnt_d + 14, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+}
+
+// the neighbours may overwrite my ghost positions for the next step only after my force kernels of this step are done
+void slab_step_done(pfmds_ctx* c) {
+    Slab* s = c->slab;
+    if (!s->p2p) return;
+    s->seq_done += 1;
+    k_sl_signal<<<1, 1, 0, c->st>>>(s->peer_flags[0] + 5, s->peer_flags[1] + 4, s->seq_done);
+    c->launches += 1;
+}
+
 // ------------------------------------------------------------------------------------------------------
 int slab_unique_id(char* id128) {
     g_nccl.load();
@@ -241,6 +359,8 @@ void slab_init(pfmds_ctx* c, int rank, int nranks, const char* id128, long long 
     CK(cudaMalloc(&s->scan_tmp, sizeof(int) * (S / 2048 + 2)));
     CK(cudaMalloc(&s->red_tmp, sizeof(double) * 64));
     CK(cudaMalloc(&c->newslot, sizeof(int) * S));
+    const char* env = std::getenv("PFMDS_SLAB_P2P");
+    s->p2p = !(env && env[0] == '0') && slab_setup_p2p(c, s);
 }
 
 void slab_destroy(pfmds_ctx* c) {
@@ -249,11 +369,14 @@ void slab_destroy(pfmds_ctx* c) {
     for (int d = 0; d < 2; ++d) { cudaFree(s->send_idx[d]); cudaFree(s->ghost_slot[d]); cudaFree(s->sbuf[d]); cudaFree(s->rbuf[d]); }
     cudaFree(s->cat); cudaFree(s->flag); for (int k = 0; k < 3; ++k) cudaFree(s->scan[k]);
     cudaFree(s->cnt_d); cudaFree(s->scan_tmp); cudaFree(s->red_tmp); cudaFree(c->newslot);
+    for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(s->flags); cudaFree(s->pslot[0]); cudaFree(s->pslot[1]);
     if (s->comm) g_nccl.CommDestroy(s->comm);
     delete s;
     c->slab = nullptr;
 }
 
+bool slab_uses_p2p(pfmds_ctx* c) { return c->slab && c->slab->p2p; }
 int slab_rank(pfmds_ctx* c) { return c->slab->rank; }
 int slab_nranks(pfmds_ctx* c) { return c->slab->nranks; }
 int slab_n_local(pfmds_ctx* c) { return c->slab->n_local; }
@@ -358,6 +481,7 @@ void slab_after_reorder(pfmds_ctx* c) {
         if (s->n_recv[d] > 0) k_sl_remap<<<(s->n_recv[d] + T - 1) / T, T, 0, c->st>>>(s->n_recv[d], s->ghost_slot[d], c->newslot);
     }
     c->launches += 4;
+    if (s->p2p) slab_exchange_peer_slots(c, s);
 }
 
 // field 0: ghost positions, field 1: ghost pos.w (1/Eb)
@@ -365,6 +489,27 @@ void slab_exchange(pfmds_ctx* c, int field) {
     Slab* s = c->slab;
     const int T = 256;
     KTimer kt(c, KS_OTHER);
+    if (s->p2p) {
+        const int nl = s->n_send[0], nr = s->n_send[1], n = nl + nr;
+        double4 *pl = s->peer_pos[0][s->peer_parity[0]], *pr = s->peer_pos[1][s->peer_parity[1]];
+        if (field == 0) {
+            // my neighbours' force kernels of the previous step must be done with the old ghost positions
+            k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 4, s->flags + 5, s->seq_done, c->err);
+            if (n > 0) k_sl_push<0><<<(n + T - 1) / T, T, 0, c->st>>>(nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
+            s->seq_pos += 1;
+            k_sl_signal<<<1, 1, 0, c->st>>>(s->peer_flags[0] + 1, s->peer_flags[1] + 0, s->seq_pos);   // I am my left neighbour's right neighbour
+            k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 0, s->flags + 1, s->seq_pos, c->err);
+            c->launches += 4;
+        } else {
+            if (n > 0) k_sl_push<1><<<(n + T - 1) / T, T, 0, c->st>>>(nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
+            s->seq_w += 1;
+            k_sl_signal<<<1, 1, 0, c->st>>>(s->peer_flags[0] + 3, s->peer_flags[1] + 2, s->seq_w);
+            k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 2, s->flags + 3, s->seq_w, c->err);
+            c->launches += 3;
+        }
+        CK(cudaGetLastError());
+        return;
+    }
     for (int d = 0; d < 2; ++d) {
         if (s->n_send[d] == 0) continue;
         if (field == 0) k_sl_pack_halo<0><<<(s->n_send[d] + T - 1) / T, T, 0, c->st>>>(s->n_send[d], s->send_idx[d], c->pos, s->sbuf[d]);
