@@ -365,7 +365,7 @@ def main():
     line = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "atoms_per_gpu": n_atoms, "parallelism": ("x-slab decomposition over %d GPUs, NCCL halo exchange" % world if slab else "ensemble x%d (independent replicas, reference MPI mode)" % world) if world > 1 else "single GPU",
+        "config": {"workload": desc, "atoms_per_gpu": n_atoms, "parallelism": ("x-slab decomposition over %d GPUs, halo by direct NVLink stores into the neighbours' ghost slots (IPC peer memory), NCCL for migration and all-reduce" % world if slab else "ensemble x%d (independent replicas, reference MPI mode)" % world) if world > 1 else "single GPU",
                    "l2": "working set (lists %.0f MB + state) exceeds the 126 MB L2" % (pairs * 4 / 1e6), "ns_per_day": K / (ms_max * 1e-3) * dt * 86400e-6},
         "clocks": cs.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},

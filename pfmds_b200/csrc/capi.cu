@@ -59,7 +59,7 @@ void check_device_error(pfmds_ctx* c) {
     CK(cudaMemcpyAsync(h, c->err, sizeof h, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (h[0] == 0) return;
-    if (h[0] == 31) fail(PFMDS_ERR_CUDA, "slab decomposition: a neighbour rank did not signal within 10 s (peer-memory halo)");
+    if (h[0] == 31) fail(PFMDS_ERR_CUDA, "slab decomposition: a neighbour rank did not signal within 3 s (peer-memory halo)");
     if (h[0] == 30) fail(PFMDS_ERR_UNSUPPORTED, "slab decomposition: an atom moved farther than one slab between two list rebuilds");
     if (h[0] == E_OUT_OF_CELL) fail(PFMDS_ERR_OUT_OF_CELL, " " + std::to_string(h[1] + 1) + "  particle out of cell");
     if (h[0] == E_TOO_MANY) fail(PFMDS_ERR_TOO_MANY_NEIGHBOURS, "error: too many neighbours (atom " + std::to_string(h[1] + 1) + ", " + std::to_string(h[2]) + " found)");
@@ -296,7 +296,10 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call) {
         if (c->invert_z) integ_invert_z(c);
         if (step != 0) {
             if (kind == PFMDS_NVT && c->nhc_fusable && c->nhc_ke_valid) {
-                integ_nvt_open_kick_drift(c, dt);  // consumes the pending closing scale of the previous step
+                bool rebuild = false;
+                for (auto& it : c->inter)
+                    for (int j = 0; j < it.nl_n; ++j) rebuild |= (step % it.nl[j].period == 0) || !it.nl[j].built;
+                integ_nvt_open_kick_drift(c, dt, rebuild);  // consumes the pending closing scale of the previous step
                 c->nhc_pending = false;
             } else {
                 integ_flush_pending(c);
@@ -563,7 +566,15 @@ int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) {
                 for (int j = 0; j < it.nl_n; ++j) rebuild |= (s % it.nl[j].period == 0) || !it.nl[j].built;
             const bool graphable = c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && !rebuild &&
                                    (s % c->zero_momentum_period != 0);
-            if (!graphable) { do_step(c, s, kind, dt, s == first); continue; }
+            if (!graphable) {
+                do_step(c, s, kind, dt, s == first);
+                if (c->slab && std::getenv("PFMDS_SLAB_DEBUG")) {
+                    std::fprintf(stderr, "[slab %d] step %d queued\n", slab_rank(c), s); std::fflush(stderr);
+                    cudaError_t e = cudaStreamSynchronize(c->st);
+                    std::fprintf(stderr, "[slab %d] step %d done (%s)\n", slab_rank(c), s, cudaGetErrorString(e)); std::fflush(stderr);
+                }
+                continue;
+            }
             pfmds_ctx::StepGraph* g = nullptr;
             for (auto& e : c->graphs)
                 if (e.kind == kind && e.dt == dt && e.pos == (const void*)c->pos && e.pending == c->nhc_pending && e.ke_valid == c->nhc_ke_valid) g = &e;

@@ -108,4 +108,50 @@ struct RJLp { double A0, xi, p, q, r0, R1, R2; };
 #define NHC_MAXF 4
 struct NhcPack { int n; uint32_t bit[NHC_MAXF]; double* state[NHC_MAXF]; int M[NHC_MAXF]; int L[NHC_MAXF]; double T[NHC_MAXF]; };
 
+// Slab decomposition, fused halo: what a compute kernel needs to store its border atoms' results straight into
+// the neighbours' ghost slots (IPC-mapped peer memory over NVLink), publish a sequence number when the whole grid
+// is done, and/or wait for the neighbours' sequence number before it starts.  All zeros = single-GPU behaviour.
+struct SlabDev {
+    int push;                      // store to the peers and signal
+    const int* rs_l; const int* rs_r;   // per slot: ghost slot of this atom in the left / right neighbour, -1 if it is not a border atom
+    double4* peer_l; double4* peer_r;   // the neighbours' current position arrays
+    int* sig_l; int* sig_r; int sig_seq; unsigned int* counter;
+    const int* wait_a; const int* wait_b; int wait_seq;   // 0: nothing to wait for
+    int* err;
+};
+__device__ __forceinline__ void slab_wait(const SlabDev& S) {
+    if (S.wait_seq > 0) {
+        if (threadIdx.x == 0) {
+            unsigned long long t0, t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (*reinterpret_cast<const volatile int*>(S.wait_a) < S.wait_seq || *reinterpret_cast<const volatile int*>(S.wait_b) < S.wait_seq) {
+                if (*reinterpret_cast<volatile int*>(S.err) != 0) break;  // the run is already failing: do not wait once per block
+                __nanosleep(100);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > 3000000000ull) { raise_error(S.err, 31, S.wait_seq, 1); break; }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+}
+// last block of the grid publishes the sequence number; only the threads that stored to a peer pay the system-scope
+// fence (a few per cent of them), the block barrier and the device-scope counter order the rest
+__device__ __forceinline__ void slab_signal(const SlabDev& S, bool pushed) {
+    if (S.push) {
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int t = atomicAdd(S.counter, 1u);
+            if (t == gridDim.x * gridDim.y - 1) {
+                *S.counter = 0;
+                __threadfence_system();
+                *reinterpret_cast<volatile int*>(S.sig_l) = S.sig_seq;
+                *reinterpret_cast<volatile int*>(S.sig_r) = S.sig_seq;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
 struct ListView { const int* nlist; const int* nnum; size_t stride; };

@@ -135,6 +135,10 @@ void slab_after_reorder(pfmds_ctx* c);
 void slab_exchange(pfmds_ctx* c, int field);
 void slab_step_done(pfmds_ctx* c);
 bool slab_uses_p2p(pfmds_ctx* c);
+bool slab_fused(pfmds_ctx* c);
+// stage 0: kick+drift pushes positions; 1: rjl density waits for positions, pushes 1/Eb; 2: rjl force waits for 1/Eb
+SlabDev slab_dev(pfmds_ctx* c, int stage);
+bool slab_pos_pushed_by_kick(pfmds_ctx* c, bool rebuild_step);
 void slab_allreduce_sum(pfmds_ctx* c, double* d, int n);
 void slab_allreduce_max(pfmds_ctx* c, double* d, int n);
 void slab_allreduce_max_int(pfmds_ctx* c, int* d, int n);
@@ -158,7 +162,7 @@ void integ_kick_drift(pfmds_ctx* c, double dt);
 void integ_kick(pfmds_ctx* c, double dt);
 void integ_quench(pfmds_ctx* c);
 void integ_zero_momentum(pfmds_ctx* c);
-void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt);
+void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step);
 void integ_nvt_kick_close(pfmds_ctx* c, double dt);
 void integ_flush_pending(pfmds_ctx* c);
 // out[0]=KE(group) ; group sums for diagnostics: out[0..2]=sum F, [3..5]=sum m x, [6..8]=sum m v, [9]=sum m, [10]=max v^2

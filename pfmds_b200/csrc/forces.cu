@@ -204,10 +204,12 @@ __device__ __forceinline__ void rjl_density_pair(const double4& pi, const double
     }
 }
 template <bool E>
-__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part) {
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part, SlabDev S) {
     const double* tab = nullptr;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
+    bool pushed = false;
+    slab_wait(S);  // slab mode: the neighbours' positions of this step have landed in my ghost slots
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
         // The .w of every record is being written by this kernel (1/Eb of its owner) while x,y,z are
@@ -232,9 +234,16 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* po
         if (p < n) rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, tab, sq, sp);
         double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
         reinterpret_cast<double*>(&pos[i])[3] = ie;
+        if (S.push) {  // the same 1/Eb goes straight into the ghost copies of this atom on the neighbour GPUs (NVLink stores)
+            int a = S.rs_l[i], b = S.rs_r[i];
+            if (a >= 0) reinterpret_cast<double*>(&S.peer_l[a])[3] = ie;
+            if (b >= 0) reinterpret_cast<double*>(&S.peer_r[b])[3] = ie;
+            pushed = (a >= 0) || (b >= 0);
+        }
         if (E) e = C.A0 * sp - C.xi * (sq * ie);
     }
     if (E) store_partial(e, part);
+    slab_signal(S, pushed);
 }
 
 // small systems: SPLIT lanes per atom, plain loop (latency is hidden by the extra warps)
@@ -280,9 +289,10 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
     }
 }
 __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
-                                                            WrapC W) {
+                                                            WrapC W, SlabDev S) {
     const double* tab = nullptr;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    slab_wait(S);  // slab mode: the neighbours' 1/Eb have landed in my ghost slots
     if (i >= N) return;
     int n = lv.nnum[i];
     if (n == 0) return;
@@ -618,16 +628,17 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
     {
         const RjlC C = rjl_consts(it.rjl);
         const WrapC W = wrap_consts(c->box);
+        const bool fused = c->slab && !small && slab_fused(c);  // density stores 1/Eb into the neighbours' ghosts itself
         {
             KTimer kt(c, KS_RJL_DENSITY);
             if (small) k_rjl_density_split<false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr);
-            else k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr);
+            else k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr, fused ? slab_dev(c, 1) : SlabDev{});
         }
-        if (c->slab) slab_exchange(c, 1);  // ghost 1/Eb from their owners
+        if (c->slab && !fused) slab_exchange(c, 1);  // ghost 1/Eb from their owners
         {
             KTimer kt(c, KS_RJL_FORCE);
             if (small) k_rjl_force_split<SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W);
-            else k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W);
+            else k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W, fused ? slab_dev(c, 2) : SlabDev{});
         }
     }
         c->launches += 2;
@@ -677,7 +688,7 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     case K_LJ1G: if (small) k_lj1g<false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); else k_lj1g<false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
     case K_RJL: {
         if (small) k_rjl_density_split<true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
-        else k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
+        else k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part, SlabDev{});
         break;
     }
     case K_TB: {

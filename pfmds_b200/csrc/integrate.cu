@@ -313,37 +313,45 @@ __global__ void k_nhc_open(NhcPack P, double ts2, double ts3, double ts4) {
 }
 __global__ void __launch_bounds__(IT) k_kick_drift_nvt(int N, double4* __restrict__ pos, double4* __restrict__ vel, const double4* __restrict__ frc,
                                                        const uint32_t* __restrict__ gmask, const int* __restrict__ orig, uint32_t bxyz, uint32_t bz,
-                                                       double ts1, double ts2, BoxD box, NhcPack P, int* err) {
+                                                       double ts1, double ts2, BoxD box, NhcPack P, int* err, SlabDev S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    uint32_t g = gmask[i];
-    if (g & PFMDS_GHOST) return;
+    bool pushed = false;
+    slab_wait(S);  // slab mode: the neighbours' force kernels are done with the ghost positions this kernel is about to overwrite
+    uint32_t g = i < N ? gmask[i] : PFMDS_GHOST;
     bool mx = g & bxyz, mz = g & bz;
     double sc = 1.0;
     bool th = false;
     for (int k = 0; k < P.n; ++k)
         if (g & P.bit[k]) { sc = P.state[k][3 * P.M[k] + 2]; th = true; }
-    if (!mx && !mz && !th) return;
-    double4 v = vel[i];
-    v.x *= sc; v.y *= sc; v.z *= sc;
-    if (mx || mz) {
-        double4 p = pos[i], f = frc[i];
-        if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
-        if (mx) {
-            v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
-            v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
-            v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+    if (!(g & PFMDS_GHOST) && (mx || mz || th)) {  // one exit point: slab_signal() below holds a block barrier
+        double4 v = vel[i];
+        v.x *= sc; v.y *= sc; v.z *= sc;
+        if (mx || mz) {
+            double4 p = pos[i], f = frc[i];
+            if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
+            if (mx) {
+                v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
+                v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
+                v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+            }
+            if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+            if (mx) {
+                p.x = p.x + v.x * ts1; if (p.x > box.L[0]) p.x = p.x - box.L[0]; else if (p.x < 0.) p.x = p.x + box.L[0];
+                p.y = p.y + v.y * ts1; if (p.y > box.L[1]) p.y = p.y - box.L[1]; else if (p.y < 0.) p.y = p.y + box.L[1];
+                p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2];
+            }
+            if (mz) { p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2]; }
+            pos[i] = p;
+            if (S.push) {  // the new position goes straight into the ghost copies of this atom on the neighbour GPUs
+                int a = S.rs_l[i], b = S.rs_r[i];
+                if (a >= 0) { double* q = reinterpret_cast<double*>(&S.peer_l[a]); q[0] = p.x; q[1] = p.y; q[2] = p.z; }
+                if (b >= 0) { double* q = reinterpret_cast<double*>(&S.peer_r[b]); q[0] = p.x; q[1] = p.y; q[2] = p.z; }
+                pushed = (a >= 0) || (b >= 0);
+            }
         }
-        if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
-        if (mx) {
-            p.x = p.x + v.x * ts1; if (p.x > box.L[0]) p.x = p.x - box.L[0]; else if (p.x < 0.) p.x = p.x + box.L[0];
-            p.y = p.y + v.y * ts1; if (p.y > box.L[1]) p.y = p.y - box.L[1]; else if (p.y < 0.) p.y = p.y + box.L[1];
-            p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2];
-        }
-        if (mz) { p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2]; }
-        pos[i] = p;
+        vel[i] = v;
     }
-    vel[i] = v;
+    slab_signal(S, pushed);
 }
 __global__ void k_reset_pending(NhcPack P) {
     int k = threadIdx.x;
@@ -402,12 +410,14 @@ static NhcPack pack_of(pfmds_ctx* c) {
     }
     return P;
 }
-void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt) {
+void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step) {
     NhcPack P = pack_of(c);
     KTimer kt(c, KS_KICK_DRIFT);
     k_nhc_open<<<1, 32, 0, c->st>>>(P, dt / 2, dt / 4, dt / 8);
+    SlabDev S{};
+    if (c->slab && slab_pos_pushed_by_kick(c, rebuild_step)) S = slab_dev(c, 0);
     k_kick_drift_nvt<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
-                                                             1u << (c->z_moving - 1), dt, dt / 2, c->box, P, c->err);
+                                                             1u << (c->z_moving - 1), dt, dt / 2, c->box, P, c->err, S);
     k_reset_pending<<<1, 32, 0, c->st>>>(P);
     c->launches += 3;
 }

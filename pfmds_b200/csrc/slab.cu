@@ -73,12 +73,19 @@ struct Slab {
     int peer_parity[2]{0, 0};
     int* pslot[2]{nullptr, nullptr};            // ghost slot, in neighbour d, of my k-th border atom for that neighbour
     int seq_pos = 0, seq_w = 0, seq_done = 0;
+    // fused halo: the compute kernels store into the neighbours' ghost slots themselves
+    bool fused = false, pos_pushed = false;
+    int wait_pos_seq = 0;
+    int* rs[2]{nullptr, nullptr};   // per slot: ghost slot in the left / right neighbour, -1 otherwise
+    unsigned int* counter = nullptr;
     std::vector<void*> ipc_opened;
 };
 
 #define GHOST_BIT 0x80000000u
 #define MIG_W 9   // doubles per migrating atom: pos4, vel4, (mask, orig)
 #define GH_W 5    // doubles per new ghost: pos4, (mask, orig)
+
+__global__ void k_sl_scatter_rs(int n, const int* __restrict__ idx, const int* __restrict__ ps, int* __restrict__ rs);
 
 // ---- small generic pieces ---------------------------------------------------------------------------
 __global__ void k_sl_scan_block(int n, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ sums) {
@@ -246,10 +253,11 @@ __global__ void k_sl_wait(const int* from_left, const int* from_right, int seq, 
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*reinterpret_cast<const volatile int*>(from_left) < seq || *reinterpret_cast<const volatile int*>(from_right) < seq) {
+        if (*reinterpret_cast<volatile int*>(err) != 0) break;
         __nanosleep(200);
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > 10000000000ull) { raise_error(err, 31, seq, 0); break; }
+        if (t - t0 > 3000000000ull) { raise_error(err, 31, seq, 0); break; }
     }
     __threadfence_system();
 }
@@ -293,7 +301,14 @@ static bool slab_setup_p2p(pfmds_ctx* c, Slab* s) {
     NK(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMin, s->comm, c->st));
     CK(cudaMemcpyAsync(&h, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    for (int d = 0; d < 2; ++d) CK(cudaMalloc(&s->pslot[d], sizeof(int) * c->stride));
+    for (int d = 0; d < 2; ++d) { CK(cudaMalloc(&s->pslot[d], sizeof(int) * c->stride)); CK(cudaMalloc(&s->rs[d], sizeof(int) * c->stride)); }
+    CK(cudaMalloc(&s->counter, sizeof(unsigned int)));
+    CK(cudaMemset(s->counter, 0, sizeof(unsigned int)));
+    // Fusing the stores and flags into the compute kernels is implemented (SlabDev, common.cuh) but measured slower than
+    // the separate push kernel on 2 x B200 (1.31 vs 1.18 ms/step: system-scope fences and NVLink store latency land on
+    // the FP64-bound warps), so it is opt-in.
+    const char* fz = std::getenv("PFMDS_SLAB_FUSED");
+    s->fused = fz && fz[0] == '1';
     return h == 1;
 }
 
@@ -314,6 +329,12 @@ static void slab_exchange_peer_slots(pfmds_ctx* c, Slab* s) {
     NK(g_nccl.GroupEnd());
     CK(cudaMemcpyAsync(s->peer_parity, s->cnt_d + 14, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    // per-slot view of the same lists, for the kernels that push while they compute
+    for (int d = 0; d < 2; ++d) {
+        CK(cudaMemsetAsync(s->rs[d], 0xff, sizeof(int) * c->stride, c->st));
+        if (s->n_send[d] > 0) k_sl_scatter_rs<<<(s->n_send[d] + 255) / 256, 256, 0, c->st>>>(s->n_send[d], s->send_idx[d], s->pslot[d], s->rs[d]);
+    }
+    s->pos_pushed = false; s->wait_pos_seq = 0;
 }
 
 // the neighbours may overwrite my ghost positions for the next step only after my force kernels of this step are done
@@ -370,13 +391,47 @@ void slab_destroy(pfmds_ctx* c) {
     cudaFree(s->cat); cudaFree(s->flag); for (int k = 0; k < 3; ++k) cudaFree(s->scan[k]);
     cudaFree(s->cnt_d); cudaFree(s->scan_tmp); cudaFree(s->red_tmp); cudaFree(c->newslot);
     for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
-    cudaFree(s->flags); cudaFree(s->pslot[0]); cudaFree(s->pslot[1]);
+    cudaFree(s->flags); cudaFree(s->pslot[0]); cudaFree(s->pslot[1]); cudaFree(s->rs[0]); cudaFree(s->rs[1]); cudaFree(s->counter);
     if (s->comm) g_nccl.CommDestroy(s->comm);
     delete s;
     c->slab = nullptr;
 }
 
 bool slab_uses_p2p(pfmds_ctx* c) { return c->slab && c->slab->p2p; }
+bool slab_fused(pfmds_ctx* c) {
+    Slab* s = c->slab;
+    if (!s || !s->p2p || !s->fused) return false;
+    if (s->n_global / s->nranks < 400000) return false;  // small slabs run the lanes-per-atom kernels, which use the unfused halo
+    for (auto& it : c->inter) if (it.kind != K_RJL) return false;
+    return true;
+}
+__global__ void k_sl_scatter_rs(int n, const int* __restrict__ idx, const int* __restrict__ ps, int* __restrict__ rs) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) rs[idx[k]] = ps[k];
+}
+SlabDev slab_dev(pfmds_ctx* c, int stage) {
+    Slab* s = c->slab;
+    SlabDev S{};
+    S.err = c->err;
+    S.rs_l = s->rs[0]; S.rs_r = s->rs[1];
+    S.peer_l = s->peer_pos[0][s->peer_parity[0]]; S.peer_r = s->peer_pos[1][s->peer_parity[1]];
+    S.counter = s->counter;
+    if (stage == 0) {         // kick+drift: wait until the neighbours are done with the old ghost positions, push the new ones
+        S.push = 1; S.wait_a = s->flags + 4; S.wait_b = s->flags + 5; S.wait_seq = s->seq_done;
+        s->seq_pos += 1;
+        S.sig_l = s->peer_flags[0] + 1; S.sig_r = s->peer_flags[1] + 0; S.sig_seq = s->seq_pos;
+        s->pos_pushed = true;
+    } else if (stage == 1) {  // rjl density: wait for the ghost positions of this step, push 1/Eb
+        S.push = 1; S.wait_a = s->flags + 0; S.wait_b = s->flags + 1; S.wait_seq = s->wait_pos_seq;
+        s->wait_pos_seq = 0;
+        s->seq_w += 1;
+        S.sig_l = s->peer_flags[0] + 3; S.sig_r = s->peer_flags[1] + 2; S.sig_seq = s->seq_w;
+    } else {                  // rjl force: wait for the ghost 1/Eb
+        S.push = 0; S.wait_a = s->flags + 2; S.wait_b = s->flags + 3; S.wait_seq = s->seq_w;
+    }
+    return S;
+}
+bool slab_pos_pushed_by_kick(pfmds_ctx* c, bool rebuild_step) { return slab_fused(c) && !rebuild_step; }
 int slab_rank(pfmds_ctx* c) { return c->slab->rank; }
 int slab_nranks(pfmds_ctx* c) { return c->slab->nranks; }
 int slab_n_local(pfmds_ctx* c) { return c->slab->n_local; }
@@ -492,6 +547,21 @@ void slab_exchange(pfmds_ctx* c, int field) {
     if (s->p2p) {
         const int nl = s->n_send[0], nr = s->n_send[1], n = nl + nr;
         double4 *pl = s->peer_pos[0][s->peer_parity[0]], *pr = s->peer_pos[1][s->peer_parity[1]];
+        if (field == 0 && slab_fused(c)) {
+            // positions: pushed by the kick+drift kernel itself when it was the fused variant, else pushed here; either way
+            // the first density kernel waits for the neighbours' flag in its prologue
+            if (!s->pos_pushed) {
+                k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 4, s->flags + 5, s->seq_done, c->err);
+                if (n > 0) k_sl_push<0><<<(n + T - 1) / T, T, 0, c->st>>>(nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
+                s->seq_pos += 1;
+                k_sl_signal<<<1, 1, 0, c->st>>>(s->peer_flags[0] + 1, s->peer_flags[1] + 0, s->seq_pos);
+                c->launches += 3;
+            }
+            s->pos_pushed = false;
+            s->wait_pos_seq = s->seq_pos;
+            CK(cudaGetLastError());
+            return;
+        }
         if (field == 0) {
             // my neighbours' force kernels of the previous step must be done with the old ghost positions
             k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 4, s->flags + 5, s->seq_done, c->err);
