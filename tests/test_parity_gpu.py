@@ -224,3 +224,30 @@ def test_full_size_properties_cu_fcc():
     assert abs(c1 - c0) < 2e-3 * en0[1]
     fs, mc, mcv, vmax, load = e.diagnostics()
     assert np.abs(fs).max() < 1e-7 and np.linalg.norm(mcv) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["ab_gas", "cu_fcc"])
+def test_nve_energy_drift_over_10k_steps(name):
+    """north_star: NVE energy drift matches over 10^4 steps.  Trajectories of a chaotic system separate after ~10^3
+    steps, so positions are not compared; the conserved energy is: its excursion stays bounded and equal in size on
+    both sides, and the final total energies agree to the level set by that bounded fluctuation."""
+    case = CASES[name]
+    dt = case["integrators"][0][1] / 2
+    g, o = gpu(case), oracle(case)
+    tr = {}
+    for tag, e in (("gpu", g), ("cpu", o)):
+        e.advance("nve", dt, 0, 1)
+        en = e.energies()
+        e0, ke0 = en[0].sum() + en[1], en[1]
+        dev = []
+        for k in range(10):
+            e.advance("nve", dt, 1 + 1000 * k, 1000)
+            en = e.energies()
+            dev.append(en[0].sum() + en[1] - e0)
+        tr[tag] = (np.array(dev), ke0, e0)
+    dg, ke0, e0 = tr["gpu"]
+    dc = tr["cpu"][0]
+    assert abs(tr["gpu"][2] - tr["cpu"][2]) <= 1e-9 * abs(e0)                  # same starting energy
+    assert np.abs(dg).max() < 2e-3 * ke0 and np.abs(dc).max() < 2e-3 * ke0     # bounded: no drift on either side
+    assert abs(np.abs(dg).max() - np.abs(dc).max()) < 1e-3 * ke0               # same size of the Verlet fluctuation
+    assert abs(dg[:1] - dc[:1]).max() < 1e-6 * ke0                             # still the same trajectory after 10^3 steps
