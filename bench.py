@@ -312,7 +312,7 @@ def main():
         eng.advance(integrator, dt, 0, 1)
         e_bytes = 0
         for s in range(1, ke2e + 1):
-            eng.advance(integrator, dt, s, 1)
+            eng.advance(integrator, dt, s, 1, with_energy=True)
             e = eng.energies()
             e_bytes = 8 * (len(e[0]) + 1 + len(e[3]) * (3 * 3 + 2)) + 16
         out = eng.download()
@@ -323,7 +323,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": n_total * ke2e / float(te.item()), "unit": "atom-steps/s", "h2d_bytes_per_step": int(2 * 24 * n_atoms / ke2e),
                "d2h_bytes_per_step": int(e_bytes + (3 * 32 + 4) * n_atoms / ke2e), "steps": ke2e,
-               "what": "pfmds_upload(H2D pinned) + %d x [pfmds_advance(1) + pfmds_energies (D2H)] + pfmds_download(D2H)" % ke2e}
+               "what": "pfmds_upload(H2D pinned) + %d x [pfmds_advance_with_energy(1) + pfmds_energies (D2H)] + pfmds_download(D2H)" % ke2e}
         del out
 
     if rank != 0:

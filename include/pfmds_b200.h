@@ -79,6 +79,10 @@ int pfmds_add_interaction(pfmds_ctx* ctx, const char* name, int n_params, const 
  * step 0 only evaluates lists and forces).  Asynchronous. */
 int pfmds_advance(pfmds_ctx* ctx, int integrator, double dt, int first_md_step, int n_steps);
 
+/* Same, and the force evaluation of the LAST step also produces the potential energies (md() knows which steps log:
+ * md_simulation.f90:188), so the pfmds_energies that follows needs no second sweep over the neighbour lists. */
+int pfmds_advance_with_energy(pfmds_ctx* ctx, int integrator, double dt, int first_md_step, int n_steps);
+
 /* calculate_potential_energies + calculate_temperature(all_moving) + calculate_nose_hoover_chain_energy
  * (md_simulation.f90:191-198).  e_inter[n_interactions], e_nhc[n_nhc].  Synchronises. */
 int pfmds_energies(pfmds_ctx* ctx, double* e_inter, double* kinetic_energy, double* temperature, double* e_nhc);

@@ -66,7 +66,7 @@ struct OracleEngine {
         sys.interactions.push_back(std::move(it));
         allocate_graphene_norm(sys.interactions);
     }
-    void advance(int kind, double dt, int first, int n) {
+    void advance(int kind, double dt, int first, int n, bool = false) {
         init_time_steps(sys.dt, dt);
         for (int t = first; t < first + n; ++t) sys.step(t, kind_names.at((size_t)kind));
     }

@@ -289,7 +289,8 @@ void update_lists(pfmds_ctx* c, int step) {
     for (size_t k = 0; k < c->inter.size(); ++k) normals_interaction(c, (int)k);  // update_norm_in_graphene, every step
 }
 
-void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call) {
+void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bool with_energy = false) {
+    c->energy_valid = false;
     {
         PhaseTimer t(c, 0);
         if (first_of_call) integ_check_positions(c);
@@ -317,8 +318,9 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call) {
         PhaseTimer t(c, 4);
         if (step % c->zero_momentum_period == 0) integ_zero_momentum(c);
         forces_zero(c);
-        for (size_t k = 0; k < c->inter.size(); ++k) forces_interaction(c, (int)k);
+        for (size_t k = 0; k < c->inter.size(); ++k) forces_interaction(c, (int)k, with_energy);
         if (c->slab) slab_step_done(c);
+        c->energy_valid = with_energy;
     }
     if (step != 0) {
         PhaseTimer t(c, 0);
@@ -552,7 +554,10 @@ int pfmds_add_interaction(pfmds_ctx* c, const char* name, int np, const double* 
     });
 }
 
-int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) {
+static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, bool energy_last);
+int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) { return advance_impl(c, kind, dt, first, n, false); }
+int pfmds_advance_with_energy(pfmds_ctx* c, int kind, double dt, int first, int n) { return advance_impl(c, kind, dt, first, n, true); }
+static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, bool energy_last) {
     if (!c) return PFMDS_ERR_INVALID;
     return guarded(c, [&] {
         if (n < 0 || first < 0) fail(PFMDS_ERR_INVALID, "error: bad step range");
@@ -564,10 +569,11 @@ int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) {
             bool rebuild = false;
             for (auto& it : c->inter)
                 for (int j = 0; j < it.nl_n; ++j) rebuild |= (s % it.nl[j].period == 0) || !it.nl[j].built;
+            const bool with_energy = energy_last && s == first + n - 1;
             const bool graphable = c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && !rebuild &&
-                                   (s % c->zero_momentum_period != 0);
+                                   (s % c->zero_momentum_period != 0) && !with_energy;
             if (!graphable) {
-                do_step(c, s, kind, dt, s == first);
+                do_step(c, s, kind, dt, s == first, with_energy);
                 if (c->slab && std::getenv("PFMDS_SLAB_DEBUG")) {
                     std::fprintf(stderr, "[slab %d] step %d queued\n", slab_rank(c), s); std::fflush(stderr);
                     cudaError_t e = cudaStreamSynchronize(c->st);
@@ -602,6 +608,7 @@ int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) {
             }
             CK(cudaGraphLaunch(g->exec, c->st));
             c->launches += g->launches;
+            c->energy_valid = false;
             // host-side bookkeeping of do_step for this integrator
             if (kind == PFMDS_NVT && c->nhc_fusable) { c->nhc_pending = true; c->nhc_ke_valid = true; }
             else { c->nhc_pending = false; c->nhc_ke_valid = false; }
@@ -623,7 +630,8 @@ int pfmds_energies(pfmds_ctx* c, double* e_inter, double* ke, double* temp, doub
         integ_flush_pending(c);
         {
             PhaseTimer t(c, 5);
-            for (size_t k = 0; k < c->inter.size(); ++k) energy_interaction(c, (int)k);
+            if (!c->energy_valid)  // else: computed by the force pass of the last step (pfmds_advance_with_energy)
+                for (size_t k = 0; k < c->inter.size(); ++k) energy_interaction(c, (int)k);
             integ_kinetic_energy(c, c->all_moving, c->red);
         }
         std::vector<double> he(c->inter.size() + 1, 0.);
@@ -801,6 +809,7 @@ int pfmds_upload(pfmds_ctx* c, const double* pos, const double* vel) {
         const size_t n3 = 3 * (size_t)c->N;
         integ_flush_pending(c);
         c->nhc_ke_valid = false;
+        c->energy_valid = false;
         double *dp = nullptr, *dv = nullptr;
         if (pos) { CK(cudaMallocAsync(&dp, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
         if (vel) { CK(cudaMallocAsync(&dv, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
@@ -1034,6 +1043,7 @@ int pfmds_slab_upload(pfmds_ctx* c, int n_local, const double* pos, const double
         CK(cudaSetDevice(c->dev));
         integ_flush_pending(c);
         c->nhc_ke_valid = false;
+        c->energy_valid = false;
         const size_t N = (size_t)c->N;
         std::vector<uint32_t> hm(N);
         CK(cudaMemcpyAsync(hm.data(), c->gmask, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, c->st));

@@ -83,6 +83,7 @@ struct pfmds_ctx {
     struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid; cudaGraphExec_t exec; long long launches; };
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
+    bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)
     bool finalized = false;
     // fused NVT path (integrate.cu): usable when the thermostat groups are pairwise disjoint
     bool nhc_fusable = false;
@@ -150,7 +151,7 @@ long long slab_n_global(pfmds_ctx* c);
 
 // ---- forces.cu ----
 void forces_zero(pfmds_ctx* c);
-void forces_interaction(pfmds_ctx* c, int k);
+void forces_interaction(pfmds_ctx* c, int k, bool with_energy);
 void normals_interaction(pfmds_ctx* c, int k);
 void energy_interaction(pfmds_ctx* c, int k);  // result in c->energy[k]
 

@@ -608,19 +608,37 @@ void normals_interaction(pfmds_ctx* c, int k) {  // update_norm_in_graphene, md_
     c->launches += 1;
 }
 
-void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interactions.f90:210-242
+// with_energy: the same pass also yields the interaction's potential energy (what pfmds_energies would compute with a
+// second sweep over the lists): fused into the force kernels for rjl, lj1g and lj, a follow-up kernel for the others.
+void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_forces, md_interactions.f90:210-242
     Inter& it = c->inter[k];
+    double* epart = with_energy ? c->part : nullptr;
+    int e_parts = 0;
+    double e_scale = 1.0;
     const int N = c->N, nb = (N + FT - 1) / FT;
     const bool small = N < SMALL_N;
     const int nbs = (int)(((size_t)N * SMALL_SPLIT + FT - 1) / FT);
     const size_t st = c->stride;
     switch (it.kind) {
     case K_LJ:
+        if (with_energy) {
+            KTimer kt(c, KS_LJ);
+            if (small) k_lj<true, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, epart);
+            else k_lj<true, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, epart);
+            e_parts = small ? nbs : nb;
+        } else
         { KTimer kt(c, KS_LJ); if (small) k_lj<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); else k_lj<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); }
+        if (e_parts) { k_sum_partials<<<1, 1024, 0, c->st>>>(e_parts, c->part, 1.0, c->energy + k); c->launches += 1; if (c->slab) slab_allreduce_sum(c, c->energy + k, 1); e_parts = 0; with_energy = false; }
         { KTimer kt(c, KS_LJ); if (small) k_lj<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); else k_lj<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); }
         c->launches += 2;
         break;
     case K_LJ1G:
+        if (with_energy) {
+            KTimer kt(c, KS_LJ1G);
+            if (small) k_lj1g<true, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);
+            else k_lj1g<true, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);
+            e_parts = small ? nbs : nb; e_scale = 0.5;
+        } else
         { KTimer kt(c, KS_LJ1G); if (small) k_lj1g<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); else k_lj1g<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); }
         c->launches += 1;
         break;
@@ -631,6 +649,11 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
         const bool fused = c->slab && !small && slab_fused(c);  // density stores 1/Eb into the neighbours' ghosts itself
         {
             KTimer kt(c, KS_RJL_DENSITY);
+            if (with_energy) {
+                if (small) k_rjl_density_split<true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, epart);
+                else k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, epart, fused ? slab_dev(c, 1) : SlabDev{});
+                e_parts = small ? nbs : nb;
+            } else
             if (small) k_rjl_density_split<false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr);
             else k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr, fused ? slab_dev(c, 1) : SlabDev{});
         }
@@ -671,6 +694,15 @@ void forces_interaction(pfmds_ctx* c, int k) {  // calculate_forces, md_interact
         c->launches += simp ? 2 : 3;
         break;
     }
+    }
+    if (with_energy) {
+        if (e_parts) {
+            k_sum_partials<<<1, 1024, 0, c->st>>>(e_parts, c->part, e_scale, c->energy + k);
+            c->launches += 1;
+            if (c->slab) slab_allreduce_sum(c, c->energy + k, 1);
+        } else {
+            energy_interaction(c, k);  // tb, ljc, morsec: separate sweep, still inside the step (no host round trip)
+        }
     }
     CK(cudaGetLastError());
 }

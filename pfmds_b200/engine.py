@@ -44,6 +44,7 @@ _SIGS = {
     "set_misc": [C.c_void_p, C.c_int, C.c_int],
     "add_interaction": [C.c_void_p, C.c_char_p, C.c_int, _dp, C.c_int, _ip, _ip, _dp, _ip],
     "advance": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int],
+    "advance_with_energy": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int],
     "energies": [C.c_void_p, _dp, _dp, _dp, _dp],
     "diagnostics": [C.c_void_p, _dp, _dp, _dp, _dp, _ip],
     "download": [C.c_void_p, _dp, _dp, _dp],
@@ -67,7 +68,7 @@ _SIGS = {
 }
 
 
-_OPTIONAL = ("upload", "pair_count", "set_profiling", "kernel_times", "timer_start", "timer_stop")  # product-only entry points
+_OPTIONAL = ("advance_with_energy", "upload", "pair_count", "set_profiling", "kernel_times", "timer_start", "timer_stop")  # product-only entry points
 
 
 def load_library(path=LIB_PATH, prefix="pfmds_"):
@@ -140,9 +141,11 @@ class Engine:
         self.inter.append((name, list(lists)))
 
     # ---- hot path ----
-    def advance(self, integrator, dt, first_md_step, n_steps):
+    def advance(self, integrator, dt, first_md_step, n_steps, with_energy=False):
+        """with_energy: the last step's force pass also yields the potential energies (no second sweep in energies())."""
         kind = KIND[integrator] if isinstance(integrator, str) else int(integrator)
-        self._call("advance", self._ctx, kind, float(dt), int(first_md_step), int(n_steps))
+        name = "advance_with_energy" if with_energy and hasattr(self._lib, self._p + "advance_with_energy") else "advance"
+        self._call(name, self._ctx, kind, float(dt), int(first_md_step), int(n_steps))
 
     def synchronize(self):
         self._call("synchronize", self._ctx)

@@ -31,7 +31,9 @@ public:
         ++n_inter_;
         n_lists_ += s.nl_n;
     }
-    void advance(int kind, double dt, int first, int n) { ck(pfmds_advance(ctx_, kind, dt, first, n)); }
+    void advance(int kind, double dt, int first, int n, bool energy_after_last) {
+        ck(energy_after_last ? pfmds_advance_with_energy(ctx_, kind, dt, first, n) : pfmds_advance(ctx_, kind, dt, first, n));
+    }
     void energies(std::vector<double>& e_inter, double& ke, double& temp, std::vector<double>& e_nhc) {
         e_inter.assign((size_t)n_inter_ + 1, 0.);
         e_nhc.assign((size_t)n_nhc_ + 1, 0.);

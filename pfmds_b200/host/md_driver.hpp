@@ -7,7 +7,7 @@
 //
 // Engine concept (all methods throw std::runtime_error on failure, with the reference's message):
 //   create(n,pos,vel,mass,box) set_group(g,idx1) set_roles(am,xyz,z,all) add_interaction(spec)
-//   add_nhc(spec) set_misc(zero_momentum_period,invert_z) advance(kind,dt,first_md_step,n_steps)
+//   add_nhc(spec) set_misc(zero_momentum_period,invert_z) advance(kind,dt,first_md_step,n_steps,energy_after_last)
 //   energies(e_inter,ke,temp,e_nhc) diagnostics(fs,mc,mcv,vmax,nl_load) download(pos,vel,frc)
 //   timers(t[6])   -> seconds: pos_vel, nlists, nlsearch, nldistance, forces, energy
 #pragma once
@@ -241,7 +241,7 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
         while (md_step + n <= limit && !event_after(md_step + n - 1, integrator_index, kind) &&
                !(md_step + n - 1 == cum_len(integrator_index)))
             ++n;
-        eng.advance(kind, ts1, md_step, n);
+        eng.advance(kind, ts1, md_step, n, needs_energy(md_step + n - 1, integrator_index, kind));
         for (int t = md_step; t < md_step + n; ++t) {
             prev_potential_energy = potential_energy;  // :158
             if (t != 0) simulation_time = simulation_time + ts1;  // :184

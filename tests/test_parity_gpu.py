@@ -251,3 +251,19 @@ def test_nve_energy_drift_over_10k_steps(name):
     assert np.abs(dg).max() < 2e-3 * ke0 and np.abs(dc).max() < 2e-3 * ke0     # bounded: no drift on either side
     assert abs(np.abs(dg).max() - np.abs(dc).max()) < 1e-3 * ke0               # same size of the Verlet fluctuation
     assert abs(dg[:1] - dc[:1]).max() < 1e-6 * ke0                             # still the same trajectory after 10^3 steps
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_energies_from_the_force_pass(name):
+    """pfmds_advance_with_energy: the potential energies produced inside the last step's force pass equal the separate sweep."""
+    case = CASES[name]
+    integ, dt = case["integrators"][0][0], case["integrators"][0][1]
+    a, b = gpu(case), gpu(case)
+    a.advance(integ, dt, 0, 7, with_energy=True)
+    b.advance(integ, dt, 0, 7)
+    ea, eb = a.energies(), b.energies()
+    assert np.allclose(ea[0], eb[0], rtol=1e-13, atol=0) and ea[1] == eb[1]
+    assert np.array_equal(a.download()[2], b.download()[2])      # and the forces are the same bits
+    a.advance(integ, dt, 7, 3)                                     # a later plain step invalidates the cached energies
+    b.advance(integ, dt, 7, 3)
+    assert np.allclose(a.energies()[0], b.energies()[0], rtol=1e-13, atol=0)
