@@ -14,7 +14,7 @@ HOST = os.path.join(HERE, "host")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", CXX]
+NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", CXX] + os.environ.get("PFMDS_NVCC_EXTRA", "").split()
 SOURCES = ["nl.cu", "forces.cu", "integrate.cu", "capi.cu", "slab.cu"]
 LIB = os.path.join(CSRC, "libpfmds_b200.so")
 EXE = os.path.join(HOST, "run_md_simulation")

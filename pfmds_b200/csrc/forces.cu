@@ -165,7 +165,7 @@ static RjlC rjl_consts(const RJLp& P) {
 // component can need wrapping (exact, the comparison is conservative); otherwise the exact FP64 test of
 // find_distance runs.  Only atoms within r_cut of a face ever take the second path.
 #ifndef RJL_MINB
-#define RJL_MINB 6
+#define RJL_MINB 7  // measured on B200: 4: 0.997, 5: 1.004, 6: 0.968, 7: 0.948, 8: 0.957 ms/step
 #endif
 struct WrapC { int min_half_hi; };
 static WrapC wrap_consts(const BoxD& b) {
