@@ -357,6 +357,8 @@ def main():
             "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src, "copy_gbs_live": copy_gbs},
             "traffic": _ncu_traffic(name),
         }
+        if n_atoms < 200000:
+            roofline["note"] = "system of %d atoms: every kernel is launch/latency bound (grid smaller than one wave), the FP64 fraction is not the figure of merit" % n_atoms
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         n, steps, tcpu, cores = cpu_baseline_sample(20)

@@ -418,8 +418,8 @@ void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step) {
     if (c->slab && slab_pos_pushed_by_kick(c, rebuild_step)) S = slab_dev(c, 0);
     k_kick_drift_nvt<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
                                                              1u << (c->z_moving - 1), dt, dt / 2, c->box, P, c->err, S);
-    k_reset_pending<<<1, 32, 0, c->st>>>(P);
-    c->launches += 3;
+    // s_pending has been consumed; the closing half step of this same step overwrites it (k_nhc_close), so no reset here
+    c->launches += 2;
 }
 __global__ void k_reduce_ke_partials(int nparts, const double* __restrict__ part, int n, double* __restrict__ out) {
     for (int k = 0; k < n; ++k) {
