@@ -267,8 +267,8 @@ def main():
     launches0 = eng.launch_count()
     prof_in_region = n_atoms >= 200000
     eng.set_profiling(prof_in_region)
-    barrier()
     with ClockSampler(local) as cs:
+        barrier()   # after the sampler is up: in the lock-stepped slab mode a rank that starts late makes every other rank wait
         eng.timer_start()
         eng.advance(integrator, dt, W, K)
         ms = eng.timer_stop()
@@ -326,6 +326,12 @@ def main():
                "what": "pfmds_upload(H2D pinned) + %d x [pfmds_advance_with_energy(1) + pfmds_energies (D2H)] + pfmds_download(D2H)" % ke2e}
         del out
 
+    # per-rank view (explains stragglers in the lock-stepped slab mode): own kernel times and clocks
+    per_rank = None
+    if dist is not None:
+        mine = {"rank": rank, "ms": ms, "kernels_ms_per_step": {k: round(v[0] / K, 4) for k, v in ktimes.items()}, "clocks": cs.summary()}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -371,6 +377,7 @@ def main():
                    "l2": "working set (lists %.0f MB + state) exceeds the 126 MB L2" % (pairs * 4 / 1e6), "ns_per_day": K / (ms_max * 1e-3) * dt * 86400e-6},
         "clocks": cs.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
+        "per_rank": per_rank,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -87,6 +87,16 @@ struct Slab {
 
 __global__ void k_sl_scatter_rs(int n, const int* __restrict__ idx, const int* __restrict__ ps, int* __restrict__ rs);
 
+// Host waits of the redistribution block on an event instead of spinning: with one process per GPU and the NCCL /
+// watchdog threads of the host framework, eight spinning ranks oversubscribe a 16-thread host and one descheduled
+// rank stalls all the others at the next exchange.
+static void host_wait(pfmds_ctx* c) {
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, c->st));
+    CK(cudaEventSynchronize(ev));
+}
+
 // ---- small generic pieces ---------------------------------------------------------------------------
 __global__ void k_sl_scan_block(int n, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ sums) {
     __shared__ int sh[32];
@@ -328,7 +338,7 @@ static void slab_exchange_peer_slots(pfmds_ctx* c, Slab* s) {
     NK(g_nccl.Recv(s->cnt_d + 14, 1, ncclInt, s->left, s->comm, c->st));
     NK(g_nccl.GroupEnd());
     CK(cudaMemcpyAsync(s->peer_parity, s->cnt_d + 14, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    host_wait(c);
     // per-slot view of the same lists, for the kernels that push while they compute
     for (int d = 0; d < 2; ++d) {
         CK(cudaMemsetAsync(s->rs[d], 0xff, sizeof(int) * c->stride, c->st));
@@ -471,7 +481,7 @@ static void exchange_counts(pfmds_ctx* c, Slab* s, const int* ns, int* nr) {
     NK(g_nccl.Recv(s->cnt_d + 10, 1, ncclInt, s->left, s->comm, c->st));
     NK(g_nccl.GroupEnd());
     CK(cudaMemcpyAsync(nr, s->cnt_d + 10, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    host_wait(c);
 }
 
 // Rebuild step: migrate, then re-select and import ghosts.  Leaves c->N = n_local + n_ghost with the ghosts
@@ -490,7 +500,7 @@ void slab_redistribute(pfmds_ctx* c) {
     exclusive_scan(c, s, f2, s->scan[2], N0, s->cnt_d + 2);
     int h[3];
     CK(cudaMemcpyAsync(h, s->cnt_d, sizeof h, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    host_wait(c);
     int ns[2] = {h[1], h[2]}, nr[2] = {0, 0};
     exchange_counts(c, s, ns, nr);
     const int n_stay = h[0];
@@ -510,7 +520,7 @@ void slab_redistribute(pfmds_ctx* c) {
     exclusive_scan(c, s, f0, s->scan[0], NL, s->cnt_d + 3);
     exclusive_scan(c, s, f1, s->scan[1], NL, s->cnt_d + 4);
     CK(cudaMemcpyAsync(h, s->cnt_d + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    host_wait(c);
     s->n_send[0] = h[0]; s->n_send[1] = h[1];
     exchange_counts(c, s, s->n_send, s->n_recv);
     if ((size_t)NL + s->n_recv[0] + s->n_recv[1] > c->stride) throw std::string("slab decomposition: capacity exceeded by ghosts");
