@@ -59,16 +59,6 @@ __device__ __forceinline__ double fcut_only(double r, double R1, double R2) {
     mx::sincos_0pi(PFMDS_PI * (r - R1) / (R2 - R1), s, c);
     return (1.0 + c) / 2;
 }
-// Minimum image for the force kernels: the comparison with half the box is done on the high words
-// (integer pipe).  It can differ from min_image() only when |d| is within 2^-20 relative of L/2, where
-// either image is farther than every potential cut-off (the box is at least 2 r_cut wide), so the
-// contribution is zero both ways.  List building keeps the exact FP64 test.
-__device__ __forceinline__ double min_image_fast(double d, int half_hi, double L) {
-    int hi = __double2hiint(d);
-    if ((hi & 0x7fffffff) >= half_hi) d += (hi < 0) ? L : -L;
-    return d;
-}
-
 // One 256-bit load per 32-byte record (sm_100a LDG.E.256): a gather of 32 records costs the L1 one
 // request instead of the two LDG.128 the compiler emits for a double4.
 __device__ __forceinline__ double4 ld256_nc(const double4* p) {  // read-only data

@@ -119,7 +119,6 @@ struct KTimer {
 };
 
 #define RED_BLOCKS 592  // 148 SMs x 4
-#define RED_THREADS 256
 
 // ---- nl.cu ----
 void nl_setup_grid(pfmds_ctx* c);

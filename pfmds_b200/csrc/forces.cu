@@ -186,8 +186,7 @@ __device__ __forceinline__ void wrap3(double& dx, double& dy, double& dz, const 
 }
 
 template <bool E>
-__device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, const double* tab, double& sq,
-                                                 double& sp) {
+__device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& sq, double& sp) {
     double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
     wrap3(dx, dy, dz, box, mhh);
     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -205,7 +204,6 @@ __device__ __forceinline__ void rjl_density_pair(const double4& pi, const double
 }
 template <bool E>
 __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part, SlabDev S) {
-    const double* tab = nullptr;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
     bool pushed = false;
@@ -226,12 +224,12 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* po
             int j2 = p + 2 < n ? rp[2 * st] : j1;
             int j3 = p + 3 < n ? rp[3 * st] : j1;
             rp += 2 * st;
-            rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, tab, sq, sp);
+            rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, sq, sp);
             a = ld256(&pos[j2]);
-            rjl_density_pair<E>(pi, b, C, box, W.min_half_hi, tab, sq, sp);
+            rjl_density_pair<E>(pi, b, C, box, W.min_half_hi, sq, sp);
             j1 = j3;
         }
-        if (p < n) rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, tab, sq, sp);
+        if (p < n) rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, sq, sp);
         double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
         reinterpret_cast<double*>(&pos[i])[3] = ie;
         if (S.push) {  // the same 1/Eb goes straight into the ghost copies of this atom on the neighbour GPUs (NVLink stores)
@@ -254,7 +252,7 @@ __global__ void __launch_bounds__(FT) k_rjl_density_split(int N, double4* pos, L
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
         const double4 pi = ld256(&pos[i]);
-        for (int p = sub; p < n; p += SPLIT) rjl_density_pair<E>(pi, ld256(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, nullptr, sq, sp);
+        for (int p = sub; p < n; p += SPLIT) rjl_density_pair<E>(pi, ld256(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, sq, sp);
     }
     sq = split_sum<SPLIT>(sq);
     if (E) sp = split_sum<SPLIT>(sp);
@@ -266,8 +264,8 @@ __global__ void __launch_bounds__(FT) k_rjl_density_split(int N, double4* pos, L
     if (E) store_partial(e, part);
 }
 
-__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, const double* tab, double& fx,
-                                               double& fy, double& fz) {
+__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                               double& fz) {
     double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
     wrap3(dx, dy, dz, box, mhh);
     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -290,7 +288,6 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
 }
 __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
                                                             WrapC W, SlabDev S) {
-    const double* tab = nullptr;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);  // slab mode: the neighbours' 1/Eb have landed in my ghost slots
     if (i >= N) return;
@@ -308,12 +305,12 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4
         int j2 = p + 2 < n ? rp[2 * st] : j1;
         int j3 = p + 3 < n ? rp[3 * st] : j1;
         rp += 2 * st;
-        rjl_force_pair(pi, a, C, box, W.min_half_hi, tab, fx, fy, fz);
+        rjl_force_pair(pi, a, C, box, W.min_half_hi, fx, fy, fz);
         a = ld256_nc(&pos[j2]);
-        rjl_force_pair(pi, b, C, box, W.min_half_hi, tab, fx, fy, fz);
+        rjl_force_pair(pi, b, C, box, W.min_half_hi, fx, fy, fz);
         j1 = j3;
     }
-    if (p < n) rjl_force_pair(pi, a, C, box, W.min_half_hi, tab, fx, fy, fz);
+    if (p < n) rjl_force_pair(pi, a, C, box, W.min_half_hi, fx, fy, fz);
     add_force(frc, i, fx, fy, fz);
 }
 
@@ -325,7 +322,7 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
         const double4 pi = ld256_nc(&pos[i]);
-        for (int p = sub; p < n; p += SPLIT) rjl_force_pair(pi, ld256_nc(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, nullptr, fx, fy, fz);
+        for (int p = sub; p < n; p += SPLIT) rjl_force_pair(pi, ld256_nc(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, fx, fy, fz);
     }
     fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz);
     if (n > 0 && sub == 0) add_force(frc, i, fx, fy, fz);

@@ -98,36 +98,6 @@ MX_HD double exp_nc(double x) {
     return as_double(as_ll(p) + (k << 52));
 }
 
-// Table-driven exp for bounded arguments: n = round(x 32/ln2), e^x = 2^(n>>5) T[n&31] e^r', |r'| <= ln2/64,
-// e^r' by a degree-5 Taylor polynomial (truncation 2e-15).  T[j] = 2^(j/32) is read from `tab` (shared
-// memory on the device, filled from EXP_T).  10 FP64 operations instead of 16.
-MX_CONST double EXP_T[32] = {
-    1.00000000000000000000e+00, 1.02189714865411662714e+00, 1.04427378242741375480e+00, 1.06714040067682369717e+00,
-    1.09050773266525768967e+00, 1.11438674259589243221e+00, 1.13878863475669156458e+00, 1.16372485877757747552e+00,
-    1.18920711500272102690e+00, 1.21524735998046895524e+00, 1.24185781207348400201e+00, 1.26905095719173321989e+00,
-    1.29683955465100964055e+00, 1.32523664315974132322e+00, 1.35425554693689265129e+00, 1.38390988196383202258e+00,
-    1.41421356237309514547e+00, 1.44518080697704665027e+00, 1.47682614593949934623e+00, 1.50916442759342284141e+00,
-    1.54221082540794074411e+00, 1.57598084510788649659e+00, 1.61049033194925428347e+00, 1.64575547815396494578e+00,
-    1.68179283050742900407e+00, 1.71861929812247793414e+00, 1.75625216037329945351e+00, 1.79470907500310716820e+00,
-    1.83400808640934243066e+00, 1.87416763411029996256e+00, 1.91520656139714740007e+00, 1.95714412417540017941e+00};
-MX_CONST double EXP_P[5] = {1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
-MX_HD double exp_tab(double x, const double* tab) {
-    const double MAGIC = 6755399441055744.0;
-    double t = fma(x, 46.166241308446828384, MAGIC);  // 32/ln2
-    double nd = t - MAGIC;
-    int n = (int)(unsigned int)(as_ll(t) & 0xffffffffll);
-    double r = fma(nd, -0.021660849392503678, x);   // ln2/32 = hi + lo, hi has 41 significant bits: nd*hi is exact
-    r = fma(nd, 5.387326414254636e-15, r);          // -lo
-    double p = EXP_P[4];
-    p = fma(p, r, EXP_P[3]);
-    p = fma(p, r, EXP_P[2]);
-    p = fma(p, r, EXP_P[1]);
-    p = fma(p, r, EXP_P[0]);
-    p = fma(p, r, 1.0);
-    p = p * tab[n & 31];
-    return as_double(as_ll(p) + ((long long)(n >> 5) << 52));
-}
-
 // Cosine switch without selects: for a in [0, pi], u = a/2 - pi/4 in [-pi/4, pi/4],
 //   (1 + cos a)/2 = cos^2(a/2) = (cos u - sin u)^2 / 2,   sin a = (cos u - sin u)(cos u + sin u).
 MX_HD void cos_switch(double a, double& half_one_plus_cos, double& sin_a) {

@@ -56,14 +56,13 @@ NcclApi g_nccl;
 struct Slab {
     int rank = 0, nranks = 1, left = 0, right = 0;
     ncclComm_t comm = nullptr;
-    int n_local = 0, n_ghost = 0, cap = 0, cap_border = 0;
+    int n_local = 0, n_ghost = 0, cap = 0;
     long long n_global = 0;
     double W = 0, H = 0;
     int *send_idx[2]{nullptr, nullptr}, *ghost_slot[2]{nullptr, nullptr};
     int n_send[2]{0, 0}, n_recv[2]{0, 0};
     double *sbuf[2]{nullptr, nullptr}, *rbuf[2]{nullptr, nullptr};
     int *cat = nullptr, *scan[3]{nullptr, nullptr, nullptr}, *flag = nullptr, *cnt_d = nullptr, *scan_tmp = nullptr;
-    double* red_tmp = nullptr;
     // direct peer-memory halo (NVLink stores into the neighbours' ghost slots, device-side flags instead of NCCL)
     bool p2p = false;
     int* flags = nullptr;                       // mine, written by the neighbours: [0,1] pos ready from left/right, [2,3] 1/Eb ready, [4,5] step done
@@ -376,7 +375,6 @@ void slab_init(pfmds_ctx* c, int rank, int nranks, const char* id128, long long 
     memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
     NK(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
     const size_t S = c->stride;
-    s->cap_border = (int)S;  // generous: the payload buffers can hold every slot
     for (int d = 0; d < 2; ++d) {
         CK(cudaMalloc(&s->send_idx[d], sizeof(int) * S));
         CK(cudaMalloc(&s->ghost_slot[d], sizeof(int) * S));
@@ -388,7 +386,6 @@ void slab_init(pfmds_ctx* c, int rank, int nranks, const char* id128, long long 
     for (int k = 0; k < 3; ++k) CK(cudaMalloc(&s->scan[k], sizeof(int) * S));
     CK(cudaMalloc(&s->cnt_d, sizeof(int) * 16));
     CK(cudaMalloc(&s->scan_tmp, sizeof(int) * (S / 2048 + 2)));
-    CK(cudaMalloc(&s->red_tmp, sizeof(double) * 64));
     CK(cudaMalloc(&c->newslot, sizeof(int) * S));
     const char* env = std::getenv("PFMDS_SLAB_P2P");
     s->p2p = !(env && env[0] == '0') && slab_setup_p2p(c, s);
@@ -399,7 +396,7 @@ void slab_destroy(pfmds_ctx* c) {
     if (!s) return;
     for (int d = 0; d < 2; ++d) { cudaFree(s->send_idx[d]); cudaFree(s->ghost_slot[d]); cudaFree(s->sbuf[d]); cudaFree(s->rbuf[d]); }
     cudaFree(s->cat); cudaFree(s->flag); for (int k = 0; k < 3; ++k) cudaFree(s->scan[k]);
-    cudaFree(s->cnt_d); cudaFree(s->scan_tmp); cudaFree(s->red_tmp); cudaFree(c->newslot);
+    cudaFree(s->cnt_d); cudaFree(s->scan_tmp); cudaFree(c->newslot);
     for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(s->flags); cudaFree(s->pslot[0]); cudaFree(s->pslot[1]); cudaFree(s->rs[0]); cudaFree(s->rs[1]); cudaFree(s->counter);
     if (s->comm) g_nccl.CommDestroy(s->comm);

@@ -7,7 +7,6 @@ double mx_exp(double x) { return mx::exp_fast(x); }
 void mx_sincos(double a, double* s, double* c) { mx::sincos_0pi(a, *s, *c); }
 double mx_exp_nc(double x) { return mx::exp_nc(x); }
 void mx_cos_switch(double a, double* f, double* s) { mx::cos_switch(a, *f, *s); }
-double mx_exp_tab(double x) { return mx::exp_tab(x, mx::EXP_T); }
 double mx_log(double x) { return mx::log_fast(x); }
 double mx_pow(double x, double y) { return mx::pow_pos(x, y); }
 double mx_rcp(double x) { return mx::rcp_fast(x); }

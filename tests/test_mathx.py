@@ -64,20 +64,6 @@ def test_exp_nc(lib):
     assert np.max(np.abs(got - ref) / ref) < 3e-14
 
 
-def test_exp_tab(lib):
-    lib.mx_exp_tab.restype = C.c_double
-    lib.mx_exp_tab.argtypes = [C.c_double]
-    xs = np.concatenate([np.random.default_rng(6).uniform(-600, 600, 20000), np.random.default_rng(7).uniform(-12, 12, 20000)])
-    got = np.array([lib.mx_exp_tab(float(x)) for x in xs])
-    ref = np.exp(xs.astype(np.longdouble)).astype(np.float64)
-    assert np.max(np.abs(got - ref) / ref) < 5e-15
-    t = np.array([2.0 ** (j / 32.0) for j in range(32)])
-    import re, os
-    src = open(os.path.join(ROOT, "pfmds_b200", "csrc", "mathx.cuh")).read()
-    tab = [float(v) for v in re.findall(r"[0-9]\.[0-9]{20}e[+-][0-9]{2}", src.split("EXP_T[32]")[1].split("};")[0])]
-    assert len(tab) == 32 and np.max(np.abs(np.array(tab) / t - 1)) < 2e-16
-
-
 def test_log_pow_rcp(lib):
     for f in (lib.mx_log, lib.mx_rcp):
         f.restype = C.c_double

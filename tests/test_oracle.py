@@ -133,3 +133,22 @@ def test_oracle_matches_golden(name):
     o.advance(integ, dt, 1, 10)
     p, v, f = o.download()
     assert np.abs(p - g["pos10"]).max() < 1e-11 and rel_err(f, g["frc10"]) < 1e-9
+
+
+def test_half_list_rule_drops_pairs_for_non_monotone_groups():
+    """lessnnum counts the entries before the first one whose GLOBAL index exceeds the owner's
+    (md_neighbours.f90:78).  For a group whose indexes are not ascending (type columns 'B A' with file order A.., B..)
+    lj1g then silently loses pairs.  The oracle reproduces that literally; the CUDA path refuses such input."""
+    base = small_cases()["ab_gas"]
+    mono = dict(base, groups=[["A", "B"], ["A", "#"], ["B", "#"], ["#", "#"]],
+                interactions=[dict(name="lj1g", params=[0.0103, 3.405, 6.0, 7.0], lists=[(1, 1, 200, 7.5, 5)])])
+    swapped = dict(mono, groups=[["B", "A"], ["A", "#"], ["B", "#"], ["#", "#"]])
+    e = []
+    for case in (mono, swapped):
+        o = oracle(case)
+        o.advance("nve", 0.5, 0, 1)
+        nl = neighbours(o, case, 0, 0)
+        e.append((o.energies()[0][0], int(nl[2].sum()), int(nl[1].sum())))
+    (e_mono, half_mono, full_mono), (e_swap, half_swap, full_swap) = e
+    assert full_mono == full_swap and half_mono * 2 == full_mono      # monotone: the half list holds every pair once
+    assert half_swap != half_mono and abs(e_swap - e_mono) > 1e-6 * abs(e_mono)   # swapped columns: pairs are lost
