@@ -10,6 +10,38 @@ from .engine import Engine, KIND, LIB_PATH, PfmdsError, _d, _i, load_library  # 
 from .inputs import group_indexes
 
 
+def slab_partition(case, rank, world):
+    """What rank `rank` of `world` hands to pfmds_create_slab: the 0-based file indexes of its atoms (x in
+    [rank*Lx/world, (rank+1)*Lx/world), edge values clamped like the device code), the per-atom group bit masks of
+    ALL atoms and the global group sizes."""
+    box = np.asarray(case["box"], np.float64)
+    n_global = len(case["mass"])
+    W = box[0] / world
+    owner = np.clip(np.floor(np.asarray(case["pos"])[:, 0] / W).astype(np.int64), 0, world - 1)
+    mine = np.where(owner == rank)[0]
+    ng = len(case["groups"])
+    mask = np.zeros(n_global, np.uint32)
+    sizes = np.zeros(ng, np.int64)
+    for g in range(1, ng + 1):
+        idx = group_indexes(case, g)
+        sizes[g - 1] = len(idx)
+        mask[idx - 1] |= np.uint32(1 << (g - 1))
+    return mine, mask, sizes
+
+
+def halo_atoms(case, rank, world, width):
+    """0-based file indexes of the atoms rank `rank` must hold as ghosts: owned by the left / right neighbour and within
+    `width` of the shared face (numpy restatement of slab.cu k_sl_border_flags, for tests)."""
+    box = np.asarray(case["box"], np.float64)
+    W = box[0] / world
+    x = np.asarray(case["pos"])[:, 0]
+    owner = np.clip(np.floor(x / W).astype(np.int64), 0, world - 1)
+    left, right = (rank - 1) % world, (rank + 1) % world
+    from_left = np.where((owner == left) & (((left + 1) * W - x) <= width))[0]      # the left neighbour's right border
+    from_right = np.where((owner == right) & ((x - right * W) < width))[0]          # the right neighbour's left border
+    return from_left, from_right
+
+
 class SlabEngine(Engine):
     """This rank's share of a case: atoms with x in [rank*Lx/world, (rank+1)*Lx/world)."""
 
@@ -26,16 +58,8 @@ class SlabEngine(Engine):
         L.pfmds_slab_download.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         box = np.ascontiguousarray(case["box"], np.float64)
         n_global = len(case["mass"])
-        W = box[0] / world
-        owner = np.clip(np.floor(case["pos"][:, 0] / W).astype(np.int64), 0, world - 1)
-        mine = np.where(owner == rank)[0]
+        mine, mask, sizes = slab_partition(case, rank, world)
         ng = len(case["groups"])
-        mask = np.zeros(n_global, np.uint32)
-        sizes = np.zeros(ng, np.int64)
-        for g in range(1, ng + 1):
-            idx = group_indexes(case, g)
-            sizes[g - 1] = len(idx)
-            mask[idx - 1] |= np.uint32(1 << (g - 1))
         self.n = n_global
         self.n_local0 = len(mine)
         self.capacity = int(len(mine) * capacity_factor) + 4096
