@@ -270,3 +270,38 @@ def write_case(directory, case, settings="md_run_settings.txt", xyz="init.xyz", 
     with open(os.path.join(directory, settings), "w") as f:
         f.write("\n".join(L) + "\n")
     return os.path.join(directory, settings)
+
+
+def cu_fcc_slab(rank, world, cells_per_rank=(63, 63, 63), a=3.615, seed=2, temperature=300.0):
+    """This rank's share of the Cu fcc crystal of `world * cells_per_rank[0]` x cells_per_rank[1] x cells_per_rank[2] cells,
+    generated locally (the 10^8-atom crystal of BASELINE.json configs[3] cannot be built whole on every rank).
+    Atom numbering and positions are those `cu_fcc(cells=(world*cx, cy, cz), jitter=0)` gives for the same atoms; velocities
+    are Maxwell draws per rank, and the global momentum / temperature rescale needs two sums over ranks: the caller reduces
+    `sums` (sum m v (3), sum m, sum m v^2) over the ranks and calls `finish_velocities`.
+    Returns (global_index_1based, pos, vel_raw, mass, box, sums)."""
+    cx, cy, cz = cells_per_rank
+    gx = world * cx
+    basis = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]]) + 0.25
+    ii, jj, kk = np.meshgrid(np.arange(rank * cx, (rank + 1) * cx), np.arange(cy), np.arange(cz), indexing="ij")
+    cell = np.stack([ii, jj, kk], -1).reshape(-1, 1, 3)
+    pos = ((cell + basis[None]) * a).reshape(-1, 3)
+    # file order of cu_fcc(): cell-major (i, j, k) with the 4 basis atoms innermost
+    cell_id = (cell[:, 0, 0] * cy + cell[:, 0, 1]) * cz + cell[:, 0, 2]
+    gid = (cell_id[:, None] * 4 + np.arange(4)[None]).reshape(-1) + 1
+    n = len(pos)
+    mass = np.full(n, 63.546)
+    rng = np.random.Generator(np.random.Philox(key=seed, counter=[int(gid[0]), 0, 0, 0]))  # reproducible per rank, independent of the others
+    vel = rng.standard_normal((n, 3)) * np.sqrt(COEF * temperature / mass)[:, None]
+    sums = np.concatenate([(mass[:, None] * vel).sum(0), [mass.sum()], [(mass * (vel ** 2).sum(1)).sum()]])
+    box = np.array([gx * a, cy * a, cz * a])
+    return gid.astype(np.int64), pos, vel, mass, box, sums
+
+
+def finish_velocities(vel, mass, sums_all_ranks, n_total, temperature):
+    """Remove the global centre-of-mass velocity and rescale to exactly `temperature` (same steps as maxwell())."""
+    p, m = sums_all_ranks[:3], sums_all_ranks[3]
+    vcm = p / m
+    v = vel - vcm
+    ke = (sums_all_ranks[4] - m * (vcm ** 2).sum()) / 2 * MASS_COEF   # sum m (v - vcm)^2 = sum m v^2 - M vcm^2
+    t = 2 * ke / KB / (3 * n_total)
+    return v * np.sqrt(temperature / t)
