@@ -35,7 +35,7 @@ def _run(cmd):
 
 
 def build(force=False, verbose=False):
-    hdrs = [os.path.join(CSRC, h) for h in ("common.cuh", "ctx.hpp")] + [os.path.join(HERE, "..", "include", "pfmds_b200.h")]
+    hdrs = [os.path.join(CSRC, h) for h in sorted(os.listdir(CSRC)) if h.endswith((".cuh", ".hpp"))] + [os.path.join(HERE, "..", "include", "pfmds_b200.h")]
     objs = []
     jobs = []
     for s in SOURCES:

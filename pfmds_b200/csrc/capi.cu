@@ -117,6 +117,7 @@ void finalize_slab(pfmds_ctx* c) {
             if (c->nhc[a].group == c->nhc[b].group) c->nhc_fusable = false;
     if (c->nhc.size() > 1) c->nhc_fusable = false;  // several thermostats: masks are not on the host in slab mode, keep the plain path
     if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
+    c->first_overwrites = !c->inter.empty() && c->inter[0].kind == K_RJL && group_size(c, c->inter[0].nl[0].g1) == slab_n_global(c);
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
     c->finalized = true;
@@ -242,6 +243,7 @@ void finalize(pfmds_ctx* c) {
     }
     CK(cudaMemcpyAsync(c->gmask, c->h_gmask.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, c->st));
     if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
+    c->first_overwrites = !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
     c->finalized = true;

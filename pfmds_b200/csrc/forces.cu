@@ -202,8 +202,11 @@ __device__ __forceinline__ void rjl_density_pair(const double4& pi, const double
         if (E) sp = fma(mx::exp_nc(fma(C.pa, r, C.pb)), f, sp);
     }
 }
+#ifndef RJL_MINB_D
+#define RJL_MINB_D RJL_MINB
+#endif
 template <bool E>
-__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part, SlabDev S) {
+__global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part, SlabDev S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
     bool pushed = false;
@@ -287,12 +290,12 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
     }
 }
 __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
-                                                            WrapC W, SlabDev S) {
+                                                            WrapC W, SlabDev S, int overwrite) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);  // slab mode: the neighbours' 1/Eb have landed in my ghost slots
     if (i >= N) return;
     int n = lv.nnum[i];
-    if (n == 0) return;
+    if (n == 0) { if (overwrite) frc[i] = make_double4(0., 0., 0., 0.); return; }
     const double4 pi = ld256_nc(&pos[i]);
     double fx = 0, fy = 0, fz = 0;
     const int* rp = lv.nlist + i;
@@ -311,7 +314,9 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4
         j1 = j3;
     }
     if (p < n) rjl_force_pair(pi, a, C, box, W.min_half_hi, fx, fy, fz);
-    add_force(frc, i, fx, fy, fz);
+    // first interaction of the step and every atom is an owner: store instead of zero + accumulate (zero_forces fused away)
+    if (overwrite) frc[i] = make_double4(fx, fy, fz, 0.);
+    else add_force(frc, i, fx, fy, fz);
 }
 
 template <int SPLIT>
@@ -584,6 +589,7 @@ __global__ void __launch_bounds__(FT) k_cos_indirect(int N, const double4* __res
 
 // ------------------------------------------------------------------------------------------------
 void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
+    if (c->first_overwrites && c->N >= SMALL_N) return;  // the first force kernel stores instead of accumulating
     KTimer kt(c, KS_ZERO_FORCES);
     CK(cudaMemsetAsync(c->frc, 0, sizeof(double4) * (size_t)c->N, c->st));
 }
@@ -658,7 +664,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         {
             KTimer kt(c, KS_RJL_FORCE);
             if (small) k_rjl_force_split<SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W);
-            else k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W, fused ? slab_dev(c, 2) : SlabDev{});
+            else k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, (k == 0 && c->first_overwrites && N >= SMALL_N) ? 1 : 0);
         }
     }
         c->launches += 2;

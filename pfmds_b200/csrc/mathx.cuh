@@ -100,7 +100,11 @@ MX_HD double exp_nc(double x) {
 
 // Cosine switch without selects: for a in [0, pi], u = a/2 - pi/4 in [-pi/4, pi/4],
 //   (1 + cos a)/2 = cos^2(a/2) = (cos u - sin u)^2 / 2,   sin a = (cos u - sin u)(cos u + sin u).
+#ifdef MX_NOINLINE_SWITCH
+__device__ __noinline__ void cos_switch(double a, double& half_one_plus_cos, double& sin_a) {
+#else
 MX_HD void cos_switch(double a, double& half_one_plus_cos, double& sin_a) {
+#endif
     const double PIO4_HI = 7.85398163397448279e-01, PIO4_LO = 3.06161699786838302e-17;
     double u = (fma(a, 0.5, -PIO4_HI)) - PIO4_LO;
     double u2 = u * u;

@@ -267,3 +267,18 @@ def test_energies_from_the_force_pass(name):
     a.advance(integ, dt, 7, 3)                                     # a later plain step invalidates the cached energies
     b.advance(integ, dt, 7, 3)
     assert np.allclose(a.energies()[0], b.energies()[0], rtol=1e-13, atol=0)
+
+
+def test_store_instead_of_zero_plus_accumulate():
+    """When rjl is the first interaction and owns every atom its force kernel stores the force (no zero pass).  The same
+    system with a no-op interaction in front (lj1g on an empty group) takes the zero + accumulate path: identical bits."""
+    from pfmds_b200 import inputs
+    a = inputs.cu_fcc(ncell=30, jitter=0.03, period=5)          # 108 000 atoms: the large-system kernels
+    b = dict(a, interactions=[dict(name="lj1g", params=[0.01, 3.0, 6.0, 7.0], lists=[(2, 2, 8, 6.5, 5)])] + a["interactions"])   # same r_cut: same cell grid, same atom order
+    ea, eb = gpu(a), gpu(b)
+    for e in (ea, eb):
+        e.advance("nvt", 2.0, 0, 12)
+    pa, va, fa = ea.download()
+    pb, vb, fb = eb.download()
+    assert np.array_equal(fa, fb) and np.array_equal(pa, pb) and np.array_equal(va, vb)
+    assert np.abs(fa).max() > 0.1
