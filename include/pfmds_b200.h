@@ -56,6 +56,17 @@ int pfmds_set_group(pfmds_ctx* ctx, int group_num, int n, const int* indexes);
 /* all_moving / xyz_moving / z_moving / all_atoms group numbers (md_simulation.f90:57-60). */
 int pfmds_set_roles(pfmds_ctx* ctx, int all_moving_group, int xyz_moving_group, int z_moving_group, int all_atoms_group);
 
+/* One `change_group_num` entry of the settings file (md_simulation.f90:63-71): change_particle_group_N
+ * (md_general.f90:82-94) is applied to group `group_to` at the top of every md step (md_simulation.f90:116-119), i.e.
+ * group_to%N follows group_from%N up to step change_ts1, grows by one atom at change_ts1 and then every change_frec steps
+ * while step < change_ts2 (deposition); the group exposes the first N atoms of the index list given to pfmds_set_group.
+ * Entries are applied in the order they were added.  Steps must be advanced in sequence from md step 0. */
+int pfmds_add_group_change(pfmds_ctx* ctx, int group_from, int group_to, int change_ts1, int change_ts2, int change_frec);
+
+/* Current group%N (differs from the size given to pfmds_set_group only for targets of pfmds_add_group_change), after the
+ * last step queued by pfmds_advance: the writers (write_particle_group, md_read_write.f90:65-107) need it. */
+int pfmds_group_size(pfmds_ctx* ctx, int group_num, int* n);
+
 /* create_nose_hoover_chain + set_nose_hoover_chain (md_integrators.f90:165-198), one per settings line. */
 int pfmds_add_nhc(pfmds_ctx* ctx, int group_num, double temperature, int M, double q1);
 

@@ -60,6 +60,7 @@ struct Interaction {
 // md_general.f90
 void init_time_steps(TimeSteps& dt, double delta_t);
 void create_particle_group(ParticleGroup& g, const std::vector<std::string>& type_names, const Particles& atoms);
+void change_particle_group_N(ParticleGroup& group, int md_step, int change_ts1, int change_ts2, int change_frec, const ParticleGroup& init_group);
 void scale_velocities(Particles& a, const ParticleGroup& g, double s);
 void calculate_kinetic_energy(double& ke, const Particles& a, const ParticleGroup& g);
 void calculate_mass_center(double mc[3], const Particles& a, const ParticleGroup& g);
@@ -139,6 +140,9 @@ struct System {
     int all_moving = 1, xyz_moving = 1, z_moving = 1, all_atoms = 1;
     int zero_momentum_period = 1;
     bool invert_z_vel = false;
+    // md_simulation.f90:63-71: `change_group_num` entries, applied at the top of every step (:116-119)
+    struct GroupChange { int from, to, ts1, ts2, frec; };
+    std::vector<GroupChange> changes;
     double t_pos_vel = 0, t_nlists = 0, t_nlsearch = 0, t_nldistance = 0, t_forces = 0, t_energy = 0;
     // md_simulation.f90:138-186 for one md_step; integrator_name in {"nve","nvt","nvms"}.
     void step(int md_step, const std::string& integrator_name);

@@ -34,6 +34,8 @@ int oracle_set_roles(oracle_ctx* c, int am, int xyz, int z, int all) { GUARD(c->
 int oracle_add_nhc(oracle_ctx* c, int g, double T, int M, double q1) {
     GUARD(pfmds_host::NhcSpec s; s.group = g; s.temperature = T; s.M = M; s.q1 = q1; c->eng.add_nhc(s));
 }
+int oracle_add_group_change(oracle_ctx* c, int from, int to, int ts1, int ts2, int frec) { GUARD(c->eng.add_group_change(from, to, ts1, ts2, frec)); }
+int oracle_group_size(oracle_ctx* c, int g, int* n) { GUARD(*n = c->eng.group_size(g)); }
 int oracle_set_misc(oracle_ctx* c, int zmp, int inv) { GUARD(c->eng.set_misc(zmp, inv != 0)); }
 int oracle_add_interaction(oracle_ctx* c, const char* name, int np, const double* params, int nl_n, const int* gn, const int* maxn,
                            const double* rcut, const int* period) {

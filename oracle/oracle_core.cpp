@@ -32,6 +32,21 @@ void create_particle_group(ParticleGroup& g, const std::vector<std::string>& typ
     g.N = (int)g.indexes.size();
 }
 
+// :82-94  deposition: the target group exposes the first N of its indexes; N follows the source group's N up to
+// change_ts1, then grows by one atom at change_ts1 and every change_frec steps until change_ts2
+void change_particle_group_N(ParticleGroup& group, int md_step, int change_ts1, int change_ts2, int change_frec, const ParticleGroup& init_group) {
+    if (md_step <= change_ts1) {
+        group.N = init_group.N;
+        if (md_step == change_ts1) group.N = group.N + 1;
+    } else {
+        if (md_step < change_ts2) {
+            if (change_frec == 0) throw StopError("error: change_frec is zero (integer division by zero in mod)");
+            if ((md_step - change_ts1) % change_frec == 0) group.N = group.N + 1;
+        }
+    }
+    if (group.N > (int)group.indexes.size()) group.N = (int)group.indexes.size();
+}
+
 // :96-112
 void scale_velocities(Particles& a, const ParticleGroup& g, double s) {
 #pragma omp parallel for
@@ -437,6 +452,8 @@ void calculate_nose_hoover_chain_energy(NoseHooverChain& n) {
 
 // ---- md_simulation.f90:138-186, one md_step without the I/O ------------------------------------
 void System::step(int md_step, const std::string& integrator_name) {
+    for (const auto& ch : changes)  // :116-119
+        change_particle_group_N(groups.at((size_t)ch.to - 1), md_step, ch.ts1, ch.ts2, ch.frec, groups.at((size_t)ch.from - 1));
     double t = omp_get_wtime();
     check_positions(atoms, cell);
     if (invert_z_vel) invert_z_velocities(atoms, 0.8 * cell.box_size[2], 0.9 * cell.box_size[2]);

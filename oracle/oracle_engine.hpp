@@ -39,6 +39,11 @@ struct OracleEngine {
         set_nose_hoover_chain(c, n.temperature, n.q1, n.group, sys.groups.at((size_t)n.group - 1).N);
         sys.nhc.push_back(c);
     }
+    void add_group_change(int from, int to, int ts1, int ts2, int frec) {  // md_simulation.f90:63-71
+        if (from < 1 || to < 1 || from > (int)sys.groups.size() || to > (int)sys.groups.size()) throw StopError("error: group number out of range in a group change");
+        sys.changes.push_back(System::GroupChange{from, to, ts1, ts2, frec});
+    }
+    int group_size(int g) const { return sys.groups.at((size_t)g - 1).N; }
     void set_misc(int zmp, bool inv) { sys.zero_momentum_period = zmp; sys.invert_z_vel = inv; }
     void add_interaction(const pfmds_host::InteractionSpec& sp) {  // md_interactions.f90:59-136
         Interaction it;

@@ -49,6 +49,8 @@ long long group_size(pfmds_ctx* c, int g) {
         if (g < 1 || g > (int)c->group_count.size()) fail(PFMDS_ERR_INVALID, "error: group number " + std::to_string(g) + " is not defined");
         return c->group_count[(size_t)g - 1];
     }
+    group_of(c, g);
+    if (c->cur_n.size() == c->groups.size()) return c->cur_n[(size_t)g - 1];  // group%N (deposition changes it)
     return (long long)group_of(c, g).size();
 }
 
@@ -72,6 +74,7 @@ void check_device_error(pfmds_ctx* c) {
 
 // Slab mode: the masks came with pfmds_create_slab; validation works on group numbers and global sizes.
 void finalize_slab(pfmds_ctx* c) {
+    if (!c->changes.empty()) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: group changes (deposition) in slab decomposition mode");
     int period = -1;
     for (auto& it : c->inter) {
         if (it.kind != K_LJ && it.kind != K_LJ1G && it.kind != K_RJL)
@@ -243,7 +246,22 @@ void finalize(pfmds_ctx* c) {
     }
     CK(cudaMemcpyAsync(c->gmask, c->h_gmask.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, c->st));
     if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
-    c->first_overwrites = !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
+    // group%N starts at the full size (create_particle_group); change entries take over from the first step on
+    c->cur_n.resize(c->groups.size());
+    for (size_t g = 0; g < c->groups.size(); ++g) c->cur_n[g] = (int)c->groups[g].size();
+    c->d_grank.assign(c->groups.size(), nullptr);
+    c->zero_all = (int)group_of(c, c->all_atoms).size() == N;
+    for (auto& ch : c->changes) {
+        group_of(c, ch.from);
+        const auto& G = group_of(c, ch.to);
+        if (ch.to == c->all_atoms) c->zero_all = false;
+        if (c->d_grank[(size_t)ch.to - 1]) continue;
+        std::vector<int> rank((size_t)N, 0x7fffffff);
+        for (size_t r = 0; r < G.size(); ++r) rank[(size_t)G[r] - 1] = (int)r;
+        CK(cudaMalloc(&c->d_grank[(size_t)ch.to - 1], sizeof(int) * (size_t)N));
+        CK(cudaMemcpyAsync(c->d_grank[(size_t)ch.to - 1], rank.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, c->st));
+    }
+    c->first_overwrites = c->zero_all && c->changes.empty() && !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
     c->finalized = true;
@@ -261,6 +279,45 @@ struct PhaseTimer {
         c->t_phase[slot] += ms * 1e-3;
     }
 };
+
+// change_particle_group_N, md_general.f90:82-94: membership bit of group `bit` = (position in the group's index list < n)
+__global__ void k_group_resize(int N, const int* __restrict__ orig, const int* __restrict__ rank, uint32_t bit, int n, uint32_t* __restrict__ gmask) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t g = gmask[i];
+    gmask[i] = rank[orig[i]] < n ? (g | bit) : (g & ~bit);
+}
+// The `do i=1,change_group_num` loop at the top of every md step (md_simulation.f90:116-119).  Returns true when a group changed.
+bool apply_group_changes(pfmds_ctx* c, int step) {
+    if (c->changes.empty()) return false;
+    std::vector<int> before = c->cur_n;
+    for (const auto& ch : c->changes) {
+        int& n = c->cur_n[(size_t)ch.to - 1];
+        if (step <= ch.ts1) {
+            n = c->cur_n[(size_t)ch.from - 1];
+            if (step == ch.ts1) n = n + 1;
+        } else if (step < ch.ts2) {
+            if (ch.frec == 0) fail(PFMDS_ERR_INVALID, "error: change_frec is zero (integer division by zero in mod)");
+            if ((step - ch.ts1) % ch.frec == 0) n = n + 1;
+        }
+        const int cap = (int)c->groups[(size_t)ch.to - 1].size();
+        if (n > cap) n = cap;
+    }
+    bool changed = false;
+    for (size_t g = 0; g < c->cur_n.size(); ++g) {
+        if (c->cur_n[g] == before[g]) continue;
+        if (!changed) {
+            // velocity scalings still pending from the last thermostat step belong to the OLD membership
+            integ_flush_pending(c);
+            c->nhc_ke_valid = false;
+            c->energy_valid = false;
+        }
+        changed = true;
+        k_group_resize<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->orig, c->d_grank[g], 1u << g, c->cur_n[g], c->gmask);
+        c->launches += 1;
+    }
+    return changed;
+}
 
 // update_interactions_neighbour_lists, md_interactions.f90:138-178
 void update_lists(pfmds_ctx* c, int step) {
@@ -524,6 +581,20 @@ int pfmds_set_misc(pfmds_ctx* c, int zmp, int inv) {
     });
 }
 
+int pfmds_add_group_change(pfmds_ctx* c, int from, int to, int ts1, int ts2, int frec) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (c->finalized) fail(PFMDS_ERR_INVALID, "error: group changes must be defined before the first pfmds_advance");
+        if (from < 1 || to < 1) fail(PFMDS_ERR_INVALID, "error: group number out of range in a group change");
+        c->changes.push_back(pfmds_ctx::GroupChange{from, to, ts1, ts2, frec});
+    });
+}
+
+int pfmds_group_size(pfmds_ctx* c, int g, int* n) {
+    if (!c || !n) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] { *n = (int)group_size(c, g); });
+}
+
 int pfmds_add_interaction(pfmds_ctx* c, const char* name, int np, const double* p, int nl_n, const int* gn, const int* maxn, const double* rcut,
                           const int* period) {
     if (!c) return PFMDS_ERR_INVALID;
@@ -572,7 +643,8 @@ static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, boo
             for (auto& it : c->inter)
                 for (int j = 0; j < it.nl_n; ++j) rebuild |= (s % it.nl[j].period == 0) || !it.nl[j].built;
             const bool with_energy = energy_last && s == first + n - 1;
-            const bool graphable = c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && !rebuild &&
+            const bool regrouped = apply_group_changes(c, s);
+            const bool graphable = !regrouped && c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && !rebuild &&
                                    (s % c->zero_momentum_period != 0) && !with_energy;
             if (!graphable) {
                 do_step(c, s, kind, dt, s == first, with_energy);
@@ -1090,6 +1162,7 @@ int pfmds_destroy(pfmds_ctx* c) {
         cudaFree(it.aux); cudaFree(it.aux2); cudaFree(it.fpart); cudaFree(it.gnorm); cudaFree(it.tvec);
     }
     for (auto& t : c->nhc) cudaFree(t.state);
+    for (int* r : c->d_grank) cudaFree(r);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,
                     c->cid, c->posf, c->scan_tmp, c->part, c->red, c->energy, c->err};

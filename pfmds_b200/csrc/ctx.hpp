@@ -73,6 +73,12 @@ struct pfmds_ctx {
     int all_moving = 1, xyz_moving = 1, z_moving = 1, all_atoms = 1;
     int zero_momentum_period = 1;
     bool invert_z = false;
+    // deposition (change_particle_group_N, md_general.f90:82-94): group `to` exposes the first cur_n[to] atoms of its index list
+    struct GroupChange { int from, to, ts1, ts2, frec; };
+    std::vector<GroupChange> changes;
+    std::vector<int> cur_n;       // group%N of every group; differs from groups[g].size() only for the targets of change entries
+    std::vector<int*> d_grank;    // per group, targets only: device int[N] by FILE index = position in the group's index list (INT_MAX: not listed)
+    bool zero_all = true;         // the all_atoms group is every atom at every step: zero_forces is one memset
     std::vector<Inter> inter;
     std::vector<Nhc> nhc;
     // slab decomposition (slab.cu); null in single-GPU and ensemble runs

@@ -588,10 +588,17 @@ __global__ void __launch_bounds__(FT) k_cos_indirect(int N, const double4* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// zero_forces touches the all_atoms group only (md_integrators.f90:147-163): forces of atoms outside it keep accumulating
+__global__ void k_zero_group(int N, double4* __restrict__ frc, const uint32_t* __restrict__ gmask, uint32_t bit) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && (gmask[i] & bit)) frc[i] = make_double4(0., 0., 0., 0.);
+}
 void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
     if (c->first_overwrites && c->N >= SMALL_N) return;  // the first force kernel stores instead of accumulating
     KTimer kt(c, KS_ZERO_FORCES);
-    CK(cudaMemsetAsync(c->frc, 0, sizeof(double4) * (size_t)c->N, c->st));
+    if (c->zero_all) { CK(cudaMemsetAsync(c->frc, 0, sizeof(double4) * (size_t)c->N, c->st)); return; }
+    k_zero_group<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->frc, c->gmask, 1u << (c->all_atoms - 1));
+    c->launches += 1;
 }
 
 static CosP cosp_of(const Inter& it) {

@@ -42,6 +42,8 @@ _SIGS = {
     "set_roles": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int],
     "add_nhc": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double],
     "set_misc": [C.c_void_p, C.c_int, C.c_int],
+    "add_group_change": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+    "group_size": [C.c_void_p, C.c_int, _ip],
     "add_interaction": [C.c_void_p, C.c_char_p, C.c_int, _dp, C.c_int, _ip, _ip, _dp, _ip],
     "advance": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int],
     "advance_with_energy": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int],
@@ -130,6 +132,15 @@ class Engine:
 
     def set_misc(self, zero_momentum_period, invert_z_vel):
         self._call("set_misc", self._ctx, int(zero_momentum_period), int(bool(invert_z_vel)))
+
+    def add_group_change(self, group_from, group_to, ts1, ts2, frec):
+        """One change_group_num entry (deposition): md_simulation.f90:63-71, md_general.f90:82-94."""
+        self._call("add_group_change", self._ctx, int(group_from), int(group_to), int(ts1), int(ts2), int(frec))
+
+    def group_size(self, g):
+        n = C.c_int()
+        self._call("group_size", self._ctx, int(g), C.byref(n))
+        return n.value
 
     def add_interaction(self, name, params, lists):
         p = np.ascontiguousarray(params, np.float64)
@@ -278,6 +289,8 @@ def configure(case, device=0, lib_path=LIB_PATH, prefix="pfmds_"):
     for g, t, m, q in case["nhc"]:
         e.add_nhc(g, t, m, q)
     e.set_misc(case["zero_momentum_period"], case["invert_z_vel"])
+    for ch in case.get("changes", []):
+        e.add_group_change(*ch)
     for it in case["interactions"]:
         e.add_interaction(it["name"], it["params"], it["lists"])
     return e

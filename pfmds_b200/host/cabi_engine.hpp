@@ -22,6 +22,8 @@ public:
     void set_group(int g, const std::vector<int>& idx1) { ck(pfmds_set_group(ctx_, g, (int)idx1.size(), idx1.data())); }
     void set_roles(int am, int xyz, int z, int all) { ck(pfmds_set_roles(ctx_, am, xyz, z, all)); }
     void add_nhc(const NhcSpec& n) { ck(pfmds_add_nhc(ctx_, n.group, n.temperature, n.M, n.q1)); ++n_nhc_; }
+    void add_group_change(int from, int to, int ts1, int ts2, int frec) { ck(pfmds_add_group_change(ctx_, from, to, ts1, ts2, frec)); }
+    int group_size(int g) { int n = 0; ck(pfmds_group_size(ctx_, g, &n)); return n; }
     void set_misc(int zmp, bool inv) { ck(pfmds_set_misc(ctx_, zmp, inv ? 1 : 0)); }
     void add_interaction(const InteractionSpec& s) {
         std::vector<int> gn, mx, pe;

@@ -7,7 +7,7 @@
 //
 // Engine concept (all methods throw std::runtime_error on failure, with the reference's message):
 //   create(n,pos,vel,mass,box) set_group(g,idx1) set_roles(am,xyz,z,all) add_interaction(spec)
-//   add_nhc(spec) set_misc(zero_momentum_period,invert_z) advance(kind,dt,first_md_step,n_steps,energy_after_last)
+//   add_nhc(spec) set_misc(zero_momentum_period,invert_z) add_group_change(from,to,ts1,ts2,frec) group_size(g) advance(kind,dt,first_md_step,n_steps,energy_after_last)
 //   energies(e_inter,ke,temp,e_nhc) diagnostics(fs,mc,mcv,vmax,nl_load) download(pos,vel,frc)
 //   timers(t[6])   -> seconds: pos_vel, nlists, nlsearch, nldistance, forces, energy
 #pragma once
@@ -156,8 +156,6 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
         P(A(c.l1, 32, 128) + I(c.from, 12) + I(c.to, 12));
         P(A(c.l2, 32, 128) + I(c.ts1, 12) + I(c.ts2, 12) + I(c.frec, 12));
     }
-    if (s.change_group_num > 0)
-        throw std::runtime_error("error: change_group_num>0 (atom deposition) is not part of the accelerated hot path yet");
     P(A(s.l_invert, 32, 128) + L(s.invert_z_vel, 8));
     P(A(s.l_integrators, 32, 128) + I(s.integrators_num, 12));
     P(Apad(s.integrators_header, 128));
@@ -188,7 +186,14 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
     eng.set_roles(s.all_moving, s.xyz_moving, s.z_moving, s.all_atoms);
     for (auto& n : s.nhc) { check_group(n.group, "nhc"); eng.add_nhc(n); }
     eng.set_misc(s.zero_momentum_period, s.invert_z_vel);
+    for (auto& c : s.changes) { check_group(c.from, "group_change_from"); check_group(c.to, "group_change_to"); eng.add_group_change(c.from, c.to, c.ts1, c.ts2, c.frec); }
     for (auto& it : s.interactions) eng.add_interaction(it);
+    // group%N of a group right now (deposition: the first N entries of its index list, md_general.f90:82-94)
+    auto current = [&](int g) {
+        std::vector<int> v = groups[(size_t)g - 1];
+        if (!s.changes.empty()) v.resize((size_t)eng.group_size(g));
+        return v;
+    };
 
     const size_t n_inter = s.interactions.size(), n_nhc = s.nhc.size();
     std::FILE* logf = std::fopen((trim(output_prefix) + trim(s.logfilename)).c_str(), "w");
@@ -292,9 +297,9 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
         const bool traj = md_step % s.period_traj == 0;
         if (snap || traj) eng.download(pos.data(), vel.data(), nullptr);
         if (snap)  // :233-236
-            write_particle_group(trim(output_prefix) + "snapshot_" + I(md_step, 0, 6) + ".xyz", groups[s.all_atoms - 1], pos.data(), vel.data(), xyz);
+            write_particle_group(trim(output_prefix) + "snapshot_" + I(md_step, 0, 6) + ".xyz", current(s.all_atoms), pos.data(), vel.data(), xyz);
         if (traj)  // :238-241
-            write_particle_group_append(trim(output_prefix) + "traj_" + I(s.traj_group, 0, 2) + ".xyz", groups[s.traj_group - 1], pos.data(),
+            write_particle_group_append(trim(output_prefix) + "traj_" + I(s.traj_group, 0, 2) + ".xyz", current(s.traj_group), pos.data(),
                                         vel.data(), xyz, md_step);
         ++md_step;
     }
@@ -327,7 +332,7 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
     std::fprintf(logf, "%s", fin.c_str());
     if (md_step != 0) {
         eng.download(pos.data(), vel.data(), nullptr);
-        write_particle_group(trim(output_prefix) + "final_" + trim(s.init_xyz_filename), groups[s.all_atoms - 1], pos.data(), vel.data(), xyz);
+        write_particle_group(trim(output_prefix) + "final_" + trim(s.init_xyz_filename), current(s.all_atoms), pos.data(), vel.data(), xyz);
     }
     std::fprintf(logf, "\n");
     std::fclose(logf);

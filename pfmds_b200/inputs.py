@@ -7,6 +7,7 @@ A *case* is a plain dict, consumed by `pfmds_b200.engine.configure` (C-ABI calls
   box(3) pos(N,3) vel(N,3) mass(N) names[N]  groups[[type names per group row]]  roles{...}
   integrators[(name,dt,len,snap,log)] ms_de nhc[(group,T,M,q1)] zero_momentum_period invert_z_vel
   interactions[{name, params[...], lists[(g1,g2,max,r_cut,period)]}]
+  changes[(group_from, group_to, ts1, ts2, frec)]   optional: deposition entries (md_simulation.f90:63-71)
 """
 from __future__ import annotations
 
@@ -88,6 +89,37 @@ def lj_fluid(n_side=100, spacing=4.0, seed=7, temperature=100.0, steps=1000, per
         integrators=[("nve", 0.5, steps, 10 ** 9, 10 ** 9)], ms_de=1e-8, nhc=[], zero_momentum_period=10 ** 9, invert_z_vel=False,
         initial_temperature=temperature,
         interactions=[dict(name="lj1g", file="parameters_LJ_A-A.txt", params=[0.0103, 3.405, 6.0, 7.0], lists=[(1, 1, cap, 7.5, period)])],
+    )
+
+
+def lj_deposition(n_side=6, n_layers=3, n_deposit=8, spacing=3.8, seed=11, temperature=80.0, steps=60, period=5, ts1=3, ts2=40, frec=4,
+                  thermostat=True):
+    """Row (f) of SURVEY.md 8: atom deposition through `change_group_num`.  A Lennard-Jones substrate (type S, n_side^2*n_layers
+    atoms) with n_deposit atoms of type D parked above it; the moving / interacting / thermostatted group 3 = [S, D] starts
+    with the size of the substrate group 2 and takes one D atom at step ts1 and then every frec steps (md_general.f90:82-94).
+    all_atoms is the growing group too, so zero_forces, the momentum removal and the writers follow group%N."""
+    rng = np.random.default_rng(seed)
+    g = np.arange(n_side) * spacing
+    lay = np.stack(np.meshgrid(g, g, np.arange(n_layers) * spacing, indexing="ij"), -1).reshape(-1, 3) + np.array([1.0, 1.0, 4.0])
+    lay = lay + rng.uniform(-0.1, 0.1, lay.shape)
+    box = np.array([n_side * spacing, n_side * spacing, 60.0])
+    top = 4.0 + (n_layers - 1) * spacing
+    k = np.arange(n_deposit)
+    dep = np.stack([(1.7 + 2.9 * k) % box[0], (2.3 + 5.3 * k) % box[1], top + 4.5 + 0.9 * k], -1)
+    pos = np.concatenate([lay, dep])
+    ns = len(lay)
+    names = ["S"] * ns + ["D"] * n_deposit
+    mass = np.array([39.948] * ns + [39.948] * n_deposit)
+    vel = maxwell(rng, mass, temperature, np.array([True] * ns + [False] * n_deposit))
+    vel[ns:] = np.array([0.0, 0.0, -0.004])  # the parked atoms fly towards the surface once they are released
+    nhc = [(3, temperature, 3, 3 * ns * KB * temperature * 100.0 ** 2)] if thermostat else []
+    return dict(
+        title="lj_deposition", box=box, pos=pos, vel=vel, mass=mass, names=names,
+        groups=[["S", "D"], ["S", "#"], ["S", "D"], ["#", "#"]],
+        roles=dict(all_moving=3, xyz_moving=3, z_moving=4, all_atoms=3, traj_group=3, period_traj=20),
+        integrators=[("nvt" if thermostat else "nve", 1.0, steps, 20, 10)], ms_de=1e-8, nhc=nhc, zero_momentum_period=7, invert_z_vel=False,
+        initial_temperature=temperature, changes=[(2, 3, ts1, ts2, frec)],
+        interactions=[dict(name="lj1g", file="parameters_LJ_Ar.txt", params=[0.0103, 3.405, 6.0, 7.0], lists=[(3, 3, 80, 7.5, period)])],
     )
 
 
@@ -249,7 +281,10 @@ def write_case(directory, case, settings="md_run_settings.txt", xyz="init.xyz", 
     L.append("all_atoms_group_num: %d" % r["all_atoms"])
     L.append("traj_group_num: %d" % r["traj_group"])
     L.append("period_traj: %d" % r["period_traj"])
-    L.append("change_group_num: 0")
+    L.append("change_group_num: %d" % len(case.get("changes", [])))
+    for fr, to, ts1, ts2, frec in case.get("changes", []):
+        L.append("group_change_from_to: %d %d" % (fr, to))
+        L.append("change_ts1_ts2_freq: %d %d %d" % (ts1, ts2, frec))
     L.append("invert_z_vel: %s" % ("T" if case["invert_z_vel"] else "F"))
     L.append("integrators_num: %d" % len(case["integrators"]))
     L.append(" name    dt         len     snap     log")
