@@ -45,6 +45,7 @@ struct LJCParams { double eps, sig, delt, R1, R2; bool simplified; std::vector<d
 struct MorseCParams { double d, r, a, delt, R1, R2; bool simplified; std::vector<double> gr_norm; };
 struct RJLParams { double A0, xi, p, q, r0, R1, R2; };
 struct TBParams { double d, s, b, r0, delt, a0, c0, d0, R1, R2, c02, d02; };
+struct REBOscParams { double A, Q, alpha, B[3], beta[3], T, g[6], R1, R2; };  // REBOsolidcarbon.f90:6-8
 
 // MOLECULAR_DYNAMICS/md_interactions.f90:15-34
 struct Interaction {
@@ -53,7 +54,7 @@ struct Interaction {
     std::vector<NeighbourList> nl;
     double energy = 0;
     std::string interaction_name, parameters_file;
-    LJParams lj{}; LJ1gParams lj1g{}; LJCParams ljc{}; MorseCParams morsec{}; RJLParams rjl{}; TBParams tb{};
+    LJParams lj{}; LJ1gParams lj1g{}; LJCParams ljc{}; MorseCParams morsec{}; RJLParams rjl{}; TBParams tb{}; REBOscParams rebosc{};
     bool numerical_force = false;
 };
 
@@ -118,15 +119,17 @@ void RJL_forces(Particles& a, const NeighbourList& nl, const RJLParams& p);
 void TB_finish_parameters(TBParams& p);
 void TB_energy(double& e, const NeighbourList& nl, const TBParams& p);
 void TB_forces(Particles& a, const NeighbourList& nl, const TBParams& p);
+void REBOsc_energy(double& e, const NeighbourList& nl, const REBOscParams& p);
 
 // md_interactions.f90
-int nl_n_for(const std::string& name);  // lj 2, lj1g 1, ljc 3, morsec 3, tb 1, rjl 1; -1 unknown
+int nl_n_for(const std::string& name);  // lj 2, lj1g 1, ljc 3, morsec 3, tb 1, rebosc 1, rjl 1; -1 unknown
 void setup_interaction_lists(Interaction& it, const std::vector<ParticleGroup>& groups);
 void allocate_graphene_norm(std::vector<Interaction>& its);
 void update_interactions_neighbour_lists(int md_step, std::vector<Interaction>& its, const Particles& a,
                                          const std::vector<ParticleGroup>& groups, const SimulationCell& cell,
                                          double& t_search, double& t_distance);
 void calculate_forces(Particles& a, std::vector<Interaction>& its);
+void calculate_forces_numerically(Particles& a, std::vector<Interaction>& its);
 void calculate_potential_energies(std::vector<Interaction>& its);
 
 // The whole simulation state + one md step (body of the loop in md_simulation.f90:114-243 without I/O).

@@ -475,6 +475,7 @@ void System::step(int md_step, const std::string& integrator_name) {
     if (md_step % zero_momentum_period == 0) zero_momentum(atoms, groups[all_atoms - 1]);
     zero_forces(atoms, groups[all_atoms - 1]);
     calculate_forces(atoms, interactions);
+    calculate_forces_numerically(atoms, interactions);  // :165
     t_forces += omp_get_wtime() - t;
 
     t = omp_get_wtime();

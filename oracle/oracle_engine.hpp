@@ -58,7 +58,12 @@ struct OracleEngine {
         else if (sp.name == "morsec") it.morsec = MorseCParams{p.at(0), p.at(1), p.at(2), p.at(3), p.at(4), p.at(5), p.at(6) != 0., {}};
         else if (sp.name == "tb") { it.tb = TBParams{p.at(0), p.at(1), p.at(2), p.at(3), p.at(4), p.at(5), p.at(6), p.at(7), p.at(8), p.at(9), 0, 0}; TB_finish_parameters(it.tb); }
         else if (sp.name == "rjl") it.rjl = RJLParams{p.at(0), p.at(1), p.at(2), p.at(3), p.at(4), p.at(5), p.at(6)};
-        it.neib_order = (sp.name == "tb" || sp.name == "rjl") ? 2 : 0;
+        else if (sp.name == "rebosc") {  // REBOsolidcarbon.f90:12-25: A Q alpha / B(3) / beta(3) / T / g(6) / R1 R2
+            it.rebosc = REBOscParams{p.at(0), p.at(1), p.at(2), {p.at(3), p.at(4), p.at(5)}, {p.at(6), p.at(7), p.at(8)}, p.at(9),
+                                     {p.at(10), p.at(11), p.at(12), p.at(13), p.at(14), p.at(15)}, p.at(16), p.at(17)};
+            it.numerical_force = true;  // md_interactions.f90:103
+        }
+        it.neib_order = (sp.name == "tb" || sp.name == "rjl") ? 2 : (sp.name == "rebosc" ? 3 : 0);
         it.nl.resize((size_t)it.nl_n);
         for (int j = 0; j < it.nl_n; ++j) {
             it.group_nums.push_back(sp.lists[j].g1);

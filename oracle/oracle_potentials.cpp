@@ -620,6 +620,7 @@ int nl_n_for(const std::string& name) {
     if (name == "morsec") return 3;
     if (name == "tb") return 1;
     if (name == "rjl") return 1;
+    if (name == "rebosc") return 1;
     return -1;
 }
 // :123-132  (the caller has filled group_nums and nl[j].{neighb_num_max,r_cut,update_period})
@@ -688,6 +689,7 @@ void calculate_potential_energies(std::vector<Interaction>& its) {
         else if (nm == "morsec") MorseC_energy(it.energy, it.nl[0], it.morsec);
         else if (nm == "tb") TB_energy(it.energy, it.nl[0], it.tb);
         else if (nm == "rjl") RJL_energy(it.energy, it.nl[0], it.rjl);
+        else if (nm == "rebosc") REBOsc_energy(it.energy, it.nl[0], it.rebosc);
     }
 }
 

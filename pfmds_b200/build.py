@@ -15,7 +15,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", CXX] + os.environ.get("PFMDS_NVCC_EXTRA", "").split()
-SOURCES = ["nl.cu", "forces.cu", "integrate.cu", "capi.cu", "slab.cu"]
+SOURCES = ["nl.cu", "forces.cu", "rebosc.cu", "integrate.cu", "capi.cu", "slab.cu"]
 LIB = os.path.join(CSRC, "libpfmds_b200.so")
 EXE = os.path.join(HOST, "run_md_simulation")
 

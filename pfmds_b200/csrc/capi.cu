@@ -33,6 +33,7 @@ int kind_of(const std::string& n) {
     if (n == "morsec") return K_MORSEC;
     if (n == "tb") return K_TB;
     if (n == "rjl") return K_RJL;
+    if (n == "rebosc") return K_REBOSC;
     return -1;
 }
 int nl_n_of(int kind) { return kind == K_LJ ? 2 : (kind == K_LJC || kind == K_MORSEC) ? 3 : 1; }
@@ -78,7 +79,7 @@ void finalize_slab(pfmds_ctx* c) {
     int period = -1;
     for (auto& it : c->inter) {
         if (it.kind != K_LJ && it.kind != K_LJ1G && it.kind != K_RJL)
-            fail(PFMDS_ERR_UNSUPPORTED, "unsupported: slab decomposition handles lj, lj1g and rjl (" + it.name + " needs ghost bond orders / normals)");
+            fail(PFMDS_ERR_UNSUPPORTED, "unsupported: slab decomposition handles lj, lj1g and rjl (" + it.name + " needs ghost bond orders / normals / second-shell rows)");
         NList& a = it.nl[0];
         for (int j = 0; j < it.nl_n; ++j) { group_size(c, it.nl[j].g1); group_size(c, it.nl[j].g2); }
         if ((it.kind == K_LJ1G || it.kind == K_RJL) && a.g1 != a.g2) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: " + it.name + " needs group1 == group2");
@@ -145,12 +146,12 @@ void finalize(pfmds_ctx* c) {
     auto monotone = [&](int g) { const auto& v = group_of(c, g); return std::is_sorted(v.begin(), v.end()); };
     int first_tb = -1;
     for (size_t k = 0; k < c->inter.size(); ++k)
-        if (c->inter[k].kind == K_TB) { first_tb = (int)k; break; }
+        if (c->inter[k].kind == K_TB || c->inter[k].kind == K_REBOSC) { first_tb = (int)k; break; }  // md_interactions.f90:157-162
     for (size_t k = 0; k < c->inter.size(); ++k) {
         Inter& it = c->inter[k];
         for (int j = 0; j < it.nl_n; ++j) { group_of(c, it.nl[j].g1); group_of(c, it.nl[j].g2); }
         NList& a = it.nl[0];
-        if (it.kind == K_LJ1G || it.kind == K_TB || it.kind == K_RJL) {
+        if (it.kind == K_LJ1G || it.kind == K_TB || it.kind == K_RJL || it.kind == K_REBOSC) {
             // the reference indexes group-1 rows with group-2 local numbers in these potentials
             // (LennardJones_1g.f90:83, TersoffBrenner.f90:56-59, RosatoGuillopeLegrand.f90:88)
             if (group_of(c, a.g1) != group_of(c, a.g2)) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: " + it.name + " needs group1 == group2");
@@ -189,7 +190,7 @@ void finalize(pfmds_ctx* c) {
             case K_RJL: R1 = it.rjl.R1; R2 = it.rjl.R2; break;
             default: break;
             }
-            int np = it.kind == K_TB ? 0 : (it.kind == K_LJ1G || it.kind == K_RJL ? 1 : 2);
+            int np = (it.kind == K_TB || it.kind == K_REBOSC) ? 0 : (it.kind == K_LJ1G || it.kind == K_RJL ? 1 : 2);
             for (int j = 0; j < np; ++j) { it.nl[j].partition = true; it.nl[j].part_r1sq = R1 * R1; it.nl[j].part_r2sq = R2 * R2; }
         }
         for (int j = 0; j < it.nl_n; ++j) {
@@ -377,7 +378,10 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bo
         PhaseTimer t(c, 4);
         if (step % c->zero_momentum_period == 0) integ_zero_momentum(c);
         forces_zero(c);
-        for (size_t k = 0; k < c->inter.size(); ++k) forces_interaction(c, (int)k, with_energy);
+        for (size_t k = 0; k < c->inter.size(); ++k)   // calculate_forces: the analytic interactions in file order
+            if (c->inter[k].kind != K_REBOSC) forces_interaction(c, (int)k, with_energy);
+        for (size_t k = 0; k < c->inter.size(); ++k)   // calculate_forces_numerically comes after all of them (md_simulation.f90:164-165)
+            if (c->inter[k].kind == K_REBOSC) forces_interaction(c, (int)k, with_energy);
         if (c->slab) slab_step_done(c);
         c->energy_valid = with_energy;
     }
@@ -619,6 +623,10 @@ int pfmds_add_interaction(pfmds_ctx* c, const char* name, int np, const double* 
         case K_MORSEC: need(7); it.mor = MORp{p[0], p[1], p[2], p[3], p[4], p[5], p[6] != 0.}; break;
         case K_TB: need(10); it.tb = TBp{p[0], p[1], p[2], p[3], p[4], p[5], p[6] * p[6], p[7] * p[7], p[8], p[9]}; break;  // TersoffBrenner.f90:19-20
         case K_RJL: need(7); it.rjl = RJLp{p[0], p[1], p[2], p[3], p[4], p[5], p[6]}; break;
+        case K_REBOSC:  // REBOsolidcarbon.f90:12-25
+            need(18);
+            it.reb = REBp{p[0], p[1], p[2], {p[3], p[4], p[5]}, {p[6], p[7], p[8]}, p[9], {p[10], p[11], p[12], p[13], p[14], p[15]}, p[16], p[17]};
+            break;
         }
         for (int j = 0; j < nl_n; ++j) {
             it.nl[j].g1 = gn[2 * j]; it.nl[j].g2 = gn[2 * j + 1]; it.nl[j].maxn = maxn[j]; it.nl[j].rcut = rcut[j]; it.nl[j].period = period[j];

@@ -13,8 +13,21 @@
 // slot indices, only int32 indices are stored and distances are recomputed in registers every
 // step (the reference caches dr(3,max,N) and |dr| instead: md_general.f90:30-35).
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#else
+// Host build of the device code, used only by the CPU emulation tests (tests/*_host.cpp run a kernel's per-thread body in a
+// serial loop to check its logic without a GPU).  The product is always compiled by nvcc.
+#include <math.h>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+struct double4 { double x, y, z, w; };
+static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
+static inline int atomicCAS(int* a, int cmp, int val) { int old = *a; if (old == cmp) *a = val; return old; }
+#endif
 
 #include "mathx.cuh"
 
@@ -27,7 +40,7 @@
 #define PFMDS_KB (1.3806488 / 1.6021765654 * 1.0e-4)
 #define PFMDS_PI 3.14159265358979
 
-enum { K_LJ = 0, K_LJ1G = 1, K_LJC = 2, K_MORSEC = 3, K_TB = 4, K_RJL = 5 };
+enum { K_LJ = 0, K_LJ1G = 1, K_LJC = 2, K_MORSEC = 3, K_TB = 4, K_RJL = 5, K_REBOSC = 6 };
 
 struct BoxD { double L[3]; double h[3]; };
 
@@ -59,6 +72,7 @@ __device__ __forceinline__ double fcut_only(double r, double R1, double R2) {
     mx::sincos_0pi(PFMDS_PI * (r - R1) / (R2 - R1), s, c);
     return (1.0 + c) / 2;
 }
+#ifdef __CUDACC__
 // One 256-bit load per 32-byte record (sm_100a LDG.E.256): a gather of 32 records costs the L1 one
 // request instead of the two LDG.128 the compiler emits for a double4.
 __device__ __forceinline__ double4 ld256_nc(const double4* p) {  // read-only data
@@ -87,6 +101,8 @@ __device__ __forceinline__ double block_sum(double v) {
     return v;
 }
 
+#endif  // __CUDACC__
+
 // parameters of one interaction, passed by value to the kernels
 struct LJp { double eps, sig, R1, R2; };
 struct LJ1Gp { double R1, R2, c6, c12, c6t6, c12t12; };
@@ -94,6 +110,7 @@ struct LJCp { double eps, sig, delt, R1, R2; int simplified; };          // ljc
 struct MORp { double d, r, a, delt, R1, R2; int simplified; };           // morsec
 struct TBp { double d, s, b, r0, delt, a0, c02, d02, R1, R2; };
 struct RJLp { double A0, xi, p, q, r0, R1, R2; };
+struct REBp { double A, Q, alpha, B[3], beta[3], T, g[6], R1, R2; };  // rebosc, REBOsolidcarbon.f90:6-8
 
 #define NHC_MAXF 4
 struct NhcPack { int n; uint32_t bit[NHC_MAXF]; double* state[NHC_MAXF]; int M[NHC_MAXF]; int L[NHC_MAXF]; double T[NHC_MAXF]; };
@@ -109,6 +126,7 @@ struct SlabDev {
     const int* wait_a; const int* wait_b; int wait_seq;   // 0: nothing to wait for
     int* err;
 };
+#ifdef __CUDACC__
 __device__ __forceinline__ void slab_wait(const SlabDev& S) {
     if (S.wait_seq > 0) {
         if (threadIdx.x == 0) {
@@ -143,5 +161,6 @@ __device__ __forceinline__ void slab_signal(const SlabDev& S, bool pushed) {
         }
     }
 }
+#endif  // __CUDACC__
 
 struct ListView { const int* nlist; const int* nnum; size_t stride; };

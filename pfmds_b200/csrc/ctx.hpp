@@ -28,7 +28,7 @@ struct Inter {
     std::string name;
     int nl_n = 0;
     NList nl[3];
-    LJp lj{}; LJ1Gp lj1g{}; LJCp ljc{}; MORp mor{}; TBp tb{}; RJLp rjl{};
+    LJp lj{}; LJ1Gp lj1g{}; LJCp ljc{}; MORp mor{}; TBp tb{}; RJLp rjl{}; REBp reb{};
     double* aux = nullptr;    // tb: bond orders B, ELL [maxn][stride]  (rjl keeps 1/Eb in pos[].w)
     double* aux2 = nullptr;   // tb: B^(1/delt+1)
     double4* fpart = nullptr; // tb: per-(slot, atom) force contributions, summed per atom in slot order
@@ -160,6 +160,10 @@ void forces_zero(pfmds_ctx* c);
 void forces_interaction(pfmds_ctx* c, int k, bool with_energy);
 void normals_interaction(pfmds_ctx* c, int k);
 void energy_interaction(pfmds_ctx* c, int k);  // result in c->energy[k]
+
+// ---- rebosc.cu ----
+void rebosc_forces(pfmds_ctx* c, Inter& it);          // numerical forces, md_interactions.f90:273-311
+int rebosc_energy_partials(pfmds_ctx* c, Inter& it);  // REBOsc_energy block partials into c->part; returns their number
 
 // ---- integrate.cu ----
 void integ_check_positions(pfmds_ctx* c);

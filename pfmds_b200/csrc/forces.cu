@@ -676,6 +676,9 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     }
         c->launches += 2;
         break;
+    case K_REBOSC:  // no analytic force in the reference: central differences of the energy (rebosc.cu)
+        rebosc_forces(c, it);
+        break;
     case K_TB:
     {
         dim3 grid(nb, it.nl[0].maxn);
@@ -733,6 +736,7 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
         else k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part, SlabDev{});
         break;
     }
+    case K_REBOSC: nparts = rebosc_energy_partials(c, it); c->launches -= 1; break;
     case K_TB: {
         dim3 grid(nb, it.nl[0].maxn);
         k_tb_bond<<<grid, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2);

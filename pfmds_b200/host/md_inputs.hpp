@@ -86,7 +86,7 @@ inline int nl_n_for(const std::string& name) {
 }
 
 // read_*_parameters: LennardJones.f90:12-21, LennardJones_1g.f90:13-26, LennardJonesCosine.f90:14-24,
-// MorseCosine.f90:14-24, TersoffBrenner.f90:13-22, RosatoGuillopeLegrand.f90:12-21
+// MorseCosine.f90:14-24, TersoffBrenner.f90:13-22, RosatoGuillopeLegrand.f90:12-21, REBOsolidcarbon.f90:12-25
 inline std::vector<double> read_parameters(const std::string& name, const std::string& path) {
     fio::ListReader r(path);
     std::vector<double> p;
@@ -96,6 +96,7 @@ inline std::vector<double> read_parameters(const std::string& name, const std::s
     else if (name == "morsec") { reals(4); reals(2); p.push_back(fio::to_logical(r.record(1)[0]) ? 1. : 0.); }
     else if (name == "tb") { reals(8); reals(2); }
     else if (name == "rjl") { reals(5); reals(2); }
+    else if (name == "rebosc") { reals(3); reals(3); reals(3); reals(1); reals(6); reals(2); }  // REBOsolidcarbon.f90:12-25
     else throw std::runtime_error("error: unknown interaction name " + name);
     return p;
 }
@@ -161,7 +162,6 @@ inline Settings read_settings(const std::string& input_path, const std::string& 
         it.name = t[0].substr(0, 32); it.parameters_file = t[1].substr(0, 32);
         it.nl_n = nl_n_for(it.name);
         if (it.nl_n < 0) throw std::runtime_error("error: unknown interaction name " + it.name);
-        if (it.name == "rebosc") throw std::runtime_error("error: interaction 'rebosc' (numerical forces) is outside the accelerated hot path");
         it.params = read_parameters(it.name, input_path + it.parameters_file);
         for (int j = 0; j < it.nl_n; ++j) {
             auto u = r.record(5);

@@ -24,6 +24,11 @@ RJL_CU = [0.0855, 1.224, 10.960, 2.278, 2.556, 5.5, 6.0]           # Cleri-Rosat
 TB_BRENNER_I = [6.325, 1.29, 1.5, 1.315, 0.80469, 0.011304, 19.0, 2.5, 1.7, 2.0]  # d s b r0 delt a0 c0 d0 / R1 R2
 LJC_C_CU = [0.02, 3.0, 2.0, 6.0, 7.0, 0.0]                         # eps sig delt / R1 R2 / simplified
 MORSEC_C_CU = [0.03, 3.2, 1.2, 2.0, 6.0, 7.0, 0.0]                 # d r a delt / R1 R2 / simplified
+# rebosc: A Q alpha / B(3) / beta(3) / T / g(6) / R1 R2 (REBOsolidcarbon.f90:12-25).  Pair terms: Brenner 2002 C-C; g: builder-chosen
+# quintic through the knots of Brenner's G_C(cos) (-1, -2/3, -1/2, -1/3, 1) and G(0)=0.3
+REBOSC_C = [10953.544162170, 0.3134602960833, 4.7465390606595, 12388.79197798, 17.56740646509, 30.71493208065,
+            4.7204523127, 1.4332132499, 1.3826912506, -0.004048375,
+            0.3, 1.00559171667, 1.751674625, 2.24048133333, 1.943325375, 0.75892695, 1.7, 2.0]
 
 
 def maxwell(rng, mass, temperature, moving=None):
@@ -148,7 +153,7 @@ def cu_fcc(ncell=63, a=3.615, seed=2, temperature=300.0, steps=1000, dt=2.0, per
 
 
 def graphene_on_cu(gr_cells=(27, 27), cu_cells=(26, 26), n_layers=6, n_fixed=2, lz=60.0, seed=3, temperature=300.0, interface="ljc",
-                   steps=(1000, 1000), dt=1.0, period=10, jitter=0.02, simplified=False, rep=(1, 1)):
+                   steps=(1000, 1000), dt=1.0, period=10, jitter=0.02, simplified=False, rep=(1, 1), carbon="tb"):
     """C3: graphene on Cu(111), rectangular moire cell: tb (C) + ljc|morsec (C-Cu) + rjl (Cu), nvt then nvms.
     File order C, CU, CU_fixed keeps every multi-type group index-monotone."""
     rng = np.random.default_rng(seed)
@@ -207,10 +212,40 @@ def graphene_on_cu(gr_cells=(27, 27), cu_cells=(26, 26), n_layers=6, n_fixed=2, 
         nhc=[(3, temperature, 3, 3 * n_move * KB * temperature * 100.0 ** 2)], zero_momentum_period=10 ** 9, invert_z_vel=False,
         initial_temperature=temperature,
         interactions=[
-            dict(name="tb", file="parameters_TB_C.txt", params=list(TB_BRENNER_I), lists=[(1, 1, 12, 2.6, period)]),
+            dict(name="tb", file="parameters_TB_C.txt", params=list(TB_BRENNER_I), lists=[(1, 1, 12, 2.6, period)]) if carbon == "tb" else
+            dict(name="rebosc", file="parameters_REBOsc_C.txt", params=list(REBOSC_C), lists=[(1, 1, 12, 2.6, period)]),
             inter,
             dict(name="rjl", file="parameters_RJL_Cu.txt", params=list(RJL_CU), lists=[(2, 2, 100, 6.5, period)]),
         ],
+    )
+
+
+def graphene_rebosc(cells=(4, 3), lz=20.0, seed=5, temperature=300.0, steps=50, dt=0.5, period=5, jitter=0.04, with_tb=False):
+    """Row (f) of SURVEY.md 8: a free-standing graphene sheet under `rebosc` (energy only in the reference; forces by central
+    differences on truncated lists, md_interactions.f90:273-311).  Rectangular cell 2.46 x 4.2609 A, 4 C per cell."""
+    rng = np.random.default_rng(seed)
+    gx, gy = 2.46, 2.46 * np.sqrt(3.0)
+    ii, jj = np.meshgrid(np.arange(cells[0]), np.arange(cells[1]), indexing="ij")
+    base = np.stack([ii.ravel() * gx, jj.ravel() * gy], -1)
+    cs = []
+    for fx, fy in ((0.0, 0.0), (0.0, 1.0 / 3.0), (0.5, 0.5), (0.5, 5.0 / 6.0)):
+        xy = base + np.array([fx * gx, fy * gy]) + np.array([0.3, 0.2])
+        cs.append(np.concatenate([xy, np.full((len(xy), 1), lz / 2)], 1))
+    pos = np.concatenate(cs) + rng.uniform(-jitter, jitter, (4 * len(base), 3))
+    box = np.array([cells[0] * gx, cells[1] * gy, lz])
+    pos[:, 0] %= box[0]
+    pos[:, 1] %= box[1]
+    n = len(pos)
+    mass = np.full(n, 12.011)
+    vel = maxwell(rng, mass, temperature)
+    inter = [dict(name="rebosc", file="parameters_REBOsc_C.txt", params=list(REBOSC_C), lists=[(1, 1, 12, 2.6, period)])]
+    if with_tb:
+        inter.append(dict(name="tb", file="parameters_TB_C.txt", params=list(TB_BRENNER_I), lists=[(1, 1, 12, 2.6, period)]))
+    return dict(
+        title="graphene_rebosc", box=box, pos=pos, vel=vel, mass=mass, names=["C"] * n,
+        groups=[["C"], ["#"]], roles=dict(all_moving=1, xyz_moving=1, z_moving=2, all_atoms=1, traj_group=2, period_traj=10 ** 9),
+        integrators=[("nve", dt, steps, 10 ** 9, 10)], ms_de=1e-8, nhc=[], zero_momentum_period=10 ** 9, invert_z_vel=False,
+        initial_temperature=temperature, interactions=inter,
     )
 
 
@@ -244,6 +279,8 @@ def _param_lines(name, p):
         return [f(p[0:8]), f(p[8:10])]
     if name == "rjl":
         return [f(p[0:5]), f(p[5:7])]
+    if name == "rebosc":
+        return [f(p[0:3]), f(p[3:6]), f(p[6:9]), f(p[9:10]), f(p[10:16]), f(p[16:18])]
     raise ValueError(name)
 
 
