@@ -18,6 +18,8 @@ NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccb
 SOURCES = ["nl.cu", "forces.cu", "rebosc.cu", "integrate.cu", "capi.cu", "slab.cu"]
 LIB = os.path.join(CSRC, "libpfmds_b200.so")
 EXE = os.path.join(HOST, "run_md_simulation")
+EXE_FIT = os.path.join(HOST, "run_gr_moire_fitting")
+EXE_ANALYSIS = os.path.join(HOST, "run_gr_analysis")
 
 
 def _newer(target, deps):
@@ -50,9 +52,11 @@ def build(force=False, verbose=False):
     if force or jobs or _newer(LIB, objs):
         _run([NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB] + objs + ["-ldl"])
     host_deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))]
-    if force or _newer(EXE, host_deps + [LIB]):
-        _run([CXX, "-O2", "-std=c++17", "-o", EXE, os.path.join(HOST, "run_md_simulation.cpp"), "-pthread", "-L" + CSRC, "-lpfmds_b200",
-              "-Wl,-rpath,$ORIGIN/../csrc"])
+    for exe, src in ((EXE, "run_md_simulation.cpp"), (EXE_FIT, "run_gr_moire_fitting.cpp")):
+        if force or _newer(exe, host_deps + [LIB]):
+            _run([CXX, "-O2", "-std=c++17", "-o", exe, os.path.join(HOST, src), "-pthread", "-L" + CSRC, "-lpfmds_b200", "-Wl,-rpath,$ORIGIN/../csrc"])
+    if force or _newer(EXE_ANALYSIS, host_deps):
+        _run([CXX, "-O2", "-std=c++17", "-o", EXE_ANALYSIS, os.path.join(HOST, "run_gr_analysis.cpp")])
     return LIB
 
 

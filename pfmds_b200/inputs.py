@@ -377,3 +377,47 @@ def finish_velocities(vel, mass, sums_all_ranks, n_total, temperature):
     ke = (sums_all_ranks[4] - m * (vcm ** 2).sum()) / 2 * MASS_COEF   # sum m (v - vcm)^2 = sum m v^2 - M vcm^2
     t = 2 * ke / KB / (3 * n_total)
     return v * np.sqrt(temperature / t)
+
+
+def write_fitting_inputs(directory, case_a, case_b, interface="ljc", out_prefix="fit_", p_min=None, p_max=None, z=0.0, be0=-0.05, grd0=(0.05, 0.05),
+                         zero_level=(0.0, 0.0)):
+    """Inputs of run_gr_moire_fitting (fit_gr_moire.f90:107-182): two cells (settings + start xyz each), the bracket of the
+    ljc / morsec parameters (min and max parameter files in parameter-file order) and the targets.  Returns the path of the
+    fitting-parameters file (`-fpfn`)."""
+    os.makedirs(directory, exist_ok=True)
+    d = directory if directory.endswith(os.sep) else directory + os.sep
+    names = []
+    for tag, case in (("a", case_a), ("b", case_b)):
+        write_case(d, case, settings="settings_%s.txt" % tag, xyz="cell_%s.xyz" % tag, log="md_%s.log" % tag)
+        os.rename(d + "cell_%s.xyz" % tag, d + "start_%s.xyz" % tag)       # calc_error renames start -> xyz around every md()
+        names.append(("settings_%s.txt" % tag, "start_%s.xyz" % tag, "final_%s.txt" % tag))
+    it = [i for i in case_a["interactions"] if i["name"] == interface][0]
+    p0 = list(it["params"])
+    npar = 3 if interface == "ljc" else 4
+    p_min = p_min if p_min is not None else [0.8 * v for v in p0[:npar]]
+    p_max = p_max if p_max is not None else [1.2 * v for v in p0[:npar]]
+    for nm, pv in (("params_min.txt", p_min), ("params_max.txt", p_max)):
+        with open(d + nm, "w") as f:
+            f.write(" ".join(repr(float(v)) for v in pv) + "\n")
+            f.write("%r %r\n" % (float(p0[npar]), float(p0[npar + 1])))
+    n_c = [sum(1 for t in c["names"] if t == "C") for c in (case_a, case_b)]
+    L = []
+    L.append("%-16s%s" % ("input_path:", d))
+    L.append("%-16s%s" % ("out_path:", d))
+    L.append("interaction_name: %s" % interface)
+    L.append("output_prefix: %s" % out_prefix)
+    for k in range(2):
+        L.append("settings_%d: %s" % (k + 1, names[k][0]))
+        L.append("start_xyz_%d: %s" % (k + 1, names[k][1]))
+        L.append("c_num_%d: %d" % (k + 1, n_c[k]))
+        L.append("zero_energy_%d: %r" % (k + 1, float(zero_level[k])))
+        L.append("final_file_%d: %s" % (k + 1, names[k][2]))
+    L.append("min_param_file: params_min.txt")
+    L.append("max_param_file: params_max.txt")
+    L.append("z: %r" % float(z))
+    L.append("be0: %r" % float(be0))
+    L.append("grd0_1: %r" % float(grd0[0]))
+    L.append("grd0_2: %r" % float(grd0[1]))
+    with open(d + "fitting.txt", "w") as f:
+        f.write("\n".join(L) + "\n")
+    return d + "fitting.txt"
