@@ -119,6 +119,18 @@ int pfmds_normals(pfmds_ctx* ctx, int interaction, double* gr_norm);
 int pfmds_get_nhc(pfmds_ctx* ctx, int k, double* x, double* v);
 int pfmds_set_nhc(pfmds_ctx* ctx, int k, const double* x, const double* v);
 
+/* Exact restart (the reference can only restart from a snapshot xyz, which loses the thermostat chains, the step
+ * counter and 3 digits of the velocities: md_simulation.f90:233-236).  pfmds_save_state fills `blob` (pfmds_state_size doubles)
+ * with what positions and velocities do not carry: every Nose-Hoover chain (x, v, q, cached kinetic energy) and group%N of
+ * every group; take positions / velocities with pfmds_download.  pfmds_restore_state puts all of it into a freshly configured
+ * context (same groups, thermostats, interactions), rebuilds every neighbour list from the given positions and evaluates the
+ * forces, i.e. leaves the context as it was after the checkpointed md step; continue with pfmds_advance(first = that step + 1).
+ * The continuation is bit-identical to the uninterrupted run when the checkpointed step is a rebuild step of every list
+ * (mod(step, update_period) == 0) and all lists share one update_period; otherwise it agrees to rounding. */
+int pfmds_state_size(pfmds_ctx* ctx, long long* n_doubles);
+int pfmds_save_state(pfmds_ctx* ctx, double* blob);
+int pfmds_restore_state(pfmds_ctx* ctx, const double* positions, const double* velocities, const double* blob);
+
 /* Seconds spent per phase, from CUDA events, when PFMDS_TIMERS=1 is set in the environment
  * (otherwise zeros): pos_vel, nlists, nlsearch, nldistance, forces, energy — the buckets of the
  * reference's PERFOMANCE table (md_simulation.f90:250-259). */

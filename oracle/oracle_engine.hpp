@@ -110,6 +110,37 @@ struct OracleEngine {
         if (vel) std::copy(sys.atoms.velocities.begin(), sys.atoms.velocities.begin() + n, vel);
         if (frc) std::copy(sys.atoms.forces.begin(), sys.atoms.forces.begin() + n, frc);
     }
+    // exact restart: what positions and velocities do not carry (thermostat chains, group%N); same role as pfmds_save_state
+    void save_state(std::vector<double>& blob) {
+        blob.clear();
+        blob.push_back((double)sys.nhc.size());
+        for (auto& n : sys.nhc) {
+            blob.push_back((double)n.M);
+            blob.insert(blob.end(), n.x.begin(), n.x.end());
+            blob.insert(blob.end(), n.v.begin(), n.v.end());
+        }
+        blob.push_back((double)sys.groups.size());
+        for (auto& g : sys.groups) blob.push_back((double)g.N);
+    }
+    void restore_state(const double* pos, const double* vel, const std::vector<double>& blob) {
+        size_t n3 = 3 * (size_t)sys.atoms.N, k = 0;
+        std::copy(pos, pos + n3, sys.atoms.positions.begin());
+        std::copy(vel, vel + n3, sys.atoms.velocities.begin());
+        if ((size_t)blob.at(k++) != sys.nhc.size()) throw StopError("error: the checkpoint does not belong to this settings file");
+        for (auto& n : sys.nhc) {
+            if ((int)blob.at(k++) != n.M) throw StopError("error: the checkpoint does not belong to this settings file");
+            for (int i = 0; i < n.M; ++i) n.x[(size_t)i] = blob.at(k++);
+            for (int i = 0; i < n.M; ++i) n.v[(size_t)i] = blob.at(k++);
+        }
+        if ((size_t)blob.at(k++) != sys.groups.size()) throw StopError("error: the checkpoint does not belong to this settings file");
+        for (auto& g : sys.groups) g.N = (int)blob.at(k++);
+        // lists and forces of the checkpointed step (md_simulation.f90:160-165 without the momentum removal)
+        double ts = 0, td = 0;
+        update_interactions_neighbour_lists(0, sys.interactions, sys.atoms, sys.groups, sys.cell, ts, td);
+        zero_forces(sys.atoms, sys.groups[(size_t)sys.all_atoms - 1]);
+        calculate_forces(sys.atoms, sys.interactions);
+        calculate_forces_numerically(sys.atoms, sys.interactions);
+    }
     void timers(double t[6]) {
         t[0] = sys.t_pos_vel; t[1] = sys.t_nlists; t[2] = sys.t_nlsearch; t[3] = sys.t_nldistance; t[4] = sys.t_forces; t[5] = sys.t_energy;
     }

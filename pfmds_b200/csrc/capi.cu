@@ -349,6 +349,17 @@ void update_lists(pfmds_ctx* c, int step) {
     for (size_t k = 0; k < c->inter.size(); ++k) normals_interaction(c, (int)k);  // update_norm_in_graphene, every step
 }
 
+// zero_forces + calculate_forces + calculate_forces_numerically, md_simulation.f90:163-165
+void compute_forces(pfmds_ctx* c, bool with_energy) {
+    forces_zero(c);
+    for (size_t k = 0; k < c->inter.size(); ++k)   // calculate_forces: the analytic interactions in file order
+        if (c->inter[k].kind != K_REBOSC) forces_interaction(c, (int)k, with_energy);
+    for (size_t k = 0; k < c->inter.size(); ++k)   // calculate_forces_numerically comes after all of them
+        if (c->inter[k].kind == K_REBOSC) forces_interaction(c, (int)k, with_energy);
+    if (c->slab) slab_step_done(c);
+    c->energy_valid = with_energy;
+}
+
 void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bool with_energy = false) {
     c->energy_valid = false;
     {
@@ -377,13 +388,7 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bo
     {
         PhaseTimer t(c, 4);
         if (step % c->zero_momentum_period == 0) integ_zero_momentum(c);
-        forces_zero(c);
-        for (size_t k = 0; k < c->inter.size(); ++k)   // calculate_forces: the analytic interactions in file order
-            if (c->inter[k].kind != K_REBOSC) forces_interaction(c, (int)k, with_energy);
-        for (size_t k = 0; k < c->inter.size(); ++k)   // calculate_forces_numerically comes after all of them (md_simulation.f90:164-165)
-            if (c->inter[k].kind == K_REBOSC) forces_interaction(c, (int)k, with_energy);
-        if (c->slab) slab_step_done(c);
-        c->energy_valid = with_energy;
+        compute_forces(c, with_energy);
     }
     if (step != 0) {
         PhaseTimer t(c, 0);
@@ -901,6 +906,91 @@ int pfmds_upload(pfmds_ctx* c, const double* pos, const double* vel) {
         if (dv) CK(cudaFreeAsync(dv, c->st));
         // membership of every list was decided on the old positions: rebuild at the next step
         for (auto& it : c->inter) for (int j = 0; j < it.nl_n; ++j) it.nl[j].built = false;
+    });
+}
+
+// ---- exact restart -------------------------------------------------------------
+// blob = [magic, n_nhc, n_groups, ke_valid] + per thermostat [M, x(M) v(M) q(M) s ke_cached s_pending spare] + group%N per group
+static const double STATE_MAGIC = 20240731.0;
+static size_t state_doubles(pfmds_ctx* c) {
+    size_t n = 4 + c->groups.size();
+    for (auto& t : c->nhc) n += 1 + (size_t)3 * t.M + 4;
+    return n;
+}
+int pfmds_state_size(pfmds_ctx* c, long long* n) {
+    if (!c || !n) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (c->slab) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: checkpoints of a slab context");
+        *n = (long long)state_doubles(c);
+    });
+}
+int pfmds_save_state(pfmds_ctx* c, double* blob) {
+    if (!c || !blob) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        if (c->slab) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: checkpoints of a slab context");
+        finalize(c);
+        integ_flush_pending(c);  // the velocities a following pfmds_download returns carry every thermostat scaling
+        CK(cudaStreamSynchronize(c->st));
+        size_t k = 0;
+        blob[k++] = STATE_MAGIC; blob[k++] = (double)c->nhc.size(); blob[k++] = (double)c->groups.size(); blob[k++] = c->nhc_ke_valid ? 1. : 0.;
+        for (auto& t : c->nhc) {
+            blob[k++] = (double)t.M;
+            CK(cudaMemcpy(blob + k, t.state, sizeof(double) * ((size_t)3 * t.M + 4), cudaMemcpyDeviceToHost));
+            k += (size_t)3 * t.M + 4;
+        }
+        for (size_t g = 0; g < c->groups.size(); ++g) blob[k++] = (double)c->cur_n[g];
+        check_device_error(c);
+    });
+}
+int pfmds_restore_state(pfmds_ctx* c, const double* pos, const double* vel, const double* blob) {
+    if (!c || !pos || !vel || !blob) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        if (c->slab) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: checkpoints of a slab context");
+        finalize(c);
+        size_t k = 0;
+        if (blob[k++] != STATE_MAGIC || (size_t)blob[k] != c->nhc.size() || (size_t)blob[k + 1] != c->groups.size())
+            fail(PFMDS_ERR_INVALID, "error: the checkpoint does not belong to this settings file (thermostats / groups differ)");
+        k += 2;
+        const bool ke_valid = blob[k++] != 0.;
+        integ_flush_pending(c);
+        {   // state in file order -> slots
+            const size_t n3 = 3 * (size_t)c->N;
+            double *dp = nullptr, *dv = nullptr;
+            CK(cudaMalloc(&dp, sizeof(double) * n3)); CK(cudaMalloc(&dv, sizeof(double) * n3));
+            CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
+            CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
+            k_upload_scatter<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->orig, dp, dv, c->pos, c->vel);
+            c->launches += 1;
+            CK(cudaStreamSynchronize(c->st));
+            cudaFree(dp); cudaFree(dv);
+        }
+        for (auto& t : c->nhc) {
+            if ((int)blob[k] != t.M) fail(PFMDS_ERR_INVALID, "error: the checkpoint does not belong to this settings file (chain length differs)");
+            ++k;
+            CK(cudaMemcpy(t.state, blob + k, sizeof(double) * ((size_t)3 * t.M + 4), cudaMemcpyHostToDevice));
+            k += (size_t)3 * t.M + 4;
+        }
+        c->nhc_pending = false;
+        c->nhc_ke_valid = ke_valid && c->nhc_fusable;
+        for (size_t g = 0; g < c->groups.size(); ++g) {
+            int n = (int)blob[k++];
+            if (n < 0 || n > (int)c->groups[g].size()) fail(PFMDS_ERR_INVALID, "error: bad group size in the checkpoint");
+            if (n != c->cur_n[g]) {
+                if (!c->d_grank[g]) fail(PFMDS_ERR_INVALID, "error: the checkpoint changes a group that has no change entry");
+                c->cur_n[g] = n;
+                k_group_resize<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->orig, c->d_grank[g], 1u << g, n, c->gmask);
+                c->launches += 1;
+            }
+        }
+        // the lists and forces of the checkpointed step: rebuilt from the checkpointed positions, which is what the interrupted
+        // run held when every update_period divides that step (the host only writes checkpoints on such steps)
+        for (auto& it : c->inter) for (int j = 0; j < it.nl_n; ++j) it.nl[j].built = false;
+        update_lists(c, 0);
+        compute_forces(c, false);
+        CK(cudaGetLastError());
+        check_device_error(c);
     });
 }
 

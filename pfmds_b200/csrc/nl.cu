@@ -122,14 +122,16 @@ __global__ void k_cell_scatter(int N, const int* __restrict__ cid, const int* __
     int c = cid[i];
     atoms[start[c] + atomicAdd(&cursor[c], 1)] = i;
 }
-// deterministic order inside each cell: ascending slot index (insertion sort, cells hold tens of atoms)
-__global__ void k_cell_sort(int ncells, const int* __restrict__ start, int* __restrict__ atoms) {
+// deterministic order inside each cell: ascending FILE index (insertion sort, cells hold tens of atoms).  The key is the
+// atom's identity, not the slot it happens to sit in, so the cell order — and with it every row order and summation order —
+// is a function of the positions alone: a run restarted from a checkpoint reproduces the interrupted run bit for bit.
+__global__ void k_cell_sort(int ncells, const int* __restrict__ start, int* __restrict__ atoms, const int* __restrict__ orig) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     int b = start[c], e = start[c + 1];
     for (int i = b + 1; i < e; ++i) {
-        int v = atoms[i], k = i - 1;
-        while (k >= b && atoms[k] > v) { atoms[k + 1] = atoms[k]; --k; }
+        int v = atoms[i], kv = orig[v], k = i - 1;
+        while (k >= b && orig[atoms[k]] > kv) { atoms[k + 1] = atoms[k]; --k; }
         atoms[k + 1] = v;
     }
 }
@@ -166,7 +168,7 @@ void nl_bin_atoms(pfmds_ctx* c, bool reorder) {
     k_scan_add<<<(c->ncells + T - 1) / T, T, 0, c->st>>>(c->ncells, c->cell_start, c->scan_tmp, c->ncells, N);
     CK(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)(c->ncells + 1), c->st));
     k_cell_scatter<<<nb, T, 0, c->st>>>(N, c->cid, c->cell_start, c->cell_cnt, c->cell_atoms);
-    k_cell_sort<<<(c->ncells + T - 1) / T, T, 0, c->st>>>(c->ncells, c->cell_start, c->cell_atoms);
+    k_cell_sort<<<(c->ncells + T - 1) / T, T, 0, c->st>>>(c->ncells, c->cell_start, c->cell_atoms, c->orig);
     c->launches += 6;
     if (reorder) {
         k_permute<<<nb, T, 0, c->st>>>(N, c->cell_atoms, c->pos, c->vel, c->gmask, c->orig, c->pos2, c->vel2, c->gmask2, c->orig2, c->newslot);

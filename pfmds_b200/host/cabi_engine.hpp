@@ -49,6 +49,18 @@ public:
         nl_load.resize((size_t)n_lists_);
     }
     void download(double* pos, double* vel, double* frc) { ck(pfmds_download(ctx_, pos, vel, frc)); }
+    void save_state(std::vector<double>& blob) {
+        long long n = 0;
+        ck(pfmds_state_size(ctx_, &n));
+        blob.assign((size_t)n, 0.);
+        ck(pfmds_save_state(ctx_, blob.data()));
+    }
+    void restore_state(const double* pos, const double* vel, const std::vector<double>& blob) {
+        long long n = 0;
+        ck(pfmds_state_size(ctx_, &n));
+        if ((long long)blob.size() != n) throw std::runtime_error("error: the checkpoint does not belong to this settings file (state size differs)");
+        ck(pfmds_restore_state(ctx_, pos, vel, blob.data()));
+    }
     void timers(double t[6]) { pfmds_synchronize(ctx_); pfmds_timers(ctx_, t); }
 
 private:

@@ -8,7 +8,7 @@
 // Engine concept (all methods throw std::runtime_error on failure, with the reference's message):
 //   create(n,pos,vel,mass,box) set_group(g,idx1) set_roles(am,xyz,z,all) add_interaction(spec)
 //   add_nhc(spec) set_misc(zero_momentum_period,invert_z) add_group_change(from,to,ts1,ts2,frec) group_size(g) advance(kind,dt,first_md_step,n_steps,energy_after_last)
-//   energies(e_inter,ke,temp,e_nhc) diagnostics(fs,mc,mcv,vmax,nl_load) download(pos,vel,frc)
+//   energies(e_inter,ke,temp,e_nhc) diagnostics(fs,mc,mcv,vmax,nl_load) download(pos,vel,frc) save_state(blob) restore_state(pos,vel,blob)
 //   timers(t[6])   -> seconds: pos_vel, nlists, nlsearch, nldistance, forces, energy
 #pragma once
 #include <chrono>
@@ -116,11 +116,67 @@ inline void write_particle_group_append(const std::string& filename, const std::
     std::fclose(f);
 }
 
+// Exact restart (not in the reference, whose only restart is a snapshot xyz: md_simulation.f90:233-236).
+// A checkpoint holds the full-precision state, the thermostat chains and the driver's own counters, so that
+// `-restart <file>` continues the interrupted run: same log rows, same final xyz.
+struct MdExtras {
+    int checkpoint_period = 0;   // > 0: write <prefix>checkpoint_NNNNNN.chk every that many md steps (rebuild steps of every list only)
+    std::string restart_file;    // non-empty: continue from this checkpoint instead of starting at md step 0
+};
+struct Checkpoint {
+    long long n = 0, md_step = 0, integrator_index = 0;
+    double simulation_time = 0, potential_energy = 0, prev_potential_energy = 0, kinetic_energy = 0, temperature = 0, total_energy = 0,
+           conserved_energy = 0, nose_hoover_energy = 0;
+    std::vector<double> e_inter, e_nhc, blob, pos, vel;
+};
+inline void write_checkpoint(const std::string& path, const Checkpoint& c) {
+    std::FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    const char magic[8] = {'P', 'F', 'M', 'D', 'S', 'C', 'K', '1'};
+    std::fwrite(magic, 1, 8, f);
+    long long h[3] = {c.n, c.md_step, c.integrator_index};
+    std::fwrite(h, sizeof(long long), 3, f);
+    double d[8] = {c.simulation_time, c.potential_energy, c.prev_potential_energy, c.kinetic_energy, c.temperature, c.total_energy, c.conserved_energy,
+                   c.nose_hoover_energy};
+    std::fwrite(d, sizeof(double), 8, f);
+    for (const std::vector<double>* v : {&c.e_inter, &c.e_nhc, &c.blob, &c.pos, &c.vel}) {
+        long long m = (long long)v->size();
+        std::fwrite(&m, sizeof m, 1, f);
+        if (m) std::fwrite(v->data(), sizeof(double), (size_t)m, f);
+    }
+    if (std::fclose(f) != 0) throw std::runtime_error("cannot write " + path);
+}
+inline Checkpoint read_checkpoint(const std::string& path) {
+    std::FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    Checkpoint c;
+    char magic[8];
+    long long h[3];
+    double d[8];
+    bool ok = std::fread(magic, 1, 8, f) == 8 && std::string(magic, 8) == "PFMDSCK1" && std::fread(h, sizeof(long long), 3, f) == 3 &&
+              std::fread(d, sizeof(double), 8, f) == 8;
+    if (ok) {
+        c.n = h[0]; c.md_step = h[1]; c.integrator_index = h[2];
+        c.simulation_time = d[0]; c.potential_energy = d[1]; c.prev_potential_energy = d[2]; c.kinetic_energy = d[3]; c.temperature = d[4];
+        c.total_energy = d[5]; c.conserved_energy = d[6]; c.nose_hoover_energy = d[7];
+        for (std::vector<double>* v : {&c.e_inter, &c.e_nhc, &c.blob, &c.pos, &c.vel}) {
+            long long m = -1;
+            ok = ok && std::fread(&m, sizeof m, 1, f) == 1 && m >= 0 && m < (1ll << 40);
+            if (!ok) break;
+            v->resize((size_t)m);
+            if (m) ok = std::fread(v->data(), sizeof(double), (size_t)m, f) == (size_t)m;
+        }
+    }
+    std::fclose(f);
+    if (!ok) throw std::runtime_error("error: " + path + " is not a pfmds checkpoint");
+    return c;
+}
+
 struct MdResult { int last_step = -1; double simulation_time = 0, total = 0, potential = 0, kinetic = 0, temperature = 0, md_seconds = 0; long atoms = 0; };
 
 template <class Engine>
 MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& input_path, const std::string& settings_filename,
-            const std::string& output_prefix, int out_period, int num_of_omp_treads, int rand_seed) {
+            const std::string& output_prefix, int out_period, int num_of_omp_treads, int rand_seed, const MdExtras& extras = MdExtras()) {
     using namespace fio;
     const double exe_time_start = wall();
     auto P = [&](const std::string& s) { std::fprintf(out, "%s\n", s.c_str()); };
@@ -196,7 +252,7 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
     };
 
     const size_t n_inter = s.interactions.size(), n_nhc = s.nhc.size();
-    std::FILE* logf = std::fopen((trim(output_prefix) + trim(s.logfilename)).c_str(), "w");
+    std::FILE* logf = std::fopen((trim(output_prefix) + trim(s.logfilename)).c_str(), extras.restart_file.empty() ? "w" : "a");
     if (!logf) throw std::runtime_error("cannot open log file " + trim(output_prefix) + trim(s.logfilename));
     P(A("PREPARATIONS TIME: ", 24, 19) + F(wall() - exe_time_start, 10, 2) + " S ");
     P(A("RUNNING ON ", 24, 11) + I(num_of_omp_treads, 6) + " OPENMP THREADS");
@@ -214,12 +270,34 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
     const int limit = s.md_step_limit;
     auto cum_len = [&](int upto) { long c = 0; for (int i = 0; i <= upto && i <= s.integrators_num; ++i) c += s.integrators[i].l; return c; };
     auto needs_energy = [&](int t, int idx, int kind) { return t % s.integrators[idx].period_log == 0 || t % out_period == 0 || kind == KIND_NVMS; };
+    auto checkpoint_step = [&](int t) {  // only steps on which every list is rebuilt reproduce the interrupted run exactly
+        if (extras.checkpoint_period <= 0 || t == 0 || t % extras.checkpoint_period != 0) return false;
+        for (auto& it : s.interactions)
+            for (auto& l : it.lists)
+                if (l.update_period > 0 && t % l.update_period != 0) return false;
+        return true;
+    };
     auto event_after = [&](int t, int idx, int kind) {
-        return needs_energy(t, idx, kind) || (t % s.integrators[idx].period_snapshot == 0 && t != 0) || t % s.period_traj == 0;
+        return needs_energy(t, idx, kind) || (t % s.integrators[idx].period_snapshot == 0 && t != 0) || t % s.period_traj == 0 || checkpoint_step(t);
     };
 
     int md_step = 0;
     bool exited = false;
+    if (!extras.restart_file.empty()) {
+        Checkpoint ck = read_checkpoint(extras.restart_file);
+        if (ck.n != xyz.N || ck.pos.size() != (size_t)3 * xyz.N || ck.vel.size() != (size_t)3 * xyz.N || ck.e_inter.size() != n_inter || ck.e_nhc.size() != n_nhc ||
+            ck.integrator_index < 1 || ck.integrator_index > s.integrators_num)
+            throw std::runtime_error("error: the checkpoint does not belong to this settings file");
+        eng.restore_state(ck.pos.data(), ck.vel.data(), ck.blob);
+        md_step = (int)ck.md_step + 1;
+        integrator_index = (int)ck.integrator_index;
+        integrator_name = s.integrators[integrator_index].int_name;
+        ts1 = s.integrators[integrator_index].dt;
+        simulation_time = ck.simulation_time; potential_energy = ck.potential_energy; prev_potential_energy = ck.prev_potential_energy;
+        kinetic_energy = ck.kinetic_energy; temperature = ck.temperature; total_energy = ck.total_energy; conserved_energy = ck.conserved_energy;
+        nose_hoover_energy = ck.nose_hoover_energy; e_inter = ck.e_inter; e_nhc = ck.e_nhc;
+        P(" restarted from " + trim(extras.restart_file) + " after step" + LI(ck.md_step));
+    }
     while (md_step <= limit) {
         // integrator phase switch, md_simulation.f90:121-136
         if (md_step - 1 == cum_len(integrator_index) || integrator_index == 0) {
@@ -301,6 +379,17 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
         if (traj)  // :238-241
             write_particle_group_append(trim(output_prefix) + "traj_" + I(s.traj_group, 0, 2) + ".xyz", current(s.traj_group), pos.data(),
                                         vel.data(), xyz, md_step);
+        if (checkpoint_step(md_step)) {
+            Checkpoint ck;
+            ck.n = xyz.N; ck.md_step = md_step; ck.integrator_index = integrator_index;
+            ck.simulation_time = simulation_time; ck.potential_energy = potential_energy; ck.prev_potential_energy = prev_potential_energy;
+            ck.kinetic_energy = kinetic_energy; ck.temperature = temperature; ck.total_energy = total_energy; ck.conserved_energy = conserved_energy;
+            ck.nose_hoover_energy = nose_hoover_energy; ck.e_inter = e_inter; ck.e_nhc = e_nhc;
+            ck.pos.resize((size_t)3 * xyz.N); ck.vel.resize((size_t)3 * xyz.N);
+            eng.save_state(ck.blob);
+            eng.download(ck.pos.data(), ck.vel.data(), nullptr);
+            write_checkpoint(trim(output_prefix) + "checkpoint_" + I(md_step, 0, 6) + ".chk", ck);
+        }
         ++md_step;
     }
     (void)exited;  // after a normal end md_step == limit+1, after an exit it is the step that was not run

@@ -19,6 +19,7 @@ namespace pfmds_host {
 
 struct CliOptions {
     int out_period = 1, threads = 1, node_id = 0, nodes = 0;  // node_id 1-based; nodes==0: plain runner
+    MdExtras extras;  // -checkpoint_period n, -restart file (single-run mode)
     int streams = 1;  // ensemble mode: runs of this rank executed concurrently (one host thread + one context/stream each)
     std::string settings_filename = "md_run_settings.txt", settings_files_list, all_out_file = "all_out.txt", output_prefix, input_path, out_path;
 };
@@ -46,6 +47,8 @@ int run_cli(int argc, char** argv, int default_threads, Factory make_engine) {
         else if (a == "-node") { o.node_id = (int)to_int(next()); mpi = true; }
         else if (a == "-nodes") { o.nodes = (int)to_int(next()); mpi = true; }
         else if (a == "-streams") o.streams = (int)to_int(next());
+        else if (a == "-checkpoint_period") o.extras.checkpoint_period = (int)to_int(next());
+        else if (a == "-restart") o.extras.restart_file = next();
         // unknown flags are silently ignored, like the reference's select case
     }
     if (mpi) {
@@ -81,7 +84,7 @@ int run_cli(int argc, char** argv, int default_threads, Factory make_engine) {
             } else {
                 std::fprintf(out, "%s\n", line.c_str());
                 auto eng = make_engine(o.threads);
-                md(eng, out, out, o.input_path, o.settings_filename, o.output_prefix, o.out_period, o.threads, 1);
+                md(eng, out, out, o.input_path, o.settings_filename, o.output_prefix, o.out_period, o.threads, 1, o.extras);
                 std::fprintf(out, "\n%s\n", line.c_str());
             }
             std::fprintf(out, "%s\n", line.c_str());
