@@ -20,6 +20,12 @@ interface
 	integer(c_int) function pfmds_set_roles(ctx,all_moving,xyz_moving,z_moving,all_atoms) bind(C,name='pfmds_set_roles')
 		import; type(c_ptr),value :: ctx; integer(c_int),value :: all_moving,xyz_moving,z_moving,all_atoms
 	end function
+	integer(c_int) function pfmds_add_group_change(ctx,group_from,group_to,change_ts1,change_ts2,change_frec) bind(C,name='pfmds_add_group_change')
+		import; type(c_ptr),value :: ctx; integer(c_int),value :: group_from,group_to,change_ts1,change_ts2,change_frec
+	end function
+	integer(c_int) function pfmds_group_size(ctx,group_num,n) bind(C,name='pfmds_group_size')
+		import; type(c_ptr),value :: ctx; integer(c_int),value :: group_num; integer(c_int) :: n
+	end function
 	integer(c_int) function pfmds_add_nhc(ctx,group_num,temperature,M,q1) bind(C,name='pfmds_add_nhc')
 		import; type(c_ptr),value :: ctx; integer(c_int),value :: group_num,M; real(c_double),value :: temperature,q1
 	end function
@@ -33,6 +39,18 @@ interface
 	end function
 	integer(c_int) function pfmds_advance(ctx,integrator,dt,first_md_step,n_steps) bind(C,name='pfmds_advance')
 		import; type(c_ptr),value :: ctx; integer(c_int),value :: integrator,first_md_step,n_steps; real(c_double),value :: dt
+	end function
+	integer(c_int) function pfmds_advance_with_energy(ctx,integrator,dt,first_md_step,n_steps) bind(C,name='pfmds_advance_with_energy')
+		import; type(c_ptr),value :: ctx; integer(c_int),value :: integrator,first_md_step,n_steps; real(c_double),value :: dt
+	end function
+	integer(c_int) function pfmds_state_size(ctx,n_doubles) bind(C,name='pfmds_state_size')
+		import; type(c_ptr),value :: ctx; integer(c_long_long) :: n_doubles
+	end function
+	integer(c_int) function pfmds_save_state(ctx,blob) bind(C,name='pfmds_save_state')
+		import; type(c_ptr),value :: ctx; real(c_double) :: blob(*)
+	end function
+	integer(c_int) function pfmds_restore_state(ctx,positions,velocities,blob) bind(C,name='pfmds_restore_state')
+		import; type(c_ptr),value :: ctx; real(c_double) :: positions(3,*),velocities(3,*),blob(*)
 	end function
 	integer(c_int) function pfmds_energies(ctx,e_inter,kinetic_energy,temperature,e_nhc) bind(C,name='pfmds_energies')
 		import; type(c_ptr),value :: ctx; real(c_double) :: e_inter(*),kinetic_energy,temperature,e_nhc(*)

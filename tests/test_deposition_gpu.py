@@ -73,3 +73,19 @@ def test_host_deposition_run_matches_the_cpu_port(tmp_path, cuda_lib, oracle_lib
         assert len(a["mass"]) == len(b["mass"]) and a["names"] == b["names"]
         assert np.abs(a["pos"] - b["pos"]).max() < 1e-8
     assert open(outs["gpu"] + "x_traj_03.xyz").read().count("time_step:") == open(outs["cpu"] + "x_traj_03.xyz").read().count("time_step:") == 2
+
+
+def test_deposition_matches_the_golden_fixture():
+    """Against the committed fixture (tests/golden/lj_deposition.npz, frozen oracle outputs)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lj_deposition.npz"))
+    case = inputs.lj_deposition()
+    e = gpu(case)
+    e.advance("nvt", 1.0, 0, 1)
+    assert rel_err(e.download()[2], g["frc0"]) < RTOL and np.allclose(e.energies()[0], g["e0"], rtol=RTOL, atol=0)
+    nl = neighbours(e, case, 0, 0)
+    assert np.array_equal(nl[1], g["nnum_0_0"]) and np.array_equal(nl[0], g["nlist_0_0"])
+    e.advance("nvt", 1.0, 1, 10)
+    p, v, f = e.download()
+    assert np.abs(p - g["pos10"]).max() < 1e-10 and rel_err(f, g["frc10"]) < 1e-8
+    assert [e.group_size(k + 1) for k in range(4)] == g["group_n10"].tolist()
+    assert np.array_equal(neighbours(e, case, 0, 0)[1], g["nnum10_0_0"])

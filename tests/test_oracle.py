@@ -135,6 +135,30 @@ def test_oracle_matches_golden(name):
     assert np.abs(p - g["pos10"]).max() < 1e-11 and rel_err(f, g["frc10"]) < 1e-9
 
 
+@pytest.mark.parametrize("name", ["lj_deposition", "graphene_rebosc"])
+def test_oracle_matches_golden_next_rows(name):
+    """Fixtures of the SURVEY.md 8(f) rows.  rebosc forces are central differences: they repeat to the rounding noise of
+    E(-dx) - E(+dx) only (thread partial sums), hence the looser force bound."""
+    from util import next_row_cases
+    case = next_row_cases()[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    assert np.array_equal(g["pos0"], case["pos"])
+    o = oracle(case)
+    integ, dt = case["integrators"][0][0], case["integrators"][0][1]
+    ftol = 2e-7 if name == "graphene_rebosc" else 1e-12
+    o.advance(integ, dt, 0, 1)
+    assert rel_err(o.download()[2], g["frc0"]) < ftol
+    assert np.allclose(o.energies()[0], g["e0"], rtol=1e-12)
+    nl = neighbours(o, case, 0, 0)
+    assert np.array_equal(nl[1], g["nnum_0_0"]) and np.array_equal(nl[0], g["nlist_0_0"])
+    o.advance(integ, dt, 1, 10)
+    p, v, f = o.download()
+    assert np.abs(p - g["pos10"]).max() < 1e-9 and rel_err(f, g["frc10"]) < max(ftol, 1e-9)
+    if "group_n10" in g:
+        assert [o.group_size(k + 1) for k in range(len(case["groups"]))] == g["group_n10"].tolist()
+        assert np.array_equal(neighbours(o, case, 0, 0)[1], g["nnum10_0_0"])
+
+
 def test_half_list_rule_drops_pairs_for_non_monotone_groups():
     """lessnnum counts the entries before the first one whose GLOBAL index exceeds the owner's
     (md_neighbours.f90:78).  For a group whose indexes are not ascending (type columns 'B A' with file order A.., B..)

@@ -81,3 +81,17 @@ def test_host_rebosc_run_matches_the_cpu_port(tmp_path, cuda_lib, oracle_lib):
     rows = lambda p: [[float(x) for x in l[15:].split()] for l in open(p).read().splitlines() if l[:6].strip() == "nve"]
     for ra, rb in zip(rows(outs["gpu"] + "x_md_run.log"), rows(outs["cpu"] + "x_md_run.log")):
         assert np.allclose(ra, rb, rtol=1e-7, atol=2e-6)
+
+
+def test_rebosc_matches_the_golden_fixture():
+    """Against the committed fixture (tests/golden/graphene_rebosc.npz, frozen oracle outputs)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graphene_rebosc.npz"))
+    case = inputs.graphene_rebosc()
+    e = gpu(case)
+    e.advance("nve", 0.5, 0, 1)
+    assert np.abs(e.download()[2] - g["frc0"]).max() < FD_NOISE * np.abs(g["frc0"]).max()
+    assert np.allclose(e.energies()[0], g["e0"], rtol=RTOL, atol=0)
+    nl = neighbours(e, case, 0, 0)
+    assert np.array_equal(nl[1], g["nnum_0_0"]) and np.array_equal(nl[0], g["nlist_0_0"])
+    e.advance("nve", 0.5, 1, 10)
+    assert np.abs(e.download()[0] - g["pos10"]).max() < 1e-8

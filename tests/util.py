@@ -36,6 +36,14 @@ def small_cases():
     }
 
 
+def next_row_cases():
+    """Small cases of the SURVEY.md 8(f) rows (deposition, rebosc): frozen in tests/golden/ too, with their own tolerances."""
+    return {
+        "lj_deposition": inputs.lj_deposition(),
+        "graphene_rebosc": inputs.graphene_rebosc(),
+    }
+
+
 def list_ids(case):
     return [(k, j) for k, it in enumerate(case["interactions"]) for j in range(len(it["lists"]))]
 
