@@ -120,8 +120,8 @@ def test_list_mode_and_ensemble_sharding(tmp_path):
         shard(1, 2, 0)
     for rank in (0, 1):
         rr = subprocess.run([ORACLE_EXE, "-node", str(rank + 1), "-nodes", "2", "-ipath", d, "-ilist", "list.txt", "-opath", d, "-op", "100"],
-                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=d)   # NNNN-out.txt goes to the working directory
         assert rr.returncode == 0
     assert os.path.exists(d + "0001-a_final_init.xyz") and os.path.exists(d + "0002-b_final_init.xyz") and os.path.exists(d + "0001-c_final_init.xyz")
     assert not os.path.exists(d + "0002-a_final_init.xyz")
-    assert "RUNNING ON NODE      1 OUT OF     2 NODES" in open("0001-out.txt").read() if os.path.exists("0001-out.txt") else True
+    assert "RUNNING ON NODE      1 OUT OF     2 NODES" in open(d + "0001-out.txt").read()

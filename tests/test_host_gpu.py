@@ -60,7 +60,7 @@ def test_gpu_ensemble_ranks(tmp_path, cuda_lib):
     inputs.write_case(d, case)
     open(d + "list.txt", "w").write("3\nmd_run_settings.txt a_\nmd_run_settings.txt b_\nmd_run_settings.txt c_\n")
     procs = [subprocess.Popen([EXE, "-node", str(r + 1), "-nodes", "2", "-gpu", "0", "-ipath", d, "-ilist", "list.txt", "-opath", d, "-op", "100"],
-                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=d) for r in range(2)]
     for p in procs:
         assert p.wait(timeout=300) == 0
     a, c = read_xyz(d + "0001-a_final_init.xyz"), read_xyz(d + "0001-c_final_init.xyz")
