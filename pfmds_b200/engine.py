@@ -54,6 +54,9 @@ _SIGS = {
     "normals": [C.c_void_p, C.c_int, _dp],
     "get_nhc": [C.c_void_p, C.c_int, _dp, _dp],
     "set_nhc": [C.c_void_p, C.c_int, _dp, _dp],
+    "state_size": [C.c_void_p, C.POINTER(C.c_longlong)],
+    "save_state": [C.c_void_p, _dp],
+    "restore_state": [C.c_void_p, _dp, _dp, _dp],
     "timers": [C.c_void_p, _dp],
     "upload": [C.c_void_p, _dp, _dp],
     "pair_count": [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_longlong)],
@@ -70,7 +73,7 @@ _SIGS = {
 }
 
 
-_OPTIONAL = ("advance_with_energy", "upload", "pair_count", "set_profiling", "kernel_times", "timer_start", "timer_stop")  # product-only entry points
+_OPTIONAL = ("state_size", "save_state", "restore_state", "advance_with_energy", "upload", "pair_count", "set_profiling", "kernel_times", "timer_start", "timer_stop")  # product-only entry points
 
 
 def load_library(path=LIB_PATH, prefix="pfmds_"):
@@ -206,6 +209,21 @@ class Engine:
         x = np.ascontiguousarray(x, np.float64)
         v = np.ascontiguousarray(v, np.float64)
         self._call("set_nhc", self._ctx, k, _d(x), _d(v))
+
+    def save_state(self):
+        """What positions and velocities do not carry (thermostat chains, group sizes): pfmds_save_state."""
+        n = C.c_longlong()
+        self._call("state_size", self._ctx, C.byref(n))
+        blob = np.zeros(n.value)
+        self._call("save_state", self._ctx, _d(blob))
+        return blob
+
+    def restore_state(self, pos, vel, blob):
+        """Exact restart of a freshly configured context: pfmds_restore_state (lists and forces are rebuilt on the device)."""
+        pos = np.ascontiguousarray(pos, np.float64).reshape(-1)
+        vel = np.ascontiguousarray(vel, np.float64).reshape(-1)
+        blob = np.ascontiguousarray(blob, np.float64)
+        self._call("restore_state", self._ctx, _d(pos), _d(vel), _d(blob))
 
     def upload(self, pos=None, vel=None):
         pos = None if pos is None else np.ascontiguousarray(pos, np.float64).reshape(-1)

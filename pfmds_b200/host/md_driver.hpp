@@ -39,20 +39,35 @@ inline std::vector<int> group_indexes_1based(const GroupSpec& g, const std::vect
 }
 
 // md_general.f90:114-159,328-340 (set_new_temperature).  The reference draws from libgfortran's rand()
-// inside an OpenMP region (thread-order dependent, source not in the tree): parity is unpinned there,
-// so this uses its own counter-free 64-bit LCG seeded with rand_seed; same Marsaglia polar method,
-// same sqrt(coef/m) scaling, momentum removal and rescale to the requested temperature.
+// inside an OpenMP region (thread-order dependent, source not in the tree): parity is unpinned there.
+// This generator is COUNTER-BASED: the uniform behind draw d of component k of atom i is a pure function
+// (SplitMix64 finaliser) of (rand_seed, i, k, d), so the velocities do not depend on the order in which atoms are
+// processed, on thread counts or on which rank / device generates them.  Same Marsaglia polar method, same
+// sqrt(coef/m) scaling, momentum removal and rescale to the requested temperature as the reference.
+inline uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+inline double counter_uniform(int rand_seed, uint64_t atom, int k, uint64_t draw) {  // [0, 1), 53 bits
+    uint64_t key = mix64((uint64_t)(uint32_t)rand_seed);
+    uint64_t ctr = (atom * 3 + (uint64_t)k) * 0x100000000ull + draw;
+    return (double)(mix64(key ^ mix64(ctr)) >> 11) * (1.0 / 9007199254740992.0);
+}
 inline void set_new_temperature(XyzFile& x, const std::vector<int>& idx1, double temp, int rand_seed) {
     const double coef = 1.3806488 / 1.6605389217 * 1.0e-6;
     const double mass_coef = 1.6605389217 / 1.6021765654 * 100.0;
     const double kt_a_degree = 1.3806488 / 1.6021765654 * 1.0e-4;
-    uint64_t st = 0x9E3779B97F4A7C15ull ^ (uint64_t)(uint32_t)rand_seed * 0xD1B54A32D192ED03ull;
-    auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (double)(st >> 11) * (1.0 / 9007199254740992.0); };
     for (int i1 : idx1) {
         int i = i1 - 1;
         for (int k = 0; k < 3; ++k) {
             double b = 2., a1 = 0., a2 = 0.;
-            while (b >= 1. || b == 0.) { a1 = 2. * rnd() - 1.; a2 = 2. * rnd() - 1.; b = a1 * a1 + a2 * a2; }
+            for (uint64_t d = 0; b >= 1. || b == 0.; d += 2) {
+                a1 = 2. * counter_uniform(rand_seed, (uint64_t)i, k, d) - 1.;
+                a2 = 2. * counter_uniform(rand_seed, (uint64_t)i, k, d + 1) - 1.;
+                b = a1 * a1 + a2 * a2;
+            }
             x.velocities[3 * i + k] = a1 * std::sqrt(-2. * std::log(b) / b) * std::sqrt(coef / x.masses[i]);
         }
     }

@@ -125,3 +125,35 @@ def test_list_mode_and_ensemble_sharding(tmp_path):
     assert os.path.exists(d + "0001-a_final_init.xyz") and os.path.exists(d + "0002-b_final_init.xyz") and os.path.exists(d + "0001-c_final_init.xyz")
     assert not os.path.exists(d + "0002-a_final_init.xyz")
     assert "RUNNING ON NODE      1 OUT OF     2 NODES" in open(d + "0001-out.txt").read()
+
+
+def test_new_velocities_are_seeded_and_order_independent(tmp_path):
+    """new_velocities T (set_new_temperature, md_general.f90:114-159,328-340) with the host's counter-based generator:
+    exact target temperature, no centre-of-mass motion, Maxwell widths, and the same velocities for the same seed."""
+    from pfmds_b200.host_io import read_xyz
+    case = inputs.cu_fcc(ncell=6, steps=0, period=5)
+    case["vel"][:] = 0.0
+    case["integrators"] = [("nve", 2.0, 1, 1, 1)]
+    case["initial_temperature"] = 250.0
+    outs = []
+    for k in range(2):
+        d, r = _run(tmp_path / ("r%d" % k), case, new_velocities=True, md_step_limit=1)
+        assert r.returncode == 0, r.stdout[-2000:]
+        outs.append((d, r.stdout))
+    a, b = read_xyz(outs[0][0] + "t_snapshot_000001.xyz"), read_xyz(outs[1][0] + "t_snapshot_000001.xyz")
+    assert np.array_equal(a["vel"], b["vel"])                                      # same rand_seed (1): same draw for every atom
+    log = [l for l in open(outs[0][0] + "t_md_run.log").read().splitlines() if l[:6].strip() == "nve"]
+    t0 = float(log[0].split()[8])
+    assert abs(t0 - 250.0) < 1e-5                                                   # rescaled to the requested temperature (f24.6 column)
+    v = a["vel"]
+    m = case["mass"]
+    assert np.abs((m[:, None] * v).sum(0)).max() < 1e-9 * m.sum()                   # momentum removed (one short step later)
+    sig = np.sqrt(inputs.COEF * 250.0 / m[0])
+    assert abs(v.std() / sig - 1.0) < 0.05 and abs(np.mean(np.abs(v) < sig) - 0.6827) < 0.03   # Maxwell: 68 % inside one sigma
+    # ensemble ranks seed with their rank number (run_md_simulation_mpi.f90:62): different velocities
+    d2 = str(tmp_path / "e") + os.sep
+    inputs.write_case(d2, case, new_velocities=True, md_step_limit=1)
+    rr = subprocess.run([ORACLE_EXE, "-node", "2", "-nodes", "2", "-ipath", d2, "-opath", d2, "-op", "100"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=d2)
+    assert rr.returncode == 0
+    c = read_xyz(d2 + "0002-snapshot_000001.xyz")
+    assert not np.allclose(c["vel"], a["vel"])
