@@ -17,16 +17,7 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #else
-// Host build of the device code, used only by the CPU emulation tests (tests/*_host.cpp run a kernel's per-thread body in a
-// serial loop to check its logic without a GPU).  The product is always compiled by nvcc.
-#include <math.h>
-#define __device__
-#define __host__
-#define __forceinline__ inline
-#define __restrict__
-struct double4 { double x, y, z, w; };
-static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
-static inline int atomicCAS(int* a, int cmp, int val) { int old = *a; if (old == cmp) *a = val; return old; }
+#include "host_emu.hpp"  // test support: the kernels of this directory compiled for the host (tests/*_host.cpp), never part of the product
 #endif
 
 #include "mathx.cuh"
@@ -161,6 +152,9 @@ __device__ __forceinline__ void slab_signal(const SlabDev& S, bool pushed) {
         }
     }
 }
+#else
+static inline void slab_wait(const SlabDev&) {}
+static inline void slab_signal(const SlabDev&, bool) {}
 #endif  // __CUDACC__
 
 struct ListView { const int* nlist; const int* nnum; size_t stride; };

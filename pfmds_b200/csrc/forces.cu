@@ -11,7 +11,11 @@
 #include <cstring>
 #include <string>
 
+#ifdef __CUDACC__
 #include "ctx.hpp"
+#else
+#include "common.cuh"  // host emulation of the kernels (tests/forces_host.cpp): no context, no launchers
+#endif
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
 #define FT 128  // threads per block for the force kernels
@@ -593,6 +597,7 @@ __global__ void k_zero_group(int N, double4* __restrict__ frc, const uint32_t* _
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N && (gmask[i] & bit)) frc[i] = make_double4(0., 0., 0., 0.);
 }
+#ifdef __CUDACC__  // ---- launchers (host side of the product) ----------------------------------------
 void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
     if (c->first_overwrites && c->N >= SMALL_N) return;  // the first force kernel stores instead of accumulating
     KTimer kt(c, KS_ZERO_FORCES);
@@ -753,3 +758,4 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     if (c->slab) slab_allreduce_sum(c, c->energy + k, 1);
     CK(cudaGetLastError());
 }
+#endif  // __CUDACC__

@@ -11,40 +11,50 @@
 #include <cmath>
 #include <cstdio>
 
+#ifdef __CUDACC__
 #include "ctx.hpp"
+#else
+#include "common.cuh"  // host emulation of the kernels (tests/nl_host.cpp): no context, no launchers
+#endif
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
 
 // ------------------------------------------------------------------------------------------------
-void nl_setup_grid(pfmds_ctx* c) {
-    double rc = 0;
-    for (auto& it : c->inter)
-        for (int j = 0; j < it.nl_n; ++j) rc = std::max(rc, it.nl[j].rcut);
+// Cell grid for a box and the largest r_cut of the run (pure arithmetic: shared by nl_setup_grid and the host emulation tests).
+// Positions may sit up to 1e-7 outside [0,L] (check_positions tolerance, md_general.f90:346) and are
+// clamped into the edge cells, so the cells are made a little wider than r_cut.
+inline long long nl_grid_dims(const BoxD& box, double rc, int ncell[3], double& cell_rc) {
     if (rc <= 0) rc = 1.0;
-    // Positions may sit up to 1e-7 outside [0,L] (check_positions tolerance, md_general.f90:346) and are
-    // clamped into the edge cells, so the cells are made a little wider than r_cut.
-    c->cell_rc = rc * (1.0 + 1e-9) + 1e-5;
+    cell_rc = rc * (1.0 + 1e-9) + 1e-5;
     long long total = 1;
     for (int k = 0; k < 3; ++k) {
-        int n = (int)std::floor(c->box.L[k] / c->cell_rc);
+        int n = (int)std::floor(box.L[k] / cell_rc);
         if (n < 1) n = 1;
         if (n > 1024) n = 1024;
-        c->ncell[k] = n;
+        ncell[k] = n;
         total *= n;
     }
     // keep the cell table bounded for sparse, huge boxes
     while (total > 64ll * 1024 * 1024) {
-        int k = (c->ncell[0] >= c->ncell[1] && c->ncell[0] >= c->ncell[2]) ? 0 : (c->ncell[1] >= c->ncell[2] ? 1 : 2);
-        total /= c->ncell[k];
-        c->ncell[k] = (c->ncell[k] + 1) / 2;
-        total *= c->ncell[k];
+        int k = (ncell[0] >= ncell[1] && ncell[0] >= ncell[2]) ? 0 : (ncell[1] >= ncell[2] ? 1 : 2);
+        total /= ncell[k];
+        ncell[k] = (ncell[k] + 1) / 2;
+        total *= ncell[k];
     }
-    c->ncells = (int)total;
+    return total;
+}
+#ifdef __CUDACC__
+void nl_setup_grid(pfmds_ctx* c) {
+    double rc = 0;
+    for (auto& it : c->inter)
+        for (int j = 0; j < it.nl_n; ++j) rc = std::max(rc, it.nl[j].rcut);
+    c->ncells = (int)nl_grid_dims(c->box, rc, c->ncell, c->cell_rc);
     if (c->cell_cnt) { cudaFree(c->cell_cnt); cudaFree(c->cell_start); cudaFree(c->scan_tmp); }
     CK(cudaMalloc(&c->cell_cnt, sizeof(int) * (size_t)(c->ncells + 1)));
     CK(cudaMalloc(&c->cell_start, sizeof(int) * (size_t)(c->ncells + 1)));
     CK(cudaMalloc(&c->scan_tmp, sizeof(int) * (size_t)(c->ncells / 2048 + 2)));
 }
+#endif
 
 struct GridD { int n[3]; double inv[3]; };
 __global__ void k_make_posf(int N, const double4* __restrict__ pos, const uint32_t* __restrict__ gmask, float4* __restrict__ posf);
@@ -64,6 +74,7 @@ __global__ void k_cell_count(int N, const double4* __restrict__ pos, GridD g, in
     atomicAdd(&cnt[c], 1);
 }
 
+#ifdef __CUDACC__  // the scans exchange data between lanes: device only (the host emulation uses a plain prefix sum)
 // exclusive scan, 2048 items per block (1024 threads x 2), block totals to `sums`
 __global__ void k_scan_block(int n, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ sums) {
     __shared__ int sh[32];
@@ -115,6 +126,7 @@ __global__ void k_scan_add(int n, int* out, const int* __restrict__ sums, int to
     if (i < n) out[i] += sums[i / 2048];
     if (i == 0) out[total_slot] = total;
 }
+#endif
 
 __global__ void k_cell_scatter(int N, const int* __restrict__ cid, const int* __restrict__ start, int* __restrict__ cursor, int* __restrict__ atoms) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +164,7 @@ __global__ void k_iota(int N, int* a) {
     if (k < N) a[k] = k;
 }
 
+#ifdef __CUDACC__
 // Bin every atom into the cell grid; with `reorder` the state arrays are physically permuted into
 // cell order (only legal when every neighbour list is rebuilt in the same step, since lists hold
 // slot indices).
@@ -186,6 +199,7 @@ void nl_bin_atoms(pfmds_ctx* c, bool reorder) {
     c->launches += 1;
     CK(cudaGetLastError());
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // One thread per list-owner atom walks the 27 (or fewer, for boxes under three cells wide) cells
@@ -269,6 +283,7 @@ __global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict_
     nnum[i] = cnt;
 }
 
+#ifdef __CUDACC__  // ballot / popc compaction across the lanes of a warp: device only
 // One WARP per list-owner atom: the lanes test 32 candidates of a cell range at a time (coalesced 16-byte
 // loads of the float4 copy), the survivors of the exact FP64 test are compacted with ballot + popc into the
 // row in candidate order (deterministic), one counter per class when PART.  The three x-neighbour cells of a
@@ -363,21 +378,35 @@ __global__ void __launch_bounds__(256) k_build_warp(int N, const double4* __rest
     if (lane == 0) nnum[i] = cnt;
 }
 
+#endif
+
+// FP32 prefilter limits for a list with cut-off rcut in `box` (pure arithmetic: shared by nl_build and the host emulation tests)
+inline PrefD nl_prefilter(const BoxD& box, double rcut) {
+    PrefD pf;
+    const double rc2 = rcut * rcut;
+    double Lmax = std::max(box.L[0], std::max(box.L[1], box.L[2])), hmin = std::min(box.h[0], std::min(box.h[1], box.h[2]));
+    for (int k = 0; k < 3; ++k) { pf.L[k] = (float)box.L[k]; pf.h[k] = (float)box.h[k]; }
+    // |delta d| <= 3 ulp-halves of L per component, r2 error <= 2 sqrt(3) r |delta d| + float rounding of r2; doubled
+    double dd = 2e-7 * Lmax, margin = 2.0 * (3.5 * rcut * dd + 4e-7 * rc2 + 3 * dd * dd);
+    pf.lim = (float)(rc2 + margin) * (1.0f + 2e-7f);
+    pf.on = hmin > rcut * 1.01 + 10 * dd;  // tiny boxes: the float wrap could pick another image, use the exact test only
+    return pf;
+}
+inline GridD nl_grid(const int ncell[3], const BoxD& box) {
+    GridD g;
+    for (int k = 0; k < 3; ++k) { g.n[k] = ncell[k]; g.inv[k] = ncell[k] / box.L[k]; }
+    return g;
+}
+
+#ifdef __CUDACC__
 void nl_build(pfmds_ctx* c, NList& l) {
     const int N = c->N;
     const bool warp_per_atom = N < 200000;  // measured: at 1e6 atoms the thread-per-atom scan is 2x faster, at 1e4 atoms 5x slower
     const int T = warp_per_atom ? 256 : 128, nb = warp_per_atom ? (int)(((size_t)N * 32 + T - 1) / T) : (N + T - 1) / T;
-    GridD g;
-    for (int k = 0; k < 3; ++k) { g.n[k] = c->ncell[k]; g.inv[k] = c->ncell[k] / c->box.L[k]; }
+    const GridD g = nl_grid(c->ncell, c->box);
     uint32_t b1 = 1u << (l.g1 - 1), b2 = 1u << (l.g2 - 1);
     double rc2 = l.rcut * l.rcut;
-    PrefD pf;
-    double Lmax = std::max(c->box.L[0], std::max(c->box.L[1], c->box.L[2])), hmin = std::min(c->box.h[0], std::min(c->box.h[1], c->box.h[2]));
-    for (int k = 0; k < 3; ++k) { pf.L[k] = (float)c->box.L[k]; pf.h[k] = (float)c->box.h[k]; }
-    // |delta d| <= 3 ulp-halves of L per component, r2 error <= 2 sqrt(3) r |delta d| + float rounding of r2; doubled
-    double dd = 2e-7 * Lmax, margin = 2.0 * (3.5 * l.rcut * dd + 4e-7 * rc2 + 3 * dd * dd);
-    pf.lim = (float)(rc2 + margin) * (1.0f + 2e-7f);
-    pf.on = hmin > l.rcut * 1.01 + 10 * dd;  // tiny boxes: the float wrap could pick another image, use the exact test only
+    const PrefD pf = nl_prefilter(c->box, l.rcut);
     KTimer kt(c, KS_NL_BUILD);
 #define LAUNCH_BUILD(ID, PT) do { if (warp_per_atom) k_build_warp<ID, PT><<<nb, T, 0, c->st>>>(N, c->pos, c->posf, c->orig, c->cell_start, c->cell_atoms, g, c->box, pf, b1, b2, rc2, \
         l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err); \
@@ -390,6 +419,7 @@ void nl_build(pfmds_ctx* c, NList& l) {
     l.built = true;
     CK(cudaGetLastError());
 }
+#endif  // __CUDACC__
 
 // graphenenorm.f90:8-36: the entries of the carbon (tb) list closer than r_cut_nn; exactly three.
 __global__ void k_nearest3(int N, const double4* __restrict__ pos, const int* __restrict__ orig, ListView src, BoxD box, double rc_nn,
@@ -416,6 +446,7 @@ __global__ void k_nearest3(int N, const double4* __restrict__ pos, const int* __
     nnnum[i] = k < 3 ? k : 3;
 }
 
+#ifdef __CUDACC__
 void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     const int N = c->N, T = 128, nb = (N + T - 1) / T;
     KTimer kt(c, KS_NL_BUILD);
@@ -424,4 +455,4 @@ void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     nn.built = true;
     CK(cudaGetLastError());
 }
-
+#endif  // __CUDACC__

@@ -1,0 +1,117 @@
+// Host build of pfmds_b200/csrc/forces.cu for tests/test_kernels_host.py: the force / energy kernels (thread-per-atom variants) run
+// as plain functions, one call per (block, thread) (pfmds_b200/csrc/host_emu.hpp), on the device's data layout — double4 records,
+// ELL lists with slot indices — with the launch sequences of forces_interaction / energy_interaction (forces.cu, bottom).
+// This checks kernel arithmetic and indexing against the CPU oracle without a GPU; it is not a CPU path of the product.
+#include <cstddef>
+#include <vector>
+
+#include "../pfmds_b200/csrc/forces.cu"
+
+namespace {
+BoxD make_box(const double* L) {
+    BoxD b;
+    for (int k = 0; k < 3; ++k) { b.L[k] = L[k]; b.h[k] = 0.5 * L[k]; }
+    return b;
+}
+double sum_parts(std::vector<double>& part, int n, double scale) {
+    double out = 0;
+    emu_launch(k_sum_partials, 1, 1, 1024, n, (const double*)part.data(), scale, &out);
+    return out;
+}
+}  // namespace
+
+extern "C" {
+
+// lj: lists 0 (g1 -> g2) and 1 (converse); energy from list 0 (LJ_energy on nl(1))
+int fh_lj(int N, const double* pos4, double* frc4, size_t stride, const int* nl0, const int* nn0, const int* nl1, const int* nn1, const double* p,
+          const double* L, double* energy) {
+    const double4* pos = (const double4*)pos4;
+    double4* frc = (double4*)frc4;
+    BoxD box = make_box(L);
+    LJp P{p[0], p[1], p[2], p[3]};
+    const int nb = (N + FT - 1) / FT;
+    std::vector<double> part((size_t)nb + 1, 0.);
+    emu_launch(k_lj<true, true, 1>, nb, 1, FT, N, pos, frc, ListView{nl0, nn0, stride}, P, box, part.data());
+    *energy = sum_parts(part, nb, 1.0);
+    emu_launch(k_lj<true, false, 1>, nb, 1, FT, N, pos, frc, ListView{nl1, nn1, stride}, P, box, (double*)nullptr);
+    return 0;
+}
+
+int fh_lj1g(int N, const double* pos4, double* frc4, size_t stride, const int* nl0, const int* nn0, const double* p, const double* L, double* energy) {
+    const double4* pos = (const double4*)pos4;
+    double4* frc = (double4*)frc4;
+    BoxD box = make_box(L);
+    double s2 = p[1] * p[1], s6 = s2 * s2 * s2, s12 = s6 * s6;  // as pfmds_add_interaction (capi.cu), LennardJones_1g.f90:21-24
+    LJ1Gp P{p[2], p[3], 4. * p[0] * s6, 4. * p[0] * s12, 6. * 4. * p[0] * s6, 12. * 4. * p[0] * s12};
+    const int nb = (N + FT - 1) / FT;
+    std::vector<double> part((size_t)nb + 1, 0.);
+    emu_launch(k_lj1g<true, true, 1>, nb, 1, FT, N, pos, frc, ListView{nl0, nn0, stride}, P, box, part.data());
+    *energy = sum_parts(part, nb, 0.5);
+    return 0;
+}
+
+// rjl: density pass (1/Eb into pos.w, energy partials) then force pass; `overwrite` = the store-instead-of-accumulate variant
+int fh_rjl(int N, double* pos4, double* frc4, size_t stride, const int* nl0, const int* nn0, const double* p, const double* L, int overwrite, double* energy) {
+    double4* pos = (double4*)pos4;
+    double4* frc = (double4*)frc4;
+    BoxD box = make_box(L);
+    RJLp R{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
+    const RjlC C = rjl_consts(R);
+    const WrapC W = wrap_consts(box);
+    const int nb = (N + FT - 1) / FT;
+    std::vector<double> part((size_t)nb + 1, 0.);
+    emu_launch(k_rjl_density<true>, nb, 1, FT, N, pos, ListView{nl0, nn0, stride}, C, box, W, part.data(), SlabDev{});
+    *energy = sum_parts(part, nb, 1.0);
+    emu_launch(k_rjl_force, nb, 1, FT, N, (const double4*)pos, frc, ListView{nl0, nn0, stride}, C, box, W, SlabDev{}, overwrite);
+    return 0;
+}
+
+// tb: bond orders, per-(slot, atom) force parts, reduction; energy from a second sweep (energy_interaction)
+int fh_tb(int N, const double* pos4, double* frc4, size_t stride, int maxn, const int* nl0, const int* nn0, const double* p, const double* L, double* energy) {
+    const double4* pos = (const double4*)pos4;
+    double4* frc = (double4*)frc4;
+    BoxD box = make_box(L);
+    TBp T{p[0], p[1], p[2], p[3], p[4], p[5], p[6] * p[6], p[7] * p[7], p[8], p[9]};  // as pfmds_add_interaction, TersoffBrenner.f90:19-20
+    const int nb = (N + FT - 1) / FT;
+    std::vector<double> aux((size_t)maxn * stride, 0.), aux2((size_t)maxn * stride, 0.), part((size_t)nb * maxn + 16, 0.);
+    std::vector<double4> fpart((size_t)maxn * stride, double4{0, 0, 0, 0});
+    ListView lv{nl0, nn0, stride};
+    emu_launch(k_tb_bond, nb, maxn, FT, N, pos, lv, T, box, aux.data(), aux2.data());
+    emu_launch(k_tb_force<true, false>, nb, maxn, FT, N, pos, fpart.data(), lv, T, box, (const double*)aux.data(), (const double*)aux2.data(), (double*)nullptr);
+    emu_launch(k_tb_reduce, nb, 1, FT, N, (const double4*)fpart.data(), frc, lv);
+    emu_launch(k_tb_force<false, true>, nb, maxn, FT, N, pos, fpart.data(), lv, T, box, (const double*)aux.data(), (const double*)aux2.data(), part.data());
+    *energy = sum_parts(part, nb * maxn, 1.0);
+    return 0;
+}
+
+// ljc / morsec: normals, graphene side (+ T vectors), normal-derivative term, metal side; energy from the graphene list
+int fh_cos(int morse, int N, const double* pos4, double* frc4, size_t stride, const int* nl0, const int* nn0, const int* nl1, const int* nn1, const int* nl2,
+           const int* nn2, const double* p, const double* L, double* gnorm4, double* energy) {
+    const double4* pos = (const double4*)pos4;
+    double4* frc = (double4*)frc4;
+    double4* gnorm = (double4*)gnorm4;
+    BoxD box = make_box(L);
+    CosP P{};
+    int simp;
+    if (!morse) { P.pe = 4. * p[0]; P.sig = p[1]; P.delt = p[2]; P.R1 = p[3]; P.R2 = p[4]; simp = p[5] != 0.; }       // cosp_of(), forces.cu
+    else { P.pe = p[0]; P.r0 = p[1]; P.a = p[2]; P.delt = p[3]; P.R1 = p[4]; P.R2 = p[5]; simp = p[6] != 0.; }
+    const int nb = (N + FT - 1) / FT;
+    std::vector<double4> tvec(stride, double4{0, 0, 0, 0});
+    std::vector<double> part((size_t)nb + 1, 0.);
+    ListView l0{nl0, nn0, stride}, l1{nl1, nn1, stride}, l2{nl2, nn2, stride};
+    emu_launch(k_normals, nb, 1, FT, N, pos, l2, box, simp, gnorm);
+    if (!morse) {
+        emu_launch(k_cos_direct<false, true, true, false, 1>, nb, 1, FT, N, pos, frc, l0, P, box, gnorm, tvec.data(), (double*)nullptr);
+        if (!simp) emu_launch(k_cos_indirect, nb, 1, FT, N, pos, frc, l2, P.pe * P.delt, box, gnorm, tvec.data());
+        emu_launch(k_cos_direct<false, false, true, false, 1>, nb, 1, FT, N, pos, frc, l1, P, box, gnorm, tvec.data(), (double*)nullptr);
+        emu_launch(k_cos_direct<false, true, false, true, 1>, nb, 1, FT, N, pos, frc, l0, P, box, gnorm, tvec.data(), part.data());
+    } else {
+        emu_launch(k_cos_direct<true, true, true, false, 1>, nb, 1, FT, N, pos, frc, l0, P, box, gnorm, tvec.data(), (double*)nullptr);
+        if (!simp) emu_launch(k_cos_indirect, nb, 1, FT, N, pos, frc, l2, 2. * P.pe * P.delt, box, gnorm, tvec.data());
+        emu_launch(k_cos_direct<true, false, true, false, 1>, nb, 1, FT, N, pos, frc, l1, P, box, gnorm, tvec.data(), (double*)nullptr);
+        emu_launch(k_cos_direct<true, true, false, true, 1>, nb, 1, FT, N, pos, frc, l0, P, box, gnorm, tvec.data(), part.data());
+    }
+    *energy = sum_parts(part, nb, 1.0);
+    return 0;
+}
+}
