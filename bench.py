@@ -13,7 +13,7 @@ into the timed region.  N>1 (torchrun, one rank per GPU), weak scaling at 1 000 
   --decomp ensemble         the reference's MPI mode: every rank integrates its own replica, no collective.
 `value` is the atoms of all ranks x steps divided by the slowest rank's device time.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cu_fcc|lj_fluid|ab_gas|graphene_cu]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cu_fcc|lj_fluid|ab_gas|graphene_cu|ensemble_graphene|graphene_rebosc|lj_deposition]
 """
 from __future__ import annotations
 
@@ -49,6 +49,10 @@ def build_case(workload, seed, steps, nx=1):
         return inputs.lj_fluid(n_side=128, seed=seed, steps=steps), "nve", "LJ fluid (lj1g) 128^3 = 2097152 atoms, NVE, dt 0.5 fs, r_cut 7.5, rebuild/20"
     if workload == "ab_gas":
         return inputs.ab_gas(seed=seed), "nvt", "A/B LJ gas 22^3 = 10648 atoms, lj + 2 x lj1g, NVT 100 K, dt 0.5 fs"
+    if workload == "graphene_rebosc":   # numerical forces, 200 x 116 cells = 92 800 C atoms
+        return inputs.graphene_rebosc(cells=(200, 116), seed=seed, steps=steps), "nve", "graphene sheet 200x116 cells = 92800 atoms, rebosc (numerical forces), NVE, dt 0.5 fs"
+    if workload == "lj_deposition":     # a growing group (small system, launch bound)
+        return inputs.lj_deposition(n_side=40, n_layers=6, n_deposit=400, steps=steps, ts2=10 ** 9), "nvt", "LJ substrate 40x40x6 + 400 deposited atoms (change_group_num), NVT 80 K, dt 1 fs"
     if workload == "graphene_cu":
         return inputs.graphene_on_cu(seed=seed), "nvt", "graphene on Cu(111) moire, 11028 atoms, tb + ljc + rjl, NVT 300 K, dt 1 fs"
     raise SystemExit("unknown workload " + workload)

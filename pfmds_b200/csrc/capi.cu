@@ -1031,7 +1031,7 @@ int pfmds_kernel_times(pfmds_ctx* c, int n, double* ms, long long* count) {
 }
 const char* pfmds_kernel_name(int k) {
     static const char* names[KS_COUNT] = {"nl_bin", "nl_build", "lj", "lj1g", "rjl_density", "rjl_force", "tb_bond", "tb_force", "cos_graphene",
-                                          "cos_indirect", "cos_metal", "normals", "kick_drift", "kick", "nhc", "zero_forces", "other"};
+                                          "cos_indirect", "cos_metal", "normals", "kick_drift", "kick", "nhc", "zero_forces", "other", "rebosc_force", "rebosc_energy"};
     return (k >= 0 && k < KS_COUNT) ? names[k] : "";
 }
 

@@ -115,7 +115,7 @@ struct pfmds_ctx {
 // per-kernel device timing (pfmds_set_profiling): CUDA events recorded on the context's stream around
 // every launch of a kernel class, accumulated at synchronisation points
 enum { KS_NL_BIN = 0, KS_NL_BUILD, KS_LJ, KS_LJ1G, KS_RJL_DENSITY, KS_RJL_FORCE, KS_TB_BOND, KS_TB_FORCE, KS_COS_GRAPHENE, KS_COS_INDIRECT,
-       KS_COS_METAL, KS_NORMALS, KS_KICK_DRIFT, KS_KICK, KS_NHC, KS_ZERO_FORCES, KS_OTHER, KS_COUNT };
+       KS_COS_METAL, KS_NORMALS, KS_KICK_DRIFT, KS_KICK, KS_NHC, KS_ZERO_FORCES, KS_OTHER, KS_REBOSC_FORCE, KS_REBOSC_ENERGY, KS_COUNT };
 
 void prof_flush(pfmds_ctx* c);
 struct KTimer {

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(RT) k_rebosc_numforce(int N, const double4* __
 }
 void rebosc_forces(pfmds_ctx* c, Inter& it) {
     const int N = c->N;
-    KTimer kt(c, KS_OTHER);
+    KTimer kt(c, KS_REBOSC_FORCE);
     k_rebosc_numforce<<<(3 * N + RT - 1) / RT, RT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(c->stride), it.reb, c->box, c->orig, c->err);
     c->launches += 1;
     CK(cudaGetLastError());
@@ -33,7 +33,7 @@ void rebosc_forces(pfmds_ctx* c, Inter& it) {
 // block partials into c->part; returns their number
 int rebosc_energy_partials(pfmds_ctx* c, Inter& it) {
     const int N = c->N, nb = (N + RT - 1) / RT;
-    KTimer kt(c, KS_OTHER);
+    KTimer kt(c, KS_REBOSC_ENERGY);
     k_rebosc_energy<<<nb, RT, 0, c->st>>>(N, c->pos, it.nl[0].view(c->stride), it.reb, c->box, c->part);
     c->launches += 1;
     CK(cudaGetLastError());

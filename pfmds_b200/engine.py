@@ -244,7 +244,7 @@ class Engine:
 
     def kernel_times(self):
         """{kernel class: (total ms, launches)} measured with CUDA events on the context's stream."""
-        n = 17
+        n = 32
         ms = np.zeros(n)
         cnt = np.zeros(n, np.int64)
         self._call("kernel_times", self._ctx, n, _d(ms), cnt.ctypes.data_as(C.POINTER(C.c_longlong)))

@@ -110,7 +110,7 @@ def lj_deposition(n_side=6, n_layers=3, n_deposit=8, spacing=3.8, seed=11, tempe
     box = np.array([n_side * spacing, n_side * spacing, 60.0])
     top = 4.0 + (n_layers - 1) * spacing
     k = np.arange(n_deposit)
-    dep = np.stack([(1.7 + 2.9 * k) % box[0], (2.3 + 5.3 * k) % box[1], top + 4.5 + 0.9 * k], -1)
+    dep = np.stack([(1.7 + 2.9 * k) % box[0], (2.3 + 5.3 * k) % box[1], top + 4.5 + 0.9 * (k % 30)], -1)
     pos = np.concatenate([lay, dep])
     ns = len(lay)
     names = ["S"] * ns + ["D"] * n_deposit
