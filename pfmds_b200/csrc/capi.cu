@@ -549,6 +549,8 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         c->timers_on = tm && tm[0] == '1';
         const char* gr = std::getenv("PFMDS_GRAPHS");
         c->use_graphs = gr ? gr[0] == '1' : n_atoms < 200000;
+        const char* lp = std::getenv("PFMDS_LJ1G_PIPE");
+        c->lj1g_pipe = lp && lp[0] == '1';
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     });
 }

@@ -337,6 +337,61 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __
     if (n > 0 && sub == 0) add_force(frc, i, fx, fy, fz);
 }
 
+// ---- lj1g, pipelined variant (opt-in: PFMDS_LJ1G_PIPE=1; unmeasured on hardware so far) ----------------
+// Same sums as k_lj1g<F, E, 1>, restructured like the rjl kernels: ping-pong prefetch of the row indices and of the 32-byte
+// records, the conservative exact wrap test instead of three unconditional selects, 1/r^2 and sqrt from the hardware seeds plus
+// one third-order step (mathx.cuh) instead of the CUDA library's division and square root with their slow-path calls.
+template <bool E>
+__device__ __forceinline__ void lj1g_pair(const double4& pi, const double4& pj, const LJ1Gp& P, double R12, double R22, double iw, const BoxD& box,
+                                          int mhh, double& fx, double& fy, double& fz, double& e) {
+    double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+    wrap3(dx, dy, dz, box, mhh);
+    double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    if (r2 < R22) {  // beyond R2 the quintic switch and its derivative are exactly 0
+        double invr2 = mx::rcp_fast(r2);
+        double U = invr2 * invr2 * invr2;
+        double f = 1.0, dfr = 0.0;
+        if (r2 > R12) {
+            double r = r2 * mx::rsqrt_fast(r2);
+            double x = (r - P.R1) * iw, x2 = x * x;
+            f = 1. + x2 * x * (-10. + 15. * x - 6. * x2);
+            dfr = r * x2 * (-30. + 60. * x - 30. * x2);
+        }
+        if (E) e += U * (P.c12 * U - P.c6) * f;
+        double c = U * invr2 * ((P.c12t12 * U - P.c6t6) * f - (P.c12 * U - P.c6) * dfr);
+        fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
+    }
+}
+template <bool E>
+__global__ void __launch_bounds__(FT) k_lj1g_pipe(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJ1Gp P, BoxD box,
+                                                  WrapC W, double* part) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0, fx = 0, fy = 0, fz = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = ld256_nc(&pos[i]);
+        const double R12 = P.R1 * P.R1, R22 = P.R2 * P.R2, iw = 1.0 / (P.R2 - P.R1);
+        const int* rp = lv.nlist + i;
+        const size_t st = lv.stride;
+        int j1 = n > 1 ? rp[st] : rp[0];
+        double4 a = ld256_nc(&pos[rp[0]]);
+        int p = 0;
+        for (; p + 1 < n; p += 2) {
+            double4 b = ld256_nc(&pos[j1]);
+            int j2 = p + 2 < n ? rp[2 * st] : j1;
+            int j3 = p + 3 < n ? rp[3 * st] : j1;
+            rp += 2 * st;
+            lj1g_pair<E>(pi, a, P, R12, R22, iw, box, W.min_half_hi, fx, fy, fz, e);
+            a = ld256_nc(&pos[j2]);
+            lj1g_pair<E>(pi, b, P, R12, R22, iw, box, W.min_half_hi, fx, fy, fz, e);
+            j1 = j3;
+        }
+        if (p < n) lj1g_pair<E>(pi, a, P, R12, R22, iw, box, W.min_half_hi, fx, fy, fz, e);
+        add_force(frc, i, fx, fy, fz);
+    }
+    if (E) store_partial(e, part);
+}
+
 // ---- tb : TersoffBrenner.f90:26-150 -------------------------------------------------------------
 __device__ __forceinline__ double tb_G(double c1, const TBp& T) { return 1. + T.c02 / T.d02 - T.c02 / (T.d02 + c1 * c1); }  // c1 = 1+cos
 
@@ -648,6 +703,13 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         c->launches += 2;
         break;
     case K_LJ1G:
+        if (c->lj1g_pipe && !small) {  // opt-in pipelined variant (thread per atom)
+            KTimer kt(c, KS_LJ1G);
+            if (with_energy) { k_lj1g_pipe<true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), epart); e_parts = nb; e_scale = 0.5; }
+            else k_lj1g_pipe<false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), nullptr);
+            c->launches += 1;
+            break;
+        }
         if (with_energy) {
             KTimer kt(c, KS_LJ1G);
             if (small) k_lj1g<true, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);

@@ -37,7 +37,7 @@ int fh_lj(int N, const double* pos4, double* frc4, size_t stride, const int* nl0
     return 0;
 }
 
-int fh_lj1g(int N, const double* pos4, double* frc4, size_t stride, const int* nl0, const int* nn0, const double* p, const double* L, double* energy) {
+int fh_lj1g(int N, const double* pos4, double* frc4, size_t stride, const int* nl0, const int* nn0, const double* p, const double* L, double* energy, int pipelined) {
     const double4* pos = (const double4*)pos4;
     double4* frc = (double4*)frc4;
     BoxD box = make_box(L);
@@ -45,7 +45,8 @@ int fh_lj1g(int N, const double* pos4, double* frc4, size_t stride, const int* n
     LJ1Gp P{p[2], p[3], 4. * p[0] * s6, 4. * p[0] * s12, 6. * 4. * p[0] * s6, 12. * 4. * p[0] * s12};
     const int nb = (N + FT - 1) / FT;
     std::vector<double> part((size_t)nb + 1, 0.);
-    emu_launch(k_lj1g<true, true, 1>, nb, 1, FT, N, pos, frc, ListView{nl0, nn0, stride}, P, box, part.data());
+    if (pipelined) emu_launch(k_lj1g_pipe<true>, nb, 1, FT, N, pos, frc, ListView{nl0, nn0, stride}, P, box, wrap_consts(box), part.data());
+    else emu_launch(k_lj1g<true, true, 1>, nb, 1, FT, N, pos, frc, ListView{nl0, nn0, stride}, P, box, part.data());
     *energy = sum_parts(part, nb, 0.5);
     return 0;
 }

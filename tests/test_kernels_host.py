@@ -89,7 +89,7 @@ def ptr(a, t):
     return a.ctypes.data_as(t)
 
 
-def run_case(L, case, seed=1, rjl_overwrite_first=False):
+def run_case(L, case, seed=1, rjl_overwrite_first=False, lj1g_pipe=False):
     lay = DeviceLayout(case, seed)
     frc4 = np.zeros((lay.n, 4))
     energies = []
@@ -105,7 +105,8 @@ def run_case(L, case, seed=1, rjl_overwrite_first=False):
                     ptr(prm, DP), ptr(lay.box, DP), C.byref(e))
         elif it["name"] == "lj1g":
             l0 = lay.ell(*lists[0][:4])
-            L.fh_lj1g(lay.n, ptr(lay.pos4, DP), ptr(frc4, DP), C.c_size_t(lay.stride), ptr(l0[0], IP), ptr(l0[1], IP), ptr(prm, DP), ptr(lay.box, DP), C.byref(e))
+            L.fh_lj1g(lay.n, ptr(lay.pos4, DP), ptr(frc4, DP), C.c_size_t(lay.stride), ptr(l0[0], IP), ptr(l0[1], IP), ptr(prm, DP), ptr(lay.box, DP), C.byref(e),
+                      int(lj1g_pipe))
         elif it["name"] == "rjl":
             l0 = lay.ell(*lists[0][:4])
             L.fh_rjl(lay.n, ptr(lay.pos4, DP), ptr(frc4, DP), C.c_size_t(lay.stride), ptr(l0[0], IP), ptr(l0[1], IP), ptr(prm, DP), ptr(lay.box, DP),
@@ -139,6 +140,21 @@ def test_emulated_kernels_match_the_oracle(oracle_lib, kernels, name):
     assert rel_err(eh, eo) < RTOL
     fh2, eh2 = run_case(kernels, case, seed=7)               # another slot permutation / row order: only rounding changes
     assert rel_err(fh2, fh) < 1e-12 and rel_err(eh2, eh) < 1e-12
+
+
+def test_emulated_lj1g_pipelined_variant(oracle_lib, kernels):
+    """The opt-in pipelined lj1g kernel (PFMDS_LJ1G_PIPE=1): same sums with 1/r^2 and sqrt from mathx.cuh; oracle parity and
+    agreement with the default kernel far inside the 1e-9 bar.  Odd and even row lengths, rows of one entry, the switch zone."""
+    for case in (small_cases()["ab_gas"], inputs.lj_fluid(n_side=7, period=5), inputs.lj_deposition()):
+        o = oracle(case)
+        o.advance(case["integrators"][0][0], case["integrators"][0][1], 0, 1)
+        fo, eo = o.download()[2], o.energies()[0]
+        if case.get("changes"):
+            case = dict(case, groups=[["S", "D"], ["S", "#"], ["S", "#"], ["#", "#"]])     # the emulated layout has no group%N: group 3 = substrate at step 0
+        fa, ea = run_case(kernels, case)
+        fb, eb = run_case(kernels, case, lj1g_pipe=True)
+        assert rel_err(fb, fo) < RTOL and rel_err(eb, eo) < RTOL
+        assert rel_err(fb, fa) < 1e-13 and rel_err(eb, ea) < 1e-13
 
 
 def test_emulated_rjl_store_variant_is_bitwise_the_accumulate_variant(kernels):

@@ -1,0 +1,30 @@
+"""Opt-in kernel variants that have not been timed on hardware yet: they must give the default kernels'
+results.  (Named zz: runs after the parity tests.)"""
+import os
+
+import numpy as np
+import pytest
+
+from pfmds_b200 import inputs
+from util import gpu, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pipelined_lj1g_kernel_matches_the_default_kernel():
+    case = inputs.lj_fluid(n_side=47, period=5)                    # 103 823 atoms: the thread-per-atom kernels
+    a = gpu(case)
+    os.environ["PFMDS_LJ1G_PIPE"] = "1"
+    try:
+        b = gpu(case)
+    finally:
+        del os.environ["PFMDS_LJ1G_PIPE"]
+    for e in (a, b):
+        e.advance("nve", 0.5, 0, 1, with_energy=True)
+    fa, fb = a.download()[2], b.download()[2]
+    assert np.abs(fa).max() > 1e-3 and rel_err(fb, fa) < 1e-12
+    assert np.allclose(a.energies()[0], b.energies()[0], rtol=1e-12, atol=0)
+    for e in (a, b):
+        e.advance("nve", 0.5, 1, 12)
+    assert np.abs(a.download()[0] - b.download()[0]).max() < 1e-10
+    assert np.allclose(a.energies()[0], b.energies()[0], rtol=1e-11, atol=0)     # energy_interaction keeps the default kernel
