@@ -314,7 +314,7 @@ bool apply_group_changes(pfmds_ctx* c, int step) {
             c->energy_valid = false;
         }
         changed = true;
-        k_group_resize<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->orig, c->d_grank[g], 1u << g, c->cur_n[g], c->gmask);
+        LAUNCH((k_group_resize), (c->N + 255) / 256, 256, c->st, c->N, c->orig, c->d_grank[g], 1u << g, c->cur_n[g], c->gmask);
         c->launches += 1;
     }
     return changed;
@@ -409,8 +409,12 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bo
 __global__ void k_max_int(int n, const int* __restrict__ a, int* out) {
     int m = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, a[i]);
+#ifdef __CUDACC__
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+#else  // host replay: no lane exchange, every thread contributes
+    atomicMax(out, m);
+#endif
 }
 
 }  // namespace
@@ -443,6 +447,7 @@ KTimer::~KTimer() {
     c->prof_used += 1;
 }
 
+#ifdef __CUDACC__
 // ---- peak micro-benchmarks (the roofline denominators MEASURED_PEAKS.json does not carry) ----------
 // 8 independent DFMA chains per thread; 2 flop per DFMA.
 __global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, double* out) {
@@ -483,14 +488,19 @@ __global__ void k_math_selftest(int n, double* out) {
     atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(e_rs));
     atomicMax((unsigned long long*)&out[3], (unsigned long long)__double_as_longlong(e_seed));
 }
+#endif  // __CUDACC__
 __global__ void k_copy(size_t n, const double4* __restrict__ a, double4* __restrict__ b) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
 }
 __global__ void k_sum_int(int n, const int* __restrict__ a, unsigned long long* out) {
     unsigned long long s = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)a[i];
+#ifdef __CUDACC__
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+#else  // host replay: no lane exchange, every thread contributes
+    atomicAdd(out, s);
+#endif
 }
 __global__ void k_upload_scatter(int N, const int* __restrict__ orig, const double* __restrict__ hp, const double* __restrict__ hv,
                                  double4* __restrict__ pos, double4* __restrict__ vel) {
@@ -549,6 +559,9 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         c->timers_on = tm && tm[0] == '1';
         const char* gr = std::getenv("PFMDS_GRAPHS");
         c->use_graphs = gr ? gr[0] == '1' : n_atoms < 200000;
+#ifndef __CUDACC__
+        c->use_graphs = false;  // host replay: no stream capture
+#endif
         const char* lp = std::getenv("PFMDS_LJ1G_PIPE");
         c->lj1g_pipe = lp && lp[0] == '1';
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
@@ -765,7 +778,7 @@ int pfmds_diagnostics(pfmds_ctx* c, double fs[3], double mc[3], double mcv[3], d
             CK(cudaMemsetAsync(d_max, 0, sizeof(int) * nl_total, c->st));
             size_t k = 0;
             for (auto& it : c->inter)
-                for (int j = 0; j < it.nl_n; ++j, ++k) { k_max_int<<<64, 256, 0, c->st>>>(c->N, it.nl[j].nnum, d_max + k); c->launches += 1; }
+                for (int j = 0; j < it.nl_n; ++j, ++k) { LAUNCH((k_max_int), 64, 256, c->st, c->N, it.nl[j].nnum, d_max + k); c->launches += 1; }
             if (c->slab) slab_allreduce_max_int(c, d_max, (int)nl_total);
             CK(cudaMemcpyAsync(hmax.data(), d_max, sizeof(int) * nl_total, cudaMemcpyDeviceToHost, c->st));
         }
@@ -902,7 +915,7 @@ int pfmds_upload(pfmds_ctx* c, const double* pos, const double* vel) {
         double *dp = nullptr, *dv = nullptr;
         if (pos) { CK(cudaMallocAsync(&dp, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
         if (vel) { CK(cudaMallocAsync(&dv, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
-        k_upload_scatter<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->orig, dp, dv, c->pos, c->vel);
+        LAUNCH((k_upload_scatter), (c->N + 255) / 256, 256, c->st, c->N, c->orig, dp, dv, c->pos, c->vel);
         c->launches += 1;
         if (dp) CK(cudaFreeAsync(dp, c->st));
         if (dv) CK(cudaFreeAsync(dv, c->st));
@@ -963,7 +976,7 @@ int pfmds_restore_state(pfmds_ctx* c, const double* pos, const double* vel, cons
             CK(cudaMalloc(&dp, sizeof(double) * n3)); CK(cudaMalloc(&dv, sizeof(double) * n3));
             CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
             CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
-            k_upload_scatter<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->orig, dp, dv, c->pos, c->vel);
+            LAUNCH((k_upload_scatter), (c->N + 255) / 256, 256, c->st, c->N, c->orig, dp, dv, c->pos, c->vel);
             c->launches += 1;
             CK(cudaStreamSynchronize(c->st));
             cudaFree(dp); cudaFree(dv);
@@ -982,7 +995,7 @@ int pfmds_restore_state(pfmds_ctx* c, const double* pos, const double* vel, cons
             if (n != c->cur_n[g]) {
                 if (!c->d_grank[g]) fail(PFMDS_ERR_INVALID, "error: the checkpoint changes a group that has no change entry");
                 c->cur_n[g] = n;
-                k_group_resize<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->orig, c->d_grank[g], 1u << g, n, c->gmask);
+                LAUNCH((k_group_resize), (c->N + 255) / 256, 256, c->st, c->N, c->orig, c->d_grank[g], 1u << g, n, c->gmask);
                 c->launches += 1;
             }
         }
@@ -1004,7 +1017,7 @@ int pfmds_pair_count(pfmds_ctx* c, int inter, int list, long long* pairs) {
         unsigned long long* d = nullptr;
         CK(cudaMalloc(&d, sizeof(unsigned long long)));
         CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->st));
-        k_sum_int<<<256, 256, 0, c->st>>>(c->N, c->inter[(size_t)inter].nl[list].nnum, d);
+        LAUNCH((k_sum_int), 256, 256, c->st, c->N, c->inter[(size_t)inter].nl[list].nnum, d);
         if (c->slab) slab_allreduce_sum_ll(c, d, 1);
         unsigned long long h = 0;
         CK(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->st));
@@ -1063,20 +1076,29 @@ int pfmds_timer_stop(pfmds_ctx* c, double* ms) {
 // Max errors of the device elementary functions: [0] exp relative, [1] switch/sincos absolute,
 // [2] rsqrt relative, [3] raw MUFU.RSQ64H seed relative.
 int pfmds_selftest_math(int device, double err[4]) {
+#ifndef __CUDACC__
+    (void)device; (void)err;
+    return PFMDS_ERR_UNSUPPORTED;  // host replay of the test suite: there is no device to test
+#else
     try {
         CK(cudaSetDevice(device));
         double* d = nullptr;
         CK(cudaMalloc(&d, 4 * sizeof(double)));
         CK(cudaMemset(d, 0, 4 * sizeof(double)));
-        k_math_selftest<<<256, 256>>>(1 << 22, d);
+        LAUNCH((k_math_selftest), 256, 256, 0, 1 << 22, d);
         CK(cudaMemcpy(err, d, 4 * sizeof(double), cudaMemcpyDeviceToHost));
         cudaFree(d);
         return PFMDS_OK;
     } catch (...) { return PFMDS_ERR_CUDA; }
+#endif
 }
 
 // FP64 FMA peak (TFLOP/s) and device-to-device copy bandwidth (GB/s, read+write) of `device`.
 int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs) {
+#ifndef __CUDACC__
+    (void)device; (void)dfma_tflops; (void)copy_gbs;
+    return PFMDS_ERR_UNSUPPORTED;
+#else
     try {
         CK(cudaSetDevice(device));
         cudaDeviceProp pr;
@@ -1089,7 +1111,7 @@ int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs) {
         double best = 0;
         for (int rep = 0; rep < 5; ++rep) {
             CK(cudaEventRecord(e0));
-            k_dfma_peak<<<blocks, threads>>>(iters, 1.0 + rep, d);
+            LAUNCH((k_dfma_peak), blocks, threads, 0, iters, 1.0 + rep, d);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms = 0;
@@ -1107,7 +1129,7 @@ int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs) {
             double bw = 0;
             for (int rep = 0; rep < 5; ++rep) {
                 CK(cudaEventRecord(e0));
-                k_copy<<<pr.multiProcessorCount * 16, 512>>>(n, a, b);
+                LAUNCH((k_copy), pr.multiProcessorCount * 16, 512, 0, n, a, b);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
                 float ms = 0;
@@ -1121,6 +1143,7 @@ int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs) {
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return PFMDS_OK;
     } catch (...) { return PFMDS_ERR_CUDA; }
+#endif
 }
 
 
@@ -1275,6 +1298,10 @@ int pfmds_destroy(pfmds_ctx* c) {
     delete c;
     return PFMDS_OK;
 }
+#ifdef __CUDACC__
 const char* pfmds_version(void) { return "pfmds_b200 0.1 (sm_100a)"; }
+#else
+const char* pfmds_version(void) { return "pfmds_b200 0.1 HOST REPLAY of the device code (test suite only, not a product path)"; }
+#endif
 
 }  // extern "C"

@@ -16,8 +16,14 @@
 #include <stdint.h>
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
+// every kernel launch of the library goes through this macro (the host replay of the test suite substitutes a serial loop)
+#define LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
 #else
 #include "host_emu.hpp"  // test support: the kernels of this directory compiled for the host (tests/*_host.cpp), never part of the product
+#endif
+
+#if defined(__CUDACC__) || defined(PFMDS_EMU_LIB)
+#define PFMDS_HAVE_CTX 1  // the context and the launch wrappers exist: the product (nvcc) and the emulated library of the test suite
 #endif
 
 #include "mathx.cuh"

@@ -1,7 +1,9 @@
 // pfmds_b200 — host-side context behind the opaque pfmds_ctx of include/pfmds_b200.h, and the
 // launch wrappers the C ABI calls (defined in nl.cu, forces.cu, integrate.cu).
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#endif
 
 #include <string>
 #include <vector>

@@ -11,7 +11,7 @@
 #include <cstring>
 #include <string>
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(PFMDS_EMU_LIB)
 #include "ctx.hpp"
 #else
 #include "common.cuh"  // host emulation of the kernels (tests/forces_host.cpp): no context, no launchers
@@ -47,7 +47,9 @@ __device__ __forceinline__ double split_sum(double v) {
     return v;
 }
 #define SMALL_SPLIT 8
+#ifndef SMALL_N
 #define SMALL_N 100000
+#endif
 
 // per-block partial of the per-thread energy; the final sum is done by k_sum_partials in block order
 __device__ __forceinline__ void store_partial(double e, double* part) {
@@ -652,12 +654,12 @@ __global__ void k_zero_group(int N, double4* __restrict__ frc, const uint32_t* _
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N && (gmask[i] & bit)) frc[i] = make_double4(0., 0., 0., 0.);
 }
-#ifdef __CUDACC__  // ---- launchers (host side of the product) ----------------------------------------
+#ifdef PFMDS_HAVE_CTX  // ---- launchers (host side of the library) ----------------------------------------
 void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
     if (c->first_overwrites && c->N >= SMALL_N) return;  // the first force kernel stores instead of accumulating
     KTimer kt(c, KS_ZERO_FORCES);
     if (c->zero_all) { CK(cudaMemsetAsync(c->frc, 0, sizeof(double4) * (size_t)c->N, c->st)); return; }
-    k_zero_group<<<(c->N + 255) / 256, 256, 0, c->st>>>(c->N, c->frc, c->gmask, 1u << (c->all_atoms - 1));
+    LAUNCH((k_zero_group), (c->N + 255) / 256, 256, c->st, c->N, c->frc, c->gmask, 1u << (c->all_atoms - 1));
     c->launches += 1;
 }
 
@@ -674,7 +676,7 @@ void normals_interaction(pfmds_ctx* c, int k) {  // update_norm_in_graphene, md_
     const int N = c->N, nb = (N + FT - 1) / FT;
     int simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
     KTimer kt(c, KS_NORMALS);
-    k_normals<<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[2].view(c->stride), c->box, simp, it.gnorm);
+    LAUNCH((k_normals), nb, FT, c->st, N, c->pos, it.nl[2].view(c->stride), c->box, simp, it.gnorm);
     c->launches += 1;
 }
 
@@ -693,30 +695,30 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     case K_LJ:
         if (with_energy) {
             KTimer kt(c, KS_LJ);
-            if (small) k_lj<true, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, epart);
-            else k_lj<true, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, epart);
+            if (small) LAUNCH((k_lj<true, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, epart);
+            else LAUNCH((k_lj<true, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, epart);
             e_parts = small ? nbs : nb;
         } else
-        { KTimer kt(c, KS_LJ); if (small) k_lj<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); else k_lj<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); }
-        if (e_parts) { k_sum_partials<<<1, 1024, 0, c->st>>>(e_parts, c->part, 1.0, c->energy + k); c->launches += 1; if (c->slab) slab_allreduce_sum(c, c->energy + k, 1); e_parts = 0; with_energy = false; }
-        { KTimer kt(c, KS_LJ); if (small) k_lj<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); else k_lj<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); }
+        { KTimer kt(c, KS_LJ); if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); else LAUNCH((k_lj<true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); }
+        if (e_parts) { LAUNCH((k_sum_partials), 1, 1024, c->st, e_parts, c->part, 1.0, c->energy + k); c->launches += 1; if (c->slab) slab_allreduce_sum(c, c->energy + k, 1); e_parts = 0; with_energy = false; }
+        { KTimer kt(c, KS_LJ); if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); else LAUNCH((k_lj<true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); }
         c->launches += 2;
         break;
     case K_LJ1G:
         if (c->lj1g_pipe && !small) {  // opt-in pipelined variant (thread per atom)
             KTimer kt(c, KS_LJ1G);
-            if (with_energy) { k_lj1g_pipe<true><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), epart); e_parts = nb; e_scale = 0.5; }
-            else k_lj1g_pipe<false><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), nullptr);
+            if (with_energy) { LAUNCH((k_lj1g_pipe<true>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), epart); e_parts = nb; e_scale = 0.5; }
+            else LAUNCH((k_lj1g_pipe<false>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), nullptr);
             c->launches += 1;
             break;
         }
         if (with_energy) {
             KTimer kt(c, KS_LJ1G);
-            if (small) k_lj1g<true, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);
-            else k_lj1g<true, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);
+            if (small) LAUNCH((k_lj1g<true, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);
+            else LAUNCH((k_lj1g<true, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);
             e_parts = small ? nbs : nb; e_scale = 0.5;
         } else
-        { KTimer kt(c, KS_LJ1G); if (small) k_lj1g<true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); else k_lj1g<true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); }
+        { KTimer kt(c, KS_LJ1G); if (small) LAUNCH((k_lj1g<true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); else LAUNCH((k_lj1g<true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); }
         c->launches += 1;
         break;
     case K_RJL:
@@ -727,18 +729,18 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         {
             KTimer kt(c, KS_RJL_DENSITY);
             if (with_energy) {
-                if (small) k_rjl_density_split<true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, epart);
-                else k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, epart, fused ? slab_dev(c, 1) : SlabDev{});
+                if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, it.nl[0].view(st), C, c->box, W, epart);
+                else LAUNCH((k_rjl_density<true>), nb, FT, c->st, N, c->pos, it.nl[0].view(st), C, c->box, W, epart, fused ? slab_dev(c, 1) : SlabDev{});
                 e_parts = small ? nbs : nb;
             } else
-            if (small) k_rjl_density_split<false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr);
-            else k_rjl_density<false><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr, fused ? slab_dev(c, 1) : SlabDev{});
+            if (small) LAUNCH((k_rjl_density_split<false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr);
+            else LAUNCH((k_rjl_density<false>), nb, FT, c->st, N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr, fused ? slab_dev(c, 1) : SlabDev{});
         }
         if (c->slab && !fused) slab_exchange(c, 1);  // ghost 1/Eb from their owners
         {
             KTimer kt(c, KS_RJL_FORCE);
-            if (small) k_rjl_force_split<SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W);
-            else k_rjl_force<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, (k == 0 && c->first_overwrites && N >= SMALL_N) ? 1 : 0);
+            if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W);
+            else LAUNCH((k_rjl_force), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, (k == 0 && c->first_overwrites && N >= SMALL_N) ? 1 : 0);
         }
     }
         c->launches += 2;
@@ -749,11 +751,11 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     case K_TB:
     {
         dim3 grid(nb, it.nl[0].maxn);
-        { KTimer kt(c, KS_TB_BOND); k_tb_bond<<<grid, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2); }
+        { KTimer kt(c, KS_TB_BOND); LAUNCH((k_tb_bond), grid, FT, c->st, N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2); }
         {
             KTimer kt(c, KS_TB_FORCE);
-            k_tb_force<true, false><<<grid, FT, 0, c->st>>>(N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, nullptr);
-            k_tb_reduce<<<nb, FT, 0, c->st>>>(N, it.fpart, c->frc, it.nl[0].view(st));
+            LAUNCH((k_tb_force<true, false>), grid, FT, c->st, N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, nullptr);
+            LAUNCH((k_tb_reduce), nb, FT, c->st, N, it.fpart, c->frc, it.nl[0].view(st));
         }
         c->launches += 3;
     }
@@ -763,13 +765,13 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         CosP P = cosp_of(it);
         bool simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
         if (it.kind == K_LJC) {
-            { KTimer kt(c, KS_COS_GRAPHENE); if (small) k_cos_direct<false, true, true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else k_cos_direct<false, true, true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
-            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec); }
-            { KTimer kt(c, KS_COS_METAL); if (small) k_cos_direct<false, false, true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else k_cos_direct<false, false, true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_GRAPHENE); if (small) LAUNCH((k_cos_direct<false, true, true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, true, true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); LAUNCH((k_cos_indirect), nb, FT, c->st, N, c->pos, c->frc, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec); }
+            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<false, false, true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, false, true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         } else {
-            { KTimer kt(c, KS_COS_GRAPHENE); if (small) k_cos_direct<true, true, true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else k_cos_direct<true, true, true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
-            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); k_cos_indirect<<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec); }
-            { KTimer kt(c, KS_COS_METAL); if (small) k_cos_direct<true, false, true, false, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else k_cos_direct<true, false, true, false, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_GRAPHENE); if (small) LAUNCH((k_cos_direct<true, true, true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, true, true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); LAUNCH((k_cos_indirect), nb, FT, c->st, N, c->pos, c->frc, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec); }
+            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<true, false, true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, false, true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         }
         c->launches += simp ? 2 : 3;
         break;
@@ -777,7 +779,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     }
     if (with_energy) {
         if (e_parts) {
-            k_sum_partials<<<1, 1024, 0, c->st>>>(e_parts, c->part, e_scale, c->energy + k);
+            LAUNCH((k_sum_partials), 1, 1024, c->st, e_parts, c->part, e_scale, c->energy + k);
             c->launches += 1;
             if (c->slab) slab_allreduce_sum(c, c->energy + k, 1);
         } else {
@@ -796,28 +798,28 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     const int nbs = (int)(((size_t)N * SMALL_SPLIT + FT - 1) / FT);
     int nparts = small ? nbs : nb;
     switch (it.kind) {
-    case K_LJ: if (small) k_lj<false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); else k_lj<false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
-    case K_LJ1G: if (small) k_lj1g<false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); else k_lj1g<false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
+    case K_LJ: if (small) LAUNCH((k_lj<false, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); else LAUNCH((k_lj<false, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
+    case K_LJ1G: if (small) LAUNCH((k_lj1g<false, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); else LAUNCH((k_lj1g<false, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
     case K_RJL: {
-        if (small) k_rjl_density_split<true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
-        else k_rjl_density<true><<<nb, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part, SlabDev{});
+        if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
+        else LAUNCH((k_rjl_density<true>), nb, FT, c->st, N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part, SlabDev{});
         break;
     }
     case K_REBOSC: nparts = rebosc_energy_partials(c, it); c->launches -= 1; break;
     case K_TB: {
         dim3 grid(nb, it.nl[0].maxn);
-        k_tb_bond<<<grid, FT, 0, c->st>>>(N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2);
-        k_tb_force<false, true><<<grid, FT, 0, c->st>>>(N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, c->part);
+        LAUNCH((k_tb_bond), grid, FT, c->st, N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2);
+        LAUNCH((k_tb_force<false, true>), grid, FT, c->st, N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, c->part);
         nparts = nb * it.nl[0].maxn;
         c->launches += 1;
         break;
     }
-    case K_LJC: if (small) k_cos_direct<false, true, false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); else k_cos_direct<false, true, false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
-    case K_MORSEC: if (small) k_cos_direct<true, true, false, true, SMALL_SPLIT><<<nbs, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); else k_cos_direct<true, true, false, true, 1><<<nb, FT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
+    case K_LJC: if (small) LAUNCH((k_cos_direct<false, true, false, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); else LAUNCH((k_cos_direct<false, true, false, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
+    case K_MORSEC: if (small) LAUNCH((k_cos_direct<true, true, false, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); else LAUNCH((k_cos_direct<true, true, false, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), cosp_of(it), c->box, it.gnorm, it.tvec, c->part); break;
     }
-    k_sum_partials<<<1, 1024, 0, c->st>>>(nparts, c->part, scale, c->energy + k);
+    LAUNCH((k_sum_partials), 1, 1024, c->st, nparts, c->part, scale, c->energy + k);
     c->launches += 2;
     if (c->slab) slab_allreduce_sum(c, c->energy + k, 1);
     CK(cudaGetLastError());
 }
-#endif  // __CUDACC__
+#endif  // PFMDS_HAVE_CTX

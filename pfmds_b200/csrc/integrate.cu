@@ -22,7 +22,7 @@ __global__ void k_check_positions(int N, const double4* __restrict__ pos, const 
     if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
 }
 void integ_check_positions(pfmds_ctx* c) {
-    k_check_positions<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->orig, c->box, c->err);
+    LAUNCH((k_check_positions), (c->N + IT - 1) / IT, IT, c->st, c->N, c->pos, c->orig, c->box, c->err);
     c->launches += 1;
 }
 
@@ -34,7 +34,7 @@ __global__ void k_invert_z(int N, const double4* __restrict__ pos, double4* __re
     if ((z > zl && z < (zl + zh) / 2 && vz > 0.) || (z < zh && z > (zl + zh) / 2 && vz < 0.)) vel[i].z = -vz;
 }
 void integ_invert_z(pfmds_ctx* c) {
-    k_invert_z<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, 0.8 * c->box.L[2], 0.9 * c->box.L[2]);
+    LAUNCH((k_invert_z), (c->N + IT - 1) / IT, IT, c->st, c->N, c->pos, c->vel, 0.8 * c->box.L[2], 0.9 * c->box.L[2]);
     c->launches += 1;
 }
 
@@ -58,8 +58,8 @@ __global__ void k_sum_to(int n, const double* __restrict__ part, double* out) {
     if (threadIdx.x == 0) *out = s;
 }
 void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out) {
-    k_ke_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->gmask, 1u << (group - 1), c->part);
-    k_sum_to<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, d_out);
+    LAUNCH((k_ke_partial), RED_BLOCKS, IT, c->st, c->N, c->vel, c->gmask, 1u << (group - 1), c->part);
+    LAUNCH((k_sum_to), 1, 1024, c->st, RED_BLOCKS, c->part, d_out);
     c->launches += 2;
     if (c->slab) slab_allreduce_sum(c, d_out, 1);
 }
@@ -123,15 +123,15 @@ __global__ void k_scale(int N, double4* __restrict__ vel, const uint32_t* __rest
 void integ_nhc_half(pfmds_ctx* c, Nhc& t, double dt) {
     uint32_t bit = 1u << (t.group - 1);
     KTimer kt(c, KS_NHC);
-    k_ke_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->gmask, bit, c->part);
+    LAUNCH((k_ke_partial), RED_BLOCKS, IT, c->st, c->N, c->vel, c->gmask, bit, c->part);
     if (c->slab) {  // sum over ranks first, then every rank runs the same chain update on the same number
-        k_sum_to<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, c->red + 48);
+        LAUNCH((k_sum_to), 1, 1024, c->st, RED_BLOCKS, c->part, c->red + 48);
         slab_allreduce_sum(c, c->red + 48, 1);
-        k_nhc<<<1, 32, 0, c->st>>>(1, c->red + 48, t.state, t.M, t.L, t.temperature, dt / 2, dt / 4, dt / 8);
+        LAUNCH((k_nhc), 1, 32, c->st, 1, c->red + 48, t.state, t.M, t.L, t.temperature, dt / 2, dt / 4, dt / 8);
         c->launches += 1;
     } else
-    k_nhc<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, t.state, t.M, t.L, t.temperature, dt / 2, dt / 4, dt / 8);
-    k_scale<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, bit, t.state + 3 * t.M);
+    LAUNCH((k_nhc), 1, 1024, c->st, RED_BLOCKS, c->part, t.state, t.M, t.L, t.temperature, dt / 2, dt / 4, dt / 8);
+    LAUNCH((k_scale), (c->N + IT - 1) / IT, IT, c->st, c->N, c->vel, c->gmask, bit, t.state + 3 * t.M);
     c->launches += 3;
 }
 
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(IT) k_kick_drift(int N, double4* __restrict__ 
 }
 void integ_kick_drift(pfmds_ctx* c, double dt) {
     KTimer kt(c, KS_KICK_DRIFT);
-    k_kick_drift<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
+    LAUNCH((k_kick_drift), (c->N + IT - 1) / IT, IT, c->st, c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
                                                          1u << (c->z_moving - 1), dt, dt / 2, c->box, c->err);
     c->launches += 1;
 }
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(IT) k_kick(int N, double4* __restrict__ vel, c
 }
 void integ_kick(pfmds_ctx* c, double dt) {
     KTimer kt(c, KS_KICK);
-    k_kick<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2);
+    LAUNCH((k_kick), (c->N + IT - 1) / IT, IT, c->st, c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2);
     c->launches += 1;
 }
 
@@ -215,7 +215,7 @@ __global__ void k_quench(int N, double4* __restrict__ vel, const double4* __rest
     vel[i] = v;
 }
 void integ_quench(pfmds_ctx* c) {
-    k_quench<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1));
+    LAUNCH((k_quench), (c->N + IT - 1) / IT, IT, c->st, c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1));
     c->launches += 1;
 }
 
@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(IT) k_sums_partial(int N, const double4* __res
         if (threadIdx.x == 0) part[blockIdx.x * 16 + k] = s;
     }
     // block max
+#ifdef __CUDACC__
     __shared__ double mx[IT / 32];
     double m = a[10];
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
@@ -256,6 +257,10 @@ __global__ void __launch_bounds__(IT) k_sums_partial(int N, const double4* __res
         for (int w = 1; w < IT / 32; ++w) m = fmax(m, mx[w]);
         part[blockIdx.x * 16 + 10] = m;
     }
+#else  // host replay (host_emu.hpp): no lane exchange; the running maximum is complete when thread 0 runs
+    double m = emu_block_max(a[10]);
+    if (threadIdx.x == 0) part[blockIdx.x * 16 + 10] = m;
+#endif
 }
 __global__ void k_sums_final(int nb, const double* __restrict__ part, double* out) {
     for (int k = 0; k < 10; ++k) {
@@ -272,8 +277,8 @@ __global__ void k_sums_final(int nb, const double* __restrict__ part, double* ou
     }
 }
 void integ_diagnostics(pfmds_ctx* c, double* d_out) {
-    k_sums_partial<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, 1u << (c->all_atoms - 1), c->part);
-    k_sums_final<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, d_out);
+    LAUNCH((k_sums_partial), RED_BLOCKS, IT, c->st, c->N, c->pos, c->vel, c->frc, c->gmask, 1u << (c->all_atoms - 1), c->part);
+    LAUNCH((k_sums_final), 1, 1024, c->st, RED_BLOCKS, c->part, d_out);
     c->launches += 2;
     if (c->slab) { slab_allreduce_sum(c, d_out, 10); slab_allreduce_max(c, d_out + 10, 1); }
 }
@@ -290,7 +295,7 @@ __global__ void k_sub_mcv(int N, double4* __restrict__ vel, const uint32_t* __re
 }
 void integ_zero_momentum(pfmds_ctx* c) {
     integ_diagnostics(c, c->red + 16);
-    k_sub_mcv<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, 1u << (c->all_atoms - 1), c->red + 16);
+    LAUNCH((k_sub_mcv), (c->N + IT - 1) / IT, IT, c->st, c->N, c->vel, c->gmask, 1u << (c->all_atoms - 1), c->red + 16);
     c->launches += 1;
 }
 
@@ -413,10 +418,10 @@ static NhcPack pack_of(pfmds_ctx* c) {
 void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step) {
     NhcPack P = pack_of(c);
     KTimer kt(c, KS_KICK_DRIFT);
-    k_nhc_open<<<1, 32, 0, c->st>>>(P, dt / 2, dt / 4, dt / 8);
+    LAUNCH((k_nhc_open), 1, 32, c->st, P, dt / 2, dt / 4, dt / 8);
     SlabDev S{};
     if (c->slab && slab_pos_pushed_by_kick(c, rebuild_step)) S = slab_dev(c, 0);
-    k_kick_drift_nvt<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
+    LAUNCH((k_kick_drift_nvt), (c->N + IT - 1) / IT, IT, c->st, c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
                                                              1u << (c->z_moving - 1), dt, dt / 2, c->box, P, c->err, S);
     // s_pending has been consumed; the closing half step of this same step overwrites it (k_nhc_close), so no reset here
     c->launches += 2;
@@ -433,14 +438,14 @@ __global__ void k_reduce_ke_partials(int nparts, const double* __restrict__ part
 void integ_nvt_kick_close(pfmds_ctx* c, double dt) {
     NhcPack P = pack_of(c);
     KTimer kt(c, KS_KICK);
-    k_kick_ke<<<RED_BLOCKS, IT, 0, c->st>>>(c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2, P, c->part);
+    LAUNCH((k_kick_ke), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2, P, c->part);
     if (c->slab) {  // rank-local sums, one all-reduce, then every rank runs the same chain update
-        k_reduce_ke_partials<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, P.n, c->red + 48);
+        LAUNCH((k_reduce_ke_partials), 1, 1024, c->st, RED_BLOCKS, c->part, P.n, c->red + 48);
         slab_allreduce_sum(c, c->red + 48, P.n);
-        k_nhc_close<<<1, 32, 0, c->st>>>(1, c->red + 48, P, dt / 2, dt / 4, dt / 8);
+        LAUNCH((k_nhc_close), 1, 32, c->st, 1, c->red + 48, P, dt / 2, dt / 4, dt / 8);
         c->launches += 1;
     } else {
-        k_nhc_close<<<1, 1024, 0, c->st>>>(RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
+        LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
     }
     c->launches += 2;
 }
@@ -449,8 +454,8 @@ void integ_flush_pending(pfmds_ctx* c) {
     if (!c->nhc_pending) return;
     NhcPack P = pack_of(c);
     for (int k = 0; k < P.n; ++k)
-        k_scale<<<(c->N + IT - 1) / IT, IT, 0, c->st>>>(c->N, c->vel, c->gmask, P.bit[k], P.state[k] + 3 * P.M[k] + 2);
-    k_reset_pending<<<1, 32, 0, c->st>>>(P);
+        LAUNCH((k_scale), (c->N + IT - 1) / IT, IT, c->st, c->N, c->vel, c->gmask, P.bit[k], P.state[k] + 3 * P.M[k] + 2);
+    LAUNCH((k_reset_pending), 1, 32, c->st, P);
     c->launches += P.n + 1;
     c->nhc_pending = false;
 }

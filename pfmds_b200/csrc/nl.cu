@@ -11,7 +11,7 @@
 #include <cmath>
 #include <cstdio>
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(PFMDS_EMU_LIB)
 #include "ctx.hpp"
 #else
 #include "common.cuh"  // host emulation of the kernels (tests/nl_host.cpp): no context, no launchers
@@ -43,7 +43,7 @@ inline long long nl_grid_dims(const BoxD& box, double rc, int ncell[3], double& 
     }
     return total;
 }
-#ifdef __CUDACC__
+#ifdef PFMDS_HAVE_CTX
 void nl_setup_grid(pfmds_ctx* c) {
     double rc = 0;
     for (auto& it : c->inter)
@@ -164,7 +164,7 @@ __global__ void k_iota(int N, int* a) {
     if (k < N) a[k] = k;
 }
 
-#ifdef __CUDACC__
+#ifdef PFMDS_HAVE_CTX
 // Bin every atom into the cell grid; with `reorder` the state arrays are physically permuted into
 // cell order (only legal when every neighbour list is rebuilt in the same step, since lists hold
 // slot indices).
@@ -174,28 +174,33 @@ void nl_bin_atoms(pfmds_ctx* c, bool reorder) {
     GridD g;
     for (int k = 0; k < 3; ++k) { g.n[k] = c->ncell[k]; g.inv[k] = c->ncell[k] / c->box.L[k]; }
     CK(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)(c->ncells + 1), c->st));
-    k_cell_count<<<nb, T, 0, c->st>>>(N, c->pos, g, c->cid, c->cell_cnt);
+    LAUNCH((k_cell_count), nb, T, c->st, N, c->pos, g, c->cid, c->cell_cnt);
+#ifdef __CUDACC__
     int sb = (c->ncells + 2047) / 2048;
-    k_scan_block<<<sb, 1024, 0, c->st>>>(c->ncells, c->cell_cnt, c->cell_start, c->scan_tmp);
-    k_scan_sums<<<1, 1024, 0, c->st>>>(sb, c->scan_tmp);
-    k_scan_add<<<(c->ncells + T - 1) / T, T, 0, c->st>>>(c->ncells, c->cell_start, c->scan_tmp, c->ncells, N);
+    LAUNCH((k_scan_block), sb, 1024, c->st, c->ncells, c->cell_cnt, c->cell_start, c->scan_tmp);
+    LAUNCH((k_scan_sums), 1, 1024, c->st, sb, c->scan_tmp);
+    LAUNCH((k_scan_add), (c->ncells + T - 1) / T, T, c->st, c->ncells, c->cell_start, c->scan_tmp, c->ncells, N);
+#else  // host replay: the scans exchange data between lanes; same exclusive prefix sum, serially
+    c->cell_start[0] = 0;
+    for (int k = 0; k < c->ncells; ++k) c->cell_start[k + 1] = c->cell_start[k] + c->cell_cnt[k];
+#endif
     CK(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)(c->ncells + 1), c->st));
-    k_cell_scatter<<<nb, T, 0, c->st>>>(N, c->cid, c->cell_start, c->cell_cnt, c->cell_atoms);
-    k_cell_sort<<<(c->ncells + T - 1) / T, T, 0, c->st>>>(c->ncells, c->cell_start, c->cell_atoms, c->orig);
+    LAUNCH((k_cell_scatter), nb, T, c->st, N, c->cid, c->cell_start, c->cell_cnt, c->cell_atoms);
+    LAUNCH((k_cell_sort), (c->ncells + T - 1) / T, T, c->st, c->ncells, c->cell_start, c->cell_atoms, c->orig);
     c->launches += 6;
     if (reorder) {
-        k_permute<<<nb, T, 0, c->st>>>(N, c->cell_atoms, c->pos, c->vel, c->gmask, c->orig, c->pos2, c->vel2, c->gmask2, c->orig2, c->newslot);
+        LAUNCH((k_permute), nb, T, c->st, N, c->cell_atoms, c->pos, c->vel, c->gmask, c->orig, c->pos2, c->vel2, c->gmask2, c->orig2, c->newslot);
         std::swap(c->pos, c->pos2);
         std::swap(c->vel, c->vel2);
         std::swap(c->gmask, c->gmask2);
         std::swap(c->orig, c->orig2);
-        k_iota<<<nb, T, 0, c->st>>>(N, c->cell_atoms);
+        LAUNCH((k_iota), nb, T, c->st, N, c->cell_atoms);
         c->identity_order = true;
         c->launches += 2;
     } else {
         c->identity_order = false;
     }
-    k_make_posf<<<nb, T, 0, c->st>>>(N, c->pos, c->gmask, c->posf);
+    LAUNCH((k_make_posf), nb, T, c->st, N, c->pos, c->gmask, c->posf);
     c->launches += 1;
     CK(cudaGetLastError());
 }
@@ -398,23 +403,32 @@ inline GridD nl_grid(const int ncell[3], const BoxD& box) {
     return g;
 }
 
-#ifdef __CUDACC__
+#ifdef PFMDS_HAVE_CTX
 void nl_build(pfmds_ctx* c, NList& l) {
     const int N = c->N;
+#ifdef __CUDACC__
     const bool warp_per_atom = N < 200000;  // measured: at 1e6 atoms the thread-per-atom scan is 2x faster, at 1e4 atoms 5x slower
+#else
+    const bool warp_per_atom = false;       // host replay: the warp-per-atom kernel compacts with ballots
+#endif
     const int T = warp_per_atom ? 256 : 128, nb = warp_per_atom ? (int)(((size_t)N * 32 + T - 1) / T) : (N + T - 1) / T;
     const GridD g = nl_grid(c->ncell, c->box);
     uint32_t b1 = 1u << (l.g1 - 1), b2 = 1u << (l.g2 - 1);
     double rc2 = l.rcut * l.rcut;
     const PrefD pf = nl_prefilter(c->box, l.rcut);
     KTimer kt(c, KS_NL_BUILD);
-#define LAUNCH_BUILD(ID, PT) do { if (warp_per_atom) k_build_warp<ID, PT><<<nb, T, 0, c->st>>>(N, c->pos, c->posf, c->orig, c->cell_start, c->cell_atoms, g, c->box, pf, b1, b2, rc2, \
-        l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err); \
-        else k_build<ID, PT><<<nb, T, 0, c->st>>>(N, c->pos, c->posf, c->orig, c->cell_start, c->cell_atoms, g, c->box, pf, b1, b2, rc2, \
-        l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err); } while (0)
+#define BUILD_ARGS N, c->pos, c->posf, c->orig, c->cell_start, c->cell_atoms, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, \
+        l.nlist_alt, l.nnum, c->err
+#ifdef __CUDACC__
+#define LAUNCH_BUILD(ID, PT) do { if (warp_per_atom) LAUNCH((k_build_warp<ID, PT>), nb, T, c->st, BUILD_ARGS); \
+        else LAUNCH((k_build<ID, PT>), nb, T, c->st, BUILD_ARGS); } while (0)
+#else
+#define LAUNCH_BUILD(ID, PT) LAUNCH((k_build<ID, PT>), nb, T, c->st, BUILD_ARGS)
+#endif
     if (c->identity_order) { if (l.partition) LAUNCH_BUILD(true, true); else LAUNCH_BUILD(true, false); }
     else { if (l.partition) LAUNCH_BUILD(false, true); else LAUNCH_BUILD(false, false); }
 #undef LAUNCH_BUILD
+#undef BUILD_ARGS
     c->launches += 1;
     l.built = true;
     CK(cudaGetLastError());
@@ -446,11 +460,11 @@ __global__ void k_nearest3(int N, const double4* __restrict__ pos, const int* __
     nnnum[i] = k < 3 ? k : 3;
 }
 
-#ifdef __CUDACC__
+#ifdef PFMDS_HAVE_CTX
 void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     const int N = c->N, T = 128, nb = (N + T - 1) / T;
     KTimer kt(c, KS_NL_BUILD);
-    k_nearest3<<<nb, T, 0, c->st>>>(N, c->pos, c->orig, src.view(c->stride), c->box, nn.rcut, c->stride, nn.nlist, nn.nnum, c->err);
+    LAUNCH((k_nearest3), nb, T, c->st, N, c->pos, c->orig, src.view(c->stride), c->box, nn.rcut, c->stride, nn.nlist, nn.nnum, c->err);
     c->launches += 1;
     nn.built = true;
     CK(cudaGetLastError());

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(RT) k_rebosc_numforce(int N, const double4* __
 void rebosc_forces(pfmds_ctx* c, Inter& it) {
     const int N = c->N;
     KTimer kt(c, KS_REBOSC_FORCE);
-    k_rebosc_numforce<<<(3 * N + RT - 1) / RT, RT, 0, c->st>>>(N, c->pos, c->frc, it.nl[0].view(c->stride), it.reb, c->box, c->orig, c->err);
+    LAUNCH((k_rebosc_numforce), (3 * N + RT - 1) / RT, RT, c->st, N, c->pos, c->frc, it.nl[0].view(c->stride), it.reb, c->box, c->orig, c->err);
     c->launches += 1;
     CK(cudaGetLastError());
 }
@@ -34,7 +34,7 @@ void rebosc_forces(pfmds_ctx* c, Inter& it) {
 int rebosc_energy_partials(pfmds_ctx* c, Inter& it) {
     const int N = c->N, nb = (N + RT - 1) / RT;
     KTimer kt(c, KS_REBOSC_ENERGY);
-    k_rebosc_energy<<<nb, RT, 0, c->st>>>(N, c->pos, it.nl[0].view(c->stride), it.reb, c->box, c->part);
+    LAUNCH((k_rebosc_energy), nb, RT, c->st, N, c->pos, it.nl[0].view(c->stride), it.reb, c->box, c->part);
     c->launches += 1;
     CK(cudaGetLastError());
     return nb;

@@ -1,0 +1,59 @@
+"""TEST SUPPORT ONLY.  Builds the HOST REPLAY of the device library: the very .cu sources of pfmds_b200/csrc compiled by g++
+(-x c++ -DPFMDS_EMU_LIB -DSMALL_N=0) with pfmds_b200/csrc/host_emu.hpp standing in for the CUDA language extensions and runtime,
+plus the run_md_simulation / run_gr_moire_fitting hosts linked against it.  Kernels run as serial loops over (block, thread).
+This exists so that the C-ABI orchestration (pfmds_advance's step sequence, the fused NVT path, deposition, checkpoints ...) and
+the kernels' arithmetic can be checked against the oracle in the CPU test suite; it is never built, loaded or shipped by the
+product (pfmds_b200/build.py compiles with nvcc only, pfmds_b200/engine.py loads libpfmds_b200.so only)."""
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "pfmds_b200", "csrc")
+HOST = os.path.join(ROOT, "pfmds_b200", "host")
+OUT = os.path.join(HERE, "_build")
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+SOURCES = ["capi.cu", "forces.cu", "nl.cu", "integrate.cu", "rebosc.cu"]
+FLAGS = ["-x", "c++", "-std=c++17", "-O2", "-ffp-contract=off", "-DPFMDS_EMU_LIB", "-DSMALL_N=0", "-fPIC"]
+LIB = os.path.join(OUT, "libpfmds_b200_emu.so")
+EXE = os.path.join(OUT, "run_md_simulation_emu")
+EXE_FIT = os.path.join(OUT, "run_gr_moire_fitting_emu")
+
+
+def _newer(target, deps):
+    return not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("emulated build failed: %s\n%s" % (" ".join(cmd), r.stdout[-4000:]))
+
+
+def build_emu():
+    os.makedirs(OUT, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".hpp"))] + [os.path.join(ROOT, "include", "pfmds_b200.h")]
+    jobs, objs = [], []
+    for s in SOURCES:
+        obj = os.path.join(OUT, s[:-3] + ".o")
+        objs.append(obj)
+        if _newer(obj, [os.path.join(CSRC, s)] + hdrs):
+            jobs.append([CXX] + FLAGS + ["-c", os.path.join(CSRC, s), "-o", obj])
+    stub = os.path.join(OUT, "slab_stub.o")
+    objs.append(stub)
+    if _newer(stub, [os.path.join(HERE, "slab_stub.cpp")] + hdrs):
+        jobs.append([CXX, "-std=c++17", "-O2", "-fPIC", "-c", os.path.join(HERE, "slab_stub.cpp"), "-o", stub])
+    with ThreadPoolExecutor(4) as ex:
+        list(ex.map(_run, jobs))
+    if jobs or _newer(LIB, objs):
+        _run([CXX, "-shared", "-o", LIB] + objs + ["-ldl", "-pthread"])
+    host_deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))]
+    for exe, src in ((EXE, "run_md_simulation.cpp"), (EXE_FIT, "run_gr_moire_fitting.cpp")):
+        if _newer(exe, host_deps + [LIB]):
+            _run([CXX, "-O2", "-std=c++17", "-o", exe, os.path.join(HOST, src), "-pthread", "-L" + OUT, "-lpfmds_b200_emu", "-Wl,-rpath,$ORIGIN"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_emu())

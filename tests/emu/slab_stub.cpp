@@ -1,0 +1,27 @@
+// TEST SUPPORT ONLY: the slab decomposition (pfmds_b200/csrc/slab.cu: NCCL, CUDA IPC, peer memory) has no host replay; the emulated
+// library links these stand-ins so that the single-context paths can be exercised.  c->slab is never set, so none of them runs.
+#define PFMDS_EMU_LIB 1
+#include <string>
+
+#include "../../pfmds_b200/csrc/ctx.hpp"
+
+static void no_slab() { throw std::string("slab decomposition is not available in the host replay"); }
+int slab_unique_id(char*) { return 20; }
+void slab_init(pfmds_ctx*, int, int, const char*, long long, int, int) { no_slab(); }
+void slab_destroy(pfmds_ctx*) {}
+void slab_redistribute(pfmds_ctx*) { no_slab(); }
+void slab_after_reorder(pfmds_ctx*) { no_slab(); }
+void slab_exchange(pfmds_ctx*, int) { no_slab(); }
+void slab_step_done(pfmds_ctx*) { no_slab(); }
+bool slab_uses_p2p(pfmds_ctx*) { return false; }
+bool slab_fused(pfmds_ctx*) { return false; }
+SlabDev slab_dev(pfmds_ctx*, int) { return SlabDev{}; }
+bool slab_pos_pushed_by_kick(pfmds_ctx*, bool) { return false; }
+void slab_allreduce_sum(pfmds_ctx*, double*, int) { no_slab(); }
+void slab_allreduce_max(pfmds_ctx*, double*, int) { no_slab(); }
+void slab_allreduce_max_int(pfmds_ctx*, int*, int) { no_slab(); }
+void slab_allreduce_sum_ll(pfmds_ctx*, unsigned long long*, int) { no_slab(); }
+int slab_rank(pfmds_ctx*) { return 0; }
+int slab_nranks(pfmds_ctx*) { return 1; }
+int slab_n_local(pfmds_ctx*) { return 0; }
+long long slab_n_global(pfmds_ctx*) { return 0; }

@@ -1,0 +1,138 @@
+"""The GPU parity tests re-run on the CPU against the HOST REPLAY of the device library (tests/emu/build_emu.py: the same .cu
+sources compiled by g++ with pfmds_b200/csrc/host_emu.hpp, kernels as serial loops over (block, thread)).  What this checks
+without a GPU: the C-ABI orchestration of libpfmds_b200 (step sequence of pfmds_advance, fused NVT path, deposition, rebosc,
+checkpoint / restore, error reporting, the hosts) and the arithmetic and indexing of every thread-per-atom kernel, against the
+oracle and the golden fixtures, with the GPU tests' own assertions.  What it cannot check: the compiled SASS, warp-cooperative
+kernels (8-lanes-per-atom variants, warp-per-atom list build, scans), CUDA graphs, streams — the `-m gpu` run remains the gate.
+The product never loads this library (tests/test_cabi.py::test_no_cpu_fallback)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from pfmds_b200 import inputs
+from pfmds_b200.engine import configure
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+import build_emu as B  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu(oracle_lib):
+    B.build_emu()
+    return B.LIB
+
+
+def emu_gpu(case):
+    return configure(case, lib_path=B.LIB)
+
+
+def replay(monkeypatch, module, **attrs):
+    """Import a GPU test module with its `gpu` engine factory (and executables) pointed at the host replay."""
+    m = importlib.import_module(module)
+    if hasattr(m, "gpu"):
+        monkeypatch.setattr(m, "gpu", emu_gpu)
+    for k, v in attrs.items():
+        monkeypatch.setattr(m, k, v)
+    return m
+
+
+SMALL = ["ab_gas", "cu_fcc", "gr_cu_ljc", "gr_cu_morsec", "gr_cu_ljc_simplified"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_step0_lists_forces_energies(monkeypatch, name):
+    replay(monkeypatch, "test_parity_gpu").test_step0_lists_forces_energies(name)
+
+
+@pytest.mark.parametrize("name", ["ab_gas", "cu_fcc", "gr_cu_morsec"])
+@pytest.mark.parametrize("integrator", ["nve", "nvt", "nvms"])
+def test_trajectory_22_steps(monkeypatch, name, integrator):
+    replay(monkeypatch, "test_parity_gpu").test_trajectory_22_steps(name, integrator)
+
+
+@pytest.mark.parametrize("fn", ["test_single_step_forces_after_move", "test_zero_momentum_and_invert_z", "test_too_many_neighbours_is_reported",
+                                "test_particle_out_of_cell_is_reported", "test_not_enough_graphene_neighbours_is_reported",
+                                "test_refuses_what_the_reference_gets_wrong_silently", "test_upload_restarts_a_context",
+                                "test_multi_step_advance_equals_single_steps", "test_two_contexts_share_a_gpu"])
+def test_parity_misc(monkeypatch, fn):
+    getattr(replay(monkeypatch, "test_parity_gpu"), fn)()
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_golden_fixtures_and_in_step_energies(monkeypatch, name):
+    m = replay(monkeypatch, "test_parity_gpu")
+    m.test_gpu_matches_golden_fixtures(name)
+    m.test_energies_from_the_force_pass(name)
+
+
+@pytest.mark.parametrize("thermostat", [True, False])
+def test_deposition(monkeypatch, thermostat):
+    replay(monkeypatch, "test_deposition_gpu").test_deposition_matches_the_oracle(thermostat)
+
+
+def test_deposition_misc(monkeypatch, tmp_path, oracle_lib):
+    m = replay(monkeypatch, "test_deposition_gpu", EXE=B.EXE)
+    m.test_forces_outside_all_atoms_accumulate_like_the_reference()
+    m.test_deposition_matches_the_golden_fixture()
+    m.test_host_deposition_run_matches_the_cpu_port(tmp_path, None, oracle_lib)
+
+
+def test_rebosc(monkeypatch, tmp_path, oracle_lib):
+    m = replay(monkeypatch, "test_rebosc_gpu", EXE=B.EXE)
+    m.test_rebosc_energy_and_numerical_forces(0.04)
+    m.test_rebosc_trajectory_and_energy_conservation()
+    m.test_rebosc_feeds_the_graphene_normals_of_ljc()
+    m.test_rebosc_matches_the_golden_fixture()
+    m.test_host_rebosc_run_matches_the_cpu_port(tmp_path, None, oracle_lib)
+
+
+@pytest.mark.parametrize("name", ["graphene", "ab_gas", "deposition", "cu_fcc"])
+def test_restart_is_bit_identical(monkeypatch, tmp_path, name):
+    replay(monkeypatch, "test_zz_restart_gpu", EXE=B.EXE).test_restart_reproduces_the_interrupted_run_on_the_gpu(tmp_path, None, name)
+
+
+def test_save_and_restore_state(monkeypatch):
+    replay(monkeypatch, "test_zz_restart_gpu").test_save_and_restore_state_through_the_c_abi()
+
+
+@pytest.mark.parametrize("which", ["ab_gas", "graphene"])
+def test_host_outputs(monkeypatch, tmp_path, oracle_lib, which):
+    replay(monkeypatch, "test_host_gpu", EXE=B.EXE).test_same_outputs_as_the_cpu_reference_port(tmp_path, None, oracle_lib, which)
+
+
+def test_host_ensemble_ranks(monkeypatch, tmp_path):
+    replay(monkeypatch, "test_host_gpu", EXE=B.EXE).test_gpu_ensemble_ranks(tmp_path, None)
+
+
+@pytest.mark.parametrize("extra", [(), ("-pair",)])
+def test_fitting_rows(monkeypatch, tmp_path, oracle_lib, extra):
+    replay(monkeypatch, "test_zz_fitting_gpu", EXE_FIT=B.EXE_FIT).test_fit_rows_match_the_cpu_port(tmp_path, None, oracle_lib, extra)
+
+
+def test_pipelined_lj1g_variant(monkeypatch):
+    """PFMDS_LJ1G_PIPE=1 through the C ABI (the replay always takes the thread-per-atom kernels)."""
+    from util import oracle, rel_err
+    case = inputs.lj_fluid(n_side=8, period=5)
+    a = emu_gpu(case)
+    monkeypatch.setenv("PFMDS_LJ1G_PIPE", "1")
+    b = emu_gpu(case)
+    o = oracle(case)
+    for e in (a, b, o):
+        e.advance("nve", 0.5, 0, 1)
+        e.advance("nve", 0.5, 1, 11)
+    fa, fb, fo = a.download()[2], b.download()[2], o.download()[2]
+    assert rel_err(fb, fo) < 1e-9 and rel_err(fb, fa) < 1e-11 and not np.array_equal(fa, fb)     # a different kernel did run
+    assert np.abs(b.download()[0] - o.download()[0]).max() < 1e-10
+
+
+def test_replay_identifies_itself():
+    import ctypes as C
+    lib = C.CDLL(B.LIB)
+    lib.pfmds_version.restype = C.c_char_p
+    assert b"HOST REPLAY" in lib.pfmds_version()
+    err = (C.c_double * 4)()
+    assert lib.pfmds_selftest_math(0, err) == 20            # no device: the device self-test refuses
