@@ -136,3 +136,46 @@ def test_replay_identifies_itself():
     assert b"HOST REPLAY" in lib.pfmds_version()
     err = (C.c_double * 4)()
     assert lib.pfmds_selftest_math(0, err) == 20            # no device: the device self-test refuses
+
+
+def _dep_case(changes, **kw):
+    case = inputs.lj_deposition(**kw)
+    # 1 all, 2 substrate, 3 growing [S, D], 4 empty, 5 a second growing group fed by group 3
+    case["groups"] = [["S", "D"], ["S", "#"], ["S", "D"], ["#", "#"], ["S", "D"]]
+    case["changes"] = changes
+    return case
+
+
+@pytest.mark.parametrize("changes", [
+    [(2, 3, 3, 40, 4), (3, 5, 6, 30, 2)],        # chained: group 5 follows group 3 until step 6, then grows twice as fast
+    [(2, 3, -5, 40, 3)],                         # change_ts1 < 0: the `<= ts1` branch never runs, the group starts full and stays capped
+    [(2, 3, 0, 1, 1)],                           # one atom at step 0, window closed at once
+    [(2, 3, 2, 10 ** 6, 1), (2, 5, 100, 200, 1)],  # one atom per step; an entry that never leaves its first branch
+])
+def test_deposition_edge_cases_against_the_oracle(changes):
+    from util import oracle, rel_err, neighbours
+    case = _dep_case(changes, thermostat=False)
+    case["interactions"][0]["lists"] = [(5, 3, 80, 7.5, 5)] if len(changes) > 1 and changes[1][1] == 5 and changes[1][2] == 6 else case["interactions"][0]["lists"]
+    if case["interactions"][0]["lists"][0][0] == 5:
+        case["interactions"][0] = dict(name="lj", file="parameters_LJ.txt", params=[0.0103, 3.405, 6.0, 7.0], lists=[(5, 3, 80, 7.5, 5), (3, 5, 80, 7.5, 5)])
+    g, o = emu_gpu(case), oracle(case)
+    s = 0
+    for n in (1, 2, 4, 5, 9):
+        g.advance("nve", 1.0, s, n)
+        o.advance("nve", 1.0, s, n)
+        s += n
+        assert [g.group_size(k) for k in range(1, 6)] == [o.group_size(k) for k in range(1, 6)]
+        assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-10 and rel_err(g.download()[2], o.download()[2]) < 1e-9
+        for j in range(len(case["interactions"][0]["lists"])):
+            a, b = neighbours(g, case, 0, j), neighbours(o, case, 0, j)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_deposition_zero_frequency_is_an_error_like_the_reference():
+    from pfmds_b200.engine import PfmdsError
+    from util import oracle
+    case = _dep_case([(2, 3, 1, 50, 0)], thermostat=False)
+    for eng in (emu_gpu(case), oracle(case)):
+        eng.advance("nve", 1.0, 0, 2)                      # steps 0, 1: still in the `<= ts1` branch
+        with pytest.raises(PfmdsError):
+            eng.advance("nve", 1.0, 2, 1)                  # mod(md_step - ts1, 0)
