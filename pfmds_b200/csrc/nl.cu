@@ -433,7 +433,7 @@ void nl_build(pfmds_ctx* c, NList& l) {
     l.built = true;
     CK(cudaGetLastError());
 }
-#endif  // __CUDACC__
+#endif  // PFMDS_HAVE_CTX
 
 // graphenenorm.f90:8-36: the entries of the carbon (tb) list closer than r_cut_nn; exactly three.
 __global__ void k_nearest3(int N, const double4* __restrict__ pos, const int* __restrict__ orig, ListView src, BoxD box, double rc_nn,
@@ -469,4 +469,4 @@ void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     nn.built = true;
     CK(cudaGetLastError());
 }
-#endif  // __CUDACC__
+#endif  // PFMDS_HAVE_CTX
