@@ -208,6 +208,31 @@ def run_ensemble(args, rank, world, local, dist, K, W):
     return 0
 
 
+def time_variant(case, integrator, dt, local, env, W, K):
+    """ms/step and per-kernel times of the same workload in a fresh context created under `env` (kernel variants are chosen
+    from the environment at pfmds_create).  Not part of `value`: reported beside it under "variants"."""
+    from pfmds_b200.engine import configure
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        eng = configure(case, device=local)
+        eng.advance(integrator, dt, 0, W)
+        eng.synchronize()
+        eng.set_profiling(True)
+        eng.timer_start()
+        eng.advance(integrator, dt, W, K)
+        ms = eng.timer_stop()
+        kt = eng.kernel_times()
+        eng.close()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return {"ms_per_step": ms / K, "steps": K, "kernels_ms_per_step": {k: round(v[0] / K, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])[:4]}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +242,7 @@ def main():
     ap.add_argument("--workload", default="cu_fcc")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the A/B timing of alternative kernel variants after the headline measurement")
     ap.add_argument("--decomp", default="slab", choices=["slab", "ensemble"])
     args = ap.parse_args()
     if args.impl == "reference":
@@ -374,6 +400,20 @@ def main():
         n, steps, tcpu, cores = cpu_baseline_sample(20)
         cpu = {"value": n * (steps + 1) / tcpu, "unit": "atom-steps/s", "cores": cores, "kind": "port",
                "sample": "Cu fcc 20^3x4 = %d atoms, step 0 + %d NVT steps (1 O(N^2) rebuild), C++/OpenMP restatement of the reference, %.1f s" % (n, steps, tcpu)}
+    # ---- kernel variants, same box, same run (A/B evidence for the defaults; never part of `value`) ----
+    variants = None
+    if not args.no_variants and world == 1 and args.workload == "cu_fcc":
+        variants = {"note": "fresh contexts after the headline measurement, 21 warm-up + 100 timed steps each; `value` is the default configuration"}
+        try:
+            eng.close()
+            variants["rjl_gen2 (default)"] = time_variant(case, integrator, dt, local, {"PFMDS_RJL_GEN": "2"}, 21, 100)
+            variants["rjl_gen1 (PFMDS_RJL_GEN=1, the round-1 kernels)"] = time_variant(case, integrator, dt, local, {"PFMDS_RJL_GEN": "1"}, 21, 100)
+            from pfmds_b200 import inputs
+            ljc = inputs.lj_fluid(n_side=96, seed=2, steps=200)
+            variants["lj_fluid 96^3 lj1g (default)"] = time_variant(ljc, "nve", ljc["integrators"][0][1], local, {"PFMDS_LJ1G_PIPE": "0"}, 21, 100)
+            variants["lj_fluid 96^3 lj1g pipelined (PFMDS_LJ1G_PIPE=1)"] = time_variant(ljc, "nve", ljc["integrators"][0][1], local, {"PFMDS_LJ1G_PIPE": "1"}, 21, 100)
+        except Exception as ex:  # the headline line must survive a failing experiment
+            variants["error"] = repr(ex)[:300]
     line = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -381,7 +421,7 @@ def main():
                    "l2": "working set (lists %.0f MB + state) exceeds the 126 MB L2" % (pairs * 4 / 1e6), "ns_per_day": K / (ms_max * 1e-3) * dt * 86400e-6},
         "clocks": cs.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
-        "per_rank": per_rank,
+        "per_rank": per_rank, "variants": variants,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -176,6 +176,9 @@ int pfmds_slab_upload(pfmds_ctx* ctx, int n_local, const double* positions, cons
 /* Device self-test of the library's FP64 elementary functions against the CUDA math library: max errors
  * [0] exp (relative), [1] cosine switch / sincos (absolute), [2] rsqrt (relative), [3] hardware rsqrt seed. */
 int pfmds_selftest_math(int device, double err[4]);
+/* Same for the reduced-instruction forms of the second-generation rjl kernels (mathx.cuh exp_m, rsqrt_q, cos_switch_m,
+ * half_switch): [0] exp relative on [-40, 40], [1] switch absolute, [2] rsqrt relative, [3] exp relative on [-600, 600]. */
+int pfmds_selftest_math2(int device, double err[4]);
 
 /* Number of kernel launches issued so far by this context and device-time of the last advance (ms). */
 int pfmds_launch_count(pfmds_ctx* ctx, long long* launches);

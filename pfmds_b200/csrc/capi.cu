@@ -97,7 +97,10 @@ void finalize_slab(pfmds_ctx* c) {
             if (l.period != period) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: slab decomposition needs one update_period for all lists");
             l.partition = true; l.part_r1sq = R1 * R1; l.part_r2sq = R2 * R2;
             CK(cudaMalloc(&l.nlist_alt, sizeof(int) * (size_t)l.maxn * c->stride));
-            CK(cudaMalloc(&l.nlist, sizeof(int) * (size_t)l.maxn * c->stride));
+            // two spare rows, and every entry a valid slot number from the start (0, later stale ones): the pipelined row walks of
+            // forces.cu prefetch up to slot n+1 without bounds tests and gather the partner record of whatever they find there
+            CK(cudaMalloc(&l.nlist, sizeof(int) * (size_t)(l.maxn + 2) * c->stride));
+            CK(cudaMemsetAsync(l.nlist, 0, sizeof(int) * (size_t)(l.maxn + 2) * c->stride, c->st));
             CK(cudaMalloc(&l.nnum, sizeof(int) * c->stride));
             CK(cudaMemsetAsync(l.nnum, 0, sizeof(int) * c->stride, c->st));
         }
@@ -197,7 +200,10 @@ void finalize(pfmds_ctx* c) {
             NList& l = it.nl[j];
             if (l.maxn < 1 || l.period < 1 || !(l.rcut > 0)) fail(PFMDS_ERR_INVALID, "error: bad neighbour list parameters");
             if (l.partition) CK(cudaMalloc(&l.nlist_alt, sizeof(int) * (size_t)l.maxn * c->stride));
-            CK(cudaMalloc(&l.nlist, sizeof(int) * (size_t)l.maxn * c->stride));
+            // two spare rows, and every entry a valid slot number from the start (0, later stale ones): the pipelined row walks of
+            // forces.cu prefetch up to slot n+1 without bounds tests and gather the partner record of whatever they find there
+            CK(cudaMalloc(&l.nlist, sizeof(int) * (size_t)(l.maxn + 2) * c->stride));
+            CK(cudaMemsetAsync(l.nlist, 0, sizeof(int) * (size_t)(l.maxn + 2) * c->stride, c->st));
             CK(cudaMalloc(&l.nnum, sizeof(int) * c->stride));
             CK(cudaMemsetAsync(l.nnum, 0, sizeof(int) * c->stride, c->st));
         }
@@ -488,6 +494,32 @@ __global__ void k_math_selftest(int n, double* out) {
     atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(e_rs));
     atomicMax((unsigned long long*)&out[3], (unsigned long long)__double_as_longlong(e_seed));
 }
+// the short forms of the second-generation rjl kernels (exp_m / exp_m2, rsqrt_q, cos_switch_m, half_switch)
+__global__ void k_math_selftest2(int n, double* out) {
+    double e_exp = 0, e_sw = 0, e_rs = 0, e_wide = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double u = (i + 0.5) / n;
+        double x = -40. + 80. * u, xb = 3. - 19. * u;
+        double a = exp(x), b = mx::exp_m(x), ea, eb;
+        e_exp = fmax(e_exp, fabs(a - b) / a);
+        mx::exp_m2(x, xb, ea, eb, 1.4426950408889634, -6.93147180559945309417e-01);
+        e_exp = fmax(e_exp, fmax(fabs(a - ea) / a, fabs(exp(xb) - eb) / exp(xb)));
+        x = -600. + 1200. * u;
+        a = exp(x);
+        e_wide = fmax(e_wide, fabs(a - mx::exp_m(x)) / a);
+        double ang = 3.14159265358979 * u, f, s, sr, cr;
+        mx::cos_switch_m(fma(ang, 0.5, -0.78539816339744830962), f, s);
+        sincos(ang, &sr, &cr);
+        e_sw = fmax(e_sw, fmax(fabs(f - (1. + cr) / 2), fabs(s - sr)));
+        e_sw = fmax(e_sw, fabs(mx::half_switch(ang - 1.57079632679489661923) - (1. + cr) / 2));
+        double v = exp(-20. + 40. * u);
+        e_rs = fmax(e_rs, fabs(mx::rsqrt_q(v) * sqrt(v) - 1.));
+    }
+    atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(e_exp));
+    atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(e_sw));
+    atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(e_rs));
+    atomicMax((unsigned long long*)&out[3], (unsigned long long)__double_as_longlong(e_wide));
+}
 #endif  // __CUDACC__
 __global__ void k_copy(size_t n, const double4* __restrict__ a, double4* __restrict__ b) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
@@ -564,6 +596,8 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
 #endif
         const char* lp = std::getenv("PFMDS_LJ1G_PIPE");
         c->lj1g_pipe = lp && lp[0] == '1';
+        const char* rg = std::getenv("PFMDS_RJL_GEN");
+        c->rjl_gen = (rg && rg[0] == '1') ? 1 : 2;
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     });
 }
@@ -1093,6 +1127,26 @@ int pfmds_selftest_math(int device, double err[4]) {
 #endif
 }
 
+// The short forms used by the second-generation rjl kernels: [0] exp_m / exp_m2 relative on [-40, 40], [1] cos_switch_m /
+// half_switch absolute, [2] rsqrt_q relative, [3] exp_m relative on [-600, 600].
+int pfmds_selftest_math2(int device, double err[4]) {
+#ifndef __CUDACC__
+    (void)device; (void)err;
+    return PFMDS_ERR_UNSUPPORTED;
+#else
+    try {
+        CK(cudaSetDevice(device));
+        double* d = nullptr;
+        CK(cudaMalloc(&d, 4 * sizeof(double)));
+        CK(cudaMemset(d, 0, 4 * sizeof(double)));
+        LAUNCH((k_math_selftest2), 256, 256, 0, 1 << 22, d);
+        CK(cudaMemcpy(err, d, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        return PFMDS_OK;
+    } catch (...) { return PFMDS_ERR_CUDA; }
+#endif
+}
+
 // FP64 FMA peak (TFLOP/s) and device-to-device copy bandwidth (GB/s, read+write) of `device`.
 int pfmds_measure_peaks(int device, double* dfma_tflops, double* copy_gbs) {
 #ifndef __CUDACC__
@@ -1200,6 +1254,8 @@ int pfmds_create_slab(pfmds_ctx** out, int device, int rank, int nranks, const c
         c->group_count.assign(group_sizes, group_sizes + n_groups);
         const char* tm = std::getenv("PFMDS_TIMERS");
         c->timers_on = tm && tm[0] == '1';
+        const char* rg = std::getenv("PFMDS_RJL_GEN");
+        c->rjl_gen = (rg && rg[0] == '1') ? 1 : 2;
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
         slab_init(c, rank, nranks, id, n_global, n_local, capacity);
     });

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ 
 //   pass 2  F_i -= [2 A0 (p/r0 f_c - f_c'/r r) e^{-p t} - xi (q/r0 f_c - f_c'/r r/2)(1/Eb_i + 1/Eb_j) e^{-2q t}]/r dr
 // Rows are class-partitioned at build time (r < R1 | switch zone | beyond R2, nl.cu k_partition) so the
 // lanes of a warp take the same branch; in a crystal the shells line up exactly.
-struct RjlC { double R1, R22, R12, qa, qb, pa, pb, A0, xi, a1, a2, sw, pi_sw; };
+struct RjlC { double R1, R22, R12, qa, qb, pa, pb, A0, xi, a1, a2, sw, pi_sw; static constexpr bool padded = false; };
 // exp arguments are affine in r: -2q(r/r0-1) = qa r + qb, -p(r/r0-1) = pa r + pb
 static RjlC rjl_consts(const RJLp& P) {
     RjlC c;
@@ -191,6 +191,114 @@ __device__ __forceinline__ void wrap3(double& dx, double& dy, double& dz, const 
     }
 }
 
+// ---- rjl, second generation pair routines (default; PFMDS_RJL_GEN=1 selects the first) -------------------------------
+// ncu on the first generation (profiles/r1e_*): 111 warp instructions per listed pair, 57 of them FP64, the FP64 pipe 67 %
+// busy and 63 % of the issue slots used: both limits bind, so instructions are removed, not overlapped.
+//   * the minimum image is decided AFTER r^2: a pair inside R2 cannot have a wrapped component when R2 <= min half box
+//     (|d_k| >= h_k gives r^2 >= h_k^2 >= R2^2 in rounded arithmetic too), so only pairs that fail r^2 < R2^2 pay the
+//     high-word test, and only atoms near a face pay the exact one; dr and r^2 keep the first generation's bits;
+//   * exp_m (13 FP64 instead of 16), rsqrt_q (3 instead of 5), minimax switch polynomials (mathx.cuh);
+//   * the prefactors of both exponentials are folded into their arguments, a1 e^x = e^(x + ln a1), so that the common
+//     class is  c = (e_p - (1/Eb_i + 1/Eb_j) e_q)/r  (3 FP64) and the switch zone only multiplies e_p and the 1/Eb sum by
+//     f + sin(a) k_p and f + sin(a) k_q (k = -pi/(2 (R2-R1)) / slope of the exponent): see rjl_force_consts;
+//   * the density pass needs the value of the switch only: one odd polynomial in a - pi/2 (half_switch).
+// Per pair of the common class: 43 FP64 instructions in the force pass (57 before), 25 in the density pass (37 before).
+struct RjlD { double R22, R12, qa, qb, pa, pb, sw, y0, A0, xi; static constexpr bool padded = true; };
+struct RjlF { double R22, R12, qa, qb, pa, pb, swh, u0, kp, kq, l2e, nln2; static constexpr bool padded = true; };
+// the second generation needs positive prefactors (their logarithms) and R2 inside the half box
+static bool rjl_gen2_ok(const RJLp& P, const BoxD& b) {
+    double hm = b.h[0] < b.h[1] ? (b.h[0] < b.h[2] ? b.h[0] : b.h[2]) : (b.h[1] < b.h[2] ? b.h[1] : b.h[2]);
+    double a1 = 2. * P.A0 * P.p / P.r0, a2 = P.xi * P.q / P.r0;
+    return a1 > 0. && a2 > 0. && a1 < 1e300 && a2 < 1e300 && P.R2 <= hm && P.R2 > P.R1 && fabs(log(a1)) < 50. && fabs(log(a2)) < 50.;
+}
+static RjlD rjl_dens_consts(const RJLp& P) {
+    const RjlC c = rjl_consts(P);
+    RjlD d;
+    d.R22 = c.R22; d.R12 = c.R12; d.qa = c.qa; d.qb = c.qb; d.pa = c.pa; d.pb = c.pb; d.A0 = c.A0; d.xi = c.xi;
+    d.sw = c.sw;                                      // a = (r - R1) sw with the reference's pi literal; y = a - pi/2
+    d.y0 = -P.R1 * c.sw - 1.57079632679489661923;
+    return d;
+}
+static RjlF rjl_force_consts(const RJLp& P) {
+    const RjlC c = rjl_consts(P);
+    RjlF f;
+    f.R22 = c.R22; f.R12 = c.R12; f.qa = c.qa; f.pa = c.pa;
+    f.pb = c.pb + log(c.a1);                          // a1 e^{-p(r/r0-1)},  a1 = 2 A0 p / r0
+    f.qb = c.qb + log(c.a2);                          // a2 e^{-2q(r/r0-1)}, a2 = xi q / r0
+    f.swh = 0.5 * c.sw;                               // u = a/2 - pi/4
+    f.u0 = -P.R1 * f.swh - 0.78539816339744830962;
+    // switch zone: 2 A0 (-pa f + s pi_sw) e_p = a1 e_p (f + s kp), kp = -pi_sw / pa;  likewise kq = -pi_sw / qa
+    f.kp = -c.pi_sw / c.pa;
+    f.kq = -c.pi_sw / c.qa;
+    f.l2e = 1.4426950408889634; f.nln2 = -6.93147180559945309417e-01;  // launch parameters stay in uniform registers (mx::exp_m2)
+    return f;
+}
+// dr and r^2 of a pair; false when the pair is beyond R2 (or not a number).  Same bits as wrap3 + the first generation's sum.
+__device__ __forceinline__ bool pair_inside(const double4& pi, const double4& pj, double R22, const BoxD& box, int mhh, double& dx, double& dy,
+                                            double& dz, double& r2) {
+    dx = pj.x - pi.x; dy = pj.y - pi.y; dz = pj.z - pi.z;
+    r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    if (!(r2 < R22)) {
+        int m = max(max(__double2hiint(dx) & 0x7fffffff, __double2hiint(dy) & 0x7fffffff), __double2hiint(dz) & 0x7fffffff);
+        if (m < mhh) return false;
+        dx = min_image(dx, box.h[0], box.L[0]);
+        dy = min_image(dy, box.h[1], box.L[1]);
+        dz = min_image(dz, box.h[2], box.L[2]);
+        r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (!(r2 < R22)) return false;
+    }
+    return true;
+}
+template <bool E>
+__device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlD& C, const BoxD& box, int mhh, double& sq, double& sp) {
+    double dx, dy, dz, r2;
+    if (pair_inside(pi, pj, C.R22, box, mhh, dx, dy, dz, r2)) {
+        double r = r2 * mx::rsqrt_q(r2);
+        double eq = mx::exp_m(fma(C.qa, r, C.qb));
+        double ep = E ? mx::exp_m(fma(C.pa, r, C.pb)) : 0.;
+        if (r2 < C.R12) {
+            sq += eq;
+            if (E) sp += ep;
+        } else {
+            double f = mx::half_switch(fma(r, C.sw, C.y0));
+            sq = fma(eq, f, sq);
+            if (E) sp = fma(ep, f, sp);
+        }
+    }
+}
+__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlF& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                               double& fz) {
+    double dx, dy, dz, r2;
+    if (pair_inside(pi, pj, C.R22, box, mhh, dx, dy, dz, r2)) {
+        double ir = mx::rsqrt_q(r2);
+        double r = r2 * ir;
+        // switch zone first, then both exponentials side by side (mx::exp_m2), then the zone's two factors
+        const bool zone = !(r2 < C.R12);
+#ifdef __CUDA_ARCH__
+        double gp, gq;  // read only when `zone`
+#else
+        double gp = 1., gq = 1.;
+#endif
+        if (zone) {
+            double f, s;
+            mx::cos_switch_m(fma(r, C.swh, C.u0), f, s);
+            gp = fma(s, C.kp, f);
+            gq = fma(s, C.kq, f);
+        }
+        double A, eq;
+        mx::exp_m2(fma(C.pa, r, C.pb), fma(C.qa, r, C.qb), A, eq, C.l2e, C.nln2);
+        double w = pi.w + pj.w;
+        if (zone) {
+#ifdef __CUDA_ARCH__
+            asm volatile("");  // keeps this a branch: if-converted it costs every pair two multiplications and four selects
+#endif
+            A *= gp; w *= gq;
+        }
+        double c = fma(-w, eq, A) * ir;
+        fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
+    }
+}
+
 template <bool E>
 __device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& sq, double& sp) {
     double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
@@ -208,11 +316,36 @@ __device__ __forceinline__ void rjl_density_pair(const double4& pi, const double
         if (E) sp = fma(mx::exp_nc(fma(C.pa, r, C.pb)), f, sp);
     }
 }
+// Row walk shared by both pipelined kernels.  PADDED rows (second generation; every list is allocated with two spare rows of
+// valid slot numbers, capi.cu) are prefetched without bounds tests: the walk reads at most slot n+1 and never uses it.
+template <bool PADDED>
+struct RowWalk {
+    const int* rp;  // PADDED: slot p+2;  otherwise slot p
+    ptrdiff_t st;
+    __device__ __forceinline__ RowWalk(const ListView& lv, int i) : rp(lv.nlist + i), st((ptrdiff_t)lv.stride) {}
+    __device__ __forceinline__ int first(int n, int& j1) {
+        int j0 = rp[0];
+        j1 = (PADDED || n > 1) ? rp[st] : j0;
+        if (PADDED) rp += 2 * st;
+        return j0;
+    }
+    // slots p+2 and p+3 while slots p, p+1 are being worked on
+    __device__ __forceinline__ void ahead(int p, int n, int j1, int& j2, int& j3) {
+        if (PADDED) {
+            j2 = rp[0]; j3 = rp[st];
+        } else {
+            j2 = p + 2 < n ? rp[2 * st] : j1;
+            j3 = p + 3 < n ? rp[3 * st] : j1;
+        }
+        rp += 2 * st;
+    }
+};
+
 #ifndef RJL_MINB_D
 #define RJL_MINB_D RJL_MINB
 #endif
-template <bool E>
-__global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part, SlabDev S) {
+template <bool E, class CT>  // CT = RjlC (first generation) or RjlD (second generation, below): picks the pair routine
+__global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* pos, ListView lv, CT C, BoxD box, WrapC W, double* part, SlabDev S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
     bool pushed = false;
@@ -223,16 +356,14 @@ __global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* 
         // constant: the whole record is fetched with one request and .w is ignored here.
         const double4 pi = ld256(&pos[i]);
         double sq = 0, sp = 0;
-        const int* rp = lv.nlist + i;
-        const size_t st = lv.stride;
-        int j1 = n > 1 ? rp[st] : rp[0];
-        double4 a = ld256(&pos[rp[0]]);
+        RowWalk<CT::padded> row(lv, i);
+        int j1;
+        double4 a = ld256(&pos[row.first(n, j1)]);
         int p = 0;
         for (; p + 1 < n; p += 2) {
             double4 b = ld256(&pos[j1]);
-            int j2 = p + 2 < n ? rp[2 * st] : j1;
-            int j3 = p + 3 < n ? rp[3 * st] : j1;
-            rp += 2 * st;
+            int j2, j3;
+            row.ahead(p, n, j1, j2, j3);
             rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, sq, sp);
             a = ld256(&pos[j2]);
             rjl_density_pair<E>(pi, b, C, box, W.min_half_hi, sq, sp);
@@ -254,8 +385,8 @@ __global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* 
 }
 
 // small systems: SPLIT lanes per atom, plain loop (latency is hidden by the extra warps)
-template <bool E, int SPLIT>
-__global__ void __launch_bounds__(FT) k_rjl_density_split(int N, double4* pos, ListView lv, RjlC C, BoxD box, WrapC W, double* part) {
+template <bool E, int SPLIT, class CT>
+__global__ void __launch_bounds__(FT) k_rjl_density_split(int N, double4* pos, ListView lv, CT C, BoxD box, WrapC W, double* part) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double e = 0, sq = 0, sp = 0;
     int n = i < N ? lv.nnum[i] : 0;
@@ -295,7 +426,8 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
         fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
     }
 }
-__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
+template <class CT>  // CT = RjlC (first generation) or RjlF (second generation)
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                             WrapC W, SlabDev S, int overwrite) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);  // slab mode: the neighbours' 1/Eb have landed in my ghost slots
@@ -304,16 +436,14 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4
     if (n == 0) { if (overwrite) frc[i] = make_double4(0., 0., 0., 0.); return; }
     const double4 pi = ld256_nc(&pos[i]);
     double fx = 0, fy = 0, fz = 0;
-    const int* rp = lv.nlist + i;
-    const size_t st = lv.stride;
-    int j1 = n > 1 ? rp[st] : rp[0];
-    double4 a = ld256_nc(&pos[rp[0]]);
+    RowWalk<CT::padded> row(lv, i);
+    int j1;
+    double4 a = ld256_nc(&pos[row.first(n, j1)]);
     int p = 0;
     for (; p + 1 < n; p += 2) {
         double4 b = ld256_nc(&pos[j1]);
-        int j2 = p + 2 < n ? rp[2 * st] : j1;
-        int j3 = p + 3 < n ? rp[3 * st] : j1;
-        rp += 2 * st;
+        int j2, j3;
+        row.ahead(p, n, j1, j2, j3);
         rjl_force_pair(pi, a, C, box, W.min_half_hi, fx, fy, fz);
         a = ld256_nc(&pos[j2]);
         rjl_force_pair(pi, b, C, box, W.min_half_hi, fx, fy, fz);
@@ -325,8 +455,8 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4
     else add_force(frc, i, fx, fy, fz);
 }
 
-template <int SPLIT>
-__global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlC C, BoxD box,
+template <int SPLIT, class CT>
+__global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                         WrapC W) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double fx = 0, fy = 0, fz = 0;
@@ -723,25 +853,34 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         break;
     case K_RJL:
     {
-        const RjlC C = rjl_consts(it.rjl);
         const WrapC W = wrap_consts(c->box);
         const bool fused = c->slab && !small && slab_fused(c);  // density stores 1/Eb into the neighbours' ghosts itself
-        {
-            KTimer kt(c, KS_RJL_DENSITY);
-            if (with_energy) {
-                if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, it.nl[0].view(st), C, c->box, W, epart);
-                else LAUNCH((k_rjl_density<true>), nb, FT, c->st, N, c->pos, it.nl[0].view(st), C, c->box, W, epart, fused ? slab_dev(c, 1) : SlabDev{});
-                e_parts = small ? nbs : nb;
-            } else
-            if (small) LAUNCH((k_rjl_density_split<false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr);
-            else LAUNCH((k_rjl_density<false>), nb, FT, c->st, N, c->pos, it.nl[0].view(st), C, c->box, W, nullptr, fused ? slab_dev(c, 1) : SlabDev{});
-        }
-        if (c->slab && !fused) slab_exchange(c, 1);  // ghost 1/Eb from their owners
-        {
-            KTimer kt(c, KS_RJL_FORCE);
-            if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W);
-            else LAUNCH((k_rjl_force), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), C, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, (k == 0 && c->first_overwrites && N >= SMALL_N) ? 1 : 0);
-        }
+        const bool gen2 = c->rjl_gen != 1 && rjl_gen2_ok(it.rjl, c->box);
+        const ListView lv = it.nl[0].view(st);
+        const int ow = (k == 0 && c->first_overwrites && N >= SMALL_N) ? 1 : 0;
+        // one launch sequence for both generations: CD / CF are the constant packs that select the pair routines
+        auto run = [&](auto CD, auto CF) {
+            using TD = decltype(CD);
+            using TF = decltype(CF);
+            {
+                KTimer kt(c, KS_RJL_DENSITY);
+                if (with_energy) {
+                    if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, epart);
+                    else LAUNCH((k_rjl_density<true, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, epart, fused ? slab_dev(c, 1) : SlabDev{});
+                    e_parts = small ? nbs : nb;
+                } else
+                if (small) LAUNCH((k_rjl_density_split<false, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, (double*)nullptr);
+                else LAUNCH((k_rjl_density<false, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, (double*)nullptr, fused ? slab_dev(c, 1) : SlabDev{});
+            }
+            if (c->slab && !fused) slab_exchange(c, 1);  // ghost 1/Eb from their owners
+            {
+                KTimer kt(c, KS_RJL_FORCE);
+                if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W);
+                else LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
+            }
+        };
+        if (gen2) run(rjl_dens_consts(it.rjl), rjl_force_consts(it.rjl));
+        else { const RjlC C = rjl_consts(it.rjl); run(C, C); }
     }
         c->launches += 2;
         break;
@@ -801,8 +940,15 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     case K_LJ: if (small) LAUNCH((k_lj<false, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); else LAUNCH((k_lj<false, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, c->part); break;
     case K_LJ1G: if (small) LAUNCH((k_lj1g<false, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); else LAUNCH((k_lj1g<false, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, c->part); scale = 0.5; break;
     case K_RJL: {
-        if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part);
-        else LAUNCH((k_rjl_density<true>), nb, FT, c->st, N, c->pos, it.nl[0].view(st), rjl_consts(it.rjl), c->box, wrap_consts(c->box), c->part, SlabDev{});
+        const WrapC W = wrap_consts(c->box);
+        const ListView lv = it.nl[0].view(st);
+        auto run = [&](auto CD) {
+            using TD = decltype(CD);
+            if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, c->part);
+            else LAUNCH((k_rjl_density<true, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, c->part, SlabDev{});
+        };
+        if (c->rjl_gen != 1 && rjl_gen2_ok(it.rjl, c->box)) run(rjl_dens_consts(it.rjl));
+        else run(rjl_consts(it.rjl));
         break;
     }
     case K_REBOSC: nparts = rebosc_energy_partials(c, it); c->launches -= 1; break;

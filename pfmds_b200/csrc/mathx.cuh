@@ -175,6 +175,138 @@ MX_HD double rsqrt_fast(double x) {
     return fma(y * e, t, y);
 }
 
+// ---- short forms for the rjl pair loops (second generation kernels, forces.cu) -------------------------------------
+// Those loops are bound by the FP64 pipe (every warp instruction holds the 16-lane pipe of an SMSP for two cycles) and by
+// issue slots at the same time, so these variants spend fewer instructions at a precision still 10^3..10^5 inside the
+// 1e-9 parity bar.  Coefficients are minimax fits (tools/minimax.py, Remez exchange in 60-digit arithmetic) with the
+// leading terms kept exact, so those enter DFMA as immediates.
+//   e^(r/2) = 1 + r/2 + r^2 Q(r),  |r| <= ln2/2:  relative error 2.3e-15
+MX_CONST double EXP_M[7] = {0x1.0000000000601p-3, 0x1.55555555fb059p-6, 0x1.5555555062fc2p-9, 0x1.11110a0e2e82cp-12,
+                            0x1.6c16e2fd4e000p-16, 0x1.a0755f88e73a1p-20, 0x1.9fb49a4f91900p-24};
+//   sin u = u + u^3 S(u^2), cos u = 1 + u^2 C(u^2),  |u| <= pi/4:  absolute errors 5.0e-15 and 9.8e-17
+MX_CONST double SIN_M[5] = {-0x1.5555555552d7dp-3, 0x1.1111110ccb02ap-7, -0x1.a019f92d8d0adp-13, 0x1.71d7452e064bfp-19, -0x1.a94b85bcf213fp-26};
+MX_CONST double COS_M[6] = {-0x1.fffffffffffbcp-2, 0x1.555555555023bp-5, -0x1.6c16c164a5ccbp-10, 0x1.a019f8578ec11p-16, -0x1.27df47e14bfc5p-22,
+                            0x1.1b87a0dbfd873p-29};
+//   (1 + cos a)/2 = 1/2 - y/2 + y^3 H(y^2),  y = a - pi/2 in [-pi/2, pi/2]:  absolute error 1.4e-16
+MX_CONST double HSW_M[7] = {0x1.55555555554f5p-4, -0x1.111111110c0eep-8, 0x1.a01a019b327e4p-14, -0x1.71de38306b5fcp-20, 0x1.ae635d685da20p-27,
+                            -0x1.60e748c48ee26p-34, 0x1.9f157524660aap-42};
+
+MX_HD int hi_word(double d) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(d);
+#else
+    return (int)(as_ll(d) >> 32);
+#endif
+}
+MX_HD int lo_word(double d) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(d);
+#else
+    return (int)(as_ll(d) & 0xffffffffll);
+#endif
+}
+MX_HD double from_words(int hi, int lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    return as_double((long long)(((unsigned long long)(unsigned int)hi << 32) | (unsigned int)lo));
+#endif
+}
+
+// exp(x) for |x| < 700 (no clamp): k = round(x log2 e) by the 1.5*2^52 trick, r = x - k ln2 with ONE fused step (the product
+// is exact inside the FMA; what is lost is |k| * (ln2 - fl(ln2)) <= 1024 * 2.3e-17 absolute in r), e^r = (1 + r/2 + r^2 Q(r))^2,
+// and 2^k enters through one integer add on the high word.  Relative error < 3e-14 on the whole range, < 8e-15 for |x| < 40 (measured 6.2e-15).
+MX_HD double exp_m(double x) {
+    const double MAGIC = 6755399441055744.0;
+    double t = fma(x, 1.4426950408889634, MAGIC);
+    double kd = t - MAGIC;
+    double r = fma(kd, -6.93147180559945309417e-01, x);
+    double p = EXP_M[6];
+    p = fma(p, r, EXP_M[5]);
+    p = fma(p, r, EXP_M[4]);
+    p = fma(p, r, EXP_M[3]);
+    p = fma(p, r, EXP_M[2]);
+    p = fma(p, r, EXP_M[1]);
+    p = fma(p, r, EXP_M[0]);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = p * p;
+    return from_words(hi_word(p) + (lo_word(t) << 20), lo_word(p));  // low word of t holds k (two's complement)
+}
+
+// two independent exp_m evaluated side by side: every coefficient is fetched once for both Horner chains, and the two
+// dependent chains fill each other's FP64 latency slots
+// (log2 e and -ln 2 are arguments so that a kernel can hand them over as launch parameters: those stay in uniform
+// registers across the pair loop, literals are rebuilt from immediates for every pair)
+MX_HD void exp_m2(double xa, double xb, double& ea, double& eb, double l2e = 1.4426950408889634, double nln2 = -6.93147180559945309417e-01) {
+    const double MAGIC = 6755399441055744.0;
+    double ta = fma(xa, l2e, MAGIC), tb = fma(xb, l2e, MAGIC);
+    double ka = ta - MAGIC, kb = tb - MAGIC;
+    double ra = fma(ka, nln2, xa), rb = fma(kb, nln2, xb);
+    double pa = EXP_M[6], pb = EXP_M[6];
+    pa = fma(pa, ra, EXP_M[5]); pb = fma(pb, rb, EXP_M[5]);
+    pa = fma(pa, ra, EXP_M[4]); pb = fma(pb, rb, EXP_M[4]);
+    pa = fma(pa, ra, EXP_M[3]); pb = fma(pb, rb, EXP_M[3]);
+    pa = fma(pa, ra, EXP_M[2]); pb = fma(pb, rb, EXP_M[2]);
+    pa = fma(pa, ra, EXP_M[1]); pb = fma(pb, rb, EXP_M[1]);
+    pa = fma(pa, ra, EXP_M[0]); pb = fma(pb, rb, EXP_M[0]);
+    pa = fma(pa, ra, 0.5); pb = fma(pb, rb, 0.5);
+    pa = fma(pa, ra, 1.0); pb = fma(pb, rb, 1.0);
+    pa = pa * pa; pb = pb * pb;
+    ea = from_words(hi_word(pa) + (lo_word(ta) << 20), lo_word(pa));
+    eb = from_words(hi_word(pb) + (lo_word(tb) << 20), lo_word(pb));
+}
+
+// 1/sqrt(x) for normal positive x: hardware seed y (relative error d <= 9e-7) and one second-order step written so that it
+// costs three FP64 instructions, y (3/2 - x y^2 / 2) = y + y (1 - x y^2)/2: -y/2 is the seed with 0x7ff00000 added to its
+// high word (exponent - 1, sign set; the seed's low word is zero).  Relative error 3/2 d^2 <= 1.3e-12.
+MX_HD double rsqrt_q(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    double y = from_words(hi_word((double)(1.0f / sqrtf((float)x)) * (1.0 + 9e-7)), 0);
+#endif
+    double yh = from_words(hi_word(y) + 0x7ff00000, 0);  // -y/2
+    double b = fma(x * yh, y, 1.5);
+    return y * b;
+}
+
+// Cosine switch from the half angle u = a/2 - pi/4 in [-pi/4, pi/4] (the caller forms u with one FMA from r):
+//   (1 + cos a)/2 = (cos u - sin u)^2 / 2,   sin a = (cos u - sin u)(cos u + sin u).
+MX_HD void cos_switch_m(double u, double& half_one_plus_cos, double& sin_a) {
+    double u2 = u * u;
+    double ps = SIN_M[4];
+    ps = fma(ps, u2, SIN_M[3]);
+    ps = fma(ps, u2, SIN_M[2]);
+    ps = fma(ps, u2, SIN_M[1]);
+    ps = fma(ps, u2, SIN_M[0]);
+    double su = fma(u * u2, ps, u);
+    double pc = COS_M[5];
+    pc = fma(pc, u2, COS_M[4]);
+    pc = fma(pc, u2, COS_M[3]);
+    pc = fma(pc, u2, COS_M[2]);
+    pc = fma(pc, u2, COS_M[1]);
+    pc = fma(pc, u2, COS_M[0]);
+    double cu = fma(u2, pc, 1.0);
+    double d = cu - su;
+    half_one_plus_cos = (0.5 * d) * d;
+    sin_a = d * (cu + su);
+}
+
+// Value of the switch alone, (1 + cos a)/2 = (1 - sin y)/2 with y = a - pi/2 in [-pi/2, pi/2] (one FMA from r in the caller).
+MX_HD double half_switch(double y) {
+    double y2 = y * y;
+    double p = HSW_M[6];
+    p = fma(p, y2, HSW_M[5]);
+    p = fma(p, y2, HSW_M[4]);
+    p = fma(p, y2, HSW_M[3]);
+    p = fma(p, y2, HSW_M[2]);
+    p = fma(p, y2, HSW_M[1]);
+    p = fma(p, y2, HSW_M[0]);
+    return fma(y * y2, p, fma(y, -0.5, 0.5));
+}
+
 // 1/x for normal x: hardware seed (MUFU.RCP64H) and one third-order step y <- y + y (e + e^2), e = 1 - x y.
 MX_HD double rcp_fast(double x) {
 #ifdef __CUDA_ARCH__

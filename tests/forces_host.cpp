@@ -51,20 +51,32 @@ int fh_lj1g(int N, const double* pos4, double* frc4, size_t stride, const int* n
     return 0;
 }
 
-// rjl: density pass (1/Eb into pos.w, energy partials) then force pass; `overwrite` = the store-instead-of-accumulate variant
-int fh_rjl(int N, double* pos4, double* frc4, size_t stride, const int* nl0, const int* nn0, const double* p, const double* L, int overwrite, double* energy) {
+// rjl: density pass (1/Eb into pos.w, energy partials) then force pass; `overwrite` = the store-instead-of-accumulate variant.
+// gen = 2: second-generation pair routines when the parameters allow them (as forces_interaction decides), 1: first generation.
+// Returns the generation that ran.  The list must carry two spare rows of valid slot numbers (capi.cu allocates them).
+int fh_rjl(int N, double* pos4, double* frc4, size_t stride, const int* nl0, const int* nn0, const double* p, const double* L, int overwrite, double* energy,
+           int gen) {
     double4* pos = (double4*)pos4;
     double4* frc = (double4*)frc4;
     BoxD box = make_box(L);
     RJLp R{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
-    const RjlC C = rjl_consts(R);
     const WrapC W = wrap_consts(box);
     const int nb = (N + FT - 1) / FT;
     std::vector<double> part((size_t)nb + 1, 0.);
-    emu_launch(k_rjl_density<true>, nb, 1, FT, N, pos, ListView{nl0, nn0, stride}, C, box, W, part.data(), SlabDev{});
+    const ListView lv{nl0, nn0, stride};
+    if (gen != 1 && rjl_gen2_ok(R, box)) {
+        const RjlD CD = rjl_dens_consts(R);
+        const RjlF CF = rjl_force_consts(R);
+        emu_launch(k_rjl_density<true, RjlD>, nb, 1, FT, N, pos, lv, CD, box, W, part.data(), SlabDev{});
+        *energy = sum_parts(part, nb, 1.0);
+        emu_launch(k_rjl_force<RjlF>, nb, 1, FT, N, (const double4*)pos, frc, lv, CF, box, W, SlabDev{}, overwrite);
+        return 2;
+    }
+    const RjlC C = rjl_consts(R);
+    emu_launch(k_rjl_density<true, RjlC>, nb, 1, FT, N, pos, lv, C, box, W, part.data(), SlabDev{});
     *energy = sum_parts(part, nb, 1.0);
-    emu_launch(k_rjl_force, nb, 1, FT, N, (const double4*)pos, frc, ListView{nl0, nn0, stride}, C, box, W, SlabDev{}, overwrite);
-    return 0;
+    emu_launch(k_rjl_force<RjlC>, nb, 1, FT, N, (const double4*)pos, frc, lv, C, box, W, SlabDev{}, overwrite);
+    return 1;
 }
 
 // tb: bond orders, per-(slot, atom) force parts, reduction; energy from a second sweep (energy_interaction)

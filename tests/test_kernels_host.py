@@ -53,7 +53,7 @@ class DeviceLayout:
 
     def ell(self, g1, g2, maxn, rcut):
         own, par = self.members(g1), self.members(g2)
-        nlist = np.zeros((maxn, self.stride), np.int32)
+        nlist = np.zeros((maxn + 2, self.stride), np.int32)   # two spare rows of valid slot numbers, as capi.cu allocates them
         nnum = np.zeros(self.stride, np.int32)
         for i in np.where(own)[0]:
             js = np.where(par & (self.r2[i] < rcut * rcut) & (np.arange(self.n) != i))[0]
@@ -89,7 +89,7 @@ def ptr(a, t):
     return a.ctypes.data_as(t)
 
 
-def run_case(L, case, seed=1, rjl_overwrite_first=False, lj1g_pipe=False):
+def run_case(L, case, seed=1, rjl_overwrite_first=False, lj1g_pipe=False, rjl_gen=2, ran=None):
     lay = DeviceLayout(case, seed)
     frc4 = np.zeros((lay.n, 4))
     energies = []
@@ -109,8 +109,10 @@ def run_case(L, case, seed=1, rjl_overwrite_first=False, lj1g_pipe=False):
                       int(lj1g_pipe))
         elif it["name"] == "rjl":
             l0 = lay.ell(*lists[0][:4])
-            L.fh_rjl(lay.n, ptr(lay.pos4, DP), ptr(frc4, DP), C.c_size_t(lay.stride), ptr(l0[0], IP), ptr(l0[1], IP), ptr(prm, DP), ptr(lay.box, DP),
-                     int(rjl_overwrite_first and k == 0), C.byref(e))
+            g = L.fh_rjl(lay.n, ptr(lay.pos4, DP), ptr(frc4, DP), C.c_size_t(lay.stride), ptr(l0[0], IP), ptr(l0[1], IP), ptr(prm, DP), ptr(lay.box, DP),
+                     int(rjl_overwrite_first and k == 0), C.byref(e), int(rjl_gen))
+            if ran is not None:
+                ran.append(g)
         elif it["name"] == "tb":
             l0 = lay.ell(*lists[0][:4])
             carbon_list = l0
@@ -162,6 +164,28 @@ def test_emulated_rjl_store_variant_is_bitwise_the_accumulate_variant(kernels):
     a, ea = run_case(kernels, case)
     b, eb = run_case(kernels, case, rjl_overwrite_first=True)
     assert np.array_equal(a, b) and np.array_equal(ea, eb)
+
+
+def test_emulated_rjl_generations(oracle_lib, kernels):
+    """Second-generation rjl pair routines (default) against the oracle and against the first generation: jittered crystal with
+    pairs in all three classes (r < R1, switch zone, beyond R2), boundary atoms whose pairs need the minimum image, rows of odd
+    and even length; a parameter set the second generation refuses (R2 beyond the half box) falls back to the first."""
+    cases = [small_cases()["cu_fcc"], inputs.cu_fcc(ncell=4, jitter=0.25, seed=5, period=5), inputs.cu_fcc(cells=(5, 4, 6), jitter=0.3, seed=9, period=5)]
+    for case in cases:
+        o = oracle(case)
+        o.advance("nvt", case["integrators"][0][1], 0, 1)
+        fo, eo = o.download()[2], o.energies()[0]
+        ran = []
+        f2, e2 = run_case(kernels, case, ran=ran)
+        f1, e1 = run_case(kernels, case, rjl_gen=1, ran=ran)
+        assert ran == [2, 1]
+        assert rel_err(f2, fo) < RTOL and rel_err(e2, eo) < RTOL
+        assert rel_err(f1, fo) < RTOL and rel_err(e1, eo) < RTOL
+        assert rel_err(f2, f1) < 5e-11 and rel_err(e2, e1) < 5e-11   # rsqrt_q: host stand-in seed off by up to 1.9e-6 -> 5e-12 in r (device 9e-7 -> 1.3e-12), times |exponent| <= 15
+    small = inputs.cu_fcc(ncell=3, jitter=0.2, seed=3, period=5)       # box 10.8 A: half box 5.42 < R2 = 6.0
+    ran = []
+    f, e = run_case(kernels, small, ran=ran)
+    assert ran == [1]
 
 
 # ---- neighbour-list build (nl.cu) ---------------------------------------------------------------------------------------------

@@ -91,3 +91,33 @@ def test_rsqrt(lib):
     got = np.array([lib.mx_rsqrt(float(x)) for x in xs])
     ref = (1 / np.sqrt(xs.astype(np.longdouble))).astype(np.float64)
     assert np.max(np.abs(got - ref) / ref) < 5e-16
+
+
+def test_short_forms(lib):
+    """The reduced-instruction variants used by the second-generation rjl kernels: exp_m, rsqrt_q, cos_switch_m, half_switch."""
+    for f in (lib.mx_exp_m, lib.mx_rsqrt_q, lib.mx_half_switch):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double]
+    lib.mx_cos_switch_m.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([rng.uniform(-40, 40, 40000), [0.0, -0.0, 0.34657359, -0.34657359, 0.34657360, 1e-300]])
+    got = np.array([lib.mx_exp_m(float(x)) for x in xs])
+    ref = np.exp(xs.astype(np.longdouble)).astype(np.float64)
+    assert np.max(np.abs(got - ref) / ref) < 8e-15
+    xs = rng.uniform(-690, 690, 20000)
+    got = np.array([lib.mx_exp_m(float(x)) for x in xs])
+    ref = np.exp(xs.astype(np.longdouble)).astype(np.float64)
+    assert np.max(np.abs(got - ref) / ref) < 3e-14
+    xs = np.concatenate([rng.uniform(0.01, 200, 20000), 10.0 ** rng.uniform(-10, 10, 5000)])
+    got = np.array([lib.mx_rsqrt_q(float(x)) for x in xs])
+    ref = (1 / np.sqrt(xs.astype(np.longdouble))).astype(np.float64)
+    assert np.max(np.abs(got - ref) / ref) < 1e-11   # host stand-in seed is up to 1.9e-6 off (device: 9e-7 -> 1.3e-12)
+    xs = np.concatenate([rng.uniform(0, np.pi, 40000), [0.0, np.pi / 2, np.pi, 3.14159265358979, 1e-9, np.pi - 1e-9]])
+    f, s = C.c_double(), C.c_double()
+    err = errh = 0.0
+    for x in xs:
+        lib.mx_cos_switch_m(float(x), C.byref(f), C.byref(s))
+        xl = np.longdouble(x)
+        err = max(err, abs(f.value - float((1 + np.cos(xl)) / 2)), abs(s.value - float(np.sin(xl))))
+        errh = max(errh, abs(lib.mx_half_switch(float(x)) - float((1 + np.cos(xl)) / 2)))
+    assert err < 2e-14 and errh < 1e-15, (err, errh)

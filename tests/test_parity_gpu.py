@@ -145,6 +145,10 @@ def test_device_math_functions():
     assert lib.pfmds_selftest_math(0, err) == 0
     print("device math errors: exp %.2e switch %.2e rsqrt %.2e seed %.2e" % tuple(err))
     assert err[0] < 3e-14 and err[1] < 1e-15 and err[2] < 1e-15
+    lib.pfmds_selftest_math2.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    assert lib.pfmds_selftest_math2(0, err) == 0
+    print("short forms: exp %.2e switch %.2e rsqrt_q %.2e exp(wide) %.2e" % tuple(err))
+    assert err[0] < 1e-14 and err[1] < 2e-14 and err[2] < 3e-12 and err[3] < 4e-14
 
 
 @pytest.mark.parametrize("name", list(CASES))
