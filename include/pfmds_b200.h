@@ -94,6 +94,15 @@ int pfmds_advance(pfmds_ctx* ctx, int integrator, double dt, int first_md_step, 
  * md_simulation.f90:188), so the pfmds_energies that follows needs no second sweep over the neighbour lists. */
 int pfmds_advance_with_energy(pfmds_ctx* ctx, int integrator, double dt, int first_md_step, int n_steps);
 
+/* md() with period_log = 1 reads the energies after every step (md_simulation.f90:188-199).  This call runs n_steps steps like
+ * pfmds_advance; the steps with mod(step, log_period) == 0 evaluate the potential energies in their force pass and append what
+ * pfmds_energies would return to a log that stays on the device, and all rows come back with ONE copy at the end of the call:
+ * rows[r*row_len + ...] = e_inter[n_interactions], kinetic energy, temperature, e_nhc[n_nhc]  (row_len >= n_interactions+2+n_nhc),
+ * *n_rows = number of logged steps.  Same numbers, bit for bit, as pfmds_advance_with_energy(1 step) + pfmds_energies per
+ * logged step.  Synchronises once. */
+int pfmds_advance_logged(pfmds_ctx* ctx, int integrator, double dt, int first_md_step, int n_steps, int log_period, double* rows,
+                         int row_len, int* n_rows);
+
 /* calculate_potential_energies + calculate_temperature(all_moving) + calculate_nose_hoover_chain_energy
  * (md_simulation.f90:191-198).  e_inter[n_interactions], e_nhc[n_nhc].  Synchronises. */
 int pfmds_energies(pfmds_ctx* ctx, double* e_inter, double* kinetic_energy, double* temperature, double* e_nhc);

@@ -48,6 +48,25 @@ int oracle_add_interaction(oracle_ctx* c, const char* name, int np, const double
         c->eng.add_interaction(s));
 }
 int oracle_advance(oracle_ctx* c, int kind, double dt, int first, int n) { GUARD(c->eng.advance(kind, dt, first, n)); }
+// checker twin of pfmds_advance_logged: the reference's sequence, one step and one energy evaluation at a time (md_simulation.f90:138-199)
+int oracle_advance_logged(oracle_ctx* c, int kind, double dt, int first, int n, int log_period, double* rows, int row_len, int* n_rows) {
+    GUARD(
+        int r = 0;
+        for (int s = first; s < first + n; ++s) {
+            c->eng.advance(kind, dt, s, 1);
+            if (log_period < 1 || s % log_period != 0) continue;
+            std::vector<double> ei, en;
+            double ke = 0, temp = 0;
+            c->eng.energies(ei, ke, temp, en);
+            if ((int)(ei.size() + 2 + en.size()) > row_len) throw std::runtime_error("error: log rows too short");
+            double* out = rows + (size_t)r * row_len;
+            std::copy(ei.begin(), ei.end(), out);
+            out[ei.size()] = ke; out[ei.size() + 1] = temp;
+            std::copy(en.begin(), en.end(), out + ei.size() + 2);
+            ++r;
+        }
+        if (n_rows) *n_rows = r);
+}
 int oracle_energies(oracle_ctx* c, double* e_inter, double* ke, double* temp, double* e_nhc) {
     GUARD(
         std::vector<double> ei, en; c->eng.energies(ei, *ke, *temp, en);

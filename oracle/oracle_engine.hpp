@@ -80,6 +80,17 @@ struct OracleEngine {
         init_time_steps(sys.dt, dt);
         for (int t = first; t < first + n; ++t) sys.step(t, kind_names.at((size_t)kind));
     }
+    // the reference's own sequence: one step, one energy evaluation (md_simulation.f90:138-199)
+    void advance_logged(int kind, double dt, int first, int n, int log_period, std::vector<pfmds_host::EnergyRow>& rows) {
+        rows.clear();
+        for (int t = first; t < first + n; ++t) {
+            advance(kind, dt, t, 1);
+            if (t % log_period != 0) continue;
+            pfmds_host::EnergyRow r;
+            energies(r.e_inter, r.ke, r.temp, r.e_nhc);
+            rows.push_back(r);
+        }
+    }
     void energies(std::vector<double>& e_inter, double& ke, double& temp, std::vector<double>& e_nhc) {  // md_simulation.f90:190-199
         double t0 = omp_wtime();
         calculate_potential_energies(sys.interactions);

@@ -753,6 +753,82 @@ static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, boo
     });
 }
 
+// one row of the device-resident energy log: [e_inter(n_inter), KE(all_moving), x v q of every chain]
+__global__ void k_log_row(int n_inter, const double* __restrict__ energy, const double* __restrict__ ke, NhcPack P, double* __restrict__ row) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int k = 0; k < n_inter; ++k) row[k] = energy[k];
+    row[n_inter] = ke[0];
+    int o = n_inter + 1;
+    for (int t = 0; t < P.n; ++t)
+        for (int i = 0; i < 3 * P.M[t]; ++i) row[o++] = P.state[t][i];
+}
+
+// md() with period_log = 1 asks for the energies after every step (md_simulation.f90:188-199); through pfmds_advance +
+// pfmds_energies that is one host round trip per step.  Here the steps of the call that satisfy mod(step, log_period) == 0
+// evaluate the energies in their force pass and append what pfmds_energies would return to a log kept on the device; the
+// host gets all rows with one copy when the call ends.  Row = e_inter[n_inter], KE, temperature, e_nhc[n_nhc]; the numbers
+// are those of the one-step-at-a-time sequence, bit for bit (same kernels in the same order).
+int pfmds_advance_logged(pfmds_ctx* c, int kind, double dt, int first, int n, int log_period, double* rows, int row_len, int* n_rows) {
+    if (!c) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        if (n < 0 || first < 0 || log_period < 1) fail(PFMDS_ERR_INVALID, "error: bad step range");
+        CK(cudaSetDevice(c->dev));
+        finalize(c);
+        if (c->nhc.size() > NHC_MAXF) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: pfmds_advance_logged with more than 4 thermostats");
+        const int nI = (int)c->inter.size(), nT = (int)c->nhc.size();
+        if (!rows || row_len < nI + 2 + nT) fail(PFMDS_ERR_INVALID, "error: pfmds_advance_logged needs rows of n_interactions + 2 + n_nhc doubles");
+        int D = nI + 1;
+        for (auto& t : c->nhc) D += 3 * t.M;
+        int want = 0;
+        for (int s = first; s < first + n; ++s) want += (s % log_period == 0);
+        if ((size_t)want * D > c->log_cap) {
+            if (c->logbuf) CK(cudaFree(c->logbuf));
+            c->logbuf = nullptr; c->log_cap = 0;
+            CK(cudaMalloc(&c->logbuf, sizeof(double) * (size_t)want * D));
+            c->log_cap = (size_t)want * D;
+        }
+        NhcPack P{};
+        P.n = nT;
+        for (int k = 0; k < nT; ++k) { P.state[k] = c->nhc[k].state; P.M[k] = c->nhc[k].M; }
+        std::vector<int> gsize;
+        int r = 0;
+        for (int s = first; s < first + n; ++s) {
+            const bool logged = s % log_period == 0;
+            apply_group_changes(c, s);
+            do_step(c, s, kind, dt, s == first, logged);
+            if (!logged) continue;
+            integ_flush_pending(c);                              // as pfmds_energies: KE of the velocities the host would download
+            integ_kinetic_energy(c, c->all_moving, c->red);
+            LAUNCH((k_log_row), 1, 32, c->st, nI, c->energy, c->red, P, c->logbuf + (size_t)r * D);
+            c->launches += 1;
+            gsize.push_back(group_size(c, c->all_moving));
+            ++r;
+        }
+        std::vector<double> h((size_t)r * D + 1, 0.);
+        if (r) CK(cudaMemcpyAsync(h.data(), c->logbuf, sizeof(double) * (size_t)r * D, cudaMemcpyDeviceToHost, c->st));
+        check_device_error(c);  // synchronises
+        for (int i = 0; i < r; ++i) {
+            const double* in = h.data() + (size_t)i * D;
+            double* out = rows + (size_t)i * row_len;
+            for (int k = 0; k < nI; ++k) out[k] = in[k];
+            const double ke = in[nI];
+            out[nI] = ke;
+            out[nI + 1] = 2 * ke / PFMDS_KB / (3 * (double)gsize[(size_t)i]);  // calculate_temperature, md_general.f90:301-311
+            const double* x = in + nI + 1;
+            for (int k = 0; k < nT; ++k) {  // calculate_nose_hoover_chain_energy, md_integrators.f90:247-260
+                const Nhc& t = c->nhc[(size_t)k];
+                const double *v = x + t.M, *q = x + 2 * t.M;
+                const double kt = PFMDS_KB * t.temperature;
+                double e = q[0] / 2 * (v[0] * v[0]) + 3. * t.L * kt * x[0];
+                for (int j = 1; j < t.M; ++j) e = e + q[j] / 2 * (v[j] * v[j]) + kt * x[j];
+                out[nI + 2 + k] = e;
+                x += 3 * t.M;
+            }
+        }
+        if (n_rows) *n_rows = r;
+    });
+}
+
 int pfmds_synchronize(pfmds_ctx* c) {
     if (!c) return PFMDS_ERR_INVALID;
     return guarded(c, [&] { CK(cudaSetDevice(c->dev)); CK(cudaStreamSynchronize(c->st)); check_device_error(c); });
@@ -1344,7 +1420,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     for (int* r : c->d_grank) cudaFree(r);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,
-                    c->cid, c->posf, c->scan_tmp, c->part, c->red, c->energy, c->err};
+                    c->cid, c->posf, c->scan_tmp, c->part, c->red, c->energy, c->err, c->logbuf};
     for (void* p : ptrs) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -68,6 +68,8 @@ struct pfmds_ctx {
     size_t part_cap = 0;
     double* red = nullptr;    // [64] reduced values
     double* energy = nullptr; // [n_inter] device energies
+    double* logbuf = nullptr; // device-resident energy log of pfmds_advance_logged
+    size_t log_cap = 0;
     int* err = nullptr;       // [PFMDS_ERRW]
     // host description
     std::vector<std::vector<int>> groups;  // 1-based group -> 1-based file indexes

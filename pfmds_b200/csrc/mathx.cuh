@@ -231,7 +231,7 @@ MX_HD double exp_m(double x) {
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = p * p;
-    return from_words(hi_word(p) + (lo_word(t) << 20), lo_word(p));  // low word of t holds k (two's complement)
+    return from_words(hi_word(p) + (int)((unsigned int)lo_word(t) << 20), lo_word(p));  // low word of t holds k (two's complement)
 }
 
 // two independent exp_m evaluated side by side: every coefficient is fetched once for both Horner chains, and the two
@@ -253,8 +253,8 @@ MX_HD void exp_m2(double xa, double xb, double& ea, double& eb, double l2e = 1.4
     pa = fma(pa, ra, 0.5); pb = fma(pb, rb, 0.5);
     pa = fma(pa, ra, 1.0); pb = fma(pb, rb, 1.0);
     pa = pa * pa; pb = pb * pb;
-    ea = from_words(hi_word(pa) + (lo_word(ta) << 20), lo_word(pa));
-    eb = from_words(hi_word(pb) + (lo_word(tb) << 20), lo_word(pb));
+    ea = from_words(hi_word(pa) + (int)((unsigned int)lo_word(ta) << 20), lo_word(pa));
+    eb = from_words(hi_word(pb) + (int)((unsigned int)lo_word(tb) << 20), lo_word(pb));
 }
 
 // 1/sqrt(x) for normal positive x: hardware seed y (relative error d <= 9e-7) and one second-order step written so that it

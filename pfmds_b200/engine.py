@@ -47,6 +47,7 @@ _SIGS = {
     "add_interaction": [C.c_void_p, C.c_char_p, C.c_int, _dp, C.c_int, _ip, _ip, _dp, _ip],
     "advance": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int],
     "advance_with_energy": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int],
+    "advance_logged": [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip],
     "energies": [C.c_void_p, _dp, _dp, _dp, _dp],
     "diagnostics": [C.c_void_p, _dp, _dp, _dp, _dp, _ip],
     "download": [C.c_void_p, _dp, _dp, _dp],
@@ -160,6 +161,18 @@ class Engine:
         kind = KIND[integrator] if isinstance(integrator, str) else int(integrator)
         name = "advance_with_energy" if with_energy and hasattr(self._lib, self._p + "advance_with_energy") else "advance"
         self._call(name, self._ctx, kind, float(dt), int(first_md_step), int(n_steps))
+
+    def advance_logged(self, integrator, dt, first_md_step, n_steps, log_period=1):
+        """n_steps steps; the energies of every step with step % log_period == 0 are logged on the device and returned with one
+        copy: (e_inter[rows, n_inter], ke[rows], temperature[rows], e_nhc[rows, n_nhc])."""
+        kind = KIND[integrator] if isinstance(integrator, str) else int(integrator)
+        ni, nt = len(self.inter), len(self.nhc_M)
+        w = ni + 2 + nt
+        rows = np.zeros((max(1, n_steps), w))
+        nr = C.c_int()
+        self._call("advance_logged", self._ctx, kind, float(dt), int(first_md_step), int(n_steps), int(log_period), _d(rows), w, C.byref(nr))
+        rows = rows[: nr.value]
+        return rows[:, :ni].copy(), rows[:, ni].copy(), rows[:, ni + 1].copy(), rows[:, ni + 2:].copy()
 
     def synchronize(self):
         self._call("synchronize", self._ctx)

@@ -36,6 +36,21 @@ public:
     void advance(int kind, double dt, int first, int n, bool energy_after_last) {
         ck(energy_after_last ? pfmds_advance_with_energy(ctx_, kind, dt, first, n) : pfmds_advance(ctx_, kind, dt, first, n));
     }
+    // n steps; the energies of every step with step % log_period == 0, kept on the device and fetched with one copy
+    void advance_logged(int kind, double dt, int first, int n, int log_period, std::vector<EnergyRow>& rows) {
+        const int w = n_inter_ + 2 + n_nhc_;
+        std::vector<double> buf((size_t)w * (size_t)(n > 0 ? n : 1), 0.);
+        int nr = 0;
+        ck(pfmds_advance_logged(ctx_, kind, dt, first, n, log_period, buf.data(), w, &nr));
+        rows.assign((size_t)nr, EnergyRow());
+        for (int r = 0; r < nr; ++r) {
+            const double* p = buf.data() + (size_t)r * w;
+            rows[(size_t)r].e_inter.assign(p, p + n_inter_);
+            rows[(size_t)r].ke = p[n_inter_];
+            rows[(size_t)r].temp = p[n_inter_ + 1];
+            rows[(size_t)r].e_nhc.assign(p + n_inter_ + 2, p + n_inter_ + 2 + n_nhc_);
+        }
+    }
     void energies(std::vector<double>& e_inter, double& ke, double& temp, std::vector<double>& e_nhc) {
         e_inter.assign((size_t)n_inter_ + 1, 0.);
         e_nhc.assign((size_t)n_nhc_ + 1, 0.);

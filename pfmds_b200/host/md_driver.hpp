@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -296,6 +297,9 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
         return needs_energy(t, idx, kind) || (t % s.integrators[idx].period_snapshot == 0 && t != 0) || t % s.period_traj == 0 || checkpoint_step(t);
     };
 
+    // PFMDS_HOST_STEPWISE_LOG=1: one engine call and one energy read per logged step, as the reference's loop does (A/B and tests)
+    const char* sw_env = std::getenv("PFMDS_HOST_STEPWISE_LOG");
+    const bool stepwise_log = sw_env && sw_env[0] == '1';
     int md_step = 0;
     bool exited = false;
     if (!extras.restart_file.empty()) {
@@ -334,20 +338,22 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
             exited = true;
             break;
         }
-        // how many steps can be queued on the device before the host has to look at anything
+        // How many steps can be queued on the device before the host has to look at anything.  A step whose only event is its
+        // log row (`soft`) does not end the queue: its energies are logged on the device (advance_logged) and read with the rest.
+        const int period_log = s.integrators[integrator_index].period_log;
+        auto soft = [&](int t) {
+            return !stepwise_log && kind != KIND_NVMS && t % period_log == 0 && t % out_period != 0 &&
+                   !(t % s.integrators[integrator_index].period_snapshot == 0 && t != 0) && t % s.period_traj != 0 && !checkpoint_step(t);
+        };
         int n = 1;
-        while (md_step + n <= limit && !event_after(md_step + n - 1, integrator_index, kind) &&
-               !(md_step + n - 1 == cum_len(integrator_index)))
+        bool soft_inside = false;
+        while (md_step + n <= limit && (!event_after(md_step + n - 1, integrator_index, kind) || soft(md_step + n - 1)) &&
+               !(md_step + n - 1 == cum_len(integrator_index))) {
+            soft_inside |= soft(md_step + n - 1);
             ++n;
-        eng.advance(kind, ts1, md_step, n, needs_energy(md_step + n - 1, integrator_index, kind));
-        for (int t = md_step; t < md_step + n; ++t) {
-            prev_potential_energy = potential_energy;  // :158
-            if (t != 0) simulation_time = simulation_time + ts1;  // :184
         }
-        md_step += n - 1;  // md_step is now the last executed step
-
-        if (needs_energy(md_step, integrator_index, kind)) {  // :188-231
-            eng.energies(e_inter, kinetic_energy, temperature, e_nhc_dev);
+        // the energies of a step, folded into the running totals and the log (md_simulation.f90:190-210)
+        auto absorb = [&](int t) {
             potential_energy = 0.;
             for (double e : e_inter) potential_energy += e;
             if (kind == KIND_NVT) e_nhc = e_nhc_dev;  // nhc%e is refreshed only while nvt runs (:194-198)
@@ -355,14 +361,36 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
             for (double e : e_nhc) nose_hoover_energy += e;
             total_energy = potential_energy + kinetic_energy;
             conserved_energy = total_energy + nose_hoover_energy;
-            if (md_step % s.integrators[integrator_index].period_log == 0) {
-                std::string l = A(trim(integrator_name), 6, (int)trim(integrator_name).size()) + I(md_step, 9) + F(simulation_time, 24, 6) +
+            if (t % period_log == 0) {
+                std::string l = A(trim(integrator_name), 6, (int)trim(integrator_name).size()) + I(t, 9) + F(simulation_time, 24, 6) +
                                 F(conserved_energy, 24, 6) + F(nose_hoover_energy, 24, 6) + F(total_energy, 24, 6) + F(potential_energy, 24, 6) +
                                 F(kinetic_energy, 24, 6) + F(temperature, 24, 6);
                 for (double e : e_inter) l += F(e, 20, 9);
                 for (double e : e_nhc) l += F(e, 20, 9);
                 std::fprintf(logf, "%s\n", l.c_str());
             }
+        };
+        std::vector<EnergyRow> rows;
+        if (soft_inside) eng.advance_logged(kind, ts1, md_step, n, period_log, rows);
+        else eng.advance(kind, ts1, md_step, n, needs_energy(md_step + n - 1, integrator_index, kind));
+        size_t row = 0;
+        for (int t = md_step; t < md_step + n; ++t) {
+            prev_potential_energy = potential_energy;  // :158
+            if (t != 0) simulation_time = simulation_time + ts1;  // :184
+            if (soft_inside && t % period_log == 0) {
+                if (row >= rows.size()) throw std::runtime_error("error: the engine logged fewer energy rows than steps asked for");
+                if (t != md_step + n - 1) {  // the last step of the queue takes the ordinary path below
+                    e_inter = rows[row].e_inter; kinetic_energy = rows[row].ke; temperature = rows[row].temp; e_nhc_dev = rows[row].e_nhc;
+                    absorb(t);
+                }
+                ++row;
+            }
+        }
+        md_step += n - 1;  // md_step is now the last executed step
+
+        if (needs_energy(md_step, integrator_index, kind)) {  // :188-231
+            eng.energies(e_inter, kinetic_energy, temperature, e_nhc_dev);
+            absorb(md_step);
             if (md_step % out_period == 0) {
                 double fs[3], mc[3], mcv[3], mav_vel;
                 eng.diagnostics(fs, mc, mcv, mav_vel, nl_load);

@@ -12,6 +12,7 @@ namespace pfmds_host {
 
 struct IntegratorParams { std::string int_name = "none"; double dt = 0; int l = 0, period_snapshot = 1, period_log = 1; };
 struct NhcSpec { int group = 1; double temperature = 0; int M = 1; double q1 = 1; };
+struct EnergyRow { std::vector<double> e_inter; double ke = 0, temp = 0; std::vector<double> e_nhc; };  // what energies() returns, per logged step
 struct ListSpec { int g1 = 0, g2 = 0, neighb_num_max = 0; double r_cut = 0; int update_period = 1; };
 struct InteractionSpec {
     std::string name, parameters_file;

@@ -62,6 +62,11 @@ def test_parity_misc(monkeypatch, fn):
     getattr(replay(monkeypatch, "test_parity_gpu"), fn)()
 
 
+@pytest.mark.parametrize("name", ["ab_gas", "cu_fcc", "gr_cu_ljc"])
+def test_advance_logged_rows(monkeypatch, name):
+    replay(monkeypatch, "test_parity_gpu").test_advance_logged_rows(name)
+
+
 @pytest.mark.parametrize("name", SMALL)
 def test_golden_fixtures_and_in_step_energies(monkeypatch, name):
     m = replay(monkeypatch, "test_parity_gpu")
@@ -102,6 +107,10 @@ def test_save_and_restore_state(monkeypatch):
 @pytest.mark.parametrize("which", ["ab_gas", "graphene"])
 def test_host_outputs(monkeypatch, tmp_path, oracle_lib, which):
     replay(monkeypatch, "test_host_gpu", EXE=B.EXE).test_same_outputs_as_the_cpu_reference_port(tmp_path, None, oracle_lib, which)
+
+
+def test_host_queued_log(monkeypatch, tmp_path):
+    replay(monkeypatch, "test_host_gpu", EXE=B.EXE).test_queued_log_rows_are_the_stepwise_log(tmp_path, None)
 
 
 def test_host_ensemble_ranks(monkeypatch, tmp_path):

@@ -157,3 +157,25 @@ def test_new_velocities_are_seeded_and_order_independent(tmp_path):
     assert rr.returncode == 0
     c = read_xyz(d2 + "0002-snapshot_000001.xyz")
     assert not np.allclose(c["vel"], a["vel"])
+
+
+def test_queued_log_rows_equal_the_stepwise_log(tmp_path):
+    """period_log = 1 with a sparse stdout period: the driver queues the steps between hard events and reads their log rows in
+    one go (advance_logged); PFMDS_HOST_STEPWISE_LOG=1 is the reference's loop, one energy read per step.  Same files."""
+    case = _tiny_case()
+    case["integrators"] = [(n, dt, ln, 20, 1 if n != "nve" else 3) for (n, dt, ln, _, _) in case["integrators"]]
+    d1, r1 = _run(tmp_path / "queued", case)
+    assert r1.returncode == 0, r1.stdout
+    os.environ["PFMDS_HOST_STEPWISE_LOG"] = "1"
+    try:
+        d2, r2 = _run(tmp_path / "stepwise", case)
+    finally:
+        del os.environ["PFMDS_HOST_STEPWISE_LOG"]
+    assert r2.returncode == 0, r2.stdout
+    a, b = open(d1 + "t_md_run.log").read(), open(d2 + "t_md_run.log").read()
+    assert len(a.splitlines()) > 45 and a == b
+    from pfmds_b200.host_io import read_xyz
+    for f in ("t_final_init.xyz", "t_snapshot_000020.xyz"):   # the oracle's OpenMP sums differ in the last bits from run to run
+        x, y = read_xyz(d1 + f), read_xyz(d2 + f)
+        assert np.allclose(x["pos"], y["pos"], rtol=0, atol=1e-10) and np.allclose(x["vel"], y["vel"], rtol=0, atol=1e-12)
+    assert len(open(d1 + "t_traj_03.xyz").read().splitlines()) == len(open(d2 + "t_traj_03.xyz").read().splitlines())

@@ -66,3 +66,23 @@ def test_gpu_ensemble_ranks(tmp_path, cuda_lib):
     a, c = read_xyz(d + "0001-a_final_init.xyz"), read_xyz(d + "0001-c_final_init.xyz")
     b = read_xyz(d + "0002-b_final_init.xyz")
     assert np.array_equal(a["pos"], c["pos"]) and np.array_equal(a["pos"], b["pos"])  # same input, deterministic kernels
+
+
+def test_queued_log_rows_are_the_stepwise_log(tmp_path, cuda_lib):
+    """period_log = 1 under a sparse stdout period: the host queues the steps between hard events (pfmds_advance_logged, one
+    copy of the log rows per queue) — every output file is identical to the run that reads the energies step by step."""
+    case = inputs.cu_fcc(ncell=5, steps=45, period=5, jitter=0.05)
+    case["integrators"] = [(n, dt, ln, 20, 1) for (n, dt, ln, _, _) in case["integrators"]]
+    case["roles"]["period_traj"] = 15
+    outs = []
+    for tag, env in (("queued", {}), ("stepwise", {"PFMDS_HOST_STEPWISE_LOG": "1"})):
+        d = str(tmp_path / tag) + os.sep
+        inputs.write_case(d, case)
+        r = subprocess.run([EXE, "-ipath", d, "-p", d + "x_", "-op", "25"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout[-2000:]
+        outs.append(d)
+    a, b = outs
+    log = open(a + "x_md_run.log").read()
+    assert len(_rows(a + "x_md_run.log")) == 46 and log == open(b + "x_md_run.log").read()
+    for f in ("x_final_init.xyz", "x_snapshot_000020.xyz", "x_snapshot_000040.xyz"):   # (the trajectory group of this case is empty)
+        assert open(a + f).read() == open(b + f).read(), f

@@ -176,3 +176,22 @@ def test_half_list_rule_drops_pairs_for_non_monotone_groups():
     (e_mono, half_mono, full_mono), (e_swap, half_swap, full_swap) = e
     assert full_mono == full_swap and half_mono * 2 == full_mono      # monotone: the half list holds every pair once
     assert half_swap != half_mono and abs(e_swap - e_mono) > 1e-6 * abs(e_mono)   # swapped columns: pairs are lost
+
+
+def test_advance_logged_is_the_stepwise_sequence(oracle_lib):
+    """oracle_advance_logged (checker twin of pfmds_advance_logged): rows = energies() after each logged step."""
+    from util import oracle, small_cases
+    case = small_cases()["cu_fcc"]
+    a, b = oracle(case), oracle(case)
+    a.advance("nvt", 2.0, 0, 1)
+    rows = a.advance_logged("nvt", 2.0, 1, 9, log_period=2)
+    b.advance("nvt", 2.0, 0, 1)
+    got = []
+    for s in range(1, 10):
+        b.advance("nvt", 2.0, s, 1)
+        if s % 2 == 0:
+            got.append(b.energies())
+    assert len(got) == 4 and rows[0].shape == (4, 1)
+    for r, g in enumerate(got):   # OpenMP partial sums: two oracle runs agree to rounding, not bit for bit
+        for k in range(4):
+            assert np.allclose(rows[k][r], g[k], rtol=1e-11, atol=1e-12)

@@ -286,3 +286,30 @@ def test_store_instead_of_zero_plus_accumulate():
     pb, vb, fb = eb.download()
     assert np.array_equal(fa, fb) and np.array_equal(pa, pb) and np.array_equal(va, vb)
     assert np.abs(fa).max() > 0.1
+
+
+@pytest.mark.parametrize("name", ["ab_gas", "cu_fcc", "gr_cu_ljc"])
+def test_advance_logged_rows(name):
+    """pfmds_advance_logged: the device-resident energy log returns, bit for bit, what advance_with_energy(1) + energies() give
+    step by step, and leaves the same state; against the oracle the rows agree to 1e-9."""
+    case = CASES[name]
+    integ, dt = case["integrators"][0][0], case["integrators"][0][1]
+    a, b, o = gpu(case), gpu(case), oracle(case)
+    for e in (a, b, o):
+        e.advance(integ, dt, 0, 1)
+    rows = a.advance_logged(integ, dt, 1, 12, log_period=3)
+    ref = o.advance_logged(integ, dt, 1, 12, log_period=3)
+    got = []
+    for s in range(1, 13):
+        b.advance(integ, dt, s, 1, with_energy=(s % 3 == 0))
+        if s % 3 == 0:
+            got.append(b.energies())
+    assert rows[0].shape[0] == 4
+    for r, g in enumerate(got):
+        assert np.array_equal(rows[0][r], g[0]) and rows[1][r] == g[1] and rows[2][r] == g[2] and np.array_equal(rows[3][r], g[3])
+    pa, va, fa = a.download()
+    pb, vb, fb = b.download()
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(fa, fb)
+    for k in range(4):
+        assert np.allclose(rows[k], ref[k], rtol=1e-7, atol=1e-9 * max(1.0, np.abs(ref[k]).max()))   # 12 steps of a trajectory, not step 0
+    assert np.allclose(rows[0][0], ref[0][0], rtol=RTOL * 100, atol=0)
