@@ -73,7 +73,7 @@ MX_HD double exp_fast(double x) {
     p = fma(p, r, EXP_C[1]);
     p = fma(p, r, EXP_C[0]);
     p = p * p;
-    return as_double(as_ll(p) + (k << 52));
+    return as_double(as_ll(p) + (long long)((unsigned long long)k << 52));
 }
 
 // exp(x) without the clamp, for arguments the caller has bounded to |x| < 700
@@ -95,7 +95,7 @@ MX_HD double exp_nc(double x) {
     p = fma(p, r, EXP_C[1]);
     p = fma(p, r, EXP_C[0]);
     p = p * p;
-    return as_double(as_ll(p) + (k << 52));
+    return as_double(as_ll(p) + (long long)((unsigned long long)k << 52));
 }
 
 // Cosine switch without selects: for a in [0, pi], u = a/2 - pi/4 in [-pi/4, pi/4],
@@ -267,7 +267,7 @@ MX_HD double rsqrt_q(double x) {
 #else
     double y = from_words(hi_word((double)(1.0f / sqrtf((float)x)) * (1.0 + 9e-7)), 0);
 #endif
-    double yh = from_words(hi_word(y) + 0x7ff00000, 0);  // -y/2
+    double yh = from_words((int)((unsigned int)hi_word(y) + 0x7ff00000u), 0);  // -y/2
     double b = fma(x * yh, y, 1.5);
     return y * b;
 }

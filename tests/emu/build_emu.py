@@ -12,10 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pfmds_b200", "csrc")
 HOST = os.path.join(ROOT, "pfmds_b200", "host")
-OUT = os.path.join(HERE, "_build")
+# PFMDS_EMU_SANITIZE=1: the same replay under AddressSanitizer + UBSan in its own directory (cudaMalloc maps onto malloc, so an
+# out-of-range slot number, list row or partial-sum index of a kernel is a heap-buffer-overflow report).  Run as
+#   LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 PFMDS_EMU_SANITIZE=1 pytest tests/test_emulated_library.py
+SAN = os.environ.get("PFMDS_EMU_SANITIZE") == "1"
+OUT = os.path.join(HERE, "_build_san" if SAN else "_build")
+SANFLAGS = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if SAN else []
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 SOURCES = ["capi.cu", "forces.cu", "nl.cu", "integrate.cu", "rebosc.cu"]
-FLAGS = ["-x", "c++", "-std=c++17", "-O2", "-ffp-contract=off", "-DPFMDS_EMU_LIB", "-DSMALL_N=0", "-fPIC"]
+FLAGS = ["-x", "c++", "-std=c++17", "-O1" if SAN else "-O2", "-ffp-contract=off", "-DPFMDS_EMU_LIB", "-DSMALL_N=0", "-fPIC"] + SANFLAGS
 LIB = os.path.join(OUT, "libpfmds_b200_emu.so")
 EXE = os.path.join(OUT, "run_md_simulation_emu")
 EXE_FIT = os.path.join(OUT, "run_gr_moire_fitting_emu")
@@ -43,15 +48,15 @@ def build_emu():
     stub = os.path.join(OUT, "slab_stub.o")
     objs.append(stub)
     if _newer(stub, [os.path.join(HERE, "slab_stub.cpp")] + hdrs):
-        jobs.append([CXX, "-std=c++17", "-O2", "-fPIC", "-c", os.path.join(HERE, "slab_stub.cpp"), "-o", stub])
+        jobs.append([CXX, "-std=c++17", "-O2", "-fPIC"] + SANFLAGS + ["-c", os.path.join(HERE, "slab_stub.cpp"), "-o", stub])
     with ThreadPoolExecutor(4) as ex:
         list(ex.map(_run, jobs))
     if jobs or _newer(LIB, objs):
-        _run([CXX, "-shared", "-o", LIB] + objs + ["-ldl", "-pthread"])
+        _run([CXX, "-shared"] + SANFLAGS + ["-o", LIB] + objs + ["-ldl", "-pthread"])
     host_deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))]
     for exe, src in ((EXE, "run_md_simulation.cpp"), (EXE_FIT, "run_gr_moire_fitting.cpp")):
         if _newer(exe, host_deps + [LIB]):
-            _run([CXX, "-O2", "-std=c++17", "-o", exe, os.path.join(HOST, src), "-pthread", "-L" + OUT, "-lpfmds_b200_emu", "-Wl,-rpath,$ORIGIN"])
+            _run([CXX, "-O2", "-std=c++17"] + SANFLAGS + ["-o", exe, os.path.join(HOST, src), "-pthread", "-L" + OUT, "-lpfmds_b200_emu", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 
