@@ -233,6 +233,48 @@ def time_variant(case, integrator, dt, local, env, W, K):
     return {"ms_per_step": ms / K, "steps": K, "kernels_ms_per_step": {k: round(v[0] / K, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])[:4]}}
 
 
+def e2e_steps(eng, integrator, dt, ke2e, stepwise=False):
+    """Steps 1..ke2e of the e2e leg with the energies of EVERY step brought to the host (period_log = 1).  Default: what the
+    run_md_simulation host does (md_driver.hpp) — one pfmds_advance_logged call, every step's energies produced by its force pass
+    and logged on the device, one D2H copy of the rows.  stepwise (slab mode, PFMDS_BENCH_STEPWISE_E2E=1, or if the logged call
+    fails): one pfmds_advance_with_energy(1) + pfmds_energies round trip per step.  Returns (D2H energy bytes per step, description)."""
+    if not stepwise:
+        try:
+            rows = eng.advance_logged(integrator, dt, 1, ke2e, log_period=1)
+            assert rows[0].shape[0] == ke2e and np.isfinite(rows[0]).all() and np.isfinite(rows[1]).all()
+            return 8 * (rows[0].shape[1] + 1 + rows[3].shape[1] * 3 * 3), "pfmds_advance_logged(%d steps, log_period 1: energies of every step, one D2H of the log)" % ke2e
+        except Exception as ex:
+            print("bench: pfmds_advance_logged failed (%r), e2e falls back to one call per step" % (ex,), file=sys.stderr)
+    e_bytes = 0
+    for s in range(1, ke2e + 1):
+        eng.advance(integrator, dt, s, 1, with_energy=True)
+        e = eng.energies()
+        e_bytes = 8 * (len(e[0]) + 1 + len(e[3]) * (3 * 3 + 2)) + 16
+    return e_bytes, "%d x [pfmds_advance_with_energy(1) + pfmds_energies (D2H)]" % ke2e
+
+
+def run_variants(local):
+    """--variants-only (child of the default run): ms/step of the rjl and lj1g kernel variants on this GPU, one JSON line."""
+    from pfmds_b200 import inputs
+    from pfmds_b200.build import build
+    build()
+    out = {"note": "child process, fresh contexts after the headline measurement, 21 warm-up + 100 timed steps each; `value` is the default configuration"}
+    case, integrator, _ = build_case("cu_fcc", seed=2, steps=200)
+    dt = case["integrators"][0][1]
+    ljc = inputs.lj_fluid(n_side=96, seed=2, steps=200)
+    for name, cs, integ, h, env in (
+            ("rjl_gen2 (default)", case, integrator, dt, {"PFMDS_RJL_GEN": "2"}),
+            ("rjl_gen1 (PFMDS_RJL_GEN=1, the round-1 kernels)", case, integrator, dt, {"PFMDS_RJL_GEN": "1"}),
+            ("lj_fluid 96^3 lj1g (default)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "0"}),
+            ("lj_fluid 96^3 lj1g pipelined (PFMDS_LJ1G_PIPE=1)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "1"})):
+        try:
+            out[name] = time_variant(cs, integ, h, local, env, 21, 100)
+        except Exception as ex:
+            out[name] = {"error": repr(ex)[:300]}
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -244,9 +286,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the A/B timing of alternative kernel variants after the headline measurement")
     ap.add_argument("--decomp", default="slab", choices=["slab", "ensemble"])
+    ap.add_argument("--variants-only", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--device", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.variants_only:
+        return run_variants(args.device)
 
     import torch
     from pfmds_b200.build import build
@@ -319,8 +365,8 @@ def main():
     value = n_total * K / (ms_max * 1e-3)
 
     # ---- e2e: through the C ABI with host buffers.  Per run: H2D of positions+velocities from pinned host
-    # memory, then every step pfmds_advance(1) + pfmds_energies (D2H of the step's energies, what md() logs
-    # with the reference's default out_period=1), and a final D2H of positions, velocities and forces.
+    # memory, then ke2e steps with the energies of every step read back (what md() logs with period_log = 1,
+    # see e2e_steps), and a final D2H of positions, velocities and forces.
     e2e = None
     if not args.no_e2e:
         ke2e = min(K, 100)
@@ -340,11 +386,7 @@ def main():
         else:
             eng.upload_ptr(hp.data_ptr(), hv.data_ptr())
         eng.advance(integrator, dt, 0, 1)
-        e_bytes = 0
-        for s in range(1, ke2e + 1):
-            eng.advance(integrator, dt, s, 1, with_energy=True)
-            e = eng.energies()
-            e_bytes = 8 * (len(e[0]) + 1 + len(e[3]) * (3 * 3 + 2)) + 16
+        e_bytes, how = e2e_steps(eng, integrator, dt, ke2e, stepwise=slab or bool(os.environ.get("PFMDS_BENCH_STEPWISE_E2E")))
         out = eng.download()
         barrier()
         t_e2e = time.perf_counter() - t0
@@ -353,7 +395,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": n_total * ke2e / float(te.item()), "unit": "atom-steps/s", "h2d_bytes_per_step": int(2 * 24 * n_atoms / ke2e),
                "d2h_bytes_per_step": int(e_bytes + (3 * 32 + 4) * n_atoms / ke2e), "steps": ke2e,
-               "what": "pfmds_upload(H2D pinned) + %d x [pfmds_advance_with_energy(1) + pfmds_energies (D2H)] + pfmds_download(D2H)" % ke2e}
+               "what": "pfmds_upload(H2D pinned) + " + how + " + pfmds_download(D2H)"}
         del out
 
     # per-rank view (explains stragglers in the lock-stepped slab mode): own kernel times and clocks
@@ -401,19 +443,18 @@ def main():
         cpu = {"value": n * (steps + 1) / tcpu, "unit": "atom-steps/s", "cores": cores, "kind": "port",
                "sample": "Cu fcc 20^3x4 = %d atoms, step 0 + %d NVT steps (1 O(N^2) rebuild), C++/OpenMP restatement of the reference, %.1f s" % (n, steps, tcpu)}
     # ---- kernel variants, same box, same run (A/B evidence for the defaults; never part of `value`) ----
+    # Measured by a CHILD process after this one has released its context: an experiment that faults (sticky CUDA error,
+    # abort) or hangs cannot take the headline line with it.
     variants = None
     if not args.no_variants and world == 1 and args.workload == "cu_fcc":
-        variants = {"note": "fresh contexts after the headline measurement, 21 warm-up + 100 timed steps each; `value` is the default configuration"}
         try:
             eng.close()
-            variants["rjl_gen2 (default)"] = time_variant(case, integrator, dt, local, {"PFMDS_RJL_GEN": "2"}, 21, 100)
-            variants["rjl_gen1 (PFMDS_RJL_GEN=1, the round-1 kernels)"] = time_variant(case, integrator, dt, local, {"PFMDS_RJL_GEN": "1"}, 21, 100)
-            from pfmds_b200 import inputs
-            ljc = inputs.lj_fluid(n_side=96, seed=2, steps=200)
-            variants["lj_fluid 96^3 lj1g (default)"] = time_variant(ljc, "nve", ljc["integrators"][0][1], local, {"PFMDS_LJ1G_PIPE": "0"}, 21, 100)
-            variants["lj_fluid 96^3 lj1g pipelined (PFMDS_LJ1G_PIPE=1)"] = time_variant(ljc, "nve", ljc["integrators"][0][1], local, {"PFMDS_LJ1G_PIPE": "1"}, 21, 100)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--variants-only", "--device", str(local)], stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, text=True, timeout=420)
+            rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            variants = json.loads(rows[-1]) if rows else {"error": "child exit %d: %s" % (r.returncode, r.stderr[-300:])}
         except Exception as ex:  # the headline line must survive a failing experiment
-            variants["error"] = repr(ex)[:300]
+            variants = {"error": repr(ex)[:300]}
     line = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -12,6 +13,8 @@
 #include "ctx.hpp"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
+
+static bool rjl_short_forms_ok(int dev);  // defined next to the device self-tests below
 
 namespace {
 
@@ -73,6 +76,19 @@ void check_device_error(pfmds_ctx* c) {
 }
 
 
+// The second-generation rjl kernels lean on properties of this device's MUFU.RSQ64H seed (relative error, zero low word) and on
+// bit-level exponent arithmetic (mathx.cuh short forms).  The first rjl context of a process has the device check them itself;
+// a device that misses the bounds gets the first generation, and says so.
+void check_rjl_generation(pfmds_ctx* c) {
+    if (c->rjl_gen == 1) return;
+    bool has_rjl = false;
+    for (auto& it : c->inter) has_rjl |= it.kind == K_RJL;
+    if (!has_rjl || rjl_short_forms_ok(c->dev)) return;
+    std::fprintf(stderr, "pfmds_b200: the short elementary functions of the second-generation rjl kernels missed their error bounds on device %d; "
+                         "using the first generation (PFMDS_RJL_GEN=1)\n", c->dev);
+    c->rjl_gen = 1;
+}
+
 // Slab mode: the masks came with pfmds_create_slab; validation works on group numbers and global sizes.
 void finalize_slab(pfmds_ctx* c) {
     if (!c->changes.empty()) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: group changes (deposition) in slab decomposition mode");
@@ -124,6 +140,7 @@ void finalize_slab(pfmds_ctx* c) {
             if (c->nhc[a].group == c->nhc[b].group) c->nhc_fusable = false;
     if (c->nhc.size() > 1) c->nhc_fusable = false;  // several thermostats: masks are not on the host in slab mode, keep the plain path
     if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
+    check_rjl_generation(c);
     c->first_overwrites = !c->inter.empty() && c->inter[0].kind == K_RJL && group_size(c, c->inter[0].nl[0].g1) == slab_n_global(c);
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
@@ -268,6 +285,7 @@ void finalize(pfmds_ctx* c) {
         CK(cudaMalloc(&c->d_grank[(size_t)ch.to - 1], sizeof(int) * (size_t)N));
         CK(cudaMemcpyAsync(c->d_grank[(size_t)ch.to - 1], rank.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, c->st));
     }
+    check_rjl_generation(c);
     c->first_overwrites = c->zero_all && c->changes.empty() && !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
@@ -521,6 +539,29 @@ __global__ void k_math_selftest2(int n, double* out) {
     atomicMax((unsigned long long*)&out[3], (unsigned long long)__double_as_longlong(e_wide));
 }
 #endif  // __CUDACC__
+static bool rjl_short_forms_ok(int dev) {
+#ifndef __CUDACC__
+    (void)dev;
+    return true;  // host replay: mathx.cuh is checked by tests/test_mathx.py
+#else
+    static std::mutex mu;
+    static int verdict[64] = {0};  // per device: 0 unknown, 1 ok, 2 out of bounds
+    std::lock_guard<std::mutex> lock(mu);
+    int& v = verdict[dev & 63];
+    if (v == 0) {
+        double* d = nullptr;
+        double err[4] = {1., 1., 1., 1.};
+        CK(cudaMalloc(&d, sizeof err));
+        CK(cudaMemset(d, 0, sizeof err));
+        LAUNCH((k_math_selftest2), 64, 256, 0, 1 << 16, d);
+        CK(cudaMemcpy(err, d, sizeof err, cudaMemcpyDeviceToHost));
+        CK(cudaFree(d));
+        // exp_m / exp_m2 relative (6e-15 by construction), switches absolute (5e-15), rsqrt_q relative (1.5 x seed error^2 = 1.2e-12)
+        v = (err[0] < 2e-14 && err[1] < 4e-14 && err[2] < 1e-11) ? 1 : 2;
+    }
+    return v == 1;
+#endif
+}
 __global__ void k_copy(size_t n, const double4* __restrict__ a, double4* __restrict__ b) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
 }
@@ -689,6 +730,56 @@ int pfmds_add_interaction(pfmds_ctx* c, const char* name, int np, const double* 
     });
 }
 
+// One md step of a call that started at step `first`.  Steady-state steps (no list rebuild, no momentum removal, no energy
+// request, not the first of the call) of small systems are replayed from a CUDA graph captured from this very code path: same
+// kernels, same order, fewer launch gaps.
+static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool with_energy) {
+    bool rebuild = false;
+    for (auto& it : c->inter)
+        for (int j = 0; j < it.nl_n; ++j) rebuild |= (s % it.nl[j].period == 0) || !it.nl[j].built;
+    const bool regrouped = apply_group_changes(c, s);
+    const bool graphable = !regrouped && c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && !rebuild &&
+                           (s % c->zero_momentum_period != 0) && !with_energy;
+    if (!graphable) {
+        do_step(c, s, kind, dt, s == first, with_energy);
+        if (c->slab && std::getenv("PFMDS_SLAB_DEBUG")) {
+            std::fprintf(stderr, "[slab %d] step %d queued\n", slab_rank(c), s); std::fflush(stderr);
+            cudaError_t e = cudaStreamSynchronize(c->st);
+            std::fprintf(stderr, "[slab %d] step %d done (%s)\n", slab_rank(c), s, cudaGetErrorString(e)); std::fflush(stderr);
+        }
+        return;
+    }
+    pfmds_ctx::StepGraph* g = nullptr;
+    for (auto& e : c->graphs)
+        if (e.kind == kind && e.dt == dt && e.pos == (const void*)c->pos && e.pending == c->nhc_pending && e.ke_valid == c->nhc_ke_valid) g = &e;
+    if (!g) {
+        pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, nullptr, 0};
+        const long long l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+        try { do_step(c, s, kind, dt, false); } catch (...) { cudaStreamEndCapture(c->st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        CK(cudaStreamEndCapture(c->st, &graph));
+        CK(cudaGraphInstantiate(&e.exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        e.launches = c->launches - l0;
+        c->launches = l0;
+        // capturing ran the host-side bookkeeping of one step: the flags now describe the state AFTER a step; a step
+        // is only graphable again from the same entry state, which holds in steady state (checked by the key)
+        if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+        c->graphs.push_back(e);
+        g = &c->graphs.back();
+        CK(cudaGraphLaunch(g->exec, c->st));
+        c->launches += g->launches;
+        return;
+    }
+    CK(cudaGraphLaunch(g->exec, c->st));
+    c->launches += g->launches;
+    c->energy_valid = false;
+    // host-side bookkeeping of do_step for this integrator
+    if (kind == PFMDS_NVT && c->nhc_fusable) { c->nhc_pending = true; c->nhc_ke_valid = true; }
+    else { c->nhc_pending = false; c->nhc_ke_valid = false; }
+}
+
 static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, bool energy_last);
 int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) { return advance_impl(c, kind, dt, first, n, false); }
 int pfmds_advance_with_energy(pfmds_ctx* c, int kind, double dt, int first, int n) { return advance_impl(c, kind, dt, first, n, true); }
@@ -698,57 +789,7 @@ static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, boo
         if (n < 0 || first < 0) fail(PFMDS_ERR_INVALID, "error: bad step range");
         CK(cudaSetDevice(c->dev));
         finalize(c);
-        for (int s = first; s < first + n; ++s) {
-            // Steady-state steps (no list rebuild, no momentum removal, not the first of the call) of small systems are
-            // replayed from a CUDA graph captured from this very code path: same kernels, same order, fewer launch gaps.
-            bool rebuild = false;
-            for (auto& it : c->inter)
-                for (int j = 0; j < it.nl_n; ++j) rebuild |= (s % it.nl[j].period == 0) || !it.nl[j].built;
-            const bool with_energy = energy_last && s == first + n - 1;
-            const bool regrouped = apply_group_changes(c, s);
-            const bool graphable = !regrouped && c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && !rebuild &&
-                                   (s % c->zero_momentum_period != 0) && !with_energy;
-            if (!graphable) {
-                do_step(c, s, kind, dt, s == first, with_energy);
-                if (c->slab && std::getenv("PFMDS_SLAB_DEBUG")) {
-                    std::fprintf(stderr, "[slab %d] step %d queued\n", slab_rank(c), s); std::fflush(stderr);
-                    cudaError_t e = cudaStreamSynchronize(c->st);
-                    std::fprintf(stderr, "[slab %d] step %d done (%s)\n", slab_rank(c), s, cudaGetErrorString(e)); std::fflush(stderr);
-                }
-                continue;
-            }
-            pfmds_ctx::StepGraph* g = nullptr;
-            for (auto& e : c->graphs)
-                if (e.kind == kind && e.dt == dt && e.pos == (const void*)c->pos && e.pending == c->nhc_pending && e.ke_valid == c->nhc_ke_valid) g = &e;
-            if (!g) {
-                pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, nullptr, 0};
-                const bool p0 = c->nhc_pending, k0 = c->nhc_ke_valid;
-                const long long l0 = c->launches;
-                cudaGraph_t graph = nullptr;
-                CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
-                try { do_step(c, s, kind, dt, false); } catch (...) { cudaStreamEndCapture(c->st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
-                CK(cudaStreamEndCapture(c->st, &graph));
-                CK(cudaGraphInstantiate(&e.exec, graph, 0));
-                CK(cudaGraphDestroy(graph));
-                e.launches = c->launches - l0;
-                c->launches = l0;
-                // capturing ran the host-side bookkeeping of one step: the flags now describe the state AFTER a step; a step
-                // is only graphable again from the same entry state, which holds in steady state (checked by the key)
-                (void)p0; (void)k0;
-                if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
-                c->graphs.push_back(e);
-                g = &c->graphs.back();
-                CK(cudaGraphLaunch(g->exec, c->st));
-                c->launches += g->launches;
-                continue;
-            }
-            CK(cudaGraphLaunch(g->exec, c->st));
-            c->launches += g->launches;
-            c->energy_valid = false;
-            // host-side bookkeeping of do_step for this integrator
-            if (kind == PFMDS_NVT && c->nhc_fusable) { c->nhc_pending = true; c->nhc_ke_valid = true; }
-            else { c->nhc_pending = false; c->nhc_ke_valid = false; }
-        }
+        for (int s = first; s < first + n; ++s) run_step(c, s, first, kind, dt, energy_last && s == first + n - 1);
         CK(cudaGetLastError());
     });
 }
@@ -794,8 +835,7 @@ int pfmds_advance_logged(pfmds_ctx* c, int kind, double dt, int first, int n, in
         int r = 0;
         for (int s = first; s < first + n; ++s) {
             const bool logged = s % log_period == 0;
-            apply_group_changes(c, s);
-            do_step(c, s, kind, dt, s == first, logged);
+            run_step(c, s, first, kind, dt, logged);   // unlogged steady-state steps of small systems replay their CUDA graph, as in pfmds_advance
             if (!logged) continue;
             integ_flush_pending(c);                              // as pfmds_energies: KE of the velocities the host would download
             integ_kinetic_energy(c, c->all_moving, c->red);

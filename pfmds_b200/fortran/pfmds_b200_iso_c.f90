@@ -43,6 +43,11 @@ interface
 	integer(c_int) function pfmds_advance_with_energy(ctx,integrator,dt,first_md_step,n_steps) bind(C,name='pfmds_advance_with_energy')
 		import; type(c_ptr),value :: ctx; integer(c_int),value :: integrator,first_md_step,n_steps; real(c_double),value :: dt
 	end function
+	integer(c_int) function pfmds_advance_logged(ctx,integrator,dt,first_md_step,n_steps,log_period,rows,row_len,n_rows) &
+	bind(C,name='pfmds_advance_logged')
+		import; type(c_ptr),value :: ctx; integer(c_int),value :: integrator,first_md_step,n_steps,log_period,row_len
+		real(c_double),value :: dt; real(c_double) :: rows(row_len,*); integer(c_int) :: n_rows
+	end function
 	integer(c_int) function pfmds_state_size(ctx,n_doubles) bind(C,name='pfmds_state_size')
 		import; type(c_ptr),value :: ctx; integer(c_long_long) :: n_doubles
 	end function

@@ -29,6 +29,24 @@ def test_time_variant_on_the_host_replay(oracle_lib, monkeypatch):
         assert "PFMDS_RJL_GEN" not in os.environ
 
 
+def test_e2e_steps_logged_and_stepwise_agree(oracle_lib):
+    """The e2e leg's two ways of reading every step's energies (one pfmds_advance_logged call / one round trip per step) leave the
+    same state and count their D2H bytes."""
+    import build_emu as B
+    import bench
+    from pfmds_b200.engine import configure
+    import numpy as np
+    B.build_emu()
+    case = inputs.cu_fcc(ncell=5, jitter=0.05, period=5)
+    a, b = configure(case, lib_path=B.LIB), configure(case, lib_path=B.LIB)
+    for e in (a, b):
+        e.advance("nvt", 2.0, 0, 1)
+    ba, ha = bench.e2e_steps(a, "nvt", 2.0, 7)
+    bb, hb = bench.e2e_steps(b, "nvt", 2.0, 7, stepwise=True)
+    assert "advance_logged" in ha and "pfmds_energies" in hb and ba == 8 * (1 + 1 + 9) and bb > ba
+    assert np.array_equal(a.download()[0], b.download()[0]) and np.array_equal(a.download()[2], b.download()[2])
+
+
 def test_reference_arm_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0"], capture_output=True, text=True,
                          timeout=600, env=dict(os.environ, OMP_NUM_THREADS="4"))
