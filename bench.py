@@ -379,6 +379,8 @@ def main():
         hv = torch.empty((n_here, 3), dtype=torch.float64).pin_memory()
         hp.numpy()[:] = p0
         hv.numpy()[:] = v0
+        # results land in pinned host memory too (single GPU; the slab path returns this rank's atoms in fresh arrays)
+        ho = None if slab else [torch.empty((n_here, 3), dtype=torch.float64).pin_memory().numpy() for _ in range(3)]
         barrier()
         t0 = time.perf_counter()
         if slab:
@@ -387,14 +389,14 @@ def main():
             eng.upload_ptr(hp.data_ptr(), hv.data_ptr())
         eng.advance(integrator, dt, 0, 1)
         e_bytes, how = e2e_steps(eng, integrator, dt, ke2e, stepwise=slab or bool(os.environ.get("PFMDS_BENCH_STEPWISE_E2E")))
-        out = eng.download()
+        out = eng.download() if slab else eng.download(out=ho)
         barrier()
         t_e2e = time.perf_counter() - t0
         te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": n_total * ke2e / float(te.item()), "unit": "atom-steps/s", "h2d_bytes_per_step": int(2 * 24 * n_atoms / ke2e),
-               "d2h_bytes_per_step": int(e_bytes + (3 * 32 + 4) * n_atoms / ke2e), "steps": ke2e,
+               "d2h_bytes_per_step": int(e_bytes + ((3 * 32 + 4) if slab else 3 * 24) * n_atoms / ke2e), "steps": ke2e,
                "what": "pfmds_upload(H2D pinned) + " + how + " + pfmds_download(D2H)"}
         del out
 

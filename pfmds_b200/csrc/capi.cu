@@ -584,6 +584,15 @@ __global__ void k_upload_scatter(int N, const int* __restrict__ orig, const doub
     if (hv) { double4 v = vel[s]; v.x = hv[3 * f]; v.y = hv[3 * f + 1]; v.z = hv[3 * f + 2]; vel[s] = v; }
 }
 
+// file-order copy of one state array: out[3 f + k] = component k of the atom whose file index is f = orig[slot]
+__global__ void k_download_gather(int N, const int* __restrict__ orig, const double4* __restrict__ a, double* __restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const double4 v = a[s];
+    double* o = out + 3 * (size_t)orig[s];
+    o[0] = v.x; o[1] = v.y; o[2] = v.z;
+}
+
 extern "C" {
 
 int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, const double* vel, const double* mass, const double box[3]) {
@@ -951,20 +960,36 @@ int pfmds_download(pfmds_ctx* c, double* pos, double* vel, double* frc) {
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
         if (c->slab) fail(PFMDS_ERR_INVALID, "error: use pfmds_slab_download on a slab context");
-        const size_t N = (size_t)c->N;
+        const size_t n3 = 3 * (size_t)c->N;
         integ_flush_pending(c);
-        std::vector<int> ho(N);
-        std::vector<double4> buf(N);
-        CK(cudaMemcpyAsync(ho.data(), c->orig, sizeof(int) * N, cudaMemcpyDeviceToHost, c->st));
-        auto pull = [&](const double4* d, double* out) {
-            if (!out) return;
-            CK(cudaMemcpyAsync(buf.data(), d, sizeof(double4) * N, cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            for (size_t s = 0; s < N; ++s) { double* o = out + 3 * (size_t)ho[s]; o[0] = buf[s].x; o[1] = buf[s].y; o[2] = buf[s].z; }
-        };
-        CK(cudaStreamSynchronize(c->st));
-        pull(c->pos, pos); pull(c->vel, vel); pull(c->frc, frc);
-        check_device_error(c);
+        // The device undoes its own cell ordering: each requested array is gathered into file order (x y z per atom, the
+        // layout of the caller's buffer) in a staging block, then copied out with one transfer per array straight into the
+        // caller's memory -- no host-side permutation, no intermediate host buffer.
+        double* out[3] = {pos, vel, frc};
+        const double4* src[3] = {c->pos, c->vel, c->frc};
+        int want = 0;
+        for (double* o : out) want += o != nullptr;
+        if (n3 * (size_t)want > c->io_cap) {  // staging block of the context, grown on demand and kept (no allocation per call)
+            if (c->io_stage) CK(cudaFree(c->io_stage));
+            c->io_stage = nullptr; c->io_cap = 0;
+            CK(cudaMalloc(&c->io_stage, sizeof(double) * n3 * (size_t)want));
+            c->io_cap = n3 * (size_t)want;
+        }
+        double* stage = c->io_stage;
+        int k = 0;
+        for (int a = 0; a < 3; ++a) {
+            if (!out[a]) continue;
+            LAUNCH((k_download_gather), (c->N + 255) / 256, 256, c->st, c->N, c->orig, src[a], stage + n3 * (size_t)k);
+            c->launches += 1;
+            ++k;
+        }
+        k = 0;
+        for (int a = 0; a < 3; ++a) {
+            if (!out[a]) continue;
+            CK(cudaMemcpyAsync(out[a], stage + n3 * (size_t)k, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->st));
+            ++k;
+        }
+        check_device_error(c);  // synchronises
     });
 }
 
@@ -1460,7 +1485,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     for (int* r : c->d_grank) cudaFree(r);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,
-                    c->cid, c->posf, c->scan_tmp, c->part, c->red, c->energy, c->err, c->logbuf};
+                    c->cid, c->posf, c->scan_tmp, c->part, c->red, c->energy, c->err, c->logbuf, c->io_stage};
     for (void* p : ptrs) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

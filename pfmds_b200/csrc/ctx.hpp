@@ -70,6 +70,8 @@ struct pfmds_ctx {
     double* energy = nullptr; // [n_inter] device energies
     double* logbuf = nullptr; // device-resident energy log of pfmds_advance_logged
     size_t log_cap = 0;
+    double* io_stage = nullptr; // file-order staging block of pfmds_download / pfmds_upload
+    size_t io_cap = 0;
     int* err = nullptr;       // [PFMDS_ERRW]
     // host description
     std::vector<std::vector<int>> groups;  // 1-based group -> 1-based file indexes

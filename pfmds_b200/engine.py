@@ -192,9 +192,17 @@ class Engine:
         self._call("diagnostics", self._ctx, _d(fs), _d(mc), _d(mcv), C.byref(vmax), _i(nl))
         return fs, mc, mcv, vmax.value, nl
 
-    def download(self, forces=True):
-        pos, vel = np.zeros((self.n, 3)), np.zeros((self.n, 3))
-        frc = np.zeros((self.n, 3)) if forces else None
+    def download(self, forces=True, out=None):
+        """(pos, vel, frc) in file order, [n, 3] each.  `out`: three preallocated C-contiguous float64 [n, 3] arrays to fill
+        (e.g. views of pinned host memory; None entries are skipped) instead of fresh ones."""
+        if out is not None:
+            pos, vel, frc = out
+            for a in (pos, vel, frc):
+                if a is not None and not (a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape == (self.n, 3)):
+                    raise PfmdsError(1, "download(out=...) needs C-contiguous float64 arrays of shape (n, 3)")
+        else:
+            pos, vel = np.zeros((self.n, 3)), np.zeros((self.n, 3))
+            frc = np.zeros((self.n, 3)) if forces else None
         self._call("download", self._ctx, _d(pos), _d(vel), _d(frc))
         return pos, vel, frc
 

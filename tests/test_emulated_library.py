@@ -57,7 +57,8 @@ def test_trajectory_22_steps(monkeypatch, name, integrator):
 @pytest.mark.parametrize("fn", ["test_single_step_forces_after_move", "test_zero_momentum_and_invert_z", "test_too_many_neighbours_is_reported",
                                 "test_particle_out_of_cell_is_reported", "test_not_enough_graphene_neighbours_is_reported",
                                 "test_refuses_what_the_reference_gets_wrong_silently", "test_upload_restarts_a_context",
-                                "test_multi_step_advance_equals_single_steps", "test_two_contexts_share_a_gpu"])
+                                "test_multi_step_advance_equals_single_steps", "test_two_contexts_share_a_gpu",
+                                "test_download_into_caller_buffers"])
 def test_parity_misc(monkeypatch, fn):
     getattr(replay(monkeypatch, "test_parity_gpu"), fn)()
 

@@ -313,3 +313,20 @@ def test_advance_logged_rows(name):
     for k in range(4):
         assert np.allclose(rows[k], ref[k], rtol=1e-7, atol=1e-9 * max(1.0, np.abs(ref[k]).max()))   # 12 steps of a trajectory, not step 0
     assert np.allclose(rows[0][0], ref[0][0], rtol=RTOL * 100, atol=0)
+
+
+def test_download_into_caller_buffers():
+    """pfmds_download gathers into file order on the device and copies straight into the caller's arrays; arrays that are
+    not asked for (NULL) are skipped."""
+    case = CASES["gr_cu_ljc"]
+    e = gpu(case)
+    e.advance("nvt", 1.0, 0, 7)                     # past a rebuild: slots are in cell order, not file order
+    p, v, f = e.download()
+    n = len(case["mass"])
+    bp, bf = np.full((n, 3), np.nan), np.full((n, 3), np.nan)
+    q = e.download(out=(bp, None, bf))
+    assert q[0] is bp and q[1] is None and np.array_equal(bp, p) and np.array_equal(bf, f)
+    p2, v2, f2 = e.download(forces=False)
+    assert f2 is None and np.array_equal(p2, p) and np.array_equal(v2, v)
+    with pytest.raises(PfmdsError):
+        e.download(out=(np.zeros((n, 2)), None, None))
