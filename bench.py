@@ -13,7 +13,7 @@ into the timed region.  N>1 (torchrun, one rank per GPU), weak scaling at 1 000 
   --decomp ensemble         the reference's MPI mode: every rank integrates its own replica, no collective.
 `value` is the atoms of all ranks x steps divided by the slowest rank's device time.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cu_fcc|lj_fluid|ab_gas|graphene_cu|ensemble_graphene|graphene_rebosc|lj_deposition]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cu_fcc|cu_fcc_1e8|lj_fluid|ab_gas|graphene_cu|ensemble_graphene|graphene_rebosc|lj_deposition]
 """
 from __future__ import annotations
 
@@ -30,12 +30,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# algorithmic (source-level) FP64 operation counts per listed directed pair, DESIGN.md §4 / SURVEY.md §8d:
-# FMA = 2, every exp/sqrt/div/sin/cos = 1.  distance + min-image = 30.
-FLOPS_PER_PAIR = {"rjl_force": 30 + 45, "rjl_density": 30 + 25, "lj1g": 30 + 41, "lj": 30 + 25, "tb_force": 0, "cos_graphene": 30 + 60, "cos_metal": 30 + 60}
-# algorithmic HBM bytes per list-owner atom and launch: 4n (int32 row) + per-atom records
-BYTES_PER_ATOM = {"rjl_force": lambda n: 4 * n + 32 + 32 + 64 + 8 + 4, "rjl_density": lambda n: 4 * n + 32 + 32 + 8 + 4,
-                  "lj1g": lambda n: 4 * n + 32 + 32 + 64 + 4, "lj": lambda n: 4 * n + 32 + 32 + 64 + 4}
+# Algorithmic (source-level) FP64 operation counts per listed directed pair and HBM bytes per list-owner atom and launch
+# (4n for the int32 row + per-atom records): frozen next to the kernel source in pfmds_b200/csrc/roofline.json
+# (DESIGN.md section 4 / SURVEY.md 8d: FMA = 2, every exp/sqrt/div/sin/cos = 1, distance + min-image = 30).
+_RM = json.load(open(os.path.join(ROOT, "pfmds_b200", "csrc", "roofline.json")))["kernels"]
+FLOPS_PER_PAIR = {k: v["flop_per_pair"] for k, v in _RM.items()}
+BYTES_PER_ATOM = {k: (lambda n, c=v["bytes_per_atom_const"]: 4 * n + c) for k, v in _RM.items() if v.get("bytes_per_atom_const") is not None}
+
+
+BIG_CELLS_PER_RANK = (37, 293, 293)   # x 8 ranks = 296 x 293 x 293 cells = 101 646 416 atoms (BASELINE.json configs[3])
 
 
 def build_case(workload, seed, steps, nx=1):
@@ -45,6 +48,10 @@ def build_case(workload, seed, steps, nx=1):
             return (inputs.cu_fcc(cells=(63 * nx, 63, 63), seed=seed, steps=steps), "nvt",
                     "Cu fcc %dx63x63 cells = %d atoms in x-slabs, rjl, NVT 300 K, dt 2 fs, r_cut 6.5, rebuild/20" % (63 * nx, 1000188 * nx))
         return inputs.cu_fcc(ncell=63, seed=seed, steps=steps), "nvt", "Cu fcc 63^3x4 = 1000188 atoms, rjl, NVT 300 K, dt 2 fs, r_cut 6.5, rebuild/20"
+    if workload == "cu_fcc_1e8":   # one GPU's share of the 10^8-atom crystal (the N>1 path generates per rank, see main)
+        cx, cy, cz = BIG_CELLS_PER_RANK
+        return (inputs.cu_fcc(cells=BIG_CELLS_PER_RANK, seed=seed, steps=steps), "nvt",
+                "Cu fcc %dx%dx%d cells = %d atoms, rjl, NVT 300 K, dt 2 fs, r_cut 6.5, rebuild/20" % (cx, cy, cz, 4 * cx * cy * cz))
     if workload == "lj_fluid":
         return inputs.lj_fluid(n_side=128, seed=seed, steps=steps), "nve", "LJ fluid (lj1g) 128^3 = 2097152 atoms, NVE, dt 0.5 fs, r_cut 7.5, rebuild/20"
     if workload == "ab_gas":
@@ -313,19 +320,37 @@ def main():
     K, W = args.steps, max(3, args.warmup)
     if args.workload == "ensemble_graphene":
         return run_ensemble(args, rank, world, local, dist, K, W)
-    slab = world > 1 and args.decomp == "slab" and args.workload == "cu_fcc"
-    if slab:
+    slab = world > 1 and args.decomp == "slab" and args.workload in ("cu_fcc", "cu_fcc_1e8")
+    n_global = None
+    if slab and args.workload == "cu_fcc_1e8":
+        # BASELINE.json configs[3] at its stated size: 8 x (37 x 293 x 293) cells = 1.0165e8 atoms on 8 GPUs (1.27e7 per GPU at any N);
+        # every rank generates only its own slab, the velocity initialisation's global sums go through one all-reduce
+        from pfmds_b200.slab import broadcast_unique_id, configure_slab, cu_fcc_slab_inputs
+
+        def allsum(v):
+            t = torch.from_numpy(np.ascontiguousarray(v, np.float64)).cuda()
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+        case, loc = cu_fcc_slab_inputs(rank, world, BIG_CELLS_PER_RANK, allsum, seed=2, steps=K + W)
+        integrator, n_global = "nvt", loc["n_global"]
+        desc = "Cu fcc %dx293x293 cells = %d atoms in x-slabs (generated per rank), rjl, NVT 300 K, dt 2 fs, r_cut 6.5, rebuild/20" % (37 * world, n_global)
+        uid = broadcast_unique_id(dist, torch.device("cuda", local))
+        eng = configure_slab(case, rank, world, local, uid, capacity_factor=1.15, local=loc)
+        n_atoms = eng.n_local0
+        del loc
+    elif slab:
         from pfmds_b200.slab import broadcast_unique_id, configure_slab
         case, integrator, desc = build_case(args.workload, seed=2, steps=K + W, nx=world)   # every rank builds the same crystal
         uid = broadcast_unique_id(dist, torch.device("cuda", local))
         eng = configure_slab(case, rank, world, local, uid, capacity_factor=1.25)
         n_atoms = eng.n_local0
+        n_global = len(case["mass"])
     else:
         case, integrator, desc = build_case(args.workload, seed=2 + rank, steps=K + W)
         eng = configure(case, device=local)
         n_atoms = len(case["mass"])
     dt = case["integrators"][0][1]
-    n_total = len(case["mass"]) if slab else n_atoms * world
+    n_total = n_global if slab else n_atoms * world
 
     def barrier():
         if dist is not None:

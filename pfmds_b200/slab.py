@@ -42,10 +42,32 @@ def halo_atoms(case, rank, world, width):
     return from_left, from_right
 
 
-class SlabEngine(Engine):
-    """This rank's share of a case: atoms with x in [rank*Lx/world, (rank+1)*Lx/world)."""
+def cu_fcc_slab_inputs(rank, world, cells_per_rank, all_reduce_sum, seed=2, temperature=300.0, steps=1000, period=20):
+    """BASELINE.json configs[3] at its stated size (10^8 atoms cannot be built whole on every rank): this rank generates only
+    its own slab of the crystal (`inputs.cu_fcc_slab`), the two global sums of the velocity initialisation go through
+    `all_reduce_sum` (a callable that sums a float64 numpy vector over the ranks: torch.distributed in the bench and tests),
+    and the settings (groups, roles, thermostat, rjl list) are those of `inputs.cu_fcc` for the whole crystal.
+    Returns (settings_case, local) with local = dict(gid, pos, vel, mass, mask, sizes, box, n_global) as SlabEngine takes it."""
+    from . import inputs
+    gid, pos, vel, mass, box, sums = inputs.cu_fcc_slab(rank, world, cells_per_rank, seed=seed, temperature=temperature)
+    n_global = int(all_reduce_sum(np.array([float(len(gid))]))[0])
+    sums = all_reduce_sum(np.asarray(sums, np.float64))
+    vel = inputs.finish_velocities(vel, mass, sums, n_global, temperature)
+    q1 = 3 * n_global * inputs.KB * temperature * 100.0 ** 2
+    settings = inputs.cu_fcc(ncell=1, steps=steps, period=period, temperature=temperature, q1=q1)   # 4 atoms: only its tables are used
+    for k in ("pos", "vel", "mass", "names"):
+        settings.pop(k)
+    settings["box"] = box
+    mask = np.full(len(gid), 1, np.uint32)                # groups of cu_fcc: 1 = every CU atom, 2 = empty
+    sizes = np.array([n_global, 0], np.int64)
+    return settings, dict(gid=gid, pos=pos, vel=vel, mass=mass, mask=mask, sizes=sizes, box=box, n_global=n_global)
 
-    def __init__(self, case, rank, world, device, unique_id, capacity_factor=1.6, lib_path=LIB_PATH):
+
+class SlabEngine(Engine):
+    """This rank's share of a case: atoms with x in [rank*Lx/world, (rank+1)*Lx/world).  `local` (see cu_fcc_slab_inputs)
+    replaces the whole-crystal arrays of `case` by this rank's own atoms."""
+
+    def __init__(self, case, rank, world, device, unique_id, capacity_factor=1.6, lib_path=LIB_PATH, local=None):
         self._lib = load_library(lib_path)
         self._p = "pfmds_"
         self._ctx = C.c_void_p()
@@ -57,18 +79,35 @@ class SlabEngine(Engine):
         L.pfmds_slab_download.restype = C.c_int
         L.pfmds_slab_download.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         box = np.ascontiguousarray(case["box"], np.float64)
-        n_global = len(case["mass"])
-        mine, mask, sizes = slab_partition(case, rank, world)
         ng = len(case["groups"])
+        if local is None:
+            n_global = len(case["mass"])
+            mine, mask, sizes = slab_partition(case, rank, world)
+            pos = np.ascontiguousarray(case["pos"][mine], np.float64).reshape(-1)
+            vel = np.ascontiguousarray(case["vel"][mine], np.float64).reshape(-1)
+            mass = np.ascontiguousarray(case["mass"][mine], np.float64)
+            gid = np.ascontiguousarray(mine + 1, np.int32)
+            m = np.ascontiguousarray(mask[mine], np.uint32)
+            self.groups = {g: group_indexes(case, g) for g in range(1, ng + 1)}
+        else:
+            n_global = int(local["n_global"])
+            if n_global >= 2 ** 31:
+                raise PfmdsError(1, "atom numbers are int32 in the C ABI")
+            W = box[0] / world
+            own = np.clip(np.floor(np.asarray(local["pos"])[:, 0] / W).astype(np.int64), 0, world - 1)
+            if not np.all(own == rank):
+                raise PfmdsError(1, "local atoms outside this rank's slab")
+            mine = local["gid"]
+            pos = np.ascontiguousarray(local["pos"], np.float64).reshape(-1)
+            vel = np.ascontiguousarray(local["vel"], np.float64).reshape(-1)
+            mass = np.ascontiguousarray(local["mass"], np.float64)
+            gid = np.ascontiguousarray(local["gid"], np.int32)
+            m = np.ascontiguousarray(local["mask"], np.uint32)
+            sizes = np.ascontiguousarray(local["sizes"], np.int64)
+            self.groups = {}
         self.n = n_global
         self.n_local0 = len(mine)
         self.capacity = int(len(mine) * capacity_factor) + 4096
-        pos = np.ascontiguousarray(case["pos"][mine], np.float64).reshape(-1)
-        vel = np.ascontiguousarray(case["vel"][mine], np.float64).reshape(-1)
-        mass = np.ascontiguousarray(case["mass"][mine], np.float64)
-        gid = np.ascontiguousarray(mine + 1, np.int32)
-        m = np.ascontiguousarray(mask[mine], np.uint32)
-        self.groups = {g: group_indexes(case, g) for g in range(1, ng + 1)}
         self.inter, self.nhc_M = [], []
         self._call("create_slab", C.byref(self._ctx), device, rank, world, unique_id, n_global, len(mine), _i(gid), _d(pos), _d(vel), _d(mass),
                    m.ctypes.data_as(C.POINTER(C.c_uint)), ng, sizes.ctypes.data_as(C.POINTER(C.c_longlong)), _d(box), self.capacity)

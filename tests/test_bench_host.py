@@ -47,6 +47,15 @@ def test_e2e_steps_logged_and_stepwise_agree(oracle_lib):
     assert np.array_equal(a.download()[0], b.download()[0]) and np.array_equal(a.download()[2], b.download()[2])
 
 
+def test_work_model_is_the_frozen_one():
+    """bench.py takes its algorithmic flop / byte counts from pfmds_b200/csrc/roofline.json (frozen next to the kernels)."""
+    import bench
+    assert bench.FLOPS_PER_PAIR["rjl_force"] == 75 and bench.FLOPS_PER_PAIR["rjl_density"] == 55 and bench.FLOPS_PER_PAIR["lj1g"] == 71
+    assert bench.BYTES_PER_ATOM["rjl_force"](86) == 4 * 86 + 140 and bench.BYTES_PER_ATOM["rjl_density"](86) == 4 * 86 + 76
+    cx, cy, cz = bench.BIG_CELLS_PER_RANK
+    assert 8 * 4 * cx * cy * cz == 101646416
+
+
 def test_reference_arm_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0"], capture_output=True, text=True,
                          timeout=600, env=dict(os.environ, OMP_NUM_THREADS="4"))

@@ -51,6 +51,22 @@ for r in range(world):
         d -= L * np.round(d / L)
         near = np.where((d * d).sum(1) < 6.5 ** 2)[0]
         assert set(near.tolist()) <= have
+# the per-rank generator of the 10^8-atom workload (bench.py --workload cu_fcc_1e8): same atoms, numbers and positions as the
+# partition of the whole crystal, global momentum zero and exactly 300 K after the one all-reduce of its velocity sums
+from pfmds_b200.slab import cu_fcc_slab_inputs
+def allsum(v):
+    t = torch.from_numpy(np.ascontiguousarray(v, np.float64).copy()); dist.all_reduce(t); return t.numpy()
+settings, loc = cu_fcc_slab_inputs(rank, world, (3, 4, 4), allsum, seed=5)
+whole = inputs.cu_fcc(cells=(3 * world, 4, 4), seed=5)
+mine_w, mask_w, sizes_w = slab_partition(whole, rank, world)
+assert loc["n_global"] == len(whole["mass"]) and np.array_equal(np.sort(loc["gid"]), mine_w + 1)
+assert np.allclose(loc["pos"], whole["pos"][loc["gid"] - 1], rtol=0, atol=1e-12)
+assert np.array_equal(loc["sizes"], sizes_w) and np.array_equal(loc["mask"], mask_w[loc["gid"] - 1])
+assert settings["interactions"] == whole["interactions"] and settings["groups"] == whole["groups"] and np.allclose(settings["box"], whole["box"])
+assert abs(settings["nhc"][0][3] / whole["nhc"][0][3] - 1) < 1e-12 and "pos" not in settings
+mom = allsum((loc["mass"][:, None] * loc["vel"]).sum(0))
+ke = allsum(np.array([(loc["mass"] * (loc["vel"] ** 2).sum(1)).sum()]))[0] / 2 * inputs.MASS_COEF
+assert np.abs(mom).max() < 1e-9 and abs(2 * ke / inputs.KB / (3 * loc["n_global"]) - 300.0) < 1e-9
 if rank == 0:
     print("PLAN_OK", world, [len(o) for o in owned], [len(g[0]) + len(g[1]) for g in ghosts])
 dist.destroy_process_group()

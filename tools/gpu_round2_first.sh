@@ -20,3 +20,5 @@ for f in sorted(glob.glob("gpurun_out/r2_*.json")):
 PY
 # 3. memcheck / racecheck of the new kernels on small systems (the reference has no sanitizer story)
 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_rebosc_gpu.py tests/test_deposition_gpu.py -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r2_memcheck.log
+# 4. (separate call, 8 GPUs)  BASELINE.json configs[3] at its stated size, 1.0165e8 atoms:
+#   gpurun --gpus 8 --timeout 900 -- 'BENCH_ARGS="--workload cu_fcc_1e8 --steps 100" bash tools/gpu_scale.sh 8'
