@@ -38,7 +38,7 @@ FLOPS_PER_PAIR = {k: v["flop_per_pair"] for k, v in _RM.items()}
 BYTES_PER_ATOM = {k: (lambda n, c=v["bytes_per_atom_const"]: 4 * n + c) for k, v in _RM.items() if v.get("bytes_per_atom_const") is not None}
 
 
-BIG_CELLS_PER_RANK = (37, 293, 293)   # x 8 ranks = 296 x 293 x 293 cells = 101 646 416 atoms (BASELINE.json configs[3])
+BIG_CELLS_PER_RANK = (37, 293, 293)   # x 8 ranks = 296 x 293 x 293 cells = 101 645 216 atoms (BASELINE.json configs[3])
 
 
 def build_case(workload, seed, steps, nx=1):
