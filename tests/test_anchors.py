@@ -1,0 +1,134 @@
+"""Known answers that do not come from this repository: closed forms of the potentials on perfect lattices, evaluated here in a
+few lines of numpy straight from the formulas of the reference's source files, and the figures the potentials were fitted to in
+their source papers.  The reference ships no golden vectors (parity unpinned), so these are the independent anchors
+of the oracle, and of the CUDA library (on the GPU, and replayed on the host in the CPU suite):
+
+* rjl with the Cleri-Rosato copper parameters (RosatoGuillopeLegrand.f90:23-49; parameters of F. Cleri and V. Rosato, Phys. Rev. B
+  48, 22 (1993), fitted with interactions up to the fifth neighbour shell): cohesive energy 3.544 eV/atom at a = 3.615 A.
+* tb with Brenner's parameter set I (TersoffBrenner.f90:26-72; D. W. Brenner, Phys. Rev. B 42, 9458 (1990)): graphite sheet,
+  7.3756 eV/atom at a bond length of 1.42 A.  (Published figures quoted from the papers' tables; this container has no network
+  to re-read them.  The rounded parameters of the settings files give 7.3767.)
+* lj1g: an isolated pair, E(r) = 4 eps ((sig/r)^12 - (sig/r)^6) and its derivative, minimum -eps at 2^(1/6) sig.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from pfmds_b200 import inputs
+from pfmds_b200.engine import configure
+from util import gpu, oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+
+def _emu(case):
+    import build_emu as B
+    B.build_emu()
+    return configure(case, lib_path=B.LIB)
+
+
+ENGINES = [pytest.param(oracle, id="oracle"), pytest.param(_emu, id="host-replay"), pytest.param(gpu, id="gpu", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(oracle_lib):
+    return None
+
+
+def _energy_per_atom(make, case):
+    e = make(case)
+    e.advance("nve", 1.0, 0, 1)
+    f = e.download()[2]
+    return e.energies()[0][0] / len(case["mass"]), np.abs(f).max()
+
+
+# ---- rjl: fcc copper --------------------------------------------------------------------------------------------------
+FCC_SHELLS = [(1, 12), (2, 6), (3, 24), (4, 12), (5, 24)]          # r = a sqrt(n/2), multiplicity
+
+
+def _rjl_closed_form(a, shells=FCC_SHELLS):
+    A0, xi, p, q, r0 = inputs.RJL_CU[:5]
+    rep = sum(m * A0 * np.exp(-p * (a * np.sqrt(n / 2.0) / r0 - 1.0)) for n, m in shells)
+    band = sum(m * xi * xi * np.exp(-2.0 * q * (a * np.sqrt(n / 2.0) / r0 - 1.0)) for n, m in shells)
+    return rep - np.sqrt(band)
+
+
+def _cu(a):
+    c = inputs.cu_fcc(ncell=4, a=a, jitter=0.0)
+    c["vel"] = c["vel"] * 0
+    # the switch between the fifth (a sqrt 2.5 = 5.72 A) and the sixth shell (a sqrt 3 = 6.26 A): the sum is exactly five shells
+    c["interactions"] = [dict(c["interactions"][0], params=list(inputs.RJL_CU[:5]) + [5.9, 6.1])]
+    return c
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_rjl_copper_cohesive_energy(make):
+    e0, fmax = _energy_per_atom(make, _cu(3.615))
+    # the formula, shell by shell.  The oracle uses libm; the library's rjl kernels use the short elementary functions of
+    # mathx.cuh (r from a hardware-seeded rsqrt good to 1.3e-12, which the exponents amplify by p r / r0 ~ 10): 1e-10, still ten
+    # times inside the parity bar.  Opposite partners can fall into different seed intervals, so the forces of the perfect
+    # lattice cancel to that level, not to rounding.
+    tol, ftol = (1e-12, 1e-12) if make is oracle else (1e-10, 1e-9)
+    assert abs(e0 - _rjl_closed_form(3.615)) < tol * abs(e0)
+    assert fmax < ftol                                                       # perfect lattice
+    assert abs(e0 - (-3.544)) < 1e-3                                         # Cleri & Rosato 1993: E_coh(Cu) = 3.544 eV
+    lo, _ = _energy_per_atom(make, _cu(3.585))
+    hi, _ = _energy_per_atom(make, _cu(3.645))
+    assert e0 < lo and e0 < hi                                               # ... at their lattice constant, 3.615 A
+
+
+# ---- tb: graphene sheet -----------------------------------------------------------------------------------------------
+def _tb_closed_form(d):
+    D, S, beta, R, delt, a0, c0, d0 = inputs.TB_BRENNER_I[:8]
+    c1 = 1.0 + np.cos(2.0 * np.pi / 3.0)                                     # every bond angle is 120 degrees
+    G = 1.0 + c0 * c0 / (d0 * d0) - c0 * c0 / (d0 * d0 + c1 * c1)
+    B = (1.0 + a0 * 2.0 * G) ** (-delt)                                      # two other bonds on each atom
+    vr = D / (S - 1.0) * np.exp(-np.sqrt(2.0 * S) * beta * (d - R))
+    va = D * S / (S - 1.0) * np.exp(-np.sqrt(2.0 / S) * beta * (d - R))
+    return 1.5 * (vr - B * va)                                               # three half bonds per atom
+
+
+def _graphene(d):
+    c = inputs.graphene_rebosc(cells=(6, 4), jitter=0.0, with_tb=True)
+    s = d * np.sqrt(3.0) / 2.46
+    c["pos"] = c["pos"].copy()
+    c["pos"][:, :2] *= s
+    c["box"] = c["box"].copy()
+    c["box"][:2] *= s
+    c["vel"] = c["vel"] * 0
+    c["interactions"] = [i for i in c["interactions"] if i["name"] == "tb"]
+    return c
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_tb_graphite_sheet_energy(make):
+    e0, fmax = _energy_per_atom(make, _graphene(1.42))
+    assert abs(e0 - _tb_closed_form(1.42)) < 1e-12 * abs(e0)
+    assert fmax < 1e-10
+    assert abs(e0 - (-7.3756)) < 2e-3                                        # Brenner 1990, potential I, graphite
+    lo, _ = _energy_per_atom(make, _graphene(1.40))
+    hi, _ = _energy_per_atom(make, _graphene(1.44))
+    assert e0 < lo and e0 < hi                                               # ... at 1.42 A
+
+
+# ---- lj1g: an isolated pair -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("make", ENGINES)
+def test_lj_pair(make):
+    eps, sig = 0.0103, 3.405
+    for r in (2.0 ** (1.0 / 6.0) * sig, 3.2, 5.0):
+        pos = np.array([[10.0, 10.0, 10.0], [10.0 + r * 0.6, 10.0 + r * 0.8, 10.0]])
+        case = dict(title="pair", box=np.array([40.0, 40.0, 40.0]), pos=pos, vel=np.zeros((2, 3)), mass=np.ones(2), names=["A", "A"],
+                    groups=[["A"], ["#"]], roles=dict(all_moving=1, xyz_moving=1, z_moving=2, all_atoms=1, traj_group=2, period_traj=10 ** 9),
+                    integrators=[("nve", 0.5, 10, 10 ** 9, 10 ** 9)], ms_de=1e-8, nhc=[], zero_momentum_period=10 ** 9, invert_z_vel=False,
+                    initial_temperature=0.0, interactions=[dict(name="lj1g", file="p.txt", params=[eps, sig, 6.0, 7.0], lists=[(1, 1, 4, 7.5, 5)])])
+        e = make(case)
+        e.advance("nve", 0.5, 0, 1)
+        en, f = e.energies()[0][0], e.download()[2]
+        x = (sig / r) ** 6
+        assert abs(en - 4 * eps * (x * x - x)) < 1e-13 * eps
+        fr = 24 * eps * (2 * x * x - x) / r                                  # -dE/dr, repulsive positive
+        assert np.allclose(f[1], fr * np.array([0.6, 0.8, 0.0]), rtol=1e-12, atol=1e-16) and np.allclose(f[0], -f[1], rtol=0, atol=1e-18)
+    assert abs(en - 4 * eps * ((sig / 5.0) ** 12 - (sig / 5.0) ** 6)) < 1e-15 and abs(-eps - 4 * eps * (0.25 - 0.5)) < 1e-18
