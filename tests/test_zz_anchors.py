@@ -1,4 +1,4 @@
-"""Known answers that do not come from this repository: closed forms of the potentials on perfect lattices, evaluated here in a
+"""(Named zz: on the GPU box it runs after the parity tests.)  Known answers that do not come from this repository: closed forms of the potentials on perfect lattices, evaluated here in a
 few lines of numpy straight from the formulas of the reference's source files, and the figures the potentials were fitted to in
 their source papers.  The reference ships no golden vectors (parity unpinned), so these are the independent anchors
 of the oracle, and of the CUDA library (on the GPU, and replayed on the host in the CPU suite):
