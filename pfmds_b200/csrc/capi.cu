@@ -433,7 +433,7 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bo
 __global__ void k_max_int(int n, const int* __restrict__ a, int* out) {
     int m = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, a[i]);
-#ifdef __CUDACC__
+#ifdef PFMDS_COOP
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 #else  // host replay: no lane exchange, every thread contributes
@@ -568,7 +568,7 @@ __global__ void k_copy(size_t n, const double4* __restrict__ a, double4* __restr
 __global__ void k_sum_int(int n, const int* __restrict__ a, unsigned long long* out) {
     unsigned long long s = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)a[i];
-#ifdef __CUDACC__
+#ifdef PFMDS_COOP
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 #else  // host replay: no lane exchange, every thread contributes

@@ -22,6 +22,9 @@
 #include "host_emu.hpp"  // test support: the kernels of this directory compiled for the host (tests/*_host.cpp), never part of the product
 #endif
 
+#if defined(__CUDACC__) || defined(PFMDS_EMU_WARP)
+#define PFMDS_COOP 1  // warp-cooperative code (shuffles, ballots, shared-memory reductions) is compiled: nvcc, or the lock-step host replay
+#endif
 #if defined(__CUDACC__) || defined(PFMDS_EMU_LIB)
 #define PFMDS_HAVE_CTX 1  // the context and the launch wrappers exist: the product (nvcc) and the emulated library of the test suite
 #endif
@@ -82,7 +85,9 @@ __device__ __forceinline__ double4 ld256(const double4* p) {
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
 }
+#endif  // __CUDACC__
 
+#ifdef PFMDS_COOP
 // block-wide sum of `v` (blockDim.x multiple of 32, <= 1024); result valid in thread 0
 __device__ __forceinline__ double block_sum(double v) {
     __shared__ double sh[32];
@@ -98,7 +103,7 @@ __device__ __forceinline__ double block_sum(double v) {
     return v;
 }
 
-#endif  // __CUDACC__
+#endif  // PFMDS_COOP
 
 // parameters of one interaction, passed by value to the kernels
 struct LJp { double eps, sig, R1, R2; };

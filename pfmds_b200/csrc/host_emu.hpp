@@ -7,8 +7,10 @@
 //     reach thread 0 — the only thread that uses them in these kernels — last;
 //   - the CUDA runtime calls the library makes are mapped onto malloc / memcpy / no-ops (one "device", synchronous "streams");
 //   - kernels that exchange data between the lanes of a warp (shuffles with SPLIT > 1, ballots, scans) cannot be run this way:
-//     the library's emulated build takes the thread-per-atom variants (SMALL_N = 0, no warp-per-atom list build) and the few
-//     shuffle-based reductions have a serial twin under #ifndef __CUDACC__.
+//     the SERIAL flavour of the emulated library takes the thread-per-atom variants (SMALL_N = 0, no warp-per-atom list build)
+//     and the few shuffle-based reductions have a serial twin under #ifndef PFMDS_COOP;
+//   - the LOCK-STEP flavour (-DPFMDS_EMU_WARP, below) runs every thread of a block as a fiber and implements the warp
+//     collectives and block barriers between them, so those kernels run as they are.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -33,7 +35,9 @@ struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
-static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+// one instance per process (C++17 inline variables): non-static inline device functions of the shared headers are merged across
+// translation units by the linker and must all see the same indices
+inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 static inline int atomicCAS(int* a, int cmp, int val) { int old = *a; if (old == cmp) *a = val; return old; }
 static inline int atomicAdd(int* a, int v) { int old = *a; *a += v; return old; }
@@ -49,14 +53,17 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+#ifndef PFMDS_EMU_WARP
 static inline void __syncthreads() {}
 // only reached with SPLIT == 1 (no iterations) or in code paths the emulated build never launches
 static inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }
+#endif
 
 static inline double4 ld256(const double4* p) { return *p; }
 static inline double4 ld256_nc(const double4* p) { return *p; }
 
+#ifndef PFMDS_EMU_WARP
 // running per-block totals, one per block_sum() call in the order a thread makes them
 static thread_local double emu_block_mx;
 static thread_local double emu_block_acc[64];
@@ -89,6 +96,189 @@ static void emu_launch_cfg(K kernel, dim3 grid, dim3 block, A... args) {
             }
         }
 }
+#else
+// ---- PFMDS_EMU_WARP: lock-step replay ---------------------------------------------------------------------------------------
+// Every thread of a block is a fiber (ucontext) on the calling OS thread.  A fiber runs until it reaches a warp collective
+// (__shfl_*_sync, __ballot_sync, __syncwarp) or a block barrier (__syncthreads) and yields; when every live lane of its warp
+// (every live thread of the block) waits at the same kind of point the scheduler exchanges the values and resumes them.  This
+// is what lets the CPU suite run the kernels the GPU actually launches for small systems: 8 lanes per atom with shuffle-tree
+// sums, the warp-per-atom list build with ballot / popc compaction, the block scans and the shared-memory reductions.
+// Reading a shuffle source lane that has exited returns a poison pattern (on hardware the value is undefined); lanes of one
+// warp waiting at different kinds of points, or a barrier that part of the block can never reach, abort with a message.
+#include <functional>
+#include <stdio.h>
+#include <sys/mman.h>
+#include <ucontext.h>
+#include <vector>
+
+enum { EMU_READY = 0, EMU_WARP = 1, EMU_BLOCK = 2, EMU_DONE = 3 };
+enum { EMU_OP_IDX = 0, EMU_OP_UP, EMU_OP_DOWN, EMU_OP_XOR, EMU_OP_BALLOT, EMU_OP_SYNCWARP };
+#if defined(__x86_64__) && !defined(PFMDS_EMU_UCONTEXT)
+// Fiber switch without the two rt_sigprocmask system calls of swapcontext (a reduction kernel yields ~10^7 times): saves the
+// callee-saved registers and the FP control words on the current stack, swaps stack pointers, restores.  System V x86-64 only.
+#define EMU_FAST_SWITCH 1
+extern "C" void emu_ctx_switch(void** save_sp, void* load_sp);
+asm(".text\n.weak emu_ctx_switch\n.type emu_ctx_switch,@function\nemu_ctx_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n  subq $8, %rsp\n  stmxcsr (%rsp)\n  fnstcw 4(%rsp)\n"
+    "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
+    "  ldmxcsr (%rsp)\n  fldcw 4(%rsp)\n  addq $8, %rsp\n  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
+    ".size emu_ctx_switch,.-emu_ctx_switch\n");
+struct EmuFiber { void* sp; int state, op, arg; unsigned long long val, out; };
+inline thread_local void* emu_sched_sp = nullptr;
+#define EMU_TO_SCHED(f) emu_ctx_switch(&(f).sp, emu_sched_sp)
+#define EMU_TO_FIBER(f) emu_ctx_switch(&emu_sched_sp, (f).sp)
+#else
+struct EmuFiber { ucontext_t ctx; int state, op, arg; unsigned long long val, out; };
+#define EMU_TO_SCHED(f) swapcontext(&(f).ctx, &emu_sched)
+#define EMU_TO_FIBER(f) swapcontext(&emu_sched, &(f).ctx)
+#endif
+inline thread_local std::vector<EmuFiber>* emu_fib = nullptr;
+inline thread_local std::vector<char*>* emu_stacks = nullptr;
+inline thread_local ucontext_t emu_sched;
+inline thread_local int emu_cur = 0;
+inline thread_local std::function<void()>* emu_body = nullptr;
+static const size_t EMU_STACK = 256 * 1024;
+static const unsigned long long EMU_POISON = 0x7ff8deadbeefdeadull;  // a NaN as double, a large negative number as int
+
+static void emu_tramp() {
+    (*emu_body)();
+    (*emu_fib)[(size_t)emu_cur].state = EMU_DONE;
+    EMU_TO_SCHED((*emu_fib)[(size_t)emu_cur]);
+    abort();  // a finished fiber is never resumed
+}
+static inline unsigned long long emu_yield(int state, int op, unsigned long long v, int arg) {
+    EmuFiber& f = (*emu_fib)[(size_t)emu_cur];
+    f.state = state; f.op = op; f.val = v; f.arg = arg;
+    EMU_TO_SCHED(f);
+    return f.out;
+}
+template <class T> static inline unsigned long long emu_bits(T v) { unsigned long long b = 0; static_assert(sizeof(T) <= 8, "shuffle of a wide type"); memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> static inline T emu_unbits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int lane) { return emu_unbits<T>(emu_yield(EMU_WARP, EMU_OP_IDX, emu_bits(v), lane)); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_unbits<T>(emu_yield(EMU_WARP, EMU_OP_UP, emu_bits(v), d)); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_unbits<T>(emu_yield(EMU_WARP, EMU_OP_DOWN, emu_bits(v), d)); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_unbits<T>(emu_yield(EMU_WARP, EMU_OP_XOR, emu_bits(v), m)); }
+static inline unsigned __ballot_sync(unsigned, int pred) { return (unsigned)emu_yield(EMU_WARP, EMU_OP_BALLOT, pred ? 1ull : 0ull, 0); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_yield(EMU_WARP, EMU_OP_SYNCWARP, 0, 0); }
+static inline void __syncthreads() { emu_yield(EMU_BLOCK, 0, 0, 0); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+
+static void emu_fail(const char* what) {
+    fprintf(stderr, "host replay (lock-step): %s in block (%u,%u)\n", what, blockIdx.x, blockIdx.y);
+    abort();
+}
+// all live lanes of warp [w0, w1) wait at a warp collective: exchange and resume
+static void emu_resolve_warp(std::vector<EmuFiber>& F, int w0, int w1) {
+    int op = -1;
+    for (int t = w0; t < w1; ++t)
+        if (F[(size_t)t].state == EMU_WARP) {
+            if (op < 0) op = F[(size_t)t].op;
+            else if (op != F[(size_t)t].op) emu_fail("lanes of one warp wait at different collectives");
+        }
+    unsigned ballot = 0;
+    for (int t = w0; t < w1; ++t)
+        if (F[(size_t)t].state == EMU_WARP && F[(size_t)t].val) ballot |= 1u << (t - w0);
+    for (int t = w0; t < w1; ++t) {
+        EmuFiber& f = F[(size_t)t];
+        if (f.state != EMU_WARP) continue;
+        const int l = t - w0;
+        int src = l;
+        switch (op) {
+        case EMU_OP_IDX: src = f.arg & 31; break;
+        case EMU_OP_UP: src = l - f.arg; break;
+        case EMU_OP_DOWN: src = l + f.arg; break;
+        case EMU_OP_XOR: src = l ^ f.arg; break;
+        default: break;
+        }
+        if (op == EMU_OP_BALLOT) f.out = ballot;
+        else if (op == EMU_OP_SYNCWARP) f.out = 0;
+        else if (src < 0 || src > 31) f.out = f.val;                                  // out of range: own value (defined)
+        else if (w0 + src >= w1 || F[(size_t)(w0 + src)].state != EMU_WARP) f.out = EMU_POISON;  // exited lane: undefined on hardware
+        else f.out = F[(size_t)(w0 + src)].val;
+    }
+    for (int t = w0; t < w1; ++t)
+        if (F[(size_t)t].state == EMU_WARP) F[(size_t)t].state = EMU_READY;
+}
+static void emu_run_block(int T) {
+    if (!emu_fib) { emu_fib = new std::vector<EmuFiber>(); emu_stacks = new std::vector<char*>(); }
+    std::vector<EmuFiber>& F = *emu_fib;
+    if ((int)F.size() < T) F.resize((size_t)T);
+    while ((int)emu_stacks->size() < T) {
+        void* m = mmap(nullptr, EMU_STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED) emu_fail("no memory for fiber stacks");
+        emu_stacks->push_back((char*)m);
+    }
+    for (int t = 0; t < T; ++t) {
+        EmuFiber& f = F[(size_t)t];
+#ifdef EMU_FAST_SWITCH
+        // initial frame as emu_ctx_switch leaves it: [mxcsr | x87 cw][r15 r14 r13 r12 rbx rbp][return address = emu_tramp]
+        char* top = (*emu_stacks)[(size_t)t] + EMU_STACK;          // 16-byte aligned (mmap)
+        void** slot = (void**)(top - 16);
+        *slot = (void*)emu_tramp;                                   // `ret` lands there with rsp = top - 8, as after a call
+        for (int k = 1; k <= 6; ++k) slot[-k] = nullptr;
+        unsigned int* cw = (unsigned int*)(top - 16 - 56);
+        cw[0] = 0x1f80u; cw[1] = 0x037fu;                           // default MXCSR and x87 control word
+        f.sp = (void*)cw;
+#else
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = (*emu_stacks)[(size_t)t];
+        f.ctx.uc_stack.ss_size = EMU_STACK;
+        f.ctx.uc_link = &emu_sched;
+        makecontext(&f.ctx, emu_tramp, 0);
+#endif
+        f.state = EMU_READY;
+    }
+    for (;;) {
+        bool ran = false;
+        for (int t = 0; t < T; ++t)
+            if (F[(size_t)t].state == EMU_READY) {
+                emu_cur = t;
+                threadIdx.x = (unsigned)t;
+                EMU_TO_FIBER(F[(size_t)t]);
+                ran = true;
+            }
+        int live = 0, at_block = 0;
+        for (int t = 0; t < T; ++t) { live += F[(size_t)t].state != EMU_DONE; at_block += F[(size_t)t].state == EMU_BLOCK; }
+        if (live == 0) return;
+        bool released = false;
+        for (int w0 = 0; w0 < T; w0 += 32) {
+            const int w1 = w0 + 32 < T ? w0 + 32 : T;
+            int nw = 0, nb = 0;
+            for (int t = w0; t < w1; ++t) { nw += F[(size_t)t].state == EMU_WARP; nb += F[(size_t)t].state == EMU_BLOCK; }
+            if (nw && nb) emu_fail("lanes of one warp wait at a warp collective and at __syncthreads");
+            if (nw) { emu_resolve_warp(F, w0, w1); released = true; }
+        }
+        if (!released && at_block == live) {
+            for (int t = 0; t < T; ++t)
+                if (F[(size_t)t].state == EMU_BLOCK) F[(size_t)t].state = EMU_READY;
+            released = true;
+        }
+        if (!ran && !released) emu_fail("deadlock");
+    }
+}
+template <class K, class... A>
+static void emu_launch_cfg(K kernel, dim3 grid, dim3 block, A... args) {
+    gridDim = grid; blockDim = block;
+#ifdef PFMDS_EMU_TRACE
+    fprintf(stderr, "launch %s grid (%u,%u) block %u\n", __PRETTY_FUNCTION__, grid.x, grid.y, block.x);
+#endif
+    std::function<void()> body = [&] { kernel(args...); };
+    std::function<void()>* saved = emu_body;
+    emu_body = &body;
+    for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+            blockIdx.x = bx; blockIdx.y = by;
+#ifdef PFMDS_EMU_TRACE
+            if (bx < 3 || bx + 2 > grid.x) fprintf(stderr, "  block %u\n", bx);
+#endif
+            emu_run_block((int)block.x);
+        }
+#ifdef PFMDS_EMU_TRACE
+    fprintf(stderr, "  done\n");
+#endif
+    emu_body = saved;
+}
+#endif  // PFMDS_EMU_WARP
 #define LAUNCH(kernel, grid, block, stream, ...) emu_launch_cfg(kernel, dim3(grid), dim3(block), __VA_ARGS__)
 // the standalone harnesses (tests/forces_host.cpp, tests/nl_host.cpp) launch with explicit grid sizes
 template <class K, class... A>

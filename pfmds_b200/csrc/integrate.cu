@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(IT) k_sums_partial(int N, const double4* __res
         if (threadIdx.x == 0) part[blockIdx.x * 16 + k] = s;
     }
     // block max
-#ifdef __CUDACC__
+#ifdef PFMDS_COOP
     __shared__ double mx[IT / 32];
     double m = a[10];
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));

@@ -74,7 +74,7 @@ __global__ void k_cell_count(int N, const double4* __restrict__ pos, GridD g, in
     atomicAdd(&cnt[c], 1);
 }
 
-#ifdef __CUDACC__  // the scans exchange data between lanes: device only (the host emulation uses a plain prefix sum)
+#ifdef PFMDS_COOP  // the scans exchange data between lanes: device, or the lock-step host replay (the serial replay uses a plain prefix sum)
 // exclusive scan, 2048 items per block (1024 threads x 2), block totals to `sums`
 __global__ void k_scan_block(int n, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ sums) {
     __shared__ int sh[32];
@@ -175,7 +175,7 @@ void nl_bin_atoms(pfmds_ctx* c, bool reorder) {
     for (int k = 0; k < 3; ++k) { g.n[k] = c->ncell[k]; g.inv[k] = c->ncell[k] / c->box.L[k]; }
     CK(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)(c->ncells + 1), c->st));
     LAUNCH((k_cell_count), nb, T, c->st, N, c->pos, g, c->cid, c->cell_cnt);
-#ifdef __CUDACC__
+#ifdef PFMDS_COOP
     int sb = (c->ncells + 2047) / 2048;
     LAUNCH((k_scan_block), sb, 1024, c->st, c->ncells, c->cell_cnt, c->cell_start, c->scan_tmp);
     LAUNCH((k_scan_sums), 1, 1024, c->st, sb, c->scan_tmp);
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict_
     nnum[i] = cnt;
 }
 
-#ifdef __CUDACC__  // ballot / popc compaction across the lanes of a warp: device only
+#ifdef PFMDS_COOP  // ballot / popc compaction across the lanes of a warp: device, or the lock-step host replay
 // One WARP per list-owner atom: the lanes test 32 candidates of a cell range at a time (coalesced 16-byte
 // loads of the float4 copy), the survivors of the exact FP64 test are compacted with ballot + popc into the
 // row in candidate order (deterministic), one counter per class when PART.  The three x-neighbour cells of a
@@ -406,7 +406,7 @@ inline GridD nl_grid(const int ncell[3], const BoxD& box) {
 #ifdef PFMDS_HAVE_CTX
 void nl_build(pfmds_ctx* c, NList& l) {
     const int N = c->N;
-#ifdef __CUDACC__
+#ifdef PFMDS_COOP
     const bool warp_per_atom = N < 200000;  // measured: at 1e6 atoms the thread-per-atom scan is 2x faster, at 1e4 atoms 5x slower
 #else
     const bool warp_per_atom = false;       // host replay: the warp-per-atom kernel compacts with ballots
@@ -419,7 +419,7 @@ void nl_build(pfmds_ctx* c, NList& l) {
     KTimer kt(c, KS_NL_BUILD);
 #define BUILD_ARGS N, c->pos, c->posf, c->orig, c->cell_start, c->cell_atoms, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, \
         l.nlist_alt, l.nnum, c->err
-#ifdef __CUDACC__
+#ifdef PFMDS_COOP
 #define LAUNCH_BUILD(ID, PT) do { if (warp_per_atom) LAUNCH((k_build_warp<ID, PT>), nb, T, c->st, BUILD_ARGS); \
         else LAUNCH((k_build<ID, PT>), nb, T, c->st, BUILD_ARGS); } while (0)
 #else

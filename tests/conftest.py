@@ -22,7 +22,19 @@ def _have_gpu():
         return False
 
 
+# tests/test_emulated_library.py in its lock-step flavour: the subset kept in the default CPU run (substrings of the test id)
+LOCKSTEP_KEEP = ["test_step0_lists_forces_energies", "test_parity_misc", "test_advance_logged_rows[lockstep-cu_fcc", "test_advance_logged_rows[lockstep-ab_gas",
+                 "test_golden_fixtures_and_in_step_energies[lockstep-cu_fcc", "test_golden_fixtures_and_in_step_energies[lockstep-gr_cu_morsec",
+                 "test_trajectory_22_steps[lockstep-nvt", "test_anchors", "test_rebosc", "test_save_and_restore_state",
+                 "test_deposition_edge_cases_against_the_oracle[lockstep-changes0", "test_replay_identifies_itself"]
+
+
 def pytest_collection_modifyitems(config, items):
+    if os.environ.get("PFMDS_LOCKSTEP_TESTS") != "all":
+        drop = [it for it in items if "test_emulated_library.py" in it.nodeid and "[lockstep" in it.name and not any(k in it.name for k in LOCKSTEP_KEEP)]
+        if drop:
+            config.hook.pytest_deselected(items=drop)
+            items[:] = [it for it in items if it not in drop]
     if _have_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

@@ -12,18 +12,52 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pfmds_b200", "csrc")
 HOST = os.path.join(ROOT, "pfmds_b200", "host")
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 # PFMDS_EMU_SANITIZE=1: the same replay under AddressSanitizer + UBSan in its own directory (cudaMalloc maps onto malloc, so an
 # out-of-range slot number, list row or partial-sum index of a kernel is a heap-buffer-overflow report).  Run as
 #   LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 PFMDS_EMU_SANITIZE=1 pytest tests/test_emulated_library.py
 SAN = os.environ.get("PFMDS_EMU_SANITIZE") == "1"
-OUT = os.path.join(HERE, "_build_san" if SAN else "_build")
 SANFLAGS = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if SAN else []
-CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 SOURCES = ["capi.cu", "forces.cu", "nl.cu", "integrate.cu", "rebosc.cu"]
-FLAGS = ["-x", "c++", "-std=c++17", "-O1" if SAN else "-O2", "-ffp-contract=off", "-DPFMDS_EMU_LIB", "-DSMALL_N=0", "-fPIC"] + SANFLAGS
-LIB = os.path.join(OUT, "libpfmds_b200_emu.so")
-EXE = os.path.join(OUT, "run_md_simulation_emu")
-EXE_FIT = os.path.join(OUT, "run_gr_moire_fitting_emu")
+
+
+class Build:
+    """One flavour of the host replay.  warp=False: the SERIAL replay (threads of a block one after the other; the library takes
+    its thread-per-atom kernels, -DSMALL_N=0).  warp=True: the LOCK-STEP replay (-DPFMDS_EMU_WARP, host_emu.hpp): every thread of
+    a block is a fiber, warp collectives and block barriers exchange values between them, so the library takes the very kernels
+    the GPU launches for small systems (8 lanes per atom, warp-per-atom list build, scans, shared-memory reductions)."""
+
+    def __init__(self, warp=False):
+        self.warp = warp
+        self.out = os.path.join(HERE, "_build" + ("_warp" if warp else "") + ("_san" if SAN else ""))
+        self.flags = ["-x", "c++", "-std=c++17", "-O1" if SAN else "-O2", "-ffp-contract=off", "-DPFMDS_EMU_LIB", "-fPIC"] + \
+                     (["-DPFMDS_EMU_WARP"] if warp else ["-DSMALL_N=0"]) + SANFLAGS
+        self.lib = os.path.join(self.out, "libpfmds_b200_emu.so")
+        self.exe = os.path.join(self.out, "run_md_simulation_emu")
+        self.exe_fit = os.path.join(self.out, "run_gr_moire_fitting_emu")
+
+    def build(self):
+        os.makedirs(self.out, exist_ok=True)
+        hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".hpp"))] + [os.path.join(ROOT, "include", "pfmds_b200.h")]
+        jobs, objs = [], []
+        for s in SOURCES:
+            obj = os.path.join(self.out, s[:-3] + ".o")
+            objs.append(obj)
+            if _newer(obj, [os.path.join(CSRC, s)] + hdrs):
+                jobs.append([CXX] + self.flags + ["-c", os.path.join(CSRC, s), "-o", obj])
+        stub = os.path.join(self.out, "slab_stub.o")
+        objs.append(stub)
+        if _newer(stub, [os.path.join(HERE, "slab_stub.cpp")] + hdrs):
+            jobs.append([CXX, "-std=c++17", "-O2", "-fPIC"] + SANFLAGS + ["-c", os.path.join(HERE, "slab_stub.cpp"), "-o", stub])
+        with ThreadPoolExecutor(4) as ex:
+            list(ex.map(_run, jobs))
+        if jobs or _newer(self.lib, objs):
+            _run([CXX, "-shared"] + SANFLAGS + ["-o", self.lib] + objs + ["-ldl", "-pthread"])
+        host_deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))]
+        for exe, src in ((self.exe, "run_md_simulation.cpp"), (self.exe_fit, "run_gr_moire_fitting.cpp")):
+            if _newer(exe, host_deps + [self.lib]):
+                _run([CXX, "-O2", "-std=c++17"] + SANFLAGS + ["-o", exe, os.path.join(HOST, src), "-pthread", "-L" + self.out, "-lpfmds_b200_emu", "-Wl,-rpath,$ORIGIN"])
+        return self.lib
 
 
 def _newer(target, deps):
@@ -36,29 +70,15 @@ def _run(cmd):
         raise RuntimeError("emulated build failed: %s\n%s" % (" ".join(cmd), r.stdout[-4000:]))
 
 
+SERIAL, LOCKSTEP = Build(False), Build(True)
+# the serial replay under its historical names
+OUT, LIB, EXE, EXE_FIT = SERIAL.out, SERIAL.lib, SERIAL.exe, SERIAL.exe_fit
+
+
 def build_emu():
-    os.makedirs(OUT, exist_ok=True)
-    hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".hpp"))] + [os.path.join(ROOT, "include", "pfmds_b200.h")]
-    jobs, objs = [], []
-    for s in SOURCES:
-        obj = os.path.join(OUT, s[:-3] + ".o")
-        objs.append(obj)
-        if _newer(obj, [os.path.join(CSRC, s)] + hdrs):
-            jobs.append([CXX] + FLAGS + ["-c", os.path.join(CSRC, s), "-o", obj])
-    stub = os.path.join(OUT, "slab_stub.o")
-    objs.append(stub)
-    if _newer(stub, [os.path.join(HERE, "slab_stub.cpp")] + hdrs):
-        jobs.append([CXX, "-std=c++17", "-O2", "-fPIC"] + SANFLAGS + ["-c", os.path.join(HERE, "slab_stub.cpp"), "-o", stub])
-    with ThreadPoolExecutor(4) as ex:
-        list(ex.map(_run, jobs))
-    if jobs or _newer(LIB, objs):
-        _run([CXX, "-shared"] + SANFLAGS + ["-o", LIB] + objs + ["-ldl", "-pthread"])
-    host_deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))]
-    for exe, src in ((EXE, "run_md_simulation.cpp"), (EXE_FIT, "run_gr_moire_fitting.cpp")):
-        if _newer(exe, host_deps + [LIB]):
-            _run([CXX, "-O2", "-std=c++17"] + SANFLAGS + ["-o", exe, os.path.join(HOST, src), "-pthread", "-L" + OUT, "-lpfmds_b200_emu", "-Wl,-rpath,$ORIGIN"])
-    return LIB
+    return SERIAL.build()
 
 
 if __name__ == "__main__":
-    print(build_emu())
+    import sys
+    print((LOCKSTEP if "--lockstep" in sys.argv else SERIAL).build())

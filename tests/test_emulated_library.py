@@ -2,8 +2,9 @@
 sources compiled by g++ with pfmds_b200/csrc/host_emu.hpp, kernels as serial loops over (block, thread)).  What this checks
 without a GPU: the C-ABI orchestration of libpfmds_b200 (step sequence of pfmds_advance, fused NVT path, deposition, rebosc,
 checkpoint / restore, error reporting, the hosts) and the arithmetic and indexing of every thread-per-atom kernel, against the
-oracle and the golden fixtures, with the GPU tests' own assertions.  What it cannot check: the compiled SASS, warp-cooperative
-kernels (8-lanes-per-atom variants, warp-per-atom list build, scans), CUDA graphs, streams — the `-m gpu` run remains the gate.
+oracle and the golden fixtures, with the GPU tests' own assertions; in the lock-step flavour (fibers, see below) also the
+warp-cooperative kernels the GPU launches for small systems (8 lanes per atom, warp-per-atom list build, scans, shared-memory
+reductions).  What it cannot check: the compiled SASS, CUDA graphs, streams, NVLink — the `-m gpu` run remains the gate.
 The product never loads this library (tests/test_cabi.py::test_no_cpu_fallback)."""
 import importlib
 import os
@@ -17,17 +18,30 @@ from pfmds_b200.engine import configure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "emu"))
-import build_emu as B  # noqa: E402
+import build_emu as BE  # noqa: E402
+
+B = BE.SERIAL   # the flavour the current test runs against (set per test by the `flavour` fixture)
+
+# Every test exists in two flavours: `serial` (threads of a block one after the other, thread-per-atom kernels) and `lockstep`
+# (fibers; the kernels the GPU launches for systems under 10^5 atoms: 8 lanes per atom, warp-per-atom list build, block scans,
+# shuffle / shared-memory reductions).  The lock-step replay costs ~3x more per launch: tests/conftest.py keeps a representative
+# subset of its tests in the default run (LOCKSTEP_KEEP); PFMDS_LOCKSTEP_TESTS=all runs all of them (12 min).
+def pytest_generate_tests(metafunc):
+    if "flavour" in metafunc.fixturenames:
+        metafunc.parametrize("flavour", ["serial", "lockstep"])
 
 
-@pytest.fixture(scope="module", autouse=True)
-def emu(oracle_lib):
-    B.build_emu()
-    return B.LIB
+@pytest.fixture(autouse=True)
+def _flavour(flavour, oracle_lib):
+    global B
+    B = BE.LOCKSTEP if flavour == "lockstep" else BE.SERIAL
+    B.build()
+    yield
+    B = BE.SERIAL
 
 
 def emu_gpu(case):
-    return configure(case, lib_path=B.LIB)
+    return configure(case, lib_path=B.lib)
 
 
 def replay(monkeypatch, module, **attrs):
@@ -81,14 +95,14 @@ def test_deposition(monkeypatch, thermostat):
 
 
 def test_deposition_misc(monkeypatch, tmp_path, oracle_lib):
-    m = replay(monkeypatch, "test_deposition_gpu", EXE=B.EXE)
+    m = replay(monkeypatch, "test_deposition_gpu", EXE=B.exe)
     m.test_forces_outside_all_atoms_accumulate_like_the_reference()
     m.test_deposition_matches_the_golden_fixture()
     m.test_host_deposition_run_matches_the_cpu_port(tmp_path, None, oracle_lib)
 
 
 def test_rebosc(monkeypatch, tmp_path, oracle_lib):
-    m = replay(monkeypatch, "test_rebosc_gpu", EXE=B.EXE)
+    m = replay(monkeypatch, "test_rebosc_gpu", EXE=B.exe)
     m.test_rebosc_energy_and_numerical_forces(0.04)
     m.test_rebosc_trajectory_and_energy_conservation()
     m.test_rebosc_feeds_the_graphene_normals_of_ljc()
@@ -98,7 +112,7 @@ def test_rebosc(monkeypatch, tmp_path, oracle_lib):
 
 @pytest.mark.parametrize("name", ["graphene", "ab_gas", "deposition", "cu_fcc"])
 def test_restart_is_bit_identical(monkeypatch, tmp_path, name):
-    replay(monkeypatch, "test_zz_restart_gpu", EXE=B.EXE).test_restart_reproduces_the_interrupted_run_on_the_gpu(tmp_path, None, name)
+    replay(monkeypatch, "test_zz_restart_gpu", EXE=B.exe).test_restart_reproduces_the_interrupted_run_on_the_gpu(tmp_path, None, name)
 
 
 def test_save_and_restore_state(monkeypatch):
@@ -107,24 +121,33 @@ def test_save_and_restore_state(monkeypatch):
 
 @pytest.mark.parametrize("which", ["ab_gas", "graphene"])
 def test_host_outputs(monkeypatch, tmp_path, oracle_lib, which):
-    replay(monkeypatch, "test_host_gpu", EXE=B.EXE).test_same_outputs_as_the_cpu_reference_port(tmp_path, None, oracle_lib, which)
+    replay(monkeypatch, "test_host_gpu", EXE=B.exe).test_same_outputs_as_the_cpu_reference_port(tmp_path, None, oracle_lib, which)
 
 
 def test_host_queued_log(monkeypatch, tmp_path):
-    replay(monkeypatch, "test_host_gpu", EXE=B.EXE).test_queued_log_rows_are_the_stepwise_log(tmp_path, None)
+    replay(monkeypatch, "test_host_gpu", EXE=B.exe).test_queued_log_rows_are_the_stepwise_log(tmp_path, None)
 
 
 def test_host_ensemble_ranks(monkeypatch, tmp_path):
-    replay(monkeypatch, "test_host_gpu", EXE=B.EXE).test_gpu_ensemble_ranks(tmp_path, None)
+    replay(monkeypatch, "test_host_gpu", EXE=B.exe).test_gpu_ensemble_ranks(tmp_path, None)
 
 
 @pytest.mark.parametrize("extra", [(), ("-pair",)])
 def test_fitting_rows(monkeypatch, tmp_path, oracle_lib, extra):
-    replay(monkeypatch, "test_zz_fitting_gpu", EXE_FIT=B.EXE_FIT).test_fit_rows_match_the_cpu_port(tmp_path, None, oracle_lib, extra)
+    replay(monkeypatch, "test_zz_fitting_gpu", EXE_FIT=B.exe_fit).test_fit_rows_match_the_cpu_port(tmp_path, None, oracle_lib, extra)
 
 
-def test_pipelined_lj1g_variant(monkeypatch):
-    """PFMDS_LJ1G_PIPE=1 through the C ABI (the replay always takes the thread-per-atom kernels)."""
+@pytest.mark.parametrize("fn", ["test_rjl_copper_cohesive_energy", "test_tb_graphite_sheet_energy", "test_lj_pair"])
+def test_anchors(fn):
+    """Closed forms and published figures (tests/test_zz_anchors.py) on this flavour of the replay."""
+    import test_zz_anchors as A
+    getattr(A, fn)(emu_gpu)
+
+
+def test_pipelined_lj1g_variant(monkeypatch, flavour):
+    """PFMDS_LJ1G_PIPE=1 through the C ABI (the serial replay always takes the thread-per-atom kernels)."""
+    if flavour == "lockstep":
+        pytest.skip("512 atoms take the 8-lanes-per-atom kernel in the lock-step replay, as on the GPU: the variant is not selected")
     from util import oracle, rel_err
     case = inputs.lj_fluid(n_side=8, period=5)
     a = emu_gpu(case)
@@ -141,7 +164,7 @@ def test_pipelined_lj1g_variant(monkeypatch):
 
 def test_replay_identifies_itself():
     import ctypes as C
-    lib = C.CDLL(B.LIB)
+    lib = C.CDLL(B.lib)
     lib.pfmds_version.restype = C.c_char_p
     assert b"HOST REPLAY" in lib.pfmds_version()
     err = (C.c_double * 4)()
