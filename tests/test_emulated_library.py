@@ -72,7 +72,7 @@ def test_trajectory_22_steps(monkeypatch, name, integrator):
                                 "test_particle_out_of_cell_is_reported", "test_not_enough_graphene_neighbours_is_reported",
                                 "test_refuses_what_the_reference_gets_wrong_silently", "test_upload_restarts_a_context",
                                 "test_multi_step_advance_equals_single_steps", "test_two_contexts_share_a_gpu",
-                                "test_download_into_caller_buffers"])
+                                "test_download_into_caller_buffers", "test_rjl_in_a_box_narrower_than_twice_R2"])
 def test_parity_misc(monkeypatch, fn):
     getattr(replay(monkeypatch, "test_parity_gpu"), fn)()
 

@@ -330,3 +330,19 @@ def test_download_into_caller_buffers():
     assert f2 is None and np.array_equal(p2, p) and np.array_equal(v2, v)
     with pytest.raises(PfmdsError):
         e.download(out=(np.zeros((n, 2)), None, None))
+
+
+def test_rjl_in_a_box_narrower_than_twice_R2():
+    """The second-generation rjl routines decide the minimum image after r^2, which needs R2 <= half the shortest box edge; a
+    narrower box (10.8 A against R2 = 6.0) takes the first-generation routines.  Same lists, forces and trajectory as the oracle."""
+    from pfmds_b200 import inputs
+    case = inputs.cu_fcc(ncell=3, jitter=0.05, period=5)
+    g, o = gpu(case), oracle(case)
+    for e in (g, o):
+        e.advance("nvt", 2.0, 0, 1)
+    a, b = neighbours(g, case, 0, 0), neighbours(o, case, 0, 0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert rel_err(g.download()[2], o.download()[2]) < 1e-12 and abs(g.energies()[0][0] / o.energies()[0][0] - 1) < 1e-13   # libm-grade routines
+    for e in (g, o):
+        e.advance("nvt", 2.0, 1, 12)
+    assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-12
