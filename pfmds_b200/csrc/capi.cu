@@ -641,9 +641,6 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         c->timers_on = tm && tm[0] == '1';
         const char* gr = std::getenv("PFMDS_GRAPHS");
         c->use_graphs = gr ? gr[0] == '1' : n_atoms < 200000;
-#ifndef __CUDACC__
-        c->use_graphs = false;  // host replay: no stream capture
-#endif
         const char* lp = std::getenv("PFMDS_LJ1G_PIPE");
         c->lj1g_pipe = lp && lp[0] == '1';
         const char* rg = std::getenv("PFMDS_RJL_GEN");

@@ -17,6 +17,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <functional>
+#include <vector>
+
 #define PFMDS_HOST_EMU 1
 #define __device__
 #define __host__
@@ -53,6 +56,12 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+// ---- stream capture: while a capture is open, launches and asynchronous copies / fills are recorded instead of executed, and a
+// graph launch replays them (arguments by value, as CUDA does) -- so the library's CUDA-graph replay of steady-state steps and
+// its host-side bookkeeping run in the CPU suite too
+struct emu_graph_s { std::vector<std::function<void()>> ops; };
+inline thread_local emu_graph_s* emu_capture = nullptr;
+
 #ifndef PFMDS_EMU_WARP
 static inline void __syncthreads() {}
 // only reached with SPLIT == 1 (no iterations) or in code paths the emulated build never launches
@@ -84,7 +93,7 @@ static inline double block_sum(double v) {
 }
 
 template <class K, class... A>
-static void emu_launch_cfg(K kernel, dim3 grid, dim3 block, A... args) {
+static void emu_launch_now(K kernel, dim3 grid, dim3 block, A... args) {
     gridDim = grid; blockDim = block;
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -257,7 +266,7 @@ static void emu_run_block(int T) {
     }
 }
 template <class K, class... A>
-static void emu_launch_cfg(K kernel, dim3 grid, dim3 block, A... args) {
+static void emu_launch_now(K kernel, dim3 grid, dim3 block, A... args) {
     gridDim = grid; blockDim = block;
 #ifdef PFMDS_EMU_TRACE
     fprintf(stderr, "launch %s grid (%u,%u) block %u\n", __PRETTY_FUNCTION__, grid.x, grid.y, block.x);
@@ -279,6 +288,11 @@ static void emu_launch_cfg(K kernel, dim3 grid, dim3 block, A... args) {
     emu_body = saved;
 }
 #endif  // PFMDS_EMU_WARP
+template <class K, class... A>
+static void emu_launch_cfg(K kernel, dim3 grid, dim3 block, A... args) {
+    if (emu_capture) emu_capture->ops.push_back([=] { emu_launch_now(kernel, grid, block, args...); });
+    else emu_launch_now(kernel, grid, block, args...);
+}
 #define LAUNCH(kernel, grid, block, stream, ...) emu_launch_cfg(kernel, dim3(grid), dim3(block), __VA_ARGS__)
 // the standalone harnesses (tests/forces_host.cpp, tests/nl_host.cpp) launch with explicit grid sizes
 template <class K, class... A>
@@ -289,34 +303,43 @@ typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorEmu = 1 };
 typedef struct emu_stream_s* cudaStream_t;
 typedef struct emu_event_s* cudaEvent_t;
-typedef struct emu_graph_s* cudaGraph_t;
-typedef struct emu_graphexec_s* cudaGraphExec_t;
+typedef emu_graph_s* cudaGraph_t;
+typedef emu_graph_s* cudaGraphExec_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaStreamNonBlocking = 1, cudaStreamCaptureModeThreadLocal = 1 };
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "not available in the host replay"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) { *p = (T*)calloc(bytes ? bytes : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) { if (emu_capture) return cudaErrorEmu; *p = (T*)calloc(bytes ? bytes : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
 template <class T> static inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
-static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (emu_capture) return cudaErrorEmu; memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    if (emu_capture) emu_capture->ops.push_back([=] { memmove(d, s, n); });
+    else memmove(d, s, n);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
+    if (emu_capture) emu_capture->ops.push_back([=] { memset(d, v, n); });
+    else memset(d, v, n);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)calloc(1, 8); return cudaSuccess; }
-static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+// as on the device: synchronising, allocating or copying synchronously while a capture is open is an error
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return emu_capture ? cudaErrorEmu : cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)calloc(1, 8); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
-static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return emu_capture ? cudaErrorEmu : cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
-// CUDA graphs are never used by the emulated build (use_graphs is forced off); the calls only have to compile
-static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorEmu; }
-static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorEmu; }
-static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { *e = nullptr; return cudaErrorEmu; }
-static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
-static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
-static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorEmu; }
+// CUDA graphs: a capture records closures (above), an executable graph is a copy of the list, a launch runs it
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { if (emu_capture) return cudaErrorEmu; emu_capture = new emu_graph_s; return cudaSuccess; }
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = emu_capture; emu_capture = nullptr; return *g ? cudaSuccess : cudaErrorEmu; }
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) { *e = new emu_graph_s(*g); return cudaSuccess; }
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) { for (auto& op : e->ops) op(); return cudaSuccess; }
