@@ -266,8 +266,12 @@ __device__ __forceinline__ void rjl_density_pair(const double4& pi, const double
         }
     }
 }
-__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlF& C, const BoxD& box, int mhh, double& fx, double& fy,
-                                               double& fz) {
+// E: also accumulate a1 e_p f into `se` (the repulsive energy of the owner up to the factor A0 / a1 = r0 / 2p): the force pass has
+// that exponential in hand, so a step that must report its energies pays one FP64 instruction per pair here instead of a second
+// exponential per pair in the density pass.
+template <bool E>
+__device__ __forceinline__ void rjl_force_pair_g2(const double4& pi, const double4& pj, const RjlF& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                                  double& fz, double& se) {
     double dx, dy, dz, r2;
     if (pair_inside(pi, pj, C.R22, box, mhh, dx, dy, dz, r2)) {
         double ir = mx::rsqrt_q(r2);
@@ -275,15 +279,16 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
         // switch zone first, then both exponentials side by side (mx::exp_m2), then the zone's two factors
         const bool zone = !(r2 < C.R12);
 #ifdef __CUDA_ARCH__
-        double gp, gq;  // read only when `zone`
+        double gp, gq, fsw;  // read only when `zone`
 #else
-        double gp = 1., gq = 1.;
+        double gp = 1., gq = 1., fsw = 1.;
 #endif
         if (zone) {
             double f, s;
             mx::cos_switch_m(fma(r, C.swh, C.u0), f, s);
             gp = fma(s, C.kp, f);
             gq = fma(s, C.kq, f);
+            fsw = f;
         }
         double A, eq;
         mx::exp_m2(fma(C.pa, r, C.pb), fma(C.qa, r, C.qb), A, eq, C.l2e, C.nln2);
@@ -292,11 +297,17 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
 #ifdef __CUDA_ARCH__
             asm volatile("");  // keeps this a branch: if-converted it costs every pair two multiplications and four selects
 #endif
+            if (E) se = fma(A, fsw, se);
             A *= gp; w *= gq;
-        }
+        } else if (E) se += A;
         double c = fma(-w, eq, A) * ir;
         fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
     }
+}
+__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlF& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                               double& fz) {
+    double unused = 0.;
+    rjl_force_pair_g2<false>(pi, pj, C, box, mhh, fx, fy, fz, unused);
 }
 
 template <bool E>
@@ -467,6 +478,58 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __
     }
     fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz);
     if (n > 0 && sub == 0) add_force(frc, i, fx, fy, fz);
+}
+
+// Force pass that also yields the interaction's energy (second generation only; steps that report their energies):
+// e_i = (r0 / 2p) sum_j a1 e_p f  -  xi sqrt(sum_j e_q f),  the square root being 1 / (1/Eb_i) from the density pass.
+// Same row walk and pair routine as k_rjl_force; no early exits, every thread reaches the block sum.
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlF C, BoxD box,
+                                                              WrapC W, SlabDev S, int overwrite, double erep, double xi, double* __restrict__ part) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    slab_wait(S);
+    double e = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = ld256_nc(&pos[i]);
+        double fx = 0, fy = 0, fz = 0, se = 0;
+        RowWalk<true> row(lv, i);
+        int j1;
+        double4 a = ld256_nc(&pos[row.first(n, j1)]);
+        int p = 0;
+        for (; p + 1 < n; p += 2) {
+            double4 b = ld256_nc(&pos[j1]);
+            int j2, j3;
+            row.ahead(p, n, j1, j2, j3);
+            rjl_force_pair_g2<true>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
+            a = ld256_nc(&pos[j2]);
+            rjl_force_pair_g2<true>(pi, b, C, box, W.min_half_hi, fx, fy, fz, se);
+            j1 = j3;
+        }
+        if (p < n) rjl_force_pair_g2<true>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
+        if (overwrite) frc[i] = make_double4(fx, fy, fz, 0.);
+        else add_force(frc, i, fx, fy, fz);
+        e = erep * se - (pi.w > 0. ? xi / pi.w : 0.);
+    } else if (i < N && overwrite) frc[i] = make_double4(0., 0., 0., 0.);
+    store_partial(e, part);
+}
+template <int SPLIT>
+__global__ void __launch_bounds__(FT) k_rjl_force_split_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlF C, BoxD box,
+                                                          WrapC W, double erep, double xi, double* __restrict__ part) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
+    double fx = 0, fy = 0, fz = 0, se = 0, e = 0, ie = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = ld256_nc(&pos[i]);
+        ie = pi.w;
+        for (int p = sub; p < n; p += SPLIT)
+            rjl_force_pair_g2<true>(pi, ld256_nc(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, fx, fy, fz, se);
+    }
+    fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz); se = split_sum<SPLIT>(se);
+    if (n > 0 && sub == 0) {
+        add_force(frc, i, fx, fy, fz);
+        e = erep * se - (ie > 0. ? xi / ie : 0.);
+    }
+    store_partial(e, part);
 }
 
 // ---- lj1g, pipelined variant (opt-in: PFMDS_LJ1G_PIPE=1; unmeasured on hardware so far) ----------------
@@ -858,13 +921,16 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         const bool gen2 = c->rjl_gen != 1 && rjl_gen2_ok(it.rjl, c->box);
         const ListView lv = it.nl[0].view(st);
         const int ow = (k == 0 && c->first_overwrites && N >= SMALL_N) ? 1 : 0;
-        // one launch sequence for both generations: CD / CF are the constant packs that select the pair routines
+        // one launch sequence for both generations: CD / CF are the constant packs that select the pair routines.
+        // Energies of the step: the first generation evaluates them in its density pass (a second exponential per pair), the
+        // second takes them from the force pass, which has that exponential in hand (k_rjl_force_e).
+        const bool e_in_force = with_energy && gen2;
         auto run = [&](auto CD, auto CF) {
             using TD = decltype(CD);
             using TF = decltype(CF);
             {
                 KTimer kt(c, KS_RJL_DENSITY);
-                if (with_energy) {
+                if (with_energy && !e_in_force) {
                     if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, epart);
                     else LAUNCH((k_rjl_density<true, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, epart, fused ? slab_dev(c, 1) : SlabDev{});
                     e_parts = small ? nbs : nb;
@@ -873,12 +939,21 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
                 else LAUNCH((k_rjl_density<false, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, (double*)nullptr, fused ? slab_dev(c, 1) : SlabDev{});
             }
             if (c->slab && !fused) slab_exchange(c, 1);  // ghost 1/Eb from their owners
-            {
+            if (!e_in_force) {
                 KTimer kt(c, KS_RJL_FORCE);
                 if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W);
                 else LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
             }
         };
+        if (e_in_force) {
+            run(rjl_dens_consts(it.rjl), rjl_force_consts(it.rjl));
+            const RjlF CF = rjl_force_consts(it.rjl);
+            const double erep = it.rjl.r0 / (2. * it.rjl.p);   // A0 / a1, a1 = 2 A0 p / r0
+            KTimer kt(c, KS_RJL_FORCE);
+            if (small) LAUNCH((k_rjl_force_split_e<SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, erep, it.rjl.xi, epart);
+            else LAUNCH((k_rjl_force_e), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow, erep, it.rjl.xi, epart);
+            e_parts = small ? nbs : nb;
+        } else
         if (gen2) run(rjl_dens_consts(it.rjl), rjl_force_consts(it.rjl));
         else { const RjlC C = rjl_consts(it.rjl); run(C, C); }
     }

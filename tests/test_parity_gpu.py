@@ -266,11 +266,12 @@ def test_energies_from_the_force_pass(name):
     a.advance(integ, dt, 0, 7, with_energy=True)
     b.advance(integ, dt, 0, 7)
     ea, eb = a.energies(), b.energies()
-    assert np.allclose(ea[0], eb[0], rtol=1e-13, atol=0) and ea[1] == eb[1]
+    # (rjl takes the in-step energy from its force pass, the sweep from its density pass: two formulas, measured 2e-16 apart)
+    assert np.allclose(ea[0], eb[0], rtol=1e-12, atol=0) and ea[1] == eb[1]
     assert np.array_equal(a.download()[2], b.download()[2])      # and the forces are the same bits
     a.advance(integ, dt, 7, 3)                                     # a later plain step invalidates the cached energies
     b.advance(integ, dt, 7, 3)
-    assert np.allclose(a.energies()[0], b.energies()[0], rtol=1e-13, atol=0)
+    assert np.allclose(a.energies()[0], b.energies()[0], rtol=1e-12, atol=0)
 
 
 def test_store_instead_of_zero_plus_accumulate():
