@@ -461,6 +461,7 @@ def main():
             "avg_launch_ms": avg_ms, "launches": cnt, "share_of_step": tot_ms / ms_prof, "flop_per_pair": FLOPS_PER_PAIR.get(name, 0), "pairs_per_launch": pairs,
             "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src, "copy_gbs_live": copy_gbs},
             "traffic": _ncu_traffic(name),
+            "traffic_source": "profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture r1e_top (first-generation kernel; the second generation reads the same lists and records)",
         }
         if n_atoms < 200000:
             roofline["note"] = "system of %d atoms: every kernel is launch/latency bound (grid smaller than one wave), the FP64 fraction is not the figure of merit" % n_atoms
