@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <time.h>
+
 #include <functional>
 #include <vector>
 
@@ -333,9 +335,15 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return emu_captu
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)calloc(1, 8); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+// events carry the host clock: elapsed times of the replay are wall times of the serial loops (never zero)
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) {
+    if (emu_capture) return cudaSuccess;
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    *(double*)e = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    return cudaSuccess;
+}
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return emu_capture ? cudaErrorEmu : cudaSuccess; }
-static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { double d = *(double*)b - *(double*)a; *ms = (float)(d > 1e-6 ? d : 1e-6); return cudaSuccess; }
 // CUDA graphs: a capture records closures (above), an executable graph is a copy of the list, a launch runs it
 static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { if (emu_capture) return cudaErrorEmu; emu_capture = new emu_graph_s; return cudaSuccess; }
 static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = emu_capture; emu_capture = nullptr; return *g ? cudaSuccess : cudaErrorEmu; }

@@ -63,3 +63,36 @@ def test_reference_arm_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "atom-steps/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_main_dry_run_on_the_host_replay(oracle_lib, monkeypatch, capsys):
+    """bench.py's default arm end to end WITHOUT a GPU: main() runs unchanged on the host replay of the library (a small crystal
+    in place of the 10^6-atom one, torch.cuda stubbed) and must print one complete JSON line.  No number of it means anything;
+    the point is that no code path of the bench script is first executed on the GPU box."""
+    import numpy as np
+    import torch
+    import build_emu as B
+    import pfmds_b200.engine as E
+    import bench
+    B.build_emu()
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch, "tensor", lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items() if k != "device"}))
+    orig = E.configure
+    monkeypatch.setattr(E, "configure", lambda case, device=0, **kw: orig(case, lib_path=B.LIB))
+    monkeypatch.setattr(E, "measure_peaks", lambda device=0: (34.8, 6400.0))          # the device micro-benchmarks do not exist on the host
+    small = inputs.cu_fcc(ncell=5, jitter=0.02, period=20, steps=40)
+    monkeypatch.setattr(bench, "build_case", lambda workload, seed, steps, nx=1: (small, "nvt", "dry run: Cu fcc 5^3 cells"))
+    monkeypatch.setattr(bench, "cpu_baseline_sample", lambda steps, threads=None: (500, steps, 1.0, 1))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "8", "--warmup", "3", "--no-variants"])
+    assert bench.main() == 0
+    line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["steps"] == 8 and line["gpu_launches"] > 0 and line["config"]["workload"].startswith("dry run")
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and "pfmds_advance_logged" in line["e2e"]["what"]
+    assert line["cpu_baseline"]["kind"] == "port"
