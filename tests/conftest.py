@@ -23,10 +23,10 @@ def _have_gpu():
 
 
 # tests/test_emulated_library.py in its lock-step flavour: the subset kept in the default CPU run (substrings of the test id)
-LOCKSTEP_KEEP = ["test_step0_lists_forces_energies", "test_parity_misc", "test_advance_logged_rows[lockstep-cu_fcc", "test_advance_logged_rows[lockstep-ab_gas",
-                 "test_golden_fixtures_and_in_step_energies[lockstep-cu_fcc", "test_golden_fixtures_and_in_step_energies[lockstep-gr_cu_morsec",
-                 "test_trajectory_22_steps[lockstep-nvt", "test_anchors", "test_rebosc", "test_save_and_restore_state",
-                 "test_deposition_edge_cases_against_the_oracle[lockstep-changes0", "test_replay_identifies_itself"]
+LOCKSTEP_KEEP = ["test_step0_lists_forces_energies", "test_parity_misc", "test_advance_logged_rows[lockstep-cu_fcc",
+                 "test_golden_fixtures_and_in_step_energies[lockstep-cu_fcc", "test_golden_fixtures_and_in_step_energies[lockstep-gr_cu_ljc]",
+                 "test_trajectory_22_steps[lockstep-nvt-ab_gas", "test_anchors", "test_deposition_edge_cases_against_the_oracle[lockstep-changes0",
+                 "test_replay_identifies_itself"]
 
 
 def pytest_collection_modifyitems(config, items):
