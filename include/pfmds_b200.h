@@ -113,7 +113,9 @@ int pfmds_energies(pfmds_ctx* ctx, double* e_inter, double* kinetic_energy, doub
 int pfmds_diagnostics(pfmds_ctx* ctx, double force_sum[3], double mass_center[3], double mass_center_velocity[3],
                       double* max_velocity, int* nl_load);
 
-/* Copies state back in file order; any pointer may be NULL.  Synchronises. */
+/* Copies state back in file order (x y z per atom, what write_particle_group prints: md_read_write.f90:65-107); any pointer may be
+ * NULL.  The device undoes its cell ordering itself and every requested array arrives with one transfer straight into the
+ * caller's buffer, so pinned buffers are filled at full PCIe rate.  Synchronises. */
 int pfmds_download(pfmds_ctx* ctx, double* positions, double* velocities, double* forces);
 
 /* The reference-shaped view of one neighbour list (type neighbour_list, md_general.f90:30-35):
