@@ -6,7 +6,10 @@
 // the shipped binaries are Win32) and it holds no tests, golden vectors or sample outputs.  This
 // restatement follows the reference line by line (citations below are relative to
 // /root/reference/code_source/) and is validated by physics invariants (force = -grad E by finite
-// differences, sum F = 0, conserved energy) in tests/test_oracle_*.py.
+// differences, sum F = 0, conserved energy) in tests/test_oracle.py, and anchored from outside the repository by
+// tests/test_zz_anchors.py: closed forms of rjl / tb / lj1g on perfect lattices written in numpy from the formulas (1e-12) and the
+// figures the parameter sets were fitted to in their source papers (Cleri-Rosato Cu 3.544 eV/atom at a = 3.615 A; Brenner set I
+// graphite 7.3756 eV/atom at 1.42 A).
 //
 // Conventions: all reals are double (the reference builds with -fdefault-real-8); indices are
 // 0-based here and 1-based in the reference; arrays dimensioned (3,N) in Fortran are [3*i+k] here;
