@@ -137,11 +137,14 @@ def test_fitting_rows(monkeypatch, tmp_path, oracle_lib, extra):
     replay(monkeypatch, "test_zz_fitting_gpu", EXE_FIT=B.exe_fit).test_fit_rows_match_the_cpu_port(tmp_path, None, oracle_lib, extra)
 
 
-@pytest.mark.parametrize("fn", ["test_rjl_copper_cohesive_energy", "test_tb_graphite_sheet_energy", "test_lj_pair"])
+@pytest.mark.parametrize("fn", ["test_rjl_copper_cohesive_energy", "test_tb_graphite_sheet_energy", "test_lj_pair", "ljc", "morsec"])
 def test_anchors(fn):
     """Closed forms and published figures (tests/test_zz_anchors.py) on this flavour of the replay."""
     import test_zz_anchors as A
-    getattr(A, fn)(emu_gpu)
+    if fn in ("ljc", "morsec"):
+        A.test_cosine_potentials_adatom_over_graphene(emu_gpu, fn)
+    else:
+        getattr(A, fn)(emu_gpu)
 
 
 def test_pipelined_lj1g_variant(monkeypatch, flavour):

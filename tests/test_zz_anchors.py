@@ -9,6 +9,8 @@ of the oracle, and of the CUDA library (on the GPU, and replayed on the host in 
   7.3756 eV/atom at a bond length of 1.42 A.  (Published figures quoted from the papers' tables; this container has no network
   to re-read them.  The rounded parameters of the settings files give 7.3767.)
 * lj1g: an isolated pair, E(r) = 4 eps ((sig/r)^12 - (sig/r)^6) and its derivative, minimum -eps at 2^(1/6) sig.
+* ljc / morsec (LennardJonesCosine.f90:26-51, MorseCosine.f90:26-51): one metal atom over a flat graphene sheet, where every carbon
+  normal is (0, 0, 1): the sum of the pair terms with V3 = (|dz| / r)^delt, and the force on the atom as -dE/dh.
 """
 import os
 import sys
@@ -132,3 +134,55 @@ def test_lj_pair(make):
         fr = 24 * eps * (2 * x * x - x) / r                                  # -dE/dr, repulsive positive
         assert np.allclose(f[1], fr * np.array([0.6, 0.8, 0.0]), rtol=1e-12, atol=1e-16) and np.allclose(f[0], -f[1], rtol=0, atol=1e-18)
     assert abs(en - 4 * eps * ((sig / 5.0) ** 12 - (sig / 5.0) ** 6)) < 1e-15 and abs(-eps - 4 * eps * (0.25 - 0.5)) < 1e-18
+
+
+# ---- ljc / morsec: one metal atom over a flat graphene sheet ----------------------------------------------------------------
+def _adatom(interface, h):
+    c = inputs.graphene_rebosc(cells=(8, 5), jitter=0.0, lz=40.0)
+    n = len(c["mass"])
+    top = c["pos"][0] + np.array([0.37, 0.21, h])                      # off every symmetry point, h above the sheet
+    params = {"ljc": [0.02, 3.0, 2.0, 6.0, 7.0, 0.0], "morsec": [0.03, 3.2, 1.2, 2.0, 6.0, 7.0, 0.0]}[interface]
+    return dict(
+        title="adatom", box=c["box"], pos=np.vstack([c["pos"], top]), vel=np.zeros((n + 1, 3)), mass=np.append(c["mass"], 63.546),
+        names=["C"] * n + ["CU"], groups=[["C", "#"], ["CU", "#"], ["C", "CU"], ["#", "#"]],
+        roles=dict(all_moving=3, xyz_moving=3, z_moving=4, all_atoms=3, traj_group=4, period_traj=10 ** 9),
+        integrators=[("nve", 0.5, 10, 10 ** 9, 10 ** 9)], ms_de=1e-8, nhc=[], zero_momentum_period=10 ** 9, invert_z_vel=False, initial_temperature=0.0,
+        interactions=[dict(name=interface, file="p.txt", params=params, lists=[(1, 2, 4, 7.5, 5), (2, 1, 160, 7.5, 5), (1, 1, 3, 1.9, 5)])]), params
+
+
+def _cos_closed_form(interface, case, p):
+    """E = sum over carbon atoms within R2 of the pair term of LennardJonesCosine.f90:26-51 / MorseCosine.f90:26-51 with the sheet's
+    normal (0, 0, 1): V3 = (|dz| / r)^delt."""
+    pos, L = case["pos"], case["box"]
+    d = pos[:-1] - pos[-1]
+    d -= L * np.round(d / L)
+    r = np.sqrt((d * d).sum(1))
+    R1, R2 = (p[3], p[4]) if interface == "ljc" else (p[4], p[5])
+    delt = p[2] if interface == "ljc" else p[3]
+    keep = r < R2
+    r, dz = r[keep], np.abs(d[keep, 2])
+    f = np.where(r < R1, 1.0, 0.5 * (1.0 + np.cos(3.14159265358979 * (r - R1) / (R2 - R1))))     # cut_off_function.f90:6-16
+    v3 = (dz / r) ** delt
+    if interface == "ljc":
+        v2 = (p[1] / r) ** 6
+        return (4.0 * p[0] * (v2 * v2 - v2 * v3) * f).sum()
+    v2 = np.exp(-p[2] * (r - p[1]))
+    return (p[0] * (v2 * v2 - 2.0 * v2 * v3) * f).sum()
+
+
+@pytest.mark.parametrize("interface", ["ljc", "morsec"])
+@pytest.mark.parametrize("make", ENGINES)
+def test_cosine_potentials_adatom_over_graphene(make, interface):
+    h = 2.9
+    case, p = _adatom(interface, h)
+    e = make(case)
+    e.advance("nve", 0.5, 0, 1)
+    en, f = e.energies()[0][0], e.download()[2]
+    exact = _cos_closed_form(interface, case, p)
+    assert abs(exact) > 1e-3 and abs(en - exact) < 1e-11 * abs(exact)
+    # force on the metal atom along z = -dE/dh of the closed form (central difference); the sheet takes the opposite total
+    dh = 1e-5
+    ep = _cos_closed_form(interface, _adatom(interface, h + dh)[0], p)
+    em = _cos_closed_form(interface, _adatom(interface, h - dh)[0], p)
+    assert abs(f[-1, 2] - (-(ep - em) / (2 * dh))) < 2e-7 * np.abs(f).max()
+    assert np.abs(f.sum(0)).max() < 1e-12
