@@ -53,6 +53,12 @@ static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int __double2hiint(double d) { long long v; memcpy(&v, &d, 8); return (int)(v >> 32); }
 static inline int __double2loint(double d) { long long v; memcpy(&v, &d, 8); return (int)(v & 0xffffffffll); }
+static inline double __hiloint2double(int hi, int lo) { unsigned long long v = ((unsigned long long)(unsigned int)hi << 32) | (unsigned int)lo; double d; memcpy(&d, &v, 8); return d; }
+// ranks of the slab decomposition are OS threads in the replay: fences are real, a sleeping spin loop gives up its time slice
+#include <sched.h>
+#include <atomic>
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __nanosleep(unsigned) { sched_yield(); }
 // separately rounded product / sum: the emulated builds use -ffp-contract=off, so plain operators do that
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
@@ -334,6 +340,13 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return emu_capture ? cudaErrorEmu : cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)calloc(1, 8); return cudaSuccess; }
+enum { cudaEventBlockingSync = 1, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+// "inter-process" handles of the slab decomposition: the ranks of the replay share one address space, a handle is the pointer
+struct cudaIpcMemHandle_t { char reserved[64]; };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 // events carry the host clock: elapsed times of the replay are wall times of the serial loops (never zero)
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) {

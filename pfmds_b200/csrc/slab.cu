@@ -13,8 +13,13 @@
 // library has no link-time dependency on it (inside a torch process the bundled libnccl.so.2 is reused).
 // Supported interactions in this mode: lj, lj1g, rjl (tb / ljc / morsec would need ghost bond orders and
 // normals: refused).
+#include "ctx.hpp"
+#ifdef __CUDACC__
 #include <dlfcn.h>
 #include <nccl.h>
+#else
+#include "nccl_emu.hpp"  // test support: the lock-step host replay of the test suite runs the ranks as threads of one process
+#endif
 
 #include <algorithm>
 #include <cstdio>
@@ -41,12 +46,19 @@ struct NcclApi {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     void load() {
         if (h) return;
+#ifndef __CUDACC__   // host replay (tests/emu): in-process stand-in, see nccl_emu.hpp
+        h = this;
+        GetUniqueId = emu_ncclGetUniqueId; CommInitRank = emu_ncclCommInitRank; CommDestroy = emu_ncclCommDestroy; Send = emu_ncclSend; Recv = emu_ncclRecv;
+        AllReduce = emu_ncclAllReduce; GroupStart = emu_ncclGroupStart; GroupEnd = emu_ncclGroupEnd; GetErrorString = emu_ncclGetErrorString;
+        return;
+#else
         h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!h) throw std::string("cannot load libnccl.so.2: ") + dlerror();
 #define SYM(f) *(void**)(&f) = dlsym(h, "nccl" #f); if (!f) throw std::string("libnccl lacks nccl" #f)
         SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllReduce); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
+#endif
     }
 };
 NcclApi g_nccl;
@@ -131,9 +143,9 @@ __global__ void k_sl_scan_add(int n, int* out, const int* __restrict__ sums) {
 static void exclusive_scan(pfmds_ctx* c, Slab* s, const int* in, int* out, int n, int* total_d) {
     if (n == 0) { CK(cudaMemsetAsync(total_d, 0, sizeof(int), c->st)); return; }
     int sb = (n + 2047) / 2048;
-    k_sl_scan_block<<<sb, 1024, 0, c->st>>>(n, in, out, s->scan_tmp);
-    k_sl_scan_sums<<<1, 32, 0, c->st>>>(sb, s->scan_tmp, total_d);
-    k_sl_scan_add<<<(n + 255) / 256, 256, 0, c->st>>>(n, out, s->scan_tmp);
+    LAUNCH((k_sl_scan_block), sb, 1024, c->st, n, in, out, s->scan_tmp);
+    LAUNCH((k_sl_scan_sums), 1, 32, c->st, sb, s->scan_tmp, total_d);
+    LAUNCH((k_sl_scan_add), (n + 255) / 256, 256, c->st, n, out, s->scan_tmp);
     c->launches += 3;
 }
 
@@ -257,15 +269,23 @@ __global__ void k_sl_signal(int* to_left, int* to_right, int seq) {
     *reinterpret_cast<volatile int*>(to_right) = seq;
     __threadfence_system();
 }
+__device__ __forceinline__ unsigned long long sl_now_ns() {
+    unsigned long long t;
+#ifdef __CUDACC__
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#else  // host replay
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    t = (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+#endif
+    return t;
+}
 // wait until both neighbours have published at least `seq`; gives up after ~10 s and records an error instead of hanging
 __global__ void k_sl_wait(const int* from_left, const int* from_right, int seq, int* err) {
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned long long t0 = sl_now_ns();
     while (*reinterpret_cast<const volatile int*>(from_left) < seq || *reinterpret_cast<const volatile int*>(from_right) < seq) {
         if (*reinterpret_cast<volatile int*>(err) != 0) break;
         __nanosleep(200);
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        unsigned long long t = sl_now_ns();
         if (t - t0 > 3000000000ull) { raise_error(err, 31, seq, 0); break; }
     }
     __threadfence_system();
@@ -341,7 +361,7 @@ static void slab_exchange_peer_slots(pfmds_ctx* c, Slab* s) {
     // per-slot view of the same lists, for the kernels that push while they compute
     for (int d = 0; d < 2; ++d) {
         CK(cudaMemsetAsync(s->rs[d], 0xff, sizeof(int) * c->stride, c->st));
-        if (s->n_send[d] > 0) k_sl_scatter_rs<<<(s->n_send[d] + 255) / 256, 256, 0, c->st>>>(s->n_send[d], s->send_idx[d], s->pslot[d], s->rs[d]);
+        if (s->n_send[d] > 0) LAUNCH((k_sl_scatter_rs), (s->n_send[d] + 255) / 256, 256, c->st, s->n_send[d], s->send_idx[d], s->pslot[d], s->rs[d]);
     }
     s->pos_pushed = false; s->wait_pos_seq = 0;
 }
@@ -351,7 +371,7 @@ void slab_step_done(pfmds_ctx* c) {
     Slab* s = c->slab;
     if (!s->p2p) return;
     s->seq_done += 1;
-    k_sl_signal<<<1, 1, 0, c->st>>>(s->peer_flags[0] + 5, s->peer_flags[1] + 4, s->seq_done);
+    LAUNCH((k_sl_signal), 1, 1, c->st, s->peer_flags[0] + 5, s->peer_flags[1] + 4, s->seq_done);
     c->launches += 1;
 }
 
@@ -491,7 +511,7 @@ void slab_redistribute(pfmds_ctx* c) {
     if ((s->nranks == 2 && s->W <= 2.0 * s->H) || s->W <= s->H)
         throw std::string("slab decomposition: slabs of width ") + std::to_string(s->W) + " A are too thin for a halo of " + std::to_string(s->H) + " A";
     int *f0 = s->flag, *f1 = s->flag + c->stride, *f2 = s->flag + 2 * c->stride;
-    k_sl_classify<<<(N0 + T - 1) / T, T, 0, c->st>>>(N0, c->pos, c->gmask, c->orig, s->W, s->nranks, s->rank, s->cat, f0, f1, f2, c->err);
+    LAUNCH((k_sl_classify), (N0 + T - 1) / T, T, c->st, N0, c->pos, c->gmask, c->orig, s->W, s->nranks, s->rank, s->cat, f0, f1, f2, c->err);
     exclusive_scan(c, s, f0, s->scan[0], N0, s->cnt_d + 0);
     exclusive_scan(c, s, f1, s->scan[1], N0, s->cnt_d + 1);
     exclusive_scan(c, s, f2, s->scan[2], N0, s->cnt_d + 2);
@@ -502,18 +522,18 @@ void slab_redistribute(pfmds_ctx* c) {
     exchange_counts(c, s, ns, nr);
     const int n_stay = h[0];
     if ((size_t)n_stay + nr[0] + nr[1] > c->stride) throw std::string("slab decomposition: capacity exceeded by migration");
-    k_sl_pack_migrants<<<(N0 + T - 1) / T, T, 0, c->st>>>(N0, c->pos, c->vel, c->gmask, c->orig, s->cat, s->scan[0], s->scan[1], s->scan[2], c->pos2,
+    LAUNCH((k_sl_pack_migrants), (N0 + T - 1) / T, T, c->st, N0, c->pos, c->vel, c->gmask, c->orig, s->cat, s->scan[0], s->scan[1], s->scan[2], c->pos2,
                                                          c->vel2, c->gmask2, c->orig2, s->sbuf[0], s->sbuf[1]);
     std::swap(c->pos, c->pos2); std::swap(c->vel, c->vel2); std::swap(c->gmask, c->gmask2); std::swap(c->orig, c->orig2);
     neighbour_exchange(c, s, ns, nr, MIG_W);
-    if (nr[0] > 0) k_sl_unpack_migrants<<<(nr[0] + T - 1) / T, T, 0, c->st>>>(nr[0], s->rbuf[0], n_stay, c->pos, c->vel, c->gmask, c->orig);
-    if (nr[1] > 0) k_sl_unpack_migrants<<<(nr[1] + T - 1) / T, T, 0, c->st>>>(nr[1], s->rbuf[1], n_stay + nr[0], c->pos, c->vel, c->gmask, c->orig);
+    if (nr[0] > 0) LAUNCH((k_sl_unpack_migrants), (nr[0] + T - 1) / T, T, c->st, nr[0], s->rbuf[0], n_stay, c->pos, c->vel, c->gmask, c->orig);
+    if (nr[1] > 0) LAUNCH((k_sl_unpack_migrants), (nr[1] + T - 1) / T, T, c->st, nr[1], s->rbuf[1], n_stay + nr[0], c->pos, c->vel, c->gmask, c->orig);
     s->n_local = n_stay + nr[0] + nr[1];
     c->launches += 4;
     // ghosts
     const int NL = s->n_local;
     const double x_lo = s->rank * s->W, x_hi = (s->rank + 1) * s->W;
-    k_sl_border_flags<<<(NL + T - 1) / T, T, 0, c->st>>>(NL, c->pos, x_lo, x_hi, s->H, f0, f1);
+    LAUNCH((k_sl_border_flags), (NL + T - 1) / T, T, c->st, NL, c->pos, x_lo, x_hi, s->H, f0, f1);
     exclusive_scan(c, s, f0, s->scan[0], NL, s->cnt_d + 3);
     exclusive_scan(c, s, f1, s->scan[1], NL, s->cnt_d + 4);
     CK(cudaMemcpyAsync(h, s->cnt_d + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -521,13 +541,13 @@ void slab_redistribute(pfmds_ctx* c) {
     s->n_send[0] = h[0]; s->n_send[1] = h[1];
     exchange_counts(c, s, s->n_send, s->n_recv);
     if ((size_t)NL + s->n_recv[0] + s->n_recv[1] > c->stride) throw std::string("slab decomposition: capacity exceeded by ghosts");
-    k_sl_pack_ghosts<<<(NL + T - 1) / T, T, 0, c->st>>>(NL, c->pos, c->gmask, c->orig, f0, f1, s->scan[0], s->scan[1], s->send_idx[0], s->send_idx[1],
+    LAUNCH((k_sl_pack_ghosts), (NL + T - 1) / T, T, c->st, NL, c->pos, c->gmask, c->orig, f0, f1, s->scan[0], s->scan[1], s->send_idx[0], s->send_idx[1],
                                                        s->sbuf[0], s->sbuf[1]);
     neighbour_exchange(c, s, s->n_send, s->n_recv, GH_W);
     if (s->n_recv[0] > 0)
-        k_sl_unpack_ghosts<<<(s->n_recv[0] + T - 1) / T, T, 0, c->st>>>(s->n_recv[0], s->rbuf[0], NL, c->pos, c->vel, c->gmask, c->orig, s->ghost_slot[0]);
+        LAUNCH((k_sl_unpack_ghosts), (s->n_recv[0] + T - 1) / T, T, c->st, s->n_recv[0], s->rbuf[0], NL, c->pos, c->vel, c->gmask, c->orig, s->ghost_slot[0]);
     if (s->n_recv[1] > 0)
-        k_sl_unpack_ghosts<<<(s->n_recv[1] + T - 1) / T, T, 0, c->st>>>(s->n_recv[1], s->rbuf[1], NL + s->n_recv[0], c->pos, c->vel, c->gmask, c->orig,
+        LAUNCH((k_sl_unpack_ghosts), (s->n_recv[1] + T - 1) / T, T, c->st, s->n_recv[1], s->rbuf[1], NL + s->n_recv[0], c->pos, c->vel, c->gmask, c->orig,
                                                                        s->ghost_slot[1]);
     s->n_ghost = s->n_recv[0] + s->n_recv[1];
     c->N = NL + s->n_ghost;
@@ -539,8 +559,8 @@ void slab_after_reorder(pfmds_ctx* c) {
     Slab* s = c->slab;
     const int T = 256;
     for (int d = 0; d < 2; ++d) {
-        if (s->n_send[d] > 0) k_sl_remap<<<(s->n_send[d] + T - 1) / T, T, 0, c->st>>>(s->n_send[d], s->send_idx[d], c->newslot);
-        if (s->n_recv[d] > 0) k_sl_remap<<<(s->n_recv[d] + T - 1) / T, T, 0, c->st>>>(s->n_recv[d], s->ghost_slot[d], c->newslot);
+        if (s->n_send[d] > 0) LAUNCH((k_sl_remap), (s->n_send[d] + T - 1) / T, T, c->st, s->n_send[d], s->send_idx[d], c->newslot);
+        if (s->n_recv[d] > 0) LAUNCH((k_sl_remap), (s->n_recv[d] + T - 1) / T, T, c->st, s->n_recv[d], s->ghost_slot[d], c->newslot);
     }
     c->launches += 4;
     if (s->p2p) slab_exchange_peer_slots(c, s);
@@ -558,10 +578,10 @@ void slab_exchange(pfmds_ctx* c, int field) {
             // positions: pushed by the kick+drift kernel itself when it was the fused variant, else pushed here; either way
             // the first density kernel waits for the neighbours' flag in its prologue
             if (!s->pos_pushed) {
-                k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 4, s->flags + 5, s->seq_done, c->err);
-                if (n > 0) k_sl_push<0><<<(n + T - 1) / T, T, 0, c->st>>>(nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
+                LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 4, s->flags + 5, s->seq_done, c->err);
+                if (n > 0) LAUNCH((k_sl_push<0>), (n + T - 1) / T, T, c->st, nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
                 s->seq_pos += 1;
-                k_sl_signal<<<1, 1, 0, c->st>>>(s->peer_flags[0] + 1, s->peer_flags[1] + 0, s->seq_pos);
+                LAUNCH((k_sl_signal), 1, 1, c->st, s->peer_flags[0] + 1, s->peer_flags[1] + 0, s->seq_pos);
                 c->launches += 3;
             }
             s->pos_pushed = false;
@@ -571,17 +591,17 @@ void slab_exchange(pfmds_ctx* c, int field) {
         }
         if (field == 0) {
             // my neighbours' force kernels of the previous step must be done with the old ghost positions
-            k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 4, s->flags + 5, s->seq_done, c->err);
-            if (n > 0) k_sl_push<0><<<(n + T - 1) / T, T, 0, c->st>>>(nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
+            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 4, s->flags + 5, s->seq_done, c->err);
+            if (n > 0) LAUNCH((k_sl_push<0>), (n + T - 1) / T, T, c->st, nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
             s->seq_pos += 1;
-            k_sl_signal<<<1, 1, 0, c->st>>>(s->peer_flags[0] + 1, s->peer_flags[1] + 0, s->seq_pos);   // I am my left neighbour's right neighbour
-            k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 0, s->flags + 1, s->seq_pos, c->err);
+            LAUNCH((k_sl_signal), 1, 1, c->st, s->peer_flags[0] + 1, s->peer_flags[1] + 0, s->seq_pos);   // I am my left neighbour's right neighbour
+            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 0, s->flags + 1, s->seq_pos, c->err);
             c->launches += 4;
         } else {
-            if (n > 0) k_sl_push<1><<<(n + T - 1) / T, T, 0, c->st>>>(nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
+            if (n > 0) LAUNCH((k_sl_push<1>), (n + T - 1) / T, T, c->st, nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
             s->seq_w += 1;
-            k_sl_signal<<<1, 1, 0, c->st>>>(s->peer_flags[0] + 3, s->peer_flags[1] + 2, s->seq_w);
-            k_sl_wait<<<1, 1, 0, c->st>>>(s->flags + 2, s->flags + 3, s->seq_w, c->err);
+            LAUNCH((k_sl_signal), 1, 1, c->st, s->peer_flags[0] + 3, s->peer_flags[1] + 2, s->seq_w);
+            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 2, s->flags + 3, s->seq_w, c->err);
             c->launches += 3;
         }
         CK(cudaGetLastError());
@@ -589,14 +609,14 @@ void slab_exchange(pfmds_ctx* c, int field) {
     }
     for (int d = 0; d < 2; ++d) {
         if (s->n_send[d] == 0) continue;
-        if (field == 0) k_sl_pack_halo<0><<<(s->n_send[d] + T - 1) / T, T, 0, c->st>>>(s->n_send[d], s->send_idx[d], c->pos, s->sbuf[d]);
-        else k_sl_pack_halo<1><<<(s->n_send[d] + T - 1) / T, T, 0, c->st>>>(s->n_send[d], s->send_idx[d], c->pos, s->sbuf[d]);
+        if (field == 0) LAUNCH((k_sl_pack_halo<0>), (s->n_send[d] + T - 1) / T, T, c->st, s->n_send[d], s->send_idx[d], c->pos, s->sbuf[d]);
+        else LAUNCH((k_sl_pack_halo<1>), (s->n_send[d] + T - 1) / T, T, c->st, s->n_send[d], s->send_idx[d], c->pos, s->sbuf[d]);
     }
     neighbour_exchange(c, s, s->n_send, s->n_recv, field == 0 ? 3 : 1);
     for (int d = 0; d < 2; ++d) {
         if (s->n_recv[d] == 0) continue;
-        if (field == 0) k_sl_unpack_halo<0><<<(s->n_recv[d] + T - 1) / T, T, 0, c->st>>>(s->n_recv[d], s->ghost_slot[d], s->rbuf[d], c->pos);
-        else k_sl_unpack_halo<1><<<(s->n_recv[d] + T - 1) / T, T, 0, c->st>>>(s->n_recv[d], s->ghost_slot[d], s->rbuf[d], c->pos);
+        if (field == 0) LAUNCH((k_sl_unpack_halo<0>), (s->n_recv[d] + T - 1) / T, T, c->st, s->n_recv[d], s->ghost_slot[d], s->rbuf[d], c->pos);
+        else LAUNCH((k_sl_unpack_halo<1>), (s->n_recv[d] + T - 1) / T, T, c->st, s->n_recv[d], s->ghost_slot[d], s->rbuf[d], c->pos);
     }
     c->launches += 4;
     CK(cudaGetLastError());

@@ -40,14 +40,15 @@ class Build:
         os.makedirs(self.out, exist_ok=True)
         hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".hpp"))] + [os.path.join(ROOT, "include", "pfmds_b200.h")]
         jobs, objs = [], []
-        for s in SOURCES:
+        for s in SOURCES + (["slab.cu"] if self.warp else []):   # the slab decomposition needs the lock-step flavour (scans, spin waits)
             obj = os.path.join(self.out, s[:-3] + ".o")
             objs.append(obj)
             if _newer(obj, [os.path.join(CSRC, s)] + hdrs):
                 jobs.append([CXX] + self.flags + ["-c", os.path.join(CSRC, s), "-o", obj])
         stub = os.path.join(self.out, "slab_stub.o")
-        objs.append(stub)
-        if _newer(stub, [os.path.join(HERE, "slab_stub.cpp")] + hdrs):
+        if not self.warp:
+            objs.append(stub)
+        if not self.warp and _newer(stub, [os.path.join(HERE, "slab_stub.cpp")] + hdrs):
             jobs.append([CXX, "-std=c++17", "-O2", "-fPIC"] + SANFLAGS + ["-c", os.path.join(HERE, "slab_stub.cpp"), "-o", stub])
         with ThreadPoolExecutor(4) as ex:
             list(ex.map(_run, jobs))

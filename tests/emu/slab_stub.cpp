@@ -1,5 +1,6 @@
-// TEST SUPPORT ONLY: the slab decomposition (pfmds_b200/csrc/slab.cu: NCCL, CUDA IPC, peer memory) has no host replay; the emulated
-// library links these stand-ins so that the single-context paths can be exercised.  c->slab is never set, so none of them runs.
+// TEST SUPPORT ONLY: the SERIAL flavour of the host replay cannot run the slab decomposition (pfmds_b200/csrc/slab.cu uses warp
+// scans and spin waits) and links these stand-ins; c->slab is never set there, so none of them runs.  The LOCK-STEP flavour
+// compiles slab.cu itself (tests/test_slab_lockstep.py).
 #define PFMDS_EMU_LIB 1
 #include <string>
 

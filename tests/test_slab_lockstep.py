@@ -1,0 +1,100 @@
+"""The slab decomposition (pfmds_b200/csrc/slab.cu) WITHOUT GPUs: the lock-step host replay of the library with the ranks as
+threads of this process — NCCL replaced by an in-process stand-in (pfmds_b200/csrc/nccl_emu.hpp), CUDA IPC handles by plain
+pointers, the spin-wait / signal kernels of the peer-memory halo running against each other for real.  Same comparison as
+tests/test_slab_gpu.py: the decomposed run against the whole system in one context — atom ownership, positions, velocities,
+forces, energies, thermostat and diagnostics after steps that include list rebuilds, migration and ghost re-selection; with 2
+ranks (left neighbour = right neighbour) and 3, with the direct halo and with the NCCL halo (PFMDS_SLAB_P2P=0)."""
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from pfmds_b200 import inputs
+from pfmds_b200.engine import configure
+from pfmds_b200.slab import configure_slab, make_unique_id
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+import build_emu as BE  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(oracle_lib):
+    return BE.LOCKSTEP.build()
+
+
+def _case(which):
+    if which == "rjl":
+        case = inputs.cu_fcc(cells=(12, 4, 4), jitter=0.05, period=5, temperature=900.0)    # hot, and shifted so that an atomic plane
+        case["pos"] = case["pos"].copy()                                                    # lies on every slab face: atoms cross it
+        case["pos"][:, 0] = (case["pos"][:, 0] - 0.25 * 3.615 + 0.02) % case["box"][0]
+        return case, "nvt", 2.0
+    if which == "lj1g":
+        return inputs.lj_fluid(n_side=10, period=5, temperature=300.0), "nve", 1.0
+    case = inputs.ab_gas(n_side=10, period=5, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, temperature=300.0)
+    case["zero_momentum_period"] = 7
+    return case, "nvt", 1.0
+
+
+def _run_ranks(world, body):
+    errors = []
+
+    def wrap(rank):
+        try:
+            body(rank)
+        except BaseException as ex:  # noqa: BLE001 - reported below, with the rank
+            import traceback
+            errors.append("rank %d: %s" % (rank, traceback.format_exc()))
+    threads = [threading.Thread(target=wrap, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not any(t.is_alive() for t in threads), "a rank did not finish (deadlock in the halo protocol?)"
+    assert not errors, "\n".join(errors)
+
+
+@pytest.mark.parametrize("which,world,p2p", [("rjl", 2, "1"), ("rjl", 3, "1"), ("rjl", 2, "0"), ("lj1g", 2, "1"), ("lj", 3, "1")])
+def test_slab_ranks_as_threads_match_the_single_context(monkeypatch, which, world, p2p):
+    monkeypatch.setenv("PFMDS_SLAB_P2P", p2p)
+    lib = BE.LOCKSTEP.lib
+    case, integ, dt = _case(which)
+    n = len(case["mass"])
+    ref = configure(case, lib_path=lib)
+    snaps = []
+    ref.advance(integ, dt, 0, 1)
+    snaps.append((ref.download(), ref.energies(), ref.diagnostics()))
+    ref.advance(integ, dt, 1, 12)                       # rebuilds (with migration) at 5 and 10
+    snaps.append((ref.download(), ref.energies(), ref.diagnostics()))
+    uid = make_unique_id(lib)
+    owned = [[None, None] for _ in range(world)]
+
+    def body(rank):
+        slab = configure_slab(case, rank, world, 0, uid, lib_path=lib)
+
+        def compare(k, tol_f, tol_x):
+            (P, V, F), er, dr = snaps[k]
+            gid, p, v, f = slab.download()
+            owned[rank][k] = gid.copy()
+            assert np.abs(p - P[gid - 1]).max() < tol_x and np.abs(v - V[gid - 1]).max() <= tol_x * np.abs(V).max() * 1e3 + 1e-18
+            assert np.abs(f - F[gid - 1]).max() < tol_f * np.abs(F).max()
+            es = slab.energies()
+            assert np.allclose(es[0], er[0], rtol=max(tol_f, 1e-12), atol=1e-9)
+            assert abs(es[1] - er[1]) <= max(tol_f, 1e-12) * abs(er[1]) + 1e-12 and abs(es[2] - er[2]) <= 1e-9 * er[2] + 1e-9
+            if case["nhc"]:
+                assert np.allclose(es[3], er[3], rtol=1e-7, atol=1e-9)
+            ds = slab.diagnostics()
+            assert np.allclose(ds[1], dr[1], rtol=1e-11) and abs(ds[3] - dr[3]) <= 1e-12 * dr[3] and np.array_equal(ds[4], dr[4])
+        slab.advance(integ, dt, 0, 1)
+        compare(0, 1e-11, 1e-12)
+        slab.advance(integ, dt, 1, 12)
+        compare(1, 1e-8, 1e-9)
+        slab.close()
+    _run_ranks(world, body)
+    for k in (0, 1):                                     # every atom has exactly one owner, before and after the migrations
+        assert sorted(np.concatenate([owned[r][k] for r in range(world)]).tolist()) == list(range(1, n + 1))
+    moved = sum(len(set(owned[r][0].tolist()) ^ set(owned[r][1].tolist())) for r in range(world))
+    if which == "rjl":
+        assert moved > 0, "the hot crystal should have sent atoms across a slab face"
