@@ -98,3 +98,69 @@ def test_slab_ranks_as_threads_match_the_single_context(monkeypatch, which, worl
     moved = sum(len(set(owned[r][0].tolist()) ^ set(owned[r][1].tolist())) for r in range(world))
     if which == "rjl":
         assert moved > 0, "the hot crystal should have sent atoms across a slab face"
+
+
+class _ThreadAllReduce:
+    """sum of a float64 vector over the rank threads (what torch.distributed does for bench.py)."""
+
+    def __init__(self, world):
+        self.world, self.parts, self.barrier = world, {}, threading.Barrier(world)
+
+    def __call__(self, rank, v):
+        self.parts[rank] = np.array(v, np.float64)
+        self.barrier.wait()
+        out = sum(self.parts[r] for r in range(self.world))
+        self.barrier.wait()
+        return out
+
+
+def test_per_rank_generated_crystal_and_the_bench_e2e_sequence(monkeypatch):
+    """bench.py --workload cu_fcc_1e8 in miniature: every rank generates only its own slab (cu_fcc_slab_inputs, velocity sums
+    all-reduced), hands it to pfmds_create_slab (SlabEngine local=...), and runs the e2e leg of the bench in slab mode (download,
+    upload, one energy read per step).  Against one context holding the whole crystal assembled from the ranks' own arrays."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+    from pfmds_b200.slab import cu_fcc_slab_inputs
+    world, lib = 3, BE.LOCKSTEP.lib
+    monkeypatch.setenv("PFMDS_SLAB_P2P", "1")
+    uid = make_unique_id(lib)
+    allsum = _ThreadAllReduce(world)
+    gather, out = {}, {}
+    ready = threading.Barrier(world)
+
+    def body(rank):
+        settings, loc = cu_fcc_slab_inputs(rank, world, (4, 4, 4), lambda v: allsum(rank, v), seed=9, steps=40, period=5)
+        gather[rank] = loc
+        ready.wait()
+        eng = configure_slab(settings, rank, world, 0, uid, lib_path=lib, capacity_factor=1.6, local=loc)
+        assert eng.n == 3 * 256 and eng.n_local0 == 256
+        eng.advance("nvt", 2.0, 0, 4)
+        gid0, p0, v0, _ = eng.download(forces=False)            # the e2e leg of bench.py, slab branch
+        eng.upload_local(p0, v0)
+        eng.advance("nvt", 2.0, 0, 1)
+        e_bytes, how = bench.e2e_steps(eng, "nvt", 2.0, 6, stepwise=True)
+        assert e_bytes > 0 and "pfmds_energies" in how
+        out[rank] = (eng.download(), eng.energies())
+        eng.close()
+    _run_ranks(world, body)
+    # the same crystal in one context
+    n = 3 * 256
+    pos, vel, mass = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(n)
+    for r in range(world):
+        g = gather[r]["gid"] - 1
+        pos[g], vel[g], mass[g] = gather[r]["pos"], gather[r]["vel"], gather[r]["mass"]
+    whole = inputs.cu_fcc(cells=(12, 4, 4), steps=40, period=5)
+    q1 = 3 * n * inputs.KB * 300.0 * 100.0 ** 2
+    whole.update(pos=pos, vel=vel, mass=mass, nhc=[(1, 300.0, 3, q1)])
+    ref = configure(whole, lib_path=lib)
+    ref.advance("nvt", 2.0, 0, 4)
+    P, V, _ = ref.download()
+    ref.upload(P, V)
+    ref.advance("nvt", 2.0, 0, 1)
+    for s in range(1, 7):
+        ref.advance("nvt", 2.0, s, 1, with_energy=True)
+    (P, V, F), er = ref.download(), ref.energies()
+    for r in range(world):
+        (gid, p, v, f), es = out[r]
+        assert np.abs(p - P[gid - 1]).max() < 1e-10 and np.abs(f - F[gid - 1]).max() < 1e-9 * np.abs(F).max()
+        assert np.allclose(es[0], er[0], rtol=1e-11) and abs(es[1] / er[1] - 1) < 1e-10 and np.allclose(es[3], er[3], rtol=1e-7, atol=1e-9)
