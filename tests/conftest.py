@@ -24,7 +24,7 @@ def _have_gpu():
 
 # tests/test_emulated_library.py in its lock-step flavour: the subset kept in the default CPU run (substrings of the test id)
 LOCKSTEP_KEEP = ["test_step0_lists_forces_energies", "test_parity_misc", "test_advance_logged_rows[lockstep-cu_fcc",
-                 "test_golden_fixtures_and_in_step_energies[lockstep-cu_fcc", "test_golden_fixtures_and_in_step_energies[lockstep-gr_cu_ljc]",
+                 "test_golden_fixtures_and_in_step_energies[lockstep-cu_fcc",
                  "test_trajectory_22_steps[lockstep-nvt-ab_gas", "test_anchors", "test_deposition_edge_cases_against_the_oracle[lockstep-changes0",
                  "test_replay_identifies_itself"]
 

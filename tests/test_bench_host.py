@@ -21,11 +21,11 @@ def test_time_variant_on_the_host_replay(oracle_lib, monkeypatch):
     B.build_emu()
     orig = E.configure
     monkeypatch.setattr(E, "configure", lambda case, device=0, **kw: orig(case, lib_path=B.LIB))
-    case = inputs.cu_fcc(ncell=5, jitter=0.05, period=5)
+    case = inputs.cu_fcc(ncell=4, jitter=0.05, period=5)
     monkeypatch.delenv("PFMDS_RJL_GEN", raising=False)
     for gen in ("1", "2"):
-        r = bench.time_variant(case, "nvt", 2.0, 0, {"PFMDS_RJL_GEN": gen}, 3, 5)
-        assert r["steps"] == 5 and set(r["kernels_ms_per_step"]) >= {"rjl_force", "rjl_density"}
+        r = bench.time_variant(case, "nvt", 2.0, 0, {"PFMDS_RJL_GEN": gen}, 2, 3)
+        assert r["steps"] == 3 and set(r["kernels_ms_per_step"]) >= {"rjl_force", "rjl_density"}
         assert "PFMDS_RJL_GEN" not in os.environ
 
 

@@ -25,15 +25,15 @@ def _lib(oracle_lib):
     return BE.LOCKSTEP.build()
 
 
-def _case(which):
+def _case(which, world=2):
     if which == "rjl":
-        case = inputs.cu_fcc(cells=(12, 4, 4), jitter=0.05, period=5, temperature=900.0)    # hot, and shifted so that an atomic plane
+        case = inputs.cu_fcc(cells=(max(12, 4 * world), 4, 4), jitter=0.05, period=5, temperature=900.0)    # hot, and shifted so that an atomic plane
         case["pos"] = case["pos"].copy()                                                    # lies on every slab face: atoms cross it
         case["pos"][:, 0] = (case["pos"][:, 0] - 0.25 * 3.615 + 0.02) % case["box"][0]
         return case, "nvt", 2.0
     if which == "lj1g":
         return inputs.lj_fluid(n_side=10, period=5, temperature=300.0), "nve", 1.0
-    case = inputs.ab_gas(n_side=10, period=5, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, temperature=300.0)
+    case = inputs.ab_gas(n_side=9, period=5, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, temperature=300.0)
     case["zero_momentum_period"] = 7
     return case, "nvt", 1.0
 
@@ -56,11 +56,16 @@ def _run_ranks(world, body):
     assert not errors, "\n".join(errors)
 
 
-@pytest.mark.parametrize("which,world,p2p", [("rjl", 2, "1"), ("rjl", 3, "1"), ("rjl", 2, "0"), ("lj1g", 2, "1"), ("lj", 3, "1")])
+CONFIGS = [("rjl", 2, "1"), ("rjl", 3, "1"), ("rjl", 2, "0"), ("lj", 3, "1")]
+if os.environ.get("PFMDS_SLAB_TESTS") == "all":      # the longer list: 8 ranks as in the scaling run, 4 ranks over the NCCL halo, lj1g
+    CONFIGS += [("lj1g", 2, "1"), ("rjl", 8, "1"), ("rjl", 4, "0")]
+
+
+@pytest.mark.parametrize("which,world,p2p", CONFIGS)
 def test_slab_ranks_as_threads_match_the_single_context(monkeypatch, which, world, p2p):
     monkeypatch.setenv("PFMDS_SLAB_P2P", p2p)
     lib = BE.LOCKSTEP.lib
-    case, integ, dt = _case(which)
+    case, integ, dt = _case(which, world)
     n = len(case["mass"])
     ref = configure(case, lib_path=lib)
     snaps = []
