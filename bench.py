@@ -243,8 +243,8 @@ def time_variant(case, integrator, dt, local, env, W, K):
 def e2e_steps(eng, integrator, dt, ke2e, stepwise=False):
     """Steps 1..ke2e of the e2e leg with the energies of EVERY step brought to the host (period_log = 1).  Default: what the
     run_md_simulation host does (md_driver.hpp) — one pfmds_advance_logged call, every step's energies produced by its force pass
-    and logged on the device, one D2H copy of the rows.  stepwise (slab mode, PFMDS_BENCH_STEPWISE_E2E=1, or if the logged call
-    fails): one pfmds_advance_with_energy(1) + pfmds_energies round trip per step.  Returns (D2H energy bytes per step, description)."""
+    and logged on the device, one D2H copy of the rows (in slab mode every rank gets the all-reduced rows).  stepwise
+    (PFMDS_BENCH_STEPWISE_E2E=1, or if the logged call fails): one pfmds_advance_with_energy(1) + pfmds_energies round trip per step.  Returns (D2H energy bytes per step, description)."""
     if not stepwise:
         try:
             rows = eng.advance_logged(integrator, dt, 1, ke2e, log_period=1)
@@ -413,7 +413,7 @@ def main():
         else:
             eng.upload_ptr(hp.data_ptr(), hv.data_ptr())
         eng.advance(integrator, dt, 0, 1)
-        e_bytes, how = e2e_steps(eng, integrator, dt, ke2e, stepwise=slab or bool(os.environ.get("PFMDS_BENCH_STEPWISE_E2E")))
+        e_bytes, how = e2e_steps(eng, integrator, dt, ke2e, stepwise=bool(os.environ.get("PFMDS_BENCH_STEPWISE_E2E")))
         out = eng.download() if slab else eng.download(out=ho)
         barrier()
         t_e2e = time.perf_counter() - t0

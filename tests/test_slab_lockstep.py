@@ -73,6 +73,7 @@ def test_slab_ranks_as_threads_match_the_single_context(monkeypatch, which, worl
     snaps.append((ref.download(), ref.energies(), ref.diagnostics()))
     ref.advance(integ, dt, 1, 12)                       # rebuilds (with migration) at 5 and 10
     snaps.append((ref.download(), ref.energies(), ref.diagnostics()))
+    rows_ref = ref.advance_logged(integ, dt, 13, 4, log_period=2)     # the device-resident energy log works across ranks too
     uid = make_unique_id(lib)
     owned = [[None, None] for _ in range(world)]
 
@@ -96,6 +97,10 @@ def test_slab_ranks_as_threads_match_the_single_context(monkeypatch, which, worl
         compare(0, 1e-11, 1e-12)
         slab.advance(integ, dt, 1, 12)
         compare(1, 1e-8, 1e-9)
+        rows = slab.advance_logged(integ, dt, 13, 4, log_period=2)
+        assert rows[0].shape[0] == 2
+        for k in range(4):
+            assert np.allclose(rows[k], rows_ref[k], rtol=1e-7, atol=1e-9)
         slab.close()
     _run_ranks(world, body)
     for k in (0, 1):                                     # every atom has exactly one owner, before and after the migrations
