@@ -1,0 +1,92 @@
+"""Seeded random systems against the oracle: non-cubic boxes with a different number of cells per axis (down to two), sparse and
+dense regions (empty cells, crowded cells), atoms exactly on the box faces, random cut-offs and switch radii — neighbour lists
+bit-exact, forces and energies to 1e-9, a few steps of trajectory.  Runs on the serial host replay (thread-per-atom kernels, the
+large-system path), on the lock-step replay (warp-per-atom list build, 8 lanes per atom: the small-system path) and on the GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from pfmds_b200 import inputs
+from pfmds_b200.engine import configure
+from util import gpu, neighbours, oracle, rel_err
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+
+def _serial(case):
+    import build_emu as B
+    B.SERIAL.build()
+    return configure(case, lib_path=B.SERIAL.lib)
+
+
+def _lockstep(case):
+    import build_emu as B
+    B.LOCKSTEP.build()
+    return configure(case, lib_path=B.LOCKSTEP.lib)
+
+
+ENGINES = [pytest.param(_serial, id="serial-replay"), pytest.param(_lockstep, id="lockstep-replay"), pytest.param(gpu, id="gpu", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(oracle_lib):
+    return None
+
+
+def random_case(seed, kind):
+    rng = np.random.default_rng(seed)
+    box = rng.uniform(13.5, 34.0, 3)
+    if seed % 3 == 0:
+        box[rng.integers(3)] = rng.uniform(13.2, 14.9)             # one axis only two cells wide
+    n_try = int(rng.integers(150, 420))
+    pos = rng.uniform(0, 1, (n_try, 3)) * box
+    if seed % 2 == 0:                                              # a crowded blob and a void
+        pos[: n_try // 3] = (box * rng.uniform(0.2, 0.8, 3) + rng.normal(0, 2.5, (n_try // 3, 3))) % box
+    pos[0] = [0.0, 0.0, 0.0]                                       # exactly on the faces (x = L is "out of cell" in the reference)
+    pos[1] = [0.0, box[1] * (1 - 2.0 ** -53), box[2] / 2]
+    pos[2] = [box[0] * (1 - 2.0 ** -53), box[1] / 2, box[2] / 3]
+    keep = []                                                      # no pair closer than 2.1 A (minimum image)
+    for i in range(n_try):
+        d = pos[keep] - pos[i]
+        d -= box * np.round(d / box)
+        if not keep or (d * d).sum(1).min() > 2.1 ** 2:
+            keep.append(i)
+    pos = pos[keep]
+    n = len(pos)
+    rcut = float(rng.uniform(5.0, min(6.6, 0.49 * box.min())))
+    R2 = float(rng.uniform(rcut - 1.2, rcut - 0.05))
+    R1 = R2 - 1.0 if kind == "lj1g" else float(rng.uniform(R2 - 1.0, R2 - 0.2))       # lj1g: the switch width the reference's derivative assumes
+    mass = np.full(n, 63.546)
+    vel = inputs.maxwell(rng, mass, 300.0)
+    if kind == "lj1g":
+        inter = dict(name="lj1g", file="p.txt", params=[0.0103, 3.405, R1, R2], lists=[(1, 1, 200, rcut, 3)])
+    else:
+        inter = dict(name="rjl", file="p.txt", params=list(inputs.RJL_CU[:5]) + [R1, R2], lists=[(1, 1, 200, rcut, 3)])
+    return dict(title="random", box=box, pos=pos, vel=vel, mass=mass, names=["A"] * n, groups=[["A"], ["#"]],
+                roles=dict(all_moving=1, xyz_moving=1, z_moving=2, all_atoms=1, traj_group=2, period_traj=10 ** 9),
+                integrators=[("nve", 0.5, 10, 10 ** 9, 10 ** 9)], ms_de=1e-8, nhc=[], zero_momentum_period=10 ** 9, invert_z_vel=False,
+                initial_temperature=300.0, interactions=[inter])
+
+
+@pytest.mark.parametrize("kind", ["lj1g", "rjl"])
+@pytest.mark.parametrize("make", ENGINES)
+def test_random_systems_match_the_oracle(make, kind):
+    for seed in range(1, 7):
+        case = random_case(seed, kind)
+        g, o = make(case), oracle(case)
+        for e in (g, o):
+            e.advance("nve", 0.5, 0, 1)
+        a, b = neighbours(g, case, 0, 0), neighbours(o, case, 0, 0)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]), (seed, "lists")
+        assert a[1].max() > 3, seed
+        fo = o.download()[2]
+        assert rel_err(g.download()[2], fo) < 1e-9, (seed, "forces")
+        assert abs(g.energies()[0][0] - o.energies()[0][0]) < 1e-9 * abs(o.energies()[0][0]) + 1e-12, (seed, "energy")
+        for e in (g, o):
+            e.advance("nve", 0.5, 1, 4)                              # a rebuild at step 3
+        assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-9, (seed, "trajectory")
+        g.close()
+        o.close()
