@@ -1,4 +1,4 @@
-"""Seeded random systems against the oracle: non-cubic boxes with a different number of cells per axis (down to two), sparse and
+"""(Named zz: on the GPU box it runs after the parity tests.)  Seeded random systems against the oracle: non-cubic boxes with a different number of cells per axis (down to two), sparse and
 dense regions (empty cells, crowded cells), atoms exactly on the box faces, random cut-offs and switch radii — neighbour lists
 bit-exact, forces and energies to 1e-9, a few steps of trajectory.  Runs on the serial host replay (thread-per-atom kernels, the
 large-system path), on the lock-step replay (warp-per-atom list build, 8 lanes per atom: the small-system path) and on the GPU."""
