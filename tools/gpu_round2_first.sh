@@ -22,3 +22,6 @@ PY
 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_rebosc_gpu.py tests/test_deposition_gpu.py -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r2_memcheck.log
 # 4. (separate call, 8 GPUs)  BASELINE.json configs[3] at its stated size, 1.0165e8 atoms:
 #   gpurun --gpus 8 --timeout 900 -- 'BENCH_ARGS="--workload cu_fcc_1e8 --steps 100" bash tools/gpu_scale.sh 8'
+# 5. (second call) launch list + full capture of the second-generation rjl kernels, to replace profiles/r1e_* :
+#   gpurun --timeout 900 -- 'ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 160 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 25 --warmup 21 --no-cpu-baseline --no-e2e --no-variants > gpurun_out/ncu_list.log 2>&1; bash tools/gpu_ncu.sh "k_rjl" r2_rjl_gen2'
+#   then here:  python profiles/ncu_raw.py gpurun_out/r2_rjl_gen2.ncu-rep  /  python profiles/sass_mix.py ...   (see profiles/README.md)
