@@ -47,13 +47,13 @@ def _run_ranks(world, body):
         except BaseException as ex:  # noqa: BLE001 - reported below, with the rank
             import traceback
             errors.append("rank %d: %s" % (rank, traceback.format_exc()))
-    threads = [threading.Thread(target=wrap, args=(r,)) for r in range(world)]
+    threads = [threading.Thread(target=wrap, args=(r,), daemon=True) for r in range(world)]   # daemon: a rank stuck in a collective after another one failed must not keep the process alive
     for t in threads:
         t.start()
     for t in threads:
-        t.join(timeout=600)
-    assert not any(t.is_alive() for t in threads), "a rank did not finish (deadlock in the halo protocol?)"
+        t.join(timeout=300)
     assert not errors, "\n".join(errors)
+    assert not any(t.is_alive() for t in threads), "a rank did not finish (deadlock in the halo protocol?)"
 
 
 CONFIGS = [("rjl", 2, "1"), ("rjl", 3, "1"), ("rjl", 2, "0"), ("lj", 3, "1")]
