@@ -271,6 +271,8 @@ def run_variants(local):
     ljc = inputs.lj_fluid(n_side=96, seed=2, steps=200)
     for name, cs, integ, h, env in (
             ("rjl_gen2 (default)", case, integrator, dt, {"PFMDS_RJL_GEN": "2"}),
+            ("rjl_gen2, force kernel held to 5 blocks/SM instead of 7 (PFMDS_RJL_MINB=5: 94 registers, no constant reloads in the loop)", case, integrator, dt,
+             {"PFMDS_RJL_GEN": "2", "PFMDS_RJL_MINB": "5"}),
             ("rjl_gen1 (PFMDS_RJL_GEN=1, the round-1 kernels)", case, integrator, dt, {"PFMDS_RJL_GEN": "1"}),
             ("lj_fluid 96^3 lj1g (default)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "0"}),
             ("lj_fluid 96^3 lj1g pipelined (PFMDS_LJ1G_PIPE=1)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "1"})):

@@ -645,6 +645,8 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         c->lj1g_pipe = lp && lp[0] == '1';
         const char* rg = std::getenv("PFMDS_RJL_GEN");
         c->rjl_gen = (rg && rg[0] == '1') ? 1 : 2;
+        const char* mb = std::getenv("PFMDS_RJL_MINB");
+        c->rjl_minb = (mb && mb[0] == '5') ? 5 : 7;
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     });
 }
@@ -1394,6 +1396,8 @@ int pfmds_create_slab(pfmds_ctx** out, int device, int rank, int nranks, const c
         c->timers_on = tm && tm[0] == '1';
         const char* rg = std::getenv("PFMDS_RJL_GEN");
         c->rjl_gen = (rg && rg[0] == '1') ? 1 : 2;
+        const char* mb = std::getenv("PFMDS_RJL_MINB");
+        c->rjl_minb = (mb && mb[0] == '5') ? 5 : 7;
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
         slab_init(c, rank, nranks, id, n_global, n_local, capacity);
     });

@@ -437,9 +437,13 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
         fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
     }
 }
-template <class CT>  // CT = RjlC (first generation) or RjlF (second generation)
-__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
-                                                            WrapC W, SlabDev S, int overwrite) {
+// MB = blocks per SM the register allocation is held to.  7 (72 registers) is the measured optimum of the first generation; at
+// 5 (94 registers) the second generation's loop keeps its loop-invariant constants in registers and drops the 31 LDC per trip
+// it otherwise re-issues (255 instead of 286 instructions per trip, profiles/r1g_static_loop_mix.txt) at 20 instead of 28
+// resident warps: PFMDS_RJL_MINB=5 selects it, unmeasured so far.
+template <class CT, int MB = RJL_MINB>  // CT = RjlC (first generation) or RjlF (second generation)
+__global__ void __launch_bounds__(FT, MB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
+                                                      WrapC W, SlabDev S, int overwrite) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);  // slab mode: the neighbours' 1/Eb have landed in my ghost slots
     if (i >= N) return;
@@ -942,7 +946,12 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
             if (!e_in_force) {
                 KTimer kt(c, KS_RJL_FORCE);
                 if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W);
-                else LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
+                else {
+                    bool launched = false;
+                    if constexpr (TF::padded)   // second generation only
+                        if (c->rjl_minb == 5) { LAUNCH((k_rjl_force<TF, 5>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow); launched = true; }
+                    if (!launched) LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
+                }
             }
         };
         if (e_in_force) {

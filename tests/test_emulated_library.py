@@ -165,6 +165,17 @@ def test_pipelined_lj1g_variant(monkeypatch, flavour):
     assert np.abs(b.download()[0] - o.download()[0]).max() < 1e-10
 
 
+def test_rjl_minb_switch(monkeypatch):
+    """PFMDS_RJL_MINB=5 selects another instantiation of the same force kernel: same bits (replayed from the GPU test with a small crystal)."""
+    case = inputs.cu_fcc(ncell=5, jitter=0.05, period=5)
+    a = emu_gpu(case)
+    monkeypatch.setenv("PFMDS_RJL_MINB", "5")
+    b = emu_gpu(case)
+    for e in (a, b):
+        e.advance("nvt", 2.0, 0, 7)
+    assert np.array_equal(a.download()[2], b.download()[2]) and np.abs(a.download()[2]).max() > 0.05
+
+
 def test_replay_identifies_itself():
     import ctypes as C
     lib = C.CDLL(B.lib)

@@ -28,3 +28,19 @@ def test_pipelined_lj1g_kernel_matches_the_default_kernel():
         e.advance("nve", 0.5, 1, 12)
     assert np.abs(a.download()[0] - b.download()[0]).max() < 1e-10
     assert np.allclose(a.energies()[0], b.energies()[0], rtol=1e-11, atol=0)     # energy_interaction keeps the default kernel
+
+
+def test_rjl_force_kernel_at_five_blocks_per_sm_gives_the_same_bits():
+    """PFMDS_RJL_MINB=5: the second-generation force kernel compiled for 5 instead of 7 blocks per SM (more registers, no constant
+    reloads in the pair loop).  Same source, same operations in the same order: identical forces and trajectory, bit for bit."""
+    case = inputs.cu_fcc(ncell=30, jitter=0.03, period=5)              # 108 000 atoms: the thread-per-atom kernels
+    a = gpu(case)
+    os.environ["PFMDS_RJL_MINB"] = "5"
+    try:
+        b = gpu(case)
+    finally:
+        del os.environ["PFMDS_RJL_MINB"]
+    for e in (a, b):
+        e.advance("nvt", 2.0, 0, 12)
+    (pa, va, fa), (pb, vb, fb) = a.download(), b.download()
+    assert np.abs(fa).max() > 0.05 and np.array_equal(fa, fb) and np.array_equal(pa, pb) and np.array_equal(va, vb)
