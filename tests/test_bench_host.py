@@ -96,3 +96,19 @@ def test_bench_main_dry_run_on_the_host_replay(oracle_lib, monkeypatch, capsys):
     assert line["steps"] == 8 and line["gpu_launches"] > 0 and line["config"]["workload"].startswith("dry run")
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and "pfmds_advance_logged" in line["e2e"]["what"]
     assert line["cpu_baseline"]["kind"] == "port"
+
+
+def test_smoke_dry_run_on_the_lockstep_replay(oracle_lib, monkeypatch, capsys):
+    """__graft_entry__.smoke() as the driver calls it, with the engine factory pointed at the lock-step host replay (the small-system
+    kernels the GPU would launch): the graphene-on-Cu case, its oracle comparison and its assertions run unchanged."""
+    import build_emu as B
+    import pfmds_b200.engine as E
+    import __graft_entry__ as G
+    B.LOCKSTEP.build()
+    orig = E.configure
+
+    def configure(case, device=0, lib_path=None, prefix="pfmds_"):
+        return orig(case, lib_path=lib_path or B.LOCKSTEP.lib, prefix=prefix)
+    monkeypatch.setattr(E, "configure", configure)
+    G.smoke()
+    assert "smoke ok" in capsys.readouterr().out
