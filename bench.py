@@ -402,7 +402,7 @@ def main():
     e2e = None
 
     def e2e_leg():
-        ke2e = min(K, 100)
+        ke2e = K   # the same K steps as the device-timed region, now from host buffers to host buffers
         if slab:
             gid0, p0, v0, _ = eng.download(forces=False)
             n_here = len(gid0)
