@@ -242,7 +242,8 @@ def time_variant(case, integrator, dt, local, env, W, K):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    return {"ms_per_step": ms / K, "steps": K, "kernels_ms_per_step": {k: round(v[0] / K, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])[:4]}}
+    return {"ms_per_step": ms / K, "steps": K, "atom_steps_per_s": len(case["mass"]) * K / (ms * 1e-3),
+            "kernels_ms_per_step": {k: round(v[0] / K, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])[:4]}}
 
 
 def e2e_steps(eng, integrator, dt, ke2e, stepwise=False):
@@ -265,15 +266,21 @@ def e2e_steps(eng, integrator, dt, ke2e, stepwise=False):
     return e_bytes, "%d x [pfmds_advance_with_energy(1) + pfmds_energies (D2H)]" % ke2e
 
 
-def run_variants(local):
-    """--variants-only (child of the default run): ms/step of the rjl and lj1g kernel variants on this GPU, one JSON line."""
+def run_variants(local, small=False):
+    """--variants-only (child of the default run): ms/step of the rjl and lj1g kernel variants on this GPU, one cumulative JSON line
+    per finished experiment.  small: miniature systems and a few steps (the CPU suite runs this function on the host replay)."""
     from pfmds_b200 import inputs
-    from pfmds_b200.build import build
-    build()
-    out = {"note": "child process, fresh contexts after the headline measurement, 21 warm-up + 100 timed steps each; `value` is the default configuration"}
-    case, integrator, _ = build_case("cu_fcc", seed=2, steps=200)
+    W, K = (2, 3) if small else (21, 100)
+    out = {"note": "child process, fresh contexts after the headline measurement, %d warm-up + %d timed steps each; `value` is the default configuration" % (W, K)}
+    if small:
+        case, integrator = inputs.cu_fcc(ncell=4, jitter=0.05, period=5), "nvt"
+        ljc = inputs.lj_fluid(n_side=8, seed=2, steps=20, period=5)
+    else:
+        from pfmds_b200.build import build
+        build()
+        case, integrator, _ = build_case("cu_fcc", seed=2, steps=200)
+        ljc = inputs.lj_fluid(n_side=96, seed=2, steps=200)
     dt = case["integrators"][0][1]
-    ljc = inputs.lj_fluid(n_side=96, seed=2, steps=200)
     for name, cs, integ, h, env in (
             ("rjl_gen2 (default)", case, integrator, dt, {"PFMDS_RJL_GEN": "2"}),
             ("rjl_gen2, force kernel held to 5 blocks/SM instead of 7 (PFMDS_RJL_MINB=5: 94 registers, no constant reloads in the loop)", case, integrator, dt,
@@ -282,10 +289,26 @@ def run_variants(local):
             ("lj_fluid 96^3 lj1g (default)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "0"}),
             ("lj_fluid 96^3 lj1g pipelined (PFMDS_LJ1G_PIPE=1)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "1"})):
         try:
-            out[name] = time_variant(cs, integ, h, local, env, 21, 100)
+            out[name] = time_variant(cs, integ, h, local, env, W, K)
         except Exception as ex:
             out[name] = {"error": repr(ex)[:300]}
-    print(json.dumps(out))
+        print(json.dumps(out), flush=True)   # cumulative: the parent keeps the last complete line, also when it has to stop this process
+    # the other device rows of SURVEY 8(f) and the small-system configurations, default kernels (per-kernel events on: small systems
+    # run without their CUDA graphs here, so these are upper bounds of their ms/step; `bench.py --workload X` is the clean line)
+    for wl, k in (("graphene_rebosc", 50), ("lj_deposition", 200), ("ab_gas", 200), ("graphene_cu", 200)):
+        try:
+            if small:
+                k = K
+                cs, integ, desc = {"graphene_rebosc": lambda: (inputs.graphene_rebosc(), "nve", "miniature"),
+                                   "lj_deposition": lambda: (inputs.lj_deposition(), "nvt", "miniature"),
+                                   "ab_gas": lambda: (inputs.ab_gas(n_side=8, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, period=5), "nvt", "miniature"),
+                                   "graphene_cu": lambda: (inputs.graphene_on_cu_small(interface="ljc", period=5), "nvt", "miniature")}[wl]()
+            else:
+                cs, integ, desc = build_case(wl, seed=2, steps=21 + k)
+            out["workload " + wl + ": " + desc] = time_variant(cs, integ, cs["integrators"][0][1], local, {}, W, k)
+        except Exception as ex:
+            out["workload " + wl] = {"error": repr(ex)[:300]}
+        print(json.dumps(out), flush=True)
     return 0
 
 
@@ -501,12 +524,26 @@ def main():
     # abort) or hangs cannot take the headline line with it.
     variants = None
     if not args.no_variants and world == 1 and args.workload == "cu_fcc":
+        def last_row(text):
+            if isinstance(text, bytes):
+                text = text.decode("utf-8", "replace")
+            for l in reversed((text or "").splitlines()):
+                if l.startswith("{") and l.rstrip().endswith("}"):
+                    try:
+                        return json.loads(l)
+                    except Exception:
+                        continue
+            return None
         try:
             eng.close()
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--variants-only", "--device", str(local)], stdout=subprocess.PIPE,
                                stderr=subprocess.PIPE, text=True, timeout=240)
-            rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
-            variants = json.loads(rows[-1]) if rows else {"error": "child exit %d: %s" % (r.returncode, r.stderr[-300:])}
+            variants = last_row(r.stdout) or {"error": "child exit %d: %s" % (r.returncode, r.stderr[-300:])}
+            if r.returncode != 0:
+                variants["child_exit"] = r.returncode
+        except subprocess.TimeoutExpired as ex:   # keep what the child had finished
+            variants = last_row(ex.stdout) or {}
+            variants["error"] = "child stopped after 240 s"
         except Exception as ex:  # the headline line must survive a failing experiment
             variants = {"error": repr(ex)[:300]}
     line = {

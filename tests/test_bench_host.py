@@ -29,6 +29,24 @@ def test_time_variant_on_the_host_replay(oracle_lib, monkeypatch):
         assert "PFMDS_RJL_GEN" not in os.environ
 
 
+def test_variants_child_on_the_host_replay(oracle_lib, monkeypatch, capsys):
+    """bench.run_variants (the child process of the default bench run) in miniature: every experiment and every extra workload
+    yields a timing, one cumulative JSON line per finished experiment."""
+    import build_emu as B
+    import pfmds_b200.engine as E
+    import bench
+    B.build_emu()
+    orig = E.configure
+    monkeypatch.setattr(E, "configure", lambda case, device=0, **kw: orig(case, lib_path=B.LIB))
+    assert bench.run_variants(0, small=True) == 0
+    rows = [json.loads(l) for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(rows) == 9 and all(len(b) == len(a) + 1 for a, b in zip(rows, rows[1:]))
+    last = rows[-1]
+    bad = {k: v for k, v in last.items() if k != "note" and "error" in v}
+    assert not bad, bad
+    assert sum(k.startswith("workload ") for k in last) == 4 and all(v["atom_steps_per_s"] > 0 for k, v in last.items() if k != "note")
+
+
 def test_e2e_steps_logged_and_stepwise_agree(oracle_lib):
     """The e2e leg's two ways of reading every step's energies (one pfmds_advance_logged call / one round trip per step) leave the
     same state and count their D2H bytes."""
