@@ -281,6 +281,18 @@ def run_variants(local, small=False):
         case, integrator, _ = build_case("cu_fcc", seed=2, steps=200)
         ljc = inputs.lj_fluid(n_side=96, seed=2, steps=200)
     dt = case["integrators"][0][1]
+    if not small:   # elementary functions of mathx.cuh on this device (the bounds tests/test_parity_gpu.py asserts): [exp, switch, rsqrt, seed] / short forms
+        try:
+            import ctypes as C
+            from pfmds_b200.engine import load_library
+            lib, err = load_library(), (C.c_double * 4)()
+            for fn in ("pfmds_selftest_math", "pfmds_selftest_math2"):
+                f = getattr(lib, fn)
+                f.argtypes, f.restype = [C.c_int, C.POINTER(C.c_double)], C.c_int
+                rc = f(local, err)
+                out[fn] = {"rc": rc, "err": [float(x) for x in err]}
+        except Exception as ex:
+            out["device_math"] = {"error": repr(ex)[:300]}
     for name, cs, integ, h, env in (
             ("rjl_gen2 (default)", case, integrator, dt, {"PFMDS_RJL_GEN": "2"}),
             ("rjl_gen2, force kernel held to 5 blocks/SM instead of 7 (PFMDS_RJL_MINB=5: 94 registers, no constant reloads in the loop)", case, integrator, dt,
@@ -443,18 +455,24 @@ def main():
             eng.upload_local(hp.numpy(), hv.numpy())
         else:
             eng.upload_ptr(hp.data_ptr(), hv.data_ptr())
+        eng.synchronize()
+        t1 = time.perf_counter()
         eng.advance(integrator, dt, 0, 1)
+        eng.synchronize()
+        t2 = time.perf_counter()
         e_bytes, how = e2e_steps(eng, integrator, dt, ke2e, stepwise=bool(os.environ.get("PFMDS_BENCH_STEPWISE_E2E")))
+        t3 = time.perf_counter()
         out = eng.download() if slab else eng.download(out=ho)
         barrier()
         t_e2e = time.perf_counter() - t0
+        phases = {"upload": (t1 - t0) * 1e3, "step0_lists_forces": (t2 - t1) * 1e3, "steps_with_energies": (t3 - t2) * 1e3, "download": (t0 + t_e2e - t3) * 1e3}
         te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         del out
         return {"value": n_total * ke2e / float(te.item()), "unit": "atom-steps/s", "h2d_bytes_per_step": int(2 * 24 * n_atoms / ke2e),
                 "d2h_bytes_per_step": int(e_bytes + ((3 * 32 + 4) if slab else 3 * 24) * n_atoms / ke2e), "steps": ke2e,
-                "what": "pfmds_upload(H2D pinned) + " + how + " + pfmds_download(D2H)"}
+                "what": "pfmds_upload(H2D pinned) + " + how + " + pfmds_download(D2H)", "phases_ms": {k: round(v, 3) for k, v in phases.items()}}
 
     if not args.no_e2e:
         if dist is not None:
