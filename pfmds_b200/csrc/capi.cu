@@ -512,6 +512,8 @@ __global__ void k_math_selftest(int n, double* out) {
     atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(e_rs));
     atomicMax((unsigned long long*)&out[3], (unsigned long long)__double_as_longlong(e_seed));
 }
+// running maximum that a NaN cannot hide behind (fmax returns its other argument)
+__device__ __forceinline__ double worst(double e, double v) { return v == v ? fmax(e, v) : 1.0; }
 // the short forms of the second-generation rjl kernels (exp_m / exp_m2, rsqrt_q, cos_switch_m, half_switch)
 __global__ void k_math_selftest2(int n, double* out) {
     double e_exp = 0, e_sw = 0, e_rs = 0, e_wide = 0;
@@ -519,19 +521,19 @@ __global__ void k_math_selftest2(int n, double* out) {
         double u = (i + 0.5) / n;
         double x = -40. + 80. * u, xb = 3. - 19. * u;
         double a = exp(x), b = mx::exp_m(x), ea, eb;
-        e_exp = fmax(e_exp, fabs(a - b) / a);
+        e_exp = worst(e_exp, fabs(a - b) / a);
         mx::exp_m2(x, xb, ea, eb, 1.4426950408889634, -6.93147180559945309417e-01);
-        e_exp = fmax(e_exp, fmax(fabs(a - ea) / a, fabs(exp(xb) - eb) / exp(xb)));
+        e_exp = worst(worst(e_exp, fabs(a - ea) / a), fabs(exp(xb) - eb) / exp(xb));
         x = -600. + 1200. * u;
         a = exp(x);
-        e_wide = fmax(e_wide, fabs(a - mx::exp_m(x)) / a);
+        e_wide = worst(e_wide, fabs(a - mx::exp_m(x)) / a);
         double ang = 3.14159265358979 * u, f, s, sr, cr;
         mx::cos_switch_m(fma(ang, 0.5, -0.78539816339744830962), f, s);
         sincos(ang, &sr, &cr);
-        e_sw = fmax(e_sw, fmax(fabs(f - (1. + cr) / 2), fabs(s - sr)));
-        e_sw = fmax(e_sw, fabs(mx::half_switch(ang - 1.57079632679489661923) - (1. + cr) / 2));
+        e_sw = worst(worst(e_sw, fabs(f - (1. + cr) / 2)), fabs(s - sr));
+        e_sw = worst(e_sw, fabs(mx::half_switch(ang - 1.57079632679489661923) - (1. + cr) / 2));
         double v = exp(-20. + 40. * u);
-        e_rs = fmax(e_rs, fabs(mx::rsqrt_q(v) * sqrt(v) - 1.));
+        e_rs = worst(e_rs, fabs(mx::rsqrt_q(v) * sqrt(v) - 1.));
     }
     atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(e_exp));
     atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(e_sw));
