@@ -10,7 +10,7 @@ import pytest
 
 from pfmds_b200 import inputs
 from pfmds_b200.engine import configure
-from util import gpu, neighbours, oracle, rel_err
+from util import gpu, list_ids, neighbours, oracle, rel_err
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "emu"))
@@ -87,6 +87,79 @@ def test_random_systems_match_the_oracle(make, kind):
         assert abs(g.energies()[0][0] - o.energies()[0][0]) < 1e-9 * abs(o.energies()[0][0]) + 1e-12, (seed, "energy")
         for e in (g, o):
             e.advance("nve", 0.5, 1, 4)                              # a rebuild at step 3
+        assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-9, (seed, "trajectory")
+        g.close()
+        o.close()
+
+
+def random_graphene_case(seed, interface):
+    """Rippled, jittered graphene on Cu(111) (tb + ljc|morsec + rjl) with random interface parameters and switch radii; a
+    seed in three uses the `simplified` normals (n = z)."""
+    rng = np.random.default_rng(100 + seed)
+    case = inputs.graphene_on_cu_small(interface=interface, seed=seed, jitter=float(rng.uniform(0.02, 0.06)), period=3, simplified=(seed % 3 == 0))
+    box, pos = case["box"], case["pos"]
+    nc = case["names"].count("C")
+    amp, ph = rng.uniform(0.1, 0.4), rng.uniform(0, 2 * np.pi, 2)
+    pos[:nc, 2] += amp * np.sin(2 * np.pi * pos[:nc, 0] / box[0] + ph[0]) * np.cos(2 * np.pi * pos[:nc, 1] / box[1] + ph[1])
+    R2 = float(rng.uniform(5.6, 7.2))
+    R1 = R2 - float(rng.uniform(0.5, 1.2))
+    it = case["interactions"][1]
+    simp = it["params"][-1]
+    if interface == "ljc":
+        it["params"] = [float(rng.uniform(0.01, 0.04)), float(rng.uniform(2.6, 3.3)), float(rng.uniform(1.0, 3.0)), R1, R2, simp]
+    else:
+        it["params"] = [float(rng.uniform(0.01, 0.05)), float(rng.uniform(2.8, 3.5)), float(rng.uniform(0.8, 1.6)), float(rng.uniform(1.0, 3.0)), R1, R2, simp]
+    return case
+
+
+@pytest.mark.parametrize("interface", ["ljc", "morsec"])
+@pytest.mark.parametrize("make", ENGINES)
+def test_random_graphene_on_cu_matches_the_oracle(make, interface):
+    for seed in range(1, 3 if make is _lockstep else 4):
+        case = random_graphene_case(seed, interface)
+        g, o = make(case), oracle(case)
+        for e in (g, o):
+            e.advance("nvt", 1.0, 0, 1)
+        for k, j in list_ids(case):
+            a, b = neighbours(g, case, k, j), neighbours(o, case, k, j)
+            assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]), (seed, "list", k, j)
+        assert rel_err(g.normals(1), o.normals(1)) < 1e-12, (seed, "normals")
+        assert rel_err(g.download()[2], o.download()[2]) < 1e-9, (seed, "forces")
+        eg, eo = g.energies(), o.energies()
+        assert np.allclose(eg[0], eo[0], rtol=1e-9, atol=1e-12), (seed, "energies", eg[0], eo[0])
+        for e in (g, o):
+            e.advance("nvt", 1.0, 1, 4)                              # a rebuild at step 3
+        assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-9, (seed, "trajectory")
+        assert np.allclose(g.get_nhc(0)[1], o.get_nhc(0)[1], rtol=1e-8, atol=1e-15), (seed, "thermostat")
+        g.close()
+        o.close()
+
+
+def random_ab_gas_case(seed):
+    """Two-species lj gas (list + converse list) plus lj1g within each species: random composition, box and cut-offs."""
+    rng = np.random.default_rng(200 + seed)
+    n_side = int(rng.integers(6, 9))
+    case = inputs.ab_gas(n_side=n_side, spacing=float(rng.uniform(3.5, 4.3)), seed=seed, frac_b=float(rng.uniform(0.1, 0.4)), cap_aa=120, cap_ab=120, cap_ba=120, cap_bb=120, period=3)
+    return case
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_random_ab_gas_matches_the_oracle(make):
+    for seed in range(1, 3 if make is _lockstep else 4):
+        case = random_ab_gas_case(seed)
+        integ, dt = case["integrators"][0][0], case["integrators"][0][1]
+        g, o = make(case), oracle(case)
+        for e in (g, o):
+            e.advance(integ, dt, 0, 1)
+        for k, j in list_ids(case):
+            a, b = neighbours(g, case, k, j), neighbours(o, case, k, j)
+            assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]), (seed, "list", k, j)
+            if not (j == 1 and case["interactions"][k]["name"] == "lj"):   # the converse list has no lessnnum (md_neighbours.f90:128-160)
+                assert np.array_equal(a[2], b[2]), (seed, "lessnnum", k, j)
+        assert rel_err(g.download()[2], o.download()[2]) < 1e-9, (seed, "forces")
+        assert np.allclose(g.energies()[0], o.energies()[0], rtol=1e-9, atol=1e-12), (seed, "energies")
+        for e in (g, o):
+            e.advance(integ, dt, 1, 4)
         assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-9, (seed, "trajectory")
         g.close()
         o.close()
