@@ -163,3 +163,29 @@ def test_random_ab_gas_matches_the_oracle(make):
         assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-9, (seed, "trajectory")
         g.close()
         o.close()
+
+
+@pytest.mark.parametrize("n_b", [0, 1])
+@pytest.mark.parametrize("make", ENGINES)
+def test_empty_and_single_atom_groups(make, n_b):
+    """Edge of the two-group interactions: species B absent (the lj list, its converse and the B-B lj1g list have no rows) or
+    present with one atom (a one-row converse list, an lj1g list whose only row is empty)."""
+    n = 6 ** 3
+    case = inputs.ab_gas(n_side=6, frac_b=(n_b + 0.25) / n, cap_aa=120, cap_ab=120, cap_ba=240, cap_bb=8, period=3)
+    assert case["names"].count("B") == n_b
+    g, o = make(case), oracle(case)
+    for e in (g, o):
+        e.advance("nvt", 0.5, 0, 1)
+    for k, j in list_ids(case):
+        a, b = neighbours(g, case, k, j), neighbours(o, case, k, j)
+        assert a[0].shape[0] == (n_b if (k, j) in ((0, 1), (2, 0)) else n - n_b)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]), ("list", k, j)
+    assert rel_err(g.download()[2], o.download()[2]) < 1e-9
+    eg, eo = g.energies(), o.energies()
+    assert np.allclose(eg[0], eo[0], rtol=1e-9, atol=1e-12) and eg[0][2] == 0.0 and (n_b or eg[0][0] == 0.0)
+    for e in (g, o):
+        e.advance("nvt", 0.5, 1, 7)                                  # rebuilds at steps 3 and 6
+    assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-9
+    assert abs(g.energies()[2] - o.energies()[2]) < 1e-7            # temperature
+    g.close()
+    o.close()
