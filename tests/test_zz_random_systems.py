@@ -189,3 +189,43 @@ def test_empty_and_single_atom_groups(make, n_b):
     assert abs(g.energies()[2] - o.energies()[2]) < 1e-7            # temperature
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_list_capacity_exactly_reached(make):
+    """neighb_num_max equal to the fullest row is enough, one less stops with the reference's message (md_neighbours.f90:82,
+    :148 for the converse list) — on the oracle and on the device alike.  Perfect fcc within 6.5 A: 86 neighbours everywhere."""
+    from pfmds_b200.engine import PfmdsError
+    for cap, ok in ((86, True), (85, False)):
+        case = inputs.cu_fcc(ncell=4, period=5)
+        case["interactions"][0]["lists"] = [(1, 1, cap, 6.5, 5)]
+        for which, e in enumerate((make(case), oracle(case))):
+            if ok:
+                e.advance("nve", 1.0, 0, 1)
+                e.synchronize()
+                assert e.diagnostics()[4][0] == 86
+            else:
+                with pytest.raises(PfmdsError) as ei:
+                    e.advance("nve", 1.0, 0, 1)
+                    e.synchronize()
+                assert "too many neighbours" in str(ei.value) and (which == 1 or ei.value.code == 11)   # the oracle has one code for every stop
+            e.close()
+    # the converse list of lj has its own capacity (settings line 2)
+    n = 6 ** 3
+    base = inputs.ab_gas(n_side=6, frac_b=0.2, cap_aa=120, cap_ab=120, cap_ba=240, cap_bb=120, period=3)
+    o = oracle(base)
+    o.advance("nvt", 0.5, 0, 1)
+    full = int(neighbours(o, base, 0, 1)[1].max())
+    for cap, ok in ((full, True), (full - 1, False)):
+        case = inputs.ab_gas(n_side=6, frac_b=0.2, cap_aa=120, cap_ab=120, cap_ba=cap, cap_bb=120, period=3)
+        for which, e in enumerate((make(case), oracle(case))):
+            if ok:
+                e.advance("nvt", 0.5, 0, 1)
+                e.synchronize()
+                assert int(neighbours(e, case, 0, 1)[1].max()) == full
+            else:
+                with pytest.raises(PfmdsError) as ei:
+                    e.advance("nvt", 0.5, 0, 1)
+                    e.synchronize()
+                assert "too many neighbours" in str(ei.value) and (which == 1 or ei.value.code == 11)   # the oracle has one code for every stop
+            e.close()
