@@ -229,3 +229,39 @@ def test_list_capacity_exactly_reached(make):
                     e.synchronize()
                 assert "too many neighbours" in str(ei.value) and (which == 1 or ei.value.code == 11)   # the oracle has one code for every stop
             e.close()
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_z_only_movers_and_fixed_atoms(make):
+    """The z_moving group (integrate_verlet_z_velocities / _z_positions, md_integrators.f90:34-56,79-97; its nvms quench
+    molecular_static_1D_velocities, :125-145) next to xyz movers and fixed atoms, through nvt, nve and nvms steps."""
+    case = inputs.cu_fcc(ncell=4, jitter=0.06, period=3)
+    n = len(case["mass"])
+    rng = np.random.default_rng(5)
+    kind = rng.permutation(n) % 4                                     # 0,1: xyz movers, 2: z movers, 3: fixed
+    order = np.argsort(kind, kind="stable")                           # file order by type keeps the multi-type groups index-monotone
+    for key in ("pos", "vel"):
+        case[key] = case[key][order]
+    kind = kind[order]
+    case["names"] = [("CU", "CU", "CUZ", "CUF")[k] for k in kind]
+    case["vel"][kind == 3] = 0.0
+    case["groups"] = [["CU", "CUZ", "CUF"], ["CU", "CUZ", "#"], ["CU", "#", "#"], ["CUZ", "#", "#"]]
+    case["roles"] = dict(all_moving=2, xyz_moving=3, z_moving=4, all_atoms=1, traj_group=4, period_traj=10 ** 9)
+    case["nhc"] = [(2, 300.0, 3, case["nhc"][0][3])]
+    p0 = case["pos"].copy()
+    g, o = make(case), oracle(case)
+    step = 0
+    for integ, k in (("nvt", 7), ("nve", 4), ("nvms", 5)):
+        for e in (g, o):
+            e.advance(integ, 2.0, step, k)
+        step += k
+        (pg, vg, fg), (po, vo, fo) = g.download(), o.download()
+        assert np.abs(pg - po).max() < 1e-9 and rel_err(vg, vo) < 1e-8 and rel_err(fg, fo) < 1e-9, integ
+        assert np.array_equal(pg[kind == 3], p0[kind == 3]) and np.array_equal(pg[kind == 2][:, :2], p0[kind == 2][:, :2])
+        assert np.abs(pg[kind == 2][:, 2] - p0[kind == 2][:, 2]).max() > 1e-4
+        eg, eo = g.energies(), o.energies()
+        assert np.allclose(eg[0], eo[0], rtol=1e-9) and abs(eg[1] - eo[1]) < 1e-8 * abs(eo[1]) + 1e-12
+    vz = g.download()[1][kind == 2]
+    assert np.all(vz[:, :2] == vz[:, :2]) and (np.abs(vz[:, 2]) == 0).any() and (np.abs(vz[:, 2]) > 0).any()   # the 1D quench zeroed some, kept others
+    g.close()
+    o.close()
