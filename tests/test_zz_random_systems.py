@@ -265,3 +265,34 @@ def test_z_only_movers_and_fixed_atoms(make):
     assert np.all(vz[:, :2] == vz[:, :2]) and (np.abs(vz[:, 2]) == 0).any() and (np.abs(vz[:, 2]) > 0).any()   # the 1D quench zeroed some, kept others
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_several_thermostats_of_different_chain_lengths(make):
+    """nhc_num > 1 (md_simulation.f90:75-84, :150-154, :176-180): thermostats on disjoint groups with M = 2 and M = 1, and a third of
+    M = 4 over both (its atoms are scaled twice per half step, in file order of the thermostats)."""
+    from pfmds_b200.inputs import KB
+    case = inputs.graphene_on_cu_small(interface="morsec", period=4)
+    case["groups"] = case["groups"] + [["CU", "#", "#"]]             # 6: the moving copper
+    nC, nCu = case["names"].count("C"), case["names"].count("CU")
+    q = lambda n, T: 3 * n * KB * T * 100.0 ** 2
+    case["nhc"] = [(1, 350.0, 2, q(nC, 350.0)), (6, 250.0, 1, q(nCu, 250.0)), (3, 300.0, 4, q(nC + nCu, 300.0))]
+    g, o = make(case), oracle(case)
+    for e in (g, o):
+        e.advance("nvt", 1.0, 0, 13)                                  # rebuilds at steps 4, 8, 12
+    (pg, vg, fg), (po, vo, fo) = g.download(), o.download()
+    assert np.abs(pg - po).max() < 1e-9 and rel_err(vg, vo) < 1e-8 and rel_err(fg, fo) < 1e-9
+    eg, eo = g.energies(), o.energies()
+    assert np.allclose(eg[0], eo[0], rtol=1e-9) and abs(eg[1] - eo[1]) < 1e-8 * eo[1] and np.allclose(eg[3], eo[3], rtol=1e-7, atol=1e-12)
+    for k, (_, _, M, _) in enumerate(case["nhc"]):
+        (xg, wg), (xo, wo) = g.get_nhc(k), o.get_nhc(k)
+        assert len(xg) == M and np.allclose(xg, xo, rtol=1e-7, atol=1e-15) and np.allclose(wg, wo, rtol=1e-7, atol=1e-15), k
+        assert np.abs(wo).max() > 0
+    g2 = make(case)                                                   # the same steps one at a time, energies logged on the device
+    g2.advance("nvt", 1.0, 0, 1)
+    rows = g2.advance_logged("nvt", 1.0, 1, 12, log_period=1)
+    assert rows[0].shape == (12, 3) and rows[3].shape == (12, 3)
+    assert np.allclose(rows[0][-1], eo[0], rtol=1e-9) and np.allclose(rows[3][-1], eo[3], rtol=1e-7, atol=1e-12)
+    assert np.abs(g2.download()[0] - po).max() < 1e-9
+    for e in (g, g2, o):
+        e.close()
