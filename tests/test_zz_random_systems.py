@@ -296,3 +296,29 @@ def test_several_thermostats_of_different_chain_lengths(make):
     assert np.abs(g2.download()[0] - po).max() < 1e-9
     for e in (g, g2, o):
         e.close()
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_momentum_removal_reaches_the_fixed_atoms_too(make):
+    """zero_momentum works on the all_atoms group (md_simulation.f90:162, md_general.f90:236-253): atoms outside the moving groups
+    receive the velocity shift as well (and keep their positions).  With invert_z_vel on, a layer of fast atoms inside the
+    reflecting slab [0.8 Lz, 0.9 Lz] (md_general.f90:382-398)."""
+    case = inputs.graphene_on_cu_small(interface="ljc", period=4, lz=40.0)
+    case = dict(case, zero_momentum_period=2, invert_z_vel=True)
+    fixed = np.array([nm == "CU_fixed" for nm in case["names"]])
+    nc = case["names"].count("C")
+    case["pos"] = case["pos"].copy(); case["vel"] = case["vel"].copy()
+    case["pos"][:nc, 2] += 0.85 * 40.0 - case["pos"][:nc, 2].mean()      # lift the sheet into the reflecting slab (away from the metal)
+    case["vel"][:nc:2, 2] = 0.01
+    case["vel"][1:nc:2, 2] = -0.01
+    p0 = case["pos"].copy()
+    g, o = make(case), oracle(case)
+    for e in (g, o):
+        e.advance("nvt", 1.0, 0, 7)
+    (pg, vg, fg), (po, vo, fo) = g.download(), o.download()
+    assert np.abs(pg - po).max() < 1e-9 and np.abs(vg - vo).max() < 1e-9 * np.abs(vo).max()
+    assert np.array_equal(pg[fixed], p0[fixed]) and np.abs(vo[fixed]).max() > 0 and np.abs(vg[fixed] - vo[fixed]).max() < 1e-12 * np.abs(vo).max() + 1e-18
+    dg, do = g.diagnostics(), o.diagnostics()
+    assert np.allclose(dg[2], do[2], rtol=1e-6, atol=1e-14) and abs(dg[3] - do[3]) < 1e-9 * do[3]
+    g.close()
+    o.close()
