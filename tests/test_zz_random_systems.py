@@ -322,3 +322,29 @@ def test_momentum_removal_reaches_the_fixed_atoms_too(make):
     assert np.allclose(dg[2], do[2], rtol=1e-6, atol=1e-14) and abs(dg[3] - do[3]) < 1e-9 * do[3]
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_lists_with_different_update_periods(make):
+    """Every list follows its own mod(md_step, update_period) (md_neighbours.f90:41): tb every 3, the interface lists every 5, rjl
+    every 7 steps.  Only steps on which all of them rebuild re-sort the atoms on the device; the partial rebuilds in between must
+    give the reference's lists all the same."""
+    case = inputs.graphene_on_cu_small(interface="ljc", period=5, jitter=0.05)
+    case["interactions"][0]["lists"] = [(1, 1, 12, 2.6, 3)]
+    case["interactions"][1]["lists"] = [(1, 2, 64, 7.5, 5), (2, 1, 96, 7.5, 5), (1, 1, 3, 1.9, 3)]
+    case["interactions"][2]["lists"] = [(2, 2, 100, 6.5, 7)]
+    case["vel"] = case["vel"] * 3.0                                   # hotter: list membership changes within a few steps
+    g, o = make(case), oracle(case)
+    done = 0
+    for upto in (4, 6, 8, 11, 15, 16):                                # stops after rebuilds of one, two or all lists
+        for e in (g, o):
+            e.advance("nvt", 1.0, done, upto - done)
+        done = upto
+        for k, j in list_ids(case):
+            a, b = neighbours(g, case, k, j), neighbours(o, case, k, j)
+            assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]), (upto, "list", k, j)
+        (pg, vg, fg), (po, vo, fo) = g.download(), o.download()
+        assert np.abs(pg - po).max() < 1e-9 and rel_err(fg, fo) < 1e-9, upto
+        assert np.allclose(g.energies()[0], o.energies()[0], rtol=1e-9), upto
+    g.close()
+    o.close()
