@@ -298,6 +298,8 @@ def run_variants(local, small=False):
             ("rjl_gen2, force kernel held to 5 blocks/SM instead of 7 (PFMDS_RJL_MINB=5: 94 registers, no constant reloads in the loop)", case, integrator, dt,
              {"PFMDS_RJL_GEN": "2", "PFMDS_RJL_MINB": "5"}),
             ("rjl_gen1 (PFMDS_RJL_GEN=1, the round-1 kernels)", case, integrator, dt, {"PFMDS_RJL_GEN": "1"}),
+            ("rjl_gen2 + list build with prefilter and exact test in separate loops (PFMDS_NL_MASK=1): compare nl_build", case, integrator, dt,
+             {"PFMDS_RJL_GEN": "2", "PFMDS_NL_MASK": "1"}),
             ("lj_fluid 96^3 lj1g (default)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "0"}),
             ("lj_fluid 96^3 lj1g pipelined (PFMDS_LJ1G_PIPE=1)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "1"})):
         try:

@@ -645,6 +645,8 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         c->use_graphs = gr ? gr[0] == '1' : n_atoms < 200000;
         const char* lp = std::getenv("PFMDS_LJ1G_PIPE");
         c->lj1g_pipe = lp && lp[0] == '1';
+        const char* nm = std::getenv("PFMDS_NL_MASK");
+        c->nl_mask = nm && nm[0] == '1';
         const char* rg = std::getenv("PFMDS_RJL_GEN");
         c->rjl_gen = (rg && rg[0] == '1') ? 1 : 2;
         const char* mb = std::getenv("PFMDS_RJL_MINB");
@@ -1396,6 +1398,8 @@ int pfmds_create_slab(pfmds_ctx** out, int device, int rank, int nranks, const c
         c->group_count.assign(group_sizes, group_sizes + n_groups);
         const char* tm = std::getenv("PFMDS_TIMERS");
         c->timers_on = tm && tm[0] == '1';
+        const char* nm = std::getenv("PFMDS_NL_MASK");
+        c->nl_mask = nm && nm[0] == '1';
         const char* rg = std::getenv("PFMDS_RJL_GEN");
         c->rjl_gen = (rg && rg[0] == '1') ? 1 : 2;
         const char* mb = std::getenv("PFMDS_RJL_MINB");

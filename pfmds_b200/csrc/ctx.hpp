@@ -97,6 +97,7 @@ struct pfmds_ctx {
     bool use_graphs = false;
     int rjl_minb = 7;               // blocks/SM the rjl force kernel is compiled for: 7, or 5 with PFMDS_RJL_MINB=5 (second generation only)
     int rjl_gen = 2;                // rjl pair routines: 2 = second generation (forces.cu), 1 = first (PFMDS_RJL_GEN=1)
+    bool nl_mask = false;           // PFMDS_NL_MASK=1: thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (opt-in, unmeasured)
     bool lj1g_pipe = false;         // PFMDS_LJ1G_PIPE=1: pipelined lj1g force kernel for systems of SMALL_N atoms and more (opt-in, unmeasured)
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
     bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)

@@ -288,6 +288,87 @@ __global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict_
     nnum[i] = cnt;
 }
 
+// Thread-per-atom variant with the two tests separated (opt-in: PFMDS_NL_MASK=1; not yet timed on hardware).  In k_build the exact
+// FP64 test sits inside the candidate loop, and because nearly every candidate survives the FP32 prefilter for SOME lane of the
+// warp, the warp executes that block for all ~630 candidates of an atom with ~15 % of its lanes active.  Here the prefilter runs
+// over one cell range (32 candidates at a time) and records its survivors in a register bit mask; the exact tests then walk the
+// set bits, the lanes of the warp side by side: max-over-lanes popc(mask), about 6 trips per cell instead of ~23.  Candidate order
+// is unchanged (ascending bit = ascending cell slot, ranges in order), so every row is k_build's row, entry for entry.
+#ifdef __CUDA_ARCH__
+#define PFMDS_FFS(m) __ffs((int)(m))
+#else
+#define PFMDS_FFS(m) __builtin_ffs((int)(m))
+#endif
+template <bool IDENT, bool PART>
+__global__ void __launch_bounds__(128) k_build_mask(int N, const double4* __restrict__ pos, const float4* __restrict__ posf, const int* __restrict__ orig,
+                                                    const int* __restrict__ cstart, const int* __restrict__ catoms, GridD g, BoxD box, PrefD pf,
+                                                    uint32_t bit1, uint32_t bit2, double rc2, double r1sq, double r2sq, int maxn, size_t stride,
+                                                    int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float4 pif = posf[i];
+    if ((__float_as_uint(pif.w) & (bit1 | PFMDS_GHOST)) != bit1) { nnum[i] = 0; return; }
+    const double4 pi = pos[i];
+    const int cx = cell_coord(pi.x, g.inv[0], g.n[0]), cy = cell_coord(pi.y, g.inv[1], g.n[1]), cz = cell_coord(pi.z, g.inv[2], g.n[2]);
+    const int lo0 = g.n[0] >= 3 ? -1 : 0, hi0 = g.n[0] >= 2 ? 1 : 0;
+    const int lo1 = g.n[1] >= 3 ? -1 : 0, hi1 = g.n[1] >= 2 ? 1 : 0;
+    const int lo2 = g.n[2] >= 3 ? -1 : 0, hi2 = g.n[2] >= 2 ? 1 : 0;
+    int cnt = 0, c0 = 0, c1 = 0, c2 = 0;
+    for (int oz = lo2; oz <= hi2; ++oz) {
+        int z = cz + oz; z = z < 0 ? z + g.n[2] : (z >= g.n[2] ? z - g.n[2] : z);
+        for (int oy = lo1; oy <= hi1; ++oy) {
+            int y = cy + oy; y = y < 0 ? y + g.n[1] : (y >= g.n[1] ? y - g.n[1] : y);
+            for (int ox = lo0; ox <= hi0; ++ox) {
+                int x = cx + ox; x = x < 0 ? x + g.n[0] : (x >= g.n[0] ? x - g.n[0] : x);
+                int cc = (z * g.n[1] + y) * g.n[0] + x;
+                const int b = cstart[cc], e = cstart[cc + 1];
+                for (int b0 = b; b0 < e; b0 += 32) {
+                    const int m = e - b0 < 32 ? e - b0 : 32;
+                    uint32_t mask = 0;
+                    for (int t = 0; t < m; ++t) {  // FP32 prefilter: no branch on the outcome, one bit per candidate
+                        const int j = IDENT ? b0 + t : catoms[b0 + t];
+                        const float4 q = posf[j];
+                        bool keep = j != i && (__float_as_uint(q.w) & bit2) != 0u;
+                        if (pf.on) {
+                            float fx = q.x - pif.x, fy = q.y - pif.y, fz = q.z - pif.z;
+                            fx = fx >= pf.h[0] ? fx - pf.L[0] : (fx < -pf.h[0] ? fx + pf.L[0] : fx);
+                            fy = fy >= pf.h[1] ? fy - pf.L[1] : (fy < -pf.h[1] ? fy + pf.L[1] : fy);
+                            fz = fz >= pf.h[2] ? fz - pf.L[2] : (fz < -pf.h[2] ? fz + pf.L[2] : fz);
+                            keep = keep && (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim);
+                        }
+                        mask |= keep ? (1u << t) : 0u;
+                    }
+                    while (mask) {                  // exact test of the survivors, in candidate order
+                        const int t = PFMDS_FFS(mask) - 1;
+                        mask &= mask - 1u;
+                        const int j = IDENT ? b0 + t : catoms[b0 + t];
+                        double4 pj = pos[j];
+                        double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]);
+                        double dy = min_image(pj.y - pi.y, box.h[1], box.L[1]);
+                        double dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
+                        double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        if (dr2 < rc2) {
+                            if (cnt < maxn) {
+                                if (!PART) nlist[(size_t)cnt * stride + i] = j;
+                                else if (dr2 < r1sq) nlist[(size_t)(c0++) * stride + i] = j;
+                                else if (dr2 < r2sq) alt[(size_t)(c1++) * stride + i] = j;
+                                else alt[(size_t)(maxn - 1 - (c2++)) * stride + i] = j;
+                            }
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (cnt > maxn) { raise_error(err, E_TOO_MANY, orig[i], cnt); cnt = maxn; }  // md_neighbours.f90:80
+    if (PART) {
+        for (int k = 0; k < c1; ++k) nlist[(size_t)(c0 + k) * stride + i] = alt[(size_t)k * stride + i];
+        for (int k = 0; k < c2; ++k) nlist[(size_t)(c0 + c1 + k) * stride + i] = alt[(size_t)(maxn - 1 - k) * stride + i];
+    }
+    nnum[i] = cnt;
+}
+
 #ifdef PFMDS_COOP  // ballot / popc compaction across the lanes of a warp: device, or the lock-step host replay
 // One WARP per list-owner atom: the lanes test 32 candidates of a cell range at a time (coalesced 16-byte
 // loads of the float4 copy), the survivors of the exact FP64 test are compacted with ballot + popc into the
@@ -421,9 +502,11 @@ void nl_build(pfmds_ctx* c, NList& l) {
         l.nlist_alt, l.nnum, c->err
 #ifdef PFMDS_COOP
 #define LAUNCH_BUILD(ID, PT) do { if (warp_per_atom) LAUNCH((k_build_warp<ID, PT>), nb, T, c->st, BUILD_ARGS); \
+        else if (c->nl_mask) LAUNCH((k_build_mask<ID, PT>), nb, T, c->st, BUILD_ARGS); \
         else LAUNCH((k_build<ID, PT>), nb, T, c->st, BUILD_ARGS); } while (0)
 #else
-#define LAUNCH_BUILD(ID, PT) LAUNCH((k_build<ID, PT>), nb, T, c->st, BUILD_ARGS)
+#define LAUNCH_BUILD(ID, PT) do { if (c->nl_mask) LAUNCH((k_build_mask<ID, PT>), nb, T, c->st, BUILD_ARGS); \
+        else LAUNCH((k_build<ID, PT>), nb, T, c->st, BUILD_ARGS); } while (0)
 #endif
     if (c->identity_order) { if (l.partition) LAUNCH_BUILD(true, true); else LAUNCH_BUILD(true, false); }
     else { if (l.partition) LAUNCH_BUILD(false, true); else LAUNCH_BUILD(false, false); }

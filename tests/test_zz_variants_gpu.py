@@ -44,3 +44,23 @@ def test_rjl_force_kernel_at_five_blocks_per_sm_gives_the_same_bits():
         e.advance("nvt", 2.0, 0, 12)
     (pa, va, fa), (pb, vb, fb) = a.download(), b.download()
     assert np.abs(fa).max() > 0.05 and np.array_equal(fa, fb) and np.array_equal(pa, pb) and np.array_equal(va, vb)
+
+
+def test_mask_list_build_gives_the_default_rows():
+    """PFMDS_NL_MASK=1: thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (nl.cu k_build_mask).
+    Same candidates in the same order: the rows, and with them every force bit, are those of k_build."""
+    for case, integ, dt in ((inputs.cu_fcc(ncell=30, jitter=0.03, period=5), "nvt", 2.0),            # 108 000 atoms, class-partitioned rows
+                            (inputs.lj_fluid(n_side=60, period=5), "nve", 0.5)):                    # 216 000 atoms, half list (lessnnum)
+        a = gpu(case)
+        os.environ["PFMDS_NL_MASK"] = "1"
+        try:
+            b = gpu(case)
+        finally:
+            del os.environ["PFMDS_NL_MASK"]
+        for e in (a, b):
+            e.advance(integ, dt, 0, 12)
+        (pa, va, fa), (pb, vb, fb) = a.download(), b.download()
+        assert np.abs(fa).max() > 1e-3 and np.array_equal(fa, fb) and np.array_equal(pa, pb) and np.array_equal(va, vb)
+        assert a.pair_count(0, 0) == b.pair_count(0, 0) and np.array_equal(a.diagnostics()[4], b.diagnostics()[4])
+        a.close()
+        b.close()
