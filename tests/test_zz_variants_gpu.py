@@ -49,7 +49,7 @@ def test_rjl_force_kernel_at_five_blocks_per_sm_gives_the_same_bits():
 def test_mask_list_build_gives_the_default_rows():
     """PFMDS_NL_MASK=1: thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (nl.cu k_build_mask).
     Same candidates in the same order: the rows, and with them every force bit, are those of k_build."""
-    for case, integ, dt in ((inputs.cu_fcc(ncell=30, jitter=0.03, period=5), "nvt", 2.0),            # 108 000 atoms, class-partitioned rows
+    for case, integ, dt in ((inputs.cu_fcc(ncell=37, jitter=0.03, period=5), "nvt", 2.0),            # 202 612 atoms (thread-per-atom build from 200 000 up), class-partitioned rows
                             (inputs.lj_fluid(n_side=60, period=5), "nve", 0.5)):                    # 216 000 atoms, half list (lessnnum)
         a = gpu(case)
         os.environ["PFMDS_NL_MASK"] = "1"
