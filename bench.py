@@ -243,7 +243,7 @@ def time_variant(case, integrator, dt, local, env, W, K):
             else:
                 os.environ[k] = v
     return {"ms_per_step": ms / K, "steps": K, "atom_steps_per_s": len(case["mass"]) * K / (ms * 1e-3),
-            "kernels_ms_per_step": {k: round(v[0] / K, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])[:4]}}
+            "kernels_ms_per_step": {k: round(v[0] / K, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])[:6]}}
 
 
 def e2e_steps(eng, integrator, dt, ke2e, stepwise=False):
@@ -301,7 +301,8 @@ def run_variants(local, small=False):
             ("rjl_gen2 + list build with prefilter and exact test in separate loops (PFMDS_NL_MASK=1): compare nl_build", case, integrator, dt,
              {"PFMDS_RJL_GEN": "2", "PFMDS_NL_MASK": "1"}),
             ("lj_fluid 96^3 lj1g (default)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "0"}),
-            ("lj_fluid 96^3 lj1g pipelined (PFMDS_LJ1G_PIPE=1)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "1"})):
+            ("lj_fluid 96^3 lj1g pipelined (PFMDS_LJ1G_PIPE=1)", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "1"}),
+            ("lj_fluid 96^3 lj1g (default) + PFMDS_NL_MASK=1: compare nl_build", ljc, "nve", ljc["integrators"][0][1], {"PFMDS_LJ1G_PIPE": "0", "PFMDS_NL_MASK": "1"})):
         try:
             out[name] = time_variant(cs, integ, h, local, env, W, K)
         except Exception as ex:
