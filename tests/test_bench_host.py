@@ -144,6 +144,79 @@ def test_bench_main_dry_run_on_the_host_replay(oracle_lib, monkeypatch, capsys):
     assert line["cpu_baseline"]["kind"] == "port"
 
 
+@pytest.mark.parametrize("child", ["ok", "timeout", "crash"])
+def test_bench_main_keeps_its_line_whatever_the_variants_child_does(oracle_lib, monkeypatch, capsys, child):
+    """The parent side of the variants leg (never reached with --no-variants): the child's last complete cumulative line is kept when
+    it finishes, when it is stopped at the time limit and when it dies; the headline line is printed in every case."""
+    import torch
+    import build_emu as B
+    import pfmds_b200.engine as E
+    import bench
+    B.build_emu()
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch, "tensor", lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items() if k != "device"}))
+    orig = E.configure
+    monkeypatch.setattr(E, "configure", lambda case, device=0, **kw: orig(case, lib_path=B.LIB))
+    monkeypatch.setattr(E, "measure_peaks", lambda device=0: (34.8, 6400.0))
+    small = inputs.cu_fcc(ncell=4, jitter=0.02, period=20, steps=40)
+    monkeypatch.setattr(bench, "build_case", lambda workload, seed, steps, nx=1: (small, "nvt", "dry run: Cu fcc 4^3 cells"))
+    monkeypatch.setattr(bench, "cpu_baseline_sample", lambda steps, threads=None: (500, steps, 1.0, 1))
+    partial = json.dumps({"note": "n", "a": {"ms_per_step": 1.0}}) + "\n" + json.dumps({"note": "n", "a": {"ms_per_step": 1.0}, "b": {"ms_per_step": 2.0}}) + "\n"
+    real_run = subprocess.run
+
+    def fake_run(cmd, **kw):
+        if "--variants-only" not in cmd:
+            return real_run(cmd, **kw)
+        if child == "timeout":
+            raise subprocess.TimeoutExpired(cmd, kw.get("timeout"), output=partial + '{"note": "n", "a": {"ms_per', stderr="")
+        if child == "crash":
+            return subprocess.CompletedProcess(cmd, -11, stdout=partial + '{"trunc', stderr="Segmentation fault")
+        return subprocess.CompletedProcess(cmd, 0, stdout="noise\n" + partial, stderr="")
+    monkeypatch.setattr(bench.subprocess, "run", fake_run)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "6", "--warmup", "3"])
+    assert bench.main() == 0
+    line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+    v = line["variants"]
+    assert line["value"] > 0 and v["b"]["ms_per_step"] == 2.0 and v["a"]["ms_per_step"] == 1.0
+    assert ("error" in v) == (child == "timeout") and v.get("child_exit") == (-11 if child == "crash" else None)
+
+
+def test_bench_main_survives_failing_auxiliary_legs(oracle_lib, monkeypatch, capsys):
+    """A failing e2e leg, peak micro-benchmark or CPU baseline is reported in its own field; the device-timed line is still printed."""
+    import torch
+    import build_emu as B
+    import pfmds_b200.engine as E
+    import bench
+    B.build_emu()
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch, "tensor", lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items() if k != "device"}))
+    orig = E.configure
+    monkeypatch.setattr(E, "configure", lambda case, device=0, **kw: orig(case, lib_path=B.LIB))
+
+    def boom(*a, **kw):
+        raise RuntimeError("injected")
+    monkeypatch.setattr(E, "measure_peaks", boom)
+    monkeypatch.setattr(bench, "e2e_steps", boom)
+    monkeypatch.setattr(bench, "cpu_baseline_sample", boom)
+    small = inputs.cu_fcc(ncell=4, jitter=0.02, period=20, steps=40)
+    monkeypatch.setattr(bench, "build_case", lambda workload, seed, steps, nx=1: (small, "nvt", "dry run: Cu fcc 4^3 cells"))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "6", "--warmup", "3", "--no-variants"])
+    assert bench.main() == 0
+    line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+    assert line["value"] > 0 and line["gpu_launches"] > 0 and line["kernels_ms_per_step"]
+    assert "injected" in line["e2e"]["error"] and line["e2e"]["value"] is None
+    assert line["roofline"]["frac"] is None and line["roofline"]["peak"] is None and line["roofline"]["achieved"] >= 0
+    assert line["cpu_baseline"]["value"] is None and "injected" in line["cpu_baseline"]["sample"]
+
+
 def test_smoke_dry_run_on_the_lockstep_replay(oracle_lib, monkeypatch, capsys):
     """__graft_entry__.smoke() as the driver calls it, with the engine factory pointed at the lock-step host replay (the small-system
     kernels the GPU would launch): the graphene-on-Cu case, its oracle comparison and its assertions run unchanged."""
