@@ -348,3 +348,30 @@ def test_lists_with_different_update_periods(make):
         assert np.allclose(g.energies()[0], o.energies()[0], rtol=1e-9), upto
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("make", ENGINES)
+def test_random_rebosc_sheets_match_the_oracle(make):
+    """rebosc with its numerical forces (REBOsolidcarbon.f90:27-91, md_interactions.f90:273-311) on rippled, jittered sheets of
+    different sizes, alone and with a tb interaction behind it: energies 1e-9, forces within 2e-7 of max|F| (the noise floor of the
+    reference's own central differences), a short trajectory."""
+    for seed in range(1, 3 if make is _lockstep else 4):
+        rng = np.random.default_rng(300 + seed)
+        cells = [(4, 3), (5, 3), (6, 4)][seed % 3]
+        case = inputs.graphene_rebosc(cells=cells, seed=seed, jitter=float(rng.uniform(0.02, 0.07)), period=3, with_tb=(seed % 2 == 0))
+        box, pos = case["box"], case["pos"]
+        pos[:, 2] += rng.uniform(0.1, 0.4) * np.sin(2 * np.pi * pos[:, 0] / box[0] + rng.uniform(0, 6.28)) * np.cos(2 * np.pi * pos[:, 1] / box[1])
+        g, o = make(case), oracle(case)
+        for e in (g, o):
+            e.advance("nve", 0.5, 0, 1)
+        for k, j in list_ids(case):
+            a, b = neighbours(g, case, k, j), neighbours(o, case, k, j)
+            assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]), (seed, "list", k, j)
+        fo = o.download()[2]
+        assert rel_err(g.download()[2], fo) < 2e-7 and np.abs(fo).max() > 0.1, (seed, "forces")
+        assert np.allclose(g.energies()[0], o.energies()[0], rtol=1e-9, atol=1e-12), (seed, "energies")
+        for e in (g, o):
+            e.advance("nve", 0.5, 1, 4)
+        assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-8, (seed, "trajectory")
+        g.close()
+        o.close()
