@@ -29,7 +29,16 @@ LOCKSTEP_KEEP = ["test_step0_lists_forces_energies", "test_parity_misc", "test_a
                  "test_replay_identifies_itself"]
 
 
+# GPU tests whose code path has not run on hardware yet (written after the round's GPU minutes were spent): they go last, so that
+# `pytest -m gpu -x` reports the hardware-proven tests before it can stop at one of these.  Remove a name once it has passed on a B200.
+GPU_LATE = ["test_deposition_matches_the_golden_fixture", "test_rebosc_matches_the_golden_fixture", "test_queued_log_rows_are_the_stepwise_log",
+            "test_advance_logged_rows", "test_device_math_functions"]
+
+
 def pytest_collection_modifyitems(config, items):
+    late = [it for it in items if "gpu" in it.keywords and any(it.name.startswith(n) for n in GPU_LATE)]
+    if late:
+        items[:] = [it for it in items if it not in late] + late
     if os.environ.get("PFMDS_LOCKSTEP_TESTS") != "all":
         drop = [it for it in items if "test_emulated_library.py" in it.nodeid and "[lockstep" in it.name and not any(k in it.name for k in LOCKSTEP_KEEP)]
         if drop:
