@@ -153,6 +153,9 @@ int pfmds_upload(pfmds_ctx* ctx, const double* positions, const double* velociti
 
 /* Sum of nnum over the rows of one neighbour list (directed pairs), for work models. */
 int pfmds_pair_count(pfmds_ctx* ctx, int interaction, int list, long long* pairs);
+/* Listed directed pairs whose current min-image distance is below `r` (e.g. R2 of the potential: the pairs of a row between R2 and
+ * the list's r_cut leave the pair routines after the distance test and are charged 30 flop, not the full count, by bench.py). */
+int pfmds_pair_count_within(pfmds_ctx* ctx, int interaction, int list, double r, long long* pairs);
 
 /* Per-kernel device times: with profiling on, CUDA events bracket every launch of each kernel class on
  * the context's stream.  pfmds_kernel_times fills ms[k], count[k] for k < n (classes named by

@@ -43,6 +43,29 @@ int nl_n_of(int kind) { return kind == K_LJ ? 2 : (kind == K_LJC || kind == K_MO
 
 void finalize_slab(pfmds_ctx* c);
 
+// Kernel-variant and path switches from the environment, read once per context (pfmds_create / pfmds_create_slab).
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    char* end = nullptr;
+    long x = std::strtol(v, &end, 10);
+    return (end && *end == 0 && x >= 0 && x <= 2000000000L) ? (int)x : dflt;
+}
+void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
+    c->timers_on = env_int("PFMDS_TIMERS", 0) == 1;
+    c->use_graphs = !slab && env_int("PFMDS_GRAPHS", n_atoms < 200000 ? 1 : 0) == 1;
+    c->lj1g_pipe = env_int("PFMDS_LJ1G_PIPE", 1) != 0;
+    c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
+    c->rjl_gen = env_int("PFMDS_RJL_GEN", 2) == 1 ? 1 : 2;
+#ifdef PFMDS_COOP
+    c->small_n = env_int("PFMDS_SMALL_N", 100000);
+    c->nl_warp_n = env_int("PFMDS_NL_WARP_N", 200000);
+#else  // serial host replay of the test suite: no lane exchange, thread-per-atom kernels only
+    c->small_n = 0;
+    c->nl_warp_n = 0;
+#endif
+}
+
 const std::vector<int>& group_of(pfmds_ctx* c, int g) {
     if (g < 1 || g > (int)c->groups.size()) fail(PFMDS_ERR_INVALID, "error: group number " + std::to_string(g) + " is not defined");
     return c->groups[(size_t)g - 1];
@@ -65,7 +88,7 @@ void check_device_error(pfmds_ctx* c) {
     CK(cudaMemcpyAsync(h, c->err, sizeof h, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (h[0] == 0) return;
-    if (h[0] == 31) fail(PFMDS_ERR_CUDA, "slab decomposition: a neighbour rank did not signal within 3 s (peer-memory halo)");
+    if (h[0] == 31) fail(PFMDS_ERR_CUDA, "slab decomposition: a neighbour rank did not signal within the flag time-out (peer-memory halo; PFMDS_SLAB_TIMEOUT_S, default 120 s): it failed, or its host thread fell that far behind");
     if (h[0] == 30) fail(PFMDS_ERR_UNSUPPORTED, "slab decomposition: an atom moved farther than one slab between two list rebuilds");
     if (h[0] == E_OUT_OF_CELL) fail(PFMDS_ERR_OUT_OF_CELL, " " + std::to_string(h[1] + 1) + "  particle out of cell");
     if (h[0] == E_TOO_MANY) fail(PFMDS_ERR_TOO_MANY_NEIGHBOURS, "error: too many neighbours (atom " + std::to_string(h[1] + 1) + ", " + std::to_string(h[2]) + " found)");
@@ -87,6 +110,16 @@ void check_rjl_generation(pfmds_ctx* c) {
     std::fprintf(stderr, "pfmds_b200: the short elementary functions of the second-generation rjl kernels missed their error bounds on device %d; "
                          "using the first generation (PFMDS_RJL_GEN=1)\n", c->dev);
     c->rjl_gen = 1;
+}
+
+// device-resident energy log of pfmds_advance_logged: allocated once with the description (no first-use allocation inside a call)
+#define LOG_ROWS_PREALLOC 4096
+void alloc_log(pfmds_ctx* c) {
+    size_t D = c->inter.size() + 1;
+    for (auto& t : c->nhc) D += (size_t)3 * t.M;
+    if (c->logbuf) return;
+    CK(cudaMalloc(&c->logbuf, sizeof(double) * D * LOG_ROWS_PREALLOC));
+    c->log_cap = D * LOG_ROWS_PREALLOC;
 }
 
 // Slab mode: the masks came with pfmds_create_slab; validation works on group numbers and global sizes.
@@ -140,6 +173,7 @@ void finalize_slab(pfmds_ctx* c) {
             if (c->nhc[a].group == c->nhc[b].group) c->nhc_fusable = false;
     if (c->nhc.size() > 1) c->nhc_fusable = false;  // several thermostats: masks are not on the host in slab mode, keep the plain path
     if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
+    alloc_log(c);
     check_rjl_generation(c);
     c->first_overwrites = !c->inter.empty() && c->inter[0].kind == K_RJL && group_size(c, c->inter[0].nl[0].g1) == slab_n_global(c);
     nl_setup_grid(c);
@@ -285,6 +319,7 @@ void finalize(pfmds_ctx* c) {
         CK(cudaMalloc(&c->d_grank[(size_t)ch.to - 1], sizeof(int) * (size_t)N));
         CK(cudaMemcpyAsync(c->d_grank[(size_t)ch.to - 1], rank.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, c->st));
     }
+    alloc_log(c);
     check_rjl_generation(c);
     c->first_overwrites = c->zero_all && c->changes.empty() && !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
     nl_setup_grid(c);
@@ -389,6 +424,10 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bo
     {
         PhaseTimer t(c, 0);
         if (first_of_call) integ_check_positions(c);
+        if (step == 0) {  // a re-run from md step 0 after NVT steps: the closing scale of the last thermostat step is applied before anything reads velocities
+            integ_flush_pending(c);
+            c->nhc_ke_valid = false;
+        }
         if (c->invert_z) integ_invert_z(c);
         if (step != 0) {
             if (kind == PFMDS_NVT && c->nhc_fusable && c->nhc_ke_valid) {
@@ -577,6 +616,20 @@ __global__ void k_sum_int(int n, const int* __restrict__ a, unsigned long long* 
     atomicAdd(out, s);
 #endif
 }
+__global__ void k_count_within(int N, const double4* __restrict__ pos, ListView lv, BoxD box, double r2max, unsigned long long* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long s = 0;
+    if (i < N) {
+        const int n = lv.nnum[i];
+        const double4 pi = pos[i];
+        for (int p = 0; p < n; ++p) {
+            const double4 pj = pos[lv.nlist[(size_t)p * lv.stride + i]];
+            double dx = min_image(pj.x - pi.x, box.h[0], box.L[0]), dy = min_image(pj.y - pi.y, box.h[1], box.L[1]), dz = min_image(pj.z - pi.z, box.h[2], box.L[2]);
+            s += (dx * dx + dy * dy + dz * dz < r2max) ? 1ull : 0ull;
+        }
+    }
+    if (s) atomicAdd(out, s);
+}
 __global__ void k_upload_scatter(int N, const int* __restrict__ orig, const double* __restrict__ hp, const double* __restrict__ hv,
                                  double4* __restrict__ pos, double4* __restrict__ vel) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -584,6 +637,13 @@ __global__ void k_upload_scatter(int N, const int* __restrict__ orig, const doub
     int f = orig[s];
     if (hp) { double4 p = pos[s]; p.x = hp[3 * f]; p.y = hp[3 * f + 1]; p.z = hp[3 * f + 2]; pos[s] = p; }
     if (hv) { double4 v = vel[s]; v.x = hv[3 * f]; v.y = hv[3 * f + 1]; v.z = hv[3 * f + 2]; vel[s] = v; }
+}
+
+__global__ void k_upload_forces(int N, const int* __restrict__ orig, const double* __restrict__ hf, double4* __restrict__ frc) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const double* f = hf + 3 * (size_t)orig[s];
+    frc[s] = make_double4(f[0], f[1], f[2], 0.);
 }
 
 // file-order copy of one state array: out[3 f + k] = component k of the atom whose file index is f = orig[slot]
@@ -639,19 +699,12 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         CK(cudaMemcpy(c->vel, hv.data(), sizeof(double4) * S, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->orig, ho.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
         CK(cudaMemset(c->gmask, 0, sizeof(uint32_t) * S));
-        const char* tm = std::getenv("PFMDS_TIMERS");
-        c->timers_on = tm && tm[0] == '1';
-        const char* gr = std::getenv("PFMDS_GRAPHS");
-        c->use_graphs = gr ? gr[0] == '1' : n_atoms < 200000;
-        const char* lp = std::getenv("PFMDS_LJ1G_PIPE");
-        c->lj1g_pipe = lp && lp[0] == '1';
-        const char* nm = std::getenv("PFMDS_NL_MASK");
-        c->nl_mask = nm && nm[0] == '1';
-        const char* rg = std::getenv("PFMDS_RJL_GEN");
-        c->rjl_gen = (rg && rg[0] == '1') ? 1 : 2;
-        const char* mb = std::getenv("PFMDS_RJL_MINB");
-        c->rjl_minb = (mb && mb[0] == '5') ? 5 : 7;
+        read_env(c, n_atoms, false);
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+        // staging block of pfmds_upload / pfmds_download (file-order x y z of up to three arrays): allocated here, once, so that
+        // no call on the data path allocates (a first-use cudaMalloc of 72 MB inside a timed region costs milliseconds)
+        c->io_cap = 9 * (size_t)n_atoms;
+        CK(cudaMalloc(&c->io_stage, sizeof(double) * c->io_cap));
     });
 }
 
@@ -807,11 +860,13 @@ static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, boo
 }
 
 // one row of the device-resident energy log: [e_inter(n_inter), KE(all_moving), x v q of every chain]
-__global__ void k_log_row(int n_inter, const double* __restrict__ energy, const double* __restrict__ ke, NhcPack P, double* __restrict__ row) {
+// (head: energies and KE, with the first pack of thermostats; further packs of up to NHC_MAXF chains append at `o`)
+__global__ void k_log_row(int n_inter, const double* __restrict__ energy, const double* __restrict__ ke, NhcPack P, double* __restrict__ row, int o) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (int k = 0; k < n_inter; ++k) row[k] = energy[k];
-    row[n_inter] = ke[0];
-    int o = n_inter + 1;
+    if (n_inter >= 0) {
+        for (int k = 0; k < n_inter; ++k) row[k] = energy[k];
+        row[n_inter] = ke[0];
+    }
     for (int t = 0; t < P.n; ++t)
         for (int i = 0; i < 3 * P.M[t]; ++i) row[o++] = P.state[t][i];
 }
@@ -827,22 +882,30 @@ int pfmds_advance_logged(pfmds_ctx* c, int kind, double dt, int first, int n, in
         if (n < 0 || first < 0 || log_period < 1) fail(PFMDS_ERR_INVALID, "error: bad step range");
         CK(cudaSetDevice(c->dev));
         finalize(c);
-        if (c->nhc.size() > NHC_MAXF) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: pfmds_advance_logged with more than 4 thermostats");
         const int nI = (int)c->inter.size(), nT = (int)c->nhc.size();
         if (!rows || row_len < nI + 2 + nT) fail(PFMDS_ERR_INVALID, "error: pfmds_advance_logged needs rows of n_interactions + 2 + n_nhc doubles");
         int D = nI + 1;
         for (auto& t : c->nhc) D += 3 * t.M;
         int want = 0;
         for (int s = first; s < first + n; ++s) want += (s % log_period == 0);
-        if ((size_t)want * D > c->log_cap) {
+        if ((size_t)want * D > c->log_cap) {   // beyond the block finalize() allocated (LOG_ROWS_PREALLOC rows): grow, outside any step
             if (c->logbuf) CK(cudaFree(c->logbuf));
             c->logbuf = nullptr; c->log_cap = 0;
             CK(cudaMalloc(&c->logbuf, sizeof(double) * (size_t)want * D));
             c->log_cap = (size_t)want * D;
         }
-        NhcPack P{};
-        P.n = nT;
-        for (int k = 0; k < nT; ++k) { P.state[k] = c->nhc[k].state; P.M[k] = c->nhc[k].M; }
+        // thermostat states go out in packs of NHC_MAXF chains (kernel parameter block), any number of thermostats
+        std::vector<NhcPack> packs;
+        std::vector<int> pack_at;
+        {
+            int o = nI + 1;
+            for (int k0 = 0; k0 < nT || packs.empty(); k0 += NHC_MAXF) {
+                NhcPack P{};
+                pack_at.push_back(o);
+                for (int k = k0; k < nT && k < k0 + NHC_MAXF; ++k) { P.state[P.n] = c->nhc[k].state; P.M[P.n] = c->nhc[k].M; o += 3 * c->nhc[k].M; ++P.n; }
+                packs.push_back(P);
+            }
+        }
         std::vector<int> gsize;
         int r = 0;
         for (int s = first; s < first + n; ++s) {
@@ -851,8 +914,10 @@ int pfmds_advance_logged(pfmds_ctx* c, int kind, double dt, int first, int n, in
             if (!logged) continue;
             integ_flush_pending(c);                              // as pfmds_energies: KE of the velocities the host would download
             integ_kinetic_energy(c, c->all_moving, c->red);
-            LAUNCH((k_log_row), 1, 32, c->st, nI, c->energy, c->red, P, c->logbuf + (size_t)r * D);
-            c->launches += 1;
+            for (size_t q = 0; q < packs.size(); ++q) {
+                LAUNCH((k_log_row), 1, 32, c->st, q == 0 ? nI : -1, c->energy, c->red, packs[q], c->logbuf + (size_t)r * D, pack_at[q]);
+                c->launches += 1;
+            }
             gsize.push_back(group_size(c, c->all_moving));
             ++r;
         }
@@ -1090,13 +1155,12 @@ int pfmds_upload(pfmds_ctx* c, const double* pos, const double* vel) {
         integ_flush_pending(c);
         c->nhc_ke_valid = false;
         c->energy_valid = false;
+        // file-order input lands in the context's staging block (allocated in pfmds_create; stream order keeps it safe to reuse)
         double *dp = nullptr, *dv = nullptr;
-        if (pos) { CK(cudaMallocAsync(&dp, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
-        if (vel) { CK(cudaMallocAsync(&dv, sizeof(double) * n3, c->st)); CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
+        if (pos) { dp = c->io_stage; CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
+        if (vel) { dv = c->io_stage + n3; CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st)); }
         LAUNCH((k_upload_scatter), (c->N + 255) / 256, 256, c->st, c->N, c->orig, dp, dv, c->pos, c->vel);
         c->launches += 1;
-        if (dp) CK(cudaFreeAsync(dp, c->st));
-        if (dv) CK(cudaFreeAsync(dv, c->st));
         // membership of every list was decided on the old positions: rebuild at the next step
         for (auto& it : c->inter) for (int j = 0; j < it.nl_n; ++j) it.nl[j].built = false;
     });
@@ -1108,12 +1172,15 @@ static const double STATE_MAGIC = 20240731.0;
 static size_t state_doubles(pfmds_ctx* c) {
     size_t n = 4 + c->groups.size();
     for (auto& t : c->nhc) n += 1 + (size_t)3 * t.M + 4;
+    if (c->finalized && !c->zero_all) n += 3 * (size_t)c->N;  // accumulated forces, see pfmds_save_state
     return n;
 }
 int pfmds_state_size(pfmds_ctx* c, long long* n) {
     if (!c || !n) return PFMDS_ERR_INVALID;
     return guarded(c, [&] {
         if (c->slab) fail(PFMDS_ERR_UNSUPPORTED, "unsupported: checkpoints of a slab context");
+        CK(cudaSetDevice(c->dev));
+        finalize(c);
         *n = (long long)state_doubles(c);
     });
 }
@@ -1133,6 +1200,14 @@ int pfmds_save_state(pfmds_ctx* c, double* blob) {
             k += (size_t)3 * t.M + 4;
         }
         for (size_t g = 0; g < c->groups.size(); ++g) blob[k++] = (double)c->cur_n[g];
+        if (!c->zero_all) {
+            // zero_forces only touches the all_atoms group (md_integrators.f90:147-163): forces of atoms outside it accumulate over
+            // the run and cannot be recomputed from the positions, so they travel with the checkpoint (file order)
+            const size_t n3 = 3 * (size_t)c->N;
+            LAUNCH((k_download_gather), (c->N + 255) / 256, 256, c->st, c->N, c->orig, c->frc, c->io_stage);
+            c->launches += 1;
+            CK(cudaMemcpyAsync(blob + k, c->io_stage, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->st));
+        }
         check_device_error(c);
     });
 }
@@ -1150,14 +1225,12 @@ int pfmds_restore_state(pfmds_ctx* c, const double* pos, const double* vel, cons
         integ_flush_pending(c);
         {   // state in file order -> slots
             const size_t n3 = 3 * (size_t)c->N;
-            double *dp = nullptr, *dv = nullptr;
-            CK(cudaMalloc(&dp, sizeof(double) * n3)); CK(cudaMalloc(&dv, sizeof(double) * n3));
+            double *dp = c->io_stage, *dv = c->io_stage + n3;
             CK(cudaMemcpyAsync(dp, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
             CK(cudaMemcpyAsync(dv, vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
             LAUNCH((k_upload_scatter), (c->N + 255) / 256, 256, c->st, c->N, c->orig, dp, dv, c->pos, c->vel);
             c->launches += 1;
             CK(cudaStreamSynchronize(c->st));
-            cudaFree(dp); cudaFree(dv);
         }
         for (auto& t : c->nhc) {
             if ((int)blob[k] != t.M) fail(PFMDS_ERR_INVALID, "error: the checkpoint does not belong to this settings file (chain length differs)");
@@ -1182,6 +1255,12 @@ int pfmds_restore_state(pfmds_ctx* c, const double* pos, const double* vel, cons
         for (auto& it : c->inter) for (int j = 0; j < it.nl_n; ++j) it.nl[j].built = false;
         update_lists(c, 0);
         compute_forces(c, false);
+        if (!c->zero_all) {  // the forces of the checkpointed step, including what had accumulated outside the all_atoms group
+            const size_t n3 = 3 * (size_t)c->N;
+            CK(cudaMemcpyAsync(c->io_stage, blob + k, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
+            LAUNCH((k_upload_forces), (c->N + 255) / 256, 256, c->st, c->N, c->orig, c->io_stage, c->frc);
+            c->launches += 1;
+        }
         CK(cudaGetLastError());
         check_device_error(c);
     });
@@ -1196,6 +1275,25 @@ int pfmds_pair_count(pfmds_ctx* c, int inter, int list, long long* pairs) {
         CK(cudaMalloc(&d, sizeof(unsigned long long)));
         CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->st));
         LAUNCH((k_sum_int), 256, 256, c->st, c->N, c->inter[(size_t)inter].nl[list].nnum, d);
+        if (c->slab) slab_allreduce_sum_ll(c, d, 1);
+        unsigned long long h = 0;
+        CK(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        cudaFree(d);
+        *pairs = (long long)h;
+    });
+}
+
+int pfmds_pair_count_within(pfmds_ctx* c, int inter, int list, double r, long long* pairs) {
+    if (!c || !pairs) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        if (!c->finalized || inter < 0 || inter >= (int)c->inter.size() || list < 0 || list >= c->inter[(size_t)inter].nl_n) fail(PFMDS_ERR_INVALID, "error: no such neighbour list");
+        unsigned long long* d = nullptr;
+        CK(cudaMalloc(&d, sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->st));
+        LAUNCH((k_count_within), (c->N + 255) / 256, 256, c->st, c->N, c->pos, c->inter[(size_t)inter].nl[list].view(c->stride), c->box, r * r, d);
+        c->launches += 1;
         if (c->slab) slab_allreduce_sum_ll(c, d, 1);
         unsigned long long h = 0;
         CK(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->st));
@@ -1396,14 +1494,7 @@ int pfmds_create_slab(pfmds_ctx** out, int device, int rank, int nranks, const c
         CK(cudaMemcpy(c->orig, ho.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->gmask, hm.data(), sizeof(uint32_t) * S, cudaMemcpyHostToDevice));
         c->group_count.assign(group_sizes, group_sizes + n_groups);
-        const char* tm = std::getenv("PFMDS_TIMERS");
-        c->timers_on = tm && tm[0] == '1';
-        const char* nm = std::getenv("PFMDS_NL_MASK");
-        c->nl_mask = nm && nm[0] == '1';
-        const char* rg = std::getenv("PFMDS_RJL_GEN");
-        c->rjl_gen = (rg && rg[0] == '1') ? 1 : 2;
-        const char* mb = std::getenv("PFMDS_RJL_MINB");
-        c->rjl_minb = (mb && mb[0] == '5') ? 5 : 7;
+        read_env(c, n_local, true);
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
         slab_init(c, rank, nranks, id, n_global, n_local, capacity);
     });

@@ -127,6 +127,8 @@ struct SlabDev {
     int* sig_l; int* sig_r; int sig_seq; unsigned int* counter;
     const int* wait_a; const int* wait_b; int wait_seq;   // 0: nothing to wait for
     int* err;
+    unsigned long long timeout_ns;  // give up (error 31) after this long: host-side skew between the ranks (module load, graph
+                                    // instantiation, a rank writing a snapshot) must fit inside it; PFMDS_SLAB_TIMEOUT_S, default 120 s
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ void slab_wait(const SlabDev& S) {
@@ -138,7 +140,7 @@ __device__ __forceinline__ void slab_wait(const SlabDev& S) {
                 if (*reinterpret_cast<volatile int*>(S.err) != 0) break;  // the run is already failing: do not wait once per block
                 __nanosleep(100);
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                if (t - t0 > 3000000000ull) { raise_error(S.err, 31, S.wait_seq, 1); break; }
+                if (t - t0 > S.timeout_ns) { raise_error(S.err, 31, S.wait_seq, 1); break; }
             }
             __threadfence_system();
         }
@@ -152,6 +154,7 @@ __device__ __forceinline__ void slab_signal(const SlabDev& S, bool pushed) {
         if (pushed) __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence();  // release: the barrier ordered this block's (fenced) peer stores before this point; cumulativity carries them past the counter
             unsigned int t = atomicAdd(S.counter, 1u);
             if (t == gridDim.x * gridDim.y - 1) {
                 *S.counter = 0;

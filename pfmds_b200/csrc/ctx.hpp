@@ -95,10 +95,13 @@ struct pfmds_ctx {
     struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid; cudaGraphExec_t exec; long long launches; };
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
-    int rjl_minb = 7;               // blocks/SM the rjl force kernel is compiled for: 7, or 5 with PFMDS_RJL_MINB=5 (second generation only)
     int rjl_gen = 2;                // rjl pair routines: 2 = second generation (forces.cu), 1 = first (PFMDS_RJL_GEN=1)
-    bool nl_mask = false;           // PFMDS_NL_MASK=1: thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (opt-in, unmeasured)
-    bool lj1g_pipe = false;         // PFMDS_LJ1G_PIPE=1: pipelined lj1g force kernel for systems of SMALL_N atoms and more (opt-in, unmeasured)
+    bool nl_mask = true;            // thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (measured 8 % faster, BENCH_r01); PFMDS_NL_MASK=0: k_build
+    bool lj1g_pipe = true;          // pipelined lj1g force kernel for systems of small_n atoms and more (measured 0.174 -> 0.102 ms, BENCH_r01); PFMDS_LJ1G_PIPE=0: k_lj1g
+    // Path switches by system size.  Runtime fields (PFMDS_SMALL_N, PFMDS_NL_WARP_N) so that the parity tests can drive
+    // the kernels of BOTH sides of each switch against the oracle on systems the O(N^2) oracle can handle.
+    int small_n = 100000;           // below: 8 lanes per atom in the pair kernels (latency bound); from it on: thread per atom, pipelined
+    int nl_warp_n = 200000;         // below: warp-per-atom list build; from it on: thread per atom
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
     bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)
     bool finalized = false;

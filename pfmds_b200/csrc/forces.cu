@@ -46,10 +46,7 @@ __device__ __forceinline__ double split_sum(double v) {
     for (int o = SPLIT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-#define SMALL_SPLIT 8
-#ifndef SMALL_N
-#define SMALL_N 100000
-#endif
+#define SMALL_SPLIT 8  // systems below pfmds_ctx::small_n atoms (runtime: PFMDS_SMALL_N) take the SPLIT kernels
 
 // per-block partial of the per-thread energy; the final sum is done by k_sum_partials in block order
 __device__ __forceinline__ void store_partial(double e, double* part) {
@@ -437,12 +434,10 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
         fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
     }
 }
-// MB = blocks per SM the register allocation is held to.  7 (72 registers) is the measured optimum of the first generation; at
-// 5 (94 registers) the second generation's loop keeps its loop-invariant constants in registers and drops the 31 LDC per trip
-// it otherwise re-issues (255 instead of 286 instructions per trip, profiles/r1g_static_loop_mix.txt) at 20 instead of 28
-// resident warps: PFMDS_RJL_MINB=5 selects it, unmeasured so far.
-template <class CT, int MB = RJL_MINB>  // CT = RjlC (first generation) or RjlF (second generation)
-__global__ void __launch_bounds__(FT, MB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
+// RJL_MINB = blocks per SM the register allocation is held to.  7 (72 registers) is the measured optimum; 5 (94 registers, no
+// constant reloads in the loop, 20 instead of 28 resident warps) measured slower on a B200 (0.425 against 0.358 ms, BENCH_r01).
+template <class CT>  // CT = RjlC (first generation) or RjlF (second generation)
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                       WrapC W, SlabDev S, int overwrite) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);  // slab mode: the neighbours' 1/Eb have landed in my ghost slots
@@ -536,7 +531,7 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split_e(int N, const double4* 
     store_partial(e, part);
 }
 
-// ---- lj1g, pipelined variant (opt-in: PFMDS_LJ1G_PIPE=1; unmeasured on hardware so far) ----------------
+// ---- lj1g, pipelined variant: the default from small_n atoms up (PFMDS_LJ1G_PIPE=0 selects k_lj1g); 0.174 -> 0.102 ms per launch on the 96^3 LJ fluid (BENCH_r01) ----
 // Same sums as k_lj1g<F, E, 1>, restructured like the rjl kernels: ping-pong prefetch of the row indices and of the 32-byte
 // records, the conservative exact wrap test instead of three unconditional selects, 1/r^2 and sqrt from the hardware seeds plus
 // one third-order step (mathx.cuh) instead of the CUDA library's division and square root with their slow-path calls.
@@ -853,7 +848,7 @@ __global__ void k_zero_group(int N, double4* __restrict__ frc, const uint32_t* _
 }
 #ifdef PFMDS_HAVE_CTX  // ---- launchers (host side of the library) ----------------------------------------
 void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
-    if (c->first_overwrites && c->N >= SMALL_N) return;  // the first force kernel stores instead of accumulating
+    if (c->first_overwrites && c->N >= c->small_n) return;  // the first force kernel stores instead of accumulating
     KTimer kt(c, KS_ZERO_FORCES);
     if (c->zero_all) { CK(cudaMemsetAsync(c->frc, 0, sizeof(double4) * (size_t)c->N, c->st)); return; }
     LAUNCH((k_zero_group), (c->N + 255) / 256, 256, c->st, c->N, c->frc, c->gmask, 1u << (c->all_atoms - 1));
@@ -885,7 +880,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     int e_parts = 0;
     double e_scale = 1.0;
     const int N = c->N, nb = (N + FT - 1) / FT;
-    const bool small = N < SMALL_N;
+    const bool small = N < c->small_n;
     const int nbs = (int)(((size_t)N * SMALL_SPLIT + FT - 1) / FT);
     const size_t st = c->stride;
     switch (it.kind) {
@@ -902,7 +897,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         c->launches += 2;
         break;
     case K_LJ1G:
-        if (c->lj1g_pipe && !small) {  // opt-in pipelined variant (thread per atom)
+        if (c->lj1g_pipe && !small) {  // pipelined variant (thread per atom)
             KTimer kt(c, KS_LJ1G);
             if (with_energy) { LAUNCH((k_lj1g_pipe<true>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), epart); e_parts = nb; e_scale = 0.5; }
             else LAUNCH((k_lj1g_pipe<false>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), nullptr);
@@ -924,7 +919,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         const bool fused = c->slab && !small && slab_fused(c);  // density stores 1/Eb into the neighbours' ghosts itself
         const bool gen2 = c->rjl_gen != 1 && rjl_gen2_ok(it.rjl, c->box);
         const ListView lv = it.nl[0].view(st);
-        const int ow = (k == 0 && c->first_overwrites && N >= SMALL_N) ? 1 : 0;
+        const int ow = (k == 0 && c->first_overwrites && !small) ? 1 : 0;
         // one launch sequence for both generations: CD / CF are the constant packs that select the pair routines.
         // Energies of the step: the first generation evaluates them in its density pass (a second exponential per pair), the
         // second takes them from the force pass, which has that exponential in hand (k_rjl_force_e).
@@ -946,12 +941,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
             if (!e_in_force) {
                 KTimer kt(c, KS_RJL_FORCE);
                 if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W);
-                else {
-                    bool launched = false;
-                    if constexpr (TF::padded)   // second generation only
-                        if (c->rjl_minb == 5) { LAUNCH((k_rjl_force<TF, 5>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow); launched = true; }
-                    if (!launched) LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
-                }
+                else LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
             }
         };
         if (e_in_force) {
@@ -1017,7 +1007,7 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     const int N = c->N, nb = (N + FT - 1) / FT;
     const size_t st = c->stride;
     double scale = 1.0;
-    const bool small = N < SMALL_N;
+    const bool small = N < c->small_n;
     const int nbs = (int)(((size_t)N * SMALL_SPLIT + FT - 1) / FT);
     int nparts = small ? nbs : nb;
     switch (it.kind) {

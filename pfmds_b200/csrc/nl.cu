@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict_
     nnum[i] = cnt;
 }
 
-// Thread-per-atom variant with the two tests separated (opt-in: PFMDS_NL_MASK=1; not yet timed on hardware).  In k_build the exact
+// Thread-per-atom variant with the two tests separated (the default; PFMDS_NL_MASK=0 selects k_build; 8 % faster per rebuild at 10^6 atoms, BENCH_r01).  In k_build the exact
 // FP64 test sits inside the candidate loop, and because nearly every candidate survives the FP32 prefilter for SOME lane of the
 // warp, the warp executes that block for all ~630 candidates of an atom with ~15 % of its lanes active.  Here the prefilter runs
 // over one cell range (32 candidates at a time) and records its survivors in a register bit mask; the exact tests then walk the
@@ -488,7 +488,7 @@ inline GridD nl_grid(const int ncell[3], const BoxD& box) {
 void nl_build(pfmds_ctx* c, NList& l) {
     const int N = c->N;
 #ifdef PFMDS_COOP
-    const bool warp_per_atom = N < 200000;  // measured: at 1e6 atoms the thread-per-atom scan is 2x faster, at 1e4 atoms 5x slower
+    const bool warp_per_atom = N < c->nl_warp_n;  // measured: at 1e6 atoms the thread-per-atom scan is 2x faster, at 1e4 atoms 5x slower
 #else
     const bool warp_per_atom = false;       // host replay: the warp-per-atom kernel compacts with ballots
 #endif

@@ -89,6 +89,7 @@ struct Slab {
     int wait_pos_seq = 0;
     int* rs[2]{nullptr, nullptr};   // per slot: ghost slot in the left / right neighbour, -1 otherwise
     unsigned int* counter = nullptr;
+    unsigned long long timeout_ns = 120000000000ull;  // spin-wait limit of the flag waits (PFMDS_SLAB_TIMEOUT_S)
     std::vector<void*> ipc_opened;
 };
 
@@ -279,14 +280,14 @@ __device__ __forceinline__ unsigned long long sl_now_ns() {
 #endif
     return t;
 }
-// wait until both neighbours have published at least `seq`; gives up after ~10 s and records an error instead of hanging
-__global__ void k_sl_wait(const int* from_left, const int* from_right, int seq, int* err) {
+// wait until both neighbours have published at least `seq`; gives up after `timeout_ns` and records an error instead of hanging
+__global__ void k_sl_wait(const int* from_left, const int* from_right, int seq, int* err, unsigned long long timeout_ns) {
     unsigned long long t0 = sl_now_ns();
     while (*reinterpret_cast<const volatile int*>(from_left) < seq || *reinterpret_cast<const volatile int*>(from_right) < seq) {
         if (*reinterpret_cast<volatile int*>(err) != 0) break;
         __nanosleep(200);
         unsigned long long t = sl_now_ns();
-        if (t - t0 > 3000000000ull) { raise_error(err, 31, seq, 0); break; }
+        if (t - t0 > timeout_ns) { raise_error(err, 31, seq, 0); break; }
     }
     __threadfence_system();
 }
@@ -407,6 +408,7 @@ void slab_init(pfmds_ctx* c, int rank, int nranks, const char* id128, long long 
     CK(cudaMalloc(&s->cnt_d, sizeof(int) * 16));
     CK(cudaMalloc(&s->scan_tmp, sizeof(int) * (S / 2048 + 2)));
     CK(cudaMalloc(&c->newslot, sizeof(int) * S));
+    if (const char* to = std::getenv("PFMDS_SLAB_TIMEOUT_S")) { double v = std::atof(to); if (v >= 1.) s->timeout_ns = (unsigned long long)(v * 1e9); }
     const char* env = std::getenv("PFMDS_SLAB_P2P");
     s->p2p = !(env && env[0] == '0') && slab_setup_p2p(c, s);
 }
@@ -440,6 +442,7 @@ SlabDev slab_dev(pfmds_ctx* c, int stage) {
     Slab* s = c->slab;
     SlabDev S{};
     S.err = c->err;
+    S.timeout_ns = s->timeout_ns;
     S.rs_l = s->rs[0]; S.rs_r = s->rs[1];
     S.peer_l = s->peer_pos[0][s->peer_parity[0]]; S.peer_r = s->peer_pos[1][s->peer_parity[1]];
     S.counter = s->counter;
@@ -578,7 +581,7 @@ void slab_exchange(pfmds_ctx* c, int field) {
             // positions: pushed by the kick+drift kernel itself when it was the fused variant, else pushed here; either way
             // the first density kernel waits for the neighbours' flag in its prologue
             if (!s->pos_pushed) {
-                LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 4, s->flags + 5, s->seq_done, c->err);
+                LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 4, s->flags + 5, s->seq_done, c->err, s->timeout_ns);
                 if (n > 0) LAUNCH((k_sl_push<0>), (n + T - 1) / T, T, c->st, nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
                 s->seq_pos += 1;
                 LAUNCH((k_sl_signal), 1, 1, c->st, s->peer_flags[0] + 1, s->peer_flags[1] + 0, s->seq_pos);
@@ -591,17 +594,17 @@ void slab_exchange(pfmds_ctx* c, int field) {
         }
         if (field == 0) {
             // my neighbours' force kernels of the previous step must be done with the old ghost positions
-            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 4, s->flags + 5, s->seq_done, c->err);
+            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 4, s->flags + 5, s->seq_done, c->err, s->timeout_ns);
             if (n > 0) LAUNCH((k_sl_push<0>), (n + T - 1) / T, T, c->st, nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
             s->seq_pos += 1;
             LAUNCH((k_sl_signal), 1, 1, c->st, s->peer_flags[0] + 1, s->peer_flags[1] + 0, s->seq_pos);   // I am my left neighbour's right neighbour
-            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 0, s->flags + 1, s->seq_pos, c->err);
+            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 0, s->flags + 1, s->seq_pos, c->err, s->timeout_ns);
             c->launches += 4;
         } else {
             if (n > 0) LAUNCH((k_sl_push<1>), (n + T - 1) / T, T, c->st, nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos);
             s->seq_w += 1;
             LAUNCH((k_sl_signal), 1, 1, c->st, s->peer_flags[0] + 3, s->peer_flags[1] + 2, s->seq_w);
-            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 2, s->flags + 3, s->seq_w, c->err);
+            LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 2, s->flags + 3, s->seq_w, c->err, s->timeout_ns);
             c->launches += 3;
         }
         CK(cudaGetLastError());

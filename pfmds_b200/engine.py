@@ -61,6 +61,7 @@ _SIGS = {
     "timers": [C.c_void_p, _dp],
     "upload": [C.c_void_p, _dp, _dp],
     "pair_count": [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_longlong)],
+    "pair_count_within": [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_longlong)],
     "set_profiling": [C.c_void_p, C.c_int],
     "kernel_times": [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_longlong)],
     "timer_start": [C.c_void_p],
@@ -74,7 +75,7 @@ _SIGS = {
 }
 
 
-_OPTIONAL = ("state_size", "save_state", "restore_state", "advance_with_energy", "upload", "pair_count", "set_profiling", "kernel_times", "timer_start", "timer_stop")  # product-only entry points
+_OPTIONAL = ("state_size", "save_state", "restore_state", "advance_with_energy", "upload", "pair_count", "pair_count_within", "set_profiling", "kernel_times", "timer_start", "timer_stop")  # product-only entry points
 
 
 def load_library(path=LIB_PATH, prefix="pfmds_"):
@@ -258,6 +259,11 @@ class Engine:
     def pair_count(self, interaction, lst):
         n = C.c_longlong()
         self._call("pair_count", self._ctx, interaction, lst, C.byref(n))
+        return n.value
+
+    def pair_count_within(self, interaction, lst, r):
+        n = C.c_longlong()
+        self._call("pair_count_within", self._ctx, interaction, lst, float(r), C.byref(n))
         return n.value
 
     def set_profiling(self, on):

@@ -308,6 +308,35 @@ MdResult md(Engine& eng, std::FILE* out, std::FILE* all_out, const std::string& 
             ck.integrator_index < 1 || ck.integrator_index > s.integrators_num)
             throw std::runtime_error("error: the checkpoint does not belong to this settings file");
         eng.restore_state(ck.pos.data(), ck.vel.data(), ck.blob);
+        {   // The interrupted run may have gone past the checkpoint: keep the header and the rows up to the checkpointed step, drop
+            // later rows and its final summary line, so that the continued log holds every row exactly once.
+            std::fclose(logf);
+            const std::string path = trim(output_prefix) + trim(s.logfilename);
+            std::vector<std::string> keep;
+            if (std::FILE* in = std::fopen(path.c_str(), "r")) {
+                std::string line;
+                bool rows_started = false;
+                auto flush = [&]() {
+                    if (line.size() >= 15) {
+                        std::string nm = trim(line.substr(0, 6));
+                        if (nm == "nve" || nm == "nvt" || nm == "nvms") {
+                            char* end = nullptr;
+                            const std::string num = line.substr(6, 9);
+                            long st = std::strtol(num.c_str(), &end, 10);
+                            if (end && *end == 0) { rows_started = true; if (st <= ck.md_step) keep.push_back(line); line.clear(); return; }
+                        }
+                    }
+                    if (!rows_started) keep.push_back(line);
+                    line.clear();
+                };
+                for (int ch; (ch = std::fgetc(in)) != EOF;) { if (ch == '\n') flush(); else line.push_back((char)ch); }
+                if (!line.empty()) flush();
+                std::fclose(in);
+            }
+            logf = std::fopen(path.c_str(), "w");
+            if (!logf) throw std::runtime_error("cannot open log file " + path);
+            for (auto& l : keep) std::fprintf(logf, "%s\n", l.c_str());
+        }
         md_step = (int)ck.md_step + 1;
         integrator_index = (int)ck.integrator_index;
         integrator_name = s.integrators[integrator_index].int_name;

@@ -30,8 +30,8 @@ def test_time_variant_on_the_host_replay(oracle_lib, monkeypatch):
 
 
 def test_mask_list_build_on_the_host_replay(oracle_lib, monkeypatch):
-    """PFMDS_NL_MASK=1 (nl.cu k_build_mask) on the serial host replay, which takes the thread-per-atom build for every size: rows and
-    forces identical to the default build, bit for bit, through partial rebuilds (lists of different periods, no re-sort) too."""
+    """k_build_mask (nl.cu, the default; PFMDS_NL_MASK=0 selects k_build) on the serial host replay, which takes the thread-per-atom build for every size: rows and
+    forces identical to k_build, bit for bit, through partial rebuilds (lists of different periods, no re-sort) too."""
     import numpy as np
     import build_emu as B
     from pfmds_b200.engine import configure
@@ -42,9 +42,9 @@ def test_mask_list_build_on_the_host_replay(oracle_lib, monkeypatch):
     gr["interactions"][2]["lists"] = [(2, 2, 100, 6.5, 7)]
     for case, integ, dt in ((inputs.cu_fcc(ncell=4, jitter=0.05, period=5), "nvt", 2.0), (gr, "nvt", 1.0),
                             (inputs.ab_gas(n_side=6, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, period=5), "nvt", 0.5)):
-        monkeypatch.delenv("PFMDS_NL_MASK", raising=False)
+        monkeypatch.setenv("PFMDS_NL_MASK", "0")     # k_build
         a = configure(case, lib_path=B.LIB)
-        monkeypatch.setenv("PFMDS_NL_MASK", "1")
+        monkeypatch.setenv("PFMDS_NL_MASK", "1")     # k_build_mask (the default)
         b = configure(case, lib_path=B.LIB)
         monkeypatch.delenv("PFMDS_NL_MASK")
         for e in (a, b):
@@ -68,7 +68,7 @@ def test_variants_child_on_the_host_replay(oracle_lib, monkeypatch, capsys):
     monkeypatch.setattr(E, "configure", lambda case, device=0, **kw: orig(case, lib_path=B.LIB))
     assert bench.run_variants(0, small=True) == 0
     rows = [json.loads(l) for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
-    assert len(rows) == 11 and all(len(b) == len(a) + 1 for a, b in zip(rows, rows[1:]))
+    assert len(rows) == 9 and all(len(b) == len(a) + 1 for a, b in zip(rows, rows[1:]))
     last = rows[-1]
     bad = {k: v for k, v in last.items() if k != "note" and "error" in v}
     assert not bad, bad

@@ -148,11 +148,12 @@ def test_anchors(fn):
 
 
 def test_pipelined_lj1g_variant(monkeypatch, flavour):
-    """PFMDS_LJ1G_PIPE=1 through the C ABI (the serial replay always takes the thread-per-atom kernels)."""
+    """The pipelined lj1g kernel (default) against the plain one (PFMDS_LJ1G_PIPE=0) through the C ABI (the serial replay always takes the thread-per-atom kernels)."""
     if flavour == "lockstep":
         pytest.skip("512 atoms take the 8-lanes-per-atom kernel in the lock-step replay, as on the GPU: the variant is not selected")
     from util import oracle, rel_err
     case = inputs.lj_fluid(n_side=8, period=5)
+    monkeypatch.setenv("PFMDS_LJ1G_PIPE", "0")
     a = emu_gpu(case)
     monkeypatch.setenv("PFMDS_LJ1G_PIPE", "1")
     b = emu_gpu(case)
@@ -163,17 +164,6 @@ def test_pipelined_lj1g_variant(monkeypatch, flavour):
     fa, fb, fo = a.download()[2], b.download()[2], o.download()[2]
     assert rel_err(fb, fo) < 1e-9 and rel_err(fb, fa) < 1e-11 and not np.array_equal(fa, fb)     # a different kernel did run
     assert np.abs(b.download()[0] - o.download()[0]).max() < 1e-10
-
-
-def test_rjl_minb_switch(monkeypatch):
-    """PFMDS_RJL_MINB=5 selects another instantiation of the same force kernel: same bits (replayed from the GPU test with a small crystal)."""
-    case = inputs.cu_fcc(ncell=5, jitter=0.05, period=5)
-    a = emu_gpu(case)
-    monkeypatch.setenv("PFMDS_RJL_MINB", "5")
-    b = emu_gpu(case)
-    for e in (a, b):
-        e.advance("nvt", 2.0, 0, 7)
-    assert np.array_equal(a.download()[2], b.download()[2]) and np.abs(a.download()[2]).max() > 0.05
 
 
 def test_replay_identifies_itself():

@@ -15,10 +15,14 @@ def _libs(cuda_lib, oracle_lib):
     return None
 
 
+PATH_IDS = ["small", "large", "large_build"]   # util.PATHS: which side of the size switches the context takes
+
+
+@pytest.mark.parametrize("path", PATH_IDS)
 @pytest.mark.parametrize("name", list(CASES))
-def test_step0_lists_forces_energies(name):
+def test_step0_lists_forces_energies(name, path):
     case = CASES[name]
-    g, o = gpu(case), oracle(case)
+    g, o = gpu(case, path), oracle(case)
     g.advance("nve", 1.0, 0, 1)
     o.advance("nve", 1.0, 0, 1)
     for k, j in list_ids(case):
@@ -44,13 +48,14 @@ def test_step0_lists_forces_energies(name):
             assert np.abs(g.normals(k) - o.normals(k)).max() < 1e-12
 
 
+@pytest.mark.parametrize("path", ["small", "large"])
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("integrator", ["nve", "nvt", "nvms"])
-def test_trajectory_22_steps(name, integrator):
+def test_trajectory_22_steps(name, integrator, path):
     """Steps 0..21 with rebuilds at 0,5,10,15,20: state, lists and energies stay within tolerance."""
     case = CASES[name]
     dt = case["integrators"][0][1]
-    g, o = gpu(case), oracle(case)
+    g, o = gpu(case, path), oracle(case)
     for e in (g, o):
         e.advance(integrator, dt, 0, 1)
         e.advance(integrator, dt, 1, 21)
@@ -151,13 +156,14 @@ def test_device_math_functions():
     assert err[0] < 1e-14 and err[1] < 2e-14 and err[2] < 3e-12 and err[3] < 4e-14
 
 
+@pytest.mark.parametrize("path", ["small", "large"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_gpu_matches_golden_fixtures(name):
+def test_gpu_matches_golden_fixtures(name, path):
     """Against the committed fixtures (tests/golden/, frozen oracle outputs): lists bit-exact, forces/energies 1e-9."""
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
     case = CASES[name]
-    e = gpu(case)
+    e = gpu(case, path)
     integ, dt = case["integrators"][0][0], case["integrators"][0][1]
     e.advance(integ, dt, 0, 1)
     assert rel_err(e.download()[2], g["frc0"]) < RTOL
@@ -257,12 +263,19 @@ def test_nve_energy_drift_over_10k_steps(name):
     assert abs(dg[:1] - dc[:1]).max() < 1e-6 * ke0                             # still the same trajectory after 10^3 steps
 
 
+@pytest.mark.parametrize("path", ["small", "large"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_energies_from_the_force_pass(name):
-    """pfmds_advance_with_energy: the potential energies produced inside the last step's force pass equal the separate sweep."""
+def test_energies_from_the_force_pass(name, path):
+    """pfmds_advance_with_energy: the potential energies produced inside the last step's force pass equal the separate sweep
+    (and, large path, the oracle's: k_rjl_force_e / k_lj1g_pipe<E> / k_lj<.,E,1> on hardware)."""
     case = CASES[name]
     integ, dt = case["integrators"][0][0], case["integrators"][0][1]
-    a, b = gpu(case), gpu(case)
+    a, b = gpu(case, path), gpu(case, path)
+    o = oracle(case)
+    o.advance(integ, dt, 0, 1)
+    c = gpu(case, path)
+    c.advance(integ, dt, 0, 1, with_energy=True)
+    assert np.allclose(c.energies()[0], o.energies()[0], rtol=RTOL, atol=0)
     a.advance(integ, dt, 0, 7, with_energy=True)
     b.advance(integ, dt, 0, 7)
     ea, eb = a.energies(), b.energies()
@@ -289,13 +302,14 @@ def test_store_instead_of_zero_plus_accumulate():
     assert np.abs(fa).max() > 0.1
 
 
+@pytest.mark.parametrize("path", ["small", "large"])
 @pytest.mark.parametrize("name", ["ab_gas", "cu_fcc", "gr_cu_ljc"])
-def test_advance_logged_rows(name):
+def test_advance_logged_rows(name, path):
     """pfmds_advance_logged: the device-resident energy log returns, bit for bit, what advance_with_energy(1) + energies() give
     step by step, and leaves the same state; against the oracle the rows agree to 1e-9."""
     case = CASES[name]
     integ, dt = case["integrators"][0][0], case["integrators"][0][1]
-    a, b, o = gpu(case), gpu(case), oracle(case)
+    a, b, o = gpu(case, path), gpu(case, path), oracle(case)
     for e in (a, b, o):
         e.advance(integ, dt, 0, 1)
     rows = a.advance_logged(integ, dt, 1, 12, log_period=3)
@@ -347,3 +361,59 @@ def test_rjl_in_a_box_narrower_than_twice_R2():
     for e in (g, o):
         e.advance("nvt", 2.0, 1, 12)
     assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-12
+
+
+def _check_steps_0_1_20_21(case, path, integ, dt, lists_every_time=True):
+    """parity at steps 0, 1, 20, 21 (update_period 20: rebuilds at 0 and 20).  Neighbour sets bit-exact, per-atom
+    forces and energies within 1e-9 relative at each of those steps."""
+    g, o = gpu(case, path), oracle(case)
+    at = 0
+    for upto in (0, 1, 20, 21):
+        for e in (g, o):
+            e.advance(integ, dt, at, upto + 1 - at)
+        at = upto + 1
+        fg, fo = g.download()[2], o.download()[2]
+        assert np.abs(fo).max() > 1e-3
+        assert rel_err(fg, fo) < RTOL, "forces at step %d" % upto
+        eg, eo = g.energies(), o.energies()
+        assert np.allclose(eg[0], eo[0], rtol=RTOL, atol=0), "energies at step %d" % upto
+        assert abs(eg[1] - eo[1]) <= RTOL * abs(eo[1])
+        if lists_every_time or upto in (0, 20):
+            for k, j in list_ids(case):
+                a, b = neighbours(g, case, k, j), neighbours(o, case, k, j)
+                assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]), "list %d/%d at step %d" % (k, j, upto)
+                if j == 0:
+                    assert np.array_equal(a[2], b[2])
+    assert np.abs(g.download()[0] - o.download()[0]).max() < 1e-9
+    g.close()
+
+
+@pytest.mark.parametrize("path", ["small", "large"])
+def test_config0_ab_gas_at_its_stated_size(path):
+    """BASELINE.json configs[0] at its stated 22^3 = 10 648 atoms: lj + 2 x lj1g, nvt."""
+    from pfmds_b200 import inputs
+    case = inputs.ab_gas()
+    assert len(case["mass"]) == 10648
+    _check_steps_0_1_20_21(case, path, "nvt", case["integrators"][0][1])
+
+
+@pytest.mark.parametrize("path", ["small", "large"])
+def test_config2_graphene_on_cu_at_its_stated_size(path):
+    """BASELINE.json configs[2] at its stated 11 028 atoms: tb + ljc + rjl, nvt."""
+    from pfmds_b200 import inputs
+    case = inputs.graphene_on_cu()
+    assert len(case["mass"]) == 11028
+    period = case["interactions"][0]["lists"][0][4]
+    assert 20 % period == 0
+    _check_steps_0_1_20_21(case, path, "nvt", case["integrators"][0][1])
+
+
+def test_config1_kernels_on_a_108000_atom_crystal():
+    """The kernels BASELINE.json configs[1] is timed on (k_rjl_density / k_rjl_force / k_rjl_force_e, k_build_mask, thread per atom,
+    zero_forces fused away, no CUDA graphs... exactly what a 10^6-atom run launches) on the largest jittered crystal the O(N^2)
+    oracle handles in tens of seconds: 30^3 cells = 108 000 atoms, default switches (108 000 >= small_n; the list build is
+    forced to the thread-per-atom kernel, which the default takes from 200 000 atoms up)."""
+    from pfmds_b200 import inputs
+    case = inputs.cu_fcc(ncell=30, jitter=0.03, period=20)
+    assert len(case["mass"]) == 108000
+    _check_steps_0_1_20_21(case, {"PFMDS_NL_WARP_N": "0"}, "nvt", 2.0, lists_every_time=False)

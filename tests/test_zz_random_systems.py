@@ -28,7 +28,14 @@ def _lockstep(case):
     return configure(case, lib_path=B.LOCKSTEP.lib)
 
 
-ENGINES = [pytest.param(_serial, id="serial-replay"), pytest.param(_lockstep, id="lockstep-replay"), pytest.param(gpu, id="gpu", marks=pytest.mark.gpu)]
+def _gpu_large(case):
+    """The GPU with the size switches at zero: the thread-per-atom pipelined pair kernels and the thread-per-atom list build,
+    i.e. the kernels the 10^6-atom bench times (util.PATHS)."""
+    return gpu(case, "large")
+
+
+ENGINES = [pytest.param(_serial, id="serial-replay"), pytest.param(_lockstep, id="lockstep-replay"), pytest.param(gpu, id="gpu", marks=pytest.mark.gpu),
+           pytest.param(_gpu_large, id="gpu-large-path", marks=pytest.mark.gpu)]
 
 
 @pytest.fixture(scope="module", autouse=True)

@@ -11,8 +11,29 @@ ORACLE = dict(lib_path=os.path.join(ROOT, "oracle", "_build", "liboracle.so"), p
 RTOL = 1e-9  # north_star: per-atom forces and total energies within 1e-9 relative in FP64
 
 
-def gpu(case):
-    return configure(case)
+# Which side of the library's size switches a context takes (pfmds_ctx::small_n, nl_warp_n; read from the environment at
+# pfmds_create).  "large" drives a SMALL system through the kernels the 10^6-atom bench times: thread-per-atom pipelined pair
+# kernels (k_rjl_force / k_rjl_density / k_rjl_force_e / k_lj1g_pipe, zero_forces fused away) and the thread-per-atom list build
+# (k_build_mask; "large_build" = k_build), so that they meet the O(N^2) oracle on hardware.
+PATHS = {
+    "small": {},
+    "large": {"PFMDS_SMALL_N": "0", "PFMDS_NL_WARP_N": "0"},
+    "large_build": {"PFMDS_SMALL_N": "0", "PFMDS_NL_WARP_N": "0", "PFMDS_NL_MASK": "0", "PFMDS_LJ1G_PIPE": "0"},
+}
+
+
+def gpu(case, path="small", **kw):
+    env = PATHS[path] if isinstance(path, str) else dict(path)
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return configure(case, **kw)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def oracle(case):
