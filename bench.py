@@ -313,6 +313,8 @@ def run_variants(local, small=False):
             out["device_math"] = {"error": repr(ex)[:300]}
     for name, cs, integ, h, env in (
             ("cu_fcc defaults", case, integrator, dt, {}),
+            ("cu_fcc, rjl third generation with the force kernel held to 8 blocks/SM (PFMDS_RJL_MINB=8: 64 registers)", case, integrator, dt, {"PFMDS_RJL_MINB": "8"}),
+            ("cu_fcc, rjl second generation (PFMDS_RJL_GEN=2: analytic exponentials)", case, integrator, dt, {"PFMDS_RJL_GEN": "2"}),
             ("cu_fcc, rjl first generation (PFMDS_RJL_GEN=1, the round-1 kernels)", case, integrator, dt, {"PFMDS_RJL_GEN": "1"}),
             ("cu_fcc, list build with the exact test inside the candidate loop (PFMDS_NL_MASK=0, k_build): compare nl_build", case, integrator, dt, {"PFMDS_NL_MASK": "0"}),
             ("lj_fluid 96^3 lj1g defaults (pipelined kernel)", ljc, "nve", ljc["integrators"][0][1], {}),

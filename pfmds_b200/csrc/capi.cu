@@ -56,7 +56,9 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     c->use_graphs = !slab && env_int("PFMDS_GRAPHS", n_atoms < 200000 ? 1 : 0) == 1;
     c->lj1g_pipe = env_int("PFMDS_LJ1G_PIPE", 1) != 0;
     c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
-    c->rjl_gen = env_int("PFMDS_RJL_GEN", 2) == 1 ? 1 : 2;
+    c->rjl_gen = env_int("PFMDS_RJL_GEN", 3);
+    if (c->rjl_gen < 1 || c->rjl_gen > 3) c->rjl_gen = 3;
+    c->rjl_minb = env_int("PFMDS_RJL_MINB", 7) == 8 ? 8 : 7;
 #ifdef PFMDS_COOP
     c->small_n = env_int("PFMDS_SMALL_N", 100000);
     c->nl_warp_n = env_int("PFMDS_NL_WARP_N", 200000);
@@ -175,6 +177,7 @@ void finalize_slab(pfmds_ctx* c) {
     if (!c->inter.empty()) CK(cudaMalloc(&c->energy, sizeof(double) * c->inter.size()));
     alloc_log(c);
     check_rjl_generation(c);
+    for (auto& it : c->inter) rjl_prepare(c, it);
     c->first_overwrites = !c->inter.empty() && c->inter[0].kind == K_RJL && group_size(c, c->inter[0].nl[0].g1) == slab_n_global(c);
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
@@ -321,6 +324,7 @@ void finalize(pfmds_ctx* c) {
     }
     alloc_log(c);
     check_rjl_generation(c);
+    for (auto& it : c->inter) rjl_prepare(c, it);
     c->first_overwrites = c->zero_all && c->changes.empty() && !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));

@@ -31,7 +31,7 @@ struct Inter {
     int nl_n = 0;
     NList nl[3];
     LJp lj{}; LJ1Gp lj1g{}; LJCp ljc{}; MORp mor{}; TBp tb{}; RJLp rjl{}; REBp reb{};
-    double* aux = nullptr;    // tb: bond orders B, ELL [maxn][stride]  (rjl keeps 1/Eb in pos[].w)
+    double* aux = nullptr;    // tb: bond orders B, ELL [maxn][stride];  rjl: node table of the third-generation routines (double2 entries; 1/Eb lives in pos[].w)
     double* aux2 = nullptr;   // tb: B^(1/delt+1)
     double4* fpart = nullptr; // tb: per-(slot, atom) force contributions, summed per atom in slot order
     double4* gnorm = nullptr; // ljc/morsec: unit normal per carbon atom {nx,ny,nz,-}
@@ -95,7 +95,8 @@ struct pfmds_ctx {
     struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid; cudaGraphExec_t exec; long long launches; };
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
-    int rjl_gen = 2;                // rjl pair routines: 2 = second generation (forces.cu), 1 = first (PFMDS_RJL_GEN=1)
+    int rjl_minb = 7;               // blocks/SM the third-generation rjl force kernels are compiled for: 7 (72 registers) or 8 (64; PFMDS_RJL_MINB=8)
+    int rjl_gen = 3;                // rjl pair routines: 3 = node-table exponentials (forces.cu), 2 = analytic short forms, 1 = first generation (PFMDS_RJL_GEN)
     bool nl_mask = true;            // thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (measured 8 % faster, BENCH_r01); PFMDS_NL_MASK=0: k_build
     bool lj1g_pipe = true;          // pipelined lj1g force kernel for systems of small_n atoms and more (measured 0.174 -> 0.102 ms, BENCH_r01); PFMDS_LJ1G_PIPE=0: k_lj1g
     // Path switches by system size.  Runtime fields (PFMDS_SMALL_N, PFMDS_NL_WARP_N) so that the parity tests can drive
@@ -170,6 +171,7 @@ long long slab_n_global(pfmds_ctx* c);
 
 // ---- forces.cu ----
 void forces_zero(pfmds_ctx* c);
+void rjl_prepare(pfmds_ctx* c, Inter& it);  // third-generation rjl: node table of the exponentials, built once
 void forces_interaction(pfmds_ctx* c, int k, bool with_energy);
 void normals_interaction(pfmds_ctx* c, int k);
 void energy_interaction(pfmds_ctx* c, int k);  // result in c->energy[k]

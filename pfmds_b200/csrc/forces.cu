@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
+#include <vector>
 
 #if defined(__CUDACC__) || defined(PFMDS_EMU_LIB)
 #include "ctx.hpp"
@@ -146,7 +148,13 @@ __global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ 
 //   pass 2  F_i -= [2 A0 (p/r0 f_c - f_c'/r r) e^{-p t} - xi (q/r0 f_c - f_c'/r r/2)(1/Eb_i + 1/Eb_j) e^{-2q t}]/r dr
 // Rows are class-partitioned at build time (r < R1 | switch zone | beyond R2, nl.cu k_partition) so the
 // lanes of a warp take the same branch; in a crystal the shells line up exactly.
-struct RjlC { double R1, R22, R12, qa, qb, pa, pb, A0, xi, a1, a2, sw, pi_sw; static constexpr bool padded = false; };
+struct RjlC {
+    double R1, R22, R12, qa, qb, pa, pb, A0, xi, a1, a2, sw, pi_sw;
+    static constexpr bool padded = false;
+    // row epilogue of the density pass: 1/Eb from the row sum, and the owner's energy A0 sum_p - xi Eb
+    __device__ __forceinline__ double inv_eb(double sq) const { return sq > 0. ? mx::rsqrt_fast(sq) : 0.; }
+    __device__ __forceinline__ double energy(double sq, double sp, double ie) const { return A0 * sp - xi * (sq * ie); }
+};
 // exp arguments are affine in r: -2q(r/r0-1) = qa r + qb, -p(r/r0-1) = pa r + pb
 static RjlC rjl_consts(const RJLp& P) {
     RjlC c;
@@ -200,7 +208,12 @@ __device__ __forceinline__ void wrap3(double& dx, double& dy, double& dz, const 
 //     f + sin(a) k_p and f + sin(a) k_q (k = -pi/(2 (R2-R1)) / slope of the exponent): see rjl_force_consts;
 //   * the density pass needs the value of the switch only: one odd polynomial in a - pi/2 (half_switch).
 // Per pair of the common class: 43 FP64 instructions in the force pass (57 before), 25 in the density pass (37 before).
-struct RjlD { double R22, R12, qa, qb, pa, pb, sw, y0, A0, xi; static constexpr bool padded = true; };
+struct RjlD {
+    double R22, R12, qa, qb, pa, pb, sw, y0, A0, xi;
+    static constexpr bool padded = true;
+    __device__ __forceinline__ double inv_eb(double sq) const { return sq > 0. ? mx::rsqrt_fast(sq) : 0.; }
+    __device__ __forceinline__ double energy(double sq, double sp, double ie) const { return A0 * sp - xi * (sq * ie); }
+};
 struct RjlF { double R22, R12, qa, qb, pa, pb, swh, u0, kp, kq, l2e, nln2; static constexpr bool padded = true; };
 // the second generation needs positive prefactors (their logarithms) and R2 inside the half box
 static bool rjl_gen2_ok(const RJLp& P, const BoxD& b) {
@@ -307,6 +320,172 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
     rjl_force_pair_g2<false>(pi, pj, C, box, mhh, fx, fy, fz, unused);
 }
 
+// ---- rjl, third generation pair routines (default; PFMDS_RJL_GEN=2 / 1 select the older ones) ---------------------------------
+// ncu on the second generation (profiles/r2a_*): still bound by FP64 issue, 24 of the 43 FP64 instructions of a common-class pair
+// are the two exponentials (two range reductions by ln 2 and two degree-8 polynomials).  Both exponents are affine in the SAME r,
+// so one range reduction serves both: r = r_J + d with r_J = J g the nearest node of a grid of spacing g = 2^-m (J from the
+// 1.5 x 2^52 rounding trick, d exact), and
+//     a1 e^{pa r + pb} = [a1 e^{pa r_J + pb}] e^{pa d},   a2 e^{qa r + qb} = [a2 e^{qa r_J + qb}] e^{qa d}
+// with the bracketed node values read from a table in global memory (16 bytes per node, a few tens of KB: L1 resident) and
+// e^{x} for |x| <= max(|pa|,|qa|) g/2 <= 0.0045 from its degree-4 Taylor polynomial (truncation x^5/120 <= 1.6e-14 relative;
+// the table entries are rounded from long double).  11 FP64 instructions replace 24: 30 per common-class pair in the force
+// pass, 19 in the density pass.  Pairs closer than the table's first node (r < r_lo ~ 0.7 r0: none in a solid or liquid at any
+// temperature MD is run at) take the second generation's analytic routine, so the result is defined for every input.
+struct RjlG {
+    double R22, R12;
+    double inv_g, ng;             // 1/g and -g
+    double cp1, cp2, cp3, cp4;    // pa^n / n!
+    double cq1, cq2, cq3, cq4;    // qa^n / n!
+    double swh, u0, kp, kq;       // force pass, switch zone (as RjlF)
+    double sw, y0;                // density pass, value-only switch (as RjlD)
+    double inv_a2, erep, xi;      // density epilogue: the table carries a2 e_q and a1 e_p; sum e_q = sq inv_a2, A0 sum e_p = erep sp
+    const double2* tab;           // biased by -J_lo entries: tab[J] = {a1 e^{pa r_J + pb}, a2 e^{qa r_J + qb}}
+    int J_lo;                     // first node of the table
+    double pa, pb, qa, qb, l2e, nln2;  // exponents with the prefactors folded in (as RjlF): analytic exponentials for r below the table
+    static constexpr bool padded = true;
+    __device__ __forceinline__ double inv_eb(double sq) const { sq *= inv_a2; return sq > 0. ? mx::rsqrt_fast(sq) : 0.; }
+    __device__ __forceinline__ double energy(double sq, double sp, double ie) const { return erep * sp - xi * ((sq * inv_a2) * ie); }
+};
+#define RJL_TAB_MAGIC 6755399441055744.0  // 1.5 x 2^52: fma(r, 1/g, MAGIC) rounds r/g to an integer held in the low word
+__device__ __forceinline__ double2 rjl_tab_load(const double2* p) {
+#ifdef __CUDA_ARCH__
+    double2 v;
+    asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+template <bool E>
+__device__ __forceinline__ void rjl_force_pair_g3(const double4& pi, const double4& pj, const RjlG& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                                  double& fz, double& se) {
+    double dx, dy, dz, r2;
+    if (pair_inside(pi, pj, C.R22, box, mhh, dx, dy, dz, r2)) {
+        double ir = mx::rsqrt_q(r2);
+        double r = r2 * ir;
+        const double u = fma(r, C.inv_g, RJL_TAB_MAGIC);
+        const int J = mx::lo_word(u);
+        double A, eq;
+        if (J >= C.J_lo) {
+            const double2 T = rjl_tab_load(C.tab + J);
+            const double d = fma(u - RJL_TAB_MAGIC, C.ng, r);
+            double Pp = fma(fma(fma(fma(C.cp4, d, C.cp3), d, C.cp2), d, C.cp1), d, 1.0);
+            double Pq = fma(fma(fma(fma(C.cq4, d, C.cq3), d, C.cq2), d, C.cq1), d, 1.0);
+            A = T.x * Pp; eq = T.y * Pq;
+        } else {  // closer than the table's first node (never in a condensed phase): both exponentials analytically
+            mx::exp_m2(fma(C.pa, r, C.pb), fma(C.qa, r, C.qb), A, eq, C.l2e, C.nln2);
+        }
+        double w = pi.w + pj.w;
+        if (!(r2 < C.R12)) {
+#ifdef __CUDA_ARCH__
+            asm volatile("");  // keeps this a branch (rows are class-partitioned: warp-uniform in a crystal)
+#endif
+            double f, sn;
+            mx::cos_switch_m(fma(r, C.swh, C.u0), f, sn);
+            if (E) se = fma(A, f, se);
+            A *= fma(sn, C.kp, f);
+            w *= fma(sn, C.kq, f);
+        } else if (E) se += A;
+        double c = fma(-w, eq, A) * ir;
+        fx = fma(-c, dx, fx); fy = fma(-c, dy, fy); fz = fma(-c, dz, fz);
+    }
+}
+__device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlG& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                               double& fz) {
+    double unused = 0.;
+    rjl_force_pair_g3<false>(pi, pj, C, box, mhh, fx, fy, fz, unused);
+}
+template <bool E>
+__device__ __forceinline__ void rjl_force_pair_e(const double4& pi, const double4& pj, const RjlF& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                                 double& fz, double& se) {
+    rjl_force_pair_g2<E>(pi, pj, C, box, mhh, fx, fy, fz, se);
+}
+template <bool E>
+__device__ __forceinline__ void rjl_force_pair_e(const double4& pi, const double4& pj, const RjlG& C, const BoxD& box, int mhh, double& fx, double& fy,
+                                                 double& fz, double& se) {
+    rjl_force_pair_g3<E>(pi, pj, C, box, mhh, fx, fy, fz, se);
+}
+template <bool E>
+__device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlG& C, const BoxD& box, int mhh, double& sq, double& sp) {
+    double dx, dy, dz, r2;
+    if (pair_inside(pi, pj, C.R22, box, mhh, dx, dy, dz, r2)) {
+        double r = r2 * mx::rsqrt_q(r2);
+        const double u = fma(r, C.inv_g, RJL_TAB_MAGIC);
+        const int J = mx::lo_word(u);
+        double Pq, Pp = 0., tp = 0., tq;   // a2 e_q = tq Pq, a1 e_p = tp Pp
+        if (J >= C.J_lo) {
+            const double d = fma(u - RJL_TAB_MAGIC, C.ng, r);
+            Pq = fma(fma(fma(fma(C.cq4, d, C.cq3), d, C.cq2), d, C.cq1), d, 1.0);
+            if (E) {
+                const double2 T = rjl_tab_load(C.tab + J);
+                tp = T.x; tq = T.y;
+                Pp = fma(fma(fma(fma(C.cp4, d, C.cp3), d, C.cp2), d, C.cp1), d, 1.0);
+            } else {
+#ifdef __CUDA_ARCH__
+                asm("ld.global.nc.f64 %0, [%1];" : "=d"(tq) : "l"(reinterpret_cast<const double*>(C.tab + J) + 1));
+#else
+                tq = C.tab[J].y;
+#endif
+            }
+        } else {  // closer than the table's first node: analytic exponentials, in the table's units
+            mx::exp_m2(fma(C.pa, r, C.pb), fma(C.qa, r, C.qb), tp, tq, C.l2e, C.nln2);
+            Pq = 1.; Pp = 1.;
+        }
+        if (r2 < C.R12) {
+            sq = fma(tq, Pq, sq);
+            if (E) sp = fma(tp, Pp, sp);
+        } else {
+            double f = mx::half_switch(fma(r, C.sw, C.y0));
+            sq = fma(tq * Pq, f, sq);
+            if (E) sp = fma(tp * Pp, f, sp);
+        }
+    }
+}
+
+// Node table of the third generation: spacing, range and entries (host side; pure arithmetic, shared with tests/forces_host.cpp).
+struct RjlTabSpec { int m, J_lo, J_hi; double g; };
+static bool rjl_gen3_ok(const RJLp& P, const BoxD& b) { return rjl_gen2_ok(P, b) && P.r0 > 0. && P.R2 > 0.; }
+static RjlTabSpec rjl_tab_spec(const RJLp& P) {
+    const RjlC c = rjl_consts(P);
+    const double X = fmax(fabs(c.pa), fabs(c.qa));
+    RjlTabSpec t;
+    t.m = 0;
+    while (X * ldexp(1., -t.m) * 0.5 > 0.0045 && t.m < 24) ++t.m;   // degree-4 Taylor of e^x on |x| <= X g / 2: x^5/120 <= 1.6e-14
+    t.g = ldexp(1., -t.m);
+    double r_lo = 0.7 * P.r0;
+    if (r_lo > 0.5 * P.R2) r_lo = 0.5 * P.R2;
+    if (P.R2 - r_lo > 8192. * t.g) r_lo = P.R2 - 8192. * t.g;      // at most 128 KB of table
+    t.J_lo = (int)floor(r_lo / t.g);
+    if (t.J_lo < 1) t.J_lo = 1;
+    t.J_hi = (int)ceil(P.R2 / t.g) + 2;
+    return t;
+}
+static void rjl_tab_fill(const RJLp& P, const RjlTabSpec& t, double2* out) {  // out[J - J_lo], J_lo <= J <= J_hi
+    const long double a1 = 2.0L * P.A0 * P.p / P.r0, a2 = (long double)P.xi * P.q / P.r0;
+    for (int J = t.J_lo; J <= t.J_hi; ++J) {
+        const long double x = (long double)J * t.g / P.r0 - 1.0L;
+        out[J - t.J_lo].x = (double)(a1 * expl(-(long double)P.p * x));
+        out[J - t.J_lo].y = (double)(a2 * expl(-2.0L * P.q * x));
+    }
+}
+static RjlG rjl_g3_consts(const RJLp& P, const RjlTabSpec& t, const double2* tab) {  // tab = the filled table (device or host memory)
+    const RjlC c = rjl_consts(P);
+    RjlG G;
+    const RjlF f2 = rjl_force_consts(P);
+    const RjlD d2 = rjl_dens_consts(P);
+    G.pa = f2.pa; G.pb = f2.pb; G.qa = f2.qa; G.qb = f2.qb; G.l2e = f2.l2e; G.nln2 = f2.nln2;
+    G.R22 = c.R22; G.R12 = c.R12;
+    G.inv_g = ldexp(1., t.m); G.ng = -t.g;
+    G.cp1 = c.pa; G.cp2 = c.pa * c.pa / 2.; G.cp3 = c.pa * c.pa * c.pa / 6.; G.cp4 = c.pa * c.pa * c.pa * c.pa / 24.;
+    G.cq1 = c.qa; G.cq2 = c.qa * c.qa / 2.; G.cq3 = c.qa * c.qa * c.qa / 6.; G.cq4 = c.qa * c.qa * c.qa * c.qa / 24.;
+    G.swh = f2.swh; G.u0 = f2.u0; G.kp = f2.kp; G.kq = f2.kq;
+    G.sw = d2.sw; G.y0 = d2.y0;
+    G.inv_a2 = 1. / c.a2; G.erep = c.A0 / c.a1; G.xi = c.xi;
+    G.tab = tab - t.J_lo;
+    G.J_lo = t.J_lo;
+    return G;
+}
+
 template <bool E>
 __device__ __forceinline__ void rjl_density_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& sq, double& sp) {
     double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
@@ -378,7 +557,7 @@ __global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* 
             j1 = j3;
         }
         if (p < n) rjl_density_pair<E>(pi, a, C, box, W.min_half_hi, sq, sp);
-        double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
+        double ie = C.inv_eb(sq);
         reinterpret_cast<double*>(&pos[i])[3] = ie;
         if (S.push) {  // the same 1/Eb goes straight into the ghost copies of this atom on the neighbour GPUs (NVLink stores)
             int a = S.rs_l[i], b = S.rs_r[i];
@@ -386,7 +565,7 @@ __global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* 
             if (b >= 0) reinterpret_cast<double*>(&S.peer_r[b])[3] = ie;
             pushed = (a >= 0) || (b >= 0);
         }
-        if (E) e = C.A0 * sp - C.xi * (sq * ie);
+        if (E) e = C.energy(sq, sp, ie);
     }
     if (E) store_partial(e, part);
     slab_signal(S, pushed);
@@ -405,9 +584,9 @@ __global__ void __launch_bounds__(FT) k_rjl_density_split(int N, double4* pos, L
     sq = split_sum<SPLIT>(sq);
     if (E) sp = split_sum<SPLIT>(sp);
     if (n > 0 && sub == 0) {
-        double ie = sq > 0. ? mx::rsqrt_fast(sq) : 0.;
+        double ie = C.inv_eb(sq);
         reinterpret_cast<double*>(&pos[i])[3] = ie;
-        if (E) e = C.A0 * sp - C.xi * (sq * ie);
+        if (E) e = C.energy(sq, sp, ie);
     }
     if (E) store_partial(e, part);
 }
@@ -436,8 +615,8 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
 }
 // RJL_MINB = blocks per SM the register allocation is held to.  7 (72 registers) is the measured optimum; 5 (94 registers, no
 // constant reloads in the loop, 20 instead of 28 resident warps) measured slower on a B200 (0.425 against 0.358 ms, BENCH_r01).
-template <class CT>  // CT = RjlC (first generation) or RjlF (second generation)
-__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
+template <class CT, int MB = RJL_MINB>  // CT = RjlC (first generation), RjlF (second) or RjlG (third: also instantiated for 8 blocks/SM = 64 registers, PFMDS_RJL_MINB=8)
+__global__ void __launch_bounds__(FT, MB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                       WrapC W, SlabDev S, int overwrite) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);  // slab mode: the neighbours' 1/Eb have landed in my ghost slots
@@ -482,7 +661,8 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __
 // Force pass that also yields the interaction's energy (second generation only; steps that report their energies):
 // e_i = (r0 / 2p) sum_j a1 e_p f  -  xi sqrt(sum_j e_q f),  the square root being 1 / (1/Eb_i) from the density pass.
 // Same row walk and pair routine as k_rjl_force; no early exits, every thread reaches the block sum.
-__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlF C, BoxD box,
+template <class CT, int MB = RJL_MINB>  // RjlF (second generation) or RjlG (third)
+__global__ void __launch_bounds__(FT, MB) k_rjl_force_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                               WrapC W, SlabDev S, int overwrite, double erep, double xi, double* __restrict__ part) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);
@@ -499,20 +679,20 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force_e(int N, const doubl
             double4 b = ld256_nc(&pos[j1]);
             int j2, j3;
             row.ahead(p, n, j1, j2, j3);
-            rjl_force_pair_g2<true>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
+            rjl_force_pair_e<true>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
             a = ld256_nc(&pos[j2]);
-            rjl_force_pair_g2<true>(pi, b, C, box, W.min_half_hi, fx, fy, fz, se);
+            rjl_force_pair_e<true>(pi, b, C, box, W.min_half_hi, fx, fy, fz, se);
             j1 = j3;
         }
-        if (p < n) rjl_force_pair_g2<true>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
+        if (p < n) rjl_force_pair_e<true>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
         if (overwrite) frc[i] = make_double4(fx, fy, fz, 0.);
         else add_force(frc, i, fx, fy, fz);
         e = erep * se - (pi.w > 0. ? xi / pi.w : 0.);
     } else if (i < N && overwrite) frc[i] = make_double4(0., 0., 0., 0.);
     store_partial(e, part);
 }
-template <int SPLIT>
-__global__ void __launch_bounds__(FT) k_rjl_force_split_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, RjlF C, BoxD box,
+template <int SPLIT, class CT>
+__global__ void __launch_bounds__(FT) k_rjl_force_split_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                           WrapC W, double erep, double xi, double* __restrict__ part) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double fx = 0, fy = 0, fz = 0, se = 0, e = 0, ie = 0;
@@ -521,7 +701,7 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split_e(int N, const double4* 
         const double4 pi = ld256_nc(&pos[i]);
         ie = pi.w;
         for (int p = sub; p < n; p += SPLIT)
-            rjl_force_pair_g2<true>(pi, ld256_nc(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, fx, fy, fz, se);
+            rjl_force_pair_e<true>(pi, ld256_nc(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, fx, fy, fz, se);
     }
     fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz); se = split_sum<SPLIT>(se);
     if (n > 0 && sub == 0) {
@@ -862,6 +1042,16 @@ static CosP cosp_of(const Inter& it) {
     return P;
 }
 
+// third-generation rjl: build the node table of an interaction once (called when the description is finalized)
+void rjl_prepare(pfmds_ctx* c, Inter& it) {
+    if (it.kind != K_RJL || c->rjl_gen != 3 || it.aux || !rjl_gen3_ok(it.rjl, c->box)) return;
+    const RjlTabSpec t = rjl_tab_spec(it.rjl);
+    std::vector<double2> h((size_t)(t.J_hi - t.J_lo + 1));
+    rjl_tab_fill(it.rjl, t, h.data());
+    CK(cudaMalloc(&it.aux, sizeof(double2) * h.size()));
+    CK(cudaMemcpy(it.aux, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
+}
+
 void normals_interaction(pfmds_ctx* c, int k) {  // update_norm_in_graphene, md_interactions.f90:195-208
     Inter& it = c->inter[k];
     if (it.kind != K_LJC && it.kind != K_MORSEC) return;
@@ -918,6 +1108,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         const WrapC W = wrap_consts(c->box);
         const bool fused = c->slab && !small && slab_fused(c);  // density stores 1/Eb into the neighbours' ghosts itself
         const bool gen2 = c->rjl_gen != 1 && rjl_gen2_ok(it.rjl, c->box);
+        const bool gen3 = gen2 && c->rjl_gen == 3 && it.aux != nullptr;  // node table built by rjl_prepare
         const ListView lv = it.nl[0].view(st);
         const int ow = (k == 0 && c->first_overwrites && !small) ? 1 : 0;
         // one launch sequence for both generations: CD / CF are the constant packs that select the pair routines.
@@ -941,17 +1132,34 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
             if (!e_in_force) {
                 KTimer kt(c, KS_RJL_FORCE);
                 if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W);
-                else LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
+                else {
+                    bool launched = false;
+                    if constexpr (std::is_same<TF, RjlG>::value)
+                        if (c->rjl_minb == 8) { LAUNCH((k_rjl_force<TF, 8>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow); launched = true; }
+                    if (!launched) LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
+                }
             }
         };
-        if (e_in_force) {
-            run(rjl_dens_consts(it.rjl), rjl_force_consts(it.rjl));
-            const RjlF CF = rjl_force_consts(it.rjl);
-            const double erep = it.rjl.r0 / (2. * it.rjl.p);   // A0 / a1, a1 = 2 A0 p / r0
+        const double erep = it.rjl.r0 / (2. * it.rjl.p);   // A0 / a1, a1 = 2 A0 p / r0
+        auto force_e = [&](auto CF) {
+            using TF = decltype(CF);
             KTimer kt(c, KS_RJL_FORCE);
-            if (small) LAUNCH((k_rjl_force_split_e<SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, erep, it.rjl.xi, epart);
-            else LAUNCH((k_rjl_force_e), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow, erep, it.rjl.xi, epart);
+            if (small) LAUNCH((k_rjl_force_split_e<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, erep, it.rjl.xi, epart);
+            else {
+                bool launched = false;
+                if constexpr (std::is_same<TF, RjlG>::value)
+                    if (c->rjl_minb == 8) { LAUNCH((k_rjl_force_e<TF, 8>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow, erep, it.rjl.xi, epart); launched = true; }
+                if (!launched) LAUNCH((k_rjl_force_e<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow, erep, it.rjl.xi, epart);
+            }
             e_parts = small ? nbs : nb;
+        };
+        if (gen3) {
+            const RjlG G = rjl_g3_consts(it.rjl, rjl_tab_spec(it.rjl), reinterpret_cast<const double2*>(it.aux));
+            run(G, G);
+            if (e_in_force) force_e(G);
+        } else if (e_in_force) {
+            run(rjl_dens_consts(it.rjl), rjl_force_consts(it.rjl));
+            force_e(rjl_force_consts(it.rjl));
         } else
         if (gen2) run(rjl_dens_consts(it.rjl), rjl_force_consts(it.rjl));
         else { const RjlC C = rjl_consts(it.rjl); run(C, C); }
@@ -1021,7 +1229,8 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
             if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, c->part);
             else LAUNCH((k_rjl_density<true, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, c->part, SlabDev{});
         };
-        if (c->rjl_gen != 1 && rjl_gen2_ok(it.rjl, c->box)) run(rjl_dens_consts(it.rjl));
+        if (c->rjl_gen == 3 && it.aux != nullptr && rjl_gen2_ok(it.rjl, c->box)) run(rjl_g3_consts(it.rjl, rjl_tab_spec(it.rjl), reinterpret_cast<const double2*>(it.aux)));
+        else if (c->rjl_gen != 1 && rjl_gen2_ok(it.rjl, c->box)) run(rjl_dens_consts(it.rjl));
         else run(rjl_consts(it.rjl));
         break;
     }

@@ -33,6 +33,7 @@
 #define __shared__ static thread_local
 
 struct double4 { double x, y, z, w; };
+struct double2 { double x, y; };
 struct float4 { float x, y, z, w; };
 static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }

@@ -2,6 +2,7 @@
 // as plain functions, one call per (block, thread) (pfmds_b200/csrc/host_emu.hpp), on the device's data layout — double4 records,
 // ELL lists with slot indices — with the launch sequences of forces_interaction / energy_interaction (forces.cu, bottom).
 // This checks kernel arithmetic and indexing against the CPU oracle without a GPU; it is not a CPU path of the product.
+#include <algorithm>
 #include <cstddef>
 #include <vector>
 
@@ -64,6 +65,21 @@ int fh_rjl(int N, double* pos4, double* frc4, size_t stride, const int* nl0, con
     const int nb = (N + FT - 1) / FT;
     std::vector<double> part((size_t)nb + 1, 0.);
     const ListView lv{nl0, nn0, stride};
+    if (gen == 3 && rjl_gen3_ok(R, box)) {   // third generation: node-table exponentials (the table lives in host memory here)
+        const RjlTabSpec t = rjl_tab_spec(R);
+        std::vector<double2> tab((size_t)(t.J_hi - t.J_lo + 1));
+        rjl_tab_fill(R, t, tab.data());
+        const RjlG G = rjl_g3_consts(R, t, tab.data());
+        emu_launch(k_rjl_density<true, RjlG>, nb, 1, FT, N, pos, lv, G, box, W, part.data(), SlabDev{});
+        *energy = sum_parts(part, nb, 1.0);
+        if (overwrite >= 2) {   // the force pass that also yields the energy (k_rjl_force_e): energy from it, forces as usual
+            std::fill(part.begin(), part.end(), 0.);
+            emu_launch(k_rjl_force_e<RjlG>, nb, 1, FT, N, (const double4*)pos, frc, lv, G, box, W, SlabDev{}, overwrite & 1, R.r0 / (2. * R.p), R.xi, part.data());
+            *energy = sum_parts(part, nb, 1.0);
+        } else
+        emu_launch(k_rjl_force<RjlG>, nb, 1, FT, N, (const double4*)pos, frc, lv, G, box, W, SlabDev{}, overwrite);
+        return 3;
+    }
     if (gen != 1 && rjl_gen2_ok(R, box)) {
         const RjlD CD = rjl_dens_consts(R);
         const RjlF CF = rjl_force_consts(R);

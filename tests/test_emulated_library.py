@@ -40,7 +40,8 @@ def _flavour(flavour, oracle_lib):
     B = BE.SERIAL
 
 
-def emu_gpu(case):
+def emu_gpu(case, path="small", **kw):
+    """(the replay has one path per flavour: `path` of the GPU tests, util.PATHS, does not apply)"""
     return configure(case, lib_path=B.lib)
 
 
@@ -59,13 +60,13 @@ SMALL = ["ab_gas", "cu_fcc", "gr_cu_ljc", "gr_cu_morsec", "gr_cu_ljc_simplified"
 
 @pytest.mark.parametrize("name", SMALL)
 def test_step0_lists_forces_energies(monkeypatch, name):
-    replay(monkeypatch, "test_parity_gpu").test_step0_lists_forces_energies(name)
+    replay(monkeypatch, "test_parity_gpu").test_step0_lists_forces_energies(name, "small")
 
 
 @pytest.mark.parametrize("name", ["ab_gas", "cu_fcc", "gr_cu_morsec"])
 @pytest.mark.parametrize("integrator", ["nve", "nvt", "nvms"])
 def test_trajectory_22_steps(monkeypatch, name, integrator):
-    replay(monkeypatch, "test_parity_gpu").test_trajectory_22_steps(name, integrator)
+    replay(monkeypatch, "test_parity_gpu").test_trajectory_22_steps(name, integrator, "small")
 
 
 @pytest.mark.parametrize("fn", ["test_single_step_forces_after_move", "test_zero_momentum_and_invert_z", "test_too_many_neighbours_is_reported",
@@ -79,14 +80,14 @@ def test_parity_misc(monkeypatch, fn):
 
 @pytest.mark.parametrize("name", ["ab_gas", "cu_fcc", "gr_cu_ljc"])
 def test_advance_logged_rows(monkeypatch, name):
-    replay(monkeypatch, "test_parity_gpu").test_advance_logged_rows(name)
+    replay(monkeypatch, "test_parity_gpu").test_advance_logged_rows(name, "small")
 
 
 @pytest.mark.parametrize("name", SMALL)
 def test_golden_fixtures_and_in_step_energies(monkeypatch, name):
     m = replay(monkeypatch, "test_parity_gpu")
-    m.test_gpu_matches_golden_fixtures(name)
-    m.test_energies_from_the_force_pass(name)
+    m.test_gpu_matches_golden_fixtures(name, "small")
+    m.test_energies_from_the_force_pass(name, "small")
 
 
 @pytest.mark.parametrize("thermostat", [True, False])

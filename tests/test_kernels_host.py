@@ -89,7 +89,7 @@ def ptr(a, t):
     return a.ctypes.data_as(t)
 
 
-def run_case(L, case, seed=1, rjl_overwrite_first=False, lj1g_pipe=False, rjl_gen=2, ran=None):
+def run_case(L, case, seed=1, rjl_overwrite_first=False, lj1g_pipe=False, rjl_gen=2, ran=None, rjl_energy_in_force=False):
     lay = DeviceLayout(case, seed)
     frc4 = np.zeros((lay.n, 4))
     energies = []
@@ -110,7 +110,7 @@ def run_case(L, case, seed=1, rjl_overwrite_first=False, lj1g_pipe=False, rjl_ge
         elif it["name"] == "rjl":
             l0 = lay.ell(*lists[0][:4])
             g = L.fh_rjl(lay.n, ptr(lay.pos4, DP), ptr(frc4, DP), C.c_size_t(lay.stride), ptr(l0[0], IP), ptr(l0[1], IP), ptr(prm, DP), ptr(lay.box, DP),
-                     int(rjl_overwrite_first and k == 0), C.byref(e), int(rjl_gen))
+                     int(rjl_overwrite_first and k == 0) + (2 if rjl_energy_in_force else 0), C.byref(e), int(rjl_gen))
             if ran is not None:
                 ran.append(g)
         elif it["name"] == "tb":
@@ -178,10 +178,15 @@ def test_emulated_rjl_generations(oracle_lib, kernels):
         ran = []
         f2, e2 = run_case(kernels, case, ran=ran)
         f1, e1 = run_case(kernels, case, rjl_gen=1, ran=ran)
-        assert ran == [2, 1]
+        f3, e3 = run_case(kernels, case, rjl_gen=3, ran=ran)                                # third generation: node-table exponentials
+        f3e, e3e = run_case(kernels, case, rjl_gen=3, ran=ran, rjl_energy_in_force=True)    # ... and its force pass that also yields the energy
+        assert ran == [2, 1, 3, 3]
         assert rel_err(f2, fo) < RTOL and rel_err(e2, eo) < RTOL
         assert rel_err(f1, fo) < RTOL and rel_err(e1, eo) < RTOL
+        assert rel_err(f3, fo) < 1e-10 and rel_err(e3, eo) < 1e-10
         assert rel_err(f2, f1) < 5e-11 and rel_err(e2, e1) < 5e-11   # rsqrt_q: host stand-in seed off by up to 1.9e-6 -> 5e-12 in r (device 9e-7 -> 1.3e-12), times |exponent| <= 15
+        assert rel_err(f3, f2) < 5e-13 and rel_err(e3, e2) < 5e-13   # same r, same switch: only the exponentials differ (table + degree-4 Taylor: 1.6e-14 each)
+        assert np.array_equal(f3e, f3) and rel_err(e3e, e3) < 1e-13
     small = inputs.cu_fcc(ncell=3, jitter=0.2, seed=3, period=5)       # box 10.8 A: half box 5.42 < R2 = 6.0
     ran = []
     f, e = run_case(kernels, small, ran=ran)
