@@ -313,8 +313,7 @@ def run_variants(local, small=False):
             out["device_math"] = {"error": repr(ex)[:300]}
     for name, cs, integ, h, env in (
             ("cu_fcc defaults", case, integrator, dt, {}),
-            ("cu_fcc, rjl third generation with the force kernel held to 8 blocks/SM (PFMDS_RJL_MINB=8: 64 registers)", case, integrator, dt, {"PFMDS_RJL_MINB": "8"}),
-            ("cu_fcc, rjl second generation (PFMDS_RJL_GEN=2: analytic exponentials)", case, integrator, dt, {"PFMDS_RJL_GEN": "2"}),
+            ("cu_fcc, rjl third generation (PFMDS_RJL_GEN=3: node-table exponentials, fewer FP64 instructions but twice the L1 wavefronts)", case, integrator, dt, {"PFMDS_RJL_GEN": "3"}),
             ("cu_fcc, rjl first generation (PFMDS_RJL_GEN=1, the round-1 kernels)", case, integrator, dt, {"PFMDS_RJL_GEN": "1"}),
             ("cu_fcc, list build with the exact test inside the candidate loop (PFMDS_NL_MASK=0, k_build): compare nl_build", case, integrator, dt, {"PFMDS_NL_MASK": "0"}),
             ("lj_fluid 96^3 lj1g defaults (pipelined kernel)", ljc, "nve", ljc["integrators"][0][1], {}),
@@ -418,8 +417,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- multi-GPU lines check themselves (the driver's test box has one GPU: the 2-GPU pytest never runs there) ----
+    check = None
+    if slab:
+        check = {}
+        try:
+            from pfmds_b200.slab import slab_parity_check
+            check["slab_parity_detail"] = slab_parity_check(dist, rank, world, local)
+            check["slab_parity"] = "ok"
+        except AssertionError as ex:
+            check["slab_parity"] = "FAILED: " + repr(ex)[:300]
+
     # ---- warm-up: step 0 (lists + forces) and W-1 steps ----
-    eng.advance(integrator, dt, 0, W)
+    eng.advance(integrator, dt, 0, 1)
+    if slab:   # potential energy per atom of the perfect lattice at step 0 against a single-context crystal (size independent)
+        e0 = eng.energies()                      # all-reduced inside the library: every rank calls
+        check["pe_per_atom_step0"] = float(np.sum(e0[0]) / n_total)
+        if rank == 0:
+            from pfmds_b200 import inputs as _inp
+            small = configure(_inp.cu_fcc(ncell=4), device=local)
+            small.advance("nvt", dt, 0, 1)
+            pe1 = float(np.sum(small.energies()[0]) / 256)
+            small.close()
+            check["pe_per_atom_single_gpu"] = pe1
+            check["pe_rel_diff"] = abs(check["pe_per_atom_step0"] - pe1) / abs(pe1)
+    eng.advance(integrator, dt, 1, W - 1)
     eng.synchronize()
     pairs = eng.pair_count(0, 0) // (world if slab else 1)   # the library sums over ranks in slab mode
     pairs_within_cache = {}
@@ -455,6 +477,15 @@ def main():
         ms_prof = eng.timer_stop()
     ktimes = eng.kernel_times()
     eng.set_profiling(False)
+    if slab:   # after the timed steps (rebuilds with migration among them): every atom still has exactly one owner, sum F = 0
+        fs = eng.diagnostics()[0]                # all-reduced inside the library
+        cnt = torch.tensor([eng.slab_counts()[0]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        check["atoms"] = int(cnt.item())
+        check["atoms_expected"] = int(n_total)
+        check["force_sum_max_abs"] = float(np.abs(fs).max())
+        check["ok"] = bool(check["atoms"] == check["atoms_expected"] and check.get("slab_parity") == "ok" and check["force_sum_max_abs"] < 1e-6 and
+                           (rank != 0 or check.get("pe_rel_diff", 1.0) < 1e-12))
     ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
@@ -628,7 +659,7 @@ def main():
                    "l2": "working set (lists %.0f MB + state) exceeds the 126 MB L2" % (pairs * 4 / 1e6), "ns_per_day": K / (ms_max * 1e-3) * dt * 86400e-6},
         "clocks": cs.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
-        "per_rank": per_rank, "variants": variants,
+        "per_rank": per_rank, "variants": variants, "check": check,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -183,6 +183,8 @@ int pfmds_slab_unique_id(char id[128]);
 int pfmds_create_slab(pfmds_ctx** ctx, int device, int rank, int nranks, const char id[128], long long n_global, int n_local,
                       const int* global_index, const double* positions, const double* velocities, const double* masses,
                       const unsigned int* group_mask, int n_groups, const long long* group_sizes, const double box_size[3], int capacity);
+/* Atoms this rank owns right now and the ghost copies it holds (they change at every list rebuild: migration, halo re-selection). */
+int pfmds_slab_counts(pfmds_ctx* ctx, int* n_local, int* n_ghost);
 int pfmds_slab_download(pfmds_ctx* ctx, int* n_local, int* global_index, double* positions, double* velocities, double* forces);
 /* Overwrite the state of this rank's atoms, given in the order of the last pfmds_slab_download. */
 int pfmds_slab_upload(pfmds_ctx* ctx, int n_local, const double* positions, const double* velocities);

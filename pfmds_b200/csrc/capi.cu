@@ -56,8 +56,11 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     c->use_graphs = !slab && env_int("PFMDS_GRAPHS", n_atoms < 200000 ? 1 : 0) == 1;
     c->lj1g_pipe = env_int("PFMDS_LJ1G_PIPE", 1) != 0;
     c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
-    c->rjl_gen = env_int("PFMDS_RJL_GEN", 3);
-    if (c->rjl_gen < 1 || c->rjl_gen > 3) c->rjl_gen = 3;
+    // 2 is the default: the third generation (node-table exponentials) removes 13 of 43 FP64 instructions per pair but its table
+    // look-ups double the L1 data-pipe wavefronts, and that pipe is what bounds these kernels (ncu, profiles/r2b_*): measured
+    // 0.343 against 0.277 ms (density) and 0.362 against 0.360 ms (force) per launch at 10^6 atoms
+    c->rjl_gen = env_int("PFMDS_RJL_GEN", 2);
+    if (c->rjl_gen < 1 || c->rjl_gen > 3) c->rjl_gen = 2;
     c->rjl_minb = env_int("PFMDS_RJL_MINB", 7) == 8 ? 8 : 7;
 #ifdef PFMDS_COOP
     c->small_n = env_int("PFMDS_SMALL_N", 100000);
@@ -1501,6 +1504,16 @@ int pfmds_create_slab(pfmds_ctx** out, int device, int rank, int nranks, const c
         read_env(c, n_local, true);
         CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
         slab_init(c, rank, nranks, id, n_global, n_local, capacity);
+    });
+}
+
+int pfmds_slab_counts(pfmds_ctx* c, int* n_local, int* n_ghost) {
+    if (!c || !c->slab) return PFMDS_ERR_INVALID;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->dev));
+        CK(cudaStreamSynchronize(c->st));
+        if (n_local) *n_local = slab_n_local(c);
+        if (n_ghost) *n_ghost = c->N - slab_n_local(c);
     });
 }
 

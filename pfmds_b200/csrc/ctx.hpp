@@ -96,7 +96,7 @@ struct pfmds_ctx {
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
     int rjl_minb = 7;               // blocks/SM the third-generation rjl force kernels are compiled for: 7 (72 registers) or 8 (64; PFMDS_RJL_MINB=8)
-    int rjl_gen = 3;                // rjl pair routines: 3 = node-table exponentials (forces.cu), 2 = analytic short forms, 1 = first generation (PFMDS_RJL_GEN)
+    int rjl_gen = 2;                // rjl pair routines: 2 = analytic short forms (default), 3 = node-table exponentials (measured slower: L1-bound), 1 = first generation (PFMDS_RJL_GEN)
     bool nl_mask = true;            // thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (measured 8 % faster, BENCH_r01); PFMDS_NL_MASK=0: k_build
     bool lj1g_pipe = true;          // pipelined lj1g force kernel for systems of small_n atoms and more (measured 0.174 -> 0.102 ms, BENCH_r01); PFMDS_LJ1G_PIPE=0: k_lj1g
     // Path switches by system size.  Runtime fields (PFMDS_SMALL_N, PFMDS_NL_WARP_N) so that the parity tests can drive

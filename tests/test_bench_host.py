@@ -68,7 +68,7 @@ def test_variants_child_on_the_host_replay(oracle_lib, monkeypatch, capsys):
     monkeypatch.setattr(E, "configure", lambda case, device=0, **kw: orig(case, lib_path=B.LIB))
     assert bench.run_variants(0, small=True) == 0
     rows = [json.loads(l) for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
-    assert len(rows) == 11 and all(len(b) == len(a) + 1 for a, b in zip(rows, rows[1:]))
+    assert len(rows) == 10 and all(len(b) == len(a) + 1 for a, b in zip(rows, rows[1:]))
     last = rows[-1]
     bad = {k: v for k, v in last.items() if k != "note" and "error" in v}
     assert not bad, bad
