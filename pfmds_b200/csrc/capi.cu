@@ -56,6 +56,7 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     c->use_graphs = !slab && env_int("PFMDS_GRAPHS", n_atoms < 200000 ? 1 : 0) == 1;
     c->lj1g_pipe = env_int("PFMDS_LJ1G_PIPE", 1) != 0;
     c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
+    c->nl_cell = env_int("PFMDS_NL_CELL", 1) != 0;
     // 2 is the default: the third generation (node-table exponentials) removes 13 of 43 FP64 instructions per pair but its table
     // look-ups double the L1 data-pipe wavefronts, and that pipe is what bounds these kernels (ncu, profiles/r2b_*): measured
     // 0.343 against 0.277 ms (density) and 0.362 against 0.360 ms (force) per launch at 10^6 atoms

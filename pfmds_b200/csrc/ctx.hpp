@@ -76,6 +76,7 @@ struct pfmds_ctx {
     // host description
     std::vector<std::vector<int>> groups;  // 1-based group -> 1-based file indexes
     std::vector<uint32_t> h_gmask;         // by file index
+    bool all_in_group(int g) const { return g >= 1 && g <= (int)groups.size() && cur_n.empty() ? groups[(size_t)g - 1].size() == (size_t)N : (g >= 1 && g <= (int)groups.size() && groups[(size_t)g - 1].size() == (size_t)N && changes.empty()); }
     int all_moving = 1, xyz_moving = 1, z_moving = 1, all_atoms = 1;
     int zero_momentum_period = 1;
     bool invert_z = false;
@@ -101,6 +102,7 @@ struct pfmds_ctx {
     bool lj1g_pipe = true;          // pipelined lj1g force kernel for systems of small_n atoms and more (measured 0.174 -> 0.102 ms, BENCH_r01); PFMDS_LJ1G_PIPE=0: k_lj1g
     // Path switches by system size.  Runtime fields (PFMDS_SMALL_N, PFMDS_NL_WARP_N) so that the parity tests can drive
     // the kernels of BOTH sides of each switch against the oracle on systems the O(N^2) oracle can handle.
+    bool nl_cell = true;            // cell-tiled list build (one warp per cell, candidates staged in shared memory by bulk copies) for large systems; PFMDS_NL_CELL=0: k_build_mask
     int small_n = 100000;           // below: 8 lanes per atom in the pair kernels (latency bound); from it on: thread per atom, pipelined
     int nl_warp_n = 200000;         // below: warp-per-atom list build; from it on: thread per atom
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass

@@ -30,6 +30,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __noinline__
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static thread_local
 
 struct double4 { double x, y, z, w; };

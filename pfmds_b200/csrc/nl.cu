@@ -369,6 +369,205 @@ __global__ void __launch_bounds__(128) k_build_mask(int N, const double4* __rest
     nnum[i] = cnt;
 }
 
+#ifdef PFMDS_COOP
+// ------------------------------------------------------------------------------------------------
+// Cell-tiled build (large systems, atoms physically in cell order, every axis at least three cells wide).
+// ncu on k_build_mask (profiles/r2a_k_build_mask.txt): 84 warp instructions per candidate, issue slots 83 % busy, 19 of 32 lanes
+// active -- every thread walks the 27 cells on its own, fetching each candidate's 16-byte record with its own load and folding it
+// into the box with three compare/select pairs.  Here ONE WARP owns ONE CELL: its lanes are the cell's atoms (list owners), and
+// the candidates of the 27 surrounding cells are staged in shared memory, one x-row of three cells (one or two contiguous ranges
+// of the float4 copy) at a time, double buffered, by 1-D bulk copies (cp.async.bulk, completion on an mbarrier) -- the one
+// tile-shaped movement of this code.  Every lane then reads the SAME staged record (shared-memory broadcast, one wavefront per
+// warp and candidate) and the periodic image is a property of the range, not of the pair: the owner's coordinates are shifted
+// once per range, so the FP32 prefilter is three subtractions, three multiply-adds and a compare per candidate.  Survivors are
+// recorded in a per-lane bit mask (32 candidates at a time) and take the exact FP64 test in candidate order, as in k_build_mask.
+//   Bit-identical rows: the candidates are visited in k_build's order (oz, oy, ox; slot order inside a cell), and the exact test
+// computes d = (x_j - x_i) + s with s = 0 or -+L of the range, which is min_image's own arithmetic whenever both agree on the
+// image -- they do for every survivor: a survivor has |d| < r_cut + margin < L/2 in each component under the range's image, and
+// with three or more cells per axis each neighbouring cell is visited under exactly one image.
+#define CB_WARPS 4     // cells (warps) per block; each warp works alone: no block-wide barrier after the prologue
+#define CB_CAP 128     // records per stage buffer (2 KB); a three-cell row of a dense liquid goes through in several pieces
+struct CbRange { int start, count; float sx, sy, sz; int shifted; };
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned cb_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+#endif
+// lane 0: arm the barrier with the byte count and start the bulk copy of `n` records; other lanes: nothing
+__device__ __forceinline__ void cb_issue(float4* dst, const float4* src, int n, unsigned long long* bar, int lane) {
+#ifdef __CUDA_ARCH__
+    if (lane == 0) {
+        const unsigned bytes = (unsigned)n * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cb_smem(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cb_smem(dst)), "l"(src), "r"(bytes),
+                     "r"(cb_smem(bar))
+                     : "memory");
+    }
+#else  // host replay: a plain copy by the lanes of the warp
+    (void)bar;
+    for (int k = lane; k < n; k += 32) dst[k] = src[k];
+#endif
+}
+__device__ __forceinline__ void cb_wait(unsigned long long* bar, unsigned parity) {
+#ifdef __CUDA_ARCH__
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(cb_smem(bar)),
+        "r"(parity)
+        : "memory");
+#else
+    (void)bar; (void)parity;
+    __syncwarp();
+#endif
+}
+template <bool PART, bool CHECK2>
+__global__ void __launch_bounds__(32 * CB_WARPS) k_build_cell(int ncells, const double4* __restrict__ pos, const float4* __restrict__ posf,
+                                                              const int* __restrict__ orig, const int* __restrict__ cstart, GridD g, BoxD box, PrefD pf,
+                                                              uint32_t bit1, uint32_t bit2, double rc2, double r1sq, double r2sq, int maxn, size_t stride,
+                                                              int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err) {
+    __shared__ __align__(128) float4 buf[CB_WARPS][2][CB_CAP];
+    __shared__ __align__(8) unsigned long long bars[CB_WARPS][2];
+    __shared__ CbRange rng[CB_WARPS][18];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * CB_WARPS + w;
+    if (c >= ncells) return;
+    const int ob = cstart[c], oe = cstart[c + 1];
+    if (ob >= oe) return;  // empty cell
+    // ---- the 18 candidate ranges of this cell: 9 (oz, oy) rows x [cells x-1..x+1, split where the row wraps] ----
+    const int cx = c % g.n[0], cy = (c / g.n[0]) % g.n[1], cz = c / (g.n[0] * g.n[1]);
+    if (lane < 18) {
+        const int r = lane >> 1, part = lane & 1;
+        const int oz = r / 3 - 1, oy = r % 3 - 1;
+        int z = cz + oz, y = cy + oy;
+        float sz = 0.f, sy = 0.f, sx = 0.f;
+        if (z < 0) { z += g.n[2]; sz = -pf.L[2]; } else if (z >= g.n[2]) { z -= g.n[2]; sz = pf.L[2]; }
+        if (y < 0) { y += g.n[1]; sy = -pf.L[1]; } else if (y >= g.n[1]) { y -= g.n[1]; sy = pf.L[1]; }
+        const int rowc = (z * g.n[1] + y) * g.n[0];
+        int first, last;  // cells of this part, in visiting order x-1, x, x+1
+        if (cx == 0) { if (part == 0) { first = last = g.n[0] - 1; sx = -pf.L[0]; } else { first = 0; last = 1; } }
+        else if (cx == g.n[0] - 1) { if (part == 0) { first = cx - 1; last = cx; } else { first = last = 0; sx = pf.L[0]; } }
+        else { if (part == 0) { first = cx - 1; last = cx + 1; } else { first = 0; last = -1; } }
+        CbRange R;
+        R.start = cstart[rowc + first];
+        R.count = last >= first ? cstart[rowc + last + 1] - R.start : 0;
+        R.sx = sx; R.sy = sy; R.sz = sz;
+        R.shifted = (sx != 0.f) || (sy != 0.f) || (sz != 0.f);
+        rng[w][lane] = R;
+    }
+#ifdef __CUDA_ARCH__
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cb_smem(&bars[w][0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cb_smem(&bars[w][1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+#endif
+    __syncwarp();
+    unsigned use0 = 0u, use1 = 0u;  // completed uses of each stage buffer: parity of the next wait
+    for (int o0 = ob; o0 < oe; o0 += 32) {  // the cell's atoms, 32 at a time (one pass for a crystal)
+        const int i = o0 + lane;
+        bool owner = false;
+        float4 pif = make_float4(0.f, 0.f, 0.f, 0.f);
+        double4 pi = make_double4(0., 0., 0., 0.);
+        if (i < oe) {
+            pif = posf[i];
+            owner = (__float_as_uint(pif.w) & (bit1 | PFMDS_GHOST)) == bit1;
+            if (owner) pi = pos[i]; else nnum[i] = 0;
+        }
+        int cnt = 0, c0 = 0, c1 = 0, c2 = 0;
+        // piece iterator over (range, offset): `q*` is the piece being fetched, `p*` the piece being processed
+        int qr = 0, qo = 0, k_issue = 0, k_done = 0;
+        auto skip_empty = [&](int& r, int& o) { while (r < 18 && o >= rng[w][r].count) { ++r; o = 0; } };
+        skip_empty(qr, qo);
+        auto issue_next = [&]() {
+            if (qr >= 18) return;
+            const CbRange R = rng[w][qr];
+            const int n = R.count - qo < CB_CAP ? R.count - qo : CB_CAP;
+            cb_issue(buf[w][k_issue & 1], posf + R.start + qo, n, &bars[w][k_issue & 1], lane);
+            ++k_issue;
+            qo += n;
+            skip_empty(qr, qo);
+        };
+        int pr = 0, po = 0;
+        skip_empty(pr, po);
+        issue_next();
+        issue_next();
+        while (pr < 18) {
+            const CbRange R = rng[w][pr];
+            const int n = R.count - po < CB_CAP ? R.count - po : CB_CAP;
+            const int b = k_done & 1;
+            cb_wait(&bars[w][b], (b ? use1 : use0) & 1u);
+            if (b) use1 += 1u; else use0 += 1u;
+            const float4* cand = buf[w][b];
+            const int j0 = R.start + po;
+            const float ox = pif.x - R.sx, oy = pif.y - R.sy, oz = pif.z - R.sz;  // candidate + s - owner = candidate - (owner - s)
+            const double dsx = R.sx == 0.f ? 0. : (R.sx < 0.f ? -box.L[0] : box.L[0]), dsy = R.sy == 0.f ? 0. : (R.sy < 0.f ? -box.L[1] : box.L[1]),
+                         dsz = R.sz == 0.f ? 0. : (R.sz < 0.f ? -box.L[2] : box.L[2]);
+            for (int g0 = 0; g0 < n; g0 += 32) {
+                const int m = n - g0 < 32 ? n - g0 : 32;
+                uint32_t mask = 0;
+                if (owner) {
+                    if (m == 32) {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const float4 q = cand[g0 + t];
+                            const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
+                            bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (j0 + g0 + t != i);
+                            if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
+                            mask |= keep ? (1u << t) : 0u;
+                        }
+                    } else {
+                        for (int t = 0; t < m; ++t) {
+                            const float4 q = cand[g0 + t];
+                            const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
+                            bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (j0 + g0 + t != i);
+                            if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
+                            mask |= keep ? (1u << t) : 0u;
+                        }
+                    }
+                }
+                while (mask) {  // exact test of the survivors, in candidate order
+                    const int t = PFMDS_FFS(mask) - 1;
+                    mask &= mask - 1u;
+                    const int j = j0 + g0 + t;
+                    const double4 pj = pos[j];
+                    double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+                    if (R.shifted) { dx += dsx; dy += dsy; dz += dsz; }  // min_image's own d - L / d + L (see the header of this kernel)
+                    const double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    if (dr2 < rc2) {
+                        if (cnt < maxn) {
+                            if (!PART) nlist[(size_t)cnt * stride + i] = j;
+                            else if (dr2 < r1sq) nlist[(size_t)(c0++) * stride + i] = j;
+                            else if (dr2 < r2sq) alt[(size_t)(c1++) * stride + i] = j;
+                            else alt[(size_t)(maxn - 1 - (c2++)) * stride + i] = j;
+                        }
+                        ++cnt;
+                    }
+                }
+            }
+            __syncwarp();  // every lane is done with this stage buffer: it may be refilled
+            ++k_done;
+            po += n;
+            skip_empty(pr, po);
+            issue_next();
+        }
+        if (owner) {
+            if (cnt > maxn) { raise_error(err, E_TOO_MANY, orig[i], cnt); cnt = maxn; }  // md_neighbours.f90:80
+            if (PART) {
+                for (int k = 0; k < c1; ++k) nlist[(size_t)(c0 + k) * stride + i] = alt[(size_t)k * stride + i];
+                for (int k = 0; k < c2; ++k) nlist[(size_t)(c0 + c1 + k) * stride + i] = alt[(size_t)(maxn - 1 - k) * stride + i];
+            }
+            nnum[i] = cnt;
+        }
+        __syncwarp();
+    }
+}
+#endif  // PFMDS_COOP
+
 #ifdef PFMDS_COOP  // ballot / popc compaction across the lanes of a warp: device, or the lock-step host replay
 // One WARP per list-owner atom: the lanes test 32 candidates of a cell range at a time (coalesced 16-byte
 // loads of the float4 copy), the survivors of the exact FP64 test are compacted with ballot + popc into the
@@ -498,6 +697,22 @@ void nl_build(pfmds_ctx* c, NList& l) {
     double rc2 = l.rcut * l.rcut;
     const PrefD pf = nl_prefilter(c->box, l.rcut);
     KTimer kt(c, KS_NL_BUILD);
+#ifdef PFMDS_COOP
+    // cell-tiled build: large systems in cell order, three or more cells per axis, FP32 prefilter usable
+    if (c->nl_cell && !warp_per_atom && c->identity_order && pf.on && g.n[0] >= 3 && g.n[1] >= 3 && g.n[2] >= 3) {
+        const int nbc = (c->ncells + CB_WARPS - 1) / CB_WARPS;
+        const bool check2 = !c->slab && c->h_gmask.size() == (size_t)N && !c->all_in_group(l.g2);
+        const bool chk = c->slab || check2;  // slab mode keeps its masks on the device only: always test
+#define CELL_ARGS c->ncells, c->pos, c->posf, c->orig, c->cell_start, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err
+        if (l.partition) { if (chk) LAUNCH((k_build_cell<true, true>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); else LAUNCH((k_build_cell<true, false>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); }
+        else { if (chk) LAUNCH((k_build_cell<false, true>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); else LAUNCH((k_build_cell<false, false>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); }
+#undef CELL_ARGS
+        c->launches += 1;
+        l.built = true;
+        CK(cudaGetLastError());
+        return;
+    }
+#endif
 #define BUILD_ARGS N, c->pos, c->posf, c->orig, c->cell_start, c->cell_atoms, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, \
         l.nlist_alt, l.nnum, c->err
 #ifdef PFMDS_COOP
