@@ -23,6 +23,9 @@
 #include <vector>
 
 #define PFMDS_HOST_EMU 1
+// dynamic shared memory of a launch (kernels that declare `extern __shared__` take this buffer instead)
+static inline std::vector<unsigned char>& emu_dyn_buf() { static thread_local std::vector<unsigned char> b; return b; }
+static inline void emu_dynamic_smem(size_t n) { if (emu_dyn_buf().size() < n) emu_dyn_buf().resize(n); }
 #define __device__
 #define __host__
 #define __global__

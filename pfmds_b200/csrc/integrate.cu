@@ -449,6 +449,15 @@ void integ_nvt_kick_close(pfmds_ctx* c, double dt) {
     }
     c->launches += 2;
 }
+NhcPack integ_nhc_pack(pfmds_ctx* c) { return pack_of(c); }
+// closing chain update when the kick and the KE partials came out of the force kernel (forces.cu k_rjl_force_x): `nparts` rows of
+// NHC_MAXF partial sums, summed in row order
+void integ_nvt_close_only(pfmds_ctx* c, double dt, int nparts, const double* part) {
+    NhcPack P = pack_of(c);
+    KTimer kt(c, KS_KICK);
+    LAUNCH((k_nhc_close), 1, 1024, c->st, nparts, part, P, dt / 2, dt / 4, dt / 8);
+    c->launches += 1;
+}
 // apply scalings that are still pending (before anything else reads or changes velocities)
 void integ_flush_pending(pfmds_ctx* c) {
     if (!c->nhc_pending) return;

@@ -227,12 +227,10 @@ __global__ void k_make_posf(int N, const double4* __restrict__ pos, const uint32
 // Thread-per-atom variant (large systems: the grid already fills the GPU and a serial scan issues fewer
 // warp instructions than 32 lanes sharing ~23-atom cells).
 template <bool IDENT, bool PART>
-__global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict__ pos, const float4* __restrict__ posf, const int* __restrict__ orig,
-                                               const int* __restrict__ cstart, const int* __restrict__ catoms, GridD g, BoxD box, PrefD pf,
-                                               uint32_t bit1, uint32_t bit2, double rc2, double r1sq, double r2sq, int maxn, size_t stride,
-                                               int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+__device__ __forceinline__ void build_row(int i, const double4* __restrict__ pos, const float4* __restrict__ posf, const int* __restrict__ orig,
+                                          const int* __restrict__ cstart, const int* __restrict__ catoms, const GridD& g, const BoxD& box, const PrefD& pf,
+                                          uint32_t bit1, uint32_t bit2, double rc2, double r1sq, double r2sq, int maxn, size_t stride,
+                                          int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err) {
     const float4 pif = posf[i];
     if ((__float_as_uint(pif.w) & (bit1 | PFMDS_GHOST)) != bit1) { nnum[i] = 0; return; }  // owners: in group 1 and not a ghost copy
     const double4 pi = pos[i];
@@ -286,6 +284,15 @@ __global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict_
         for (int k = 0; k < c2; ++k) nlist[(size_t)(c0 + c1 + k) * stride + i] = alt[(size_t)(maxn - 1 - k) * stride + i];
     }
     nnum[i] = cnt;
+}
+template <bool IDENT, bool PART>
+__global__ void __launch_bounds__(128) k_build(int N, const double4* __restrict__ pos, const float4* __restrict__ posf, const int* __restrict__ orig,
+                                               const int* __restrict__ cstart, const int* __restrict__ catoms, GridD g, BoxD box, PrefD pf,
+                                               uint32_t bit1, uint32_t bit2, double rc2, double r1sq, double r2sq, int maxn, size_t stride,
+                                               int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    build_row<IDENT, PART>(i, pos, posf, orig, cstart, catoms, g, box, pf, bit1, bit2, rc2, r1sq, r2sq, maxn, stride, nlist, alt, nnum, err);
 }
 
 // Thread-per-atom variant with the two tests separated (the default; PFMDS_NL_MASK=0 selects k_build; 8 % faster per rebuild at 10^6 atoms, BENCH_r01).  In k_build the exact
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(128) k_build_mask(int N, const double4* __rest
 // image -- they do for every survivor: a survivor has |d| < r_cut + margin < L/2 in each component under the range's image, and
 // with three or more cells per axis each neighbouring cell is visited under exactly one image.
 #define CB_WARPS 4     // cells (warps) per block; each warp works alone: no block-wide barrier after the prologue
-#define CB_CAP 128     // records per stage buffer (2 KB); a three-cell row of a dense liquid goes through in several pieces
+#define CB_CAP 64      // records per stage buffer (1 KB); a three-cell row goes through in one or two pieces
 struct CbRange { int start, count; float sx, sy, sz; int shifted; };
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ unsigned cb_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -424,19 +431,32 @@ __device__ __forceinline__ void cb_wait(unsigned long long* bar, unsigned parity
     __syncwarp();
 #endif
 }
+// Phase 1 (lanes = the cell's atoms): every staged candidate is read by all lanes at once (broadcast) and the FP32 prefilter's
+// survivors are appended, in candidate order, to a per-lane list in shared memory (16-bit entries: range number, offset in range).
+// Phase 2 (lanes = one atom's survivors): the warp takes the atoms of the cell one after the other and gives each survivor of that
+// atom a lane for the exact FP64 test; the accepted entries are compacted into the row with ballot + popc in candidate order, one
+// counter per class.  (A first version ran the exact test inside phase 1, each lane looping over its own survivors: the warp then
+// executes the FP64 block max-over-lanes times per 32 candidates with 13 of 32 lanes active on average -- ncu, profiles/r2e_*.)
+#define CB_OFF_BITS 11                      // offset of a candidate inside its range (three cells): ranges longer than 2048 atoms use k_build_mask
 template <bool PART, bool CHECK2>
 __global__ void __launch_bounds__(32 * CB_WARPS) k_build_cell(int ncells, const double4* __restrict__ pos, const float4* __restrict__ posf,
                                                               const int* __restrict__ orig, const int* __restrict__ cstart, GridD g, BoxD box, PrefD pf,
                                                               uint32_t bit1, uint32_t bit2, double rc2, double r1sq, double r2sq, int maxn, size_t stride,
-                                                              int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err) {
+                                                              int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err, int lcap) {
     __shared__ __align__(128) float4 buf[CB_WARPS][2][CB_CAP];
     __shared__ __align__(8) unsigned long long bars[CB_WARPS][2];
     __shared__ CbRange rng[CB_WARPS][18];
+#ifdef __CUDACC__
+    extern __shared__ __align__(16) unsigned short surv_all[];  // [CB_WARPS][32][lcap]: prefilter survivors of each lane's atom
+#else
+    unsigned short* const surv_all = reinterpret_cast<unsigned short*>(emu_dyn_buf().data());  // host replay: the block's dynamic shared memory
+#endif
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * CB_WARPS + w;
     if (c >= ncells) return;
     const int ob = cstart[c], oe = cstart[c + 1];
     if (ob >= oe) return;  // empty cell
+    unsigned short* const surv = surv_all + (size_t)w * 32 * lcap;
     // ---- the 18 candidate ranges of this cell: 9 (oz, oy) rows x [cells x-1..x+1, split where the row wraps] ----
     const int cx = c % g.n[0], cy = (c / g.n[0]) % g.n[1], cz = c / (g.n[0] * g.n[1]);
     if (lane < 18) {
@@ -467,20 +487,21 @@ __global__ void __launch_bounds__(32 * CB_WARPS) k_build_cell(int ncells, const 
     }
 #endif
     __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
     unsigned use0 = 0u, use1 = 0u;  // completed uses of each stage buffer: parity of the next wait
     for (int o0 = ob; o0 < oe; o0 += 32) {  // the cell's atoms, 32 at a time (one pass for a crystal)
         const int i = o0 + lane;
         bool owner = false;
         float4 pif = make_float4(0.f, 0.f, 0.f, 0.f);
-        double4 pi = make_double4(0., 0., 0., 0.);
         if (i < oe) {
             pif = posf[i];
             owner = (__float_as_uint(pif.w) & (bit1 | PFMDS_GHOST)) == bit1;
-            if (owner) pi = pos[i]; else nnum[i] = 0;
+            if (!owner) nnum[i] = 0;
         }
-        int cnt = 0, c0 = 0, c1 = 0, c2 = 0;
-        // piece iterator over (range, offset): `q*` is the piece being fetched, `p*` the piece being processed
-        int qr = 0, qo = 0, k_issue = 0, k_done = 0;
+        // ---- phase 1: FP32 prefilter, lanes = atoms of the cell ----
+        int ns = 0;                                   // survivors of this lane's atom so far (may pass lcap: the atom is then redone by the slow path)
+        unsigned short* const mine = surv + (size_t)lane * lcap;
+        int qr = 0, qo = 0, k_issue = 0, k_done = 0;  // piece being fetched (q*) / processed (p*)
         auto skip_empty = [&](int& r, int& o) { while (r < 18 && o >= rng[w][r].count) { ++r; o = 0; } };
         skip_empty(qr, qo);
         auto issue_next = [&]() {
@@ -503,49 +524,20 @@ __global__ void __launch_bounds__(32 * CB_WARPS) k_build_cell(int ncells, const 
             cb_wait(&bars[w][b], (b ? use1 : use0) & 1u);
             if (b) use1 += 1u; else use0 += 1u;
             const float4* cand = buf[w][b];
-            const int j0 = R.start + po;
+            const int self = i - (R.start + po);          // this lane's own atom as a candidate of the piece (negative / >= n: not in it)
+            const unsigned tag = ((unsigned)pr << CB_OFF_BITS) + (unsigned)po;
             const float ox = pif.x - R.sx, oy = pif.y - R.sy, oz = pif.z - R.sz;  // candidate + s - owner = candidate - (owner - s)
-            const double dsx = R.sx == 0.f ? 0. : (R.sx < 0.f ? -box.L[0] : box.L[0]), dsy = R.sy == 0.f ? 0. : (R.sy < 0.f ? -box.L[1] : box.L[1]),
-                         dsz = R.sz == 0.f ? 0. : (R.sz < 0.f ? -box.L[2] : box.L[2]);
-            for (int g0 = 0; g0 < n; g0 += 32) {
-                const int m = n - g0 < 32 ? n - g0 : 32;
-                uint32_t mask = 0;
-                if (owner) {
-                    if (m == 32) {
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) {
-                            const float4 q = cand[g0 + t];
-                            const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
-                            bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (j0 + g0 + t != i);
-                            if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
-                            mask |= keep ? (1u << t) : 0u;
-                        }
-                    } else {
-                        for (int t = 0; t < m; ++t) {
-                            const float4 q = cand[g0 + t];
-                            const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
-                            bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (j0 + g0 + t != i);
-                            if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
-                            mask |= keep ? (1u << t) : 0u;
-                        }
-                    }
-                }
-                while (mask) {  // exact test of the survivors, in candidate order
-                    const int t = PFMDS_FFS(mask) - 1;
-                    mask &= mask - 1u;
-                    const int j = j0 + g0 + t;
-                    const double4 pj = pos[j];
-                    double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-                    if (R.shifted) { dx += dsx; dy += dsy; dz += dsz; }  // min_image's own d - L / d + L (see the header of this kernel)
-                    const double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    if (dr2 < rc2) {
-                        if (cnt < maxn) {
-                            if (!PART) nlist[(size_t)cnt * stride + i] = j;
-                            else if (dr2 < r1sq) nlist[(size_t)(c0++) * stride + i] = j;
-                            else if (dr2 < r2sq) alt[(size_t)(c1++) * stride + i] = j;
-                            else alt[(size_t)(maxn - 1 - (c2++)) * stride + i] = j;
-                        }
-                        ++cnt;
+            if (R.count > (1 << CB_OFF_BITS)) ns = lcap + 1;  // offsets would not fit the 16-bit entries: these atoms take the serial path
+            if (owner) {
+#pragma unroll 4
+                for (int t = 0; t < n; ++t) {
+                    const float4 q = cand[t];
+                    const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
+                    bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (t != self);
+                    if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
+                    if (keep) {
+                        if (ns < lcap) mine[ns] = (unsigned short)(tag + (unsigned)t);
+                        ++ns;
                     }
                 }
             }
@@ -555,13 +547,67 @@ __global__ void __launch_bounds__(32 * CB_WARPS) k_build_cell(int ncells, const 
             skip_empty(pr, po);
             issue_next();
         }
-        if (owner) {
-            if (cnt > maxn) { raise_error(err, E_TOO_MANY, orig[i], cnt); cnt = maxn; }  // md_neighbours.f90:80
-            if (PART) {
-                for (int k = 0; k < c1; ++k) nlist[(size_t)(c0 + k) * stride + i] = alt[(size_t)k * stride + i];
-                for (int k = 0; k < c2; ++k) nlist[(size_t)(c0 + c1 + k) * stride + i] = alt[(size_t)(maxn - 1 - k) * stride + i];
+        __syncwarp();
+        // ---- phase 2: exact FP64 test, lanes = survivors of one atom ----
+        const int nown = oe - o0 < 32 ? oe - o0 : 32;
+        for (int o = 0; o < nown; ++o) {
+            const int io = o0 + o;
+            const int nso = __shfl_sync(0xffffffffu, ns, o);
+            const bool is_owner = __shfl_sync(0xffffffffu, (int)owner, o) != 0;
+            if (!is_owner) continue;
+            if (nso > lcap) {  // survivor list overflowed (more than ~1.25 maxn candidates passed the prefilter): the atom is redone serially by lane 0
+                if (lane == 0) build_row<true, PART>(io, pos, posf, orig, cstart, nullptr, g, box, pf, bit1, bit2, rc2, r1sq, r2sq, maxn, stride, nlist, alt, nnum, err);
+                continue;
             }
-            nnum[i] = cnt;
+            const double4 pi = pos[io];
+            const unsigned short* lst = surv + (size_t)o * lcap;
+            int cnt = 0, c0 = 0, c1 = 0, c2 = 0;
+            for (int s0 = 0; s0 < nso; s0 += 32) {
+                const int sidx = s0 + lane;
+                bool ok = sidx < nso;
+                int j = 0;
+                double dr2 = 0.;
+                if (ok) {
+                    const unsigned e = lst[sidx];
+                    const CbRange R = rng[w][e >> CB_OFF_BITS];
+                    j = R.start + (int)(e & ((1u << CB_OFF_BITS) - 1u));
+                    const double4 pj = pos[j];
+                    double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+                    if (R.shifted) {  // min_image's own d - L / d + L (see the header of this kernel)
+                        dx += R.sx == 0.f ? 0. : (R.sx < 0.f ? -box.L[0] : box.L[0]);
+                        dy += R.sy == 0.f ? 0. : (R.sy < 0.f ? -box.L[1] : box.L[1]);
+                        dz += R.sz == 0.f ? 0. : (R.sz < 0.f ? -box.L[2] : box.L[2]);
+                    }
+                    dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    ok = dr2 < rc2;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (m == 0) continue;
+                if (!PART) {
+                    const int slot = cnt + __popc(m & lt);
+                    if (ok && slot < maxn) nlist[(size_t)slot * stride + io] = j;
+                } else {
+                    const int cls = dr2 < r1sq ? 0 : (dr2 < r2sq ? 1 : 2);
+                    const unsigned m0 = __ballot_sync(0xffffffffu, ok && cls == 0), m1 = __ballot_sync(0xffffffffu, ok && cls == 1), m2 = m & ~(m0 | m1);
+                    if (ok && cnt + __popc(m & lt) < maxn) {  // entries beyond the capacity are only counted
+                        if (cls == 0) nlist[(size_t)(c0 + __popc(m0 & lt)) * stride + io] = j;
+                        else if (cls == 1) alt[(size_t)(c1 + __popc(m1 & lt)) * stride + io] = j;
+                        else alt[(size_t)(maxn - 1 - (c2 + __popc(m2 & lt))) * stride + io] = j;
+                    }
+                    c0 += __popc(m0); c1 += __popc(m1); c2 += __popc(m2);
+                }
+                cnt += __popc(m);
+            }
+            if (cnt > maxn) {  // md_neighbours.f90:80
+                if (lane == 0) { raise_error(err, E_TOO_MANY, orig[io], cnt); nnum[io] = maxn; }
+                continue;      // the run stops at the next synchronisation; the row content is irrelevant
+            }
+            if (PART) {
+                __syncwarp();
+                for (int k = lane; k < c1; k += 32) nlist[(size_t)(c0 + k) * stride + io] = alt[(size_t)k * stride + io];
+                for (int k = lane; k < c2; k += 32) nlist[(size_t)(c0 + c1 + k) * stride + io] = alt[(size_t)(maxn - 1 - k) * stride + io];
+            }
+            if (lane == 0) nnum[io] = cnt;
         }
         __syncwarp();
     }
@@ -698,14 +744,26 @@ void nl_build(pfmds_ctx* c, NList& l) {
     const PrefD pf = nl_prefilter(c->box, l.rcut);
     KTimer kt(c, KS_NL_BUILD);
 #ifdef PFMDS_COOP
-    // cell-tiled build: large systems in cell order, three or more cells per axis, FP32 prefilter usable
-    if (c->nl_cell && !warp_per_atom && c->identity_order && pf.on && g.n[0] >= 3 && g.n[1] >= 3 && g.n[2] >= 3) {
+    // cell-tiled build: large, dense systems in cell order, three or more cells per axis, FP32 prefilter usable
+    // (sparse cells leave most lanes of a cell's warp without an atom: below 12 atoms per cell the thread-per-atom build is faster, measured on the LJ fluid)
+    if (c->nl_cell && !warp_per_atom && c->identity_order && pf.on && g.n[0] >= 3 && g.n[1] >= 3 && g.n[2] >= 3 && (double)N >= 12. * c->ncells) {
         const int nbc = (c->ncells + CB_WARPS - 1) / CB_WARPS;
         const bool check2 = !c->slab && c->h_gmask.size() == (size_t)N && !c->all_in_group(l.g2);
         const bool chk = c->slab || check2;  // slab mode keeps its masks on the device only: always test
-#define CELL_ARGS c->ncells, c->pos, c->posf, c->orig, c->cell_start, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err
-        if (l.partition) { if (chk) LAUNCH((k_build_cell<true, true>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); else LAUNCH((k_build_cell<true, false>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); }
-        else { if (chk) LAUNCH((k_build_cell<false, true>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); else LAUNCH((k_build_cell<false, false>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); }
+        int lcap = l.maxn + l.maxn / 4 + 16;  // prefilter survivors per atom kept in shared memory (16-bit entries); more: serial path
+        if (lcap > 320) lcap = 320;
+        lcap = (lcap + 7) & ~7;
+        const size_t dyn = (size_t)CB_WARPS * 32 * lcap * sizeof(unsigned short);
+#define CELL_ARGS c->ncells, c->pos, c->posf, c->orig, c->cell_start, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err, lcap
+#ifdef __CUDACC__
+#define CELL_LAUNCH(PT, CH) do { CK(cudaFuncSetAttribute(k_build_cell<PT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+        k_build_cell<PT, CH><<<nbc, 32 * CB_WARPS, dyn, c->st>>>(CELL_ARGS); } while (0)
+#else
+#define CELL_LAUNCH(PT, CH) do { emu_dynamic_smem(dyn); LAUNCH((k_build_cell<PT, CH>), nbc, 32 * CB_WARPS, c->st, CELL_ARGS); } while (0)
+#endif
+        if (l.partition) { if (chk) CELL_LAUNCH(true, true); else CELL_LAUNCH(true, false); }
+        else { if (chk) CELL_LAUNCH(false, true); else CELL_LAUNCH(false, false); }
+#undef CELL_LAUNCH
 #undef CELL_ARGS
         c->launches += 1;
         l.built = true;
