@@ -476,7 +476,8 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bo
         PhaseTimer t(c, 0);
         const bool kicked = c->kick_req.done;
         if (kind == PFMDS_NVT && c->nhc_fusable) {
-            if (kicked) integ_nvt_close_only(c, dt, c->kick_req.nparts, c->part + c->part_cap / 2);
+            if (kicked && c->kick_req.closed) {}   // the force kernel's last block summed the partials and ran the chain update
+            else if (kicked) integ_nvt_close_only(c, dt, c->kick_req.nparts, c->part + c->part_cap / 2);
             else integ_nvt_kick_close(c, dt);
             c->nhc_pending = true;
             c->nhc_ke_valid = true;
@@ -706,8 +707,8 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         CK(cudaMalloc(&c->part, sizeof(double) * 16 * nparts));
         c->part_cap = 16 * nparts;
         CK(cudaMalloc(&c->red, sizeof(double) * 64));
-        CK(cudaMalloc(&c->err, sizeof(int) * PFMDS_ERRW));
-        CK(cudaMemset(c->err, 0, sizeof(int) * PFMDS_ERRW));
+        CK(cudaMalloc(&c->err, sizeof(int) * (PFMDS_ERRW + 4)));   // error word + the block ticket counter of the fused kick
+        CK(cudaMemset(c->err, 0, sizeof(int) * (PFMDS_ERRW + 4)));
         CK(cudaMemset(c->frc, 0, sizeof(double4) * S));
         std::vector<double4> hp(S, make_double4(0, 0, 0, 0)), hv(S, make_double4(0, 0, 0, 1));
         std::vector<int> ho(S, 0);
@@ -1498,8 +1499,8 @@ int pfmds_create_slab(pfmds_ctx** out, int device, int rank, int nranks, const c
         size_t nparts = (S + 127) / 128 + RED_BLOCKS;
         CK(cudaMalloc(&c->part, sizeof(double) * 16 * nparts));
         CK(cudaMalloc(&c->red, sizeof(double) * 64));
-        CK(cudaMalloc(&c->err, sizeof(int) * PFMDS_ERRW));
-        CK(cudaMemset(c->err, 0, sizeof(int) * PFMDS_ERRW));
+        CK(cudaMalloc(&c->err, sizeof(int) * (PFMDS_ERRW + 4)));   // error word + the block ticket counter of the fused kick
+        CK(cudaMemset(c->err, 0, sizeof(int) * (PFMDS_ERRW + 4)));
         CK(cudaMemset(c->frc, 0, sizeof(double4) * S));
         std::vector<double4> hp(S, make_double4(0, 0, 0, 0)), hv(S, make_double4(0, 0, 0, 1));
         std::vector<int> ho(S, 0);

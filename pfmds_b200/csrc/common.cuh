@@ -117,6 +117,43 @@ struct REBp { double A, Q, alpha, B[3], beta[3], T, g[6], R1, R2; };  // rebosc,
 #define NHC_MAXF 4
 struct NhcPack { int n; uint32_t bit[NHC_MAXF]; double* state[NHC_MAXF]; int M[NHC_MAXF]; int L[NHC_MAXF]; double T[NHC_MAXF]; };
 
+// ---- Nose-Hoover chain half step: md_integrators.f90:200-245 ---------------------------------------
+// state = x[M], v[M], q[M], s, ke_cached, s_pending.  Returns the velocity scale s = exp(-v1 dt/2).
+__device__ __forceinline__ double nhc_chain(double* state, int M, int L, double temperature, double ke, double ts2, double ts3, double ts4) {
+    double* x = state;
+    double* v = state + M;
+    const double* q = state + 2 * M;
+    double kt = PFMDS_KB * temperature;
+    double kedif = 2. * ke - 3. * L * kt, b = 0.;
+    if (M == 1) {
+        v[0] = v[0] + kedif / q[0] * ts3;
+    } else {
+        v[M - 1] = v[M - 1] + (q[M - 2] * v[M - 2] * v[M - 2] - kt) / q[M - 1] * ts3;
+        for (int i = M - 2; i >= 1; --i) {
+            b = exp(-v[i + 1] * ts4);
+            v[i] = v[i] * (b * b) + (q[i - 1] * v[i - 1] * v[i - 1] - kt) / q[i] * ts3 * b;
+        }
+        b = exp(-v[1] * ts4);
+        v[0] = v[0] * (b * b) + kedif / q[0] * ts3 * b;
+    }
+    double s = exp(-v[0] * ts2);
+    state[3 * M] = s;
+    kedif = 2. * ke * (s * s) - 3. * L * kt;
+    for (int i = 0; i < M; ++i) x[i] = x[i] + v[i] * ts2;
+    if (M == 1) {
+        v[0] = v[0] + kedif / q[0] * ts3;
+    } else {
+        v[0] = v[0] * (b * b) + kedif / q[0] * ts3 * b;  // the reference reuses the last b here (:236)
+        for (int i = 1; i <= M - 2; ++i) {
+            b = exp(-v[i + 1] * ts4);
+            v[i] = v[i] * (b * b) + (q[i - 1] * v[i - 1] * v[i - 1] - kt) / q[i] * ts3 * b;
+        }
+        v[M - 1] = v[M - 1] + (q[M - 2] * v[M - 2] * v[M - 2] - kt) / q[M - 1] * ts3;
+    }
+    state[3 * M + 1] = ke * (s * s);  // kinetic energy of the group after the scaling
+    return s;
+}
+
 // Slab decomposition, fused halo: what a compute kernel needs to store its border atoms' results straight into
 // the neighbours' ghost slots (IPC-mapped peer memory over NVLink), publish a sequence number when the whole grid
 // is done, and/or wait for the neighbours' sequence number before it starts.  All zeros = single-GPU behaviour.

@@ -107,7 +107,7 @@ struct pfmds_ctx {
     int nl_warp_n = 200000;         // below: warp-per-atom list build; from it on: thread per atom
     // closing half kick fused into the last force kernel of the step (forces.cu k_rjl_force_x): requested by do_step, honoured by
     // forces_interaction when that interaction is a large-system rjl pass; `done` tells do_step to skip integ_kick / k_kick_ke
-    struct KickReq { bool active = false, done = false; int last_inter = -1, nparts = 0; double ts2 = 0; NhcPack P{}; } kick_req;
+    struct KickReq { bool active = false, done = false, closed = false; int last_inter = -1, nparts = 0; double ts2 = 0; NhcPack P{}; } kick_req;
     bool fuse_kick = true;          // PFMDS_FUSE_KICK=0: separate kick kernels
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
     bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)

@@ -665,7 +665,9 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __
 // the step's last force kernel: the thread has the atom's total force in registers, so k_kick_ke's launch and its read of frc go
 // away (integrate.cu k_kick_ke, same expressions: velocities are the unfused path's bit for bit; the KE partials are summed per
 // block of this grid, in block order by k_nhc_close: reproducible from run to run).
-struct KickFuse { double4* vel; const uint32_t* gmask; uint32_t bxyz, bz; double ts2; NhcPack P; double* kpart; };
+// Under NVT the block that finishes last also closes the thermostat step: it sums the per-block partials in block order (fixed order:
+// reproducible) and runs the chain update (k_nhc_close's work, without its launch).
+struct KickFuse { double4* vel; const uint32_t* gmask; uint32_t bxyz, bz; double ts2; NhcPack P; double* kpart; unsigned int* done; double ts3, ts4; };
 template <class CT, int MB, bool E, bool KICK>  // CT = RjlF (second generation) or RjlG (third)
 __global__ void __launch_bounds__(FT, MB) k_rjl_force_x(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                         WrapC W, SlabDev S, int overwrite, double erep, double xi, double* __restrict__ part, KickFuse K) {
@@ -732,6 +734,31 @@ __global__ void __launch_bounds__(FT, MB) k_rjl_force_x(int N, const double4* __
                 double sk = block_sum(ke[k]);
                 if (threadIdx.x == 0) K.kpart[(size_t)blockIdx.x * NHC_MAXF + k] = sk;
             }
+#ifdef PFMDS_COOP
+        if (K.P.n > 0) {
+            __shared__ bool last;
+            if (threadIdx.x == 0) {
+                __threadfence();                                   // this block's partials before its ticket
+                last = atomicAdd(K.done, 1u) == gridDim.x - 1;
+            }
+            __syncthreads();
+            if (last) {
+                __threadfence();                                   // every other block's partials after their tickets
+                for (int k = 0; k < K.P.n; ++k) {
+                    double sk = 0.;
+                    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) sk += reinterpret_cast<const volatile double*>(K.kpart)[(size_t)b * NHC_MAXF + k];
+                    sk = block_sum(sk);
+                    if (threadIdx.x == 0) {
+                        double* st = K.P.state[k];
+                        const int M = K.P.M[k];
+                        st[3 * M + 2] = nhc_chain(st, M, K.P.L[k], K.P.T[k], sk, K.ts2, K.ts3, K.ts4);
+                    }
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) *K.done = 0u;                // ready for the next launch
+            }
+        }
+#endif
     }
 }
 template <int SPLIT, class CT>
@@ -1164,6 +1191,10 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         if (kick) {
             KF.vel = c->vel; KF.gmask = c->gmask; KF.bxyz = 1u << (c->xyz_moving - 1); KF.bz = 1u << (c->z_moving - 1); KF.ts2 = c->kick_req.ts2;
             KF.P = c->kick_req.P; KF.kpart = c->part + c->part_cap / 2;
+            KF.done = reinterpret_cast<unsigned int*>(c->err + PFMDS_ERRW); KF.ts3 = c->kick_req.ts2 / 2; KF.ts4 = c->kick_req.ts2 / 4;
+#ifdef PFMDS_COOP
+            c->kick_req.closed = KF.P.n > 0;   // the force kernel's last block runs the chain update itself
+#endif
             c->kick_req.done = true;
             c->kick_req.nparts = nb;
         }

@@ -63,6 +63,7 @@ static inline double __hiloint2double(int hi, int lo) { unsigned long long v = (
 #include <sched.h>
 #include <atomic>
 static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __nanosleep(unsigned) { sched_yield(); }
 // separately rounded product / sum: the emulated builds use -ffp-contract=off, so plain operators do that
 static inline double __dmul_rn(double a, double b) { return a * b; }

@@ -64,42 +64,7 @@ void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out) {
     if (c->slab) slab_allreduce_sum(c, d_out, 1);
 }
 
-// ---- Nose-Hoover chain half step: md_integrators.f90:200-245 ---------------------------------------
-// state = x[M], v[M], q[M], s, ke_cached, s_pending.  Returns the velocity scale s = exp(-v1 dt/2).
-__device__ double nhc_chain(double* state, int M, int L, double temperature, double ke, double ts2, double ts3, double ts4) {
-    double* x = state;
-    double* v = state + M;
-    const double* q = state + 2 * M;
-    double kt = PFMDS_KB * temperature;
-    double kedif = 2. * ke - 3. * L * kt, b = 0.;
-    if (M == 1) {
-        v[0] = v[0] + kedif / q[0] * ts3;
-    } else {
-        v[M - 1] = v[M - 1] + (q[M - 2] * v[M - 2] * v[M - 2] - kt) / q[M - 1] * ts3;
-        for (int i = M - 2; i >= 1; --i) {
-            b = exp(-v[i + 1] * ts4);
-            v[i] = v[i] * (b * b) + (q[i - 1] * v[i - 1] * v[i - 1] - kt) / q[i] * ts3 * b;
-        }
-        b = exp(-v[1] * ts4);
-        v[0] = v[0] * (b * b) + kedif / q[0] * ts3 * b;
-    }
-    double s = exp(-v[0] * ts2);
-    state[3 * M] = s;
-    kedif = 2. * ke * (s * s) - 3. * L * kt;
-    for (int i = 0; i < M; ++i) x[i] = x[i] + v[i] * ts2;
-    if (M == 1) {
-        v[0] = v[0] + kedif / q[0] * ts3;
-    } else {
-        v[0] = v[0] * (b * b) + kedif / q[0] * ts3 * b;  // the reference reuses the last b here (:236)
-        for (int i = 1; i <= M - 2; ++i) {
-            b = exp(-v[i + 1] * ts4);
-            v[i] = v[i] * (b * b) + (q[i - 1] * v[i - 1] * v[i - 1] - kt) / q[i] * ts3 * b;
-        }
-        v[M - 1] = v[M - 1] + (q[M - 2] * v[M - 2] * v[M - 2] - kt) / q[M - 1] * ts3;
-    }
-    state[3 * M + 1] = ke * (s * s);  // kinetic energy of the group after the scaling
-    return s;
-}
+// (nhc_chain, the Nose-Hoover chain half step of md_integrators.f90:200-245, lives in common.cuh: the fused force + kick kernel of forces.cu runs it too)
 // One block sums the KE partials (fixed order), thread 0 runs the chain.
 __global__ void k_nhc(int nparts, const double* __restrict__ part, double* state, int M, int L, double temperature, double ts2, double ts3,
                       double ts4) {

@@ -439,7 +439,7 @@ __device__ __forceinline__ void cb_wait(unsigned long long* bar, unsigned parity
 // executes the FP64 block max-over-lanes times per 32 candidates with 13 of 32 lanes active on average -- ncu, profiles/r2e_*.)
 #define CB_OFF_BITS 11                      // offset of a candidate inside its range (three cells): ranges longer than 2048 atoms use k_build_mask
 template <bool PART, bool CHECK2>
-__global__ void __launch_bounds__(32 * CB_WARPS) k_build_cell(int ncells, const double4* __restrict__ pos, const float4* __restrict__ posf,
+__global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, const double4* __restrict__ pos, const float4* __restrict__ posf,
                                                               const int* __restrict__ orig, const int* __restrict__ cstart, GridD g, BoxD box, PrefD pf,
                                                               uint32_t bit1, uint32_t bit2, double rc2, double r1sq, double r2sq, int maxn, size_t stride,
                                                               int* __restrict__ nlist, int* __restrict__ alt, int* __restrict__ nnum, int* err, int lcap) {
@@ -498,26 +498,77 @@ __global__ void __launch_bounds__(32 * CB_WARPS) k_build_cell(int ncells, const 
             owner = (__float_as_uint(pif.w) & (bit1 | PFMDS_GHOST)) == bit1;
             if (!owner) nnum[i] = 0;
         }
-        // ---- phase 1: FP32 prefilter, lanes = atoms of the cell ----
-        int ns = 0;                                   // survivors of this lane's atom so far (may pass lcap: the atom is then redone by the slow path)
+        // Row state of this lane's atom (phase 2 reads and updates it through shuffles): entries so far, per class
+        int cnt = 0, c0 = 0, c1 = 0, c2 = 0;
+        bool ovf = false;                             // a survivor list overflowed: the atom is redone by the serial routine at the end
+        int ns = 0;                                   // survivors of this lane's atom in the current plane of cells
         unsigned short* const mine = surv + (size_t)lane * lcap;
-        int qr = 0, qo = 0, k_issue = 0, k_done = 0;  // piece being fetched (q*) / processed (p*)
-        auto skip_empty = [&](int& r, int& o) { while (r < 18 && o >= rng[w][r].count) { ++r; o = 0; } };
-        skip_empty(qr, qo);
-        auto issue_next = [&]() {
-            if (qr >= 18) return;
-            const CbRange R = rng[w][qr];
-            const int n = R.count - qo < CB_CAP ? R.count - qo : CB_CAP;
-            cb_issue(buf[w][k_issue & 1], posf + R.start + qo, n, &bars[w][k_issue & 1], lane);
-            ++k_issue;
-            qo += n;
-            skip_empty(qr, qo);
+        const int nown = oe - o0 < 32 ? oe - o0 : 32;
+        // ---- phase 2: exact FP64 test, lanes = survivors of one atom; called after each plane (oz) of nine cells ----
+        auto flush = [&]() {
+            __syncwarp();
+            for (int o = 0; o < nown; ++o) {
+                const int nso = __shfl_sync(0xffffffffu, ns, o);
+                if (nso == 0 || __shfl_sync(0xffffffffu, (int)ovf, o)) continue;
+                const int io = o0 + o;
+                int rc = __shfl_sync(0xffffffffu, cnt, o), r0 = __shfl_sync(0xffffffffu, c0, o), r1 = __shfl_sync(0xffffffffu, c1, o),
+                    r2 = __shfl_sync(0xffffffffu, c2, o);
+                const double4 pi = pos[io];
+                const unsigned short* lst = surv + (size_t)o * lcap;
+                for (int s0 = 0; s0 < nso; s0 += 32) {
+                    const int sidx = s0 + lane;
+                    bool ok = sidx < nso;
+                    int j = 0;
+                    double dr2 = 0.;
+                    if (ok) {
+                        const unsigned e = lst[sidx];
+                        const CbRange R = rng[w][e >> CB_OFF_BITS];
+                        j = R.start + (int)(e & ((1u << CB_OFF_BITS) - 1u));
+                        const double4 pj = pos[j];
+                        double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+                        if (R.shifted) {  // min_image's own d - L / d + L (see the header of this kernel)
+                            dx += R.sx == 0.f ? 0. : (R.sx < 0.f ? -box.L[0] : box.L[0]);
+                            dy += R.sy == 0.f ? 0. : (R.sy < 0.f ? -box.L[1] : box.L[1]);
+                            dz += R.sz == 0.f ? 0. : (R.sz < 0.f ? -box.L[2] : box.L[2]);
+                        }
+                        dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        ok = dr2 < rc2;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (m == 0) continue;
+                    if (!PART) {
+                        const int slot = rc + __popc(m & lt);
+                        if (ok && slot < maxn) nlist[(size_t)slot * stride + io] = j;
+                    } else {
+                        const int cls = dr2 < r1sq ? 0 : (dr2 < r2sq ? 1 : 2);
+                        const unsigned m0 = __ballot_sync(0xffffffffu, ok && cls == 0), m1 = __ballot_sync(0xffffffffu, ok && cls == 1), m2 = m & ~(m0 | m1);
+                        if (ok && rc + __popc(m & lt) < maxn) {  // entries beyond the capacity are only counted
+                            if (cls == 0) nlist[(size_t)(r0 + __popc(m0 & lt)) * stride + io] = j;
+                            else if (cls == 1) alt[(size_t)(r1 + __popc(m1 & lt)) * stride + io] = j;
+                            else alt[(size_t)(maxn - 1 - (r2 + __popc(m2 & lt))) * stride + io] = j;
+                        }
+                        r0 += __popc(m0); r1 += __popc(m1); r2 += __popc(m2);
+                    }
+                    rc += __popc(m);
+                }
+                if (lane == o) { cnt = rc; c0 = r0; c1 = r1; c2 = r2; }
+            }
+            ns = 0;
+            __syncwarp();
         };
+        // ---- phase 1: FP32 prefilter, lanes = atoms of the cell ----
+        int qr = 0, qo = 0, k_issue = 0, k_done = 0;  // piece being fetched (q*) / processed (p*)
+#define CB_SKIP_EMPTY(r, o) while ((r) < 18 && (o) >= rng[w][(r)].count) { ++(r); (o) = 0; }
+#define CB_ISSUE_NEXT() do { if (qr < 18) { const int s_ = rng[w][qr].start, c_ = rng[w][qr].count; const int n_ = c_ - qo < CB_CAP ? c_ - qo : CB_CAP; \
+            cb_issue(buf[w][k_issue & 1], posf + s_ + qo, n_, &bars[w][k_issue & 1], lane); ++k_issue; qo += n_; CB_SKIP_EMPTY(qr, qo) } } while (0)
+        CB_SKIP_EMPTY(qr, qo)
         int pr = 0, po = 0;
-        skip_empty(pr, po);
-        issue_next();
-        issue_next();
+        CB_SKIP_EMPTY(pr, po)
+        CB_ISSUE_NEXT();
+        CB_ISSUE_NEXT();
+        int plane = pr / 6;
         while (pr < 18) {
+            if (pr / 6 != plane) { flush(); plane = pr / 6; }
             const CbRange R = rng[w][pr];
             const int n = R.count - po < CB_CAP ? R.count - po : CB_CAP;
             const int b = k_done & 1;
@@ -527,87 +578,65 @@ __global__ void __launch_bounds__(32 * CB_WARPS) k_build_cell(int ncells, const 
             const int self = i - (R.start + po);          // this lane's own atom as a candidate of the piece (negative / >= n: not in it)
             const unsigned tag = ((unsigned)pr << CB_OFF_BITS) + (unsigned)po;
             const float ox = pif.x - R.sx, oy = pif.y - R.sy, oz = pif.z - R.sz;  // candidate + s - owner = candidate - (owner - s)
-            if (R.count > (1 << CB_OFF_BITS)) ns = lcap + 1;  // offsets would not fit the 16-bit entries: these atoms take the serial path
-            if (owner) {
-#pragma unroll 4
-                for (int t = 0; t < n; ++t) {
-                    const float4 q = cand[t];
-                    const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
-                    bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (t != self);
-                    if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
-                    if (keep) {
-                        if (ns < lcap) mine[ns] = (unsigned short)(tag + (unsigned)t);
-                        ++ns;
+            if (R.count > (1 << CB_OFF_BITS)) ovf = owner;  // offsets would not fit the 16-bit entries: these atoms take the serial path
+            if (owner && !ovf) {
+                for (int g0 = 0; g0 < n; g0 += 32) {
+                    const int m = n - g0 < 32 ? n - g0 : 32;
+                    uint32_t mask = 0;
+                    if (m == 32) {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const float4 q = cand[g0 + t];
+                            const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
+                            bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (g0 + t != self);
+                            if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
+                            mask |= keep ? (1u << t) : 0u;
+                        }
+                    } else {
+                        for (int t = 0; t < m; ++t) {
+                            const float4 q = cand[g0 + t];
+                            const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
+                            bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (g0 + t != self);
+                            if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
+                            mask |= keep ? (1u << t) : 0u;
+                        }
+                    }
+                    if (ns + __popc(mask) > lcap) { ovf = true; mask = 0; }
+                    while (mask) {  // append the survivors of this group, in candidate order
+                        const int t = PFMDS_FFS(mask) - 1;
+                        mask &= mask - 1u;
+                        mine[ns++] = (unsigned short)(tag + (unsigned)(g0 + t));
                     }
                 }
             }
             __syncwarp();  // every lane is done with this stage buffer: it may be refilled
             ++k_done;
             po += n;
-            skip_empty(pr, po);
-            issue_next();
+            CB_SKIP_EMPTY(pr, po)
+            CB_ISSUE_NEXT();
         }
-        __syncwarp();
-        // ---- phase 2: exact FP64 test, lanes = survivors of one atom ----
-        const int nown = oe - o0 < 32 ? oe - o0 : 32;
+#undef CB_SKIP_EMPTY
+#undef CB_ISSUE_NEXT
+        flush();
+        // ---- row epilogue, one atom after the other (lanes share the copy of the staged classes) ----
         for (int o = 0; o < nown; ++o) {
+            if (!__shfl_sync(0xffffffffu, (int)owner, o)) continue;
             const int io = o0 + o;
-            const int nso = __shfl_sync(0xffffffffu, ns, o);
-            const bool is_owner = __shfl_sync(0xffffffffu, (int)owner, o) != 0;
-            if (!is_owner) continue;
-            if (nso > lcap) {  // survivor list overflowed (more than ~1.25 maxn candidates passed the prefilter): the atom is redone serially by lane 0
+            if (__shfl_sync(0xffffffffu, (int)ovf, o)) {
                 if (lane == 0) build_row<true, PART>(io, pos, posf, orig, cstart, nullptr, g, box, pf, bit1, bit2, rc2, r1sq, r2sq, maxn, stride, nlist, alt, nnum, err);
                 continue;
             }
-            const double4 pi = pos[io];
-            const unsigned short* lst = surv + (size_t)o * lcap;
-            int cnt = 0, c0 = 0, c1 = 0, c2 = 0;
-            for (int s0 = 0; s0 < nso; s0 += 32) {
-                const int sidx = s0 + lane;
-                bool ok = sidx < nso;
-                int j = 0;
-                double dr2 = 0.;
-                if (ok) {
-                    const unsigned e = lst[sidx];
-                    const CbRange R = rng[w][e >> CB_OFF_BITS];
-                    j = R.start + (int)(e & ((1u << CB_OFF_BITS) - 1u));
-                    const double4 pj = pos[j];
-                    double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-                    if (R.shifted) {  // min_image's own d - L / d + L (see the header of this kernel)
-                        dx += R.sx == 0.f ? 0. : (R.sx < 0.f ? -box.L[0] : box.L[0]);
-                        dy += R.sy == 0.f ? 0. : (R.sy < 0.f ? -box.L[1] : box.L[1]);
-                        dz += R.sz == 0.f ? 0. : (R.sz < 0.f ? -box.L[2] : box.L[2]);
-                    }
-                    dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    ok = dr2 < rc2;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (m == 0) continue;
-                if (!PART) {
-                    const int slot = cnt + __popc(m & lt);
-                    if (ok && slot < maxn) nlist[(size_t)slot * stride + io] = j;
-                } else {
-                    const int cls = dr2 < r1sq ? 0 : (dr2 < r2sq ? 1 : 2);
-                    const unsigned m0 = __ballot_sync(0xffffffffu, ok && cls == 0), m1 = __ballot_sync(0xffffffffu, ok && cls == 1), m2 = m & ~(m0 | m1);
-                    if (ok && cnt + __popc(m & lt) < maxn) {  // entries beyond the capacity are only counted
-                        if (cls == 0) nlist[(size_t)(c0 + __popc(m0 & lt)) * stride + io] = j;
-                        else if (cls == 1) alt[(size_t)(c1 + __popc(m1 & lt)) * stride + io] = j;
-                        else alt[(size_t)(maxn - 1 - (c2 + __popc(m2 & lt))) * stride + io] = j;
-                    }
-                    c0 += __popc(m0); c1 += __popc(m1); c2 += __popc(m2);
-                }
-                cnt += __popc(m);
-            }
-            if (cnt > maxn) {  // md_neighbours.f90:80
-                if (lane == 0) { raise_error(err, E_TOO_MANY, orig[io], cnt); nnum[io] = maxn; }
+            const int rc = __shfl_sync(0xffffffffu, cnt, o), r0 = __shfl_sync(0xffffffffu, c0, o), r1 = __shfl_sync(0xffffffffu, c1, o),
+                      r2 = __shfl_sync(0xffffffffu, c2, o);
+            if (rc > maxn) {  // md_neighbours.f90:80
+                if (lane == 0) { raise_error(err, E_TOO_MANY, orig[io], rc); nnum[io] = maxn; }
                 continue;      // the run stops at the next synchronisation; the row content is irrelevant
             }
             if (PART) {
-                __syncwarp();
-                for (int k = lane; k < c1; k += 32) nlist[(size_t)(c0 + k) * stride + io] = alt[(size_t)k * stride + io];
-                for (int k = lane; k < c2; k += 32) nlist[(size_t)(c0 + c1 + k) * stride + io] = alt[(size_t)(maxn - 1 - k) * stride + io];
+                for (int k = lane; k < r1; k += 32) nlist[(size_t)(r0 + k) * stride + io] = alt[(size_t)k * stride + io];
+                for (int k = lane; k < r2; k += 32) nlist[(size_t)(r0 + r1 + k) * stride + io] = alt[(size_t)(maxn - 1 - k) * stride + io];
             }
-            if (lane == 0) nnum[io] = cnt;
+            if (lane == 0) nnum[io] = rc;
         }
         __syncwarp();
     }
@@ -750,9 +779,8 @@ void nl_build(pfmds_ctx* c, NList& l) {
         const int nbc = (c->ncells + CB_WARPS - 1) / CB_WARPS;
         const bool check2 = !c->slab && c->h_gmask.size() == (size_t)N && !c->all_in_group(l.g2);
         const bool chk = c->slab || check2;  // slab mode keeps its masks on the device only: always test
-        int lcap = l.maxn + l.maxn / 4 + 16;  // prefilter survivors per atom kept in shared memory (16-bit entries); more: serial path
-        if (lcap > 320) lcap = 320;
-        lcap = (lcap + 7) & ~7;
+        int lcap = 64;                        // prefilter survivors per atom and plane of nine cells kept in shared memory (16-bit entries); more: serial path
+        if (l.maxn > 120) lcap = 128;
         const size_t dyn = (size_t)CB_WARPS * 32 * lcap * sizeof(unsigned short);
 #define CELL_ARGS c->ncells, c->pos, c->posf, c->orig, c->cell_start, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err, lcap
 #ifdef __CUDACC__
