@@ -57,7 +57,6 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     c->lj1g_pipe = env_int("PFMDS_LJ1G_PIPE", 1) != 0;
     c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
     c->nl_cell = env_int("PFMDS_NL_CELL", 1) != 0;
-    c->fuse_kick = env_int("PFMDS_FUSE_KICK", 1) != 0;
     // 2 is the default: the third generation (node-table exponentials) removes 13 of 43 FP64 instructions per pair but its table
     // look-ups double the L1 data-pipe wavefronts, and that pipe is what bounds these kernels (ncu, profiles/r2b_*): measured
     // 0.343 against 0.277 ms (density) and 0.362 against 0.360 ms (force) per launch at 10^6 atoms
@@ -399,7 +398,11 @@ void update_lists(pfmds_ctx* c, int step) {
             all &= rb;
         }
     }
-    if (c->slab && !any) slab_exchange(c, 0);  // ghost positions follow their owners every step
+    if (c->slab && !any) {  // ghost positions follow their owners every step
+        // lean halo: when the first kernel that reads positions is a large-system rjl density pass, it waits for the ghosts itself
+        slab_set_consumer_waits(c, !c->inter.empty() && c->inter[0].kind == K_RJL && c->N >= c->small_n && c->rjl_gen != 1);
+        slab_exchange(c, 0);
+    }
     if (any) {
         PhaseTimer t(c, 2);
         if (c->slab) slab_redistribute(c);   // finalize_slab guarantees any == all
@@ -460,29 +463,16 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bo
     {
         PhaseTimer t(c, 4);
         if (step % c->zero_momentum_period == 0) integ_zero_momentum(c);
-        // The closing half kick can ride in the epilogue of the step's last force kernel when that is a large-system rjl pass over
-        // every atom (forces.cu decides and sets kick_req.done); under NVT with disjoint thermostat groups it also produces the KE partials
-        c->kick_req = pfmds_ctx::KickReq{};
-        if (step != 0 && c->fuse_kick && !c->slab && !c->inter.empty() && c->inter.back().kind == K_RJL && c->changes.empty() &&
-            (int)group_of(c, c->inter.back().nl[0].g1).size() == c->N) {
-            c->kick_req.active = true;
-            c->kick_req.last_inter = (int)c->inter.size() - 1;
-            c->kick_req.ts2 = dt / 2;
-            if (kind == PFMDS_NVT && c->nhc_fusable) c->kick_req.P = integ_nhc_pack(c);
-        }
         compute_forces(c, with_energy);
     }
     if (step != 0) {
         PhaseTimer t(c, 0);
-        const bool kicked = c->kick_req.done;
         if (kind == PFMDS_NVT && c->nhc_fusable) {
-            if (kicked && c->kick_req.closed) {}   // the force kernel's last block summed the partials and ran the chain update
-            else if (kicked) integ_nvt_close_only(c, dt, c->kick_req.nparts, c->part + c->part_cap / 2);
-            else integ_nvt_kick_close(c, dt);
+            integ_nvt_kick_close(c, dt);
             c->nhc_pending = true;
             c->nhc_ke_valid = true;
         } else {
-            if (!kicked) integ_kick(c, dt);
+            integ_kick(c, dt);
             if (kind == PFMDS_NVT)
                 for (auto& th : c->nhc) integ_nhc_half(c, th, dt);
             if (kind == PFMDS_NVMS) integ_quench(c);
@@ -707,8 +697,8 @@ int pfmds_create(pfmds_ctx** out, int device, int n_atoms, const double* pos, co
         CK(cudaMalloc(&c->part, sizeof(double) * 16 * nparts));
         c->part_cap = 16 * nparts;
         CK(cudaMalloc(&c->red, sizeof(double) * 64));
-        CK(cudaMalloc(&c->err, sizeof(int) * (PFMDS_ERRW + 4)));   // error word + the block ticket counter of the fused kick
-        CK(cudaMemset(c->err, 0, sizeof(int) * (PFMDS_ERRW + 4)));
+        CK(cudaMalloc(&c->err, sizeof(int) * PFMDS_ERRW));
+        CK(cudaMemset(c->err, 0, sizeof(int) * PFMDS_ERRW));
         CK(cudaMemset(c->frc, 0, sizeof(double4) * S));
         std::vector<double4> hp(S, make_double4(0, 0, 0, 0)), hv(S, make_double4(0, 0, 0, 1));
         std::vector<int> ho(S, 0);
@@ -1499,8 +1489,8 @@ int pfmds_create_slab(pfmds_ctx** out, int device, int rank, int nranks, const c
         size_t nparts = (S + 127) / 128 + RED_BLOCKS;
         CK(cudaMalloc(&c->part, sizeof(double) * 16 * nparts));
         CK(cudaMalloc(&c->red, sizeof(double) * 64));
-        CK(cudaMalloc(&c->err, sizeof(int) * (PFMDS_ERRW + 4)));   // error word + the block ticket counter of the fused kick
-        CK(cudaMemset(c->err, 0, sizeof(int) * (PFMDS_ERRW + 4)));
+        CK(cudaMalloc(&c->err, sizeof(int) * PFMDS_ERRW));
+        CK(cudaMemset(c->err, 0, sizeof(int) * PFMDS_ERRW));
         CK(cudaMemset(c->frc, 0, sizeof(double4) * S));
         std::vector<double4> hp(S, make_double4(0, 0, 0, 0)), hv(S, make_double4(0, 0, 0, 1));
         std::vector<int> ho(S, 0);

@@ -167,17 +167,25 @@ struct SlabDev {
     unsigned long long timeout_ns;  // give up (error 31) after this long: host-side skew between the ranks (module load, graph
                                     // instantiation, a rank writing a snapshot) must fit inside it; PFMDS_SLAB_TIMEOUT_S, default 120 s
 };
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(PFMDS_EMU_WARP)  // device, or the lock-step host replay (ranks as threads: the flags are real)
+__device__ __forceinline__ unsigned long long pf_now_ns() {
+#ifdef __CUDA_ARCH__
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#else
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+#endif
+}
 __device__ __forceinline__ void slab_wait(const SlabDev& S) {
     if (S.wait_seq > 0) {
         if (threadIdx.x == 0) {
-            unsigned long long t0, t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            const unsigned long long t0 = pf_now_ns();
             while (*reinterpret_cast<const volatile int*>(S.wait_a) < S.wait_seq || *reinterpret_cast<const volatile int*>(S.wait_b) < S.wait_seq) {
                 if (*reinterpret_cast<volatile int*>(S.err) != 0) break;  // the run is already failing: do not wait once per block
                 __nanosleep(100);
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                if (t - t0 > S.timeout_ns) { raise_error(S.err, 31, S.wait_seq, 1); break; }
+                if (pf_now_ns() - t0 > S.timeout_ns) { raise_error(S.err, 31, S.wait_seq, 1); break; }
             }
             __threadfence_system();
         }
@@ -206,6 +214,6 @@ __device__ __forceinline__ void slab_signal(const SlabDev& S, bool pushed) {
 #else
 static inline void slab_wait(const SlabDev&) {}
 static inline void slab_signal(const SlabDev&, bool) {}
-#endif  // __CUDACC__
+#endif
 
 struct ListView { const int* nlist; const int* nnum; size_t stride; };

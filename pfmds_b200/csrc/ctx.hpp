@@ -105,10 +105,6 @@ struct pfmds_ctx {
     bool nl_cell = true;            // cell-tiled list build (one warp per cell, candidates staged in shared memory by bulk copies) for large systems; PFMDS_NL_CELL=0: k_build_mask
     int small_n = 100000;           // below: 8 lanes per atom in the pair kernels (latency bound); from it on: thread per atom, pipelined
     int nl_warp_n = 200000;         // below: warp-per-atom list build; from it on: thread per atom
-    // closing half kick fused into the last force kernel of the step (forces.cu k_rjl_force_x): requested by do_step, honoured by
-    // forces_interaction when that interaction is a large-system rjl pass; `done` tells do_step to skip integ_kick / k_kick_ke
-    struct KickReq { bool active = false, done = false, closed = false; int last_inter = -1, nparts = 0; double ts2 = 0; NhcPack P{}; } kick_req;
-    bool fuse_kick = true;          // PFMDS_FUSE_KICK=0: separate kick kernels
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
     bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)
     bool finalized = false;
@@ -166,6 +162,8 @@ bool slab_fused(pfmds_ctx* c);
 // stage 0: kick+drift pushes positions; 1: rjl density waits for positions, pushes 1/Eb; 2: rjl force waits for 1/Eb
 SlabDev slab_dev(pfmds_ctx* c, int stage);
 bool slab_pos_pushed_by_kick(pfmds_ctx* c, bool rebuild_step);
+SlabDev slab_wait_dev(pfmds_ctx* c, int field);          // lean halo: the consumer kernel waits for its ghosts itself
+void slab_set_consumer_waits(pfmds_ctx* c, bool on);
 void slab_allreduce_sum(pfmds_ctx* c, double* d, int n);
 void slab_allreduce_max(pfmds_ctx* c, double* d, int n);
 void slab_allreduce_max_int(pfmds_ctx* c, int* d, int n);
@@ -196,8 +194,6 @@ void integ_quench(pfmds_ctx* c);
 void integ_zero_momentum(pfmds_ctx* c);
 void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step);
 void integ_nvt_kick_close(pfmds_ctx* c, double dt);
-NhcPack integ_nhc_pack(pfmds_ctx* c);
-void integ_nvt_close_only(pfmds_ctx* c, double dt, int nparts, const double* part);  // chain update from KE partials another kernel produced (fused kick)
 void integ_flush_pending(pfmds_ctx* c);
 // out[0]=KE(group) ; group sums for diagnostics: out[0..2]=sum F, [3..5]=sum m x, [6..8]=sum m v, [9]=sum m, [10]=max v^2
 void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out);

@@ -661,20 +661,18 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __
 // Force pass that also yields the interaction's energy (second generation only; steps that report their energies):
 // e_i = (r0 / 2p) sum_j a1 e_p f  -  xi sqrt(sum_j e_q f),  the square root being 1 / (1/Eb_i) from the density pass.
 // Same row walk and pair routine as k_rjl_force; no early exits, every thread reaches the block sum.
-// KICK: the closing half kick of the step (and, under NVT, the thermostat groups' kinetic-energy partial sums) in the epilogue of
-// the step's last force kernel: the thread has the atom's total force in registers, so k_kick_ke's launch and its read of frc go
-// away (integrate.cu k_kick_ke, same expressions: velocities are the unfused path's bit for bit; the KE partials are summed per
-// block of this grid, in block order by k_nhc_close: reproducible from run to run).
-// Under NVT the block that finishes last also closes the thermostat step: it sums the per-block partials in block order (fixed order:
-// reproducible) and runs the chain update (k_nhc_close's work, without its launch).
-struct KickFuse { double4* vel; const uint32_t* gmask; uint32_t bxyz, bz; double ts2; NhcPack P; double* kpart; unsigned int* done; double ts3, ts4; };
-template <class CT, int MB, bool E, bool KICK>  // CT = RjlF (second generation) or RjlG (third)
-__global__ void __launch_bounds__(FT, MB) k_rjl_force_x(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
-                                                        WrapC W, SlabDev S, int overwrite, double erep, double xi, double* __restrict__ part, KickFuse K) {
+// Force pass that also yields the interaction's energy (steps that report their energies):
+// e_i = (r0 / 2p) sum_j a1 e_p f  -  xi sqrt(sum_j e_q f),  the square root being 1 / (1/Eb_i) from the density pass.
+// Same row walk and pair routine as k_rjl_force; no early exits, every thread reaches the block sum.
+// (Tried and dropped, measured on a B200 at 10^6 atoms: the closing half kick + thermostat KE partials in this kernel's epilogue,
+//  with and without the last block of the grid running the chain update: 0.375 / 0.398 ms against 0.359 ms + 0.034 ms for the
+//  separate k_kick_ke -- the extra 64 B/atom of velocity traffic lands in a kernel whose L1 data pipe is already the limit.)
+template <class CT, int MB = RJL_MINB>  // CT = RjlF (second generation) or RjlG (third)
+__global__ void __launch_bounds__(FT, MB) k_rjl_force_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
+                                                        WrapC W, SlabDev S, int overwrite, double erep, double xi, double* __restrict__ part) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);
     double e = 0;
-    double tx = 0, ty = 0, tz = 0;  // total force on the atom after this interaction (KICK)
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
         const double4 pi = ld256_nc(&pos[i]);
@@ -687,79 +685,17 @@ __global__ void __launch_bounds__(FT, MB) k_rjl_force_x(int N, const double4* __
             double4 b = ld256_nc(&pos[j1]);
             int j2, j3;
             row.ahead(p, n, j1, j2, j3);
-            rjl_force_pair_e<E>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
+            rjl_force_pair_e<true>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
             a = ld256_nc(&pos[j2]);
-            rjl_force_pair_e<E>(pi, b, C, box, W.min_half_hi, fx, fy, fz, se);
+            rjl_force_pair_e<true>(pi, b, C, box, W.min_half_hi, fx, fy, fz, se);
             j1 = j3;
         }
-        if (p < n) rjl_force_pair_e<E>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
-        if (overwrite) { tx = fx; ty = fy; tz = fz; }
-        else { double4 f = frc[i]; tx = f.x + fx; ty = f.y + fy; tz = f.z + fz; }  // add_force's sums
-        frc[i] = make_double4(tx, ty, tz, 0.);
-        if (E) e = erep * se - (pi.w > 0. ? xi / pi.w : 0.);
-    } else if (i < N) {
-        if (overwrite) frc[i] = make_double4(0., 0., 0., 0.);
-        else if (KICK) { double4 f = frc[i]; tx = f.x; ty = f.y; tz = f.z; }
-    }
-    if (E) store_partial(e, part);
-    if (KICK) {
-        double ke[NHC_MAXF];
-#pragma unroll
-        for (int k = 0; k < NHC_MAXF; ++k) ke[k] = 0.;
-        const uint32_t g = i < N ? K.gmask[i] : PFMDS_GHOST;
-        if (!(g & PFMDS_GHOST)) {
-            const bool mx = g & K.bxyz, mz = g & K.bz;
-            bool th = false;
-            for (int k = 0; k < K.P.n; ++k) th |= (g & K.P.bit[k]) != 0;
-            if (mx || mz || th) {
-                double4 v = K.vel[i];
-                if (mx || mz) {
-                    if (mx) {
-                        v.x = v.x + tx / v.w / PFMDS_MASS_COEF * K.ts2;
-                        v.y = v.y + ty / v.w / PFMDS_MASS_COEF * K.ts2;
-                        v.z = v.z + tz / v.w / PFMDS_MASS_COEF * K.ts2;
-                    }
-                    if (mz) v.z = v.z + tz / v.w / PFMDS_MASS_COEF * K.ts2;
-                    K.vel[i] = v;
-                }
-                const double ek = v.w * (v.x * v.x + v.y * v.y + v.z * v.z) / 2 * PFMDS_MASS_COEF;
-#pragma unroll
-                for (int k = 0; k < NHC_MAXF; ++k)
-                    if (k < K.P.n && (g & K.P.bit[k])) ke[k] += ek;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NHC_MAXF; ++k)
-            if (k < K.P.n) {
-                double sk = block_sum(ke[k]);
-                if (threadIdx.x == 0) K.kpart[(size_t)blockIdx.x * NHC_MAXF + k] = sk;
-            }
-#ifdef PFMDS_COOP
-        if (K.P.n > 0) {
-            __shared__ bool last;
-            if (threadIdx.x == 0) {
-                __threadfence();                                   // this block's partials before its ticket
-                last = atomicAdd(K.done, 1u) == gridDim.x - 1;
-            }
-            __syncthreads();
-            if (last) {
-                __threadfence();                                   // every other block's partials after their tickets
-                for (int k = 0; k < K.P.n; ++k) {
-                    double sk = 0.;
-                    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) sk += reinterpret_cast<const volatile double*>(K.kpart)[(size_t)b * NHC_MAXF + k];
-                    sk = block_sum(sk);
-                    if (threadIdx.x == 0) {
-                        double* st = K.P.state[k];
-                        const int M = K.P.M[k];
-                        st[3 * M + 2] = nhc_chain(st, M, K.P.L[k], K.P.T[k], sk, K.ts2, K.ts3, K.ts4);
-                    }
-                    __syncthreads();
-                }
-                if (threadIdx.x == 0) *K.done = 0u;                // ready for the next launch
-            }
-        }
-#endif
-    }
+        if (p < n) rjl_force_pair_e<true>(pi, a, C, box, W.min_half_hi, fx, fy, fz, se);
+        if (overwrite) frc[i] = make_double4(fx, fy, fz, 0.);
+        else add_force(frc, i, fx, fy, fz);
+        e = erep * se - (pi.w > 0. ? xi / pi.w : 0.);
+    } else if (i < N && overwrite) frc[i] = make_double4(0., 0., 0., 0.);
+    store_partial(e, part);
 }
 template <int SPLIT, class CT>
 __global__ void __launch_bounds__(FT) k_rjl_force_split_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
@@ -1185,19 +1121,8 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         // Energies of the step: the first generation evaluates them in its density pass (a second exponential per pair), the
         // second takes them from the force pass, which has that exponential in hand (k_rjl_force_e).
         const bool e_in_force = with_energy && gen2;
-        // force pass with the energy of the step (E) and / or the closing half kick (KICK) in its epilogue
-        const bool kick = c->kick_req.active && !small && !c->slab && gen2 && k == c->kick_req.last_inter;
-        KickFuse KF{};
-        if (kick) {
-            KF.vel = c->vel; KF.gmask = c->gmask; KF.bxyz = 1u << (c->xyz_moving - 1); KF.bz = 1u << (c->z_moving - 1); KF.ts2 = c->kick_req.ts2;
-            KF.P = c->kick_req.P; KF.kpart = c->part + c->part_cap / 2;
-            KF.done = reinterpret_cast<unsigned int*>(c->err + PFMDS_ERRW); KF.ts3 = c->kick_req.ts2 / 2; KF.ts4 = c->kick_req.ts2 / 4;
-#ifdef PFMDS_COOP
-            c->kick_req.closed = KF.P.n > 0;   // the force kernel's last block runs the chain update itself
-#endif
-            c->kick_req.done = true;
-            c->kick_req.nparts = nb;
-        }
+        // slab mode, lean halo: the density pass waits for the ghost positions in its prologue, the force pass for the ghost 1/Eb
+        const SlabDev SDpos = (c->slab && !small && !fused) ? slab_wait_dev(c, 0) : SlabDev{};
         auto run = [&](auto CD, auto CF) {
             using TD = decltype(CD);
             using TF = decltype(CF);
@@ -1205,54 +1130,43 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
                 KTimer kt(c, KS_RJL_DENSITY);
                 if (with_energy && !e_in_force) {
                     if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, epart);
-                    else LAUNCH((k_rjl_density<true, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, epart, fused ? slab_dev(c, 1) : SlabDev{});
+                    else LAUNCH((k_rjl_density<true, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, epart, fused ? slab_dev(c, 1) : SDpos);
                     e_parts = small ? nbs : nb;
                 } else
                 if (small) LAUNCH((k_rjl_density_split<false, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, (double*)nullptr);
-                else LAUNCH((k_rjl_density<false, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, (double*)nullptr, fused ? slab_dev(c, 1) : SlabDev{});
+                else LAUNCH((k_rjl_density<false, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, (double*)nullptr, fused ? slab_dev(c, 1) : SDpos);
             }
-            if (c->slab && !fused) slab_exchange(c, 1);  // ghost 1/Eb from their owners
-            if (!e_in_force && !kick) {
+            if (c->slab && !fused) { slab_set_consumer_waits(c, !small); slab_exchange(c, 1); }  // ghost 1/Eb from their owners
+            if (!e_in_force) {
                 KTimer kt(c, KS_RJL_FORCE);
                 if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W);
                 else {
                     bool launched = false;
                     if constexpr (std::is_same<TF, RjlG>::value)
-                        if (c->rjl_minb == 8) { LAUNCH((k_rjl_force<TF, 8>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow); launched = true; }
-                    if (!launched) LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
+                        if (c->rjl_minb == 8) { LAUNCH((k_rjl_force<TF, 8>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : slab_wait_dev(c, 1), ow); launched = true; }
+                    if (!launched) LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : slab_wait_dev(c, 1), ow);
                 }
             }
         };
         const double erep = it.rjl.r0 / (2. * it.rjl.p);   // A0 / a1, a1 = 2 A0 p / r0
-        auto force_x = [&](auto CF) {
+        auto force_e = [&](auto CF) {   // force pass that also yields the step's energy
             using TF = decltype(CF);
             KTimer kt(c, KS_RJL_FORCE);
             if (small) { LAUNCH((k_rjl_force_split_e<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, erep, it.rjl.xi, epart); e_parts = nbs; return; }
-            const SlabDev SD = fused ? slab_dev(c, 2) : SlabDev{};
-#define FX_LAUNCH(...) LAUNCH((k_rjl_force_x<__VA_ARGS__>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart, KF)
+            const SlabDev SD = fused ? slab_dev(c, 2) : slab_wait_dev(c, 1);
             bool launched = false;
             if constexpr (std::is_same<TF, RjlG>::value)
-                if (c->rjl_minb == 8) {
-                    if (e_in_force && kick) FX_LAUNCH(TF, 8, true, true);
-                    else if (e_in_force) FX_LAUNCH(TF, 8, true, false);
-                    else FX_LAUNCH(TF, 8, false, true);
-                    launched = true;
-                }
-            if (!launched) {
-                if (e_in_force && kick) FX_LAUNCH(TF, RJL_MINB, true, true);
-                else if (e_in_force) FX_LAUNCH(TF, RJL_MINB, true, false);
-                else FX_LAUNCH(TF, RJL_MINB, false, true);
-            }
-#undef FX_LAUNCH
-            if (e_in_force) e_parts = nb;
+                if (c->rjl_minb == 8) { LAUNCH((k_rjl_force_e<TF, 8>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart); launched = true; }
+            if (!launched) LAUNCH((k_rjl_force_e<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart);
+            e_parts = nb;
         };
         if (gen3) {
             const RjlG G = rjl_g3_consts(it.rjl, rjl_tab_spec(it.rjl), reinterpret_cast<const double2*>(it.aux));
             run(G, G);
-            if (e_in_force || kick) force_x(G);
-        } else if (e_in_force || kick) {
+            if (e_in_force) force_e(G);
+        } else if (e_in_force) {
             run(rjl_dens_consts(it.rjl), rjl_force_consts(it.rjl));
-            force_x(rjl_force_consts(it.rjl));
+            force_e(rjl_force_consts(it.rjl));
         } else
         if (gen2) run(rjl_dens_consts(it.rjl), rjl_force_consts(it.rjl));
         else { const RjlC C = rjl_consts(it.rjl); run(C, C); }

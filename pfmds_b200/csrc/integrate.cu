@@ -64,7 +64,7 @@ void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out) {
     if (c->slab) slab_allreduce_sum(c, d_out, 1);
 }
 
-// (nhc_chain, the Nose-Hoover chain half step of md_integrators.f90:200-245, lives in common.cuh: the fused force + kick kernel of forces.cu runs it too)
+// (nhc_chain, the Nose-Hoover chain half step of md_integrators.f90:200-245, lives in common.cuh)
 // One block sums the KE partials (fixed order), thread 0 runs the chain.
 __global__ void k_nhc(int nparts, const double* __restrict__ part, double* state, int M, int L, double temperature, double ts2, double ts3,
                       double ts4) {
@@ -413,15 +413,6 @@ void integ_nvt_kick_close(pfmds_ctx* c, double dt) {
         LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
     }
     c->launches += 2;
-}
-NhcPack integ_nhc_pack(pfmds_ctx* c) { return pack_of(c); }
-// closing chain update when the kick and the KE partials came out of the force kernel (forces.cu k_rjl_force_x): `nparts` rows of
-// NHC_MAXF partial sums, summed in row order
-void integ_nvt_close_only(pfmds_ctx* c, double dt, int nparts, const double* part) {
-    NhcPack P = pack_of(c);
-    KTimer kt(c, KS_KICK);
-    LAUNCH((k_nhc_close), 1, 1024, c->st, nparts, part, P, dt / 2, dt / 4, dt / 8);
-    c->launches += 1;
 }
 // apply scalings that are still pending (before anything else reads or changes velocities)
 void integ_flush_pending(pfmds_ctx* c) {

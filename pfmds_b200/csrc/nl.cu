@@ -501,10 +501,10 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
         // Row state of this lane's atom (phase 2 reads and updates it through shuffles): entries so far, per class
         int cnt = 0, c0 = 0, c1 = 0, c2 = 0;
         bool ovf = false;                             // a survivor list overflowed: the atom is redone by the serial routine at the end
-        int ns = 0;                                   // survivors of this lane's atom in the current plane of cells
+        int ns = 0;                                   // survivors of this lane's atom waiting in its list
         unsigned short* const mine = surv + (size_t)lane * lcap;
         const int nown = oe - o0 < 32 ? oe - o0 : 32;
-        // ---- phase 2: exact FP64 test, lanes = survivors of one atom; called after each plane (oz) of nine cells ----
+        // ---- phase 2: exact FP64 test, lanes = survivors of one atom; called whenever a list could overflow, and at the end ----
         auto flush = [&]() {
             __syncwarp();
             for (int o = 0; o < nown; ++o) {
@@ -566,9 +566,7 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
         CB_SKIP_EMPTY(pr, po)
         CB_ISSUE_NEXT();
         CB_ISSUE_NEXT();
-        int plane = pr / 6;
         while (pr < 18) {
-            if (pr / 6 != plane) { flush(); plane = pr / 6; }
             const CbRange R = rng[w][pr];
             const int n = R.count - po < CB_CAP ? R.count - po : CB_CAP;
             const int b = k_done & 1;
@@ -579,10 +577,13 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
             const unsigned tag = ((unsigned)pr << CB_OFF_BITS) + (unsigned)po;
             const float ox = pif.x - R.sx, oy = pif.y - R.sy, oz = pif.z - R.sz;  // candidate + s - owner = candidate - (owner - s)
             if (R.count > (1 << CB_OFF_BITS)) ovf = owner;  // offsets would not fit the 16-bit entries: these atoms take the serial path
-            if (owner && !ovf) {
-                for (int g0 = 0; g0 < n; g0 += 32) {
-                    const int m = n - g0 < 32 ? n - g0 : 32;
-                    uint32_t mask = 0;
+            const bool act = owner && !ovf;
+            for (int g0 = 0; g0 < n; g0 += 32) {
+                const int m = n - g0 < 32 ? n - g0 : 32;
+                // a group adds at most 32 survivors per lane: make room first (phase 2 empties every list), so no list ever overflows
+                if (__ballot_sync(0xffffffffu, act && ns + m > lcap) != 0u) flush();
+                uint32_t mask = 0;
+                if (act) {
                     if (m == 32) {
 #pragma unroll
                         for (int t = 0; t < 32; ++t) {
@@ -601,12 +602,11 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
                             mask |= keep ? (1u << t) : 0u;
                         }
                     }
-                    if (ns + __popc(mask) > lcap) { ovf = true; mask = 0; }
-                    while (mask) {  // append the survivors of this group, in candidate order
-                        const int t = PFMDS_FFS(mask) - 1;
-                        mask &= mask - 1u;
-                        mine[ns++] = (unsigned short)(tag + (unsigned)(g0 + t));
-                    }
+                }
+                while (mask) {  // append the survivors of this group, in candidate order
+                    const int t = PFMDS_FFS(mask) - 1;
+                    mask &= mask - 1u;
+                    mine[ns++] = (unsigned short)(tag + (unsigned)(g0 + t));
                 }
             }
             __syncwarp();  // every lane is done with this stage buffer: it may be refilled
@@ -779,8 +779,11 @@ void nl_build(pfmds_ctx* c, NList& l) {
         const int nbc = (c->ncells + CB_WARPS - 1) / CB_WARPS;
         const bool check2 = !c->slab && c->h_gmask.size() == (size_t)N && !c->all_in_group(l.g2);
         const bool chk = c->slab || check2;  // slab mode keeps its masks on the device only: always test
-        int lcap = 64;                        // prefilter survivors per atom and plane of nine cells kept in shared memory (16-bit entries); more: serial path
-        if (l.maxn > 120) lcap = 128;
+        // prefilter survivors per atom kept in shared memory between two runs of phase 2 (16-bit entries): a whole row when it is short
+        int lcap = l.maxn + l.maxn / 8 + 8;
+        if (lcap > 128) lcap = 128;
+        if (lcap < 40) lcap = 40;
+        lcap = (lcap + 7) & ~7;
         const size_t dyn = (size_t)CB_WARPS * 32 * lcap * sizeof(unsigned short);
 #define CELL_ARGS c->ncells, c->pos, c->posf, c->orig, c->cell_start, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err, lcap
 #ifdef __CUDACC__

@@ -74,7 +74,7 @@ int fh_rjl(int N, double* pos4, double* frc4, size_t stride, const int* nl0, con
         *energy = sum_parts(part, nb, 1.0);
         if (overwrite >= 2) {   // the force pass that also yields the energy (k_rjl_force_e): energy from it, forces as usual
             std::fill(part.begin(), part.end(), 0.);
-            emu_launch(k_rjl_force_x<RjlG, RJL_MINB, true, false>, nb, 1, FT, N, (const double4*)pos, frc, lv, G, box, W, SlabDev{}, overwrite & 1, R.r0 / (2. * R.p), R.xi, part.data(), KickFuse{});
+            emu_launch(k_rjl_force_e<RjlG>, nb, 1, FT, N, (const double4*)pos, frc, lv, G, box, W, SlabDev{}, overwrite & 1, R.r0 / (2. * R.p), R.xi, part.data());
             *energy = sum_parts(part, nb, 1.0);
         } else
         emu_launch(k_rjl_force<RjlG>, nb, 1, FT, N, (const double4*)pos, frc, lv, G, box, W, SlabDev{}, overwrite);

@@ -52,25 +52,3 @@ def test_size_switches_are_read_from_the_environment():
     assert rel_err(fb, fa) < 1e-12 and not np.array_equal(fa, fb)
     assert a.pair_count(0, 0) == b.pair_count(0, 0)
 
-
-def test_closing_kick_in_the_force_kernel_epilogue():
-    """The closing half kick fused into the last force kernel of the step (forces.cu k_rjl_force_x, default for large rjl systems)
-    against the separate kick kernels (PFMDS_FUSE_KICK=0): identical velocity arithmetic, so NVE trajectories are the same bits;
-    under NVT the kinetic-energy partial sums are grouped per block of another grid (rounding of the thermostat scale): 1e-12."""
-    case = inputs.cu_fcc(ncell=30, jitter=0.03, period=5)          # 108 000 atoms: the thread-per-atom kernels
-    for integ, exact in (("nve", True), ("nvms", True), ("nvt", False)):
-        a, b = gpu(case, {"PFMDS_FUSE_KICK": "0"}), gpu(case)
-        for e in (a, b):
-            e.advance(integ, 2.0, 0, 1)
-            e.advance(integ, 2.0, 1, 11, with_energy=True)   # the last step also asks for the energies: kick + energy in one epilogue
-        (pa, va, fa), (pb, vb, fb) = a.download(), b.download()
-        assert np.abs(va).max() > 1e-4
-        if exact:
-            assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(fa, fb)
-            assert np.array_equal(a.energies()[0], b.energies()[0])
-        else:
-            assert np.abs(pa - pb).max() < 1e-12 and rel_err(vb, va) < 1e-12 and rel_err(fb, fa) < 1e-11
-            assert np.allclose(a.energies()[3], b.energies()[3], rtol=1e-11, atol=1e-12)
-        assert b.launch_count() < a.launch_count()
-        a.close()
-        b.close()
