@@ -165,6 +165,7 @@ bool slab_pos_pushed_by_kick(pfmds_ctx* c, bool rebuild_step);
 SlabDev slab_wait_dev(pfmds_ctx* c, int field);          // lean halo: the consumer kernel waits for its ghosts itself
 void slab_set_consumer_waits(pfmds_ctx* c, bool on);
 void slab_allreduce_sum(pfmds_ctx* c, double* d, int n);
+bool slab_ke_close(pfmds_ctx* c, const NhcPack& P, int nparts, const double* part, double ts2, double ts3, double ts4);  // thermostat KE over the ranks by peer-memory mailboxes + chain update
 void slab_allreduce_max(pfmds_ctx* c, double* d, int n);
 void slab_allreduce_max_int(pfmds_ctx* c, int* d, int n);
 void slab_allreduce_sum_ll(pfmds_ctx* c, unsigned long long* d, int n);

@@ -404,7 +404,9 @@ void integ_nvt_kick_close(pfmds_ctx* c, double dt) {
     NhcPack P = pack_of(c);
     KTimer kt(c, KS_KICK);
     LAUNCH((k_kick_ke), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, 1u << (c->xyz_moving - 1), 1u << (c->z_moving - 1), dt / 2, P, c->part);
-    if (c->slab) {  // rank-local sums, one all-reduce, then every rank runs the same chain update
+    if (c->slab && slab_ke_close(c, P, RED_BLOCKS, c->part, dt / 2, dt / 4, dt / 8)) {
+        // one kernel: local sums, all-gather through the ranks' mailboxes (peer memory), rank-ordered sum, chain update
+    } else if (c->slab) {  // rank-local sums, one all-reduce, then every rank runs the same chain update
         LAUNCH((k_reduce_ke_partials), 1, 1024, c->st, RED_BLOCKS, c->part, P.n, c->red + 48);
         slab_allreduce_sum(c, c->red + 48, P.n);
         LAUNCH((k_nhc_close), 1, 32, c->st, 1, c->red + 48, P, dt / 2, dt / 4, dt / 8);

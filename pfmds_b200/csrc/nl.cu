@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #if defined(__CUDACC__) || defined(PFMDS_EMU_LIB)
 #include "ctx.hpp"
@@ -432,11 +433,11 @@ __device__ __forceinline__ void cb_wait(unsigned long long* bar, unsigned parity
 #endif
 }
 // Phase 1 (lanes = the cell's atoms): every staged candidate is read by all lanes at once (broadcast) and the FP32 prefilter's
-// survivors are appended, in candidate order, to a per-lane list in shared memory (16-bit entries: range number, offset in range).
-// Phase 2 (lanes = one atom's survivors): the warp takes the atoms of the cell one after the other and gives each survivor of that
-// atom a lane for the exact FP64 test; the accepted entries are compacted into the row with ballot + popc in candidate order, one
-// counter per class.  (A first version ran the exact test inside phase 1, each lane looping over its own survivors: the warp then
-// executes the FP64 block max-over-lanes times per 32 candidates with 13 of 32 lanes active on average -- ncu, profiles/r2e_*.)
+// survivors (bit mask per 32 candidates) are appended, in candidate order, to a per-lane list in shared memory (16-bit entries: range
+// number, offset in range).  Phase 2: every lane takes the exact FP64 test over its own list and writes its own row, as k_build_mask
+// does per 32 candidates -- but once per ~60 listed survivors, when the lanes' trip counts are nearly equal (the first two versions
+// of this kernel, profiles/r2e_* r2f_* r2h_*: exact test inside the candidate loop, 13 of 32 lanes active; one atom's survivors spread
+// over the lanes with ballot / popc compaction, 100 instructions per trip and six shuffles per atom: both slower than k_build_mask).
 #define CB_OFF_BITS 11                      // offset of a candidate inside its range (three cells): ranges longer than 2048 atoms use k_build_mask
 template <bool PART, bool CHECK2>
 __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, const double4* __restrict__ pos, const float4* __restrict__ posf,
@@ -446,6 +447,7 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
     __shared__ __align__(128) float4 buf[CB_WARPS][2][CB_CAP];
     __shared__ __align__(8) unsigned long long bars[CB_WARPS][2];
     __shared__ CbRange rng[CB_WARPS][18];
+    __shared__ double dshift[CB_WARPS][18][3];   // the ranges' periodic shifts in FP64 (0 or -+L)
 #ifdef __CUDACC__
     extern __shared__ __align__(16) unsigned short surv_all[];  // [CB_WARPS][32][lcap]: prefilter survivors of each lane's atom
 #else
@@ -477,6 +479,9 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
         R.sx = sx; R.sy = sy; R.sz = sz;
         R.shifted = (sx != 0.f) || (sy != 0.f) || (sz != 0.f);
         rng[w][lane] = R;
+        dshift[w][lane][0] = sx == 0.f ? 0. : (sx < 0.f ? -box.L[0] : box.L[0]);
+        dshift[w][lane][1] = sy == 0.f ? 0. : (sy < 0.f ? -box.L[1] : box.L[1]);
+        dshift[w][lane][2] = sz == 0.f ? 0. : (sz < 0.f ? -box.L[2] : box.L[2]);
     }
 #ifdef __CUDA_ARCH__
     if (lane == 0) {
@@ -487,7 +492,6 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
     }
 #endif
     __syncwarp();
-    const unsigned lt = (1u << lane) - 1u;
     unsigned use0 = 0u, use1 = 0u;  // completed uses of each stage buffer: parity of the next wait
     for (int o0 = ob; o0 < oe; o0 += 32) {  // the cell's atoms, 32 at a time (one pass for a crystal)
         const int i = o0 + lane;
@@ -503,58 +507,32 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
         bool ovf = false;                             // a survivor list overflowed: the atom is redone by the serial routine at the end
         int ns = 0;                                   // survivors of this lane's atom waiting in its list
         unsigned short* const mine = surv + (size_t)lane * lcap;
-        const int nown = oe - o0 < 32 ? oe - o0 : 32;
-        // ---- phase 2: exact FP64 test, lanes = survivors of one atom; called whenever a list could overflow, and at the end ----
+        // ---- phase 2: exact FP64 test of the listed survivors; called whenever a list could overflow, and at the end ----
         auto flush = [&]() {
-            __syncwarp();
-            for (int o = 0; o < nown; ++o) {
-                const int nso = __shfl_sync(0xffffffffu, ns, o);
-                if (nso == 0 || __shfl_sync(0xffffffffu, (int)ovf, o)) continue;
-                const int io = o0 + o;
-                int rc = __shfl_sync(0xffffffffu, cnt, o), r0 = __shfl_sync(0xffffffffu, c0, o), r1 = __shfl_sync(0xffffffffu, c1, o),
-                    r2 = __shfl_sync(0xffffffffu, c2, o);
-                const double4 pi = pos[io];
-                const unsigned short* lst = surv + (size_t)o * lcap;
-                for (int s0 = 0; s0 < nso; s0 += 32) {
-                    const int sidx = s0 + lane;
-                    bool ok = sidx < nso;
-                    int j = 0;
-                    double dr2 = 0.;
-                    if (ok) {
-                        const unsigned e = lst[sidx];
-                        const CbRange R = rng[w][e >> CB_OFF_BITS];
-                        j = R.start + (int)(e & ((1u << CB_OFF_BITS) - 1u));
-                        const double4 pj = pos[j];
-                        double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-                        if (R.shifted) {  // min_image's own d - L / d + L (see the header of this kernel)
-                            dx += R.sx == 0.f ? 0. : (R.sx < 0.f ? -box.L[0] : box.L[0]);
-                            dy += R.sy == 0.f ? 0. : (R.sy < 0.f ? -box.L[1] : box.L[1]);
-                            dz += R.sz == 0.f ? 0. : (R.sz < 0.f ? -box.L[2] : box.L[2]);
-                        }
-                        dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        ok = dr2 < rc2;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, ok);
-                    if (m == 0) continue;
-                    if (!PART) {
-                        const int slot = rc + __popc(m & lt);
-                        if (ok && slot < maxn) nlist[(size_t)slot * stride + io] = j;
-                    } else {
-                        const int cls = dr2 < r1sq ? 0 : (dr2 < r2sq ? 1 : 2);
-                        const unsigned m0 = __ballot_sync(0xffffffffu, ok && cls == 0), m1 = __ballot_sync(0xffffffffu, ok && cls == 1), m2 = m & ~(m0 | m1);
-                        if (ok && rc + __popc(m & lt) < maxn) {  // entries beyond the capacity are only counted
-                            if (cls == 0) nlist[(size_t)(r0 + __popc(m0 & lt)) * stride + io] = j;
-                            else if (cls == 1) alt[(size_t)(r1 + __popc(m1 & lt)) * stride + io] = j;
-                            else alt[(size_t)(maxn - 1 - (r2 + __popc(m2 & lt))) * stride + io] = j;
-                        }
-                        r0 += __popc(m0); r1 += __popc(m1); r2 += __popc(m2);
-                    }
-                    rc += __popc(m);
+            // every lane walks its OWN list (the lists of a cell's atoms have nearly the same length: in the crystal 60 +- 5 when the first
+            // one fills up), so the lanes stay together without shuffles, ballots or a second mapping of lanes to work
+            const double4 pi = owner ? pos[i] : make_double4(0., 0., 0., 0.);
+            for (int sidx = 0; sidx < ns; ++sidx) {
+                const unsigned e = mine[sidx];
+                const int r = (int)(e >> CB_OFF_BITS);
+                const int j = rng[w][r].start + (int)(e & ((1u << CB_OFF_BITS) - 1u));
+                const double4 pj = pos[j];
+                double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+                if (rng[w][r].shifted) {  // min_image's own d - L / d + L (see the header of this kernel)
+                    dx += dshift[w][r][0]; dy += dshift[w][r][1]; dz += dshift[w][r][2];
                 }
-                if (lane == o) { cnt = rc; c0 = r0; c1 = r1; c2 = r2; }
+                const double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (dr2 < rc2) {
+                    if (cnt < maxn) {
+                        if (!PART) nlist[(size_t)cnt * stride + i] = j;
+                        else if (dr2 < r1sq) nlist[(size_t)(c0++) * stride + i] = j;
+                        else if (dr2 < r2sq) alt[(size_t)(c1++) * stride + i] = j;
+                        else alt[(size_t)(maxn - 1 - (c2++)) * stride + i] = j;
+                    }
+                    ++cnt;
+                }
             }
             ns = 0;
-            __syncwarp();
         };
         // ---- phase 1: FP32 prefilter, lanes = atoms of the cell ----
         int qr = 0, qo = 0, k_issue = 0, k_done = 0;  // piece being fetched (q*) / processed (p*)
@@ -618,25 +596,17 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
 #undef CB_SKIP_EMPTY
 #undef CB_ISSUE_NEXT
         flush();
-        // ---- row epilogue, one atom after the other (lanes share the copy of the staged classes) ----
-        for (int o = 0; o < nown; ++o) {
-            if (!__shfl_sync(0xffffffffu, (int)owner, o)) continue;
-            const int io = o0 + o;
-            if (__shfl_sync(0xffffffffu, (int)ovf, o)) {
-                if (lane == 0) build_row<true, PART>(io, pos, posf, orig, cstart, nullptr, g, box, pf, bit1, bit2, rc2, r1sq, r2sq, maxn, stride, nlist, alt, nnum, err);
-                continue;
+        // ---- row epilogue (as k_build) ----
+        if (owner) {
+            if (ovf) build_row<true, PART>(i, pos, posf, orig, cstart, nullptr, g, box, pf, bit1, bit2, rc2, r1sq, r2sq, maxn, stride, nlist, alt, nnum, err);
+            else {
+                if (cnt > maxn) { raise_error(err, E_TOO_MANY, orig[i], cnt); cnt = maxn; }  // md_neighbours.f90:80
+                if (PART) {
+                    for (int k = 0; k < c1; ++k) nlist[(size_t)(c0 + k) * stride + i] = alt[(size_t)k * stride + i];
+                    for (int k = 0; k < c2; ++k) nlist[(size_t)(c0 + c1 + k) * stride + i] = alt[(size_t)(maxn - 1 - k) * stride + i];
+                }
+                nnum[i] = cnt;
             }
-            const int rc = __shfl_sync(0xffffffffu, cnt, o), r0 = __shfl_sync(0xffffffffu, c0, o), r1 = __shfl_sync(0xffffffffu, c1, o),
-                      r2 = __shfl_sync(0xffffffffu, c2, o);
-            if (rc > maxn) {  // md_neighbours.f90:80
-                if (lane == 0) { raise_error(err, E_TOO_MANY, orig[io], rc); nnum[io] = maxn; }
-                continue;      // the run stops at the next synchronisation; the row content is irrelevant
-            }
-            if (PART) {
-                for (int k = lane; k < r1; k += 32) nlist[(size_t)(r0 + k) * stride + io] = alt[(size_t)k * stride + io];
-                for (int k = lane; k < r2; k += 32) nlist[(size_t)(r0 + r1 + k) * stride + io] = alt[(size_t)(maxn - 1 - k) * stride + io];
-            }
-            if (lane == 0) nnum[io] = rc;
         }
         __syncwarp();
     }
@@ -779,10 +749,9 @@ void nl_build(pfmds_ctx* c, NList& l) {
         const int nbc = (c->ncells + CB_WARPS - 1) / CB_WARPS;
         const bool check2 = !c->slab && c->h_gmask.size() == (size_t)N && !c->all_in_group(l.g2);
         const bool chk = c->slab || check2;  // slab mode keeps its masks on the device only: always test
-        // prefilter survivors per atom kept in shared memory between two runs of phase 2 (16-bit entries): a whole row when it is short
-        int lcap = l.maxn + l.maxn / 8 + 8;
-        if (lcap > 128) lcap = 128;
-        if (lcap < 40) lcap = 40;
+        // prefilter survivors per atom kept in shared memory between two runs of phase 2 (16-bit entries)
+        int lcap = 72;
+        if (const char* lc = std::getenv("PFMDS_NL_LCAP")) { int v = std::atoi(lc); if (v >= 40 && v <= 512) lcap = v; }
         lcap = (lcap + 7) & ~7;
         const size_t dyn = (size_t)CB_WARPS * 32 * lcap * sizeof(unsigned short);
 #define CELL_ARGS c->ncells, c->pos, c->posf, c->orig, c->cell_start, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err, lcap

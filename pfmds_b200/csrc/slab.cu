@@ -89,6 +89,12 @@ struct Slab {
     int wait_pos_seq = 0;
     int* rs[2]{nullptr, nullptr};   // per slot: ghost slot in the left / right neighbour, -1 otherwise
     unsigned int* counter = nullptr;
+    // thermostat kinetic energies without NCCL: every rank stores its partial sums into every rank's mailbox (peer memory) and
+    // sums all of them in rank order -- the same numbers in the same order on every rank (integ_nvt_kick_close)
+    double* ke_box = nullptr;                   // mine: [2 parities][nranks][KE_W] doubles, last of each row = sequence number
+    std::vector<double*> peer_box;              // every rank's mailbox (IPC mapped; [rank] = my own)
+    double** peer_box_d = nullptr;              // the same pointers on the device
+    int ke_seq = 0;
     bool lean = true;               // one kernel per exchange, consumers wait in their prologue (PFMDS_SLAB_LEAN=0: four small kernels)
     int pend[2]{0, 0};              // sequence number the next consumer of ghost positions / ghost 1/Eb still has to wait for (0: none)
     bool consumer_waits = false;    // set per step by the caller: the first kernel that reads ghost positions has a slab_wait prologue
@@ -99,6 +105,7 @@ struct Slab {
 #define GHOST_BIT 0x80000000u
 #define MIG_W 9   // doubles per migrating atom: pos4, vel4, (mask, orig)
 #define GH_W 5    // doubles per new ghost: pos4, (mask, orig)
+#define KE_W (NHC_MAXF + 1)
 
 __global__ void k_sl_scatter_rs(int n, const int* __restrict__ idx, const int* __restrict__ ps, int* __restrict__ rs);
 
@@ -362,6 +369,48 @@ static bool slab_setup_p2p(pfmds_ctx* c, Slab* s) {
     // the FP64-bound warps), so it is opt-in.
     const char* fz = std::getenv("PFMDS_SLAB_FUSED");
     s->fused = fz && fz[0] == '1';
+    if (h == 1 && !(std::getenv("PFMDS_SLAB_KE_NCCL") && std::getenv("PFMDS_SLAB_KE_NCCL")[0] == '1')) {
+        // mailboxes of the kinetic-energy all-gather: handles go to every rank
+        const int P = s->nranks;
+        const size_t bytes = sizeof(double) * 2 * (size_t)P * KE_W;
+        CK(cudaMalloc(&s->ke_box, bytes));
+        CK(cudaMemset(s->ke_box, 0, bytes));
+        cudaIpcMemHandle_t mh{};
+        bool okb = cudaIpcGetMemHandle(&mh, s->ke_box) == cudaSuccess;
+        if (!okb) cudaGetLastError();
+        char *d_m = nullptr, *d_all = nullptr;
+        CK(cudaMalloc(&d_m, sizeof mh));
+        CK(cudaMalloc(&d_all, sizeof mh * (size_t)P));
+        CK(cudaMemcpy(d_m, &mh, sizeof mh, cudaMemcpyHostToDevice));
+        NK(g_nccl.GroupStart());
+        for (int r = 0; r < P; ++r) {
+            if (r == s->rank) continue;
+            NK(g_nccl.Send(d_m, sizeof mh, ncclChar, r, s->comm, c->st));
+            NK(g_nccl.Recv(d_all + sizeof mh * (size_t)r, sizeof mh, ncclChar, r, s->comm, c->st));
+        }
+        NK(g_nccl.GroupEnd());
+        std::vector<cudaIpcMemHandle_t> all((size_t)P);
+        CK(cudaMemcpyAsync(all.data(), d_all, sizeof mh * (size_t)P, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        cudaFree(d_m); cudaFree(d_all);
+        s->peer_box.assign((size_t)P, nullptr);
+        for (int r = 0; r < P && okb; ++r) {
+            if (r == s->rank) { s->peer_box[(size_t)r] = s->ke_box; continue; }
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { okb = false; cudaGetLastError(); break; }
+            s->ipc_opened.push_back(q);
+            s->peer_box[(size_t)r] = (double*)q;
+        }
+        int hb = okb ? 1 : 0;   // every rank must take the same path
+        CK(cudaMemcpy(dflag, &hb, sizeof(int), cudaMemcpyHostToDevice));
+        NK(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMin, s->comm, c->st));
+        CK(cudaMemcpyAsync(&hb, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        if (hb == 1) {
+            CK(cudaMalloc(&s->peer_box_d, sizeof(double*) * (size_t)P));
+            CK(cudaMemcpy(s->peer_box_d, s->peer_box.data(), sizeof(double*) * (size_t)P, cudaMemcpyHostToDevice));
+        } else s->peer_box.clear();
+    }
     return h == 1;
 }
 
@@ -444,6 +493,7 @@ void slab_destroy(pfmds_ctx* c) {
     cudaFree(s->cat); cudaFree(s->flag); for (int k = 0; k < 3; ++k) cudaFree(s->scan[k]);
     cudaFree(s->cnt_d); cudaFree(s->scan_tmp); cudaFree(c->newslot);
     for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(s->ke_box); cudaFree(s->peer_box_d);
     cudaFree(s->flags); cudaFree(s->pslot[0]); cudaFree(s->pslot[1]); cudaFree(s->rs[0]); cudaFree(s->rs[1]); cudaFree(s->counter);
     if (s->comm) g_nccl.CommDestroy(s->comm);
     delete s;
@@ -501,6 +551,57 @@ int slab_rank(pfmds_ctx* c) { return c->slab->rank; }
 int slab_nranks(pfmds_ctx* c) { return c->slab->nranks; }
 int slab_n_local(pfmds_ctx* c) { return c->slab->n_local; }
 long long slab_n_global(pfmds_ctx* c) { return c->slab->n_global; }
+
+// One block: (1) this rank's KE partial sums in block order, (2) stored with their sequence number into every rank's mailbox,
+// (3) wait for every rank's row of this sequence number in my mailbox, (4) sum the rows in rank order, (5) the chain update
+// (k_nhc_close's work).  Every rank adds the same numbers in the same order: identical thermostat state on all ranks, bit for bit.
+__global__ void k_sl_ke_close(int nparts, const double* __restrict__ part, NhcPack P, double ts2, double ts3, double ts4, int rank, int nranks,
+                              double* const* __restrict__ box, int seq, int* err, unsigned long long timeout_ns) {
+    __shared__ double mine[NHC_MAXF];
+    for (int k = 0; k < P.n; ++k) {
+        double ke = 0;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i * NHC_MAXF + k];
+        ke = block_sum(ke);
+        if (threadIdx.x == 0) mine[k] = ke;
+        __syncthreads();
+    }
+    const int par = seq & 1;
+    if ((int)threadIdx.x < nranks) {   // thread r writes my row into rank r's mailbox
+        double* row = box[threadIdx.x] + ((size_t)par * nranks + rank) * KE_W;
+        for (int k = 0; k < P.n; ++k) reinterpret_cast<volatile double*>(row)[k] = mine[k];
+        __threadfence_system();
+        reinterpret_cast<volatile double*>(row)[NHC_MAXF] = (double)seq;
+    }
+    if ((int)threadIdx.x < nranks) {   // thread r waits for rank r's row in my mailbox
+        const volatile double* row = box[rank] + ((size_t)par * nranks + threadIdx.x) * KE_W;
+        const unsigned long long t0 = pf_now_ns();
+        while (row[NHC_MAXF] != (double)seq) {
+            if (*reinterpret_cast<volatile int*>(err) != 0) break;
+            __nanosleep(100);
+            if (pf_now_ns() - t0 > timeout_ns) { raise_error(err, 31, seq, 2); break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < P.n; ++k) {
+            double ke = 0;
+            for (int r = 0; r < nranks; ++r) ke += reinterpret_cast<const volatile double*>(box[rank])[((size_t)par * nranks + r) * KE_W + k];
+            double* st = P.state[k];
+            const int M = P.M[k];
+            st[3 * M + 2] = nhc_chain(st, M, P.L[k], P.T[k], ke, ts2, ts3, ts4);
+        }
+    }
+}
+// returns false when the mailboxes are not available (no peer access, PFMDS_SLAB_KE_NCCL=1): the caller takes the NCCL all-reduce
+bool slab_ke_close(pfmds_ctx* c, const NhcPack& P, int nparts, const double* part, double ts2, double ts3, double ts4) {
+    Slab* s = c->slab;
+    if (!s || !s->peer_box_d || s->nranks > 64) return false;
+    s->ke_seq += 1;
+    LAUNCH((k_sl_ke_close), 1, 256, c->st, nparts, part, P, ts2, ts3, ts4, s->rank, s->nranks, (double* const*)s->peer_box_d, s->ke_seq, c->err, s->timeout_ns);
+    c->launches += 1;
+    return true;
+}
 
 void slab_allreduce_sum(pfmds_ctx* c, double* d, int n) {
     NK(g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, ncclSum, c->slab->comm, c->st));
