@@ -562,24 +562,27 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
                 if (__ballot_sync(0xffffffffu, act && ns + m > lcap) != 0u) flush();
                 uint32_t mask = 0;
                 if (act) {
+                    const float4* cg = cand + g0;
                     if (m == 32) {
 #pragma unroll
                         for (int t = 0; t < 32; ++t) {
-                            const float4 q = cand[g0 + t];
+                            const float4 q = cg[t];
                             const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
-                            bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (g0 + t != self);
+                            bool keep = fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim;
                             if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
-                            mask |= keep ? (1u << t) : 0u;
+                            if (keep) mask |= 1u << t;
                         }
                     } else {
                         for (int t = 0; t < m; ++t) {
-                            const float4 q = cand[g0 + t];
+                            const float4 q = cg[t];
                             const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
-                            bool keep = (fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim) && (g0 + t != self);
+                            bool keep = fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim;
                             if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
-                            mask |= keep ? (1u << t) : 0u;
+                            if (keep) mask |= 1u << t;
                         }
                     }
+                    const unsigned sb = (unsigned)(self - g0);     // the atom itself is not its own neighbour (global i != j)
+                    if (sb < 32u) mask &= ~(1u << sb);
                 }
                 while (mask) {  // append the survivors of this group, in candidate order
                     const int t = PFMDS_FFS(mask) - 1;
@@ -750,7 +753,7 @@ void nl_build(pfmds_ctx* c, NList& l) {
         const bool check2 = !c->slab && c->h_gmask.size() == (size_t)N && !c->all_in_group(l.g2);
         const bool chk = c->slab || check2;  // slab mode keeps its masks on the device only: always test
         // prefilter survivors per atom kept in shared memory between two runs of phase 2 (16-bit entries)
-        int lcap = 72;
+        int lcap = 120;
         if (const char* lc = std::getenv("PFMDS_NL_LCAP")) { int v = std::atoi(lc); if (v >= 40 && v <= 512) lcap = v; }
         lcap = (lcap + 7) & ~7;
         const size_t dyn = (size_t)CB_WARPS * 32 * lcap * sizeof(unsigned short);
