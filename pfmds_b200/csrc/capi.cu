@@ -329,6 +329,23 @@ void finalize(pfmds_ctx* c) {
     alloc_log(c);
     check_rjl_generation(c);
     for (auto& it : c->inter) rjl_prepare(c, it);
+    if (c->N < c->small_n && c->inter.size() >= 2 && c->inter.size() <= 8 && env_int("PFMDS_SMALL_FORK", 1) != 0) {
+        for (size_t k = 0; k < c->inter.size(); ++k) {
+            double4* b = nullptr;
+            CK(cudaMalloc(&b, sizeof(double4) * c->stride));
+            CK(cudaMemset(b, 0, sizeof(double4) * c->stride));
+            c->fbuf.push_back(b);
+            cudaStream_t s = nullptr;
+            CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            c->aux_st.push_back(s);
+        }
+        for (size_t k = 0; k < c->inter.size() + 1; ++k) {
+            cudaEvent_t e = nullptr;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->aux_ev.push_back(e);
+        }
+        c->fbuf_on = true;
+    }
     c->first_overwrites = c->zero_all && c->changes.empty() && !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
@@ -421,7 +438,34 @@ void update_lists(pfmds_ctx* c, int step) {
 }
 
 // zero_forces + calculate_forces + calculate_forces_numerically, md_simulation.f90:163-165
-void compute_forces(pfmds_ctx* c, bool with_energy) {
+// `defer_sum`: the caller follows with integ_sum_forces(mode 1 / 2), which adds the closing kick to the sum of the buffers
+void compute_forces(pfmds_ctx* c, bool with_energy, bool defer_sum = false) {
+    // Small systems, steps that do not report energies: one branch per interaction (own stream, own force buffer): in the step's CUDA
+    // graph the interactions become parallel branches, so its depth is the longest kernel chain of ONE interaction, not their sum.
+    // The buffers are added in file order, analytic interactions first and calculate_forces_numerically (rebosc) after them, as below.
+    // Steps that report energies (or are being profiled) walk the same buffers one interaction after the other on the context's
+    // stream: the per-atom additions are the same in both cases, so a run's bits do not depend on its logging cadence.
+    if (c->fbuf_on) {
+        const bool fork = !with_energy && !c->prof_on && !c->timers_on;
+        std::vector<size_t> order;
+        for (size_t k = 0; k < c->inter.size(); ++k) if (c->inter[k].kind != K_REBOSC) order.push_back(k);
+        for (size_t k = 0; k < c->inter.size(); ++k) if (c->inter[k].kind == K_REBOSC) order.push_back(k);
+        c->fbuf_active = true;
+        if (fork) CK(cudaEventRecord(c->aux_ev[0], c->st));
+        for (size_t q = 0; q < order.size(); ++q) {
+            cudaStream_t s = fork ? c->aux_st[q] : nullptr;
+            if (fork) CK(cudaStreamWaitEvent(s, c->aux_ev[0], 0));
+            c->fst = s; c->fout = c->fbuf[q];
+            try { forces_interaction(c, (int)order[q], with_energy); } catch (...) { c->fst = nullptr; c->fout = nullptr; throw; }
+            if (fork) CK(cudaEventRecord(c->aux_ev[1 + q], s));
+        }
+        c->fst = nullptr; c->fout = nullptr;
+        if (fork)
+            for (size_t q = 0; q < order.size(); ++q) CK(cudaStreamWaitEvent(c->st, c->aux_ev[1 + q], 0));
+        if (!defer_sum) integ_sum_forces(c, 0, 0.);
+        c->energy_valid = with_energy;
+        return;
+    }
     forces_zero(c);
     for (size_t k = 0; k < c->inter.size(); ++k)   // calculate_forces: the analytic interactions in file order
         if (c->inter[k].kind != K_REBOSC) forces_interaction(c, (int)k, with_energy);
@@ -463,16 +507,19 @@ void do_step(pfmds_ctx* c, int step, int kind, double dt, bool first_of_call, bo
     {
         PhaseTimer t(c, 4);
         if (step % c->zero_momentum_period == 0) integ_zero_momentum(c);
-        compute_forces(c, with_energy);
+        compute_forces(c, with_energy, step != 0);
     }
     if (step != 0) {
         PhaseTimer t(c, 0);
+        const bool summed = c->fbuf_active;   // the forces are still in the per-interaction buffers: sum and kick in one kernel
         if (kind == PFMDS_NVT && c->nhc_fusable) {
-            integ_nvt_kick_close(c, dt);
+            if (summed) integ_sum_forces(c, 2, dt);
+            else integ_nvt_kick_close(c, dt);
             c->nhc_pending = true;
             c->nhc_ke_valid = true;
         } else {
-            integ_kick(c, dt);
+            if (summed) integ_sum_forces(c, 1, dt);
+            else integ_kick(c, dt);
             if (kind == PFMDS_NVT)
                 for (auto& th : c->nhc) integ_nhc_half(c, th, dt);
             if (kind == PFMDS_NVMS) integ_quench(c);
@@ -1604,6 +1651,9 @@ int pfmds_destroy(pfmds_ctx* c) {
     for (auto& t : c->nhc) cudaFree(t.state);
     for (int* r : c->d_grank) cudaFree(r);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    for (auto b : c->fbuf) cudaFree(b);
+    for (auto s : c->aux_st) cudaStreamDestroy(s);
+    for (auto e : c->aux_ev) cudaEventDestroy(e);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,
                     c->cid, c->posf, c->scan_tmp, c->part, c->red, c->energy, c->err, c->logbuf, c->io_stage};
     for (void* p : ptrs) cudaFree(p);

@@ -187,7 +187,15 @@ __device__ __forceinline__ void slab_wait(const SlabDev& S) {
                 __nanosleep(100);
                 if (pf_now_ns() - t0 > S.timeout_ns) { raise_error(S.err, 31, S.wait_seq, 1); break; }
             }
+            // acquire: one load per block (a system-scope FENCE here, once per block of a 7 800-block grid, cost the rjl kernels 30 us
+            // per launch on two B200s); the block barrier below carries the ordering to the other threads
+#ifdef __CUDA_ARCH__
+            int a_, b_;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(a_) : "l"(S.wait_a) : "memory");
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(b_) : "l"(S.wait_b) : "memory");
+#else
             __threadfence_system();
+#endif
         }
         __syncthreads();
     }

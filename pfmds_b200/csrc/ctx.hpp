@@ -105,6 +105,16 @@ struct pfmds_ctx {
     bool nl_cell = true;            // cell-tiled list build (one warp per cell, candidates staged in shared memory by bulk copies) for large systems; PFMDS_NL_CELL=0: k_build_mask
     int small_n = 100000;           // below: 8 lanes per atom in the pair kernels (latency bound); from it on: thread per atom, pipelined
     int nl_warp_n = 200000;         // below: warp-per-atom list build; from it on: thread per atom
+    // Small systems (latency bound): the interactions of a step run as parallel branches of its CUDA graph, each accumulating into
+    // its own force buffer (fbuf[k]); integrate.cu k_sum_kick_ke adds the buffers per atom in file order (the bits of the sequential
+    // accumulation), applies the closing kick and clears them.  fst / fout redirect the launches of forces_interaction.
+    std::vector<double4*> fbuf;
+    std::vector<cudaStream_t> aux_st;
+    std::vector<cudaEvent_t> aux_ev;     // [0] fork, [1 + k] join of branch k
+    cudaStream_t fst = nullptr;
+    double4* fout = nullptr;
+    bool fbuf_on = false;                // buffers exist (finalize): small system, at most 8 interactions, PFMDS_SMALL_FORK != 0
+    bool fbuf_active = false;            // this step's forces went into the buffers: the sum kernel must run
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
     bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)
     bool finalized = false;
@@ -195,6 +205,7 @@ void integ_quench(pfmds_ctx* c);
 void integ_zero_momentum(pfmds_ctx* c);
 void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step);
 void integ_nvt_kick_close(pfmds_ctx* c, double dt);
+void integ_sum_forces(pfmds_ctx* c, int mode, double dt);   // fbuf mode: per-atom sum of the interaction buffers; mode 0 sum, 1 + closing kick, 2 + thermostat KE partials and chain update
 void integ_flush_pending(pfmds_ctx* c);
 // out[0]=KE(group) ; group sums for diagnostics: out[0..2]=sum F, [3..5]=sum m x, [6..8]=sum m v, [9]=sum m, [10]=max v^2
 void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out);

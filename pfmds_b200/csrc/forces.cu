@@ -1035,6 +1035,7 @@ __global__ void k_zero_group(int N, double4* __restrict__ frc, const uint32_t* _
 #ifdef PFMDS_HAVE_CTX  // ---- launchers (host side of the library) ----------------------------------------
 void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
     if (c->first_overwrites && c->N >= c->small_n) return;  // the first force kernel stores instead of accumulating
+    if (c->fbuf_active) return;                             // per-interaction buffers: k_sum_kick_ke starts every atom's sum from zero_forces' value
     KTimer kt(c, KS_ZERO_FORCES);
     if (c->zero_all) { CK(cudaMemsetAsync(c->frc, 0, sizeof(double4) * (size_t)c->N, c->st)); return; }
     LAUNCH((k_zero_group), (c->N + 255) / 256, 256, c->st, c->N, c->frc, c->gmask, 1u << (c->all_atoms - 1));
@@ -1072,6 +1073,10 @@ void normals_interaction(pfmds_ctx* c, int k) {  // update_norm_in_graphene, md_
 // second sweep over the lists): fused into the force kernels for rjl, lj1g and lj, a follow-up kernel for the others.
 void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_forces, md_interactions.f90:210-242
     Inter& it = c->inter[k];
+    // small systems, steps without energies: every interaction accumulates into its own force buffer on its own stream (parallel
+    // branches of the step's CUDA graph), summed per atom in file order by integrate.cu k_sum_kick_ke -- see compute_forces (capi.cu)
+    cudaStream_t fs = c->fst ? c->fst : c->st;
+    double4* fo = c->fout ? c->fout : c->frc;
     double* epart = with_energy ? c->part : nullptr;
     int e_parts = 0;
     double e_scale = 1.0;
@@ -1083,30 +1088,30 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     case K_LJ:
         if (with_energy) {
             KTimer kt(c, KS_LJ);
-            if (small) LAUNCH((k_lj<true, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, epart);
-            else LAUNCH((k_lj<true, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, epart);
+            if (small) LAUNCH((k_lj<true, true, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj, c->box, epart);
+            else LAUNCH((k_lj<true, true, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj, c->box, epart);
             e_parts = small ? nbs : nb;
         } else
-        { KTimer kt(c, KS_LJ); if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); else LAUNCH((k_lj<true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj, c->box, nullptr); }
-        if (e_parts) { LAUNCH((k_sum_partials), 1, 1024, c->st, e_parts, c->part, 1.0, c->energy + k); c->launches += 1; if (c->slab) slab_allreduce_sum(c, c->energy + k, 1); e_parts = 0; with_energy = false; }
-        { KTimer kt(c, KS_LJ); if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); else LAUNCH((k_lj<true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), it.lj, c->box, nullptr); }
+        { KTimer kt(c, KS_LJ); if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj, c->box, nullptr); else LAUNCH((k_lj<true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj, c->box, nullptr); }
+        if (e_parts) { LAUNCH((k_sum_partials), 1, 1024, fs, e_parts, c->part, 1.0, c->energy + k); c->launches += 1; if (c->slab) slab_allreduce_sum(c, c->energy + k, 1); e_parts = 0; with_energy = false; }
+        { KTimer kt(c, KS_LJ); if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[1].view(st), it.lj, c->box, nullptr); else LAUNCH((k_lj<true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[1].view(st), it.lj, c->box, nullptr); }
         c->launches += 2;
         break;
     case K_LJ1G:
         if (c->lj1g_pipe && !small) {  // pipelined variant (thread per atom)
             KTimer kt(c, KS_LJ1G);
-            if (with_energy) { LAUNCH((k_lj1g_pipe<true>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), epart); e_parts = nb; e_scale = 0.5; }
-            else LAUNCH((k_lj1g_pipe<false>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), nullptr);
+            if (with_energy) { LAUNCH((k_lj1g_pipe<true>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), epart); e_parts = nb; e_scale = 0.5; }
+            else LAUNCH((k_lj1g_pipe<false>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), nullptr);
             c->launches += 1;
             break;
         }
         if (with_energy) {
             KTimer kt(c, KS_LJ1G);
-            if (small) LAUNCH((k_lj1g<true, true, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);
-            else LAUNCH((k_lj1g<true, true, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, epart);
+            if (small) LAUNCH((k_lj1g<true, true, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, epart);
+            else LAUNCH((k_lj1g<true, true, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, epart);
             e_parts = small ? nbs : nb; e_scale = 0.5;
         } else
-        { KTimer kt(c, KS_LJ1G); if (small) LAUNCH((k_lj1g<true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); else LAUNCH((k_lj1g<true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), it.lj1g, c->box, nullptr); }
+        { KTimer kt(c, KS_LJ1G); if (small) LAUNCH((k_lj1g<true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, nullptr); else LAUNCH((k_lj1g<true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, nullptr); }
         c->launches += 1;
         break;
     case K_RJL:
@@ -1129,22 +1134,22 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
             {
                 KTimer kt(c, KS_RJL_DENSITY);
                 if (with_energy && !e_in_force) {
-                    if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, epart);
-                    else LAUNCH((k_rjl_density<true, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, epart, fused ? slab_dev(c, 1) : SDpos);
+                    if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT, TD>), nbs, FT, fs, N, c->pos, lv, CD, c->box, W, epart);
+                    else LAUNCH((k_rjl_density<true, TD>), nb, FT, fs, N, c->pos, lv, CD, c->box, W, epart, fused ? slab_dev(c, 1) : SDpos);
                     e_parts = small ? nbs : nb;
                 } else
-                if (small) LAUNCH((k_rjl_density_split<false, SMALL_SPLIT, TD>), nbs, FT, c->st, N, c->pos, lv, CD, c->box, W, (double*)nullptr);
-                else LAUNCH((k_rjl_density<false, TD>), nb, FT, c->st, N, c->pos, lv, CD, c->box, W, (double*)nullptr, fused ? slab_dev(c, 1) : SDpos);
+                if (small) LAUNCH((k_rjl_density_split<false, SMALL_SPLIT, TD>), nbs, FT, fs, N, c->pos, lv, CD, c->box, W, (double*)nullptr);
+                else LAUNCH((k_rjl_density<false, TD>), nb, FT, fs, N, c->pos, lv, CD, c->box, W, (double*)nullptr, fused ? slab_dev(c, 1) : SDpos);
             }
             if (c->slab && !fused) { slab_set_consumer_waits(c, !small); slab_exchange(c, 1); }  // ghost 1/Eb from their owners
             if (!e_in_force) {
                 KTimer kt(c, KS_RJL_FORCE);
-                if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W);
+                if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, fs, N, c->pos, fo, lv, CF, c->box, W);
                 else {
                     bool launched = false;
                     if constexpr (std::is_same<TF, RjlG>::value)
-                        if (c->rjl_minb == 8) { LAUNCH((k_rjl_force<TF, 8>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : slab_wait_dev(c, 1), ow); launched = true; }
-                    if (!launched) LAUNCH((k_rjl_force<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, fused ? slab_dev(c, 2) : slab_wait_dev(c, 1), ow);
+                        if (c->rjl_minb == 8) { LAUNCH((k_rjl_force<TF, 8>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, fused ? slab_dev(c, 2) : slab_wait_dev(c, 1), ow); launched = true; }
+                    if (!launched) LAUNCH((k_rjl_force<TF>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, fused ? slab_dev(c, 2) : slab_wait_dev(c, 1), ow);
                 }
             }
         };
@@ -1152,12 +1157,12 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         auto force_e = [&](auto CF) {   // force pass that also yields the step's energy
             using TF = decltype(CF);
             KTimer kt(c, KS_RJL_FORCE);
-            if (small) { LAUNCH((k_rjl_force_split_e<SMALL_SPLIT, TF>), nbs, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, erep, it.rjl.xi, epart); e_parts = nbs; return; }
+            if (small) { LAUNCH((k_rjl_force_split_e<SMALL_SPLIT, TF>), nbs, FT, fs, N, c->pos, fo, lv, CF, c->box, W, erep, it.rjl.xi, epart); e_parts = nbs; return; }
             const SlabDev SD = fused ? slab_dev(c, 2) : slab_wait_dev(c, 1);
             bool launched = false;
             if constexpr (std::is_same<TF, RjlG>::value)
-                if (c->rjl_minb == 8) { LAUNCH((k_rjl_force_e<TF, 8>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart); launched = true; }
-            if (!launched) LAUNCH((k_rjl_force_e<TF>), nb, FT, c->st, N, c->pos, c->frc, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart);
+                if (c->rjl_minb == 8) { LAUNCH((k_rjl_force_e<TF, 8>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart); launched = true; }
+            if (!launched) LAUNCH((k_rjl_force_e<TF>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart);
             e_parts = nb;
         };
         if (gen3) {
@@ -1179,11 +1184,11 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     case K_TB:
     {
         dim3 grid(nb, it.nl[0].maxn);
-        { KTimer kt(c, KS_TB_BOND); LAUNCH((k_tb_bond), grid, FT, c->st, N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2); }
+        { KTimer kt(c, KS_TB_BOND); LAUNCH((k_tb_bond), grid, FT, fs, N, c->pos, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2); }
         {
             KTimer kt(c, KS_TB_FORCE);
-            LAUNCH((k_tb_force<true, false>), grid, FT, c->st, N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, nullptr);
-            LAUNCH((k_tb_reduce), nb, FT, c->st, N, it.fpart, c->frc, it.nl[0].view(st));
+            LAUNCH((k_tb_force<true, false>), grid, FT, fs, N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, nullptr);
+            LAUNCH((k_tb_reduce), nb, FT, fs, N, it.fpart, fo, it.nl[0].view(st));
         }
         c->launches += 3;
     }
@@ -1193,13 +1198,13 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         CosP P = cosp_of(it);
         bool simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
         if (it.kind == K_LJC) {
-            { KTimer kt(c, KS_COS_GRAPHENE); if (small) LAUNCH((k_cos_direct<false, true, true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, true, true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
-            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); LAUNCH((k_cos_indirect), nb, FT, c->st, N, c->pos, c->frc, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec); }
-            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<false, false, true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, false, true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_GRAPHENE); if (small) LAUNCH((k_cos_direct<false, true, true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, true, true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); LAUNCH((k_cos_indirect), nb, FT, fs, N, c->pos, fo, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec); }
+            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<false, false, true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, false, true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         } else {
-            { KTimer kt(c, KS_COS_GRAPHENE); if (small) LAUNCH((k_cos_direct<true, true, true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, true, true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
-            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); LAUNCH((k_cos_indirect), nb, FT, c->st, N, c->pos, c->frc, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec); }
-            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<true, false, true, false, SMALL_SPLIT>), nbs, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, false, true, false, 1>), nb, FT, c->st, N, c->pos, c->frc, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_GRAPHENE); if (small) LAUNCH((k_cos_direct<true, true, true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, true, true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            if (!simp) { KTimer kt(c, KS_COS_INDIRECT); LAUNCH((k_cos_indirect), nb, FT, fs, N, c->pos, fo, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec); }
+            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<true, false, true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, false, true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         }
         c->launches += simp ? 2 : 3;
         break;
@@ -1207,7 +1212,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     }
     if (with_energy) {
         if (e_parts) {
-            LAUNCH((k_sum_partials), 1, 1024, c->st, e_parts, c->part, e_scale, c->energy + k);
+            LAUNCH((k_sum_partials), 1, 1024, fs, e_parts, c->part, e_scale, c->energy + k);
             c->launches += 1;
             if (c->slab) slab_allreduce_sum(c, c->energy + k, 1);
         } else {

@@ -362,6 +362,8 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr)
     return cudaSuccess;
 }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return emu_capture ? cudaErrorEmu : cudaSuccess; }
+// (the replay runs every launch at once, in call order: a cross-stream dependency is already satisfied when it is declared)
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { double d = *(double*)b - *(double*)a; *ms = (float)(d > 1e-6 ? d : 1e-6); return cudaSuccess; }
 // CUDA graphs: a capture records closures (above), an executable graph is a copy of the list, a launch runs it
 static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { if (emu_capture) return cudaErrorEmu; emu_capture = new emu_graph_s; return cudaSuccess; }

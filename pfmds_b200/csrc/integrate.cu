@@ -372,6 +372,55 @@ __global__ void k_nhc_close(int nparts, const double* __restrict__ part, NhcPack
         __syncthreads();
     }
 }
+// ---- small systems: sum of the per-interaction force buffers (+ closing kick, + thermostat KE partials) ----------------------
+// The interactions of a step ran concurrently, each accumulating into its own buffer (ctx.hpp fbuf).  Per atom: start from what
+// zero_forces leaves (0 inside the all_atoms group, the old force outside it: md_integrators.f90:147-163), add the buffers in file
+// order -- the sequence of additions of the one-after-the-other path, so the same bits -- store, clear the buffers for the next
+// step, then k_kick / k_kick_ke's arithmetic unchanged (same grid, same partial sums: the same kinetic energy bits).
+struct FBufs { int n; double4* b[8]; };
+template <int MODE>  // 0: sum only (step 0, restore); 1: + closing half kick; 2: + KE partial sums of the thermostat groups
+__global__ void __launch_bounds__(IT) k_sum_kick_ke(int N, double4* __restrict__ vel, double4* __restrict__ frc, const uint32_t* __restrict__ gmask, FBufs F,
+                                                    int zero_all, uint32_t ball, uint32_t bxyz, uint32_t bz, double ts2, NhcPack P, double* __restrict__ part) {
+    double ke[NHC_MAXF];
+    for (int k = 0; k < NHC_MAXF; ++k) ke[k] = 0.;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const uint32_t g = gmask[i];
+        double4 f = make_double4(0., 0., 0., 0.);
+        if (!zero_all && !(g & ball)) f = frc[i];
+        for (int t = 0; t < F.n; ++t) {
+            const double4 a = F.b[t][i];
+            f.x += a.x; f.y += a.y; f.z += a.z;
+            F.b[t][i] = make_double4(0., 0., 0., 0.);
+        }
+        frc[i] = f;
+        if (MODE == 0 || (g & PFMDS_GHOST)) continue;
+        const bool mx = g & bxyz, mz = g & bz;
+        bool th = false;
+        if (MODE == 2)
+            for (int k = 0; k < P.n; ++k) th |= (g & P.bit[k]) != 0;
+        if (!mx && !mz && !th) continue;
+        double4 v = vel[i];
+        if (mx || mz) {
+            if (mx) {
+                v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
+                v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
+                v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+            }
+            if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+            vel[i] = v;
+        }
+        if (MODE == 2) {
+            double e = v.w * (v.x * v.x + v.y * v.y + v.z * v.z) / 2 * PFMDS_MASS_COEF;
+            for (int k = 0; k < P.n; ++k)
+                if (g & P.bit[k]) ke[k] += e;
+        }
+    }
+    if (MODE == 2)
+        for (int k = 0; k < P.n; ++k) {
+            double s = block_sum(ke[k]);
+            if (threadIdx.x == 0) part[blockIdx.x * NHC_MAXF + k] = s;
+        }
+}
 static NhcPack pack_of(pfmds_ctx* c) {
     NhcPack P{};
     P.n = (int)c->nhc.size();
@@ -415,6 +464,24 @@ void integ_nvt_kick_close(pfmds_ctx* c, double dt) {
         LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
     }
     c->launches += 2;
+}
+void integ_sum_forces(pfmds_ctx* c, int mode, double dt) {
+    FBufs F{};
+    F.n = (int)c->fbuf.size();
+    for (int t = 0; t < F.n; ++t) F.b[t] = c->fbuf[(size_t)t];
+    const uint32_t ball = 1u << (c->all_atoms - 1), bxyz = 1u << (c->xyz_moving - 1), bz = 1u << (c->z_moving - 1);
+    NhcPack P{};
+    if (mode == 2) P = pack_of(c);
+    KTimer kt(c, KS_KICK);
+    if (mode == 0) LAUNCH((k_sum_kick_ke<0>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, 0., P, c->part);
+    else if (mode == 1) LAUNCH((k_sum_kick_ke<1>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, dt / 2, P, c->part);
+    else {
+        LAUNCH((k_sum_kick_ke<2>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, dt / 2, P, c->part);
+        LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
+        c->launches += 1;
+    }
+    c->launches += 1;
+    c->fbuf_active = false;
 }
 // apply scalings that are still pending (before anything else reads or changes velocities)
 void integ_flush_pending(pfmds_ctx* c) {

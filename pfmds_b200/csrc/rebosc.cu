@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(RT) k_rebosc_numforce(int N, const double4* __
 void rebosc_forces(pfmds_ctx* c, Inter& it) {
     const int N = c->N;
     KTimer kt(c, KS_REBOSC_FORCE);
-    LAUNCH((k_rebosc_numforce), (3 * N + RT - 1) / RT, RT, c->st, N, c->pos, c->frc, it.nl[0].view(c->stride), it.reb, c->box, c->orig, c->err);
+    LAUNCH((k_rebosc_numforce), (3 * N + RT - 1) / RT, RT, c->fst ? c->fst : c->st, N, c->pos, c->fout ? c->fout : c->frc, it.nl[0].view(c->stride), it.reb, c->box, c->orig, c->err);
     c->launches += 1;
     CK(cudaGetLastError());
 }
