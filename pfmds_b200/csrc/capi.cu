@@ -57,6 +57,7 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     c->lj1g_pipe = env_int("PFMDS_LJ1G_PIPE", 1) != 0;
     c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
     c->nl_cell = env_int("PFMDS_NL_CELL", 1) != 0;
+    c->pre_open_enabled = env_int("PFMDS_PRE_OPEN", 1) != 0;
     // 2 is the default: the third generation (node-table exponentials) removes 13 of 43 FP64 instructions per pair but its table
     // look-ups double the L1 data-pipe wavefronts, and that pipe is what bounds these kernels (ncu, profiles/r2b_*): measured
     // 0.343 against 0.277 ms (density) and 0.362 against 0.360 ms (force) per launch at 10^6 atoms
@@ -329,22 +330,26 @@ void finalize(pfmds_ctx* c) {
     alloc_log(c);
     check_rjl_generation(c);
     for (auto& it : c->inter) rjl_prepare(c, it);
-    if (c->N < c->small_n && c->inter.size() >= 2 && c->inter.size() <= 8 && env_int("PFMDS_SMALL_FORK", 1) != 0) {
-        for (size_t k = 0; k < c->inter.size(); ++k) {
-            double4* b = nullptr;
-            CK(cudaMalloc(&b, sizeof(double4) * c->stride));
-            CK(cudaMemset(b, 0, sizeof(double4) * c->stride));
-            c->fbuf.push_back(b);
-            cudaStream_t s = nullptr;
-            CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-            c->aux_st.push_back(s);
+    {   // per-interaction force buffers of small systems (compute_forces); lj gets two: its two lists run as separate branches
+        size_t nbuf = 0;
+        for (auto& it : c->inter) nbuf += it.kind == K_LJ ? 2 : 1;
+        if (c->N < c->small_n && c->inter.size() >= 2 && nbuf <= 12 && env_int("PFMDS_SMALL_FORK", 1) != 0) {
+            for (size_t k = 0; k < nbuf; ++k) {
+                double4* b = nullptr;
+                CK(cudaMalloc(&b, sizeof(double4) * c->stride));
+                CK(cudaMemset(b, 0, sizeof(double4) * c->stride));
+                c->fbuf.push_back(b);
+                cudaStream_t st = nullptr;
+                CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                c->aux_st.push_back(st);
+            }
+            for (size_t k = 0; k < nbuf + 1; ++k) {
+                cudaEvent_t e = nullptr;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                c->aux_ev.push_back(e);
+            }
+            c->fbuf_on = true;
         }
-        for (size_t k = 0; k < c->inter.size() + 1; ++k) {
-            cudaEvent_t e = nullptr;
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->aux_ev.push_back(e);
-        }
-        c->fbuf_on = true;
     }
     c->first_overwrites = c->zero_all && c->changes.empty() && !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
     nl_setup_grid(c);
@@ -434,7 +439,8 @@ void update_lists(pfmds_ctx* c, int step) {
             }
         }
     }
-    for (size_t k = 0; k < c->inter.size(); ++k) normals_interaction(c, (int)k);  // update_norm_in_graphene, every step
+    if (!c->fbuf_on)   // (small systems: the normals are the first kernel of the ljc / morsec branch of compute_forces)
+        for (size_t k = 0; k < c->inter.size(); ++k) normals_interaction(c, (int)k);  // update_norm_in_graphene, every step
 }
 
 // zero_forces + calculate_forces + calculate_forces_numerically, md_simulation.f90:163-165
@@ -452,16 +458,20 @@ void compute_forces(pfmds_ctx* c, bool with_energy, bool defer_sum = false) {
         for (size_t k = 0; k < c->inter.size(); ++k) if (c->inter[k].kind == K_REBOSC) order.push_back(k);
         c->fbuf_active = true;
         if (fork) CK(cudaEventRecord(c->aux_ev[0], c->st));
+        size_t b = 0;   // next buffer, in summation order
         for (size_t q = 0; q < order.size(); ++q) {
-            cudaStream_t s = fork ? c->aux_st[q] : nullptr;
-            if (fork) CK(cudaStreamWaitEvent(s, c->aux_ev[0], 0));
-            c->fst = s; c->fout = c->fbuf[q];
-            try { forces_interaction(c, (int)order[q], with_energy); } catch (...) { c->fst = nullptr; c->fout = nullptr; throw; }
-            if (fork) CK(cudaEventRecord(c->aux_ev[1 + q], s));
+            const bool two = c->inter[order[q]].kind == K_LJ;   // second list of lj: its own branch and buffer
+            cudaStream_t s1 = fork ? c->aux_st[b] : nullptr, s2 = (fork && two) ? c->aux_st[b + 1] : nullptr;
+            if (fork) { CK(cudaStreamWaitEvent(s1, c->aux_ev[0], 0)); if (two) CK(cudaStreamWaitEvent(s2, c->aux_ev[0], 0)); }
+            c->fst = s1; c->fout = c->fbuf[b];
+            c->fst2 = two ? s2 : nullptr; c->fout2 = two ? c->fbuf[b + 1] : nullptr;
+            try { forces_interaction(c, (int)order[q], with_energy); } catch (...) { c->fst = c->fst2 = nullptr; c->fout = c->fout2 = nullptr; throw; }
+            if (fork) { CK(cudaEventRecord(c->aux_ev[1 + b], s1)); if (two) CK(cudaEventRecord(c->aux_ev[2 + b], s2)); }
+            b += two ? 2 : 1;
         }
-        c->fst = nullptr; c->fout = nullptr;
+        c->fst = c->fst2 = nullptr; c->fout = c->fout2 = nullptr;
         if (fork)
-            for (size_t q = 0; q < order.size(); ++q) CK(cudaStreamWaitEvent(c->st, c->aux_ev[1 + q], 0));
+            for (size_t q = 0; q < b; ++q) CK(cudaStreamWaitEvent(c->st, c->aux_ev[1 + q], 0));
         if (!defer_sum) integ_sum_forces(c, 0, 0.);
         c->energy_valid = with_energy;
         return;
@@ -857,7 +867,10 @@ int pfmds_add_interaction(pfmds_ctx* c, const char* name, int np, const double* 
 // One md step of a call that started at step `first`.  Steady-state steps (no list rebuild, no momentum removal, no energy
 // request, not the first of the call) of small systems are replayed from a CUDA graph captured from this very code path: same
 // kernels, same order, fewer launch gaps.
-static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool with_energy) {
+static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool with_energy, bool next_follows = false) {
+    // the thermostat's opening half step of step s+1 can ride in the closing kernel of step s when s+1 follows inside this call,
+    // nothing reads or regroups the chains in between (no log row, no deposition) and the fused NVT path is in use
+    c->pre_open = next_follows && kind == PFMDS_NVT && c->nhc_fusable && !c->slab && c->changes.empty() && !with_energy && c->pre_open_enabled;
     bool rebuild = false;
     for (auto& it : c->inter)
         for (int j = 0; j < it.nl_n; ++j) rebuild |= (s % it.nl[j].period == 0) || !it.nl[j].built;
@@ -875,9 +888,10 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
     }
     pfmds_ctx::StepGraph* g = nullptr;
     for (auto& e : c->graphs)
-        if (e.kind == kind && e.dt == dt && e.pos == (const void*)c->pos && e.pending == c->nhc_pending && e.ke_valid == c->nhc_ke_valid) g = &e;
+        if (e.kind == kind && e.dt == dt && e.pos == (const void*)c->pos && e.pending == c->nhc_pending && e.ke_valid == c->nhc_ke_valid &&
+            e.opened == c->nhc_opened && e.pre_open == c->pre_open) g = &e;
     if (!g) {
-        pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, nullptr, 0};
+        pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, c->nhc_opened, c->pre_open, nullptr, 0};
         const long long l0 = c->launches;
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
@@ -900,8 +914,8 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
     c->launches += g->launches;
     c->energy_valid = false;
     // host-side bookkeeping of do_step for this integrator
-    if (kind == PFMDS_NVT && c->nhc_fusable) { c->nhc_pending = true; c->nhc_ke_valid = true; }
-    else { c->nhc_pending = false; c->nhc_ke_valid = false; }
+    if (kind == PFMDS_NVT && c->nhc_fusable) { c->nhc_pending = true; c->nhc_ke_valid = true; c->nhc_opened = c->pre_open; }
+    else { c->nhc_pending = false; c->nhc_ke_valid = false; c->nhc_opened = false; }
 }
 
 static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, bool energy_last);
@@ -913,7 +927,7 @@ static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, boo
         if (n < 0 || first < 0) fail(PFMDS_ERR_INVALID, "error: bad step range");
         CK(cudaSetDevice(c->dev));
         finalize(c);
-        for (int s = first; s < first + n; ++s) run_step(c, s, first, kind, dt, energy_last && s == first + n - 1);
+        for (int s = first; s < first + n; ++s) run_step(c, s, first, kind, dt, energy_last && s == first + n - 1, s + 1 < first + n);
         CK(cudaGetLastError());
     });
 }
@@ -969,7 +983,7 @@ int pfmds_advance_logged(pfmds_ctx* c, int kind, double dt, int first, int n, in
         int r = 0;
         for (int s = first; s < first + n; ++s) {
             const bool logged = s % log_period == 0;
-            run_step(c, s, first, kind, dt, logged);   // unlogged steady-state steps of small systems replay their CUDA graph, as in pfmds_advance
+            run_step(c, s, first, kind, dt, logged, s + 1 < first + n);   // unlogged steady-state steps of small systems replay their CUDA graph, as in pfmds_advance
             if (!logged) continue;
             integ_flush_pending(c);                              // as pfmds_energies: KE of the velocities the host would download
             integ_kinetic_energy(c, c->all_moving, c->red);

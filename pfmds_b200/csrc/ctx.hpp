@@ -93,7 +93,7 @@ struct pfmds_ctx {
     int* newslot = nullptr;  // old slot -> new slot of the last cell re-sort
     std::vector<long long> group_count;  // slab mode: global size of every group
     // CUDA graphs of the steady-state step (small systems are launch-latency bound), keyed by what is baked in
-    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid; cudaGraphExec_t exec; long long launches; };
+    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid, opened, pre_open; cudaGraphExec_t exec; long long launches; };
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
     int rjl_minb = 7;               // blocks/SM the third-generation rjl force kernels are compiled for: 7 (72 registers) or 8 (64; PFMDS_RJL_MINB=8)
@@ -111,8 +111,8 @@ struct pfmds_ctx {
     std::vector<double4*> fbuf;
     std::vector<cudaStream_t> aux_st;
     std::vector<cudaEvent_t> aux_ev;     // [0] fork, [1 + k] join of branch k
-    cudaStream_t fst = nullptr;
-    double4* fout = nullptr;
+    cudaStream_t fst = nullptr, fst2 = nullptr;   // (fst2 / fout2: the converse-list launch of lj)
+    double4 *fout = nullptr, *fout2 = nullptr;
     bool fbuf_on = false;                // buffers exist (finalize): small system, at most 8 interactions, PFMDS_SMALL_FORK != 0
     bool fbuf_active = false;            // this step's forces went into the buffers: the sum kernel must run
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
@@ -122,6 +122,9 @@ struct pfmds_ctx {
     bool nhc_fusable = false;
     bool nhc_ke_valid = false;  // state[3M+1] holds the current kinetic energy of each thermostat group
     bool nhc_pending = false;   // state[3M+2] holds a velocity scale that has not been applied yet
+    bool pre_open_enabled = true;  // PFMDS_PRE_OPEN=0: k_nhc_open stays a launch of its own
+    bool pre_open = false;      // set per step by the caller: the next NVT step follows in the same call and nothing reads the chains before it
+    bool nhc_opened = false;    // the pending scale already contains the opening half step of the next step (k_nhc_close also_open)
     long long launches = 0;
     std::string err_msg;
     // phase timers (PFMDS_TIMERS=1)
@@ -188,7 +191,7 @@ long long slab_n_global(pfmds_ctx* c);
 void forces_zero(pfmds_ctx* c);
 void rjl_prepare(pfmds_ctx* c, Inter& it);  // third-generation rjl: node table of the exponentials, built once
 void forces_interaction(pfmds_ctx* c, int k, bool with_energy);
-void normals_interaction(pfmds_ctx* c, int k);
+void normals_interaction(pfmds_ctx* c, int k, cudaStream_t st = nullptr);
 void energy_interaction(pfmds_ctx* c, int k);  // result in c->energy[k]
 
 // ---- rebosc.cu ----

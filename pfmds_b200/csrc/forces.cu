@@ -1059,13 +1059,13 @@ void rjl_prepare(pfmds_ctx* c, Inter& it) {
     CK(cudaMemcpy(it.aux, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
 }
 
-void normals_interaction(pfmds_ctx* c, int k) {  // update_norm_in_graphene, md_interactions.f90:195-208
+void normals_interaction(pfmds_ctx* c, int k, cudaStream_t st) {  // update_norm_in_graphene, md_interactions.f90:195-208
     Inter& it = c->inter[k];
     if (it.kind != K_LJC && it.kind != K_MORSEC) return;
     const int N = c->N, nb = (N + FT - 1) / FT;
     int simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
     KTimer kt(c, KS_NORMALS);
-    LAUNCH((k_normals), nb, FT, c->st, N, c->pos, it.nl[2].view(c->stride), c->box, simp, it.gnorm);
+    LAUNCH((k_normals), nb, FT, st ? st : c->st, N, c->pos, it.nl[2].view(c->stride), c->box, simp, it.gnorm);
     c->launches += 1;
 }
 
@@ -1094,7 +1094,13 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         } else
         { KTimer kt(c, KS_LJ); if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj, c->box, nullptr); else LAUNCH((k_lj<true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj, c->box, nullptr); }
         if (e_parts) { LAUNCH((k_sum_partials), 1, 1024, fs, e_parts, c->part, 1.0, c->energy + k); c->launches += 1; if (c->slab) slab_allreduce_sum(c, c->energy + k, 1); e_parts = 0; with_energy = false; }
-        { KTimer kt(c, KS_LJ); if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[1].view(st), it.lj, c->box, nullptr); else LAUNCH((k_lj<true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[1].view(st), it.lj, c->box, nullptr); }
+        {   // converse list: owners are the atoms of group 2 (small systems: a branch and a buffer of its own)
+            cudaStream_t fs2 = c->fout2 ? (c->fst2 ? c->fst2 : c->st) : fs;
+            double4* fo2 = c->fout2 ? c->fout2 : fo;
+            KTimer kt(c, KS_LJ);
+            if (small) LAUNCH((k_lj<true, false, SMALL_SPLIT>), nbs, FT, fs2, N, c->pos, fo2, it.nl[1].view(st), it.lj, c->box, nullptr);
+            else LAUNCH((k_lj<true, false, 1>), nb, FT, fs2, N, c->pos, fo2, it.nl[1].view(st), it.lj, c->box, nullptr);
+        }
         c->launches += 2;
         break;
     case K_LJ1G:
@@ -1195,6 +1201,7 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         break;
     case K_LJC:
     case K_MORSEC: {
+        if (c->fbuf_on) normals_interaction(c, k, fs);   // small systems: the normals open this interaction's branch (otherwise update_lists ran them)
         CosP P = cosp_of(it);
         bool simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
         if (it.kind == K_LJC) {

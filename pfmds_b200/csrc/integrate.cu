@@ -358,7 +358,10 @@ __global__ void __launch_bounds__(IT) k_kick_ke(int N, double4* __restrict__ vel
         if (threadIdx.x == 0) part[blockIdx.x * NHC_MAXF + k] = s;
     }
 }
-__global__ void k_nhc_close(int nparts, const double* __restrict__ part, NhcPack P, double ts2, double ts3, double ts4) {
+// also_open: the next step follows at once inside the same call (nothing reads the chain in between), so its opening half step
+// -- k_nhc_open's statements, on the kinetic energy this kernel has just cached -- runs here too: one launch less on the critical
+// path of every step of a small system.
+__global__ void k_nhc_close(int nparts, const double* __restrict__ part, NhcPack P, double ts2, double ts3, double ts4, int also_open) {
     for (int k = 0; k < P.n; ++k) {
         double ke = 0;
         for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i * NHC_MAXF + k];
@@ -368,6 +371,10 @@ __global__ void k_nhc_close(int nparts, const double* __restrict__ part, NhcPack
             int M = P.M[k];
             double s = nhc_chain(st, M, P.L[k], P.T[k], ke, ts2, ts3, ts4);
             st[3 * M + 2] = s;
+            if (also_open) {
+                double so = nhc_chain(st, M, P.L[k], P.T[k], st[3 * M + 1], ts2, ts3, ts4);
+                st[3 * M + 2] *= so;
+            }
         }
         __syncthreads();
     }
@@ -377,7 +384,7 @@ __global__ void k_nhc_close(int nparts, const double* __restrict__ part, NhcPack
 // zero_forces leaves (0 inside the all_atoms group, the old force outside it: md_integrators.f90:147-163), add the buffers in file
 // order -- the sequence of additions of the one-after-the-other path, so the same bits -- store, clear the buffers for the next
 // step, then k_kick / k_kick_ke's arithmetic unchanged (same grid, same partial sums: the same kinetic energy bits).
-struct FBufs { int n; double4* b[8]; };
+struct FBufs { int n; double4* b[12]; };
 template <int MODE>  // 0: sum only (step 0, restore); 1: + closing half kick; 2: + KE partial sums of the thermostat groups
 __global__ void __launch_bounds__(IT) k_sum_kick_ke(int N, double4* __restrict__ vel, double4* __restrict__ frc, const uint32_t* __restrict__ gmask, FBufs F,
                                                     int zero_all, uint32_t ball, uint32_t bxyz, uint32_t bz, double ts2, NhcPack P, double* __restrict__ part) {
@@ -432,13 +439,14 @@ static NhcPack pack_of(pfmds_ctx* c) {
 void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step) {
     NhcPack P = pack_of(c);
     KTimer kt(c, KS_KICK_DRIFT);
-    LAUNCH((k_nhc_open), 1, 32, c->st, P, dt / 2, dt / 4, dt / 8);
+    if (!c->nhc_opened) { LAUNCH((k_nhc_open), 1, 32, c->st, P, dt / 2, dt / 4, dt / 8); c->launches += 1; }  // else: done by the previous step's k_nhc_close
+    c->nhc_opened = false;
     SlabDev S{};
     if (c->slab && slab_pos_pushed_by_kick(c, rebuild_step)) S = slab_dev(c, 0);
     LAUNCH((k_kick_drift_nvt), (c->N + IT - 1) / IT, IT, c->st, c->N, c->pos, c->vel, c->frc, c->gmask, c->orig, 1u << (c->xyz_moving - 1),
                                                              1u << (c->z_moving - 1), dt, dt / 2, c->box, P, c->err, S);
     // s_pending has been consumed; the closing half step of this same step overwrites it (k_nhc_close), so no reset here
-    c->launches += 2;
+    c->launches += 1;
 }
 __global__ void k_reduce_ke_partials(int nparts, const double* __restrict__ part, int n, double* __restrict__ out) {
     for (int k = 0; k < n; ++k) {
@@ -458,10 +466,11 @@ void integ_nvt_kick_close(pfmds_ctx* c, double dt) {
     } else if (c->slab) {  // rank-local sums, one all-reduce, then every rank runs the same chain update
         LAUNCH((k_reduce_ke_partials), 1, 1024, c->st, RED_BLOCKS, c->part, P.n, c->red + 48);
         slab_allreduce_sum(c, c->red + 48, P.n);
-        LAUNCH((k_nhc_close), 1, 32, c->st, 1, c->red + 48, P, dt / 2, dt / 4, dt / 8);
+        LAUNCH((k_nhc_close), 1, 32, c->st, 1, c->red + 48, P, dt / 2, dt / 4, dt / 8, 0);
         c->launches += 1;
     } else {
-        LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
+        LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8, (int)c->pre_open);
+        c->nhc_opened = c->pre_open;
     }
     c->launches += 2;
 }
@@ -477,7 +486,8 @@ void integ_sum_forces(pfmds_ctx* c, int mode, double dt) {
     else if (mode == 1) LAUNCH((k_sum_kick_ke<1>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, dt / 2, P, c->part);
     else {
         LAUNCH((k_sum_kick_ke<2>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, dt / 2, P, c->part);
-        LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8);
+        LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8, (int)c->pre_open);
+        c->nhc_opened = c->pre_open;
         c->launches += 1;
     }
     c->launches += 1;
