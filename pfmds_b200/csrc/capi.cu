@@ -348,6 +348,8 @@ void finalize(pfmds_ctx* c) {
                 CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 c->aux_ev.push_back(e);
             }
+            CK(cudaMalloc(&c->ticket, sizeof(unsigned int)));
+            CK(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
             c->fbuf_on = true;
         }
     }
@@ -1666,6 +1668,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     for (int* r : c->d_grank) cudaFree(r);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     for (auto b : c->fbuf) cudaFree(b);
+    cudaFree(c->ticket);
     for (auto s : c->aux_st) cudaStreamDestroy(s);
     for (auto e : c->aux_ev) cudaEventDestroy(e);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,

@@ -113,6 +113,7 @@ struct pfmds_ctx {
     std::vector<cudaEvent_t> aux_ev;     // [0] fork, [1 + k] join of branch k
     cudaStream_t fst = nullptr, fst2 = nullptr;   // (fst2 / fout2: the converse-list launch of lj)
     double4 *fout = nullptr, *fout2 = nullptr;
+    unsigned int* ticket = nullptr;      // block counter of k_sum_kick_ke (its last block closes the thermostat step)
     bool fbuf_on = false;                // buffers exist (finalize): small system, at most 8 interactions, PFMDS_SMALL_FORK != 0
     bool fbuf_active = false;            // this step's forces went into the buffers: the sum kernel must run
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass

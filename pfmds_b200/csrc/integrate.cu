@@ -66,7 +66,7 @@ void integ_kinetic_energy(pfmds_ctx* c, int group, double* d_out) {
 
 // (nhc_chain, the Nose-Hoover chain half step of md_integrators.f90:200-245, lives in common.cuh)
 // One block sums the KE partials (fixed order), thread 0 runs the chain.
-__global__ void k_nhc(int nparts, const double* __restrict__ part, double* state, int M, int L, double temperature, double ts2, double ts3,
+__global__ void __launch_bounds__(1024) k_nhc(int nparts, const double* __restrict__ part, double* state, int M, int L, double temperature, double ts2, double ts3,
                       double ts4) {
     double ke = 0;
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i];
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(IT) k_kick_ke(int N, double4* __restrict__ vel
 // also_open: the next step follows at once inside the same call (nothing reads the chain in between), so its opening half step
 // -- k_nhc_open's statements, on the kinetic energy this kernel has just cached -- runs here too: one launch less on the critical
 // path of every step of a small system.
-__global__ void k_nhc_close(int nparts, const double* __restrict__ part, NhcPack P, double ts2, double ts3, double ts4, int also_open) {
+__global__ void __launch_bounds__(1024) k_nhc_close(int nparts, const double* __restrict__ part, NhcPack P, double ts2, double ts3, double ts4, int also_open) {
     for (int k = 0; k < P.n; ++k) {
         double ke = 0;
         for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i * NHC_MAXF + k];
@@ -387,7 +387,8 @@ __global__ void k_nhc_close(int nparts, const double* __restrict__ part, NhcPack
 struct FBufs { int n; double4* b[12]; };
 template <int MODE>  // 0: sum only (step 0, restore); 1: + closing half kick; 2: + KE partial sums of the thermostat groups
 __global__ void __launch_bounds__(IT) k_sum_kick_ke(int N, double4* __restrict__ vel, double4* __restrict__ frc, const uint32_t* __restrict__ gmask, FBufs F,
-                                                    int zero_all, uint32_t ball, uint32_t bxyz, uint32_t bz, double ts2, NhcPack P, double* __restrict__ part) {
+                                                    int zero_all, uint32_t ball, uint32_t bxyz, uint32_t bz, double ts2, NhcPack P, double* __restrict__ part,
+                                                    unsigned int* ticket, int also_open) {
     double ke[NHC_MAXF];
     for (int k = 0; k < NHC_MAXF; ++k) ke[k] = 0.;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
@@ -422,11 +423,41 @@ __global__ void __launch_bounds__(IT) k_sum_kick_ke(int N, double4* __restrict__
                 if (g & P.bit[k]) ke[k] += e;
         }
     }
-    if (MODE == 2)
+    if (MODE == 2) {
         for (int k = 0; k < P.n; ++k) {
             double s = block_sum(ke[k]);
             if (threadIdx.x == 0) part[blockIdx.x * NHC_MAXF + k] = s;
         }
+#ifdef PFMDS_COOP
+        // The block that finishes last closes the thermostat step (k_nhc_close's statements: partials summed in block order by one
+        // block, chain update by its thread 0), so small systems, whose steps are chains of 5-us kernels, lose one link of the chain.
+        if (ticket) {
+            __shared__ bool last;
+            if (threadIdx.x == 0) {
+                __threadfence();                                   // this block's partials before its ticket
+                last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+            }
+            __syncthreads();
+            if (last) {
+                __threadfence();                                   // every other block's partials after their tickets
+                const volatile double* vp = part;
+                for (int k = 0; k < P.n; ++k) {
+                    double sk = 0.;
+                    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) sk += vp[(size_t)b * NHC_MAXF + k];
+                    sk = block_sum(sk);
+                    if (threadIdx.x == 0) {
+                        double* st = P.state[k];
+                        const int M = P.M[k];
+                        st[3 * M + 2] = nhc_chain(st, M, P.L[k], P.T[k], sk, ts2, ts2 / 2, ts2 / 4);
+                        if (also_open) st[3 * M + 2] *= nhc_chain(st, M, P.L[k], P.T[k], st[3 * M + 1], ts2, ts2 / 2, ts2 / 4);
+                    }
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) *ticket = 0u;                // ready for the next launch
+            }
+        }
+#endif
+    }
 }
 static NhcPack pack_of(pfmds_ctx* c) {
     NhcPack P{};
@@ -482,13 +513,18 @@ void integ_sum_forces(pfmds_ctx* c, int mode, double dt) {
     NhcPack P{};
     if (mode == 2) P = pack_of(c);
     KTimer kt(c, KS_KICK);
-    if (mode == 0) LAUNCH((k_sum_kick_ke<0>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, 0., P, c->part);
-    else if (mode == 1) LAUNCH((k_sum_kick_ke<1>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, dt / 2, P, c->part);
+    unsigned int* const none = nullptr;
+    if (mode == 0) LAUNCH((k_sum_kick_ke<0>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, 0., P, c->part, none, 0);
+    else if (mode == 1) LAUNCH((k_sum_kick_ke<1>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, dt / 2, P, c->part, none, 0);
     else {
-        LAUNCH((k_sum_kick_ke<2>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, dt / 2, P, c->part);
-        LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8, (int)c->pre_open);
+#ifdef PFMDS_COOP
+        unsigned int* tk = c->ticket;    // the kernel's last block runs the chain update itself
+#else
+        unsigned int* tk = none;         // serial host replay: no block can know it is the last
+#endif
+        LAUNCH((k_sum_kick_ke<2>), RED_BLOCKS, IT, c->st, c->N, c->vel, c->frc, c->gmask, F, (int)c->zero_all, ball, bxyz, bz, dt / 2, P, c->part, tk, (int)c->pre_open);
+        if (!tk) { LAUNCH((k_nhc_close), 1, 1024, c->st, RED_BLOCKS, c->part, P, dt / 2, dt / 4, dt / 8, (int)c->pre_open); c->launches += 1; }
         c->nhc_opened = c->pre_open;
-        c->launches += 1;
     }
     c->launches += 1;
     c->fbuf_active = false;

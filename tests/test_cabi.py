@@ -52,3 +52,19 @@ def test_product_does_not_touch_the_oracle():
                 if pat.search(open(os.path.join(d, f), errors="ignore").read()):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_kernels_launched_with_1024_threads_fit_the_register_file(cuda_lib):
+    """A block of 1024 threads can use at most 64 registers per thread (65 536 per SM): a kernel that grows past that fails at launch
+    ("too many resources requested"), which only a GPU run would show.  Checked from the cubin's resource usage."""
+    out = subprocess.run(["cuobjdump", "-res-usage", cuda_lib], stdout=subprocess.PIPE, text=True).stdout
+    big = ("k_nhc_close", "k_nhciPKd", "k_reduce_ke_partials", "k_scan_block", "k_scan_sums", "k_sl_scan_block", "k_sum_partials", "k_sum_to", "k_sums_final")
+    seen = 0
+    lines = out.splitlines()
+    for k, l in enumerate(lines):
+        if "Function" in l and any(b in l for b in big):
+            m = re.search(r"REG:(\d+)", lines[k + 1])
+            assert m, lines[k + 1]
+            assert int(m.group(1)) <= 64, (l, lines[k + 1])
+            seen += 1
+    assert seen >= 8
