@@ -19,7 +19,7 @@
 // every kernel launch of the library goes through this macro (the host replay of the test suite substitutes a serial loop)
 #define LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
 #else
-#include "host_emu.hpp"  // test support: the kernels of this directory compiled for the host (tests/*_host.cpp), never part of the product
+#include "host_emu.hpp"  // tests/emu/host_emu.hpp (the test builds add -I tests/emu): these sources compiled for the host by the test suite; the product build is nvcc only
 #endif
 
 #if defined(__CUDACC__) || defined(PFMDS_EMU_WARP)

@@ -1,5 +1,5 @@
 """TEST SUPPORT ONLY.  Builds the HOST REPLAY of the device library: the very .cu sources of pfmds_b200/csrc compiled by g++
-(-x c++ -DPFMDS_EMU_LIB -DSMALL_N=0) with pfmds_b200/csrc/host_emu.hpp standing in for the CUDA language extensions and runtime,
+(-x c++ -DPFMDS_EMU_LIB -DSMALL_N=0) with tests/emu/host_emu.hpp standing in for the CUDA language extensions and runtime,
 plus the run_md_simulation / run_gr_moire_fitting hosts linked against it.  Kernels run as serial loops over (block, thread).
 This exists so that the C-ABI orchestration (pfmds_advance's step sequence, the fused NVT path, deposition, checkpoints ...) and
 the kernels' arithmetic can be checked against the oracle in the CPU test suite; it is never built, loaded or shipped by the
@@ -30,7 +30,7 @@ class Build:
     def __init__(self, warp=False):
         self.warp = warp
         self.out = os.path.join(HERE, "_build" + ("_warp" if warp else "") + ("_san" if SAN else ""))
-        self.flags = ["-x", "c++", "-std=c++17", "-O1" if SAN else "-O2", "-ffp-contract=off", "-DPFMDS_EMU_LIB", "-fPIC"] + \
+        self.flags = ["-x", "c++", "-std=c++17", "-O1" if SAN else "-O2", "-ffp-contract=off", "-DPFMDS_EMU_LIB", "-fPIC", "-I", HERE] + \
                      (["-DPFMDS_EMU_WARP"] if warp else ["-DSMALL_N=0"]) + SANFLAGS
         self.lib = os.path.join(self.out, "libpfmds_b200_emu.so")
         self.exe = os.path.join(self.out, "run_md_simulation_emu")
@@ -38,7 +38,8 @@ class Build:
 
     def build(self):
         os.makedirs(self.out, exist_ok=True)
-        hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".hpp"))] + [os.path.join(ROOT, "include", "pfmds_b200.h")]
+        hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".hpp"))] + [os.path.join(ROOT, "include", "pfmds_b200.h")] + \
+               [os.path.join(HERE, h) for h in ("host_emu.hpp", "nccl_emu.hpp")]
         jobs, objs = [], []
         for s in SOURCES + (["slab.cu"] if self.warp else []):   # the slab decomposition needs the lock-step flavour (scans, spin waits)
             obj = os.path.join(self.out, s[:-3] + ".o")
@@ -49,7 +50,7 @@ class Build:
         if not self.warp:
             objs.append(stub)
         if not self.warp and _newer(stub, [os.path.join(HERE, "slab_stub.cpp")] + hdrs):
-            jobs.append([CXX, "-std=c++17", "-O2", "-fPIC"] + SANFLAGS + ["-c", os.path.join(HERE, "slab_stub.cpp"), "-o", stub])
+            jobs.append([CXX, "-std=c++17", "-O2", "-fPIC", "-I", HERE] + SANFLAGS + ["-c", os.path.join(HERE, "slab_stub.cpp"), "-o", stub])
         with ThreadPoolExecutor(4) as ex:
             list(ex.map(_run, jobs))
         if jobs or _newer(self.lib, objs):

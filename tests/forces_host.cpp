@@ -1,5 +1,5 @@
 // Host build of pfmds_b200/csrc/forces.cu for tests/test_kernels_host.py: the force / energy kernels (thread-per-atom variants) run
-// as plain functions, one call per (block, thread) (pfmds_b200/csrc/host_emu.hpp), on the device's data layout — double4 records,
+// as plain functions, one call per (block, thread) (tests/emu/host_emu.hpp), on the device's data layout — double4 records,
 // ELL lists with slot indices — with the launch sequences of forces_interaction / energy_interaction (forces.cu, bottom).
 // This checks kernel arithmetic and indexing against the CPU oracle without a GPU; it is not a CPU path of the product.
 #include <algorithm>

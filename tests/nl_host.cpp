@@ -1,5 +1,5 @@
 // Host build of pfmds_b200/csrc/nl.cu for tests/test_kernels_host.py: binning, cell sort, re-sort and the thread-per-atom list
-// build run as plain functions (pfmds_b200/csrc/host_emu.hpp) in the order of nl_bin_atoms / nl_build; the two device scans are
+// build run as plain functions (tests/emu/host_emu.hpp) in the order of nl_bin_atoms / nl_build; the two device scans are
 // replaced by a plain prefix sum (they exchange data between lanes).  Not a CPU path of the product.
 #include <cstddef>
 #include <vector>

@@ -1,5 +1,5 @@
 """The GPU parity tests re-run on the CPU against the HOST REPLAY of the device library (tests/emu/build_emu.py: the same .cu
-sources compiled by g++ with pfmds_b200/csrc/host_emu.hpp, kernels as serial loops over (block, thread)).  What this checks
+sources compiled by g++ with tests/emu/host_emu.hpp, kernels as serial loops over (block, thread)).  What this checks
 without a GPU: the C-ABI orchestration of libpfmds_b200 (step sequence of pfmds_advance, fused NVT path, deposition, rebosc,
 checkpoint / restore, error reporting, the hosts) and the arithmetic and indexing of every thread-per-atom kernel, against the
 oracle and the golden fixtures, with the GPU tests' own assertions; in the lock-step flavour (fibers, see below) also the

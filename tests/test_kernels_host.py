@@ -1,4 +1,4 @@
-"""The device kernels of pfmds_b200/csrc/forces.cu compiled for the host and run thread by thread (pfmds_b200/csrc/host_emu.hpp,
+"""The device kernels of pfmds_b200/csrc/forces.cu compiled for the host and run thread by thread (tests/emu/host_emu.hpp,
 tests/forces_host.cpp) on the device's data layout, against the CPU oracle: forces and energies of every interaction kind at
 step 0.  Covers the kernels' arithmetic and indexing (pipelined rjl loops, class-free row order, converse lists, tb per-slot
 parts, graphene normals and the normal-derivative term) without a GPU; the GPU parity tests (-m gpu) remain the gate for the
@@ -21,7 +21,7 @@ DP, IP = C.POINTER(C.c_double), C.POINTER(C.c_int)
 def kernels(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("fh") / "libforces_host.so")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "forces_host.cpp")], check=True)
+    subprocess.run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "emu"), "-o", out, os.path.join(ROOT, "tests", "forces_host.cpp")], check=True)
     return C.CDLL(out)
 
 
@@ -198,7 +198,7 @@ def test_emulated_rjl_generations(oracle_lib, kernels):
 def nl_kernels(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("nh") / "libnl_host.so")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "nl_host.cpp")], check=True)
+    subprocess.run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "emu"), "-o", out, os.path.join(ROOT, "tests", "nl_host.cpp")], check=True)
     return C.CDLL(out)
 
 

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def lib(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("mx") / "libmx.so")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "mathx_host.cpp")], check=True)
+    subprocess.run([cxx, "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "emu"), "-o", out, os.path.join(ROOT, "tests", "mathx_host.cpp")], check=True)
     L = C.CDLL(out)
     L.mx_exp.restype = C.c_double
     L.mx_exp.argtypes = [C.c_double]

@@ -22,7 +22,7 @@ FD_NOISE = 2e-7
 def host_kernels(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("reb") / "librebhost.so")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "rebosc_host.cpp")], check=True)
+    subprocess.run([cxx, "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "emu"), "-o", out, os.path.join(ROOT, "tests", "rebosc_host.cpp")], check=True)
     L = C.CDLL(out)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     L.reb_host_run.argtypes = [C.c_int, dp, dp, C.c_size_t, ip, ip, dp, dp, dp, ip]

@@ -1,5 +1,5 @@
 """The slab decomposition (pfmds_b200/csrc/slab.cu) WITHOUT GPUs: the lock-step host replay of the library with the ranks as
-threads of this process — NCCL replaced by an in-process stand-in (pfmds_b200/csrc/nccl_emu.hpp), CUDA IPC handles by plain
+threads of this process — NCCL replaced by an in-process stand-in (tests/emu/nccl_emu.hpp), CUDA IPC handles by plain
 pointers, the spin-wait / signal kernels of the peer-memory halo running against each other for real.  Same comparison as
 tests/test_slab_gpu.py: the decomposed run against the whole system in one context — atom ownership, positions, velocities,
 forces, energies, thermostat and diagnostics after steps that include list rebuilds, migration and ghost re-selection; with 2
