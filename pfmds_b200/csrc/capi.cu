@@ -332,7 +332,7 @@ void finalize(pfmds_ctx* c) {
     for (auto& it : c->inter) rjl_prepare(c, it);
     {   // per-interaction force buffers of small systems (compute_forces); lj gets two: its two lists run as separate branches
         size_t nbuf = 0;
-        for (auto& it : c->inter) nbuf += it.kind == K_LJ ? 2 : 1;
+        for (auto& it : c->inter) nbuf += (it.kind == K_LJ || it.kind == K_LJC || it.kind == K_MORSEC) ? 2 : 1;
         if (c->N < c->small_n && c->inter.size() >= 2 && nbuf <= 12 && env_int("PFMDS_SMALL_FORK", 1) != 0) {
             for (size_t k = 0; k < nbuf; ++k) {
                 double4* b = nullptr;
@@ -348,6 +348,7 @@ void finalize(pfmds_ctx* c) {
                 CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 c->aux_ev.push_back(e);
             }
+            CK(cudaEventCreateWithFlags(&c->aux_ev_mid, cudaEventDisableTiming));
             CK(cudaMalloc(&c->ticket, sizeof(unsigned int)));
             CK(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
             c->fbuf_on = true;
@@ -462,7 +463,8 @@ void compute_forces(pfmds_ctx* c, bool with_energy, bool defer_sum = false) {
         if (fork) CK(cudaEventRecord(c->aux_ev[0], c->st));
         size_t b = 0;   // next buffer, in summation order
         for (size_t q = 0; q < order.size(); ++q) {
-            const bool two = c->inter[order[q]].kind == K_LJ;   // second list of lj: its own branch and buffer
+            const int kq = c->inter[order[q]].kind;
+            const bool two = kq == K_LJ || kq == K_LJC || kq == K_MORSEC;   // second list of lj, metal side of ljc / morsec: own branch and buffer
             cudaStream_t s1 = fork ? c->aux_st[b] : nullptr, s2 = (fork && two) ? c->aux_st[b + 1] : nullptr;
             if (fork) { CK(cudaStreamWaitEvent(s1, c->aux_ev[0], 0)); if (two) CK(cudaStreamWaitEvent(s2, c->aux_ev[0], 0)); }
             c->fst = s1; c->fout = c->fbuf[b];
@@ -1669,6 +1671,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     for (auto b : c->fbuf) cudaFree(b);
     cudaFree(c->ticket);
+    if (c->aux_ev_mid) cudaEventDestroy(c->aux_ev_mid);
     for (auto s : c->aux_st) cudaStreamDestroy(s);
     for (auto e : c->aux_ev) cudaEventDestroy(e);
     void* ptrs[] = {c->pos, c->pos2, c->vel, c->vel2, c->frc, c->gmask, c->gmask2, c->orig, c->orig2, c->cell_cnt, c->cell_start, c->cell_atoms,

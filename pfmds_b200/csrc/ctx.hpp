@@ -111,6 +111,7 @@ struct pfmds_ctx {
     std::vector<double4*> fbuf;
     std::vector<cudaStream_t> aux_st;
     std::vector<cudaEvent_t> aux_ev;     // [0] fork, [1 + k] join of branch k
+    cudaEvent_t aux_ev_mid = nullptr;    // inside an interaction: normals done -> the metal-side branch of ljc / morsec may start
     cudaStream_t fst = nullptr, fst2 = nullptr;   // (fst2 / fout2: the converse-list launch of lj)
     double4 *fout = nullptr, *fout2 = nullptr;
     unsigned int* ticket = nullptr;      // block counter of k_sum_kick_ke (its last block closes the thermostat step)

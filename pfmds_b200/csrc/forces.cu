@@ -1202,16 +1202,20 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     case K_LJC:
     case K_MORSEC: {
         if (c->fbuf_on) normals_interaction(c, k, fs);   // small systems: the normals open this interaction's branch (otherwise update_lists ran them)
+        // the metal side needs the normals only: small systems give it a branch and a buffer of its own, next to graphene's direct + indirect chain
+        cudaStream_t fs2 = c->fout2 ? (c->fst2 ? c->fst2 : c->st) : fs;
+        double4* fo2 = c->fout2 ? c->fout2 : fo;
+        if (c->fout2 && c->fst2) { CK(cudaEventRecord(c->aux_ev_mid, fs)); CK(cudaStreamWaitEvent(fs2, c->aux_ev_mid, 0)); }
         CosP P = cosp_of(it);
         bool simp = it.kind == K_LJC ? it.ljc.simplified : it.mor.simplified;
         if (it.kind == K_LJC) {
             { KTimer kt(c, KS_COS_GRAPHENE); if (small) LAUNCH((k_cos_direct<false, true, true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, true, true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
             if (!simp) { KTimer kt(c, KS_COS_INDIRECT); LAUNCH((k_cos_indirect), nb, FT, fs, N, c->pos, fo, it.nl[2].view(st), P.pe * P.delt, c->box, it.gnorm, it.tvec); }
-            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<false, false, true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, false, true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<false, false, true, false, SMALL_SPLIT>), nbs, FT, fs2, N, c->pos, fo2, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<false, false, true, false, 1>), nb, FT, fs2, N, c->pos, fo2, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         } else {
             { KTimer kt(c, KS_COS_GRAPHENE); if (small) LAUNCH((k_cos_direct<true, true, true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, true, true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
             if (!simp) { KTimer kt(c, KS_COS_INDIRECT); LAUNCH((k_cos_indirect), nb, FT, fs, N, c->pos, fo, it.nl[2].view(st), 2. * P.pe * P.delt, c->box, it.gnorm, it.tvec); }
-            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<true, false, true, false, SMALL_SPLIT>), nbs, FT, fs, N, c->pos, fo, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, false, true, false, 1>), nb, FT, fs, N, c->pos, fo, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
+            { KTimer kt(c, KS_COS_METAL); if (small) LAUNCH((k_cos_direct<true, false, true, false, SMALL_SPLIT>), nbs, FT, fs2, N, c->pos, fo2, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); else LAUNCH((k_cos_direct<true, false, true, false, 1>), nb, FT, fs2, N, c->pos, fo2, it.nl[1].view(st), P, c->box, it.gnorm, it.tvec, nullptr); }
         }
         c->launches += simp ? 2 : 3;
         break;

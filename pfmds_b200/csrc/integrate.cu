@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(1024) k_nhc(int nparts, const double* __restri
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) ke += part[i];
     ke = block_sum(ke);
     if (threadIdx.x != 0) return;
-    nhc_chain(state, M, L, temperature, ke, ts2, ts3, ts4);
+    nhc_step(state, M, L, temperature, ke, ts2, ts3, ts4, 0);
 }
 // scale_velocities, md_general.f90:96-112
 __global__ void k_scale(int N, double4* __restrict__ vel, const uint32_t* __restrict__ gmask, uint32_t bit, const double* __restrict__ s_ptr) {
@@ -278,8 +278,7 @@ __global__ void k_nhc_open(NhcPack P, double ts2, double ts3, double ts4) {
     if (k >= P.n) return;
     double* st = P.state[k];
     int M = P.M[k];
-    double s = nhc_chain(st, M, P.L[k], P.T[k], st[3 * M + 1], ts2, ts3, ts4);
-    st[3 * M + 2] *= s;
+    nhc_step(st, M, P.L[k], P.T[k], 0., ts2, ts3, ts4, 1);
 }
 __global__ void __launch_bounds__(IT) k_kick_drift_nvt(int N, double4* __restrict__ pos, double4* __restrict__ vel, const double4* __restrict__ frc,
                                                        const uint32_t* __restrict__ gmask, const int* __restrict__ orig, uint32_t bxyz, uint32_t bz,
@@ -369,12 +368,7 @@ __global__ void __launch_bounds__(1024) k_nhc_close(int nparts, const double* __
         if (threadIdx.x == 0) {
             double* st = P.state[k];
             int M = P.M[k];
-            double s = nhc_chain(st, M, P.L[k], P.T[k], ke, ts2, ts3, ts4);
-            st[3 * M + 2] = s;
-            if (also_open) {
-                double so = nhc_chain(st, M, P.L[k], P.T[k], st[3 * M + 1], ts2, ts3, ts4);
-                st[3 * M + 2] *= so;
-            }
+            nhc_step(st, M, P.L[k], P.T[k], ke, ts2, ts3, ts4, also_open ? 3 : 2);
         }
         __syncthreads();
     }
@@ -448,8 +442,7 @@ __global__ void __launch_bounds__(IT) k_sum_kick_ke(int N, double4* __restrict__
                     if (threadIdx.x == 0) {
                         double* st = P.state[k];
                         const int M = P.M[k];
-                        st[3 * M + 2] = nhc_chain(st, M, P.L[k], P.T[k], sk, ts2, ts2 / 2, ts2 / 4);
-                        if (also_open) st[3 * M + 2] *= nhc_chain(st, M, P.L[k], P.T[k], st[3 * M + 1], ts2, ts2 / 2, ts2 / 4);
+                        nhc_step(st, M, P.L[k], P.T[k], sk, ts2, ts2 / 2, ts2 / 4, also_open ? 3 : 2);
                     }
                     __syncthreads();
                 }

@@ -589,7 +589,7 @@ __global__ void k_sl_ke_close(int nparts, const double* __restrict__ part, NhcPa
             for (int r = 0; r < nranks; ++r) ke += reinterpret_cast<const volatile double*>(box[rank])[((size_t)par * nranks + r) * KE_W + k];
             double* st = P.state[k];
             const int M = P.M[k];
-            st[3 * M + 2] = nhc_chain(st, M, P.L[k], P.T[k], ke, ts2, ts3, ts4);
+            nhc_step(st, M, P.L[k], P.T[k], ke, ts2, ts3, ts4, 2);
         }
     }
 }
