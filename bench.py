@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 _RM = json.load(open(os.path.join(ROOT, "pfmds_b200", "csrc", "roofline.json")))["kernels"]
 FLOPS_PER_PAIR = {k: v["flop_per_pair"] for k, v in _RM.items()}
 _RMX = json.load(open(os.path.join(ROOT, "pfmds_b200", "csrc", "roofline.json"))).get("executed_fp64_per_pair_ncu", {})
+_RML = json.load(open(os.path.join(ROOT, "pfmds_b200", "csrc", "roofline.json"))).get("l1_gather_model")
 BYTES_PER_ATOM = {k: (lambda n, c=v["bytes_per_atom_const"]: 4 * n + c) for k, v in _RM.items() if v.get("bytes_per_atom_const") is not None}
 
 
@@ -115,9 +116,9 @@ class ClockSampler:
 
 def _ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
-    (profiles/r1_traffic.json, same workload); None when no capture exists for it."""
+    (profiles/r2_traffic.json, same workload); None when no capture exists for it."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(kernel)
     except Exception:
         return None
 
@@ -610,7 +611,8 @@ def main():
             "executed_fp64_per_pair": _RMX.get(name),
             "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src, "copy_gbs_live": copy_gbs},
             "traffic": _ncu_traffic(name),
-            "traffic_source": "profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture r1e_top (first-generation kernel; the second generation reads the same lists and records)",
+            "traffic_source": "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of the default (second-generation) kernels, profiles/r2a_rjl_raw_summary.txt",
+            "l1_gather": _RML if name in ("rjl_force", "rjl_density") else None,
         }
         if n_atoms < 200000:
             roofline["note"] = "system of %d atoms: every kernel is launch/latency bound (grid smaller than one wave), the FP64 fraction is not the figure of merit" % n_atoms

@@ -196,6 +196,8 @@ int pfmds_selftest_math(int device, double err[4]);
  * half_switch): [0] exp relative on [-40, 40], [1] switch absolute, [2] rsqrt relative, [3] exp relative on [-600, 600]. */
 int pfmds_selftest_math2(int device, double err[4]);
 
+/* Contexts of this process alive on `device` (a context that shares its GPU leaves the parallel branches of a step to the others). */
+int pfmds_live_contexts(int device);
 /* Number of kernel launches issued so far by this context and device-time of the last advance (ms). */
 int pfmds_launch_count(pfmds_ctx* ctx, long long* launches);
 

@@ -93,7 +93,7 @@ struct pfmds_ctx {
     int* newslot = nullptr;  // old slot -> new slot of the last cell re-sort
     std::vector<long long> group_count;  // slab mode: global size of every group
     // CUDA graphs of the steady-state step (small systems are launch-latency bound), keyed by what is baked in
-    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid, opened, pre_open; cudaGraphExec_t exec; long long launches; };
+    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid, opened, pre_open, alone; cudaGraphExec_t exec; long long launches; };
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
     int rjl_minb = 7;               // blocks/SM the third-generation rjl force kernels are compiled for: 7 (72 registers) or 8 (64; PFMDS_RJL_MINB=8)
@@ -120,6 +120,7 @@ struct pfmds_ctx {
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
     bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)
     bool finalized = false;
+    bool counted = false;       // this context is in the process-wide count of live contexts of its device (capi.cu)
     // fused NVT path (integrate.cu): usable when the thermostat groups are pairwise disjoint
     bool nhc_fusable = false;
     bool nhc_ke_valid = false;  // state[3M+1] holds the current kinetic energy of each thermostat group

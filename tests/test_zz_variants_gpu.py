@@ -52,3 +52,30 @@ def test_size_switches_are_read_from_the_environment():
     assert rel_err(fb, fa) < 1e-12 and not np.array_equal(fa, fb)
     assert a.pair_count(0, 0) == b.pair_count(0, 0)
 
+
+def test_small_system_branches_give_the_sequential_results():
+    """Small systems run their interactions as parallel branches of the step's CUDA graph (own stream and force buffer per
+    interaction, capi.cu compute_forces) when the context has its GPU to itself.  Against PFMDS_SMALL_FORK=0 (one stream, one force
+    array): the A/B gas has one addend per atom and list, so the bits are the same; graphene on Cu adds the ljc terms in another
+    grouping (rounding only)."""
+    for case, integ, dt, exact in ((inputs.ab_gas(n_side=8, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, period=5), "nvt", 0.5, True),
+                                   (inputs.graphene_on_cu_small(interface="ljc", period=5), "nvt", 1.0, False),
+                                   (inputs.graphene_on_cu_small(interface="morsec", period=5), "nvms", 1.0, False)):
+        res = []
+        for env in ({}, {"PFMDS_SMALL_FORK": "0"}):
+            import gc
+            gc.collect()                           # engines of earlier tests still waiting for the collector would count as neighbours
+            e = gpu(case, env)                     # alone on the device: the previous engine is closed
+            assert e._lib.pfmds_live_contexts(0) == 1
+            e.advance(integ, dt, 0, 1)
+            e.advance(integ, dt, 1, 23)            # steady-state steps replay the graph with the forked branches
+            res.append((e.download(), e.energies(), e.launch_count()))
+            e.close()
+        (pa, va, fa), ea, _ = res[0]
+        (pb, vb, fb), eb, _ = res[1]
+        assert np.abs(fa).max() > 1e-3
+        if exact:
+            assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(fa, fb)
+        else:
+            assert np.abs(pa - pb).max() < 1e-12 and rel_err(vb, va) < 1e-11 and rel_err(fb, fa) < 1e-11
+        assert np.allclose(ea[0], eb[0], rtol=1e-11, atol=0)
