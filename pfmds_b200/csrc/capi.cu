@@ -69,7 +69,6 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     // 0.343 against 0.277 ms (density) and 0.362 against 0.360 ms (force) per launch at 10^6 atoms
     c->rjl_gen = env_int("PFMDS_RJL_GEN", 2);
     if (c->rjl_gen < 1 || c->rjl_gen > 3) c->rjl_gen = 2;
-    c->rjl_minb = env_int("PFMDS_RJL_MINB", 7) == 8 ? 8 : 7;
 #ifdef PFMDS_COOP
     c->small_n = env_int("PFMDS_SMALL_N", 100000);
     c->nl_warp_n = env_int("PFMDS_NL_WARP_N", 200000);
@@ -429,11 +428,7 @@ void update_lists(pfmds_ctx* c, int step) {
             all &= rb;
         }
     }
-    if (c->slab && !any) {  // ghost positions follow their owners every step
-        // lean halo: when the first kernel that reads positions is a large-system rjl density pass, it waits for the ghosts itself
-        slab_set_consumer_waits(c, !c->inter.empty() && c->inter[0].kind == K_RJL && c->N >= c->small_n && c->rjl_gen != 1);
-        slab_exchange(c, 0);
-    }
+    if (c->slab && !any) slab_exchange(c, 0);  // ghost positions follow their owners every step
     if (any) {
         PhaseTimer t(c, 2);
         if (c->slab) slab_redistribute(c);   // finalize_slab guarantees any == all

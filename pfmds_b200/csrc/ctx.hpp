@@ -96,7 +96,6 @@ struct pfmds_ctx {
     struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid, opened, pre_open, alone; cudaGraphExec_t exec; long long launches; };
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
-    int rjl_minb = 7;               // blocks/SM the third-generation rjl force kernels are compiled for: 7 (72 registers) or 8 (64; PFMDS_RJL_MINB=8)
     int rjl_gen = 2;                // rjl pair routines: 2 = analytic short forms (default), 3 = node-table exponentials (measured slower: L1-bound), 1 = first generation (PFMDS_RJL_GEN)
     bool nl_mask = true;            // thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (measured 8 % faster, BENCH_r01); PFMDS_NL_MASK=0: k_build
     bool lj1g_pipe = true;          // pipelined lj1g force kernel for systems of small_n atoms and more (measured 0.174 -> 0.102 ms, BENCH_r01); PFMDS_LJ1G_PIPE=0: k_lj1g
@@ -178,8 +177,6 @@ bool slab_fused(pfmds_ctx* c);
 // stage 0: kick+drift pushes positions; 1: rjl density waits for positions, pushes 1/Eb; 2: rjl force waits for 1/Eb
 SlabDev slab_dev(pfmds_ctx* c, int stage);
 bool slab_pos_pushed_by_kick(pfmds_ctx* c, bool rebuild_step);
-SlabDev slab_wait_dev(pfmds_ctx* c, int field);          // lean halo: the consumer kernel waits for its ghosts itself
-void slab_set_consumer_waits(pfmds_ctx* c, bool on);
 void slab_allreduce_sum(pfmds_ctx* c, double* d, int n);
 bool slab_ke_close(pfmds_ctx* c, const NhcPack& P, int nparts, const double* part, double ts2, double ts3, double ts4);  // thermostat KE over the ranks by peer-memory mailboxes + chain update
 void slab_allreduce_max(pfmds_ctx* c, double* d, int n);

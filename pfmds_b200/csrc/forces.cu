@@ -10,7 +10,6 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
-#include <type_traits>
 #include <vector>
 
 #if defined(__CUDACC__) || defined(PFMDS_EMU_LIB)
@@ -615,8 +614,8 @@ __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4&
 }
 // RJL_MINB = blocks per SM the register allocation is held to.  7 (72 registers) is the measured optimum; 5 (94 registers, no
 // constant reloads in the loop, 20 instead of 28 resident warps) measured slower on a B200 (0.425 against 0.358 ms, BENCH_r01).
-template <class CT, int MB = RJL_MINB>  // CT = RjlC (first generation), RjlF (second) or RjlG (third: also instantiated for 8 blocks/SM = 64 registers, PFMDS_RJL_MINB=8)
-__global__ void __launch_bounds__(FT, MB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
+template <class CT>  // CT = RjlC (first generation), RjlF (second) or RjlG (third)
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                       WrapC W, SlabDev S, int overwrite) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);  // slab mode: the neighbours' 1/Eb have landed in my ghost slots
@@ -667,8 +666,8 @@ __global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __
 // (Tried and dropped, measured on a B200 at 10^6 atoms: the closing half kick + thermostat KE partials in this kernel's epilogue,
 //  with and without the last block of the grid running the chain update: 0.375 / 0.398 ms against 0.359 ms + 0.034 ms for the
 //  separate k_kick_ke -- the extra 64 B/atom of velocity traffic lands in a kernel whose L1 data pipe is already the limit.)
-template <class CT, int MB = RJL_MINB>  // CT = RjlF (second generation) or RjlG (third)
-__global__ void __launch_bounds__(FT, MB) k_rjl_force_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
+template <class CT>  // CT = RjlF (second generation) or RjlG (third)
+__global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force_e(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                         WrapC W, SlabDev S, int overwrite, double erep, double xi, double* __restrict__ part) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     slab_wait(S);
@@ -1132,8 +1131,6 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
         // Energies of the step: the first generation evaluates them in its density pass (a second exponential per pair), the
         // second takes them from the force pass, which has that exponential in hand (k_rjl_force_e).
         const bool e_in_force = with_energy && gen2;
-        // slab mode, lean halo: the density pass waits for the ghost positions in its prologue, the force pass for the ghost 1/Eb
-        const SlabDev SDpos = (c->slab && !small && !fused) ? slab_wait_dev(c, 0) : SlabDev{};
         auto run = [&](auto CD, auto CF) {
             using TD = decltype(CD);
             using TF = decltype(CF);
@@ -1141,22 +1138,17 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
                 KTimer kt(c, KS_RJL_DENSITY);
                 if (with_energy && !e_in_force) {
                     if (small) LAUNCH((k_rjl_density_split<true, SMALL_SPLIT, TD>), nbs, FT, fs, N, c->pos, lv, CD, c->box, W, epart);
-                    else LAUNCH((k_rjl_density<true, TD>), nb, FT, fs, N, c->pos, lv, CD, c->box, W, epart, fused ? slab_dev(c, 1) : SDpos);
+                    else LAUNCH((k_rjl_density<true, TD>), nb, FT, fs, N, c->pos, lv, CD, c->box, W, epart, fused ? slab_dev(c, 1) : SlabDev{});
                     e_parts = small ? nbs : nb;
                 } else
                 if (small) LAUNCH((k_rjl_density_split<false, SMALL_SPLIT, TD>), nbs, FT, fs, N, c->pos, lv, CD, c->box, W, (double*)nullptr);
-                else LAUNCH((k_rjl_density<false, TD>), nb, FT, fs, N, c->pos, lv, CD, c->box, W, (double*)nullptr, fused ? slab_dev(c, 1) : SDpos);
+                else LAUNCH((k_rjl_density<false, TD>), nb, FT, fs, N, c->pos, lv, CD, c->box, W, (double*)nullptr, fused ? slab_dev(c, 1) : SlabDev{});
             }
-            if (c->slab && !fused) { slab_set_consumer_waits(c, !small); slab_exchange(c, 1); }  // ghost 1/Eb from their owners
+            if (c->slab && !fused) slab_exchange(c, 1);  // ghost 1/Eb from their owners
             if (!e_in_force) {
                 KTimer kt(c, KS_RJL_FORCE);
                 if (small) LAUNCH((k_rjl_force_split<SMALL_SPLIT, TF>), nbs, FT, fs, N, c->pos, fo, lv, CF, c->box, W);
-                else {
-                    bool launched = false;
-                    if constexpr (std::is_same<TF, RjlG>::value)
-                        if (c->rjl_minb == 8) { LAUNCH((k_rjl_force<TF, 8>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, fused ? slab_dev(c, 2) : slab_wait_dev(c, 1), ow); launched = true; }
-                    if (!launched) LAUNCH((k_rjl_force<TF>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, fused ? slab_dev(c, 2) : slab_wait_dev(c, 1), ow);
-                }
+                else LAUNCH((k_rjl_force<TF>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, fused ? slab_dev(c, 2) : SlabDev{}, ow);
             }
         };
         const double erep = it.rjl.r0 / (2. * it.rjl.p);   // A0 / a1, a1 = 2 A0 p / r0
@@ -1164,11 +1156,8 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
             using TF = decltype(CF);
             KTimer kt(c, KS_RJL_FORCE);
             if (small) { LAUNCH((k_rjl_force_split_e<SMALL_SPLIT, TF>), nbs, FT, fs, N, c->pos, fo, lv, CF, c->box, W, erep, it.rjl.xi, epart); e_parts = nbs; return; }
-            const SlabDev SD = fused ? slab_dev(c, 2) : slab_wait_dev(c, 1);
-            bool launched = false;
-            if constexpr (std::is_same<TF, RjlG>::value)
-                if (c->rjl_minb == 8) { LAUNCH((k_rjl_force_e<TF, 8>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart); launched = true; }
-            if (!launched) LAUNCH((k_rjl_force_e<TF>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart);
+            const SlabDev SD = fused ? slab_dev(c, 2) : SlabDev{};
+            LAUNCH((k_rjl_force_e<TF>), nb, FT, fs, N, c->pos, fo, lv, CF, c->box, W, SD, ow, erep, it.rjl.xi, epart);
             e_parts = nb;
         };
         if (gen3) {

@@ -95,9 +95,6 @@ struct Slab {
     std::vector<double*> peer_box;              // every rank's mailbox (IPC mapped; [rank] = my own)
     double** peer_box_d = nullptr;              // the same pointers on the device
     int ke_seq = 0;
-    bool lean = true;               // one kernel per exchange, consumers wait in their prologue (PFMDS_SLAB_LEAN=0: four small kernels)
-    int pend[2]{0, 0};              // sequence number the next consumer of ghost positions / ghost 1/Eb still has to wait for (0: none)
-    bool consumer_waits = false;    // set per step by the caller: the first kernel that reads ghost positions has a slab_wait prologue
     unsigned long long timeout_ns = 120000000000ull;  // spin-wait limit of the flag waits (PFMDS_SLAB_TIMEOUT_S)
     std::vector<void*> ipc_opened;
 };
@@ -272,26 +269,6 @@ __global__ void k_sl_push(int nl, const int* __restrict__ idx_l, const int* __re
     double* q = reinterpret_cast<double*>(&peer[ps[k]]);
     if (FIELD == 0) { q[0] = p.x; q[1] = p.y; q[2] = p.z; }
     else q[3] = p.w;
-}
-// Lean halo (default): ONE kernel per exchange.  Prologue: wait until the neighbours are done with what is about to be overwritten
-// (S.wait_*, positions only); body: the stores into the neighbours' ghost slots; epilogue: the last block of the grid publishes the
-// sequence number in both neighbours' flag words (slab_signal).  The wait for MY ghosts is not a kernel either: the kernel that
-// consumes them (rjl density / force pass) waits in its own prologue (slab_wait_dev), so an exchange costs one launch instead of four.
-template <int FIELD>
-__global__ void k_sl_push_sync(int nl, const int* __restrict__ idx_l, const int* __restrict__ ps_l, double4* peer_l, int nr, const int* __restrict__ idx_r,
-                               const int* __restrict__ ps_r, double4* peer_r, const double4* __restrict__ pos, SlabDev S) {
-    slab_wait(S);
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int* idx = nullptr; const int* ps = nullptr; double4* peer = nullptr;
-    if (k < nl) { idx = idx_l; ps = ps_l; peer = peer_l; }
-    else if (k < nl + nr) { k -= nl; idx = idx_r; ps = ps_r; peer = peer_r; }
-    if (idx) {
-        const double4 p = pos[idx[k]];
-        double* q = reinterpret_cast<double*>(&peer[ps[k]]);
-        if (FIELD == 0) { q[0] = p.x; q[1] = p.y; q[2] = p.z; }
-        else q[3] = p.w;
-    }
-    slab_signal(S, idx != nullptr);
 }
 // publish `seq` in both neighbours' flag words (runs after the push kernel on the same stream: its stores are complete)
 __global__ void k_sl_signal(int* to_left, int* to_right, int seq) {
@@ -481,7 +458,6 @@ void slab_init(pfmds_ctx* c, int rank, int nranks, const char* id128, long long 
     CK(cudaMalloc(&s->scan_tmp, sizeof(int) * (S / 2048 + 2)));
     CK(cudaMalloc(&c->newslot, sizeof(int) * S));
     if (const char* to = std::getenv("PFMDS_SLAB_TIMEOUT_S")) { double v = std::atof(to); if (v >= 1.) s->timeout_ns = (unsigned long long)(v * 1e9); }
-    if (const char* ln = std::getenv("PFMDS_SLAB_LEAN")) s->lean = ln[0] != '0';
     const char* env = std::getenv("PFMDS_SLAB_P2P");
     s->p2p = !(env && env[0] == '0') && slab_setup_p2p(c, s);
 }
@@ -535,17 +511,6 @@ SlabDev slab_dev(pfmds_ctx* c, int stage) {
     }
     return S;
 }
-// lean halo: what a consuming kernel waits for in its prologue (field 0: ghost positions, 1: ghost 1/Eb); zeros when nothing is pending
-SlabDev slab_wait_dev(pfmds_ctx* c, int field) {
-    Slab* s = c->slab;
-    SlabDev S{};
-    if (!s || !s->p2p || s->pend[field] == 0) return S;
-    S.err = c->err; S.timeout_ns = s->timeout_ns;
-    S.wait_a = s->flags + 2 * field; S.wait_b = s->flags + 2 * field + 1; S.wait_seq = s->pend[field];
-    s->pend[field] = 0;
-    return S;
-}
-void slab_set_consumer_waits(pfmds_ctx* c, bool on) { if (c->slab) c->slab->consumer_waits = on && c->slab->p2p && c->slab->lean; }
 bool slab_pos_pushed_by_kick(pfmds_ctx* c, bool rebuild_step) { return slab_fused(c) && !rebuild_step; }
 int slab_rank(pfmds_ctx* c) { return c->slab->rank; }
 int slab_nranks(pfmds_ctx* c) { return c->slab->nranks; }
@@ -725,28 +690,6 @@ void slab_exchange(pfmds_ctx* c, int field) {
             }
             s->pos_pushed = false;
             s->wait_pos_seq = s->seq_pos;
-            CK(cudaGetLastError());
-            return;
-        }
-        if (s->lean) {
-            SlabDev S{};
-            S.err = c->err; S.timeout_ns = s->timeout_ns; S.counter = s->counter; S.push = 1;
-            const int nb = n > 0 ? (n + T - 1) / T : 1;
-            if (field == 0) {
-                S.wait_a = s->flags + 4; S.wait_b = s->flags + 5; S.wait_seq = s->seq_done;   // neighbours done with the old ghost positions
-                s->seq_pos += 1;
-                S.sig_l = s->peer_flags[0] + 1; S.sig_r = s->peer_flags[1] + 0; S.sig_seq = s->seq_pos;   // I am my left neighbour's right neighbour
-                LAUNCH((k_sl_push_sync<0>), nb, T, c->st, nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos, S);
-                if (s->consumer_waits) s->pend[0] = s->seq_pos;
-                else { LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 0, s->flags + 1, s->seq_pos, c->err, s->timeout_ns); c->launches += 1; }
-            } else {
-                s->seq_w += 1;
-                S.sig_l = s->peer_flags[0] + 3; S.sig_r = s->peer_flags[1] + 2; S.sig_seq = s->seq_w;
-                LAUNCH((k_sl_push_sync<1>), nb, T, c->st, nl, s->send_idx[0], s->pslot[0], pl, nr, s->send_idx[1], s->pslot[1], pr, c->pos, S);
-                if (s->consumer_waits) s->pend[1] = s->seq_w;
-                else { LAUNCH((k_sl_wait), 1, 1, c->st, s->flags + 2, s->flags + 3, s->seq_w, c->err, s->timeout_ns); c->launches += 1; }
-            }
-            c->launches += 1;
             CK(cudaGetLastError());
             return;
         }

@@ -26,6 +26,4 @@ int slab_rank(pfmds_ctx*) { return 0; }
 int slab_nranks(pfmds_ctx*) { return 1; }
 int slab_n_local(pfmds_ctx*) { return 0; }
 long long slab_n_global(pfmds_ctx*) { return 0; }
-SlabDev slab_wait_dev(pfmds_ctx*, int) { return SlabDev{}; }
-void slab_set_consumer_waits(pfmds_ctx*, bool) {}
 bool slab_ke_close(pfmds_ctx*, const NhcPack&, int, const double*, double, double, double) { return false; }
