@@ -522,15 +522,14 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
                     dx += dshift[w][r][0]; dy += dshift[w][r][1]; dz += dshift[w][r][2];
                 }
                 const double dr2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if (dr2 < rc2) {
-                    if (cnt < maxn) {
-                        if (!PART) nlist[(size_t)cnt * stride + i] = j;
-                        else if (dr2 < r1sq) nlist[(size_t)(c0++) * stride + i] = j;
-                        else if (dr2 < r2sq) alt[(size_t)(c1++) * stride + i] = j;
-                        else alt[(size_t)(maxn - 1 - (c2++)) * stride + i] = j;
-                    }
-                    ++cnt;
-                }
+                // one store on one path for the three classes (a branch per class left 9 of 32 lanes active here, ncu r2i)
+                const bool in = (dr2 < rc2) && (j != i);
+                const bool k0 = !PART || dr2 < r1sq, k1 = PART && !k0 && dr2 < r2sq;
+                int* const dst = k0 ? nlist : alt;
+                const int row = !PART ? cnt : (k0 ? c0 : (k1 ? c1 : maxn - 1 - c2));
+                if (in && cnt < maxn) dst[(size_t)row * stride + i] = j;
+                if (PART && in && cnt < maxn) { c0 += k0; c1 += k1; c2 += !k0 && !k1; }
+                cnt += in;
             }
             ns = 0;
         };
@@ -551,7 +550,6 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
             cb_wait(&bars[w][b], (b ? use1 : use0) & 1u);
             if (b) use1 += 1u; else use0 += 1u;
             const float4* cand = buf[w][b];
-            const int self = i - (R.start + po);          // this lane's own atom as a candidate of the piece (negative / >= n: not in it)
             const unsigned tag = ((unsigned)pr << CB_OFF_BITS) + (unsigned)po;
             const float ox = pif.x - R.sx, oy = pif.y - R.sy, oz = pif.z - R.sz;  // candidate + s - owner = candidate - (owner - s)
             if (R.count > (1 << CB_OFF_BITS)) ovf = owner;  // offsets would not fit the 16-bit entries: these atoms take the serial path
@@ -560,9 +558,11 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
                 const int m = n - g0 < 32 ? n - g0 : 32;
                 // a group adds at most 32 survivors per lane: make room first (phase 2 empties every list), so no list ever overflows
                 if (__ballot_sync(0xffffffffu, act && ns + m > lcap) != 0u) flush();
-                uint32_t mask = 0;
                 if (act) {
+                    // every candidate's tag is stored at the end of the list and the list grows only when the candidate passes: no mask,
+                    // no loop over set bits (the atom itself passes too and is dropped by phase 2)
                     const float4* cg = cand + g0;
+                    const unsigned short tg = (unsigned short)(tag + (unsigned)g0);
                     if (m == 32) {
 #pragma unroll
                         for (int t = 0; t < 32; ++t) {
@@ -570,7 +570,8 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
                             const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
                             bool keep = fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim;
                             if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
-                            if (keep) mask |= 1u << t;
+                            mine[ns] = (unsigned short)(tg + t);
+                            ns += keep;
                         }
                     } else {
                         for (int t = 0; t < m; ++t) {
@@ -578,16 +579,10 @@ __global__ void __launch_bounds__(32 * CB_WARPS, 8) k_build_cell(int ncells, con
                             const float fx = q.x - ox, fy = q.y - oy, fz = q.z - oz;
                             bool keep = fmaf(fz, fz, fmaf(fy, fy, fx * fx)) < pf.lim;
                             if (CHECK2) keep = keep && (__float_as_uint(q.w) & bit2) != 0u;
-                            if (keep) mask |= 1u << t;
+                            mine[ns] = (unsigned short)(tg + t);
+                            ns += keep;
                         }
                     }
-                    const unsigned sb = (unsigned)(self - g0);     // the atom itself is not its own neighbour (global i != j)
-                    if (sb < 32u) mask &= ~(1u << sb);
-                }
-                while (mask) {  // append the survivors of this group, in candidate order
-                    const int t = PFMDS_FFS(mask) - 1;
-                    mask &= mask - 1u;
-                    mine[ns++] = (unsigned short)(tag + (unsigned)(g0 + t));
                 }
             }
             __syncwarp();  // every lane is done with this stage buffer: it may be refilled
@@ -753,9 +748,8 @@ void nl_build(pfmds_ctx* c, NList& l) {
         const bool check2 = !c->slab && c->h_gmask.size() == (size_t)N && !c->all_in_group(l.g2);
         const bool chk = c->slab || check2;  // slab mode keeps its masks on the device only: always test
         // prefilter survivors per atom kept in shared memory between two runs of phase 2 (16-bit entries)
-        int lcap = 120;
-        if (const char* lc = std::getenv("PFMDS_NL_LCAP")) { int v = std::atoi(lc); if (v >= 40 && v <= 512) lcap = v; }
-        lcap = (lcap + 7) & ~7;
+        int lcap = 122;   // 61 words per lane: the lanes' list tails fall into different shared-memory banks
+        if (const char* lc = std::getenv("PFMDS_NL_LCAP")) { int v = std::atoi(lc); if (v >= 40 && v <= 512) lcap = (v & ~3) | 2; }
         const size_t dyn = (size_t)CB_WARPS * 32 * lcap * sizeof(unsigned short);
 #define CELL_ARGS c->ncells, c->pos, c->posf, c->orig, c->cell_start, g, c->box, pf, b1, b2, rc2, l.part_r1sq, l.part_r2sq, l.maxn, c->stride, l.nlist, l.nlist_alt, l.nnum, c->err, lcap
 #ifdef __CUDACC__
