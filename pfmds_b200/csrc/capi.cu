@@ -1597,26 +1597,7 @@ int pfmds_slab_download(pfmds_ctx* c, int* n_local, int* global_index, double* p
     return guarded(c, [&] {
         CK(cudaSetDevice(c->dev));
         integ_flush_pending(c);
-        const size_t N = (size_t)c->N;
-        std::vector<int> ho(N);
-        std::vector<uint32_t> hm(N);
-        std::vector<double4> buf(N);
-        CK(cudaMemcpyAsync(ho.data(), c->orig, sizeof(int) * N, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(hm.data(), c->gmask, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        int nl = 0;
-        for (size_t s = 0; s < N; ++s)
-            if (!(hm[s] & PFMDS_GHOST)) { if (global_index) global_index[nl] = ho[s] + 1; ++nl; }
-        if (n_local) *n_local = nl;
-        auto pull = [&](const double4* d, double* out) {
-            if (!out) return;
-            CK(cudaMemcpyAsync(buf.data(), d, sizeof(double4) * N, cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            size_t k = 0;
-            for (size_t s = 0; s < N; ++s)
-                if (!(hm[s] & PFMDS_GHOST)) { out[3 * k] = buf[s].x; out[3 * k + 1] = buf[s].y; out[3 * k + 2] = buf[s].z; ++k; }
-        };
-        pull(c->pos, pos); pull(c->vel, vel); pull(c->frc, frc);
+        slab_download(c, n_local, global_index, pos, vel, frc);
         check_device_error(c);
     });
 }
@@ -1628,23 +1609,7 @@ int pfmds_slab_upload(pfmds_ctx* c, int n_local, const double* pos, const double
         integ_flush_pending(c);
         c->nhc_ke_valid = false;
         c->energy_valid = false;
-        const size_t N = (size_t)c->N;
-        std::vector<uint32_t> hm(N);
-        CK(cudaMemcpyAsync(hm.data(), c->gmask, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        std::vector<double4> buf(N);
-        auto push = [&](double4* d, const double* in) {
-            if (!in) return;
-            CK(cudaMemcpyAsync(buf.data(), d, sizeof(double4) * N, cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            size_t k = 0;
-            for (size_t s = 0; s < N; ++s)
-                if (!(hm[s] & PFMDS_GHOST)) { buf[s].x = in[3 * k]; buf[s].y = in[3 * k + 1]; buf[s].z = in[3 * k + 2]; ++k; }
-            if ((int)k != n_local) fail(PFMDS_ERR_INVALID, "error: pfmds_slab_upload expects the atoms of the last pfmds_slab_download");
-            CK(cudaMemcpyAsync(d, buf.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->st));
-            CK(cudaStreamSynchronize(c->st));
-        };
-        push(c->pos, pos); push(c->vel, vel);
+        slab_upload(c, n_local, pos, vel);
         for (auto& it : c->inter) for (int j = 0; j < it.nl_n; ++j) it.nl[j].built = false;
     });
 }

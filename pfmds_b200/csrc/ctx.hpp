@@ -182,6 +182,8 @@ bool slab_ke_close(pfmds_ctx* c, const NhcPack& P, int nparts, const double* par
 void slab_allreduce_max(pfmds_ctx* c, double* d, int n);
 void slab_allreduce_max_int(pfmds_ctx* c, int* d, int n);
 void slab_allreduce_sum_ll(pfmds_ctx* c, unsigned long long* d, int n);
+void slab_download(pfmds_ctx* c, int* n_local, int* gid, double* pos, double* vel, double* frc);  // owned atoms, compacted on the device
+void slab_upload(pfmds_ctx* c, int n_local, const double* pos, const double* vel);
 int slab_rank(pfmds_ctx* c);
 int slab_nranks(pfmds_ctx* c);
 int slab_n_local(pfmds_ctx* c);

@@ -568,6 +568,76 @@ bool slab_ke_close(pfmds_ctx* c, const NhcPack& P, int nparts, const double* par
     return true;
 }
 
+// ---- this rank's atoms to / from the host (pfmds_slab_download / pfmds_slab_upload) ---------------------------------------------
+// Owned atoms (not ghost copies) in slot order, compacted on the device: an exclusive scan of the owner flags gives every owned slot
+// its row in dense [n_local][3] arrays (the migration / ghost buffers, free outside a rebuild), which then cross PCIe with one
+// copy per array.  (Round 1 copied the padded double4 arrays and compacted on the host: 0.6-0.7 s per call at 1.3e7 atoms per rank.)
+__global__ void k_sl_owner_flags(int N, const uint32_t* __restrict__ gmask, int* __restrict__ f) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) f[i] = (gmask[i] & GHOST_BIT) ? 0 : 1;
+}
+__global__ void k_sl_gather_owned(int N, const uint32_t* __restrict__ gmask, const int* __restrict__ row, const double4* __restrict__ a,
+                                  double* __restrict__ out, const int* __restrict__ orig, int* __restrict__ gid) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || (gmask[i] & GHOST_BIT)) return;
+    const int r = row[i];
+    if (a) { const double4 v = a[i]; out[3 * (size_t)r] = v.x; out[3 * (size_t)r + 1] = v.y; out[3 * (size_t)r + 2] = v.z; }
+    if (gid) gid[r] = orig[i] + 1;
+}
+__global__ void k_sl_scatter_owned(int N, const uint32_t* __restrict__ gmask, const int* __restrict__ row, const double* __restrict__ in,
+                                   double4* __restrict__ a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || (gmask[i] & GHOST_BIT)) return;
+    const int r = row[i];
+    double4 v = a[i];
+    v.x = in[3 * (size_t)r]; v.y = in[3 * (size_t)r + 1]; v.z = in[3 * (size_t)r + 2];
+    a[i] = v;
+}
+static int slab_owner_rows(pfmds_ctx* c, Slab* s) {   // rows of the owned slots in s->scan[0]; returns their number (known on the host)
+    const int N = c->N, T = 256;
+    LAUNCH((k_sl_owner_flags), (N + T - 1) / T, T, c->st, N, c->gmask, s->flag);
+    exclusive_scan(c, s, s->flag, s->scan[0], N, s->cnt_d + 7);
+    c->launches += 1;
+    return s->n_local;
+}
+void slab_download(pfmds_ctx* c, int* n_local, int* gid, double* pos, double* vel, double* frc) {
+    Slab* s = c->slab;
+    const int N = c->N, T = 256, nl = slab_owner_rows(c, s);
+    const size_t n3 = 3 * (size_t)nl;
+    double* stage[3] = {s->sbuf[0], s->sbuf[1], s->rbuf[0]};
+    const double4* src[3] = {c->pos, c->vel, c->frc};
+    double* out[3] = {pos, vel, frc};
+    int* gstage = reinterpret_cast<int*>(s->rbuf[1]);
+    bool first = true;
+    for (int a = 0; a < 3; ++a) {
+        if (!out[a] && !(first && gid && a == 2)) continue;
+        LAUNCH((k_sl_gather_owned), (N + T - 1) / T, T, c->st, N, c->gmask, s->scan[0], out[a] ? src[a] : (const double4*)nullptr, stage[a], c->orig,
+               (first && gid) ? gstage : (int*)nullptr);
+        first = false;
+        c->launches += 1;
+        if (out[a]) CK(cudaMemcpyAsync(out[a], stage[a], sizeof(double) * n3, cudaMemcpyDeviceToHost, c->st));
+    }
+    if (gid) CK(cudaMemcpyAsync(gid, gstage, sizeof(int) * (size_t)nl, cudaMemcpyDeviceToHost, c->st));
+    if (n_local) *n_local = nl;
+    CK(cudaStreamSynchronize(c->st));
+}
+void slab_upload(pfmds_ctx* c, int n_local, const double* pos, const double* vel) {
+    Slab* s = c->slab;
+    const int N = c->N, T = 256, nl = slab_owner_rows(c, s);
+    if (nl != n_local) throw std::string("pfmds_slab_upload expects the atoms of the last pfmds_slab_download");
+    const size_t n3 = 3 * (size_t)nl;
+    if (pos) {
+        CK(cudaMemcpyAsync(s->sbuf[0], pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
+        LAUNCH((k_sl_scatter_owned), (N + T - 1) / T, T, c->st, N, c->gmask, s->scan[0], s->sbuf[0], c->pos);
+    }
+    if (vel) {
+        CK(cudaMemcpyAsync(s->sbuf[1], vel, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
+        LAUNCH((k_sl_scatter_owned), (N + T - 1) / T, T, c->st, N, c->gmask, s->scan[0], s->sbuf[1], c->vel);
+    }
+    c->launches += 2;
+    CK(cudaStreamSynchronize(c->st));
+}
+
 void slab_allreduce_sum(pfmds_ctx* c, double* d, int n) {
     NK(g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, ncclSum, c->slab->comm, c->st));
 }

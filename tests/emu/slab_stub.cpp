@@ -27,3 +27,5 @@ int slab_nranks(pfmds_ctx*) { return 1; }
 int slab_n_local(pfmds_ctx*) { return 0; }
 long long slab_n_global(pfmds_ctx*) { return 0; }
 bool slab_ke_close(pfmds_ctx*, const NhcPack&, int, const double*, double, double, double) { return false; }
+void slab_download(pfmds_ctx*, int*, int*, double*, double*, double*) { no_slab(); }
+void slab_upload(pfmds_ctx*, int, const double*, const double*) { no_slab(); }
