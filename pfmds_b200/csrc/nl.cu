@@ -745,8 +745,9 @@ void nl_build(pfmds_ctx* c, NList& l) {
     // (sparse cells leave most lanes of a cell's warp without an atom: below 12 atoms per cell the thread-per-atom build is faster, measured on the LJ fluid)
     if (c->nl_cell && !warp_per_atom && c->identity_order && pf.on && g.n[0] >= 3 && g.n[1] >= 3 && g.n[2] >= 3 && (double)N >= 12. * c->ncells) {
         const int nbc = (c->ncells + CB_WARPS - 1) / CB_WARPS;
-        const bool check2 = !c->slab && c->h_gmask.size() == (size_t)N && !c->all_in_group(l.g2);
-        const bool chk = c->slab || check2;  // slab mode keeps its masks on the device only: always test
+        // the partner-group test can be dropped when every atom is in group 2 (slab mode: from the global group sizes)
+        const bool chk = c->slab ? !(l.g2 >= 1 && l.g2 <= (int)c->group_count.size() && c->group_count[(size_t)l.g2 - 1] == slab_n_global(c))
+                                 : !(c->h_gmask.size() == (size_t)N && c->all_in_group(l.g2));
         // prefilter survivors per atom kept in shared memory between two runs of phase 2 (16-bit entries)
         int lcap = 122;   // 61 words per lane: the lanes' list tails fall into different shared-memory banks
         if (const char* lc = std::getenv("PFMDS_NL_LCAP")) { int v = std::atoi(lc); if (v >= 40 && v <= 512) lcap = (v & ~3) | 2; }
