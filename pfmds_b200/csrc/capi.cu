@@ -64,6 +64,8 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
     c->nl_cell = env_int("PFMDS_NL_CELL", 1) != 0;
     c->pre_open_enabled = env_int("PFMDS_PRE_OPEN", 1) != 0;
+    c->persist_enabled = env_int("PFMDS_PERSIST", 1) != 0;
+    c->persist_bpsm = env_int("PFMDS_PERSIST_BLOCKS_PER_SM", 0);
     // 2 is the default: the third generation (node-table exponentials) removes 13 of 43 FP64 instructions per pair but its table
     // look-ups double the L1 data-pipe wavefronts, and that pipe is what bounds these kernels (ncu, profiles/r2b_*): measured
     // 0.343 against 0.277 ms (density) and 0.362 against 0.360 ms (force) per launch at 10^6 atoms
@@ -927,6 +929,41 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
     else { c->nhc_pending = false; c->nhc_ke_valid = false; c->nhc_opened = false; }
 }
 
+
+}  // extern "C"
+// Runs of plain steps of small systems go through the persistent step kernel (persist.cuh): from step s, how many consecutive steps of
+// the call [first, end) are plain -- not the first of the call, no list rebuild, no momentum removal, no energies, nothing profiled --
+// with the context in the steady state the kernel continues from?  `energy_at(step)` tells which steps report energies.
+template <class EnergyAt>
+static int persist_span(pfmds_ctx* c, int s, int first, int end, int kind, EnergyAt energy_at) {
+    if (kind != PFMDS_NVT && kind != PFMDS_NVE) return 0;
+    if (!c->use_graphs || c->prof_on || c->timers_on || c->slab || !c->changes.empty()) return 0;
+    if (kind == PFMDS_NVT && !(c->nhc_fusable && c->nhc_ke_valid)) return 0;
+    if (kind == PFMDS_NVE && c->nhc_pending) return 0;   // a pending thermostat scale is flushed by the step-by-step path first
+    if (g_live_contexts[c->dev & 63].load() > 1) return 0;
+    if (!persist_usable(c, kind == PFMDS_NVT)) return 0;
+    int m = 0;
+    for (int t = s; t < end; ++t, ++m) {
+        if (t == 0 || t == first || (t % c->zero_momentum_period == 0) || energy_at(t)) break;
+        bool rebuild = false;
+        for (auto& it : c->inter)
+            for (int j = 0; j < it.nl_n; ++j) rebuild |= (t % it.nl[j].period == 0) || !it.nl[j].built;
+        if (rebuild) break;
+    }
+    return m;
+}
+// the steps s .. s+m-1 in one launch; the host-side flags end up as after m calls of run_step
+static void persist_steps(pfmds_ctx* c, int m, int kind, double dt, bool next_follows) {
+    const bool nvt = kind == PFMDS_NVT;
+    const int last_mode = (nvt && next_follows && c->pre_open_enabled) ? 3 : 2;
+    if (nvt) integ_nvt_open_only(c, dt);
+    persist_run(c, nvt, dt, m, last_mode);
+    c->energy_valid = false;
+    if (nvt) { c->nhc_pending = true; c->nhc_ke_valid = true; c->nhc_opened = last_mode == 3; c->pre_open = last_mode == 3; }
+    else { c->nhc_pending = false; c->nhc_ke_valid = false; c->nhc_opened = false; }
+}
+extern "C" {
+
 static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, bool energy_last);
 int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) { return advance_impl(c, kind, dt, first, n, false); }
 int pfmds_advance_with_energy(pfmds_ctx* c, int kind, double dt, int first, int n) { return advance_impl(c, kind, dt, first, n, true); }
@@ -936,7 +973,12 @@ static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, boo
         if (n < 0 || first < 0) fail(PFMDS_ERR_INVALID, "error: bad step range");
         CK(cudaSetDevice(c->dev));
         finalize(c);
-        for (int s = first; s < first + n; ++s) run_step(c, s, first, kind, dt, energy_last && s == first + n - 1, s + 1 < first + n);
+        const int end = first + n;
+        for (int s = first; s < end; ++s) {
+            const int m = persist_span(c, s, first, end, kind, [&](int t) { return energy_last && t == end - 1; });
+            if (m >= 2) { persist_steps(c, m, kind, dt, s + m < end); s += m - 1; continue; }
+            run_step(c, s, first, kind, dt, energy_last && s == end - 1, s + 1 < end);
+        }
         CK(cudaGetLastError());
     });
 }
@@ -992,6 +1034,10 @@ int pfmds_advance_logged(pfmds_ctx* c, int kind, double dt, int first, int n, in
         int r = 0;
         for (int s = first; s < first + n; ++s) {
             const bool logged = s % log_period == 0;
+            if (!logged) {   // runs of unlogged plain steps of small systems: one launch of the persistent step kernel
+                const int m = persist_span(c, s, first, first + n, kind, [&](int t) { return t % log_period == 0; });
+                if (m >= 2) { persist_steps(c, m, kind, dt, s + m < first + n); s += m - 1; continue; }
+            }
             run_step(c, s, first, kind, dt, logged, s + 1 < first + n);   // unlogged steady-state steps of small systems replay their CUDA graph, as in pfmds_advance
             if (!logged) continue;
             integ_flush_pending(c);                              // as pfmds_energies: KE of the velocities the host would download
@@ -1431,6 +1477,34 @@ int pfmds_timer_stop(pfmds_ctx* c, double* ms) {
     });
 }
 
+#if defined(__CUDACC__) && defined(PFMDS_STAMPS)
+// debug build only (tools/stamps_probe.py): bind / read the per-step time stamps of common.cuh
+}  // extern "C"
+void forces_stamps_bind(unsigned long long* p);
+void integ_stamps_bind(unsigned long long* p);
+extern "C" {
+static unsigned long long* g_stamps_dev = nullptr;
+int pfmds_debug_stamps_begin(void) {
+    const size_t n = 1 + (size_t)STAMP_STEPS * 2 * STAMP_SLOTS;
+    if (!g_stamps_dev && cudaMalloc(&g_stamps_dev, n * 8) != cudaSuccess) return PFMDS_ERR_CUDA;
+    std::vector<unsigned long long> h(n, 0ull);
+    for (size_t s = 0; s < STAMP_STEPS; ++s)
+        for (int k = 0; k < STAMP_SLOTS; ++k) h[1 + s * 2 * STAMP_SLOTS + k] = ~0ull;
+    cudaDeviceSynchronize();
+    cudaMemcpy(g_stamps_dev, h.data(), n * 8, cudaMemcpyHostToDevice);
+    forces_stamps_bind(g_stamps_dev);
+    integ_stamps_bind(g_stamps_dev);
+    cudaDeviceSynchronize();
+    return PFMDS_OK;
+}
+int pfmds_debug_stamps_read(unsigned long long* out) {  // 1 + STAMP_STEPS * 2 * STAMP_SLOTS words
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, g_stamps_dev, (1 + (size_t)STAMP_STEPS * 2 * STAMP_SLOTS) * 8, cudaMemcpyDeviceToHost);
+    forces_stamps_bind(nullptr);
+    integ_stamps_bind(nullptr);
+    return PFMDS_OK;
+}
+#endif
 // Max errors of the device elementary functions: [0] exp relative, [1] switch/sincos absolute,
 // [2] rsqrt relative, [3] raw MUFU.RSQ64H seed relative.
 int pfmds_selftest_math(int device, double err[4]) {
@@ -1637,7 +1711,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     if (c->st) cudaStreamSynchronize(c->st);
     slab_destroy(c);
     for (auto& it : c->inter) {
-        for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nlist_alt); cudaFree(it.nl[j].nnum); }
+        for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nlist_alt); cudaFree(it.nl[j].nnum); cudaFree(it.nl[j].owners); cudaFree(it.nl[j].n_owners); }
         cudaFree(it.aux); cudaFree(it.aux2); cudaFree(it.fpart); cudaFree(it.gnorm); cudaFree(it.tvec);
     }
     for (auto& t : c->nhc) cudaFree(t.state);
@@ -1645,6 +1719,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     for (auto b : c->fbuf) cudaFree(b);
     cudaFree(c->ticket);
+    cudaFree(c->pbar);
     if (c->aux_ev_mid) cudaEventDestroy(c->aux_ev_mid);
     for (auto s : c->aux_st) cudaStreamDestroy(s);
     for (auto e : c->aux_ev) cudaEventDestroy(e);

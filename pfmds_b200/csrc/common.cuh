@@ -119,7 +119,10 @@ struct NhcPack { int n; uint32_t bit[NHC_MAXF]; double* state[NHC_MAXF]; int M[N
 
 // ---- Nose-Hoover chain half step: md_integrators.f90:200-245 ---------------------------------------
 // state = x[M], v[M], q[M], s, ke_cached, s_pending.  Returns the velocity scale s = exp(-v1 dt/2).
-__device__ __forceinline__ double nhc_chain(double* state, int M, int L, double temperature, double ke, double ts2, double ts3, double ts4) {
+// NOT inlined: the kernels that run it (k_nhc, k_nhc_open, k_nhc_close, k_sum_kick_ke, k_sl_ke_close, k_persist) must produce the same
+// bits, and inlined into different surroundings the compiler contracts a*b + c*d into fma either way round and hoists loop-invariant
+// products out of the persistent kernel's step loop (measured: chain x, v one ulp apart between k_persist and k_sum_kick_ke).
+static __device__ __noinline__ double nhc_chain(double* state, int M, int L, double temperature, double ke, double ts2, double ts3, double ts4) {
     double* x = state;
     double* v = state + M;
     const double* q = state + 2 * M;
@@ -252,3 +255,28 @@ static inline void slab_signal(const SlabDev&, bool) {}
 #endif
 
 struct ListView { const int* nlist; const int* nnum; size_t stride; };
+
+// ---- debug build only (-DPFMDS_STAMPS, tools/stamps_probe.py): per-step time stamps of the phases of a small system's step ----------
+// Not part of the product: libpfmds_b200.so is built without the macro and every STAMP() below is empty.
+#if defined(__CUDACC__) && defined(PFMDS_STAMPS)
+#define STAMP_SLOTS 16
+#define STAMP_STEPS 4096
+static __device__ unsigned long long* g_stamp_buf;  // [0] = step counter, then per step STAMP_SLOTS minima and STAMP_SLOTS maxima
+__device__ __forceinline__ void stamp_at(int slot, bool is_min) {
+    unsigned long long* b = g_stamp_buf;
+    if (!b) return;
+    unsigned long long s = *reinterpret_cast<volatile unsigned long long*>(b);
+    if (s >= STAMP_STEPS) return;
+    unsigned long long t = pf_now_ns();
+    unsigned long long* q = b + 1 + s * 2 * STAMP_SLOTS + slot + (is_min ? 0 : STAMP_SLOTS);
+    if (is_min) atomicMin(q, t); else atomicMax(q, t);
+}
+#define STAMP_MIN(slot) do { if (threadIdx.x == 0) stamp_at(slot, true); } while (0)
+#define STAMP_MAX(slot) do { if (threadIdx.x == 0) stamp_at(slot, false); } while (0)
+#define STAMP_NEXT_STEP() do { if (g_stamp_buf) atomicAdd(g_stamp_buf, 1ull); } while (0)
+#define STAMP_BIND_FN(name) void name(unsigned long long* p) { cudaMemcpyToSymbol(g_stamp_buf, &p, sizeof p); }
+#else
+#define STAMP_MIN(slot) do { } while (0)
+#define STAMP_MAX(slot) do { } while (0)
+#define STAMP_NEXT_STEP() do { } while (0)
+#endif

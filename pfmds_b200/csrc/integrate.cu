@@ -10,10 +10,7 @@
 #include "ctx.hpp"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
-#define IT 256
-
-// md_general.f90:342-364 — every atom, tolerance 1e-7, negated condition so NaN is caught too
-__device__ __forceinline__ bool outside(double x, double L) { return !(x > (0. - 0.0000001) && x < (L + 0.0000001)); }
+#include "integ_bodies.cuh"  // IT, outside(), the per-atom bodies shared with the persistent small-system kernel
 
 __global__ void k_check_positions(int N, const double4* __restrict__ pos, const int* __restrict__ orig, BoxD box, int* err) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,28 +103,7 @@ void integ_nhc_half(pfmds_ctx* c, Nhc& t, double dt) {
 __global__ void __launch_bounds__(IT) k_kick_drift(int N, double4* __restrict__ pos, double4* __restrict__ vel, const double4* __restrict__ frc,
                                                    const uint32_t* __restrict__ gmask, const int* __restrict__ orig, uint32_t bxyz, uint32_t bz,
                                                    double ts1, double ts2, BoxD box, int* err) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    uint32_t g = gmask[i];
-    if (g & PFMDS_GHOST) return;
-    bool mx = g & bxyz, mz = g & bz;
-    if (!mx && !mz) return;
-    double4 p = pos[i], v = vel[i], f = frc[i];
-    if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
-    if (mx) {
-        v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
-        v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
-        v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
-    }
-    if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
-    if (mx) {
-        p.x = p.x + v.x * ts1; if (p.x > box.L[0]) p.x = p.x - box.L[0]; else if (p.x < 0.) p.x = p.x + box.L[0];
-        p.y = p.y + v.y * ts1; if (p.y > box.L[1]) p.y = p.y - box.L[1]; else if (p.y < 0.) p.y = p.y + box.L[1];
-        p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2];
-    }
-    if (mz) { p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2]; }
-    pos[i] = p;
-    vel[i] = v;
+    d_kick_drift(blockIdx.x * blockDim.x + threadIdx.x, N, pos, vel, frc, gmask, orig, bxyz, bz, ts1, ts2, box, err);
 }
 void integ_kick_drift(pfmds_ctx* c, double dt) {
     KTimer kt(c, KS_KICK_DRIFT);
@@ -285,41 +261,10 @@ __global__ void __launch_bounds__(IT) k_kick_drift_nvt(int N, double4* __restric
                                                        double ts1, double ts2, BoxD box, NhcPack P, int* err, SlabDev S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool pushed = false;
+    STAMP_MIN(0);
     slab_wait(S);  // slab mode: the neighbours' force kernels are done with the ghost positions this kernel is about to overwrite
-    uint32_t g = i < N ? gmask[i] : PFMDS_GHOST;
-    bool mx = g & bxyz, mz = g & bz;
-    double sc = 1.0;
-    bool th = false;
-    for (int k = 0; k < P.n; ++k)
-        if (g & P.bit[k]) { sc = P.state[k][3 * P.M[k] + 2]; th = true; }
-    if (!(g & PFMDS_GHOST) && (mx || mz || th)) {  // one exit point: slab_signal() below holds a block barrier
-        double4 v = vel[i];
-        v.x *= sc; v.y *= sc; v.z *= sc;
-        if (mx || mz) {
-            double4 p = pos[i], f = frc[i];
-            if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
-            if (mx) {
-                v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
-                v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
-                v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
-            }
-            if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
-            if (mx) {
-                p.x = p.x + v.x * ts1; if (p.x > box.L[0]) p.x = p.x - box.L[0]; else if (p.x < 0.) p.x = p.x + box.L[0];
-                p.y = p.y + v.y * ts1; if (p.y > box.L[1]) p.y = p.y - box.L[1]; else if (p.y < 0.) p.y = p.y + box.L[1];
-                p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2];
-            }
-            if (mz) { p.z = p.z + v.z * ts1; if (p.z > box.L[2]) p.z = p.z - box.L[2]; else if (p.z < 0.) p.z = p.z + box.L[2]; }
-            pos[i] = p;
-            if (S.push) {  // the new position goes straight into the ghost copies of this atom on the neighbour GPUs
-                int a = S.rs_l[i], b = S.rs_r[i];
-                if (a >= 0) { double* q = reinterpret_cast<double*>(&S.peer_l[a]); q[0] = p.x; q[1] = p.y; q[2] = p.z; }
-                if (b >= 0) { double* q = reinterpret_cast<double*>(&S.peer_r[b]); q[0] = p.x; q[1] = p.y; q[2] = p.z; }
-                pushed = (a >= 0) || (b >= 0);
-            }
-        }
-        vel[i] = v;
-    }
+    d_kick_drift_nvt(i, N, pos, vel, frc, gmask, orig, bxyz, bz, ts1, ts2, box, P, err, S, pushed);
+    STAMP_MAX(1);
     slab_signal(S, pushed);
 }
 __global__ void k_reset_pending(NhcPack P) {
@@ -378,50 +323,23 @@ __global__ void __launch_bounds__(1024) k_nhc_close(int nparts, const double* __
 // zero_forces leaves (0 inside the all_atoms group, the old force outside it: md_integrators.f90:147-163), add the buffers in file
 // order -- the sequence of additions of the one-after-the-other path, so the same bits -- store, clear the buffers for the next
 // step, then k_kick / k_kick_ke's arithmetic unchanged (same grid, same partial sums: the same kinetic energy bits).
-struct FBufs { int n; double4* b[12]; };
 template <int MODE>  // 0: sum only (step 0, restore); 1: + closing half kick; 2: + KE partial sums of the thermostat groups
 __global__ void __launch_bounds__(IT) k_sum_kick_ke(int N, double4* __restrict__ vel, double4* __restrict__ frc, const uint32_t* __restrict__ gmask, FBufs F,
                                                     int zero_all, uint32_t ball, uint32_t bxyz, uint32_t bz, double ts2, NhcPack P, double* __restrict__ part,
                                                     unsigned int* ticket, int also_open) {
     double ke[NHC_MAXF];
+    STAMP_MIN(4);
     for (int k = 0; k < NHC_MAXF; ++k) ke[k] = 0.;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        const uint32_t g = gmask[i];
-        double4 f = make_double4(0., 0., 0., 0.);
-        if (!zero_all && !(g & ball)) f = frc[i];
-        for (int t = 0; t < F.n; ++t) {
-            const double4 a = F.b[t][i];
-            f.x += a.x; f.y += a.y; f.z += a.z;
-            F.b[t][i] = make_double4(0., 0., 0., 0.);
-        }
-        frc[i] = f;
-        if (MODE == 0 || (g & PFMDS_GHOST)) continue;
-        const bool mx = g & bxyz, mz = g & bz;
-        bool th = false;
-        if (MODE == 2)
-            for (int k = 0; k < P.n; ++k) th |= (g & P.bit[k]) != 0;
-        if (!mx && !mz && !th) continue;
-        double4 v = vel[i];
-        if (mx || mz) {
-            if (mx) {
-                v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
-                v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
-                v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
-            }
-            if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
-            vel[i] = v;
-        }
-        if (MODE == 2) {
-            double e = v.w * (v.x * v.x + v.y * v.y + v.z * v.z) / 2 * PFMDS_MASS_COEF;
-            for (int k = 0; k < P.n; ++k)
-                if (g & P.bit[k]) ke[k] += e;
-        }
+        d_sum_kick_atom<MODE>(i, vel, frc, gmask, F, zero_all, ball, bxyz, bz, ts2, P, ke);
     }
+    STAMP_MAX(5);
     if (MODE == 2) {
         for (int k = 0; k < P.n; ++k) {
             double s = block_sum(ke[k]);
             if (threadIdx.x == 0) part[blockIdx.x * NHC_MAXF + k] = s;
         }
+        STAMP_MAX(6);
 #ifdef PFMDS_COOP
         // The block that finishes last closes the thermostat step (k_nhc_close's statements: partials summed in block order by one
         // block, chain update by its thread 0), so small systems, whose steps are chains of 5-us kernels, lose one link of the chain.
@@ -433,12 +351,14 @@ __global__ void __launch_bounds__(IT) k_sum_kick_ke(int N, double4* __restrict__
             }
             __syncthreads();
             if (last) {
+                STAMP_MAX(7);
                 __threadfence();                                   // every other block's partials after their tickets
                 const volatile double* vp = part;
                 for (int k = 0; k < P.n; ++k) {
                     double sk = 0.;
                     for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) sk += vp[(size_t)b * NHC_MAXF + k];
                     sk = block_sum(sk);
+                    STAMP_MAX(8);
                     if (threadIdx.x == 0) {
                         double* st = P.state[k];
                         const int M = P.M[k];
@@ -446,12 +366,16 @@ __global__ void __launch_bounds__(IT) k_sum_kick_ke(int N, double4* __restrict__
                     }
                     __syncthreads();
                 }
-                if (threadIdx.x == 0) *ticket = 0u;                // ready for the next launch
+                STAMP_MAX(9);
+                if (threadIdx.x == 0) { *ticket = 0u; STAMP_NEXT_STEP(); }   // ready for the next launch
             }
         }
 #endif
     }
 }
+#if defined(__CUDACC__) && defined(PFMDS_STAMPS)
+STAMP_BIND_FN(integ_stamps_bind)
+#endif
 static NhcPack pack_of(pfmds_ctx* c) {
     NhcPack P{};
     P.n = (int)c->nhc.size();
@@ -471,6 +395,11 @@ void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step) {
                                                              1u << (c->z_moving - 1), dt, dt / 2, c->box, P, c->err, S);
     // s_pending has been consumed; the closing half step of this same step overwrites it (k_nhc_close), so no reset here
     c->launches += 1;
+}
+// the opening half step alone (the persistent step kernel continues from the state k_kick_drift_nvt would find)
+void integ_nvt_open_only(pfmds_ctx* c, double dt) {
+    if (!c->nhc_opened) { LAUNCH((k_nhc_open), 1, 32, c->st, pack_of(c), dt / 2, dt / 4, dt / 8); c->launches += 1; }
+    c->nhc_opened = false;
 }
 __global__ void k_reduce_ke_partials(int nparts, const double* __restrict__ part, int n, double* __restrict__ out) {
     for (int k = 0; k < n; ++k) {

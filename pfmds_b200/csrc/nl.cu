@@ -765,6 +765,7 @@ void nl_build(pfmds_ctx* c, NList& l) {
 #undef CELL_ARGS
         c->launches += 1;
         l.built = true;
+        l.owners_valid = false;
         CK(cudaGetLastError());
         return;
     }
@@ -785,6 +786,7 @@ void nl_build(pfmds_ctx* c, NList& l) {
 #undef BUILD_ARGS
     c->launches += 1;
     l.built = true;
+    l.owners_valid = false;
     CK(cudaGetLastError());
 }
 #endif  // PFMDS_HAVE_CTX
@@ -821,6 +823,7 @@ void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     LAUNCH((k_nearest3), nb, T, c->st, N, c->pos, c->orig, src.view(c->stride), c->box, nn.rcut, c->stride, nn.nlist, nn.nnum, c->err);
     c->launches += 1;
     nn.built = true;
+    nn.owners_valid = false;
     CK(cudaGetLastError());
 }
 #endif  // PFMDS_HAVE_CTX
