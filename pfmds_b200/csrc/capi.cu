@@ -64,8 +64,8 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
     c->nl_cell = env_int("PFMDS_NL_CELL", 1) != 0;
     c->pre_open_enabled = env_int("PFMDS_PRE_OPEN", 1) != 0;
-    c->persist_enabled = env_int("PFMDS_PERSIST", 1) != 0;
-    c->persist_bpsm = env_int("PFMDS_PERSIST_BLOCKS_PER_SM", 0);
+    c->graph_steps = env_int("PFMDS_GRAPH_STEPS", 4);
+    if (c->graph_steps < 1 || c->graph_steps > 64) c->graph_steps = 1;
     // 2 is the default: the third generation (node-table exponentials) removes 13 of 43 FP64 instructions per pair but its table
     // look-ups double the L1 data-pipe wavefronts, and that pipe is what bounds these kernels (ncu, profiles/r2b_*): measured
     // 0.343 against 0.277 ms (density) and 0.362 against 0.360 ms (force) per launch at 10^6 atoms
@@ -878,7 +878,7 @@ int pfmds_add_interaction(pfmds_ctx* c, const char* name, int np, const double* 
 // One md step of a call that started at step `first`.  Steady-state steps (no list rebuild, no momentum removal, no energy
 // request, not the first of the call) of small systems are replayed from a CUDA graph captured from this very code path: same
 // kernels, same order, fewer launch gaps.
-static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool with_energy, bool next_follows = false) {
+static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool with_energy, bool next_follows = false, int nrep = 1) {
     // the thermostat's opening half step of step s+1 can ride in the closing kernel of step s when s+1 follows inside this call,
     // nothing reads or regroups the chains in between (no log row, no deposition) and the fused NVT path is in use
     c->pre_open = next_follows && kind == PFMDS_NVT && c->nhc_fusable && !c->slab && c->changes.empty() && !with_energy && c->pre_open_enabled;
@@ -900,13 +900,13 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
     pfmds_ctx::StepGraph* g = nullptr;
     for (auto& e : c->graphs)
         if (e.kind == kind && e.dt == dt && e.pos == (const void*)c->pos && e.pending == c->nhc_pending && e.ke_valid == c->nhc_ke_valid &&
-            e.opened == c->nhc_opened && e.pre_open == c->pre_open && e.alone == (g_live_contexts[c->dev & 63].load() <= 1)) g = &e;
+            e.opened == c->nhc_opened && e.pre_open == c->pre_open && e.alone == (g_live_contexts[c->dev & 63].load() <= 1) && e.nsteps == nrep) g = &e;
     if (!g) {
-        pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, c->nhc_opened, c->pre_open, g_live_contexts[c->dev & 63].load() <= 1, nullptr, 0};
+        pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, c->nhc_opened, c->pre_open, g_live_contexts[c->dev & 63].load() <= 1, nullptr, 0, nrep};
         const long long l0 = c->launches;
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
-        try { do_step(c, s, kind, dt, false); } catch (...) { cudaStreamEndCapture(c->st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        try { for (int r = 0; r < nrep; ++r) do_step(c, s + r, kind, dt, false); } catch (...) { cudaStreamEndCapture(c->st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
         CK(cudaStreamEndCapture(c->st, &graph));
         CK(cudaGraphInstantiate(&e.exec, graph, 0));
         CK(cudaGraphDestroy(graph));
@@ -914,7 +914,7 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
         c->launches = l0;
         // capturing ran the host-side bookkeeping of one step: the flags now describe the state AFTER a step; a step
         // is only graphable again from the same entry state, which holds in steady state (checked by the key)
-        if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+        if (c->graphs.size() >= 12) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
         c->graphs.push_back(e);
         g = &c->graphs.back();
         CK(cudaGraphLaunch(g->exec, c->st));
@@ -929,41 +929,23 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
     else { c->nhc_pending = false; c->nhc_ke_valid = false; c->nhc_opened = false; }
 }
 
-
 }  // extern "C"
-// Runs of plain steps of small systems go through the persistent step kernel (persist.cuh): from step s, how many consecutive steps of
-// the call [first, end) are plain -- not the first of the call, no list rebuild, no momentum removal, no energies, nothing profiled --
-// with the context in the steady state the kernel continues from?  `energy_at(step)` tells which steps report energies.
+// Steady-state steps of small systems are replayed from CUDA graphs; where a run of them allows it one graph launch carries
+// c->graph_steps steps (the gap between two graph launches is 4.4 us, between two nodes of one graph 2.3 us).  From step s: can the
+// next `g` steps of the call [first, end) go as one graph?  All of them must be plain (run_step's `graphable`) and followed by
+// another step of the call, so that the thermostat flags are those of the steady state on both sides of every step.
 template <class EnergyAt>
-static int persist_span(pfmds_ctx* c, int s, int first, int end, int kind, EnergyAt energy_at) {
-    if (kind != PFMDS_NVT && kind != PFMDS_NVE) return 0;
-    if (!c->use_graphs || c->prof_on || c->timers_on || c->slab || !c->changes.empty()) return 0;
-    if (kind == PFMDS_NVT && !(c->nhc_fusable && c->nhc_ke_valid)) return 0;
-    if (kind == PFMDS_NVE && c->nhc_pending) return 0;   // a pending thermostat scale is flushed by the step-by-step path first
-    if (g_live_contexts[c->dev & 63].load() > 1) return 0;
-    if (!persist_usable(c, kind == PFMDS_NVT)) return 0;
-    int m = 0;
-    for (int t = s; t < end; ++t, ++m) {
-        if (t == 0 || t == first || (t % c->zero_momentum_period == 0) || energy_at(t)) break;
-        bool rebuild = false;
+static bool graph_run_ok(pfmds_ctx* c, int s, int first, int end, int g, EnergyAt energy_at) {
+    if (g < 2 || !c->use_graphs || c->slab || c->prof_on || c->timers_on || !c->changes.empty() || s + g >= end) return false;
+    for (int t = s; t < s + g; ++t) {
+        if (t == 0 || t == first || (t % c->zero_momentum_period == 0) || energy_at(t)) return false;
         for (auto& it : c->inter)
-            for (int j = 0; j < it.nl_n; ++j) rebuild |= (t % it.nl[j].period == 0) || !it.nl[j].built;
-        if (rebuild) break;
+            for (int j = 0; j < it.nl_n; ++j)
+                if ((t % it.nl[j].period == 0) || !it.nl[j].built) return false;
     }
-    return m;
-}
-// the steps s .. s+m-1 in one launch; the host-side flags end up as after m calls of run_step
-static void persist_steps(pfmds_ctx* c, int m, int kind, double dt, bool next_follows) {
-    const bool nvt = kind == PFMDS_NVT;
-    const int last_mode = (nvt && next_follows && c->pre_open_enabled) ? 3 : 2;
-    if (nvt) integ_nvt_open_only(c, dt);
-    persist_run(c, nvt, dt, m, last_mode);
-    c->energy_valid = false;
-    if (nvt) { c->nhc_pending = true; c->nhc_ke_valid = true; c->nhc_opened = last_mode == 3; c->pre_open = last_mode == 3; }
-    else { c->nhc_pending = false; c->nhc_ke_valid = false; c->nhc_opened = false; }
+    return true;
 }
 extern "C" {
-
 static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, bool energy_last);
 int pfmds_advance(pfmds_ctx* c, int kind, double dt, int first, int n) { return advance_impl(c, kind, dt, first, n, false); }
 int pfmds_advance_with_energy(pfmds_ctx* c, int kind, double dt, int first, int n) { return advance_impl(c, kind, dt, first, n, true); }
@@ -973,10 +955,9 @@ static int advance_impl(pfmds_ctx* c, int kind, double dt, int first, int n, boo
         if (n < 0 || first < 0) fail(PFMDS_ERR_INVALID, "error: bad step range");
         CK(cudaSetDevice(c->dev));
         finalize(c);
-        const int end = first + n;
+        const int end = first + n, g = c->graph_steps;
         for (int s = first; s < end; ++s) {
-            const int m = persist_span(c, s, first, end, kind, [&](int t) { return energy_last && t == end - 1; });
-            if (m >= 2) { persist_steps(c, m, kind, dt, s + m < end); s += m - 1; continue; }
+            if (graph_run_ok(c, s, first, end, g, [&](int t) { return energy_last && t == end - 1; })) { run_step(c, s, first, kind, dt, false, true, g); s += g - 1; continue; }
             run_step(c, s, first, kind, dt, energy_last && s == end - 1, s + 1 < end);
         }
         CK(cudaGetLastError());
@@ -1034,9 +1015,10 @@ int pfmds_advance_logged(pfmds_ctx* c, int kind, double dt, int first, int n, in
         int r = 0;
         for (int s = first; s < first + n; ++s) {
             const bool logged = s % log_period == 0;
-            if (!logged) {   // runs of unlogged plain steps of small systems: one launch of the persistent step kernel
-                const int m = persist_span(c, s, first, first + n, kind, [&](int t) { return t % log_period == 0; });
-                if (m >= 2) { persist_steps(c, m, kind, dt, s + m < first + n); s += m - 1; continue; }
+            if (!logged && graph_run_ok(c, s, first, first + n, c->graph_steps, [&](int t) { return t % log_period == 0; })) {
+                run_step(c, s, first, kind, dt, false, true, c->graph_steps);
+                s += c->graph_steps - 1;
+                continue;
             }
             run_step(c, s, first, kind, dt, logged, s + 1 < first + n);   // unlogged steady-state steps of small systems replay their CUDA graph, as in pfmds_advance
             if (!logged) continue;
@@ -1711,7 +1693,7 @@ int pfmds_destroy(pfmds_ctx* c) {
     if (c->st) cudaStreamSynchronize(c->st);
     slab_destroy(c);
     for (auto& it : c->inter) {
-        for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nlist_alt); cudaFree(it.nl[j].nnum); cudaFree(it.nl[j].owners); cudaFree(it.nl[j].n_owners); }
+        for (int j = 0; j < 3; ++j) { cudaFree(it.nl[j].nlist); cudaFree(it.nl[j].nlist_alt); cudaFree(it.nl[j].nnum); }
         cudaFree(it.aux); cudaFree(it.aux2); cudaFree(it.fpart); cudaFree(it.gnorm); cudaFree(it.tvec);
     }
     for (auto& t : c->nhc) cudaFree(t.state);
@@ -1719,7 +1701,6 @@ int pfmds_destroy(pfmds_ctx* c) {
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     for (auto b : c->fbuf) cudaFree(b);
     cudaFree(c->ticket);
-    cudaFree(c->pbar);
     if (c->aux_ev_mid) cudaEventDestroy(c->aux_ev_mid);
     for (auto s : c->aux_st) cudaStreamDestroy(s);
     for (auto e : c->aux_ev) cudaEventDestroy(e);

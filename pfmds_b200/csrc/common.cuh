@@ -119,9 +119,9 @@ struct NhcPack { int n; uint32_t bit[NHC_MAXF]; double* state[NHC_MAXF]; int M[N
 
 // ---- Nose-Hoover chain half step: md_integrators.f90:200-245 ---------------------------------------
 // state = x[M], v[M], q[M], s, ke_cached, s_pending.  Returns the velocity scale s = exp(-v1 dt/2).
-// NOT inlined: the kernels that run it (k_nhc, k_nhc_open, k_nhc_close, k_sum_kick_ke, k_sl_ke_close, k_persist) must produce the same
-// bits, and inlined into different surroundings the compiler contracts a*b + c*d into fma either way round and hoists loop-invariant
-// products out of the persistent kernel's step loop (measured: chain x, v one ulp apart between k_persist and k_sum_kick_ke).
+// NOT inlined: the kernels that run it (k_nhc, k_nhc_open, k_nhc_close, k_sum_kick_ke, k_sl_ke_close) must produce the same bits, and
+// inlined into different surroundings the compiler is free to contract a*b + c*d into an fma either way round and to hoist
+// loop-invariant products (seen in round 2: chain x, v one ulp apart between two kernels that inlined it).
 static __device__ __noinline__ double nhc_chain(double* state, int M, int L, double temperature, double ke, double ts2, double ts3, double ts4) {
     double* x = state;
     double* v = state + M;

@@ -22,10 +22,6 @@ struct NList {
     bool partition = false;
     double part_r1sq = 0, part_r2sq = 0;
     int* nlist_alt = nullptr;
-    // persistent step kernel (persist.cuh): the slots that own a non-empty row, ascending, and their number (device); rebuilt lazily
-    int* owners = nullptr;
-    int* n_owners = nullptr;
-    bool owners_valid = false;
     ListView view(size_t stride) const { return ListView{nlist, nnum, stride}; }
 };
 
@@ -97,9 +93,10 @@ struct pfmds_ctx {
     int* newslot = nullptr;  // old slot -> new slot of the last cell re-sort
     std::vector<long long> group_count;  // slab mode: global size of every group
     // CUDA graphs of the steady-state step (small systems are launch-latency bound), keyed by what is baked in
-    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid, opened, pre_open, alone; cudaGraphExec_t exec; long long launches; };
+    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid, opened, pre_open, alone; cudaGraphExec_t exec; long long launches; int nsteps; };
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
+    int graph_steps = 4;            // steady-state steps per graph launch where a run of them allows it (PFMDS_GRAPH_STEPS; graph-to-graph gap 4.4 us, node-to-node 2.3 us: tools/stamps_probe.py)
     int rjl_gen = 2;                // rjl pair routines: 2 = analytic short forms (default), 3 = node-table exponentials (measured slower: L1-bound), 1 = first generation (PFMDS_RJL_GEN)
     bool nl_mask = true;            // thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (measured 8 % faster, BENCH_r01); PFMDS_NL_MASK=0: k_build
     bool lj1g_pipe = true;          // pipelined lj1g force kernel for systems of small_n atoms and more (measured 0.174 -> 0.102 ms, BENCH_r01); PFMDS_LJ1G_PIPE=0: k_lj1g
@@ -120,12 +117,6 @@ struct pfmds_ctx {
     unsigned int* ticket = nullptr;      // block counter of k_sum_kick_ke (its last block closes the thermostat step)
     bool fbuf_on = false;                // buffers exist (finalize): small system, at most 8 interactions, PFMDS_SMALL_FORK != 0
     bool fbuf_active = false;            // this step's forces went into the buffers: the sum kernel must run
-    // persistent step kernel of small systems (persist.cuh): runs of plain steps in one cooperative launch
-    bool persist_enabled = true;         // PFMDS_PERSIST=0: every step goes through the step-by-step path
-    int persist_bpsm = 0;                // PFMDS_PERSIST_BLOCKS_PER_SM: cap on its resident blocks per SM (0: what fits)
-    int persist_state = -1;              // -1: not decided yet; 0: this context cannot use it; 1: usable
-    int persist_grid = 0;                // resident blocks of k_persist on this device
-    unsigned int* pbar = nullptr;        // its grid-barrier counter
     bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
     bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)
     bool finalized = false;
@@ -205,8 +196,6 @@ void rjl_prepare(pfmds_ctx* c, Inter& it);  // third-generation rjl: node table 
 void forces_interaction(pfmds_ctx* c, int k, bool with_energy);
 void normals_interaction(pfmds_ctx* c, int k, cudaStream_t st = nullptr);
 void energy_interaction(pfmds_ctx* c, int k);  // result in c->energy[k]
-bool persist_usable(pfmds_ctx* c, bool nvt);   // persist.cuh: can runs of plain nvt / nve steps go through the persistent kernel?
-void persist_run(pfmds_ctx* c, bool nvt, double dt, int nsteps, int last_mode);
 
 // ---- rebosc.cu ----
 void rebosc_forces(pfmds_ctx* c, Inter& it);          // numerical forces, md_interactions.f90:273-311
@@ -222,7 +211,6 @@ void integ_quench(pfmds_ctx* c);
 void integ_zero_momentum(pfmds_ctx* c);
 void integ_nvt_open_kick_drift(pfmds_ctx* c, double dt, bool rebuild_step);
 void integ_nvt_kick_close(pfmds_ctx* c, double dt);
-void integ_nvt_open_only(pfmds_ctx* c, double dt);
 void integ_sum_forces(pfmds_ctx* c, int mode, double dt);   // fbuf mode: per-atom sum of the interaction buffers; mode 0 sum, 1 + closing kick, 2 + thermostat KE partials and chain update
 void integ_flush_pending(pfmds_ctx* c);
 // out[0]=KE(group) ; group sums for diagnostics: out[0..2]=sum F, [3..5]=sum m x, [6..8]=sum m v, [9]=sum m, [10]=max v^2

@@ -8,7 +8,6 @@
 //
 // FP64-pipe bound: see DESIGN.md for the per-pair operation counts the roofline uses.
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,16 +47,6 @@ __device__ __forceinline__ double split_sum(double v) {
     for (int o = SPLIT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// position gather of the rjl force pass: the non-coherent path for kernels that only read positions for their whole lifetime, plain
-// loads inside the persistent step kernel (persist.cuh), where other blocks rewrite the positions between its phases
-template <bool NC>
-__device__ __forceinline__ double4 ldpos(const double4* p) {
-#ifdef __CUDACC__
-    return NC ? ld256_nc(p) : ld256(p);
-#else
-    return *p;
-#endif
-}
 #define SMALL_SPLIT 8  // systems below pfmds_ctx::small_n atoms (runtime: PFMDS_SMALL_N) take the SPLIT kernels
 
 // per-block partial of the per-thread energy; the final sum is done by k_sum_partials in block order
@@ -74,8 +63,9 @@ __global__ void k_sum_partials(int n, const double* __restrict__ part, double sc
 
 // ---- lj : LennardJones.f90:23-69 ----------------------------------------------------------------
 template <bool F, bool E, int SPLIT>
-__device__ __forceinline__ void d_lj(const int t_, int N, const double4* pos, double4* frc, ListView lv, LJp P, BoxD box, double* part) {
-    const int t = t_, i = t / SPLIT, sub = t % SPLIT;
+__global__ void __launch_bounds__(FT) k_lj(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJp P, BoxD box,
+                                           double* part) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double e = 0, fx = 0, fy = 0, fz = 0;
     STAMP_MIN(2);
     int n = i < N ? lv.nnum[i] : 0;
@@ -108,19 +98,15 @@ __device__ __forceinline__ void d_lj(const int t_, int N, const double4* pos, do
     STAMP_MAX(3);
     if (E) store_partial(e, part);
 }
-template <bool F, bool E, int SPLIT>
-__global__ void __launch_bounds__(FT) k_lj(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJp P, BoxD box,
-                                           double* part) {
-    d_lj<F, E, SPLIT>(blockIdx.x * blockDim.x + threadIdx.x, N, pos, frc, lv, P, box, part);
-}
 
 // ---- lj1g : LennardJones_1g.f90:28-117, cut_off_poly.f90 ------------------------------------------
 // The reference visits each pair once (p <= lessnnum) and scatters +-F*dr to both atoms; with a
 // symmetric full list the same sum is a gather over all neighbours.  The switch derivative keeps the
 // reference's missing 1/(R2-R1) factor (cut_off_poly.f90:41).
 template <bool F, bool E, int SPLIT>
-__device__ __forceinline__ void d_lj1g(const int t_, int N, const double4* pos, double4* frc, ListView lv, LJ1Gp P, BoxD box, double* part) {
-    const int t = t_, i = t / SPLIT, sub = t % SPLIT;
+__global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJ1Gp P, BoxD box,
+                                             double* part) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double e = 0, fx = 0, fy = 0, fz = 0;
     STAMP_MIN(2);
     int n = i < N ? lv.nnum[i] : 0;
@@ -155,11 +141,6 @@ __device__ __forceinline__ void d_lj1g(const int t_, int N, const double4* pos, 
     }
     STAMP_MAX(3);
     if (E) store_partial(e, part);
-}
-template <bool F, bool E, int SPLIT>
-__global__ void __launch_bounds__(FT) k_lj1g(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJ1Gp P, BoxD box,
-                                             double* part) {
-    d_lj1g<F, E, SPLIT>(blockIdx.x * blockDim.x + threadIdx.x, N, pos, frc, lv, P, box, part);
 }
 
 // ---- rjl : RosatoGuillopeLegrand.f90:23-94 --------------------------------------------------------
@@ -595,8 +576,8 @@ __global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* 
 
 // small systems: SPLIT lanes per atom, plain loop (latency is hidden by the extra warps)
 template <bool E, int SPLIT, class CT>
-__device__ __forceinline__ void d_rjl_density_split(const int t_, int N, double4* pos, ListView lv, CT C, BoxD box, WrapC W, double* part) {
-    const int t = t_, i = t / SPLIT, sub = t % SPLIT;
+__global__ void __launch_bounds__(FT) k_rjl_density_split(int N, double4* pos, ListView lv, CT C, BoxD box, WrapC W, double* part) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double e = 0, sq = 0, sp = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
@@ -611,10 +592,6 @@ __device__ __forceinline__ void d_rjl_density_split(const int t_, int N, double4
         if (E) e = C.energy(sq, sp, ie);
     }
     if (E) store_partial(e, part);
-}
-template <bool E, int SPLIT, class CT>
-__global__ void __launch_bounds__(FT) k_rjl_density_split(int N, double4* pos, ListView lv, CT C, BoxD box, WrapC W, double* part) {
-    d_rjl_density_split<E, SPLIT, CT>(blockIdx.x * blockDim.x + threadIdx.x, N, pos, lv, C, box, W, part);
 }
 
 __device__ __forceinline__ void rjl_force_pair(const double4& pi, const double4& pj, const RjlC& C, const BoxD& box, int mhh, double& fx, double& fy,
@@ -670,22 +647,18 @@ __global__ void __launch_bounds__(FT, RJL_MINB) k_rjl_force(int N, const double4
     else add_force(frc, i, fx, fy, fz);
 }
 
-template <int SPLIT, class CT, bool NC = true>
-__device__ __forceinline__ void d_rjl_force_split(const int t_, int N, const double4* pos, double4* frc, ListView lv, CT C, BoxD box, WrapC W) {
-    const int t = t_, i = t / SPLIT, sub = t % SPLIT;
-    double fx = 0, fy = 0, fz = 0;
-    int n = i < N ? lv.nnum[i] : 0;
-    if (n > 0) {
-        const double4 pi = ldpos<NC>(&pos[i]);
-        for (int p = sub; p < n; p += SPLIT) rjl_force_pair(pi, ldpos<NC>(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, fx, fy, fz);
-    }
-    fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz);
-    if (n > 0 && sub == 0) add_force(frc, i, fx, fy, fz);
-}
 template <int SPLIT, class CT>
 __global__ void __launch_bounds__(FT) k_rjl_force_split(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CT C, BoxD box,
                                                         WrapC W) {
-    d_rjl_force_split<SPLIT, CT, true>(blockIdx.x * blockDim.x + threadIdx.x, N, pos, frc, lv, C, box, W);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
+    double fx = 0, fy = 0, fz = 0;
+    int n = i < N ? lv.nnum[i] : 0;
+    if (n > 0) {
+        const double4 pi = ld256_nc(&pos[i]);
+        for (int p = sub; p < n; p += SPLIT) rjl_force_pair(pi, ld256_nc(&pos[lv.nlist[(size_t)p * lv.stride + i]]), C, box, W.min_half_hi, fx, fy, fz);
+    }
+    fx = split_sum<SPLIT>(fx); fy = split_sum<SPLIT>(fy); fz = split_sum<SPLIT>(fz);
+    if (n > 0 && sub == 0) add_force(frc, i, fx, fy, fz);
 }
 
 // Force pass that also yields the interaction's energy (second generation only; steps that report their energies):
@@ -810,9 +783,10 @@ __device__ __forceinline__ double tb_G(double c1, const TBp& T) { return 1. + T.
 // in slot order by k_tb_reduce (deterministic, no atomics).
 // pass A: bond orders B(p,i) = (1 + a0 sum_{q!=p} f_c(r_q) G(theta_pq))^-delt, 0 for r_p >= R2  (:83-96).
 // Both B and B^(1/delt+1) = (1 + a0 zeta)^-(delt+1) are stored, from one logarithm: pass B then needs no pow().
-__device__ __forceinline__ void d_tb_bond(const int t_, const int p_, int N, const double4* pos, ListView lv, TBp T, BoxD box, double* B, double* Bx) {
-    int i = t_;
-    int p = p_;
+__global__ void __launch_bounds__(FT) k_tb_bond(int N, const double4* __restrict__ pos, ListView lv, TBp T, BoxD box, double* __restrict__ B,
+                                                double* __restrict__ Bx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y;
     if (i >= N) return;
     int n = lv.nnum[i];
     if (p >= n) return;
@@ -836,16 +810,13 @@ __device__ __forceinline__ void d_tb_bond(const int t_, const int p_, int N, con
     B[(size_t)p * lv.stride + i] = b;
     Bx[(size_t)p * lv.stride + i] = bx;
 }
-__global__ void __launch_bounds__(FT) k_tb_bond(int N, const double4* __restrict__ pos, ListView lv, TBp T, BoxD box, double* __restrict__ B,
-                                                double* __restrict__ Bx) {
-    d_tb_bond(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, N, pos, lv, T, box, B, Bx);
-}
 // pass B: forces (:99-146) and/or energy (:53-66) of one bond.  Bonds and partners beyond R2 contribute exactly
 // zero in the reference (f_cut = df_cut = 0, B = 0) and are skipped.
 template <bool F, bool E>
-__device__ __forceinline__ void d_tb_force(const int t_, const int p_, int N, const double4* pos, double4* fpart, ListView lv, TBp T, BoxD box, const double* B, const double* Bx, double* part) {
-    int i = t_;
-    int p = p_;
+__global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restrict__ pos, double4* __restrict__ fpart, ListView lv, TBp T, BoxD box,
+                                                 const double* __restrict__ B, const double* __restrict__ Bx, double* part) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y;
     double e = 0, fx = 0, fy = 0, fz = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (p < n) {
@@ -931,13 +902,8 @@ __device__ __forceinline__ void d_tb_force(const int t_, const int p_, int N, co
         if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
     }
 }
-template <bool F, bool E>
-__global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restrict__ pos, double4* __restrict__ fpart, ListView lv, TBp T, BoxD box,
-                                                 const double* __restrict__ B, const double* __restrict__ Bx, double* part) {
-    d_tb_force<F, E>(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, N, pos, fpart, lv, T, box, B, Bx, part);
-}
-__device__ __forceinline__ void d_tb_reduce(const int t_, int N, const double4* fpart, double4* frc, ListView lv) {
-    int i = t_;
+__global__ void __launch_bounds__(FT) k_tb_reduce(int N, const double4* __restrict__ fpart, double4* __restrict__ frc, ListView lv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int n = lv.nnum[i];
     if (n == 0) return;
@@ -948,13 +914,10 @@ __device__ __forceinline__ void d_tb_reduce(const int t_, int N, const double4* 
     }
     add_force(frc, i, fx, fy, fz);
 }
-__global__ void __launch_bounds__(FT) k_tb_reduce(int N, const double4* __restrict__ fpart, double4* __restrict__ frc, ListView lv) {
-    d_tb_reduce(blockIdx.x * blockDim.x + threadIdx.x, N, fpart, frc, lv);
-}
 
 // ---- graphene normals : graphenenorm.f90:38-56 ----------------------------------------------------
-__device__ __forceinline__ void d_normals(const int t_, int N, const double4* pos, ListView nn, BoxD box, int simplified, double4* gnorm) {
-    int i = t_;
+__global__ void k_normals(int N, const double4* __restrict__ pos, ListView nn, BoxD box, int simplified, double4* __restrict__ gnorm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     if (nn.nnum[i] != 3) return;
     if (simplified) { gnorm[i] = make_double4(0., 0., 1., 0.); return; }  // LennardJonesCosine.f90:62
@@ -969,9 +932,6 @@ __device__ __forceinline__ void d_normals(const int t_, int N, const double4* po
     double len = sqrt(dot(n, n));
     gnorm[i] = make_double4(n.x / len, n.y / len, n.z / len, 0.);
 }
-__global__ void k_normals(int N, const double4* __restrict__ pos, ListView nn, BoxD box, int simplified, double4* __restrict__ gnorm) {
-    d_normals(blockIdx.x * blockDim.x + threadIdx.x, N, pos, nn, box, simplified, gnorm);
-}
 
 // ---- ljc / morsec : LennardJonesCosine.f90, MorseCosine.f90 ---------------------------------------
 struct CosP { double pe, sig, a, r0, delt, R1, R2; };  // pe = 4 eps (ljc) or d (morsec)
@@ -985,8 +945,9 @@ __device__ __forceinline__ double cos_V2(double r, double r2, const CosP& P) {
 // the kernel also accumulates T_i = sum_p V2 V3 f_c /(n_i.dr) dr for the normal-derivative term.
 // Otherwise the owner is a metal atom and the normal is that of the carbon partner (:112-139).
 template <bool MORSE, bool GRAPHENE, bool F, bool E, int SPLIT>
-__device__ __forceinline__ void d_cos_direct(const int t_, int N, const double4* pos, double4* frc, ListView lv, CosP P, BoxD box, const double4* gnorm, double4* tvec, double* part) {
-    const int t = t_, i = t / SPLIT, sub = t % SPLIT;
+__global__ void __launch_bounds__(FT) k_cos_direct(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CosP P, BoxD box,
+                                                   const double4* __restrict__ gnorm, double4* __restrict__ tvec, double* part) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t / SPLIT, sub = t % SPLIT;
     double e = 0, fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (n > 0) {
@@ -1037,17 +998,13 @@ __device__ __forceinline__ void d_cos_direct(const int t_, int N, const double4*
     }
     if (E) store_partial(e, part);
 }
-template <bool MORSE, bool GRAPHENE, bool F, bool E, int SPLIT>
-__global__ void __launch_bounds__(FT) k_cos_direct(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, CosP P, BoxD box,
-                                                   const double4* __restrict__ gnorm, double4* __restrict__ tvec, double* part) {
-    d_cos_direct<MORSE, GRAPHENE, F, E, SPLIT>(blockIdx.x * blockDim.x + threadIdx.x, N, pos, frc, lv, P, box, gnorm, tvec, part);
-}
 // Normal-derivative term (LennardJonesCosine.f90:81-106): for each of the three nearest carbons j of
 // i, with i in slot l1 of j's row and l2,l3 the cyclic successors,
 //   F_i -= pref*delt * n_j * (T_j . (d12 (d23.d31) - d31 (d23.d12))) / (|d12|^2|d31|^2 - (d12.d31)^2)
 // where the reference's inner sum over j's metal neighbours has been collected into T_j.
-__device__ __forceinline__ void d_cos_indirect(const int t_, int N, const double4* pos, double4* frc, ListView nn, double pref_delt, BoxD box, const double4* gnorm, const double4* tvec) {
-    int i = t_;
+__global__ void __launch_bounds__(FT) k_cos_indirect(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView nn, double pref_delt,
+                                                     BoxD box, const double4* __restrict__ gnorm, const double4* __restrict__ tvec) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     if (nn.nnum[i] != 3) return;
     double fx = 0, fy = 0, fz = 0;
@@ -1071,10 +1028,6 @@ __device__ __forceinline__ void d_cos_indirect(const int t_, int N, const double
     }
     add_force(frc, i, fx, fy, fz);
 }
-__global__ void __launch_bounds__(FT) k_cos_indirect(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView nn, double pref_delt,
-                                                     BoxD box, const double4* __restrict__ gnorm, const double4* __restrict__ tvec) {
-    d_cos_indirect(blockIdx.x * blockDim.x + threadIdx.x, N, pos, frc, nn, pref_delt, box, gnorm, tvec);
-}
 
 // ------------------------------------------------------------------------------------------------
 // zero_forces touches the all_atoms group only (md_integrators.f90:147-163): forces of atoms outside it keep accumulating
@@ -1085,7 +1038,6 @@ __global__ void k_zero_group(int N, double4* __restrict__ frc, const uint32_t* _
 #if defined(__CUDACC__) && defined(PFMDS_STAMPS)
 STAMP_BIND_FN(forces_stamps_bind)
 #endif
-#include "persist.cuh"  // k_persist: the bodies above, phase by phase, in one cooperative launch
 #ifdef PFMDS_HAVE_CTX  // ---- launchers (host side of the library) ----------------------------------------
 void forces_zero(pfmds_ctx* c) {  // zero_forces, md_integrators.f90:147-163
     if (c->first_overwrites && c->N >= c->small_n) return;  // the first force kernel stores instead of accumulating
@@ -1318,141 +1270,4 @@ void energy_interaction(pfmds_ctx* c, int k) {  // energy(), md_interactions.f90
     if (c->slab) slab_allreduce_sum(c, c->energy + k, 1);
     CK(cudaGetLastError());
 }
-
-// ---- persistent step kernel of small systems (persist.cuh) ---------------------------------------------------------------------
-#ifdef __CUDACC__
-static bool persist_needs_full(pfmds_ctx* c) {
-    for (auto& it : c->inter) if (it.kind == K_TB || it.kind == K_LJC || it.kind == K_MORSEC) return true;
-    return false;
-}
-// Static conditions, decided once per context: per-interaction force buffers in use (small system, alone on its device), only
-// interactions k_persist has bodies for, second-generation rjl, thermostat chains that fit its shared-memory copy, a device that
-// can hold the grid.  The per-step conditions (no rebuild, no energies, steady thermostat state) are the caller's (capi.cu).
-bool persist_usable(pfmds_ctx* c, bool nvt) {
-    if (nvt && !c->nhc_fusable) return false;
-    if (c->persist_state >= 0) return c->persist_state == 1;
-    c->persist_state = 0;
-    if (!c->fbuf_on || c->slab || !c->changes.empty() || c->invert_z || !c->persist_enabled) return false;
-    if (c->N >= c->small_n || (size_t)c->N > (size_t)RED_BLOCKS * IT || c->fbuf.size() > FBUF_MAX) return false;
-    size_t nops = 0;
-    for (auto& it : c->inter) {
-        switch (it.kind) {
-        case K_LJ: nops += 2; break;
-        case K_LJ1G: nops += 1; break;
-        case K_RJL: if (c->rjl_gen != 2 || !rjl_gen2_ok(it.rjl, c->box)) return false; nops += 2; break;
-        case K_TB: nops += 3; break;
-        case K_LJC: case K_MORSEC: nops += 4; break;
-        default: return false;
-        }
-    }
-    if (nops > P_MAXOPS) return false;
-    for (auto& t : c->nhc) if (t.M > NHC_MLOC) return false;
-    int coop = 0, nsm = 0, per_sm = 0;
-    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->dev) != cudaSuccess || !coop) return false;
-    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev) != cudaSuccess) return false;
-    const cudaError_t oe = persist_needs_full(c) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persist<true>, PB, 0)
-                                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persist<false>, PB, 0);
-    if (oe != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
-    const int want = c->persist_bpsm > 0 && c->persist_bpsm < per_sm ? c->persist_bpsm : per_sm;
-    c->persist_grid = nsm * want;
-    if (cudaMalloc(&c->pbar, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); return false; }
-    c->persist_state = 1;
-    return true;
-}
-
-// the owner list of `l` (slots with a non-empty row), rebuilt after every build of the list
-static void persist_owners(pfmds_ctx* c, NList& l) {
-    if (!l.owners) {
-        CK(cudaMalloc(&l.owners, sizeof(int) * c->stride));
-        CK(cudaMalloc(&l.n_owners, sizeof(int)));
-    }
-    if (l.owners_valid) return;
-    LAUNCH((k_owner_compact), 1, 1024, c->st, c->N, l.nnum, l.owners, l.n_owners);
-    c->launches += 1;
-    l.owners_valid = true;
-}
-
-// `nsteps` plain steps (no rebuild, no momentum removal, no energies), nvt or nve, in one launch.  NVT: the entry state is the
-// fused path's steady state (pending scale and cached KE valid; the caller has run k_nhc_open if the pending scale does not contain
-// the opening half step yet); last_mode 3 leaves the chains as k_nhc_close(also_open) does, 2 as the plain closing half step.
-void persist_run(pfmds_ctx* c, bool nvt, double dt, int nsteps, int last_mode) {
-    PArgs A{};
-    A.N = c->N; A.nvt = nvt ? 1 : 0; A.last_mode = last_mode;
-    A.pos = c->pos; A.vel = c->vel; A.frc = c->frc; A.gmask = c->gmask; A.orig = c->orig;
-    A.ball = 1u << (c->all_atoms - 1); A.bxyz = 1u << (c->xyz_moving - 1); A.bz = 1u << (c->z_moving - 1); A.zero_all = (int)c->zero_all;
-    A.dt = dt; A.box = c->box; A.W = wrap_consts(c->box); A.err = c->err;
-    A.F.n = (int)c->fbuf.size();
-    for (int t = 0; t < A.F.n; ++t) A.F.b[t] = c->fbuf[(size_t)t];
-    if (A.nvt) {
-        A.P.n = (int)c->nhc.size();
-        for (int k = 0; k < A.P.n; ++k) {
-            A.P.bit[k] = 1u << (c->nhc[k].group - 1); A.P.state[k] = c->nhc[k].state; A.P.M[k] = c->nhc[k].M; A.P.L[k] = c->nhc[k].L; A.P.T[k] = c->nhc[k].temperature;
-        }
-    }
-    A.part = c->part; A.bar = c->pbar;
-    const size_t st = c->stride;
-    int nops = 0;
-    auto add = [&](int k, int stage, int geom, NList& l) -> POp& {
-        persist_owners(c, l);
-        POp& o = A.ops[nops++];
-        o.kind = k; o.stage = stage; o.geom = geom; o.maxn = l.maxn;
-        o.lv = l.view(st); o.owners = l.owners; o.n_owners = l.n_owners;
-        A.stage_used[stage] = 1;
-        return o;
-    };
-    size_t b = 0;  // next force buffer, in summation order: the order of compute_forces (capi.cu)
-    for (auto& it : c->inter) {
-        switch (it.kind) {
-        case K_LJ: {
-            POp& o1 = add(PO_LJ, 0, PG_SPLIT, it.nl[0]); o1.u.lj = it.lj; o1.out = c->fbuf[b];
-            POp& o2 = add(PO_LJ, 0, PG_SPLIT, it.nl[1]); o2.u.lj = it.lj; o2.out = c->fbuf[b + 1];
-            b += 2;
-            break;
-        }
-        case K_LJ1G: { POp& o = add(PO_LJ1G, 0, PG_SPLIT, it.nl[0]); o.u.lj1g = it.lj1g; o.out = c->fbuf[b]; b += 1; break; }
-        case K_RJL: {
-            POp& d = add(PO_RJL_D, 0, PG_SPLIT, it.nl[0]); d.u.rd = rjl_dens_consts(it.rjl);
-            POp& f = add(PO_RJL_F, 1, PG_SPLIT, it.nl[0]); f.u.rf = rjl_force_consts(it.rjl); f.out = c->fbuf[b];
-            b += 1;
-            break;
-        }
-        case K_TB: {
-            POp& o1 = add(PO_TB_BOND, 0, PG_BOND, it.nl[0]); o1.u.tb = it.tb; o1.aux = it.aux; o1.aux2 = it.aux2;
-            POp& o2 = add(PO_TB_FORCE, 1, PG_BOND, it.nl[0]); o2.u.tb = it.tb; o2.aux = it.aux; o2.aux2 = it.aux2; o2.fpart = it.fpart;
-            POp& o3 = add(PO_TB_REDUCE, 2, PG_ATOM, it.nl[0]); o3.fpart = it.fpart; o3.out = c->fbuf[b];
-            b += 1;
-            break;
-        }
-        case K_LJC: case K_MORSEC: {
-            const bool morse = it.kind == K_MORSEC;
-            const int simp = morse ? it.mor.simplified : it.ljc.simplified;
-            const CosP P = cosp_of(it);
-            POp& n = add(PO_NORMALS, 0, PG_ATOM, it.nl[2]); n.simplified = simp; n.gnorm = it.gnorm;
-            POp& g = add(PO_COS_G, 1, PG_SPLIT, it.nl[0]); g.u.cos = P; g.morse = morse; g.gnorm = it.gnorm; g.tvec = it.tvec; g.out = c->fbuf[b];
-            POp& m = add(PO_COS_M, 1, PG_SPLIT, it.nl[1]); m.u.cos = P; m.morse = morse; m.gnorm = it.gnorm; m.tvec = it.tvec; m.out = c->fbuf[b + 1];
-            if (!simp) {
-                POp& x = add(PO_COS_IND, 2, PG_ATOM, it.nl[2]); x.pref = (morse ? 2. : 1.) * P.pe * P.delt; x.gnorm = it.gnorm; x.tvec = it.tvec; x.out = c->fbuf[b];
-            }
-            b += 2;
-            break;
-        }
-        }
-    }
-    A.nops = nops;
-    const bool full = persist_needs_full(c);
-    for (int done = 0; done < nsteps;) {
-        const int m = nsteps - done < P_MAX_STEPS ? nsteps - done : P_MAX_STEPS;
-        A.nsteps = m;
-        A.last_mode = done + m < nsteps ? 3 : last_mode;
-        CK(cudaMemsetAsync(c->pbar, 0, sizeof(unsigned int), c->st));
-        void* args[] = {(void*)&A};
-        CK(cudaLaunchCooperativeKernel(full ? (const void*)k_persist<true> : (const void*)k_persist<false>, dim3((unsigned)c->persist_grid), dim3(PB), args, 0, c->st));
-        c->launches += 1;
-        done += m;
-    }
-}
-#else   // host replay of the test suite: no grid barrier, the step-by-step path is the only one
-bool persist_usable(pfmds_ctx*, bool) { return false; }
-void persist_run(pfmds_ctx*, bool, double, int, int) {}
-#endif
 #endif  // PFMDS_HAVE_CTX

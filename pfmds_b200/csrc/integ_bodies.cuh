@@ -1,6 +1,6 @@
-// pfmds_b200 -- per-atom bodies of the integrator kernels that the persistent small-system kernel (persist.cuh) runs too.
-// integrate.cu wraps each in its __global__ kernel (index from blockIdx / threadIdx); persist.cuh calls the same functions with
-// virtual block indices, so both paths execute the same statements on the same numbers: bit-identical results.
+// pfmds_b200 -- per-atom bodies of the integrator kernels (integrate.cu wraps each in its __global__ kernel: index from blockIdx /
+// threadIdx).  Kept apart from the launch geometry so that another driver of the same statements -- the persistent step kernel tried
+// in round 2, DESIGN section 12 -- executes them on the same numbers.
 #pragma once
 #include "common.cuh"
 

@@ -743,7 +743,10 @@ void nl_build(pfmds_ctx* c, NList& l) {
 #ifdef PFMDS_COOP
     // cell-tiled build: large, dense systems in cell order, three or more cells per axis, FP32 prefilter usable
     // (sparse cells leave most lanes of a cell's warp without an atom: below 12 atoms per cell the thread-per-atom build is faster, measured on the LJ fluid)
-    if (c->nl_cell && !warp_per_atom && c->identity_order && pf.on && g.n[0] >= 3 && g.n[1] >= 3 && g.n[2] >= 3 && (double)N >= 12. * c->ncells) {
+    // (slab mode: the grid spans the whole box, this rank's atoms sit in its 1 / nranks share of the cells -- with the global count the
+    //  8-GPU runs of round 2 fell back to k_build_mask: 0.092 against 0.065 ms/step at 2 GPUs)
+    const double cells_here = c->slab ? (double)c->ncells / slab_nranks(c) : (double)c->ncells;
+    if (c->nl_cell && !warp_per_atom && c->identity_order && pf.on && g.n[0] >= 3 && g.n[1] >= 3 && g.n[2] >= 3 && (double)N >= 12. * cells_here) {
         const int nbc = (c->ncells + CB_WARPS - 1) / CB_WARPS;
         // the partner-group test can be dropped when every atom is in group 2 (slab mode: from the global group sizes)
         const bool chk = c->slab ? !(l.g2 >= 1 && l.g2 <= (int)c->group_count.size() && c->group_count[(size_t)l.g2 - 1] == slab_n_global(c))
@@ -765,7 +768,6 @@ void nl_build(pfmds_ctx* c, NList& l) {
 #undef CELL_ARGS
         c->launches += 1;
         l.built = true;
-        l.owners_valid = false;
         CK(cudaGetLastError());
         return;
     }
@@ -786,7 +788,6 @@ void nl_build(pfmds_ctx* c, NList& l) {
 #undef BUILD_ARGS
     c->launches += 1;
     l.built = true;
-    l.owners_valid = false;
     CK(cudaGetLastError());
 }
 #endif  // PFMDS_HAVE_CTX
@@ -823,7 +824,6 @@ void nl_nearest3_from(pfmds_ctx* c, NList& nn, const NList& src) {
     LAUNCH((k_nearest3), nb, T, c->st, N, c->pos, c->orig, src.view(c->stride), c->box, nn.rcut, c->stride, nn.nlist, nn.nnum, c->err);
     c->launches += 1;
     nn.built = true;
-    nn.owners_valid = false;
     CK(cudaGetLastError());
 }
 #endif  // PFMDS_HAVE_CTX

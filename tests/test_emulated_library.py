@@ -167,6 +167,33 @@ def test_pipelined_lj1g_variant(monkeypatch, flavour):
     assert np.abs(b.download()[0] - o.download()[0]).max() < 1e-10
 
 
+@pytest.mark.parametrize("integ", ["nvt", "nve"])
+def test_multi_step_graphs(monkeypatch, integ):
+    """Steady-state steps replayed one, four (default) and seven per graph launch (capi.cu graph_run_ok; the replay records the captured
+    launches as closures): the same bits, also when a logged advance cuts the runs short, and the oracle's trajectory."""
+    from util import oracle
+    case = inputs.ab_gas(n_side=8, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, period=20)
+    res = []
+    for gs in ("1", "4", "7"):
+        monkeypatch.setenv("PFMDS_GRAPH_STEPS", gs)
+        e = emu_gpu(case)
+        e.advance(integ, 0.5, 0, 1)
+        e.advance(integ, 0.5, 1, 45)
+        rows = e.advance_logged(integ, 0.5, 46, 24, log_period=8)
+        res.append((e.download(), [e.get_nhc(k) for k in range(len(case["nhc"]))], rows))
+        e.close()
+    (pa, va, fa), na, ra = res[0]
+    for (pb, vb, fb), nb, rb in res[1:]:
+        assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(fa, fb)
+        assert all(np.array_equal(x, y) for ta, tb in zip(na, nb) for x, y in zip(ta, tb))
+        assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
+    o = oracle(case)
+    o.advance(integ, 0.5, 0, 1)
+    o.advance(integ, 0.5, 1, 45)
+    o.advance(integ, 0.5, 46, 24)
+    assert np.abs(pa - o.download()[0]).max() < 1e-9
+
+
 def test_replay_identifies_itself():
     import ctypes as C
     lib = C.CDLL(B.lib)

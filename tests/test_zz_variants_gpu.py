@@ -79,3 +79,28 @@ def test_small_system_branches_give_the_sequential_results():
         else:
             assert np.abs(pa - pb).max() < 1e-12 and rel_err(vb, va) < 1e-11 and rel_err(fb, fa) < 1e-11
         assert np.allclose(ea[0], eb[0], rtol=1e-11, atol=0)
+
+
+def test_multi_step_graphs_give_the_single_step_results():
+    """Runs of steady-state steps of small systems are replayed four steps per graph launch (PFMDS_GRAPH_STEPS, capi.cu
+    graph_run_ok): same kernels in the same order as one graph per step, so every bit must be the same -- positions, velocities,
+    forces, thermostat chains and the rows of a logged advance whose log period cuts the runs short."""
+    import gc
+    for case, integ, dt in ((inputs.ab_gas(n_side=8, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, period=20), "nvt", 0.5),
+                            (inputs.graphene_on_cu_small(interface="ljc", period=10), "nvt", 1.0),
+                            (inputs.ab_gas(n_side=8, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, period=20), "nve", 0.5)):
+        res = []
+        for env in ({"PFMDS_GRAPH_STEPS": "1"}, {}, {"PFMDS_GRAPH_STEPS": "7"}):
+            gc.collect()
+            e = gpu(case, env)
+            e.advance(integ, dt, 0, 1)
+            e.advance(integ, dt, 1, 60)
+            rows = e.advance_logged(integ, dt, 61, 40, log_period=8)
+            res.append((e.download(), [e.get_nhc(k) for k in range(len(case["nhc"]))], rows))
+            e.close()
+        (pa, va, fa), na, ra = res[0]
+        assert np.abs(fa).max() > 1e-3
+        for (pb, vb, fb), nb, rb in res[1:]:
+            assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(fa, fb)
+            assert all(np.array_equal(x, y) for ta, tb in zip(na, nb) for x, y in zip(ta, tb))
+            assert all(np.array_equal(x, y) for x, y in zip(ra, rb))

@@ -39,49 +39,7 @@ def build():
     print(LIB)
 
 
-PNAMES = {0: "step start (block 0)", 1: "kick+drift done (block 0)", 2: "barrier passed", 3: "stage 0 done (last block)", 4: "stage 1 done (last block)",
-          5: "stage 2 done (last block)", 6: "last stage barrier passed", 7: "sum+kick+KE partials done (block 0)", 8: "barrier passed",
-          9: "partials summed + chain update done"}
-
-
-def run_persist(workload="ab_gas", steps=1000):
-    """The same stamps inside the persistent step kernel (k_persist): phase boundaries as block 0 sees them, stage ends as the last block does."""
-    import bench
-    from pfmds_b200 import engine
-    case, integrator, _ = bench.build_case(workload, 1, 1000)
-    dt = case["integrators"][0][1]
-    eng = engine.configure(case, lib_path=LIB)
-    lib = eng._lib
-    eng.advance(integrator, dt, 0, 41)
-    eng.synchronize()
-    assert lib.pfmds_debug_stamps_begin() == 0
-    eng.advance(integrator, dt, 41, steps)
-    eng.synchronize()
-    buf = np.zeros(1 + STEPS * 2 * SLOTS, np.uint64)
-    lib.pfmds_debug_stamps_read(buf.ctypes.data_as(C.c_void_p))
-    n = int(buf[0])
-    st = buf[1:].reshape(STEPS, 2, SLOTS)[:n].astype(np.int64)
-    mins, maxs = st[:, 0, :], st[:, 1, :]
-    t = np.zeros((n, 10), np.float64)
-    for s in range(10):
-        t[:, s] = (mins if s == 0 else maxs)[:, s]
-    used = [s for s in range(10) if np.median(t[:, s]) > 0 and np.median(t[:, s]) < 2 ** 62]
-    ok = np.all(t[:, used] > 0, axis=1) & (mins[:, 0] < (1 << 62))
-    print("workload %s (persistent kernel): %d steps stamped, %d complete, launches %d" % (workload, n, int(ok.sum()), eng.launch_count()))
-    prev = used[0]
-    for s in used[1:]:
-        d = (t[:, s] - t[:, prev])[ok]
-        d = d[(d > -1e5) & (d < 1e6)]
-        print("  %-42s -> %-42s mean %7.2f us  median %7.2f us" % (PNAMES[prev], PNAMES[s], d.mean() / 1e3, np.median(d) / 1e3))
-        prev = s
-    d = np.diff(t[:, 0])
-    d = d[(d > 0) & (d < 2e5)]
-    print("  step start -> next step start: mean %.2f us  median %.2f us" % (d.mean() / 1e3, np.median(d) / 1e3))
-    eng.close()
-
-
 def run(workload="ab_gas", steps=1000):
-    os.environ["PFMDS_PERSIST"] = "0"   # the step-by-step (CUDA graph) path
     import bench
     from pfmds_b200 import engine
     case, integrator, _ = bench.build_case(workload, 1, 1000)
@@ -121,7 +79,5 @@ def run(workload="ab_gas", steps=1000):
 if __name__ == "__main__":
     if sys.argv[1] == "build":
         build()
-    elif sys.argv[1] == "persist":
-        run_persist(*(sys.argv[2:3] or ["ab_gas"]))
     else:
         run(*(sys.argv[2:3] or ["ab_gas"]))
