@@ -64,6 +64,7 @@ void read_env(pfmds_ctx* c, int n_atoms, bool slab) {
     c->nl_mask = env_int("PFMDS_NL_MASK", 1) != 0;
     c->nl_cell = env_int("PFMDS_NL_CELL", 1) != 0;
     c->pre_open_enabled = env_int("PFMDS_PRE_OPEN", 1) != 0;
+    c->graph_rebuilds = env_int("PFMDS_GRAPH_REBUILDS", 1) != 0;
     c->graph_steps = env_int("PFMDS_GRAPH_STEPS", 4);
     if (c->graph_steps < 1 || c->graph_steps > 64) c->graph_steps = 1;
     // 2 is the default: the third generation (node-table exponentials) removes 13 of 43 FP64 instructions per pair but its table
@@ -882,11 +883,17 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
     // the thermostat's opening half step of step s+1 can ride in the closing kernel of step s when s+1 follows inside this call,
     // nothing reads or regroups the chains in between (no log row, no deposition) and the fused NVT path is in use
     c->pre_open = next_follows && kind == PFMDS_NVT && c->nhc_fusable && !c->slab && c->changes.empty() && !with_energy && c->pre_open_enabled;
-    bool rebuild = false;
+    bool rebuild = false, rebuild_all = true, built_all = true;
     for (auto& it : c->inter)
-        for (int j = 0; j < it.nl_n; ++j) rebuild |= (s % it.nl[j].period == 0) || !it.nl[j].built;
+        for (int j = 0; j < it.nl_n; ++j) {
+            const bool rb = (s % it.nl[j].period == 0) || !it.nl[j].built;
+            rebuild |= rb; rebuild_all &= rb; built_all &= it.nl[j].built;
+        }
     const bool regrouped = apply_group_changes(c, s);
-    const bool graphable = !regrouped && c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && !rebuild &&
+    // a step that rebuilds every list (binning, cell re-sort into the other half of the double-buffered state, all builds) is a fixed
+    // sequence of launches too: its graph is keyed by the buffer it starts from, the replay redoes the host's pointer swap
+    const bool rebuild_ok = !rebuild || (rebuild_all && built_all && c->graph_rebuilds && nrep == 1);
+    const bool graphable = !regrouped && c->use_graphs && !c->slab && !c->prof_on && !c->timers_on && s != 0 && s != first && rebuild_ok &&
                            (s % c->zero_momentum_period != 0) && !with_energy;
     if (!graphable) {
         do_step(c, s, kind, dt, s == first, with_energy);
@@ -900,9 +907,9 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
     pfmds_ctx::StepGraph* g = nullptr;
     for (auto& e : c->graphs)
         if (e.kind == kind && e.dt == dt && e.pos == (const void*)c->pos && e.pending == c->nhc_pending && e.ke_valid == c->nhc_ke_valid &&
-            e.opened == c->nhc_opened && e.pre_open == c->pre_open && e.alone == (g_live_contexts[c->dev & 63].load() <= 1) && e.nsteps == nrep) g = &e;
+            e.opened == c->nhc_opened && e.pre_open == c->pre_open && e.alone == (g_live_contexts[c->dev & 63].load() <= 1) && e.nsteps == nrep && e.rebuild == rebuild) g = &e;
     if (!g) {
-        pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, c->nhc_opened, c->pre_open, g_live_contexts[c->dev & 63].load() <= 1, nullptr, 0, nrep};
+        pfmds_ctx::StepGraph e{kind, dt, (const void*)c->pos, c->nhc_pending, c->nhc_ke_valid, c->nhc_opened, c->pre_open, g_live_contexts[c->dev & 63].load() <= 1, nullptr, 0, nrep, rebuild};
         const long long l0 = c->launches;
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
@@ -914,7 +921,7 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
         c->launches = l0;
         // capturing ran the host-side bookkeeping of one step: the flags now describe the state AFTER a step; a step
         // is only graphable again from the same entry state, which holds in steady state (checked by the key)
-        if (c->graphs.size() >= 12) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+        if (c->graphs.size() >= 16) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
         c->graphs.push_back(e);
         g = &c->graphs.back();
         CK(cudaGraphLaunch(g->exec, c->st));
@@ -924,6 +931,10 @@ static void run_step(pfmds_ctx* c, int s, int first, int kind, double dt, bool w
     CK(cudaGraphLaunch(g->exec, c->st));
     c->launches += g->launches;
     c->energy_valid = false;
+    if (rebuild) {   // nl_bin_atoms(reorder): the re-sorted state is in the other buffers
+        std::swap(c->pos, c->pos2); std::swap(c->vel, c->vel2); std::swap(c->gmask, c->gmask2); std::swap(c->orig, c->orig2);
+        c->identity_order = true;
+    }
     // host-side bookkeeping of do_step for this integrator
     if (kind == PFMDS_NVT && c->nhc_fusable) { c->nhc_pending = true; c->nhc_ke_valid = true; c->nhc_opened = c->pre_open; }
     else { c->nhc_pending = false; c->nhc_ke_valid = false; c->nhc_opened = false; }

@@ -93,9 +93,10 @@ struct pfmds_ctx {
     int* newslot = nullptr;  // old slot -> new slot of the last cell re-sort
     std::vector<long long> group_count;  // slab mode: global size of every group
     // CUDA graphs of the steady-state step (small systems are launch-latency bound), keyed by what is baked in
-    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid, opened, pre_open, alone; cudaGraphExec_t exec; long long launches; int nsteps; };
+    struct StepGraph { int kind; double dt; const void* pos; bool pending, ke_valid, opened, pre_open, alone; cudaGraphExec_t exec; long long launches; int nsteps; bool rebuild; };
     std::vector<StepGraph> graphs;
     bool use_graphs = false;
+    bool graph_rebuilds = true;     // steps that rebuild EVERY list (cell re-sort included) are replayed from graphs too, one per direction of the state's double buffer (PFMDS_GRAPH_REBUILDS=0: launched one by one)
     int graph_steps = 4;            // steady-state steps per graph launch where a run of them allows it (PFMDS_GRAPH_STEPS; graph-to-graph gap 4.4 us, node-to-node 2.3 us: tools/stamps_probe.py)
     int rjl_gen = 2;                // rjl pair routines: 2 = analytic short forms (default), 3 = node-table exponentials (measured slower: L1-bound), 1 = first generation (PFMDS_RJL_GEN)
     bool nl_mask = true;            // thread-per-atom list build with the FP32 prefilter and the exact test in separate loops (measured 8 % faster, BENCH_r01); PFMDS_NL_MASK=0: k_build

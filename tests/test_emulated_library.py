@@ -176,6 +176,7 @@ def test_multi_step_graphs(monkeypatch, integ):
     res = []
     for gs in ("1", "4", "7"):
         monkeypatch.setenv("PFMDS_GRAPH_STEPS", gs)
+        monkeypatch.setenv("PFMDS_GRAPH_REBUILDS", "0" if gs == "1" else "1")   # rebuild steps kernel by kernel / replayed from their two graphs
         e = emu_gpu(case)
         e.advance(integ, 0.5, 0, 1)
         e.advance(integ, 0.5, 1, 45)

@@ -83,14 +83,16 @@ def test_small_system_branches_give_the_sequential_results():
 
 def test_multi_step_graphs_give_the_single_step_results():
     """Runs of steady-state steps of small systems are replayed four steps per graph launch (PFMDS_GRAPH_STEPS, capi.cu
-    graph_run_ok): same kernels in the same order as one graph per step, so every bit must be the same -- positions, velocities,
-    forces, thermostat chains and the rows of a logged advance whose log period cuts the runs short."""
+    graph_run_ok) and the steps that rebuild every list are replayed from graphs as well (one per half of the double-buffered state,
+    PFMDS_GRAPH_REBUILDS): same kernels in the same order as one graph per step, so every bit must be the same -- positions,
+    velocities, forces, thermostat chains and the rows of a logged advance whose log period cuts the runs short."""
     import gc
     for case, integ, dt in ((inputs.ab_gas(n_side=8, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, period=20), "nvt", 0.5),
                             (inputs.graphene_on_cu_small(interface="ljc", period=10), "nvt", 1.0),
                             (inputs.ab_gas(n_side=8, cap_aa=80, cap_ab=40, cap_ba=80, cap_bb=24, period=20), "nve", 0.5)):
         res = []
-        for env in ({"PFMDS_GRAPH_STEPS": "1"}, {}, {"PFMDS_GRAPH_STEPS": "7"}):
+        # (first: one graph per steady-state step and the rebuild steps launched kernel by kernel, as in round 1)
+        for env in ({"PFMDS_GRAPH_STEPS": "1", "PFMDS_GRAPH_REBUILDS": "0"}, {}, {"PFMDS_GRAPH_STEPS": "7"}):
             gc.collect()
             e = gpu(case, env)
             e.advance(integ, dt, 0, 1)
