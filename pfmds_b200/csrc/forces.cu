@@ -19,7 +19,9 @@
 #endif
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x; } while (0)
-#define FT 128  // threads per block for the force kernels
+#ifndef FT
+#define FT 128  // threads per block for the force kernels (tools/rjl_variants.py builds other sizes for A/B runs)
+#endif
 
 struct Vec { double x, y, z; };
 __device__ __forceinline__ double dot(const Vec& a, const Vec& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -532,7 +534,7 @@ struct RowWalk {
 };
 
 #ifndef RJL_MINB_D
-#define RJL_MINB_D RJL_MINB
+#define RJL_MINB_D 9  // density pass: 54 registers without a spill, 36 resident warps: 0.2769 -> 0.2722 ms per launch (tools/rjl_variants.py, B200; 6, 7, 8: 0.277)
 #endif
 template <bool E, class CT>  // CT = RjlC (first generation) or RjlD (second generation, below): picks the pair routine
 __global__ void __launch_bounds__(FT, RJL_MINB_D) k_rjl_density(int N, double4* pos, ListView lv, CT C, BoxD box, WrapC W, double* part, SlabDev S) {

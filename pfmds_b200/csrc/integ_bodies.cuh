@@ -13,11 +13,13 @@ __device__ __forceinline__ bool outside(double x, double L) { return !(x > (0. -
 __device__ __forceinline__ void d_kick_drift(int i, int N, double4* pos, double4* vel, const double4* frc, const uint32_t* gmask, const int* orig,
                                              uint32_t bxyz, uint32_t bz, double ts1, double ts2, const BoxD& box, int* err) {
     if (i >= N) return;
+    // the three records are requested together with the mask, not after it: one round trip to memory per atom instead of two
+    // (these kernels are latency bound: ncu, 3.3 TB/s at 45 % of the warp slots with the loads behind the mask test)
     uint32_t g = gmask[i];
+    double4 p = pos[i], v = vel[i], f = frc[i];
     if (g & PFMDS_GHOST) return;
     bool mx = g & bxyz, mz = g & bz;
     if (!mx && !mz) return;
-    double4 p = pos[i], v = vel[i], f = frc[i];
     if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
     if (mx) {
         v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
@@ -41,16 +43,17 @@ __device__ __forceinline__ void d_kick_drift_nvt(int i, int N, double4* pos, dou
                                                  uint32_t bxyz, uint32_t bz, double ts1, double ts2, const BoxD& box, const NhcPack& P, int* err,
                                                  const SlabDev& S, bool& pushed) {
     uint32_t g = i < N ? gmask[i] : PFMDS_GHOST;
+    // requested together with the mask (see d_kick_drift); slots past N are not read
+    double4 v = make_double4(0., 0., 0., 0.), p = v, f = v;
+    if (i < N) { v = vel[i]; p = pos[i]; f = frc[i]; }
     bool mx = g & bxyz, mz = g & bz;
     double sc = 1.0;
     bool th = false;
     for (int k = 0; k < P.n; ++k)
         if (g & P.bit[k]) { sc = P.state[k][3 * P.M[k] + 2]; th = true; }
     if (!(g & PFMDS_GHOST) && (mx || mz || th)) {  // one exit point: the kernel's slab_signal() holds a block barrier
-        double4 v = vel[i];
         v.x *= sc; v.y *= sc; v.z *= sc;
         if (mx || mz) {
-            double4 p = pos[i], f = frc[i];
             if (outside(p.x, box.L[0]) || outside(p.y, box.L[1]) || outside(p.z, box.L[2])) raise_error(err, E_OUT_OF_CELL, orig[i], 0);
             if (mx) {
                 v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;

@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(IT) k_kick(int N, double4* __restrict__ vel, c
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t g = gmask[i];
+    double4 v = vel[i], f = frc[i];   // requested together with the mask (integ_bodies.cuh d_kick_drift)
     if (g & PFMDS_GHOST) return;
     bool mx = g & bxyz, mz = g & bz;
     if (!mx && !mz) return;
-    double4 v = vel[i], f = frc[i];
     if (mx) {
         v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
         v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
@@ -275,27 +275,38 @@ __global__ void __launch_bounds__(IT) k_kick_ke(int N, double4* __restrict__ vel
                                                 uint32_t bxyz, uint32_t bz, double ts2, NhcPack P, double* __restrict__ part) {
     double ke[NHC_MAXF];
     for (int k = 0; k < NHC_MAXF; ++k) ke[k] = 0.;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        uint32_t g = gmask[i];
-        if (g & PFMDS_GHOST) continue;
-        bool mx = g & bxyz, mz = g & bz;
-        bool th = false;
-        for (int k = 0; k < P.n; ++k) th |= (g & P.bit[k]) != 0;
-        if (!mx && !mz && !th) continue;
-        double4 v = vel[i];
-        if (mx || mz) {
-            double4 f = frc[i];
-            if (mx) {
-                v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
-                v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
-                v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+    // fixed grid (RED_BLOCKS: the order of the partial sums), so a thread walks several atoms: the records of the next one are
+    // requested before the current one is worked on (the loop was a chain of round trips to memory, one per atom)
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t g = 0;
+    double4 v = make_double4(0., 0., 0., 0.), f = v;
+    if (i < N) { g = gmask[i]; v = vel[i]; f = frc[i]; }
+    while (i < N) {
+        const int in = i + stride;
+        uint32_t g2 = 0;
+        double4 v2 = make_double4(0., 0., 0., 0.), f2 = v2;
+        if (in < N) { g2 = gmask[in]; v2 = vel[in]; f2 = frc[in]; }
+        do {
+            if (g & PFMDS_GHOST) break;
+            bool mx = g & bxyz, mz = g & bz;
+            bool th = false;
+            for (int k = 0; k < P.n; ++k) th |= (g & P.bit[k]) != 0;
+            if (!mx && !mz && !th) break;
+            if (mx || mz) {
+                if (mx) {
+                    v.x = v.x + f.x / v.w / PFMDS_MASS_COEF * ts2;
+                    v.y = v.y + f.y / v.w / PFMDS_MASS_COEF * ts2;
+                    v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+                }
+                if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
+                vel[i] = v;
             }
-            if (mz) v.z = v.z + f.z / v.w / PFMDS_MASS_COEF * ts2;
-            vel[i] = v;
-        }
-        double e = v.w * (v.x * v.x + v.y * v.y + v.z * v.z) / 2 * PFMDS_MASS_COEF;
-        for (int k = 0; k < P.n; ++k)
-            if (g & P.bit[k]) ke[k] += e;
+            double e = v.w * (v.x * v.x + v.y * v.y + v.z * v.z) / 2 * PFMDS_MASS_COEF;
+            for (int k = 0; k < P.n; ++k)
+                if (g & P.bit[k]) ke[k] += e;
+        } while (false);
+        i = in; g = g2; v = v2; f = f2;
     }
     for (int k = 0; k < P.n; ++k) {
         double s = block_sum(ke[k]);
