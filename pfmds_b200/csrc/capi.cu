@@ -364,7 +364,8 @@ void finalize(pfmds_ctx* c) {
             c->fbuf_on = true;
         }
     }
-    c->first_overwrites = c->zero_all && c->changes.empty() && !c->inter.empty() && c->inter[0].kind == K_RJL && (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
+    c->first_overwrites = c->zero_all && c->changes.empty() && !c->inter.empty() && (c->inter[0].kind == K_RJL || (c->inter[0].kind == K_LJ1G && c->lj1g_pipe)) &&
+                          (int)group_of(c, c->inter[0].nl[0].g1).size() == N;
     nl_setup_grid(c);
     CK(cudaStreamSynchronize(c->st));
     c->finalized = true;

@@ -118,7 +118,7 @@ struct pfmds_ctx {
     unsigned int* ticket = nullptr;      // block counter of k_sum_kick_ke (its last block closes the thermostat step)
     bool fbuf_on = false;                // buffers exist (finalize): small system, at most 8 interactions, PFMDS_SMALL_FORK != 0
     bool fbuf_active = false;            // this step's forces went into the buffers: the sum kernel must run
-    bool first_overwrites = false;  // interaction 0 is rjl and owns every atom: its force kernel stores, no zero pass
+    bool first_overwrites = false;  // interaction 0 is rjl (or lj1g with the pipelined kernel) and owns every atom: its force kernel stores, no zero pass
     bool energy_valid = false;  // c->energy[] holds the potential energies of the current positions (computed inside the last step)
     bool finalized = false;
     bool counted = false;       // this context is in the process-wide count of live contexts of its device (capi.cu)

@@ -749,7 +749,7 @@ __device__ __forceinline__ void lj1g_pair(const double4& pi, const double4& pj, 
 }
 template <bool E>
 __global__ void __launch_bounds__(FT) k_lj1g_pipe(int N, const double4* __restrict__ pos, double4* __restrict__ frc, ListView lv, LJ1Gp P, BoxD box,
-                                                  WrapC W, double* part) {
+                                                  WrapC W, double* part, int overwrite) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0, fx = 0, fy = 0, fz = 0;
     int n = i < N ? lv.nnum[i] : 0;
@@ -772,8 +772,10 @@ __global__ void __launch_bounds__(FT) k_lj1g_pipe(int N, const double4* __restri
             j1 = j3;
         }
         if (p < n) lj1g_pair<E>(pi, a, P, R12, R22, iw, box, W.min_half_hi, fx, fy, fz, e);
-        add_force(frc, i, fx, fy, fz);
-    }
+        // first interaction of the step and every atom is an owner: store instead of zero + accumulate (zero_forces fused away, as in k_rjl_force)
+        if (overwrite) frc[i] = make_double4(fx, fy, fz, 0.);
+        else add_force(frc, i, fx, fy, fz);
+    } else if (overwrite && i < N) frc[i] = make_double4(0., 0., 0., 0.);
     if (E) store_partial(e, part);
 }
 
@@ -1114,8 +1116,9 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
     case K_LJ1G:
         if (c->lj1g_pipe && !small) {  // pipelined variant (thread per atom)
             KTimer kt(c, KS_LJ1G);
-            if (with_energy) { LAUNCH((k_lj1g_pipe<true>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), epart); e_parts = nb; e_scale = 0.5; }
-            else LAUNCH((k_lj1g_pipe<false>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), nullptr);
+            const int ow = (k == 0 && c->first_overwrites) ? 1 : 0;
+            if (with_energy) { LAUNCH((k_lj1g_pipe<true>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), epart, ow); e_parts = nb; e_scale = 0.5; }
+            else LAUNCH((k_lj1g_pipe<false>), nb, FT, fs, N, c->pos, fo, it.nl[0].view(st), it.lj1g, c->box, wrap_consts(c->box), (double*)nullptr, ow);
             c->launches += 1;
             break;
         }

@@ -46,7 +46,7 @@ int fh_lj1g(int N, const double* pos4, double* frc4, size_t stride, const int* n
     LJ1Gp P{p[2], p[3], 4. * p[0] * s6, 4. * p[0] * s12, 6. * 4. * p[0] * s6, 12. * 4. * p[0] * s12};
     const int nb = (N + FT - 1) / FT;
     std::vector<double> part((size_t)nb + 1, 0.);
-    if (pipelined) emu_launch(k_lj1g_pipe<true>, nb, 1, FT, N, pos, frc, ListView{nl0, nn0, stride}, P, box, wrap_consts(box), part.data());
+    if (pipelined) emu_launch(k_lj1g_pipe<true>, nb, 1, FT, N, pos, frc, ListView{nl0, nn0, stride}, P, box, wrap_consts(box), part.data(), 0);
     else emu_launch(k_lj1g<true, true, 1>, nb, 1, FT, N, pos, frc, ListView{nl0, nn0, stride}, P, box, part.data());
     *energy = sum_parts(part, nb, 0.5);
     return 0;

@@ -106,3 +106,22 @@ def test_multi_step_graphs_give_the_single_step_results():
             assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(fa, fb)
             assert all(np.array_equal(x, y) for ta, tb in zip(na, nb) for x, y in zip(ta, tb))
             assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
+
+
+def test_lj1g_force_kernel_stores_instead_of_zero_plus_accumulate():
+    """lj1g as the only / first interaction, owning every atom, on the thread-per-atom path: the pipelined kernel stores its result
+    (zero_forces fused away, like k_rjl_force).  Against the oracle over rebuilds, and against the plain kernel + memset."""
+    from util import oracle
+    case = inputs.lj_fluid(n_side=10, period=5)
+    g, p, o = gpu(case, "large"), gpu(case, "large_build"), oracle(case)
+    for e in (g, p, o):
+        e.advance("nve", 0.5, 0, 1)
+    fo = o.download()[2]
+    assert np.abs(fo).max() > 1e-3 and rel_err(g.download()[2], fo) < 1e-9 and rel_err(p.download()[2], fo) < 1e-9
+    for e in (g, p, o):
+        e.advance("nve", 0.5, 1, 17)
+    (pg, vg, fg), (po, vo, fo) = g.download(), o.download()
+    assert np.abs(pg - po).max() < 1e-9 and rel_err(fg, fo) < 1e-8 and rel_err(p.download()[2], fo) < 1e-8
+    assert np.allclose(g.energies()[0], o.energies()[0], rtol=1e-9, atol=0)
+    for e in (g, p, o):
+        e.close()
