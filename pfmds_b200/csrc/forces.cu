@@ -816,6 +816,88 @@ __global__ void __launch_bounds__(FT) k_tb_bond(int N, const double4* __restrict
 }
 // pass B: forces (:99-146) and/or energy (:53-66) of one bond.  Bonds and partners beyond R2 contribute exactly
 // zero in the reference (f_cut = df_cut = 0, B = 0) and are skipped.
+// forces (:99-146) and / or energy (:53-66) of bond p of atom i (p < n = its row length): everything atom i feels through that bond --
+// the pair term with both bond orders, the derivative of its own bond order and the cross terms through j's other bonds.
+// Bonds and partners beyond R2 contribute exactly zero in the reference (f_cut = df_cut = 0, B = 0) and are skipped.
+template <bool F, bool E>
+__device__ __forceinline__ void tb_bond_terms(int i, int p, int n, const double4* __restrict__ pos, const ListView& lv, const TBp& T, const BoxD& box,
+                                              const double* __restrict__ B, const double* __restrict__ Bx, double& e, double& fx, double& fy, double& fz) {
+    const double4 pi = pos[i];
+    const double s2s = sqrt(2. * T.s), s2is = sqrt(2. / T.s), dpre = T.d / (T.s - 1.);
+    do {
+        int j = lv.nlist[(size_t)p * lv.stride + i];
+        const double4 pj = pos[j];
+        double rp2;
+        Vec dp = bond_vec(pi, pj, box, rp2);
+        double rp = sqrt(rp2);
+        if (!(rp < T.R2)) break;
+        double Bip = B[(size_t)p * lv.stride + i];
+        // reverse slot: i in j's row
+        int nj = lv.nnum[j], l = 0;
+        for (; l < nj; ++l)
+            if (lv.nlist[(size_t)l * lv.stride + j] == i) break;
+        if (l >= nj) break;  // cannot happen: same group, same r_cut, symmetric dr2
+        double Bjl = B[(size_t)l * lv.stride + j];
+        double f_c, dfr_p;
+        fcut_dfcut(rp, T.R1, T.R2, f_c, dfr_p);
+        double a = -s2s * T.b * (rp - T.r0);
+        double ea = mx::exp_fast(a), eas = mx::exp_fast(a / T.s);
+        if (E) {
+            if (j > i) e += f_c * dpre * (ea - (Bip + Bjl) / 2 * T.s * eas);
+        }
+        if (F) {
+            Vec dB = {0., 0., 0.};
+            for (int q = 0; q < n; ++q) {  // :112-120 own row
+                if (q == p) continue;
+                double rq2;
+                Vec dq = bond_vec(pi, pos[lv.nlist[(size_t)q * lv.stride + i]], box, rq2);
+                double rq = sqrt(rq2);
+                if (!(rq < T.R2)) continue;
+                double fq, dfq;
+                fcut_dfcut(rq, T.R1, T.R2, fq, dfq);
+                double rr = 1. / rp / rq, cosi = dot(dp, dq) * rr, c1 = 1. + cosi, den = T.d02 + c1 * c1;
+                double g1 = fq * 2. * T.a0 * T.c02 * c1 / (den * den);
+                double g2 = dfq * T.a0 * tb_G(c1, T);
+                dB.x += g1 * ((dp.x + dq.x) * rr - cosi * (dp.x / rp2 + dq.x / rq2)) + g2 * dq.x;
+                dB.y += g1 * ((dp.y + dq.y) * rr - cosi * (dp.y / rp2 + dq.y / rq2)) + g2 * dq.y;
+                dB.z += g1 * ((dp.z + dq.z) * rr - cosi * (dp.z / rp2 + dq.z / rq2)) + g2 * dq.z;
+            }
+            double bp = Bx[(size_t)p * lv.stride + i];
+            dB.x *= bp; dB.y *= bp; dB.z *= bp;
+            const Vec dl = {-dp.x, -dp.y, -dp.z};  // j -> i
+            double bl = Bx[(size_t)l * lv.stride + j];
+            double cx = 0, cy = 0, cz = 0;  // cross terms :142-152
+            for (int q = 0; q < nj; ++q) {  // :126-133 and :142-152 share the geometry of j's row
+                if (q == l) continue;
+                double rq2;
+                Vec dq = bond_vec(pj, pos[lv.nlist[(size_t)q * lv.stride + j]], box, rq2);
+                double rq = sqrt(rq2);
+                if (!(rq < T.R2)) continue;
+                double fq = fcut_only(rq, T.R1, T.R2);
+                double rr = 1. / rp / rq, cosi = dot(dl, dq) * rr, c1 = 1. + cosi, den = T.d02 + c1 * c1;
+                double gg = 2. * T.a0 * T.c02 * c1 / (den * den);
+                Vec w = {-dq.x * rr + cosi * dl.x / rp2, -dq.y * rr + cosi * dl.y / rp2, -dq.z * rr + cosi * dl.z / rp2};
+                double g = bl * fq * gg;
+                dB.x += g * w.x; dB.y += g * w.y; dB.z += g * w.z;
+                double pre = T.delt / 2 * Bx[(size_t)q * lv.stride + j];
+                double g1 = f_c * gg, g2 = dfr_p * T.a0 * tb_G(c1, T);
+                double tail = fq * dpre * T.s * mx::exp_fast(-s2s * T.b * (rq - T.r0) / T.s);
+                cx += pre * (g1 * w.x + dp.x * g2) * tail;
+                cy += pre * (g1 * w.y + dp.y * g2) * tail;
+                cz += pre * (g1 * w.z + dp.z * g2) * tail;
+            }
+            double h = -T.delt / 2.;
+            dB.x *= h; dB.y *= h; dB.z *= h;
+            double dff = dfr_p / f_c;
+            double k1 = (dff - s2s * T.b / rp) * ea;       // multiplies dp
+            double k2 = (Bip + Bjl) / 2 * (dff - s2is * T.b / rp);
+            double A = f_c * dpre, se = T.s * eas;
+            fx = A * (dp.x * k1 - (dB.x + k2 * dp.x) * se) + cx;
+            fy = A * (dp.y * k1 - (dB.y + k2 * dp.y) * se) + cy;
+            fz = A * (dp.z * k1 - (dB.z + k2 * dp.z) * se) + cz;
+        }
+    } while (false);
+}
 template <bool F, bool E>
 __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restrict__ pos, double4* __restrict__ fpart, ListView lv, TBp T, BoxD box,
                                                  const double* __restrict__ B, const double* __restrict__ Bx, double* part) {
@@ -824,81 +906,7 @@ __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restric
     double e = 0, fx = 0, fy = 0, fz = 0;
     int n = i < N ? lv.nnum[i] : 0;
     if (p < n) {
-        const double4 pi = pos[i];
-        const double s2s = sqrt(2. * T.s), s2is = sqrt(2. / T.s), dpre = T.d / (T.s - 1.);
-        do {
-            int j = lv.nlist[(size_t)p * lv.stride + i];
-            const double4 pj = pos[j];
-            double rp2;
-            Vec dp = bond_vec(pi, pj, box, rp2);
-            double rp = sqrt(rp2);
-            if (!(rp < T.R2)) break;
-            double Bip = B[(size_t)p * lv.stride + i];
-            // reverse slot: i in j's row
-            int nj = lv.nnum[j], l = 0;
-            for (; l < nj; ++l)
-                if (lv.nlist[(size_t)l * lv.stride + j] == i) break;
-            if (l >= nj) break;  // cannot happen: same group, same r_cut, symmetric dr2
-            double Bjl = B[(size_t)l * lv.stride + j];
-            double f_c, dfr_p;
-            fcut_dfcut(rp, T.R1, T.R2, f_c, dfr_p);
-            double a = -s2s * T.b * (rp - T.r0);
-            double ea = mx::exp_fast(a), eas = mx::exp_fast(a / T.s);
-            if (E) {
-                if (j > i) e += f_c * dpre * (ea - (Bip + Bjl) / 2 * T.s * eas);
-            }
-            if (F) {
-                Vec dB = {0., 0., 0.};
-                for (int q = 0; q < n; ++q) {  // :112-120 own row
-                    if (q == p) continue;
-                    double rq2;
-                    Vec dq = bond_vec(pi, pos[lv.nlist[(size_t)q * lv.stride + i]], box, rq2);
-                    double rq = sqrt(rq2);
-                    if (!(rq < T.R2)) continue;
-                    double fq, dfq;
-                    fcut_dfcut(rq, T.R1, T.R2, fq, dfq);
-                    double rr = 1. / rp / rq, cosi = dot(dp, dq) * rr, c1 = 1. + cosi, den = T.d02 + c1 * c1;
-                    double g1 = fq * 2. * T.a0 * T.c02 * c1 / (den * den);
-                    double g2 = dfq * T.a0 * tb_G(c1, T);
-                    dB.x += g1 * ((dp.x + dq.x) * rr - cosi * (dp.x / rp2 + dq.x / rq2)) + g2 * dq.x;
-                    dB.y += g1 * ((dp.y + dq.y) * rr - cosi * (dp.y / rp2 + dq.y / rq2)) + g2 * dq.y;
-                    dB.z += g1 * ((dp.z + dq.z) * rr - cosi * (dp.z / rp2 + dq.z / rq2)) + g2 * dq.z;
-                }
-                double bp = Bx[(size_t)p * lv.stride + i];
-                dB.x *= bp; dB.y *= bp; dB.z *= bp;
-                const Vec dl = {-dp.x, -dp.y, -dp.z};  // j -> i
-                double bl = Bx[(size_t)l * lv.stride + j];
-                double cx = 0, cy = 0, cz = 0;  // cross terms :142-152
-                for (int q = 0; q < nj; ++q) {  // :126-133 and :142-152 share the geometry of j's row
-                    if (q == l) continue;
-                    double rq2;
-                    Vec dq = bond_vec(pj, pos[lv.nlist[(size_t)q * lv.stride + j]], box, rq2);
-                    double rq = sqrt(rq2);
-                    if (!(rq < T.R2)) continue;
-                    double fq = fcut_only(rq, T.R1, T.R2);
-                    double rr = 1. / rp / rq, cosi = dot(dl, dq) * rr, c1 = 1. + cosi, den = T.d02 + c1 * c1;
-                    double gg = 2. * T.a0 * T.c02 * c1 / (den * den);
-                    Vec w = {-dq.x * rr + cosi * dl.x / rp2, -dq.y * rr + cosi * dl.y / rp2, -dq.z * rr + cosi * dl.z / rp2};
-                    double g = bl * fq * gg;
-                    dB.x += g * w.x; dB.y += g * w.y; dB.z += g * w.z;
-                    double pre = T.delt / 2 * Bx[(size_t)q * lv.stride + j];
-                    double g1 = f_c * gg, g2 = dfr_p * T.a0 * tb_G(c1, T);
-                    double tail = fq * dpre * T.s * mx::exp_fast(-s2s * T.b * (rq - T.r0) / T.s);
-                    cx += pre * (g1 * w.x + dp.x * g2) * tail;
-                    cy += pre * (g1 * w.y + dp.y * g2) * tail;
-                    cz += pre * (g1 * w.z + dp.z * g2) * tail;
-                }
-                double h = -T.delt / 2.;
-                dB.x *= h; dB.y *= h; dB.z *= h;
-                double dff = dfr_p / f_c;
-                double k1 = (dff - s2s * T.b / rp) * ea;       // multiplies dp
-                double k2 = (Bip + Bjl) / 2 * (dff - s2is * T.b / rp);
-                double A = f_c * dpre, se = T.s * eas;
-                fx = A * (dp.x * k1 - (dB.x + k2 * dp.x) * se) + cx;
-                fy = A * (dp.y * k1 - (dB.y + k2 * dp.y) * se) + cy;
-                fz = A * (dp.z * k1 - (dB.z + k2 * dp.z) * se) + cz;
-            }
-        } while (false);
+        tb_bond_terms<F, E>(i, p, n, pos, lv, T, box, B, Bx, e, fx, fy, fz);
         if (F) fpart[(size_t)p * lv.stride + i] = make_double4(fx, fy, fz, 0.);
     }
     if (E) {
@@ -906,6 +914,9 @@ __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restric
         if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
     }
 }
+// (Tried and dropped, measured on a B200: pass B and the per-atom sum in one kernel, four lanes per atom taking its bonds and lane 0
+//  adding them in slot order -- bit-identical, one launch less, but the lanes of a warp then skip different q in the loops below:
+//  0.057 against 0.035 ms per step for the tb force pass of graphene on Cu, 1.02e8 against 1.37e8 atom-steps/s.)
 __global__ void __launch_bounds__(FT) k_tb_reduce(int N, const double4* __restrict__ fpart, double4* __restrict__ frc, ListView lv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -1196,8 +1207,8 @@ void forces_interaction(pfmds_ctx* c, int k, bool with_energy) {  // calculate_f
             KTimer kt(c, KS_TB_FORCE);
             LAUNCH((k_tb_force<true, false>), grid, FT, fs, N, c->pos, it.fpart, it.nl[0].view(st), it.tb, c->box, it.aux, it.aux2, nullptr);
             LAUNCH((k_tb_reduce), nb, FT, fs, N, it.fpart, fo, it.nl[0].view(st));
+            c->launches += 3;
         }
-        c->launches += 3;
     }
         break;
     case K_LJC:
