@@ -916,7 +916,10 @@ __global__ void __launch_bounds__(FT) k_tb_force(int N, const double4* __restric
 }
 // (Tried and dropped, measured on a B200: pass B and the per-atom sum in one kernel, four lanes per atom taking its bonds and lane 0
 //  adding them in slot order -- bit-identical, one launch less, but the lanes of a warp then skip different q in the loops below:
-//  0.057 against 0.035 ms per step for the tb force pass of graphene on Cu, 1.02e8 against 1.37e8 atom-steps/s.)
+//  0.057 against 0.035 ms per step for the tb force pass of graphene on Cu, 1.02e8 against 1.37e8 atom-steps/s.
+//  Also tried and dropped: eight lanes per (atom, bond) sharing the two partner loops of a bond (9 row entries each in graphene: 3
+//  bonds + 6 second neighbours the switch zeroes) with a shuffle-tree sum -- parity with the oracle 1e-9, but eight times the
+//  blocks, most of them empty: tb force pass 0.034 -> 0.041 ms, graphene on Cu 1.37e8 -> 1.13e8, 64 replicas on one GPU 2.9e8 -> 1.8e8.)
 __global__ void __launch_bounds__(FT) k_tb_reduce(int N, const double4* __restrict__ fpart, double4* __restrict__ frc, ListView lv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;

@@ -125,4 +125,3 @@ def test_lj1g_force_kernel_stores_instead_of_zero_plus_accumulate():
     assert np.allclose(g.energies()[0], o.energies()[0], rtol=1e-9, atol=0)
     for e in (g, p, o):
         e.close()
-
